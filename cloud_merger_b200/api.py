@@ -1,0 +1,334 @@
+"""Thin Python host layer over the C ABI (include/cloud_merger_gpu.h): used by the tests, bench.py and the multi-GPU
+drivers. All compute happens in libcloud_merger_gpu.so on the GPU; nothing here computes on the CPU.
+
+Names follow the reference's domain: clouds, sensors, extrinsics, crop passes (PassThrough), voxels, frames.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+from typing import Iterable, List, Optional, Sequence, Tuple
+
+import numpy as np
+
+from . import _lib
+from ._lib import (CmConfig, CmDeviceOut, CmFrameInfo, CmFrameOut, CmLayout, CmPass, CmSegment, CmStats)
+
+# ---- layouts the reference's sensors produce ------------------------------------------------------
+LAYOUT_PACKED16 = dict(point_step=16, off_x=0, off_y=4, off_z=8, off_intensity=12)   # float4 x y z intensity
+LAYOUT_PCL32 = dict(point_step=32, off_x=0, off_y=4, off_z=8, off_intensity=16)      # pcl::PointXYZI / Velodyne (Melodic)
+LAYOUT_VELODYNE22 = dict(point_step=22, off_x=0, off_y=4, off_z=8, off_intensity=12)  # x y z intensity ring(u16) time(f32)
+LAYOUT_LIVOX18 = dict(point_step=18, off_x=0, off_y=4, off_z=8, off_intensity=12)     # x y z reflectivity tag line
+
+# getROI defaults, pcl_preprocessing/src/Parameter.h:31-35 (axis, lo, hi, negative)
+ROI_PASSES = [(2, -0.5, 3.0, 0), (1, -5.0, 5.0, 0), (0, -15.0, 60.0, 0)]
+
+
+class CloudMergerError(RuntimeError):
+    def __init__(self, code: int, what: str):
+        super().__init__("cloud_merger_gpu error %d: %s" % (code, what))
+        self.code = code
+
+
+def make_layout(point_step=16, off_x=0, off_y=4, off_z=8, off_intensity=12, is_dense=1) -> CmLayout:
+    return CmLayout(point_step, off_x, off_y, off_z, off_intensity, int(is_dense))
+
+
+@dataclass
+class FrameInfo:
+    survivor_begin: int
+    survivor_end: int
+    voxel_begin: int
+    voxel_end: int
+    min_b: Tuple[int, int, int]
+    max_b: Tuple[int, int, int]
+    div_b: Tuple[int, int, int]
+    pcl_overflow: bool
+
+
+@dataclass
+class FrameResult:
+    voxel_xyzi: np.ndarray      # (V, 4) float32 centroids (x, y, z, intensity)
+    voxel_count: np.ndarray     # (V,) uint32
+    voxel_idx: np.ndarray       # (V,) uint64 PCL voxel index
+    survivor_xyzi: np.ndarray   # (M, 4) float32 merged cropped cloud
+    survivor_src: np.ndarray    # (M,) uint32 index in the un-cropped concatenation
+    info: FrameInfo
+    used_mask: int
+    stamp: int
+
+
+def _info(fi: CmFrameInfo) -> FrameInfo:
+    return FrameInfo(fi.survivor_begin, fi.survivor_end, fi.voxel_begin, fi.voxel_end, tuple(fi.min_b), tuple(fi.max_b),
+                     tuple(fi.div_b), bool(fi.pcl_overflow))
+
+
+class DeviceBuffer:
+    """A device allocation owned through the C ABI (cm_dev_alloc)."""
+
+    def __init__(self, merger: "CloudMerger", nbytes: int):
+        self._m = merger
+        self.nbytes = int(nbytes)
+        p = C.c_void_p()
+        merger._check(merger._lib.cm_dev_alloc(merger._h, C.byref(p), C.c_size_t(max(self.nbytes, 16))))
+        self.ptr = p.value
+
+    def upload(self, arr: np.ndarray, offset: int = 0) -> "DeviceBuffer":
+        a = np.ascontiguousarray(arr)
+        assert offset + a.nbytes <= self.nbytes
+        self._m._check(self._m._lib.cm_memcpy_h2d(self._m._h, C.c_void_p(self.ptr + offset), a.ctypes.data_as(C.c_void_p),
+                                                  C.c_size_t(a.nbytes), None))
+        return self
+
+    def free(self):
+        if self.ptr:
+            self._m._lib.cm_dev_free(self._m._h, C.c_void_p(self.ptr))
+            self.ptr = None
+
+
+class CloudMerger:
+    """One handle = one GPU. Mirrors the reference's per-frame flow: submit_cloud() from each sensor callback
+    (callbackFrontRight ..., pc_preprocessing_main.cpp:318-508), merge_frame() from the main loop (:574-578)."""
+
+    def __init__(self, device: int = 0, max_sensors: int = 6, max_points_per_sensor: int = 262144,
+                 max_point_step: int = 32, frames_in_flight: int = 2, max_batch_points: int = 0,
+                 max_batch_frames: int = 1, max_batch_segments: int = 0, out_point_step: int = 16):
+        self._lib = _lib.load()
+        self._h = C.c_void_p()
+        cfg = CmConfig(device, max_sensors, max_points_per_sensor, max_point_step, frames_in_flight, max_batch_points,
+                       max_batch_frames, max_batch_segments, out_point_step, 0)
+        rc = self._lib.cm_create(C.byref(cfg), C.byref(self._h))
+        if rc != _lib.CM_OK:
+            self._h = None
+            raise CloudMergerError(rc, self._lib.cm_strerror(rc).decode() + " (cm_create; a B200 / sm_100 GPU is required)")
+        self.out_point_step = 32 if out_point_step == 32 else 16
+        self.max_sensors = max_sensors
+        self._buffers: List[DeviceBuffer] = []
+
+    # -- plumbing ----------------------------------------------------------------------------------------------------
+    def _check(self, rc: int):
+        if rc != _lib.CM_OK:
+            raise CloudMergerError(rc, "%s: %s" % (self._lib.cm_strerror(rc).decode(),
+                                                   self._lib.cm_last_error(self._h).decode()))
+
+    def close(self):
+        if self._h:
+            for b in self._buffers:
+                b.free()
+            self._buffers = []
+            self._lib.cm_destroy(self._h)
+            self._h = None
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # -- configuration -----------------------------------------------------------------------------------------------
+    def set_extrinsic(self, sensor: int, m: np.ndarray, col_major: bool = False):
+        """m: 4x4 (or 3x4 / 12 floats row-major) sensor -> base transform (tf::Transform of the reference callbacks)."""
+        a = np.asarray(m, np.float32).reshape(-1)
+        if a.size == 12:
+            a = np.concatenate([a, np.array([0, 0, 0, 1], np.float32)])
+        a = np.ascontiguousarray(a[:16])
+        self._check(self._lib.cm_set_extrinsic(self._h, sensor, a.ctypes.data_as(C.POINTER(C.c_float)), int(col_major)))
+
+    def set_extrinsic_tf(self, sensor: int, quat_xyzw: Sequence[float], origin_xyz: Sequence[float]):
+        q = (C.c_double * 4)(*[float(v) for v in quat_xyzw])
+        t = (C.c_double * 3)(*[float(v) for v in origin_xyz])
+        self._check(self._lib.cm_set_extrinsic_tf(self._h, sensor, q, t))
+
+    def get_extrinsic(self, sensor: int) -> np.ndarray:
+        m = np.empty(12, np.float32)
+        self._check(self._lib.cm_get_extrinsic(self._h, sensor, m.ctypes.data_as(C.POINTER(C.c_float))))
+        return m
+
+    def set_crop(self, passes: Iterable[Tuple[int, float, float, int]]):
+        """passes: (axis, lo, hi, negative) per pcl::PassThrough stage; [] disables cropping."""
+        passes = list(passes)
+        arr = (CmPass * max(len(passes), 1))()
+        for i, (axis, lo, hi, neg) in enumerate(passes):
+            arr[i] = CmPass(int(axis), float(np.float32(lo)), float(np.float32(hi)), int(neg))
+        self._check(self._lib.cm_set_crop(self._h, len(passes), arr))
+
+    def set_voxel(self, leaf, min_points: int = 2, downsample_all: bool = True):
+        leaf = np.broadcast_to(np.asarray(leaf, np.float32), (3,)).copy()
+        self._check(self._lib.cm_set_voxel(self._h, leaf.ctypes.data_as(C.POINTER(C.c_float)), int(min_points),
+                                           int(downsample_all)))
+
+    def set_overflow_mode(self, pcl_like: bool):
+        self._check(self._lib.cm_set_overflow_mode(self._h, int(pcl_like)))
+
+    def set_profiling(self, on: bool):
+        self._check(self._lib.cm_set_profiling(self._h, int(on)))
+
+    # -- host path ---------------------------------------------------------------------------------------------------
+    def submit_cloud(self, sensor: int, data, n_points: int, layout: CmLayout, stamp: int = 0, pinned: bool = False):
+        """data: numpy buffer (any dtype) holding n_points records of layout.point_step bytes, or a raw address."""
+        if isinstance(data, int):
+            ptr = C.c_void_p(data)
+        else:
+            a = np.ascontiguousarray(data)
+            assert a.nbytes >= n_points * layout.point_step
+            ptr = a.ctypes.data_as(C.c_void_p)
+        fn = self._lib.cm_submit_cloud_pinned if pinned else self._lib.cm_submit_cloud
+        self._check(fn(self._h, sensor, ptr, n_points, C.byref(layout), C.c_uint64(stamp)))
+
+    def merge_frame_async(self, sensor_mask: int = (1 << 64) - 1) -> int:
+        t = C.c_int64()
+        self._check(self._lib.cm_merge_frame_async(self._h, C.c_uint64(sensor_mask), C.byref(t)))
+        return t.value
+
+    def _make_out(self, voxel_cap: int, surv_cap: int, want_survivors: bool):
+        step_f = self.out_point_step // 4
+        bufs = dict(vx=np.empty((max(voxel_cap, 1), step_f), np.float32), vc=np.empty(max(voxel_cap, 1), np.uint32),
+                    vi=np.empty(max(voxel_cap, 1), np.uint64))
+        out = CmFrameOut()
+        out.voxel_xyzi = bufs["vx"].ctypes.data
+        out.voxel_capacity = voxel_cap
+        out.voxel_count = bufs["vc"].ctypes.data
+        out.voxel_idx = bufs["vi"].ctypes.data
+        if want_survivors:
+            bufs["sx"] = np.empty((max(surv_cap, 1), 4), np.float32)
+            bufs["ss"] = np.empty(max(surv_cap, 1), np.uint32)
+            out.survivor_xyzi = bufs["sx"].ctypes.data
+            out.survivor_src = bufs["ss"].ctypes.data
+            out.survivor_capacity = surv_cap
+        return out, bufs
+
+    def _result(self, out: CmFrameOut, bufs, used: int, stamp: int) -> FrameResult:
+        v, m = out.n_voxels, out.n_survivors
+        vx = bufs["vx"][:v]
+        if self.out_point_step == 32:
+            vx = np.concatenate([vx[:, 0:3], vx[:, 4:5]], axis=1)
+        sx = bufs["sx"][:m].copy() if "sx" in bufs else np.zeros((0, 4), np.float32)
+        ss = bufs["ss"][:m].copy() if "ss" in bufs else np.zeros(0, np.uint32)
+        res = FrameResult(vx.copy(), bufs["vc"][:v].copy(), bufs["vi"][:v].copy(), sx, ss, _info(out.info), used, stamp)
+        res.raw_voxel_records = bufs["vx"][:v].copy()
+        return res
+
+    def wait_frame(self, ticket: int, capacity: int, want_survivors: bool = True) -> FrameResult:
+        out, bufs = self._make_out(capacity, capacity, want_survivors)
+        used, stamp = C.c_uint64(), C.c_uint64()
+        self._check(self._lib.cm_wait_frame(self._h, ticket, C.byref(out), C.byref(used), C.byref(stamp)))
+        return self._result(out, bufs, used.value, stamp.value)
+
+    def merge_frame(self, capacity: int, sensor_mask: int = (1 << 64) - 1, want_survivors: bool = True) -> FrameResult:
+        """fusePointclouds + voxelgrid of the reference main loop (pc_preprocessing_main.cpp:574-578)."""
+        out, bufs = self._make_out(capacity, capacity, want_survivors)
+        used, stamp = C.c_uint64(), C.c_uint64()
+        self._check(self._lib.cm_merge_frame(self._h, C.c_uint64(sensor_mask), C.byref(out), C.byref(used),
+                                             C.byref(stamp)))
+        return self._result(out, bufs, used.value, stamp.value)
+
+    # -- device path -------------------------------------------------------------------------------------------------
+    def device_buffer(self, nbytes: int) -> DeviceBuffer:
+        b = DeviceBuffer(self, nbytes)
+        self._buffers.append(b)
+        return b
+
+    def upload(self, arr: np.ndarray) -> DeviceBuffer:
+        a = np.ascontiguousarray(arr)
+        b = self.device_buffer(a.nbytes)
+        self._check(self._lib.cm_memcpy_h2d(self._h, C.c_void_p(b.ptr), a.ctypes.data_as(C.c_void_p),
+                                            C.c_size_t(a.nbytes), None))
+        return b
+
+    def download(self, ptr: int, dtype, count: int) -> np.ndarray:
+        out = np.empty(count, dtype)
+        if count:
+            self._check(self._lib.cm_memcpy_d2h(self._h, out.ctypes.data_as(C.c_void_p), C.c_void_p(ptr),
+                                                C.c_size_t(out.nbytes), None))
+        return out
+
+    @staticmethod
+    def make_segments(items) -> "C.Array":
+        """items: iterable of (device_ptr, n_points, CmLayout, sensor, frame)."""
+        items = list(items)
+        arr = (CmSegment * max(len(items), 1))()
+        for i, (ptr, n, layout, sensor, frame) in enumerate(items):
+            arr[i].data = ptr
+            arr[i].n_points = int(n)
+            arr[i].layout = layout
+            arr[i].sensor = int(sensor)
+            arr[i].frame = int(frame)
+        arr._n = len(items)
+        return arr
+
+    def run_batch(self, segments, n_segments: Optional[int] = None, stream: int = 0):
+        n = n_segments if n_segments is not None else getattr(segments, "_n", len(segments))
+        self._check(self._lib.cm_run_batch(self._h, segments, n, C.c_void_p(stream)))
+
+    def dev_transform_crop(self, segments, n_segments: Optional[int] = None, stream: int = 0):
+        n = n_segments if n_segments is not None else getattr(segments, "_n", len(segments))
+        self._check(self._lib.cm_dev_transform_crop(self._h, segments, n, C.c_void_p(stream)))
+
+    def dev_voxelgrid(self, xyzi_ptr: int, n_points: int, is_dense: bool = True, stream: int = 0):
+        self._check(self._lib.cm_dev_voxelgrid(self._h, C.c_void_p(xyzi_ptr), n_points, int(is_dense), C.c_void_p(stream)))
+
+    def sync(self):
+        self._check(self._lib.cm_sync(self._h))
+
+    def stats(self) -> CmStats:
+        s = CmStats()
+        self._check(self._lib.cm_get_stats(self._h, C.byref(s)))
+        return s
+
+    def frame_info(self) -> List[FrameInfo]:
+        n = C.c_int()
+        self._check(self._lib.cm_get_frame_info(self._h, None, 0, C.byref(n)))
+        arr = (CmFrameInfo * max(n.value, 1))()
+        self._check(self._lib.cm_get_frame_info(self._h, arr, n.value, C.byref(n)))
+        return [_info(arr[i]) for i in range(n.value)]
+
+    def device_out(self) -> CmDeviceOut:
+        o = CmDeviceOut()
+        self._check(self._lib.cm_get_device_out(self._h, C.byref(o)))
+        return o
+
+    def launch_count(self) -> int:
+        return int(self._lib.cm_launch_count(self._h))
+
+    def stage_ms(self, stage: str) -> float:
+        v = C.c_float()
+        self._check(self._lib.cm_stage_ms(self._h, stage.encode(), C.byref(v)))
+        return v.value
+
+    def fetch_batch_outputs(self, want_sorted: bool = True) -> dict:
+        """Downloads everything the last device run produced (test helper; sizes come from the run's stats)."""
+        st = self.stats()
+        o = self.device_out()
+        m, v = int(st.survivors), int(st.voxels_out)
+        res = dict(stats=st, frames=self.frame_info(), key_bytes=o.key_bytes, key_idx_bits=o.key_idx_bits)
+        res["survivor_xyzi"] = self.download(o.survivor_xyzi, np.float32, m * 4).reshape(m, 4) if o.survivor_xyzi else None
+        res["survivor_src"] = self.download(o.survivor_src, np.uint32, m) if o.survivor_src else None
+        if o.voxel_xyzi:
+            step_f = self.out_point_step // 4
+            vx = self.download(o.voxel_xyzi, np.float32, v * step_f).reshape(v, step_f)
+            res["voxel_records"] = vx
+            res["voxel_xyzi"] = vx if step_f == 4 else np.concatenate([vx[:, 0:3], vx[:, 4:5]], axis=1)
+            res["voxel_count"] = self.download(o.voxel_count, np.uint32, v)
+            res["voxel_idx"] = self.download(o.voxel_idx, np.uint64, v)
+            if want_sorted:
+                kd = np.uint32 if o.key_bytes == 4 else np.uint64
+                res["sorted_key"] = self.download(o.sorted_key, kd, m).astype(np.uint64)
+                res["sorted_point"] = self.download(o.sorted_point, np.uint32, m)
+        return res
+
+
+def host_alloc(nbytes: int) -> Tuple[np.ndarray, int]:
+    """Page-locked host memory as a uint8 numpy array (cm_host_alloc). Returns (array, address); never freed by GC."""
+    lib = _lib.load()
+    p = C.c_void_p()
+    rc = lib.cm_host_alloc(C.byref(p), C.c_size_t(max(nbytes, 1)))
+    if rc != _lib.CM_OK:
+        raise CloudMergerError(rc, "cm_host_alloc(%d)" % nbytes)
+    buf = (C.c_uint8 * max(nbytes, 1)).from_address(p.value)
+    return np.frombuffer(buf, dtype=np.uint8, count=nbytes), p.value

@@ -1,0 +1,968 @@
+// cm_api.cu -- host side of the C ABI declared in include/cloud_merger_gpu.h.
+//
+// Owns every device allocation (made once, at creation / first use -- no per-frame cudaMalloc), the per-sensor copy
+// streams, the frame slots of the host path and the launch sequence of a run:
+//     memset(control block) -> K1 transform_crop -> grid_setup -> key_hist -> P x onesweep pass -> centroid
+// There is no CPU implementation behind any entry point: without a CUDA device cm_create fails.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <limits>
+#include <mutex>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "../../include/cloud_merger_gpu.h"
+#include "cm_kernels.h"
+
+using namespace cm;
+
+namespace {
+
+constexpr size_t kAlign = 256;
+inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+struct MetaLayout {
+  size_t off_ctrl, off_acc, off_hist, zero_bytes, off_info, off_fstart, off_segstart, off_grid, total;
+  void build(uint32_t frames, uint32_t segs) {
+    off_ctrl = 0;
+    off_acc = align_up(sizeof(Ctrl), 64);
+    off_hist = align_up(off_acc + sizeof(FrameAcc) * frames, 64);
+    zero_bytes = off_hist + sizeof(uint32_t) * CM_MAX_SORT_PASSES * CM_RADIX;
+    off_info = align_up(zero_bytes, 64);
+    off_fstart = align_up(off_info + sizeof(SortInfo), 64);
+    off_segstart = align_up(off_fstart + sizeof(uint32_t) * (frames + 1), 64);
+    off_grid = align_up(off_segstart + sizeof(uint32_t) * segs, 64);
+    total = align_up(off_grid + sizeof(GridDev) * frames, 256);
+  }
+};
+
+enum StageEv { EV_START = 0, EV_K1, EV_GRID, EV_KEY, EV_SORT, EV_CENT, EV_COUNT };
+
+struct Workspace {
+  bool ready = false;
+  uint32_t cap_points = 0, cap_frames = 0, cap_segs = 0;
+  int out_step = 16;
+  MetaLayout ml{};
+  uint8_t* meta = nullptr;
+  uint8_t* report = nullptr;  // pinned host mirror of meta
+  SegDev* segs = nullptr;
+  std::vector<SegDev> segs_host;  // what is currently uploaded
+  float4* surv_xyzi = nullptr;
+  uint32_t* surv_src = nullptr;
+  void *keys_a = nullptr, *keys_b = nullptr;
+  uint32_t *vals_a = nullptr, *vals_b = nullptr;
+  unsigned long long *lb_k1 = nullptr, *lb_sort = nullptr, *lb_cent = nullptr;
+  size_t lb_k1_n = 0, lb_sort_n = 0, lb_cent_n = 0;
+  void* out_xyzi = nullptr;
+  uint32_t* out_count = nullptr;
+  unsigned long long* out_idx = nullptr;
+  cudaEvent_t ev[EV_COUNT]{};
+  // description of the last run
+  bool has_run = false, report_valid = false, profiled = false;
+  uint32_t n_frames = 0, n_segs = 0;
+  int64_t points_in = 0;
+  uint32_t key_bytes = 8, max_passes = 8;
+  const float4* voxel_pts = nullptr;  // points the voxel stage read (survivors or the caller's cloud)
+  bool ran_k1 = false, ran_voxel = false;
+  int64_t launches = 0;
+  cudaStream_t stream = nullptr;
+};
+
+struct SensorState {
+  bool submitted = false;
+  int64_t n_points = 0;
+  cm_layout_t layout{};
+  uint64_t stamp = 0;
+  cudaEvent_t copied = nullptr;
+};
+
+struct Slot {
+  Workspace ws;
+  uint8_t* raw_dev = nullptr;
+  uint8_t* raw_pinned = nullptr;
+  std::vector<SensorState> sensor;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t done = nullptr;
+  int64_t ticket = -1;
+  bool busy = false;
+  uint64_t used_mask = 0, stamp = 0;
+};
+
+}  // namespace
+
+struct cm_handle_s {
+  cm_config_t cfg{};
+  int device = 0;
+  std::mutex mu;
+  std::string last_error;
+  // configuration
+  float mats_host[CM_MAX_SENSORS * 12];
+  float* mats_dev = nullptr;
+  CropDev crop{};
+  float leaf[3] = {0.1f, 0.1f, 0.1f};
+  float inv_leaf[3] = {10.f, 10.f, 10.f};
+  uint32_t min_points = 2;
+  uint32_t downsample_all = 1;
+  int overflow_mode = 0;
+  bool profiling = false;
+  // run bookkeeping
+  uint32_t run_counter = 0;
+  Workspace batch;          // device-resident batch path
+  Workspace* last = nullptr;  // workspace of the most recent run
+  std::vector<cm_frame_info_t> frame_info;
+  cm_stats_t stats{};
+  float stage_ms[EV_COUNT]{};
+  // host path
+  std::vector<Slot> slots;
+  std::vector<cudaStream_t> sensor_stream;
+  size_t slot_stride = 0;
+  int fill = 0;
+  int64_t ticket_counter = 0;
+  bool host_ready = false;
+};
+
+namespace {
+
+int fail(cm_handle_t h, int code, const char* fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  if (h) h->last_error = buf;
+  return code;
+}
+
+#define CM_CUDA(h, expr)                                                                              \
+  do {                                                                                                \
+    cudaError_t e__ = (expr);                                                                         \
+    if (e__ != cudaSuccess) return fail(h, CM_E_CUDA, "%s: %s (%s:%d)", #expr, cudaGetErrorString(e__), \
+                                        __FILE__, __LINE__);                                          \
+  } while (0)
+
+template <typename T>
+cudaError_t dev_alloc(T** p, size_t count) {
+  return cudaMalloc(reinterpret_cast<void**>(p), std::max<size_t>(count * sizeof(T), kAlign));
+}
+
+void ws_free(Workspace& w) {
+  if (!w.ready) return;
+  cudaFree(w.meta); cudaFreeHost(w.report); cudaFree(w.segs); cudaFree(w.surv_xyzi); cudaFree(w.surv_src);
+  cudaFree(w.keys_a); cudaFree(w.keys_b); cudaFree(w.vals_a); cudaFree(w.vals_b);
+  cudaFree(w.lb_k1); cudaFree(w.lb_sort); cudaFree(w.lb_cent);
+  cudaFree(w.out_xyzi); cudaFree(w.out_count); cudaFree(w.out_idx);
+  for (auto& e : w.ev) if (e) cudaEventDestroy(e);
+  w = Workspace();
+}
+
+int ws_alloc(cm_handle_t h, Workspace& w, uint32_t points, uint32_t frames, uint32_t segs, int out_step) {
+  w.cap_points = points; w.cap_frames = frames; w.cap_segs = segs; w.out_step = out_step;
+  w.ml.build(frames, segs);
+  const size_t np = std::max<uint32_t>(points, 1);
+  CM_CUDA(h, dev_alloc(&w.meta, w.ml.total));
+  CM_CUDA(h, cudaMemset(w.meta, 0, w.ml.total));
+  CM_CUDA(h, cudaMallocHost(reinterpret_cast<void**>(&w.report), w.ml.total));
+  memset(w.report, 0, w.ml.total);
+  CM_CUDA(h, dev_alloc(&w.segs, segs));
+  CM_CUDA(h, dev_alloc(&w.surv_xyzi, np));
+  CM_CUDA(h, dev_alloc(&w.surv_src, np));
+  CM_CUDA(h, cudaMalloc(&w.keys_a, np * 8));
+  CM_CUDA(h, cudaMalloc(&w.keys_b, np * 8));
+  CM_CUDA(h, dev_alloc(&w.vals_a, np));
+  CM_CUDA(h, dev_alloc(&w.vals_b, np));
+  // every segment owns at least one K1 tile
+  w.lb_k1_n = np / k1_tile_points() + segs + 2;
+  const uint32_t st = std::min(sort_tile_items(4), sort_tile_items(8));
+  w.lb_sort_n = (np / st + 2) * CM_RADIX;
+  w.lb_cent_n = np / centroid_tile_items() + 2;
+  CM_CUDA(h, dev_alloc(&w.lb_k1, w.lb_k1_n));
+  CM_CUDA(h, dev_alloc(&w.lb_sort, w.lb_sort_n));
+  CM_CUDA(h, dev_alloc(&w.lb_cent, w.lb_cent_n));
+  CM_CUDA(h, cudaMemset(w.lb_k1, 0, w.lb_k1_n * 8));
+  CM_CUDA(h, cudaMemset(w.lb_sort, 0, w.lb_sort_n * 8));
+  CM_CUDA(h, cudaMemset(w.lb_cent, 0, w.lb_cent_n * 8));
+  CM_CUDA(h, cudaMalloc(&w.out_xyzi, np * (size_t)out_step));
+  CM_CUDA(h, dev_alloc(&w.out_count, np));
+  CM_CUDA(h, dev_alloc(&w.out_idx, np));
+  for (auto& e : w.ev) CM_CUDA(h, cudaEventCreate(&e));
+  w.ready = true;
+  return CM_OK;
+}
+
+uint32_t next_epoch(cm_handle_t h) {
+  // epochs are 30-bit; a run uses 16 of them. On wrap the look-back arrays are cleared.
+  if ((uint64_t)(h->run_counter + 2) * 16ull >= (1ull << 30)) {
+    auto clear = [](Workspace& w) {
+      if (!w.ready) return;
+      cudaMemset(w.lb_k1, 0, w.lb_k1_n * 8); cudaMemset(w.lb_sort, 0, w.lb_sort_n * 8);
+      cudaMemset(w.lb_cent, 0, w.lb_cent_n * 8);
+    };
+    cudaDeviceSynchronize();
+    clear(h->batch);
+    for (auto& s : h->slots) clear(s.ws);
+    h->run_counter = 0;
+  }
+  ++h->run_counter;
+  return h->run_counter * 16u;
+}
+
+uint32_t seg_mode(const cm_layout_t& L) {
+  if (L.point_step == 16 && L.off_x == 0 && L.off_y == 4 && L.off_z == 8 && L.off_intensity == 12) return SEG_PACKED16;
+  if (L.point_step == 32 && L.off_x == 0 && L.off_y == 4 && L.off_z == 8 && L.off_intensity == 16) return SEG_PCL32;
+  const bool a4 = (L.point_step % 4 == 0) && (L.off_x % 4 == 0) && (L.off_y % 4 == 0) && (L.off_z % 4 == 0) &&
+                  (L.off_intensity < 0 || L.off_intensity % 4 == 0);
+  if (a4) return SEG_ALIGNED4;
+  if (L.point_step <= CM_MAX_STAGED_STEP) return SEG_STAGED;
+  return SEG_BYTES;
+}
+
+bool layout_ok(const cm_layout_t& L) {
+  if (L.point_step < 12 || L.point_step > 65535) return false;
+  auto in = [&](int off) { return off >= 0 && off + 4 <= L.point_step; };
+  if (!in(L.off_x) || !in(L.off_y) || !in(L.off_z)) return false;
+  if (L.off_intensity >= 0 && !in(L.off_intensity)) return false;
+  return true;
+}
+
+inline uint32_t bits_for(unsigned long long count) {  // bits needed to index `count` distinct values
+  uint32_t b = 0;
+  while (b < 64 && (count - 1ull) >> b) ++b;
+  return count <= 1 ? 0 : b;
+}
+
+// Upper bound of the cells of one frame that follows from the crop box alone (no device round trip).
+bool crop_cell_bound(cm_handle_t h, unsigned long long* cells) {
+  if (h->crop.n_pass <= 0) return false;
+  unsigned long long prod = 1;
+  for (int a = 0; a < 3; ++a) {
+    float lo = -std::numeric_limits<float>::infinity(), hi = std::numeric_limits<float>::infinity();
+    for (int k = 0; k < h->crop.n_pass; ++k) {
+      const PassDev& ps = h->crop.pass[k];
+      if (ps.axis != a || ps.negative) continue;
+      if (!(ps.lo == ps.lo) || !(ps.hi == ps.hi)) return false;  // NaN limits bound nothing
+      lo = std::max(lo, ps.lo);
+      hi = std::min(hi, ps.hi);
+    }
+    if (!std::isfinite(lo) || !std::isfinite(hi)) return false;
+    long long div = 1;
+    if (hi >= lo) {
+      const float flo = std::floor(lo * h->inv_leaf[a]), fhi = std::floor(hi * h->inv_leaf[a]);
+      if (!(std::fabs(flo) < 1e9f) || !(std::fabs(fhi) < 1e9f)) return false;
+      div = (long long)fhi - (long long)flo + 1;
+    }
+    if (div > (1ll << 21)) return false;
+    prod *= (unsigned long long)div;
+  }
+  *cells = prod;
+  return true;
+}
+
+void fill_voxel_params(cm_handle_t h, Workspace& w, VoxelParams& vp, const float4* pts, uint32_t n_frames,
+                       uint32_t max_points, uint32_t epoch) {
+  vp.pts = pts;
+  vp.frame_surv_start = reinterpret_cast<uint32_t*>(w.meta + w.ml.off_fstart);
+  vp.n_frames = n_frames;
+  vp.max_points = max_points;
+  for (int k = 0; k < 3; ++k) vp.inv_leaf[k] = h->inv_leaf[k];
+  vp.min_points = h->min_points;
+  vp.downsample_all = h->downsample_all;
+  vp.key_bytes = 8;
+  vp.out_step = (uint32_t)w.out_step;
+  vp.ctrl = reinterpret_cast<Ctrl*>(w.meta + w.ml.off_ctrl);
+  vp.acc = reinterpret_cast<FrameAcc*>(w.meta + w.ml.off_acc);
+  vp.grid = reinterpret_cast<GridDev*>(w.meta + w.ml.off_grid);
+  vp.info = reinterpret_cast<SortInfo*>(w.meta + w.ml.off_info);
+  vp.hist = reinterpret_cast<uint32_t*>(w.meta + w.ml.off_hist);
+  vp.keys_a = w.keys_a; vp.keys_b = w.keys_b; vp.vals_a = w.vals_a; vp.vals_b = w.vals_b;
+  vp.lb_sort = w.lb_sort; vp.lb_cent = w.lb_cent;
+  vp.epoch = epoch;
+  vp.max_passes = CM_MAX_SORT_PASSES;
+  vp.out_xyzi = w.out_xyzi; vp.out_count = w.out_count; vp.out_idx = w.out_idx;
+}
+
+// VoxelGrid stages on vp.pts. bounded: the crop box bounds the key width, so no device round trip is needed.
+int run_voxel(cm_handle_t h, Workspace& w, VoxelParams& vp, cudaStream_t st) {
+  unsigned long long cells = 0;
+  const bool bounded = w.ran_k1 && crop_cell_bound(h, &cells);
+  if (bounded) {
+    const uint32_t bits = bits_for(cells) + bits_for(vp.n_frames);
+    vp.key_bytes = bits <= 32 ? 4 : 8;
+    vp.max_passes = std::max<uint32_t>(1, (bits + CM_RADIX_BITS - 1) / CM_RADIX_BITS);
+  } else {
+    vp.key_bytes = 8;
+    vp.max_passes = CM_MAX_SORT_PASSES;
+  }
+  CM_CUDA(h, launch_grid_setup(vp, st));
+  ++w.launches;
+  if (h->profiling) CM_CUDA(h, cudaEventRecord(w.ev[EV_GRID], st));
+  if (!bounded) {
+    // the key width is only known on the device: fetch the plan (one small round trip), then size the sort to it
+    SortInfo si;
+    CM_CUDA(h, cudaMemcpyAsync(w.report + w.ml.off_info, w.meta + w.ml.off_info, sizeof(SortInfo), cudaMemcpyDeviceToHost, st));
+    CM_CUDA(h, cudaStreamSynchronize(st));
+    memcpy(&si, w.report + w.ml.off_info, sizeof(si));
+    vp.key_bytes = si.total_bits <= 32 ? 4 : 8;
+    vp.max_passes = si.num_passes;
+  }
+  w.key_bytes = vp.key_bytes;
+  w.max_passes = vp.max_passes;
+  CM_CUDA(h, launch_key_hist(vp, st));
+  ++w.launches;
+  if (h->profiling) CM_CUDA(h, cudaEventRecord(w.ev[EV_KEY], st));
+  for (uint32_t ps = 0; ps < vp.max_passes; ++ps) {
+    CM_CUDA(h, launch_sort_pass(vp, (int)ps, st));
+    ++w.launches;
+  }
+  if (h->profiling) CM_CUDA(h, cudaEventRecord(w.ev[EV_SORT], st));
+  CM_CUDA(h, launch_centroid(vp, st));
+  ++w.launches;
+  CM_CUDA(h, cudaEventRecord(w.ev[EV_CENT], st));
+  w.ran_voxel = true;
+  return CM_OK;
+}
+
+// Build the device segment table for a batch; returns total points / frames / K1 tiles.
+int build_segments(cm_handle_t h, Workspace& w, const cm_segment_t* segs, int n_seg, std::vector<SegDev>& out,
+                   uint32_t* n_frames, uint32_t* n_tiles, int64_t* total_points, uint32_t* staged_smem) {
+  if (n_seg <= 0 || !segs) return fail(h, CM_E_INVALID, "no segments");
+  if ((uint32_t)n_seg > w.cap_segs) return fail(h, CM_E_CAPACITY, "%d segments > capacity %u", n_seg, w.cap_segs);
+  out.resize(n_seg);
+  const uint32_t T = k1_tile_points();
+  uint32_t tile = 0, frame = 0, src_base = 0, max_step_staged = 0;
+  int64_t total = 0;
+  for (int s = 0; s < n_seg; ++s) {
+    const cm_segment_t& g = segs[s];
+    if (!layout_ok(g.layout)) return fail(h, CM_E_INVALID, "segment %d: bad layout", s);
+    if (g.n_points < 0 || g.n_points > 0xFFFFFFF0ll) return fail(h, CM_E_INVALID, "segment %d: bad n_points", s);
+    if (g.n_points > 0 && (!g.data || (reinterpret_cast<uintptr_t>(g.data) & 15u)))
+      return fail(h, CM_E_INVALID, "segment %d: data must be a 16-byte aligned device pointer", s);
+    if (g.sensor < 0 || g.sensor >= h->cfg.max_sensors) return fail(h, CM_E_INVALID, "segment %d: bad sensor", s);
+    const bool first = (s == 0) || (g.frame != segs[s - 1].frame);
+    if (s == 0 ? g.frame != 0 : (g.frame != segs[s - 1].frame && g.frame != segs[s - 1].frame + 1))
+      return fail(h, CM_E_INVALID, "segment %d: frames must start at 0 and increase by steps of 1", s);
+    if (first) { frame = (uint32_t)g.frame; src_base = 0; }
+    SegDev& d = out[s];
+    d.data = static_cast<const uint8_t*>(g.data);
+    d.n_points = (uint32_t)g.n_points;
+    d.tile_begin = tile;
+    d.src_base = src_base;
+    d.frame = frame;
+    d.point_step = g.layout.point_step;
+    d.off_x = g.layout.off_x; d.off_y = g.layout.off_y; d.off_z = g.layout.off_z;
+    d.off_i = g.layout.off_intensity >= 0 ? g.layout.off_intensity : -1;
+    d.is_dense = g.layout.is_dense ? 1u : 0u;
+    d.sensor = (uint32_t)g.sensor;
+    d.first_of_frame = first ? 1u : 0u;
+    d.mode = seg_mode(g.layout);
+    d.pad_ = 0;
+    if (d.mode == SEG_STAGED) max_step_staged = std::max<uint32_t>(max_step_staged, (uint32_t)d.point_step);
+    tile += std::max<uint32_t>(1u, (d.n_points + T - 1) / T);
+    src_base += d.n_points;
+    total += g.n_points;
+  }
+  if (frame + 1 > w.cap_frames) return fail(h, CM_E_CAPACITY, "%u frames > capacity %u", frame + 1, w.cap_frames);
+  if (total > (int64_t)w.cap_points) return fail(h, CM_E_CAPACITY, "%lld points > capacity %u", (long long)total, w.cap_points);
+  if ((size_t)tile + 1 > w.lb_k1_n) return fail(h, CM_E_CAPACITY, "too many tiles");
+  *n_frames = frame + 1; *n_tiles = tile; *total_points = total;
+  *staged_smem = max_step_staged ? T * max_step_staged + 16u : 0u;
+  return CM_OK;
+}
+
+int run_pipeline(cm_handle_t h, Workspace& w, const cm_segment_t* segs, int n_seg, cudaStream_t st, bool with_voxel) {
+  uint32_t n_frames = 0, n_tiles = 0, staged = 0;
+  int64_t total = 0;
+  std::vector<SegDev> sd;
+  int rc = build_segments(h, w, segs, n_seg, sd, &n_frames, &n_tiles, &total, &staged);
+  if (rc != CM_OK) return rc;
+  if (sd.size() != w.segs_host.size() || memcmp(sd.data(), w.segs_host.data(), sd.size() * sizeof(SegDev)) != 0) {
+    CM_CUDA(h, cudaMemcpyAsync(w.segs, sd.data(), sd.size() * sizeof(SegDev), cudaMemcpyHostToDevice, st));
+    w.segs_host = sd;
+  }
+  const uint32_t epoch = next_epoch(h);
+  w.has_run = true; w.report_valid = false; w.profiled = h->profiling;
+  w.n_frames = n_frames; w.n_segs = (uint32_t)n_seg; w.points_in = total; w.launches = 0;
+  w.ran_k1 = true; w.ran_voxel = false; w.stream = st;
+  w.voxel_pts = w.surv_xyzi;
+  h->last = &w;
+
+  CM_CUDA(h, cudaEventRecord(w.ev[EV_START], st));
+  CM_CUDA(h, cudaMemsetAsync(w.meta, 0, w.ml.zero_bytes, st));
+  K1Params kp;
+  kp.segs = w.segs; kp.n_seg = (uint32_t)n_seg; kp.n_tiles = n_tiles; kp.n_frames = n_frames; kp.epoch = epoch;
+  kp.mats = h->mats_dev; kp.crop = h->crop;
+  kp.surv_xyzi = w.surv_xyzi; kp.surv_src = w.surv_src;
+  kp.ctrl = reinterpret_cast<Ctrl*>(w.meta + w.ml.off_ctrl);
+  kp.acc = reinterpret_cast<FrameAcc*>(w.meta + w.ml.off_acc);
+  kp.frame_surv_start = reinterpret_cast<uint32_t*>(w.meta + w.ml.off_fstart);
+  kp.seg_surv_start = reinterpret_cast<uint32_t*>(w.meta + w.ml.off_segstart);
+  kp.lb = w.lb_k1;
+  CM_CUDA(h, launch_transform_crop(kp, staged, st));
+  ++w.launches;
+  CM_CUDA(h, cudaEventRecord(w.ev[EV_K1], st));
+  if (!with_voxel) return CM_OK;
+  VoxelParams vp;
+  fill_voxel_params(h, w, vp, w.surv_xyzi, n_frames, (uint32_t)total, epoch);
+  return run_voxel(h, w, vp, st);
+}
+
+// D2H of the control block of the last run + decode into stats / frame info. Blocks.
+int fetch_report(cm_handle_t h, Workspace& w) {
+  if (!w.has_run) return fail(h, CM_E_INVALID, "nothing has run on this handle");
+  if (w.report_valid) return CM_OK;
+  CM_CUDA(h, cudaMemcpyAsync(w.report, w.meta, w.ml.total, cudaMemcpyDeviceToHost, w.stream));
+  CM_CUDA(h, cudaStreamSynchronize(w.stream));
+  const Ctrl* ctrl = reinterpret_cast<const Ctrl*>(w.report + w.ml.off_ctrl);
+  const FrameAcc* acc = reinterpret_cast<const FrameAcc*>(w.report + w.ml.off_acc);
+  const SortInfo* si = reinterpret_cast<const SortInfo*>(w.report + w.ml.off_info);
+  const uint32_t* fstart = reinterpret_cast<const uint32_t*>(w.report + w.ml.off_fstart);
+  const GridDev* grid = reinterpret_cast<const GridDev*>(w.report + w.ml.off_grid);
+  cm_stats_t& s = h->stats;
+  memset(&s, 0, sizeof(s));
+  s.points_in = w.points_in;
+  s.frames = (int32_t)w.n_frames;
+  s.survivors = fstart[w.n_frames];
+  s.device_error = (int32_t)ctrl->error;
+  h->frame_info.assign(w.n_frames, cm_frame_info_t{});
+  int64_t vbeg = 0;
+  for (uint32_t f = 0; f < w.n_frames; ++f) {
+    cm_frame_info_t& fi = h->frame_info[f];
+    fi.survivor_begin = fstart[f];
+    fi.survivor_end = fstart[f + 1];
+    if (w.ran_voxel) {
+      fi.voxel_begin = vbeg;
+      vbeg += acc[f].voxel_count;
+      fi.voxel_end = vbeg;
+      for (int k = 0; k < 3; ++k) { fi.min_b[k] = grid[f].min_b[k]; fi.max_b[k] = grid[f].max_b[k]; fi.div_b[k] = grid[f].div_b[k]; }
+      fi.pcl_overflow = grid[f].pcl_overflow;
+      s.pcl_overflow += grid[f].pcl_overflow;
+    }
+  }
+  if (w.ran_voxel) {
+    s.voxels_out = ctrl->total_voxels;
+    s.key_bits = (int32_t)si->total_bits;
+    s.sort_passes = (int32_t)si->num_passes;
+    s.key_bytes = (int32_t)w.key_bytes;
+  }
+  const int last_ev = w.ran_voxel ? EV_CENT : EV_K1;
+  float ms = 0.f;
+  if (cudaEventElapsedTime(&ms, w.ev[EV_START], w.ev[last_ev]) == cudaSuccess) s.gpu_ms = ms;
+  for (auto& v : h->stage_ms) v = -1.f;
+  h->stage_ms[EV_START] = s.gpu_ms;
+  if (w.profiled) {
+    float t;
+    if (cudaEventElapsedTime(&t, w.ev[EV_START], w.ev[EV_K1]) == cudaSuccess) h->stage_ms[EV_K1] = t;
+    if (w.ran_voxel) {
+      if (cudaEventElapsedTime(&t, w.ev[EV_K1], w.ev[EV_GRID]) == cudaSuccess) h->stage_ms[EV_GRID] = t;
+      if (cudaEventElapsedTime(&t, w.ev[EV_GRID], w.ev[EV_KEY]) == cudaSuccess) h->stage_ms[EV_KEY] = t;
+      if (cudaEventElapsedTime(&t, w.ev[EV_KEY], w.ev[EV_SORT]) == cudaSuccess) h->stage_ms[EV_SORT] = t;
+      if (cudaEventElapsedTime(&t, w.ev[EV_SORT], w.ev[EV_CENT]) == cudaSuccess) h->stage_ms[EV_CENT] = t;
+    }
+  }
+  w.report_valid = true;
+  if (ctrl->error == CM_DEV_E_KEY_RANGE) return fail(h, CM_E_KEY_RANGE, "voxel grid exceeds the key range (leaf too small for the extent)");
+  if (ctrl->error) return fail(h, CM_E_INTERNAL, "device watchdog tripped (code %u)", ctrl->error);
+  return CM_OK;
+}
+
+int ensure_batch_ws(cm_handle_t h) {
+  if (h->batch.ready) return CM_OK;
+  const cm_config_t& c = h->cfg;
+  return ws_alloc(h, h->batch, (uint32_t)c.max_batch_points, (uint32_t)c.max_batch_frames, (uint32_t)c.max_batch_segments,
+                  c.out_point_step);
+}
+
+int ensure_host_path(cm_handle_t h) {
+  if (h->host_ready) return CM_OK;
+  const cm_config_t& c = h->cfg;
+  h->slot_stride = align_up((size_t)c.max_points_per_sensor * (size_t)c.max_point_step + 16, kAlign);
+  h->sensor_stream.resize(c.max_sensors);
+  for (auto& s : h->sensor_stream) CM_CUDA(h, cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
+  h->slots.resize(c.frames_in_flight);
+  const uint64_t pts = (uint64_t)c.max_sensors * (uint64_t)c.max_points_per_sensor;
+  if (pts > 0xFFFFFFF0ull) return fail(h, CM_E_CAPACITY, "max_sensors * max_points_per_sensor too large");
+  for (auto& sl : h->slots) {
+    int rc = ws_alloc(h, sl.ws, (uint32_t)pts, 1, (uint32_t)c.max_sensors, c.out_point_step);
+    if (rc != CM_OK) return rc;
+    CM_CUDA(h, cudaMalloc(reinterpret_cast<void**>(&sl.raw_dev), h->slot_stride * c.max_sensors));
+    CM_CUDA(h, cudaMallocHost(reinterpret_cast<void**>(&sl.raw_pinned), h->slot_stride * c.max_sensors));
+    sl.sensor.resize(c.max_sensors);
+    for (auto& ss : sl.sensor) CM_CUDA(h, cudaEventCreateWithFlags(&ss.copied, cudaEventDisableTiming));
+    CM_CUDA(h, cudaStreamCreateWithFlags(&sl.stream, cudaStreamNonBlocking));
+    CM_CUDA(h, cudaEventCreateWithFlags(&sl.done, cudaEventDisableTiming));
+  }
+  h->host_ready = true;
+  return CM_OK;
+}
+
+int submit_impl(cm_handle_t h, int sensor, const void* data, int64_t n_points, const cm_layout_t* layout, uint64_t stamp,
+                bool pinned_src) {
+  if (!h) return CM_E_INVALID;
+  std::lock_guard<std::mutex> lk(h->mu);
+  CM_CUDA(h, cudaSetDevice(h->device));
+  if (sensor < 0 || sensor >= h->cfg.max_sensors) return fail(h, CM_E_INVALID, "sensor %d out of range", sensor);
+  if (!layout || !layout_ok(*layout)) return fail(h, CM_E_INVALID, "bad layout");
+  if (n_points < 0 || (n_points > 0 && !data)) return fail(h, CM_E_INVALID, "bad cloud");
+  if (n_points > h->cfg.max_points_per_sensor) return fail(h, CM_E_CAPACITY, "cloud of %lld points > max_points_per_sensor", (long long)n_points);
+  if (layout->point_step > h->cfg.max_point_step) return fail(h, CM_E_CAPACITY, "point_step %d > max_point_step", layout->point_step);
+  int rc = ensure_host_path(h);
+  if (rc != CM_OK) return rc;
+  Slot& sl = h->slots[h->fill];
+  if (sl.busy) return fail(h, CM_E_CAPACITY, "all %d frame slots are in flight: call cm_wait_frame first", h->cfg.frames_in_flight);
+  SensorState& ss = sl.sensor[sensor];
+  const size_t bytes = (size_t)n_points * (size_t)layout->point_step;
+  uint8_t* dst = sl.raw_dev + (size_t)sensor * h->slot_stride;
+  cudaStream_t st = h->sensor_stream[sensor];
+  if (bytes) {
+    if (pinned_src) {
+      CM_CUDA(h, cudaMemcpyAsync(dst, data, bytes, cudaMemcpyHostToDevice, st));
+    } else {
+      uint8_t* stg = sl.raw_pinned + (size_t)sensor * h->slot_stride;
+      CM_CUDA(h, cudaEventSynchronize(ss.copied));  // the previous copy out of this staging buffer is done
+      memcpy(stg, data, bytes);
+      CM_CUDA(h, cudaMemcpyAsync(dst, stg, bytes, cudaMemcpyHostToDevice, st));
+    }
+  }
+  CM_CUDA(h, cudaEventRecord(ss.copied, st));
+  ss.submitted = true; ss.n_points = n_points; ss.layout = *layout; ss.stamp = stamp;
+  return CM_OK;
+}
+
+int merge_async_impl(cm_handle_t h, uint64_t mask, int64_t* ticket) {
+  int rc = ensure_host_path(h);
+  if (rc != CM_OK) return rc;
+  Slot& sl = h->slots[h->fill];
+  if (sl.busy) return fail(h, CM_E_CAPACITY, "frame slot still in flight");
+  std::vector<cm_segment_t> segs;
+  uint64_t used = 0, stamp = 0;
+  for (int s = 0; s < h->cfg.max_sensors; ++s) {
+    if (!((mask >> s) & 1ull)) continue;
+    SensorState& ss = sl.sensor[s];
+    if (!ss.submitted) continue;
+    cm_segment_t g;
+    g.data = sl.raw_dev + (size_t)s * h->slot_stride;
+    g.n_points = ss.n_points; g.layout = ss.layout; g.sensor = s; g.frame = 0;
+    segs.push_back(g);
+    used |= 1ull << s;
+    stamp = std::max(stamp, ss.stamp);  // operator+= keeps the newest stamp
+    CM_CUDA(h, cudaStreamWaitEvent(sl.stream, ss.copied, 0));
+  }
+  if (segs.empty()) return fail(h, CM_E_NOT_READY, "no submitted cloud for any sensor in the mask");
+  rc = run_pipeline(h, sl.ws, segs.data(), (int)segs.size(), sl.stream, true);
+  if (rc != CM_OK) return rc;
+  CM_CUDA(h, cudaMemcpyAsync(sl.ws.report, sl.ws.meta, sl.ws.ml.total, cudaMemcpyDeviceToHost, sl.stream));
+  CM_CUDA(h, cudaEventRecord(sl.done, sl.stream));
+  for (int s = 0; s < h->cfg.max_sensors; ++s)
+    if ((used >> s) & 1ull) sl.sensor[s].submitted = false;
+  sl.busy = true; sl.used_mask = used; sl.stamp = stamp;
+  sl.ticket = ++h->ticket_counter;
+  *ticket = sl.ticket;
+  h->fill = (h->fill + 1) % (int)h->slots.size();
+  return CM_OK;
+}
+
+int wait_impl(cm_handle_t h, int64_t ticket, cm_frame_out_t* out, uint64_t* used_mask, uint64_t* out_stamp) {
+  Slot* sl = nullptr;
+  for (auto& s : h->slots) if (s.busy && s.ticket == ticket) sl = &s;
+  if (!sl) return fail(h, CM_E_INVALID, "unknown ticket %lld", (long long)ticket);
+  Workspace& w = sl->ws;
+  h->last = &w;
+  int rc = fetch_report(h, w);
+  sl->busy = false;
+  if (rc != CM_OK) return rc;
+  if (used_mask) *used_mask = sl->used_mask;
+  if (out_stamp) *out_stamp = sl->stamp;
+  if (!out) return CM_OK;
+  const cm_frame_info_t& fi = h->frame_info[0];
+  out->info = fi;
+  out->n_survivors = fi.survivor_end - fi.survivor_begin;
+  out->n_voxels = fi.voxel_end - fi.voxel_begin;
+  const bool pcl_refuses = h->overflow_mode == 1 && fi.pcl_overflow;
+  if (pcl_refuses) out->n_voxels = out->n_survivors;  // PCL 1.8.1: output = *input_
+  if ((out->voxel_xyzi || out->voxel_count || out->voxel_idx) && out->n_voxels > out->voxel_capacity)
+    return fail(h, CM_E_CAPACITY, "voxel_capacity %lld < %lld voxels", (long long)out->voxel_capacity, (long long)out->n_voxels);
+  if ((out->survivor_xyzi || out->survivor_src) && out->n_survivors > out->survivor_capacity)
+    return fail(h, CM_E_CAPACITY, "survivor_capacity %lld < %lld survivors", (long long)out->survivor_capacity, (long long)out->n_survivors);
+  cudaStream_t st = sl->stream;
+  const size_t nv = (size_t)out->n_voxels, ns = (size_t)out->n_survivors;
+  if (pcl_refuses) {
+    if (out->voxel_xyzi && nv) {
+      if (w.out_step == 16) {
+        CM_CUDA(h, cudaMemcpyAsync(out->voxel_xyzi, w.surv_xyzi, nv * 16, cudaMemcpyDeviceToHost, st));
+      } else {
+        // expand packed survivors into pcl::PointXYZI records on the host side of the copy
+        std::vector<float> tmp(nv * 4);
+        CM_CUDA(h, cudaMemcpyAsync(tmp.data(), w.surv_xyzi, nv * 16, cudaMemcpyDeviceToHost, st));
+        CM_CUDA(h, cudaStreamSynchronize(st));
+        float* o = static_cast<float*>(out->voxel_xyzi);
+        for (size_t i = 0; i < nv; ++i) {
+          o[i * 8 + 0] = tmp[i * 4 + 0]; o[i * 8 + 1] = tmp[i * 4 + 1]; o[i * 8 + 2] = tmp[i * 4 + 2]; o[i * 8 + 3] = 1.0f;
+          o[i * 8 + 4] = tmp[i * 4 + 3]; o[i * 8 + 5] = 0.f; o[i * 8 + 6] = 0.f; o[i * 8 + 7] = 0.f;
+        }
+      }
+    }
+    if (out->voxel_count) for (size_t i = 0; i < nv; ++i) out->voxel_count[i] = 1;
+    if (out->voxel_idx) for (size_t i = 0; i < nv; ++i) out->voxel_idx[i] = 0;
+  } else {
+    if (out->voxel_xyzi && nv) CM_CUDA(h, cudaMemcpyAsync(out->voxel_xyzi, w.out_xyzi, nv * (size_t)w.out_step, cudaMemcpyDeviceToHost, st));
+    if (out->voxel_count && nv) CM_CUDA(h, cudaMemcpyAsync(out->voxel_count, w.out_count, nv * 4, cudaMemcpyDeviceToHost, st));
+    if (out->voxel_idx && nv) CM_CUDA(h, cudaMemcpyAsync(out->voxel_idx, w.out_idx, nv * 8, cudaMemcpyDeviceToHost, st));
+  }
+  if (out->survivor_xyzi && ns) CM_CUDA(h, cudaMemcpyAsync(out->survivor_xyzi, w.surv_xyzi, ns * 16, cudaMemcpyDeviceToHost, st));
+  if (out->survivor_src && ns) CM_CUDA(h, cudaMemcpyAsync(out->survivor_src, w.surv_src, ns * 4, cudaMemcpyDeviceToHost, st));
+  CM_CUDA(h, cudaStreamSynchronize(st));
+  return CM_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* cm_version(void) { return "cloud_merger_b200 0.1 (sm_100a)"; }
+
+const char* cm_strerror(int code) {
+  switch (code) {
+    case CM_OK: return "ok";
+    case CM_E_INVALID: return "invalid argument";
+    case CM_E_CAPACITY: return "capacity exceeded";
+    case CM_E_CUDA: return "CUDA error";
+    case CM_E_NO_DEVICE: return "no usable CUDA device";
+    case CM_E_KEY_RANGE: return "voxel grid exceeds the key range";
+    case CM_E_INTERNAL: return "device watchdog tripped";
+    case CM_E_NOT_READY: return "no cloud submitted";
+    default: return "unknown error";
+  }
+}
+
+const char* cm_last_error(cm_handle_t h) { return h ? h->last_error.c_str() : "null handle"; }
+
+int cm_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
+  return n;
+}
+
+int cm_create(const cm_config_t* cfg, cm_handle_t* out) {
+  if (!cfg || !out) return CM_E_INVALID;
+  *out = nullptr;
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0) return CM_E_NO_DEVICE;
+  if (cfg->device < 0 || cfg->device >= n) return CM_E_INVALID;
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, cfg->device) != cudaSuccess) return CM_E_CUDA;
+  if (prop.major != 10) return CM_E_NO_DEVICE;  // sm_100a code only
+  cm_handle_t h = new (std::nothrow) cm_handle_s();
+  if (!h) return CM_E_INTERNAL;
+  h->cfg = *cfg;
+  cm_config_t& c = h->cfg;
+  if (c.max_sensors <= 0) c.max_sensors = 6;
+  if (c.max_sensors > CM_MAX_SENSORS) { delete h; return CM_E_INVALID; }
+  if (c.max_points_per_sensor <= 0) c.max_points_per_sensor = 262144;
+  if (c.max_point_step <= 0) c.max_point_step = 32;
+  if (c.frames_in_flight <= 0) c.frames_in_flight = 2;
+  if (c.frames_in_flight > 8) c.frames_in_flight = 8;
+  if (c.max_batch_frames <= 0) c.max_batch_frames = 1;
+  if (c.max_batch_points <= 0) c.max_batch_points = (int64_t)c.max_sensors * c.max_points_per_sensor * c.max_batch_frames;
+  if (c.max_batch_segments <= 0) c.max_batch_segments = c.max_batch_frames * c.max_sensors;
+  if (c.out_point_step != 32) c.out_point_step = 16;
+  if (c.max_batch_points > 0xFFFFFFF0ll) { delete h; return CM_E_CAPACITY; }
+  h->device = c.device;
+  if (cudaSetDevice(h->device) != cudaSuccess) { delete h; return CM_E_CUDA; }
+  if (configure_device_kernels() != cudaSuccess) { delete h; return CM_E_CUDA; }
+  for (int s = 0; s < CM_MAX_SENSORS; ++s) {
+    float* m = h->mats_host + s * 12;
+    for (int k = 0; k < 12; ++k) m[k] = (k % 5 == 0) ? 1.f : 0.f;  // identity rows
+  }
+  if (cudaMalloc(reinterpret_cast<void**>(&h->mats_dev), sizeof(h->mats_host)) != cudaSuccess ||
+      cudaMemcpy(h->mats_dev, h->mats_host, sizeof(h->mats_host), cudaMemcpyHostToDevice) != cudaSuccess) {
+    delete h;
+    return CM_E_CUDA;
+  }
+  // defaults = getROI with Parameter.h:31-35 (z [-0.5, 3], y +-5, x [-15, 60]) and Parameter.h:27-28 (0.1 m, 2 points)
+  h->crop.n_pass = 3;
+  h->crop.pass[0] = PassDev{2, -0.5f, 3.0f, 0};
+  h->crop.pass[1] = PassDev{1, -10.0f / 2, 10.0f / 2, 0};
+  h->crop.pass[2] = PassDev{0, -15.0f, 75.0f - 15.0f, 0};
+  *out = h;
+  return CM_OK;
+}
+
+int cm_destroy(cm_handle_t h) {
+  if (!h) return CM_E_INVALID;
+  cudaSetDevice(h->device);
+  cudaDeviceSynchronize();
+  ws_free(h->batch);
+  for (auto& sl : h->slots) {
+    ws_free(sl.ws);
+    cudaFree(sl.raw_dev); cudaFreeHost(sl.raw_pinned);
+    for (auto& ss : sl.sensor) if (ss.copied) cudaEventDestroy(ss.copied);
+    if (sl.stream) cudaStreamDestroy(sl.stream);
+    if (sl.done) cudaEventDestroy(sl.done);
+  }
+  for (auto& s : h->sensor_stream) if (s) cudaStreamDestroy(s);
+  cudaFree(h->mats_dev);
+  delete h;
+  return CM_OK;
+}
+
+int cm_set_extrinsic(cm_handle_t h, int sensor, const float* m16, int col_major) {
+  if (!h || !m16) return CM_E_INVALID;
+  std::lock_guard<std::mutex> lk(h->mu);
+  if (sensor < 0 || sensor >= h->cfg.max_sensors) return fail(h, CM_E_INVALID, "sensor %d out of range", sensor);
+  float* m = h->mats_host + sensor * 12;
+  for (int r = 0; r < 3; ++r)
+    for (int c = 0; c < 4; ++c) m[r * 4 + c] = col_major ? m16[c * 4 + r] : m16[r * 4 + c];
+  CM_CUDA(h, cudaSetDevice(h->device));
+  CM_CUDA(h, cudaMemcpy(h->mats_dev + sensor * 12, m, 12 * sizeof(float), cudaMemcpyHostToDevice));
+  return CM_OK;
+}
+
+int cm_set_extrinsic_tf(cm_handle_t h, int sensor, const double* q, const double* t) {
+  if (!h || !q || !t) return CM_E_INVALID;
+  // pcl_ros::transformPointCloud(in, out, tf::Transform): Eigen::Quaternionf(q.w, q.x, q.y, q.z), Vector3f(origin),
+  // Affine3f(Translation3f(origin) * rotation); Eigen 3.3 QuaternionBase::toRotationMatrix.
+  const float x = (float)q[0], y = (float)q[1], z = (float)q[2], w = (float)q[3];
+  const float tx = 2.0f * x, ty = 2.0f * y, tz = 2.0f * z;
+  const float twx = tx * w, twy = ty * w, twz = tz * w;
+  const float txx = tx * x, txy = ty * x, txz = tz * x;
+  const float tyy = ty * y, tyz = tz * y, tzz = tz * z;
+  float m[16] = {1.0f - (tyy + tzz), txy - twz, txz + twy, (float)t[0],
+                 txy + twz, 1.0f - (txx + tzz), tyz - twx, (float)t[1],
+                 txz - twy, tyz + twx, 1.0f - (txx + tyy), (float)t[2],
+                 0.f, 0.f, 0.f, 1.f};
+  return cm_set_extrinsic(h, sensor, m, 0);
+}
+
+int cm_get_extrinsic(cm_handle_t h, int sensor, float* m12) {
+  if (!h || !m12) return CM_E_INVALID;
+  std::lock_guard<std::mutex> lk(h->mu);
+  if (sensor < 0 || sensor >= h->cfg.max_sensors) return fail(h, CM_E_INVALID, "sensor %d out of range", sensor);
+  memcpy(m12, h->mats_host + sensor * 12, 12 * sizeof(float));
+  return CM_OK;
+}
+
+int cm_set_crop(cm_handle_t h, int n_pass, const cm_pass_t* passes) {
+  if (!h) return CM_E_INVALID;
+  std::lock_guard<std::mutex> lk(h->mu);
+  if (n_pass < 0 || n_pass > CM_MAX_PASSES || (n_pass > 0 && !passes)) return fail(h, CM_E_INVALID, "0..%d passes", CM_MAX_PASSES);
+  for (int k = 0; k < n_pass; ++k)
+    if (passes[k].axis < 0 || passes[k].axis > 3) return fail(h, CM_E_INVALID, "pass %d: axis must be 0..3", k);
+  h->crop.n_pass = n_pass;
+  for (int k = 0; k < n_pass; ++k) h->crop.pass[k] = PassDev{passes[k].axis, passes[k].lo, passes[k].hi, passes[k].negative ? 1 : 0};
+  return CM_OK;
+}
+
+int cm_set_voxel(cm_handle_t h, const float* leaf3, int min_points, int downsample_all) {
+  if (!h || !leaf3) return CM_E_INVALID;
+  std::lock_guard<std::mutex> lk(h->mu);
+  for (int k = 0; k < 3; ++k)
+    if (!(leaf3[k] > 0.f) || !std::isfinite(leaf3[k])) return fail(h, CM_E_INVALID, "leaf size must be positive");
+  for (int k = 0; k < 3; ++k) {
+    h->leaf[k] = leaf3[k];
+    h->inv_leaf[k] = 1.0f / leaf3[k];  // PCL: inverse_leaf_size_ = Array4f::Ones() / leaf_size_.array()
+  }
+  h->min_points = min_points < 0 ? 0u : (uint32_t)min_points;
+  h->downsample_all = downsample_all ? 1u : 0u;
+  return CM_OK;
+}
+
+int cm_set_overflow_mode(cm_handle_t h, int mode) {
+  if (!h || (mode != 0 && mode != 1)) return CM_E_INVALID;
+  h->overflow_mode = mode;
+  return CM_OK;
+}
+
+int cm_set_profiling(cm_handle_t h, int on) {
+  if (!h) return CM_E_INVALID;
+  h->profiling = on != 0;
+  return CM_OK;
+}
+
+int cm_submit_cloud(cm_handle_t h, int sensor, const void* data, int64_t n_points, const cm_layout_t* layout, uint64_t stamp) {
+  return submit_impl(h, sensor, data, n_points, layout, stamp, false);
+}
+
+int cm_submit_cloud_pinned(cm_handle_t h, int sensor, const void* data, int64_t n_points, const cm_layout_t* layout,
+                           uint64_t stamp) {
+  return submit_impl(h, sensor, data, n_points, layout, stamp, true);
+}
+
+int cm_merge_frame_async(cm_handle_t h, uint64_t sensor_mask, int64_t* ticket) {
+  if (!h || !ticket) return CM_E_INVALID;
+  std::lock_guard<std::mutex> lk(h->mu);
+  CM_CUDA(h, cudaSetDevice(h->device));
+  return merge_async_impl(h, sensor_mask, ticket);
+}
+
+int cm_wait_frame(cm_handle_t h, int64_t ticket, cm_frame_out_t* out, uint64_t* out_used_mask, uint64_t* out_stamp) {
+  if (!h) return CM_E_INVALID;
+  std::lock_guard<std::mutex> lk(h->mu);
+  CM_CUDA(h, cudaSetDevice(h->device));
+  return wait_impl(h, ticket, out, out_used_mask, out_stamp);
+}
+
+int cm_merge_frame(cm_handle_t h, uint64_t sensor_mask, cm_frame_out_t* out, uint64_t* out_used_mask, uint64_t* out_stamp) {
+  if (!h) return CM_E_INVALID;
+  std::lock_guard<std::mutex> lk(h->mu);
+  CM_CUDA(h, cudaSetDevice(h->device));
+  int64_t ticket = 0;
+  int rc = merge_async_impl(h, sensor_mask, &ticket);
+  if (rc != CM_OK) return rc;
+  return wait_impl(h, ticket, out, out_used_mask, out_stamp);
+}
+
+int cm_host_alloc(void** p, size_t bytes) {
+  if (!p) return CM_E_INVALID;
+  return cudaMallocHost(p, bytes ? bytes : 1) == cudaSuccess ? CM_OK : CM_E_CUDA;
+}
+int cm_host_free(void* p) { return cudaFreeHost(p) == cudaSuccess ? CM_OK : CM_E_CUDA; }
+
+int cm_run_batch(cm_handle_t h, const cm_segment_t* segments, int n_segments, void* stream) {
+  if (!h) return CM_E_INVALID;
+  std::lock_guard<std::mutex> lk(h->mu);
+  CM_CUDA(h, cudaSetDevice(h->device));
+  int rc = ensure_batch_ws(h);
+  if (rc != CM_OK) return rc;
+  return run_pipeline(h, h->batch, segments, n_segments, static_cast<cudaStream_t>(stream), true);
+}
+
+int cm_dev_transform_crop(cm_handle_t h, const cm_segment_t* segments, int n_segments, void* stream) {
+  if (!h) return CM_E_INVALID;
+  std::lock_guard<std::mutex> lk(h->mu);
+  CM_CUDA(h, cudaSetDevice(h->device));
+  int rc = ensure_batch_ws(h);
+  if (rc != CM_OK) return rc;
+  return run_pipeline(h, h->batch, segments, n_segments, static_cast<cudaStream_t>(stream), false);
+}
+
+int cm_dev_voxelgrid(cm_handle_t h, const float* xyzi_dev, int64_t n_points, int is_dense, void* stream) {
+  (void)is_dense;  // non-finite points are skipped either way (PCL skips them when !is_dense; undefined otherwise)
+  if (!h) return CM_E_INVALID;
+  std::lock_guard<std::mutex> lk(h->mu);
+  CM_CUDA(h, cudaSetDevice(h->device));
+  int rc = ensure_batch_ws(h);
+  if (rc != CM_OK) return rc;
+  Workspace& w = h->batch;
+  if (n_points < 0 || n_points > (int64_t)w.cap_points) return fail(h, CM_E_CAPACITY, "%lld points > capacity %u", (long long)n_points, w.cap_points);
+  if (n_points > 0 && (!xyzi_dev || (reinterpret_cast<uintptr_t>(xyzi_dev) & 15u))) return fail(h, CM_E_INVALID, "xyzi_dev must be 16-byte aligned");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const uint32_t epoch = next_epoch(h);
+  w.has_run = true; w.report_valid = false; w.profiled = h->profiling;
+  w.n_frames = 1; w.n_segs = 0; w.points_in = n_points; w.launches = 0;
+  w.ran_k1 = false; w.ran_voxel = false; w.stream = st;
+  w.voxel_pts = reinterpret_cast<const float4*>(xyzi_dev);
+  h->last = &w;
+  CM_CUDA(h, cudaEventRecord(w.ev[EV_START], st));
+  CM_CUDA(h, cudaMemsetAsync(w.meta, 0, w.ml.zero_bytes, st));
+  VoxelParams vp;
+  fill_voxel_params(h, w, vp, w.voxel_pts, 1, (uint32_t)n_points, epoch);
+  CM_CUDA(h, launch_minmax(w.voxel_pts, (uint32_t)n_points, vp.ctrl, vp.acc, const_cast<uint32_t*>(vp.frame_surv_start), st));
+  ++w.launches;
+  CM_CUDA(h, cudaEventRecord(w.ev[EV_K1], st));
+  return run_voxel(h, w, vp, st);
+}
+
+int cm_sync(cm_handle_t h) {
+  if (!h) return CM_E_INVALID;
+  std::lock_guard<std::mutex> lk(h->mu);
+  CM_CUDA(h, cudaSetDevice(h->device));
+  if (!h->last) return fail(h, CM_E_INVALID, "nothing has run on this handle");
+  return fetch_report(h, *h->last);
+}
+
+int cm_get_stats(cm_handle_t h, cm_stats_t* out) {
+  if (!h || !out) return CM_E_INVALID;
+  int rc = cm_sync(h);
+  *out = h->stats;
+  return rc;
+}
+
+int cm_get_device_out(cm_handle_t h, cm_device_out_t* out) {
+  if (!h || !out) return CM_E_INVALID;
+  std::lock_guard<std::mutex> lk(h->mu);
+  if (!h->last || !h->last->has_run) return fail(h, CM_E_INVALID, "nothing has run on this handle");
+  Workspace& w = *h->last;
+  int rc = fetch_report(h, w);
+  memset(out, 0, sizeof(*out));
+  out->survivor_xyzi = reinterpret_cast<const float*>(w.voxel_pts);
+  out->survivor_src = w.ran_k1 ? w.surv_src : nullptr;
+  if (w.ran_voxel) {
+    const bool odd = (h->stats.sort_passes & 1) != 0;
+    out->sorted_key = odd ? w.keys_b : w.keys_a;
+    out->sorted_point = odd ? w.vals_b : w.vals_a;
+    out->voxel_xyzi = w.out_xyzi;
+    out->voxel_count = w.out_count;
+    out->voxel_idx = reinterpret_cast<const uint64_t*>(w.out_idx);
+    out->key_bytes = (int32_t)w.key_bytes;
+    const SortInfo* si = reinterpret_cast<const SortInfo*>(w.report + w.ml.off_info);
+    out->key_idx_bits = (int32_t)si->idx_bits;
+  }
+  return rc;
+}
+
+int cm_get_frame_info(cm_handle_t h, cm_frame_info_t* out, int capacity, int* n_frames) {
+  if (!h) return CM_E_INVALID;
+  int rc = cm_sync(h);
+  std::lock_guard<std::mutex> lk(h->mu);
+  const int n = (int)h->frame_info.size();
+  if (n_frames) *n_frames = n;
+  if (out) {
+    if (capacity < n) return fail(h, CM_E_CAPACITY, "capacity %d < %d frames", capacity, n);
+    for (int i = 0; i < n; ++i) out[i] = h->frame_info[i];
+  }
+  return rc;
+}
+
+int64_t cm_launch_count(cm_handle_t h) {
+  if (!h || !h->last) return 0;
+  return h->last->launches;
+}
+
+int cm_stage_ms(cm_handle_t h, const char* stage, float* ms) {
+  if (!h || !stage || !ms) return CM_E_INVALID;
+  int rc = cm_sync(h);
+  int which = -1;
+  if (!strcmp(stage, "total")) which = EV_START;
+  else if (!strcmp(stage, "transform_crop")) which = EV_K1;
+  else if (!strcmp(stage, "grid")) which = EV_GRID;
+  else if (!strcmp(stage, "key_hist")) which = EV_KEY;
+  else if (!strcmp(stage, "sort")) which = EV_SORT;
+  else if (!strcmp(stage, "centroid")) which = EV_CENT;
+  if (which < 0) return fail(h, CM_E_INVALID, "unknown stage '%s'", stage);
+  *ms = h->stage_ms[which];
+  return rc;
+}
+
+int cm_dev_alloc(cm_handle_t h, void** p, size_t bytes) {
+  if (!h || !p) return CM_E_INVALID;
+  CM_CUDA(h, cudaSetDevice(h->device));
+  CM_CUDA(h, cudaMalloc(p, bytes ? bytes : 16));
+  return CM_OK;
+}
+int cm_dev_free(cm_handle_t h, void* p) {
+  if (!h) return CM_E_INVALID;
+  CM_CUDA(h, cudaSetDevice(h->device));
+  CM_CUDA(h, cudaFree(p));
+  return CM_OK;
+}
+int cm_memcpy_h2d(cm_handle_t h, void* dst, const void* src, size_t bytes, void* stream) {
+  if (!h) return CM_E_INVALID;
+  CM_CUDA(h, cudaSetDevice(h->device));
+  CM_CUDA(h, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, static_cast<cudaStream_t>(stream)));
+  CM_CUDA(h, cudaStreamSynchronize(static_cast<cudaStream_t>(stream)));
+  return CM_OK;
+}
+int cm_memcpy_d2h(cm_handle_t h, void* dst, const void* src, size_t bytes, void* stream) {
+  if (!h) return CM_E_INVALID;
+  CM_CUDA(h, cudaSetDevice(h->device));
+  CM_CUDA(h, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, static_cast<cudaStream_t>(stream)));
+  CM_CUDA(h, cudaStreamSynchronize(static_cast<cudaStream_t>(stream)));
+  return CM_OK;
+}
+
+}  // extern "C"

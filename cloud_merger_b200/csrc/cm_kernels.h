@@ -1,0 +1,72 @@
+// cm_kernels.h -- launch interface between the C-ABI host layer (cm_api.cu) and the sm_100a kernels.
+#pragma once
+
+#include "cm_common.cuh"
+
+namespace cm {
+
+// ---- K1: fused unpack + transform + crop + stable compaction (cm_transform_crop.cu) ---------------------------------
+struct K1Params {
+  const SegDev* segs;
+  uint32_t n_seg;
+  uint32_t n_tiles;
+  uint32_t n_frames;
+  uint32_t epoch;
+  const float* mats;  // [sensor][12], row-major 3x4
+  CropDev crop;
+  float4* surv_xyzi;
+  uint32_t* surv_src;  // may be null
+  Ctrl* ctrl;
+  FrameAcc* acc;
+  uint32_t* frame_surv_start;  // [n_frames + 1]
+  uint32_t* seg_surv_start;    // [n_seg]
+  unsigned long long* lb;      // [n_tiles]
+};
+uint32_t k1_tile_points();
+cudaError_t launch_transform_crop(const K1Params& p, uint32_t staged_smem_bytes, cudaStream_t stream);
+
+// ---- VoxelGrid front/back ends (cm_voxel.cu) ---------------------------------------------------------------------
+struct VoxelParams {
+  const float4* pts;                 // survivors (packed xyzi)
+  const uint32_t* frame_surv_start;  // [n_frames + 1]; [n_frames] = number of points M
+  uint32_t n_frames;
+  uint32_t max_points;               // host-side upper bound of M (sizes the grids)
+  float inv_leaf[3];
+  uint32_t min_points;
+  uint32_t downsample_all;
+  uint32_t key_bytes;                // 4 or 8
+  uint32_t out_step;                 // 16 or 32
+  Ctrl* ctrl;
+  FrameAcc* acc;
+  GridDev* grid;                     // [n_frames]
+  SortInfo* info;
+  uint32_t* hist;                    // [CM_MAX_SORT_PASSES][256]
+  void* keys_a;                      // key buffers (ping-pong)
+  void* keys_b;
+  uint32_t* vals_a;
+  uint32_t* vals_b;
+  unsigned long long* lb_sort;       // [sort tiles][256]
+  unsigned long long* lb_cent;       // [centroid tiles]
+  uint32_t epoch;                    // epochs epoch+1 .. epoch+8 are used by the sort passes, epoch+9 by the centroid pass
+  uint32_t max_passes;               // how many pass launches the host enqueues
+  void* out_xyzi;
+  uint32_t* out_count;
+  unsigned long long* out_idx;
+};
+
+// bounding box of n packed points (used when VoxelGrid runs on a cloud that did not come out of K1)
+cudaError_t launch_minmax(const float4* pts, uint32_t n, Ctrl* ctrl, FrameAcc* acc, uint32_t* frame_surv_start,
+                          cudaStream_t stream);
+cudaError_t launch_grid_setup(const VoxelParams& p, cudaStream_t stream);
+cudaError_t launch_key_hist(const VoxelParams& p, cudaStream_t stream);
+cudaError_t launch_sort_pass(const VoxelParams& p, int pass, cudaStream_t stream);
+cudaError_t launch_centroid(const VoxelParams& p, cudaStream_t stream);
+
+uint32_t sort_tile_items(uint32_t key_bytes);
+uint32_t centroid_tile_items();
+
+// per-device one-time kernel attribute setup (opt-in shared memory sizes)
+cudaError_t configure_device_kernels();
+uint32_t k1_max_staged_smem();
+
+}  // namespace cm

@@ -1,0 +1,172 @@
+// cm_radix_sort.cu -- in-house onesweep LSD radix sort of (voxel key, point index) pairs for sm_100a.
+//
+// Replaces the std::sort(index_vector) at the heart of pcl::VoxelGrid::applyFilter (PCL 1.8.1 voxel_grid.hpp, reached
+// from the reference's voxelgrid(), pc_preprocessing_main.cpp:168-177). No CUB / Thrust.
+//
+// One launch per 8-bit digit. The digit histograms of all passes were produced up front by k_voxel_key_hist, so a pass
+// is a single sweep: each CTA takes a tile (dynamic id), ranks its keys by digit (warp match-any, stable), obtains for
+// each of the 256 digits the number of equal-digit keys in all earlier tiles with a decoupled look-back, and scatters
+// keys and values to their final place of this pass through shared memory so that global stores are digit-contiguous.
+// The number of passes is decided on the device (SortInfo.num_passes, from the significant key bits); a pass beyond it
+// returns immediately, and every kernel derives the ping-pong buffer it reads from the pass number.
+//
+// Roofline: HBM. Algorithmic bytes per pass = n * 2 * (key_bytes + 4), minus 4 n in pass 0 whose values are implicit.
+#include "cm_kernels.h"
+
+namespace cm {
+
+namespace {
+
+constexpr int RS_THREADS = 256;
+constexpr int RS_WARPS = RS_THREADS / 32;
+
+template <typename KeyT>
+struct SortCfg;
+template <>
+struct SortCfg<uint32_t> {
+  static constexpr int IPT = 16;
+};
+template <>
+struct SortCfg<unsigned long long> {
+  static constexpr int IPT = 12;
+};
+
+template <typename KeyT>
+__global__ void __launch_bounds__(RS_THREADS) k_onesweep_pass(const VoxelParams p, const int pass) {
+  constexpr int IPT = SortCfg<KeyT>::IPT;
+  constexpr int TILE = RS_THREADS * IPT;
+  constexpr int WARP_ITEMS = 32 * IPT;
+
+  __shared__ uint32_t s_warp_hist[RS_WARPS][CM_RADIX + 1];  // [..][256] is the bin of out-of-range items
+  __shared__ uint32_t s_bin_start[CM_RADIX];                 // first position of digit d inside the sorted tile
+  __shared__ uint32_t s_scatter[CM_RADIX];                   // global position of sorted-tile position 0 of digit d, minus s_bin_start
+  __shared__ uint32_t s_scan[9];
+  __shared__ uint32_t s_tile;
+  __shared__ __align__(16) KeyT s_keys[TILE];
+  __shared__ uint32_t s_vals[TILE];
+
+  const SortInfo si = *p.info;
+  if ((uint32_t)pass >= si.num_passes) return;
+  const uint32_t M = si.n_keys;
+  const uint32_t n_tiles = (M + TILE - 1) / TILE;
+
+  const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+  if (tid == 0) s_tile = atomicAdd(&p.ctrl->tile_counter[1 + pass], 1u);
+  for (uint32_t i = tid; i < RS_WARPS * (CM_RADIX + 1); i += RS_THREADS) (&s_warp_hist[0][0])[i] = 0;
+  __syncthreads();
+  const uint32_t tile = s_tile;
+  if (tile >= n_tiles) return;
+
+  const bool odd = (pass & 1) != 0;
+  const KeyT* __restrict__ in_keys = reinterpret_cast<const KeyT*>(odd ? p.keys_b : p.keys_a);
+  KeyT* __restrict__ out_keys = reinterpret_cast<KeyT*>(odd ? p.keys_a : p.keys_b);
+  const uint32_t* __restrict__ in_vals = odd ? p.vals_b : p.vals_a;
+  uint32_t* __restrict__ out_vals = odd ? p.vals_a : p.vals_b;
+  const uint32_t shift = (uint32_t)pass * CM_RADIX_BITS;
+
+  const uint32_t tile_base = tile * TILE;
+  const uint32_t n_here = min((uint32_t)TILE, M - tile_base);
+  const uint32_t item0 = warp * WARP_ITEMS + lane;  // tile-local index of item 0 of this thread; item i = item0 + 32 i
+
+  // ---- load keys (warp-striped, coalesced) -----------------------------------------------------------------------
+  KeyT key[IPT];
+#pragma unroll
+  for (int i = 0; i < IPT; ++i) {
+    const uint32_t li = item0 + 32 * i;
+    key[i] = (li < n_here) ? in_keys[tile_base + li] : (KeyT)0;
+  }
+
+  // ---- stable rank of every key among the keys of its digit inside the warp -----------------------------------------
+  uint32_t rank[IPT];
+#pragma unroll
+  for (int i = 0; i < IPT; ++i) {
+    const uint32_t li = item0 + 32 * i;
+    const uint32_t d = (li < n_here) ? ((uint32_t)(key[i] >> shift) & (CM_RADIX - 1)) : (uint32_t)CM_RADIX;
+    const uint32_t peers = __match_any_sync(0xFFFFFFFFu, d);
+    const int leader = __ffs(peers) - 1;
+    uint32_t prev = 0;
+    if ((int)lane == leader) {
+      prev = s_warp_hist[warp][d];
+      s_warp_hist[warp][d] = prev + (uint32_t)__popc(peers);
+    }
+    prev = __shfl_sync(0xFFFFFFFFu, prev, leader);
+    rank[i] = prev + (uint32_t)__popc(peers & lanemask_lt());
+    __syncwarp();
+  }
+  __syncthreads();
+
+  // ---- per digit: prefix over warps, tile count, position in the sorted tile, global base, look-back ------------------
+  uint32_t cnt = 0;
+  if (tid < CM_RADIX) {
+#pragma unroll
+    for (int w = 0; w < RS_WARPS; ++w) {
+      const uint32_t t = s_warp_hist[w][tid];
+      s_warp_hist[w][tid] = cnt;
+      cnt += t;
+    }
+  }
+  uint32_t tot;
+  const uint32_t bin_start = block_excl_scan_256(cnt, s_scan, &tot);
+  const uint32_t gcount = (tid < CM_RADIX) ? p.hist[pass * CM_RADIX + tid] : 0u;
+  const uint32_t gbase = block_excl_scan_256(gcount, s_scan, &tot);
+  if (tid < CM_RADIX) {
+    const uint32_t before = lb_exclusive_digit(p.lb_sort, tile, tid, cnt, p.epoch + 1u + (uint32_t)pass, &p.ctrl->error);
+    s_bin_start[tid] = bin_start;
+    s_scatter[tid] = gbase + before - bin_start;  // modulo 2^32
+  }
+  __syncthreads();
+
+  // ---- keys into sorted-tile order in shared memory -----------------------------------------------------------------
+#pragma unroll
+  for (int i = 0; i < IPT; ++i) {
+    const uint32_t li = item0 + 32 * i;
+    if (li < n_here) {
+      const uint32_t d = (uint32_t)(key[i] >> shift) & (CM_RADIX - 1);
+      const uint32_t pos = s_bin_start[d] + s_warp_hist[warp][d] + rank[i];
+      rank[i] = pos;
+      s_keys[pos] = key[i];
+    }
+  }
+  // values travel the same way (pass 0: the value is the key's own position)
+#pragma unroll
+  for (int i = 0; i < IPT; ++i) {
+    const uint32_t li = item0 + 32 * i;
+    if (li < n_here) {
+      const uint32_t v = (pass == 0) ? (tile_base + li) : in_vals[tile_base + li];
+      s_vals[rank[i]] = v;
+    }
+  }
+  __syncthreads();
+
+  // ---- scatter: consecutive threads write consecutive addresses inside each digit's run ------------------------------
+#pragma unroll
+  for (int j = 0; j < IPT; ++j) {
+    const uint32_t pos = j * RS_THREADS + tid;
+    if (pos < n_here) {
+      const KeyT kk = s_keys[pos];
+      const uint32_t d = (uint32_t)(kk >> shift) & (CM_RADIX - 1);
+      const uint32_t dst = s_scatter[d] + pos;
+      out_keys[dst] = kk;
+      out_vals[dst] = s_vals[pos];
+    }
+  }
+}
+
+}  // namespace
+
+uint32_t sort_tile_items(uint32_t key_bytes) {
+  return key_bytes == 4 ? RS_THREADS * SortCfg<uint32_t>::IPT : RS_THREADS * SortCfg<unsigned long long>::IPT;
+}
+
+cudaError_t launch_sort_pass(const VoxelParams& p, int pass, cudaStream_t stream) {
+  const uint32_t tile = sort_tile_items(p.key_bytes);
+  const uint32_t tiles = (p.max_points + tile - 1) / tile;
+  if (tiles == 0) return cudaSuccess;
+  if (p.key_bytes == 4)
+    k_onesweep_pass<uint32_t><<<tiles, RS_THREADS, 0, stream>>>(p, pass);
+  else
+    k_onesweep_pass<unsigned long long><<<tiles, RS_THREADS, 0, stream>>>(p, pass);
+  return cudaGetLastError();
+}
+
+}  // namespace cm

@@ -1,0 +1,235 @@
+/*
+ * cloud_merger_gpu.h -- C ABI of the B200-native merge hot path of cloud_merger
+ * (per-sensor extrinsic transform -> concat -> PassThrough crop -> VoxelGrid).
+ *
+ * This is the drop-in boundary: plain pointers and sizes, no PCL / Eigen / ROS / torch types. Each entry point names
+ * the reference interface it replaces (paths relative to the reference repository timspilak/cloud_merger). The
+ * reference-side binding a maintainer adds is shown in INTEGRATION.md and implemented, header-only, in
+ * include/cloud_merger_shim.hpp (exact reference signatures: getROI, getCloudPart, fusePointclouds, voxelgrid,
+ * transformPointCloud).
+ *
+ * There is no CPU fallback: every compute entry point needs a CUDA device of compute capability 10.0 (B200) and
+ * returns CM_E_CUDA / CM_E_NO_DEVICE otherwise.
+ *
+ * Threading: cm_submit_cloud is safe to call concurrently for DISTINCT sensor ids of one handle (the reference runs
+ * its six sensor callbacks on ros::AsyncSpinner(6), pc_preprocessing_main.cpp:513); cm_merge_frame* may be called
+ * from another thread. One handle per GPU.
+ */
+#ifndef CLOUD_MERGER_GPU_H_
+#define CLOUD_MERGER_GPU_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(_WIN32)
+#define CM_API
+#else
+#define CM_API __attribute__((visibility("default")))
+#endif
+
+typedef struct cm_handle_s* cm_handle_t;
+
+/* ---- status codes (the reference functions are void and PCL only warns; every call here returns a code) ---- */
+enum {
+  CM_OK = 0,
+  CM_E_INVALID = 1,     /* bad argument */
+  CM_E_CAPACITY = 2,    /* a caller buffer or the handle's configured capacity is too small */
+  CM_E_CUDA = 3,        /* CUDA runtime error; cm_last_error(h) has the text */
+  CM_E_NO_DEVICE = 4,   /* no CUDA device / not sm_100 */
+  CM_E_KEY_RANGE = 5,   /* voxel grid too large for the 64-bit key (more than 2^21 cells on an axis per frame) */
+  CM_E_INTERNAL = 6,    /* device-side watchdog tripped (look-back did not make progress) */
+  CM_E_NOT_READY = 7    /* no cloud submitted for a sensor named in the mask */
+};
+
+/* ---- limits ---- */
+#define CM_MAX_PASSES 8
+#define CM_MAX_SENSORS 64
+#define CM_NO_FIELD (-1)
+
+/* ---- crop: one pcl::PassThrough stage ----
+ * Replaces: pcl::PassThrough<pcl::PointXYZI> as configured in getROI (pc_preprocessing_main.cpp:20-40), getCloudPart
+ * (:49-59), the z windows of removeGround (:80-92), filter_ROI_R (CloudFusionNode.h:145-190), remove_ground
+ * (CloudFusionNode.h:201-216). Limits are float (PCL 1.8.1 setFilterLimits(const float&, const float&)); the window is
+ * inclusive; points with a non-finite x, y, z or field value are always removed; negative keeps the outside. Chained
+ * passes AND together. With zero passes nothing is removed (the plain cloud_fusion concat, CloudFusionNode.h:59-72). */
+typedef struct {
+  int32_t axis; /* 0 = "x", 1 = "y", 2 = "z", 3 = "intensity" */
+  float lo;
+  float hi;
+  int32_t negative;
+} cm_pass_t;
+
+/* ---- layout of one incoming sensor cloud ----
+ * Replaces: the sensor_msgs/PointCloud2 -> pcl::PointCloud<pcl::PointXYZI> deserialisation done by the pcl_ros
+ * subscriber (pc_preprocessing_main.cpp:520-525, CloudFusionNode.h:51-56): data[], point_step and the byte offsets of the
+ * FLOAT32 fields "x", "y", "z", "intensity". pcl::PointXYZI itself is {32, 0, 4, 8, 16}; packed xyzi is {16, 0, 4, 8, 12}. */
+typedef struct {
+  int32_t point_step;
+  int32_t off_x, off_y, off_z;
+  int32_t off_intensity; /* CM_NO_FIELD: no intensity, read as 0 */
+  int32_t is_dense;      /* PointCloud2.is_dense: 0 = non-finite points may be present and are left untransformed */
+} cm_layout_t;
+
+/* ---- one segment of a device-resident batch: one sensor cloud of one frame ---- */
+typedef struct {
+  const void* data;   /* DEVICE pointer, 16-byte aligned */
+  int64_t n_points;
+  cm_layout_t layout;
+  int32_t sensor;     /* which extrinsic (cm_set_extrinsic) applies */
+  int32_t frame;      /* 0-based frame number inside the batch; segments must be ordered by frame, then concat order */
+} cm_segment_t;
+
+/* ---- creation-time configuration ---- */
+typedef struct {
+  int32_t device;                 /* CUDA device ordinal */
+  int32_t max_sensors;            /* sensors per frame (<= CM_MAX_SENSORS) */
+  int64_t max_points_per_sensor;  /* capacity of one submitted cloud (host path) */
+  int32_t max_point_step;         /* largest point_step the host path will see (bytes) */
+  int32_t frames_in_flight;       /* host-path pipeline depth: 1..8 */
+  int64_t max_batch_points;       /* capacity (points) of one device-resident batch; 0 = max_sensors*max_points_per_sensor */
+  int32_t max_batch_frames;       /* frames per device-resident batch (>= 1) */
+  int32_t max_batch_segments;     /* segments per batch; 0 = max_batch_frames*max_sensors */
+  int32_t out_point_step;         /* 16 = packed float4 xyzi; 32 = pcl::PointXYZI record (pad@12 = 1.0f) so pcl::toROSMsg is a memcpy */
+  int32_t reserved;
+} cm_config_t;
+
+/* ---- per-run statistics (metrics the reference only prints via ROS_INFO) ---- */
+typedef struct {
+  int64_t points_in;       /* points submitted */
+  int64_t survivors;       /* points after the crop */
+  int64_t voxels_out;      /* voxels emitted */
+  int32_t frames;          /* frames in the run */
+  int32_t key_bits;        /* significant voxel-key bits that were sorted */
+  int32_t sort_passes;     /* radix passes executed */
+  int32_t key_bytes;       /* 4 or 8 */
+  int32_t pcl_overflow;    /* number of frames for which PCL 1.8.1 would refuse ("Leaf size is too small") */
+  int32_t device_error;    /* 0 or a CM_E_* raised on the device */
+  float gpu_ms;            /* device time of the run between its first and last kernel (CUDA events) */
+  float reserved;
+} cm_stats_t;
+
+/* ---- per-frame results of a batch (device arrays are indexed by these) ---- */
+typedef struct {
+  int64_t survivor_begin, survivor_end; /* this frame's slice of the merged, cropped cloud */
+  int64_t voxel_begin, voxel_end;       /* this frame's slice of the voxel output */
+  int32_t min_b[3], max_b[3], div_b[3]; /* pcl::VoxelGrid getMinBoxCoordinates / getMaxBoxCoordinates / getNrDivisions */
+  int32_t pcl_overflow;                 /* 1: PCL 1.8.1 would have returned the input unchanged for this frame */
+} cm_frame_info_t;
+
+/* ---- device-resident outputs of the last batch run on a handle (valid until the next run) ---- */
+typedef struct {
+  const float* survivor_xyzi;    /* [survivors][4] merged + cropped cloud, transform applied (concat order) */
+  const uint32_t* survivor_src;  /* [survivors] index of each survivor in its frame's un-cropped concatenation */
+  const void* sorted_key;        /* [survivors] voxel keys ascending (uint32 or uint64, see key_bytes) */
+  const uint32_t* sorted_point;  /* [survivors] survivor index belonging to sorted_key[i] (voxel membership) */
+  const void* voxel_xyzi;        /* [voxels] centroids, out_point_step bytes each */
+  const uint32_t* voxel_count;   /* [voxels] points per voxel */
+  const uint64_t* voxel_idx;     /* [voxels] PCL's voxel index idx = i + j*div_x + k*div_x*div_y (64-bit) */
+  int32_t key_bytes;
+  int32_t key_idx_bits;          /* key = (frame << key_idx_bits) | idx */
+} cm_device_out_t;
+
+/* ---- host-side result of one merged frame ---- */
+typedef struct {
+  /* caller buffers (any may be NULL to skip that output) and their capacities in elements */
+  void* voxel_xyzi;        int64_t voxel_capacity;     /* out_point_step bytes per voxel */
+  uint32_t* voxel_count;
+  uint64_t* voxel_idx;
+  float* survivor_xyzi;    int64_t survivor_capacity;  /* [survivors][4] the merged cropped cloud (== /points_no_ground input of voxelgrid) */
+  uint32_t* survivor_src;
+  /* filled by the call */
+  int64_t n_voxels;
+  int64_t n_survivors;
+  cm_frame_info_t info;
+} cm_frame_out_t;
+
+/* ---- lifecycle ---- */
+CM_API int cm_create(const cm_config_t* cfg, cm_handle_t* out);
+CM_API int cm_destroy(cm_handle_t h);
+CM_API const char* cm_strerror(int code);
+CM_API const char* cm_last_error(cm_handle_t h);
+CM_API const char* cm_version(void);
+CM_API int cm_device_count(void);
+
+/* ---- configuration ----
+ * cm_set_extrinsic replaces the tf::Transform -> Eigen::Affine3f argument of pcl_ros::transformPointCloud
+ * (pc_preprocessing_main.cpp:320-322 and the five other callbacks; CloudFusionNode.h:506-534). m is a 4x4 float matrix;
+ * col_major != 0 reads Eigen::Matrix4f::data() order. Only rows 0..2 are used (rigid / affine transform).
+ * cm_set_extrinsic_tf builds it the way pcl_ros does from a tf::Transform: double quaternion (x, y, z, w) + origin,
+ * narrowed to float, Eigen 3.3 toRotationMatrix. */
+CM_API int cm_set_extrinsic(cm_handle_t h, int sensor, const float* m16, int col_major);
+CM_API int cm_set_extrinsic_tf(cm_handle_t h, int sensor, const double* quat_xyzw, const double* origin_xyz);
+CM_API int cm_get_extrinsic(cm_handle_t h, int sensor, float* m12_row_major);
+/* cm_set_crop replaces the PassThrough chains (see cm_pass_t). Defaults = getROI with Parameter.h:31-35. */
+CM_API int cm_set_crop(cm_handle_t h, int n_pass, const cm_pass_t* passes);
+/* cm_set_voxel replaces voxel_grid.setLeafSize / setDownsampleAllData / setMinimumPointsNumberPerVoxel
+ * (pc_preprocessing_main.cpp:171-175). Defaults: leaf 0.1, min_points 2, downsample_all 1 (Parameter.h:27-28). */
+CM_API int cm_set_voxel(cm_handle_t h, const float* leaf3, int min_points, int downsample_all);
+/* PCL 1.8.1 returns the input cloud unchanged when dx*dy*dz > INT32_MAX. mode 0 (default): keep going with the 64-bit
+ * key and report it in cm_frame_info_t.pcl_overflow; mode 1: behave like PCL (the frame's output is its cropped cloud). */
+CM_API int cm_set_overflow_mode(cm_handle_t h, int mode);
+
+/* ---- host path: one frame at a time, callable from the ROS callbacks ----
+ * cm_submit_cloud replaces the body of callbackFrontRight .. callbackFrontMiddle up to the hand-off into the globals
+ * (pc_preprocessing_main.cpp:318-337 ...) and add_*_velodyne (CloudFusionNode.h:506-534): it takes the raw point records,
+ * copies them to the device asynchronously and returns; latest submission per sensor wins (subscriber queue size 0/1 +
+ * flag gate, :330). stamp feeds operator+='s "newest stamp" rule. */
+CM_API int cm_submit_cloud(cm_handle_t h, int sensor, const void* data, int64_t n_points, const cm_layout_t* layout,
+                           uint64_t stamp);
+/* Same, for a caller buffer that is page-locked (cm_host_alloc / cudaHostRegister) and stays untouched until the frame it
+ * belongs to has been waited for: the copy goes straight from the caller's memory, with no staging memcpy. */
+CM_API int cm_submit_cloud_pinned(cm_handle_t h, int sensor, const void* data, int64_t n_points,
+                                  const cm_layout_t* layout, uint64_t stamp);
+/* cm_merge_frame replaces fusePointclouds + voxelgrid (pc_preprocessing_main.cpp:131-177, main loop :574-578):
+ * merges the latest cloud of every sensor in sensor_mask (bit s = sensor s, concat order = ascending sensor id),
+ * crops, voxel-filters and copies the results into the caller's buffers. Blocks until the results are on the host.
+ * Sensors in the mask that have nothing submitted are skipped (the reference's optional top sensor, :134-136);
+ * *out_used_mask (may be NULL) receives the sensors actually merged. The merged clouds are consumed (flags reset). */
+CM_API int cm_merge_frame(cm_handle_t h, uint64_t sensor_mask, cm_frame_out_t* out, uint64_t* out_used_mask,
+                          uint64_t* out_stamp);
+/* Pipelined form: cm_merge_frame_async enqueues the work and returns a ticket; cm_wait_frame blocks on that ticket and
+ * copies out. Up to frames_in_flight tickets may be outstanding. */
+CM_API int cm_merge_frame_async(cm_handle_t h, uint64_t sensor_mask, int64_t* ticket);
+CM_API int cm_wait_frame(cm_handle_t h, int64_t ticket, cm_frame_out_t* out, uint64_t* out_used_mask,
+                         uint64_t* out_stamp);
+/* Pinned host memory for callers that want true asynchronous H2D/D2H (e.g. the ROS message buffers). */
+CM_API int cm_host_alloc(void** p, size_t bytes);
+CM_API int cm_host_free(void* p);
+
+/* ---- device path: a batch of frames whose raw clouds already sit in device memory ----
+ * One call runs the whole path for every frame of the batch (F frames x S sensors = n_segments segments) with a fixed
+ * number of kernel launches; stream is a cudaStream_t (NULL = legacy default stream). Results stay on the device
+ * (cm_get_device_out) with per-frame slices in cm_get_frame_info. */
+CM_API int cm_run_batch(cm_handle_t h, const cm_segment_t* segments, int n_segments, void* stream);
+/* Stage-level entry points on device pointers (benchmarks, tests, and the building blocks of the shim):
+ *  cm_dev_transform_crop: the fused unpack + transform + crop + stable compaction only
+ *      (== transformPointCloud + getROI + operator+=); results in cm_get_device_out().survivor_*.
+ *  cm_dev_voxelgrid: VoxelGrid only on n packed float4 xyzi points already on the device (== voxelgrid()). */
+CM_API int cm_dev_transform_crop(cm_handle_t h, const cm_segment_t* segments, int n_segments, void* stream);
+CM_API int cm_dev_voxelgrid(cm_handle_t h, const float* xyzi_dev, int64_t n_points, int is_dense, void* stream);
+/* Blocks until the last run on the handle finished, then reports. */
+CM_API int cm_sync(cm_handle_t h);
+CM_API int cm_get_stats(cm_handle_t h, cm_stats_t* out);
+CM_API int cm_get_device_out(cm_handle_t h, cm_device_out_t* out);
+CM_API int cm_get_frame_info(cm_handle_t h, cm_frame_info_t* out, int capacity, int* n_frames);
+/* Number of kernel launches the last run enqueued (the caller's "gpu_launches" evidence). */
+CM_API int64_t cm_launch_count(cm_handle_t h);
+/* Device time (ms) of one named stage of the last run, measured with CUDA events on the run's stream:
+ * "transform_crop", "grid", "key_hist", "sort", "centroid", "total". Needs cm_set_profiling(h, 1). */
+CM_API int cm_set_profiling(cm_handle_t h, int on);
+CM_API int cm_stage_ms(cm_handle_t h, const char* stage, float* ms);
+
+/* ---- small device-memory helpers so that non-CUDA callers (ctypes, cgo, JNI) can stage data ---- */
+CM_API int cm_dev_alloc(cm_handle_t h, void** p, size_t bytes);
+CM_API int cm_dev_free(cm_handle_t h, void* p);
+CM_API int cm_memcpy_h2d(cm_handle_t h, void* dst_dev, const void* src_host, size_t bytes, void* stream);
+CM_API int cm_memcpy_d2h(cm_handle_t h, void* dst_host, const void* src_dev, size_t bytes, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CLOUD_MERGER_GPU_H_ */

@@ -1,0 +1,208 @@
+"""CPU tests of the oracle (not gpu): the C++ restatement (oracle/cm_oracle.cpp) against the hand-computed known-answer
+vector, against the independent numpy restatement (oracle/np_oracle.py), and against the properties the PCL 1.8.1
+algorithms guarantee. The reference ships no golden vectors of its own (parity unpinned)."""
+import numpy as np
+import pytest
+
+from cloud_merger_b200 import synth
+from oracle import np_oracle as npo
+
+from helpers import assert_bit_equal, assert_centroids_close, cloud_dict, known_answer
+
+
+def _ka_clouds(ka):
+    mA = np.array(ka["extrinsics_row_major_3x4"]["A"], np.float32)
+    mB = np.array(ka["extrinsics_row_major_3x4"]["B"], np.float32)
+    return [cloud_dict(ka["A"], mA, ka["sensor_A_is_dense"]), cloud_dict(ka["B"], mB, ka["sensor_B_is_dense"])]
+
+
+@pytest.mark.parametrize("min_points", [1, 2])
+def test_known_answer_cpp(oracle, min_points):
+    ka = known_answer()
+    e = ka["expected"]
+    r = oracle.merge_frame(_ka_clouds(ka), [tuple(p) for p in ka["crop_passes"]], ka["leaf"], min_points, True, False)
+    assert r["survivor_src"].tolist() == e["survivor_src"]
+    assert_bit_equal(r["survivor_xyzi"][:, :3], np.array(e["survivor_xyz"], np.float32), "survivor xyz")
+    assert r["min_b"].tolist() == e["min_b"] and r["max_b"].tolist() == e["max_b"] and r["div_b"].tolist() == e["div_b"]
+    assert r["point_idx"].tolist() == e["point_idx"]
+    ex = e["min_points_%d" % min_points]
+    assert r["idx"].tolist() == ex["idx"] and r["count"].tolist() == ex["count"]
+    assert_bit_equal(r["centroid"], np.array(ex["centroid"], np.float32), "centroid")
+    assert not r["pcl_overflow"]
+
+
+@pytest.mark.parametrize("min_points", [1, 2])
+def test_known_answer_numpy(min_points):
+    ka = known_answer()
+    e = ka["expected"]
+    r = npo.merge_frame(_ka_clouds(ka), [tuple(p) for p in ka["crop_passes"]], ka["leaf"], min_points, True, False)
+    assert r["survivor_src"].tolist() == e["survivor_src"]
+    assert_bit_equal(r["survivor_xyzi"][:, :3], np.array(e["survivor_xyz"], np.float32), "survivor xyz")
+    v = r["voxel"]
+    assert v["min_b"].tolist() == e["min_b"] and v["div_b"].tolist() == e["div_b"]
+    ex = e["min_points_%d" % min_points]
+    assert v["idx"].tolist() == ex["idx"] and v["count"].tolist() == ex["count"]
+    np.testing.assert_allclose(v["centroid_f64"], np.array(ex["centroid"], np.float64), rtol=1e-6)
+
+
+def test_inclusive_bounds_and_nan(oracle):
+    """PassThrough keeps v == lo and v == hi, drops NaN/Inf in x|y|z or the field, keeps order; negative flips."""
+    p = np.array([[0, 0, -0.5, 1], [0, 0, 3.0, 2], [0, 0, np.nextafter(np.float32(3.0), np.float32(4)), 3],
+                  [np.nan, 0, 1, 4], [0, np.inf, 1, 5], [0, 0, np.nan, 6], [0, 0, 1.0, 7],
+                  [0, 0, np.nextafter(np.float32(-0.5), np.float32(-1)), 8]], np.float32)
+    assert oracle.passthrough(p, 2, -0.5, 3.0).tolist() == [0, 1, 6]
+    assert oracle.passthrough(p, 2, -0.5, 3.0, True).tolist() == [2, 7]
+    assert np.nonzero(npo.passthrough_mask(p, 2, -0.5, 3.0))[0].tolist() == [0, 1, 6]
+    assert np.nonzero(npo.passthrough_mask(p, 2, -0.5, 3.0, True))[0].tolist() == [2, 7]
+    # intensity as the filter field
+    assert oracle.passthrough(p, 3, 2, 6).tolist() == [1, 2]
+
+
+def test_transform_is_unfused(oracle):
+    """x' = ((m00*x + m01*y) + m02*z) + m03 with separately rounded products: a fused multiply-add gives another result
+    for these operands, so this pins the no-FMA contract (reference built with -std=c++14 only, no -march)."""
+    m = np.array([1.0000001, 3.0000002, 5.0000005, 0.1, 0.9999999, 1.0000002, 0.3333333, 7, 1e-3, 1e3, 0.1, -2], np.float32)
+    rng = np.random.default_rng(7)
+    p = rng.uniform(-100, 100, size=(4096, 4)).astype(np.float32)
+    a = oracle.transform(p, m)
+    b = npo.transform(p, m)
+    assert_bit_equal(a, b, "cpp vs numpy transform")
+    x, y, z = (p[:, k].astype(np.float64) for k in range(3))
+    m64 = m.astype(np.float64)
+    exact = np.float32(m64[0] * x + m64[1] * y + m64[2] * z + m64[3])  # what a fully fused evaluation approaches
+    assert (a[:, 0] != exact).any(), "the unfused chain must differ from the exactly rounded sum somewhere"
+    # non-dense clouds keep non-finite points untouched; dense clouds transform everything
+    q = p.copy(); q[5, 0] = np.nan; q[9, 2] = np.inf
+    nd = oracle.transform(q, m, is_dense=False)
+    assert_bit_equal(nd[[5, 9]], q[[5, 9]], "non-dense keeps invalid points")
+    assert_bit_equal(nd[:5], a[:5], "finite points unchanged by the flag")
+
+
+@pytest.mark.parametrize("layout", [(16, 0, 4, 8, 12), (32, 0, 4, 8, 16), (22, 0, 4, 8, 12), (18, 0, 4, 8, 12),
+                                    (48, 8, 12, 16, 36), (20, 4, 8, 12, -1), (19, 3, 7, 11, 15)])
+def test_unpack_layouts(oracle, layout):
+    step, ox, oy, oz, oi = layout
+    rng = np.random.default_rng(3)
+    p = rng.normal(size=(1000, 4)).astype(np.float32)
+    data = synth.pack_cloud(p, step, ox, oy, oz, oi)
+    a = oracle.unpack(data, len(p), step, ox, oy, oz, oi)
+    b = npo.unpack(data, len(p), step, ox, oy, oz, oi)
+    want = p.copy()
+    if oi < 0:
+        want[:, 3] = 0
+    assert_bit_equal(a, want, "cpp unpack")
+    assert_bit_equal(b, want, "numpy unpack")
+
+
+@pytest.mark.parametrize("cfg,leaf,min_points", [("cfg1", 0.1, 2), ("cfg1", 0.1, 1), ("cfg2", 0.05, 2)])
+def test_cpp_vs_numpy_on_config_shapes(oracle, cfg, leaf, min_points):
+    """Both restatements, written independently, agree on the BASELINE shapes: survivors bit-exact, voxel membership,
+    counts and order exact, centroids within the 1e-5 contract (float vs double accumulation)."""
+    c = synth.CONFIGS[cfg]
+    clouds, mats = synth.frame_clouds(cfg, 1000 * int(cfg[-1]), 0)
+    cds = [cloud_dict(p, m[:3]) for p, m in zip(clouds, mats)]
+    a = oracle.merge_frame(cds, c["passes"], [leaf] * 3, min_points, True, True)
+    b = npo.merge_frame(cds, c["passes"], [leaf] * 3, min_points, True, True)
+    assert a["n_survivors"] == len(b["survivor_src"]) > 1000
+    assert (a["survivor_src"] == b["survivor_src"]).all()
+    assert_bit_equal(a["survivor_xyzi"], b["survivor_xyzi"], "survivors")
+    v = b["voxel"]
+    assert (a["idx"] == v["idx"]).all() and (a["count"] == v["count"]).all()
+    assert (a["point_idx"] == v["point_idx"]).all()
+    assert a["min_b"].tolist() == v["min_b"].tolist() and a["div_b"].tolist() == v["div_b"].tolist()
+    worst = assert_centroids_close(a["centroid"], v["centroid_f64"], "float(asc. index) vs numpy f64")
+    np.testing.assert_allclose(a["centroid_f64"], v["centroid_f64"], rtol=1e-12, atol=1e-12)
+    assert worst < 1e-5
+    assert a["count"].min() >= min_points
+
+
+def test_pcl_int32_and_64bit_formulations_agree(oracle):
+    """Inside PCL's domain the int32 formulation (force64=0) and the 64-bit extension give identical voxels."""
+    clouds, mats = synth.frame_clouds("cfg1", 1000, 1)
+    x = np.concatenate([oracle.transform(p, m[:3].reshape(-1)) for p, m in zip(clouds, mats)])
+    x = x[npo.crop(x, synth.ROI_BOX)]
+    a = oracle.voxelgrid(x, [0.1] * 3, 2, True, force64=False)
+    b = oracle.voxelgrid(x, [0.1] * 3, 2, True, force64=True)
+    assert not a["pcl_overflow"]
+    for k in ("idx", "count", "point_idx"):
+        assert (a[k] == b[k]).all(), k
+    assert_bit_equal(a["centroid"], b["centroid"], "centroid")
+    # std::sort order vs ascending index order: both inside the tolerance band of the double sum
+    assert_centroids_close(a["centroid_sort"], a["centroid_f64"], "std::sort order")
+    assert_centroids_close(a["centroid"], a["centroid_f64"], "ascending order")
+
+
+def test_pcl_overflow_guard(oracle):
+    """dx*dy*dz > INT32_MAX: PCL 1.8.1 warns and returns the input unchanged; the 64-bit extension carries on."""
+    x = synth.uniform_cloud(5, 20000, extent=(200.0, 200.0, 10.0))
+    a = oracle.voxelgrid(x, [0.02] * 3, 1, True, force64=False)
+    assert a["pcl_overflow"] and a["returned_input"] and a["n"] == len(x)
+    assert_bit_equal(a["centroid"], x, "output = input")
+    b = oracle.voxelgrid(x, [0.02] * 3, 1, True, force64=True)
+    assert b["pcl_overflow"] and not b["returned_input"]
+    n = npo.voxelgrid(x, [0.02] * 3, 1, True, True)
+    assert (b["idx"] == n["idx"]).all() and (b["count"] == n["count"]).all()
+    assert b["idx"].max() > 2**31
+    c = oracle.voxelgrid(x, [0.5] * 3, 1, True, force64=False)
+    assert not c["pcl_overflow"]
+
+
+def test_voxel_membership_is_permutation_invariant(oracle):
+    rng = np.random.default_rng(11)
+    x = synth.uniform_cloud(9, 50000, extent=(20.0, 20.0, 4.0))
+    perm = rng.permutation(len(x))
+    a = oracle.voxelgrid(x, [0.25] * 3, 2)
+    b = oracle.voxelgrid(x[perm], [0.25] * 3, 2)
+    assert (a["idx"] == b["idx"]).all() and (a["count"] == b["count"]).all()
+    assert (a["point_idx"][perm] == b["point_idx"]).all()
+    assert_centroids_close(b["centroid"], a["centroid_f64"], "permuted")
+
+
+def test_crop_commutes_with_concat(oracle):
+    """transform -> crop -> concat (reference order) == transform -> concat -> crop (north_star order)."""
+    clouds, mats = synth.frame_clouds("cfg1", 1000, 2, nan_frac=0.005)
+    tr = [oracle.transform(p, m[:3].reshape(-1), is_dense=False) for p, m in zip(clouds, mats)]
+    per = np.concatenate([t[npo.crop(t, synth.ROI_BOX)] for t in tr])
+    allc = np.concatenate(tr)
+    assert_bit_equal(per, allc[npo.crop(allc, synth.ROI_BOX)], "crop o concat")
+    cds = [cloud_dict(p, m[:3], is_dense=0) for p, m in zip(clouds, mats)]
+    r = oracle.merge_frame(cds, synth.ROI_BOX, [0.1] * 3, 2)
+    assert_bit_equal(r["survivor_xyzi"], per, "merge_frame survivors")
+    assert np.isfinite(r["survivor_xyzi"]).all()
+
+
+def test_min_points_filter_and_empty_inputs(oracle):
+    x = np.array([[0.01, 0.01, 0.01, 1], [0.02, 0.02, 0.02, 3], [5, 5, 5, 7]], np.float32)
+    a = oracle.voxelgrid(x, [0.1] * 3, 2)
+    assert a["n"] == 1 and a["count"].tolist() == [2]
+    assert_bit_equal(a["centroid"], np.array([[np.float32(0.03) / np.float32(2), np.float32(0.03) / np.float32(2),
+                                               np.float32(0.03) / np.float32(2), 2.0]], np.float32), "mean")
+    assert oracle.voxelgrid(x, [0.1] * 3, 0)["n"] == 2 and oracle.voxelgrid(x, [0.1] * 3, 4)["n"] == 0
+    assert oracle.voxelgrid(x, [0.1] * 3, 1, downsample_all=False)["centroid"][:, 3].tolist() == [0.0, 0.0]
+    e = oracle.voxelgrid(np.zeros((0, 4), np.float32), [0.1] * 3, 1)
+    assert e["n"] == 0
+    allnan = np.full((4, 4), np.nan, np.float32)
+    assert oracle.voxelgrid(allnan, [0.1] * 3, 1, is_dense=False)["n"] == 0
+    r = oracle.merge_frame([cloud_dict(np.zeros((0, 4), np.float32), np.eye(4)[:3])], synth.ROI_BOX, [0.1] * 3, 1)
+    assert r["n_survivors"] == 0 and r["n_voxels"] == 0
+
+
+def test_tf_to_matrix(oracle):
+    """Eigen 3.3 quaternion -> rotation as pcl_ros builds the Affine3f from the tf::Transform (host glue)."""
+    q = np.array([0.0, 0.0, np.sin(np.pi / 4), np.cos(np.pi / 4)])  # yaw +90 deg
+    m = oracle.tf_to_matrix(q, [0.0, 2.0, 0.0]).reshape(3, 4)
+    np.testing.assert_allclose(m, [[0, -1, 0, 0], [1, 0, 0, 2], [0, 0, 1, 0]], atol=1e-7)
+    rng = np.random.default_rng(5)
+    for _ in range(20):
+        qq = rng.normal(size=4); qq /= np.linalg.norm(qq)
+        t = rng.normal(size=3)
+        assert_bit_equal(oracle.tf_to_matrix(qq, t), npo.tf_to_matrix(qq, t), "tf matrix")
+
+
+def test_threads_do_not_change_results(oracle):
+    clouds, mats = synth.frame_clouds("cfg1", 1000, 3)
+    cds = [cloud_dict(p, m[:3]) for p, m in zip(clouds, mats)]
+    a = oracle.merge_frame(cds, synth.ROI_BOX, [0.1] * 3, 2, threads=1)
+    b = oracle.merge_frame(cds, synth.ROI_BOX, [0.1] * 3, 2, threads=6)
+    assert (a["idx"] == b["idx"]).all() and (a["survivor_src"] == b["survivor_src"]).all()
+    assert_bit_equal(a["centroid"], b["centroid"], "threads")
