@@ -214,6 +214,36 @@ class CloudMerger:
         res.raw_voxel_records = bufs["vx"][:v].copy()
         return res
 
+    def make_frame_buffers(self, capacity: int, want_survivors: bool = False, pinned: bool = True):
+        """Reusable (page-locked) result buffers for wait_frame_into(): no per-frame allocation on the hot path."""
+        step = self.out_point_step
+
+        def alloc(nbytes, dtype, shape):
+            if pinned:
+                raw, _ = host_alloc(nbytes)
+                return raw.view(dtype).reshape(shape)
+            return np.empty(shape, dtype)
+        cap = max(capacity, 1)
+        bufs = dict(vx=alloc(cap * step, np.float32, (cap, step // 4)), vc=alloc(cap * 4, np.uint32, (cap,)),
+                    vi=alloc(cap * 8, np.uint64, (cap,)))
+        out = CmFrameOut()
+        out.voxel_xyzi = bufs["vx"].ctypes.data
+        out.voxel_capacity = capacity
+        out.voxel_count = bufs["vc"].ctypes.data
+        out.voxel_idx = bufs["vi"].ctypes.data
+        if want_survivors:
+            bufs["sx"] = alloc(cap * 16, np.float32, (cap, 4))
+            bufs["ss"] = alloc(cap * 4, np.uint32, (cap,))
+            out.survivor_xyzi = bufs["sx"].ctypes.data
+            out.survivor_src = bufs["ss"].ctypes.data
+            out.survivor_capacity = capacity
+        return out, bufs
+
+    def wait_frame_into(self, ticket: int, out: CmFrameOut) -> CmFrameOut:
+        """cm_wait_frame into caller-owned buffers (see make_frame_buffers); returns `out` with the counts filled in."""
+        self._check(self._lib.cm_wait_frame(self._h, ticket, C.byref(out), None, None))
+        return out
+
     def wait_frame(self, ticket: int, capacity: int, want_survivors: bool = True) -> FrameResult:
         out, bufs = self._make_out(capacity, capacity, want_survivors)
         used, stamp = C.c_uint64(), C.c_uint64()

@@ -10,6 +10,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <limits>
 #include <mutex>
@@ -53,6 +54,8 @@ struct Workspace {
   uint8_t* report = nullptr;  // pinned host mirror of meta
   SegDev* segs = nullptr;
   std::vector<SegDev> segs_host;  // what is currently uploaded
+  uint32_t* tile_seg = nullptr;
+  std::vector<uint32_t> tile_seg_host;
   float4* surv_xyzi = nullptr;
   uint32_t* surv_src = nullptr;
   void *keys_a = nullptr, *keys_b = nullptr;
@@ -62,6 +65,9 @@ struct Workspace {
   void* out_xyzi = nullptr;
   uint32_t* out_count = nullptr;
   unsigned long long* out_idx = nullptr;
+  unsigned long long* trace_k1 = nullptr;    // debug traces (CM_TRACE=1): 8 stamps per tile
+  unsigned long long* trace_sort = nullptr;
+  size_t trace_k1_n = 0, trace_sort_n = 0;
   cudaEvent_t ev[EV_COUNT]{};
   // description of the last run
   bool has_run = false, report_valid = false, profiled = false;
@@ -103,7 +109,6 @@ struct cm_handle_s {
   std::string last_error;
   // configuration
   float mats_host[CM_MAX_SENSORS * 12];
-  float* mats_dev = nullptr;
   CropDev crop{};
   float leaf[3] = {0.1f, 0.1f, 0.1f};
   float inv_leaf[3] = {10.f, 10.f, 10.f};
@@ -153,10 +158,11 @@ cudaError_t dev_alloc(T** p, size_t count) {
 
 void ws_free(Workspace& w) {
   if (!w.ready) return;
-  cudaFree(w.meta); cudaFreeHost(w.report); cudaFree(w.segs); cudaFree(w.surv_xyzi); cudaFree(w.surv_src);
+  cudaFree(w.meta); cudaFreeHost(w.report); cudaFree(w.segs); cudaFree(w.tile_seg); cudaFree(w.surv_xyzi); cudaFree(w.surv_src);
   cudaFree(w.keys_a); cudaFree(w.keys_b); cudaFree(w.vals_a); cudaFree(w.vals_b);
   cudaFree(w.lb_k1); cudaFree(w.lb_sort); cudaFree(w.lb_cent);
   cudaFree(w.out_xyzi); cudaFree(w.out_count); cudaFree(w.out_idx);
+  cudaFree(w.trace_k1); cudaFree(w.trace_sort);
   for (auto& e : w.ev) if (e) cudaEventDestroy(e);
   w = Workspace();
 }
@@ -177,7 +183,8 @@ int ws_alloc(cm_handle_t h, Workspace& w, uint32_t points, uint32_t frames, uint
   CM_CUDA(h, dev_alloc(&w.vals_a, np));
   CM_CUDA(h, dev_alloc(&w.vals_b, np));
   // every segment owns at least one K1 tile
-  w.lb_k1_n = np / k1_tile_points() + segs + 2;
+  w.lb_k1_n = np / k1_min_tile_points() + segs + 2;
+  CM_CUDA(h, dev_alloc(&w.tile_seg, w.lb_k1_n));
   const uint32_t st = std::min(sort_tile_items(4), sort_tile_items(8));
   w.lb_sort_n = (np / st + 2) * CM_RADIX;
   w.lb_cent_n = np / centroid_tile_items() + 2;
@@ -191,6 +198,13 @@ int ws_alloc(cm_handle_t h, Workspace& w, uint32_t points, uint32_t frames, uint
   CM_CUDA(h, dev_alloc(&w.out_count, np));
   CM_CUDA(h, dev_alloc(&w.out_idx, np));
   for (auto& e : w.ev) CM_CUDA(h, cudaEventCreate(&e));
+  if (getenv("CM_TRACE")) {
+    w.trace_k1_n = w.lb_k1_n * 8; w.trace_sort_n = (w.lb_sort_n / CM_RADIX) * 8;
+    CM_CUDA(h, dev_alloc(&w.trace_k1, w.trace_k1_n));
+    CM_CUDA(h, dev_alloc(&w.trace_sort, w.trace_sort_n));
+    CM_CUDA(h, cudaMemset(w.trace_k1, 0, w.trace_k1_n * 8));
+    CM_CUDA(h, cudaMemset(w.trace_sort, 0, w.trace_sort_n * 8));
+  }
   w.ready = true;
   return CM_OK;
 }
@@ -284,6 +298,9 @@ void fill_voxel_params(cm_handle_t h, Workspace& w, VoxelParams& vp, const float
   vp.epoch = epoch;
   vp.max_passes = CM_MAX_SORT_PASSES;
   vp.out_xyzi = w.out_xyzi; vp.out_count = w.out_count; vp.out_idx = w.out_idx;
+  vp.trace = w.trace_sort;
+  const char* tp = getenv("CM_TRACE_PASS");
+  vp.trace_pass = tp ? (uint32_t)atoi(tp) : 1u;
 }
 
 // VoxelGrid stages on vp.pts. bounded: the crop box bounds the key width, so no device round trip is needed.
@@ -327,15 +344,36 @@ int run_voxel(cm_handle_t h, Workspace& w, VoxelParams& vp, cudaStream_t st) {
   return CM_OK;
 }
 
-// Build the device segment table for a batch; returns total points / frames / K1 tiles.
+// Derives the single-box form of the crop chain (see CropDev) whenever the chain allows it.
+void derive_crop_box(CropDev& c) {
+  const float fmax = std::numeric_limits<float>::max();
+  c.is_box = 0; c.use_i = 0;
+  for (int a = 0; a < 4; ++a) { c.lo[a] = -fmax; c.hi[a] = fmax; }
+  if (c.n_pass <= 0) return;
+  for (int k = 0; k < c.n_pass; ++k) {
+    const PassDev& ps = c.pass[k];
+    if (ps.negative || !(ps.lo == ps.lo) || !(ps.hi == ps.hi)) return;  // negative window or NaN limit: general chain
+    c.lo[ps.axis] = std::max(c.lo[ps.axis], ps.lo);
+    c.hi[ps.axis] = std::min(c.hi[ps.axis], ps.hi);
+    if (ps.axis == 3) c.use_i = 1;
+  }
+  c.is_box = 1;
+}
+
+struct SegPlan {
+  uint32_t n_frames = 0, n_tiles = 0, tile_points = 0, tiles_per_seg = 0, staged_smem = 0;
+  int mode = -1;
+  int64_t total_points = 0;
+};
+
+// Build the device segment table for a batch.
 int build_segments(cm_handle_t h, Workspace& w, const cm_segment_t* segs, int n_seg, std::vector<SegDev>& out,
-                   uint32_t* n_frames, uint32_t* n_tiles, int64_t* total_points, uint32_t* staged_smem) {
+                   std::vector<uint32_t>& tile_seg, SegPlan* plan) {
   if (n_seg <= 0 || !segs) return fail(h, CM_E_INVALID, "no segments");
   if ((uint32_t)n_seg > w.cap_segs) return fail(h, CM_E_CAPACITY, "%d segments > capacity %u", n_seg, w.cap_segs);
-  out.resize(n_seg);
-  const uint32_t T = k1_tile_points();
-  uint32_t tile = 0, frame = 0, src_base = 0, max_step_staged = 0;
   int64_t total = 0;
+  uint32_t max_step_staged = 0;
+  int common_mode = -2;
   for (int s = 0; s < n_seg; ++s) {
     const cm_segment_t& g = segs[s];
     if (!layout_ok(g.layout)) return fail(h, CM_E_INVALID, "segment %d: bad layout", s);
@@ -343,11 +381,26 @@ int build_segments(cm_handle_t h, Workspace& w, const cm_segment_t* segs, int n_
     if (g.n_points > 0 && (!g.data || (reinterpret_cast<uintptr_t>(g.data) & 15u)))
       return fail(h, CM_E_INVALID, "segment %d: data must be a 16-byte aligned device pointer", s);
     if (g.sensor < 0 || g.sensor >= h->cfg.max_sensors) return fail(h, CM_E_INVALID, "segment %d: bad sensor", s);
-    const bool first = (s == 0) || (g.frame != segs[s - 1].frame);
     if (s == 0 ? g.frame != 0 : (g.frame != segs[s - 1].frame && g.frame != segs[s - 1].frame + 1))
       return fail(h, CM_E_INVALID, "segment %d: frames must start at 0 and increase by steps of 1", s);
+    const int md = (int)seg_mode(g.layout);
+    if (md == (int)SEG_STAGED) max_step_staged = std::max<uint32_t>(max_step_staged, (uint32_t)g.layout.point_step);
+    common_mode = (common_mode == -2 || common_mode == md) ? md : -1;
+    total += g.n_points;
+  }
+  if (total > (int64_t)w.cap_points) return fail(h, CM_E_CAPACITY, "%lld points > capacity %u", (long long)total, w.cap_points);
+  uint32_t T = k1_tile_points(total);
+  if (max_step_staged && k1_staged_smem(T, max_step_staged) > 200u * 1024u) T = k1_min_tile_points();
+  out.resize(n_seg);
+  uint32_t tile = 0, frame = 0, src_base = 0;
+  bool uniform = true;
+  uint32_t tps = 0;
+  for (int s = 0; s < n_seg; ++s) {
+    const cm_segment_t& g = segs[s];
+    const bool first = (s == 0) || (g.frame != segs[s - 1].frame);
     if (first) { frame = (uint32_t)g.frame; src_base = 0; }
     SegDev& d = out[s];
+    memset(&d, 0, sizeof(d));
     d.data = static_cast<const uint8_t*>(g.data);
     d.n_points = (uint32_t)g.n_points;
     d.tile_begin = tile;
@@ -360,30 +413,45 @@ int build_segments(cm_handle_t h, Workspace& w, const cm_segment_t* segs, int n_
     d.sensor = (uint32_t)g.sensor;
     d.first_of_frame = first ? 1u : 0u;
     d.mode = seg_mode(g.layout);
-    d.pad_ = 0;
-    if (d.mode == SEG_STAGED) max_step_staged = std::max<uint32_t>(max_step_staged, (uint32_t)d.point_step);
-    tile += std::max<uint32_t>(1u, (d.n_points + T - 1) / T);
+    memcpy(d.m, h->mats_host + g.sensor * 12, sizeof(d.m));
+    const uint32_t nt = std::max<uint32_t>(1u, (d.n_points + T - 1) / T);
+    if (s == 0) tps = nt; else if (nt != tps) uniform = false;
+    tile += nt;
     src_base += d.n_points;
-    total += g.n_points;
   }
   if (frame + 1 > w.cap_frames) return fail(h, CM_E_CAPACITY, "%u frames > capacity %u", frame + 1, w.cap_frames);
-  if (total > (int64_t)w.cap_points) return fail(h, CM_E_CAPACITY, "%lld points > capacity %u", (long long)total, w.cap_points);
   if ((size_t)tile + 1 > w.lb_k1_n) return fail(h, CM_E_CAPACITY, "too many tiles");
-  *n_frames = frame + 1; *n_tiles = tile; *total_points = total;
-  *staged_smem = max_step_staged ? T * max_step_staged + 16u : 0u;
+  tile_seg.clear();
+  if (!uniform) {
+    tile_seg.resize(tile);
+    for (int s = 0; s < n_seg; ++s) {
+      const uint32_t te = (s + 1 < n_seg) ? out[s + 1].tile_begin : tile;
+      for (uint32_t t = out[s].tile_begin; t < te; ++t) tile_seg[t] = (uint32_t)s;
+    }
+  }
+  plan->n_frames = frame + 1; plan->n_tiles = tile; plan->tile_points = T; plan->total_points = total;
+  plan->tiles_per_seg = uniform ? tps : 0u;
+  plan->mode = (common_mode == (int)SEG_PACKED16 || common_mode == (int)SEG_PCL32) ? common_mode : -1;
+  plan->staged_smem = max_step_staged ? k1_staged_smem(T, max_step_staged) : 0u;
   return CM_OK;
 }
 
 int run_pipeline(cm_handle_t h, Workspace& w, const cm_segment_t* segs, int n_seg, cudaStream_t st, bool with_voxel) {
-  uint32_t n_frames = 0, n_tiles = 0, staged = 0;
-  int64_t total = 0;
+  SegPlan plan;
   std::vector<SegDev> sd;
-  int rc = build_segments(h, w, segs, n_seg, sd, &n_frames, &n_tiles, &total, &staged);
+  std::vector<uint32_t> ts;
+  int rc = build_segments(h, w, segs, n_seg, sd, ts, &plan);
   if (rc != CM_OK) return rc;
   if (sd.size() != w.segs_host.size() || memcmp(sd.data(), w.segs_host.data(), sd.size() * sizeof(SegDev)) != 0) {
     CM_CUDA(h, cudaMemcpyAsync(w.segs, sd.data(), sd.size() * sizeof(SegDev), cudaMemcpyHostToDevice, st));
     w.segs_host = sd;
   }
+  if (!ts.empty() && ts != w.tile_seg_host) {
+    CM_CUDA(h, cudaMemcpyAsync(w.tile_seg, ts.data(), ts.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
+    w.tile_seg_host = ts;
+  }
+  const uint32_t n_frames = plan.n_frames;
+  const int64_t total = plan.total_points;
   const uint32_t epoch = next_epoch(h);
   w.has_run = true; w.report_valid = false; w.profiled = h->profiling;
   w.n_frames = n_frames; w.n_segs = (uint32_t)n_seg; w.points_in = total; w.launches = 0;
@@ -394,15 +462,17 @@ int run_pipeline(cm_handle_t h, Workspace& w, const cm_segment_t* segs, int n_se
   CM_CUDA(h, cudaEventRecord(w.ev[EV_START], st));
   CM_CUDA(h, cudaMemsetAsync(w.meta, 0, w.ml.zero_bytes, st));
   K1Params kp;
-  kp.segs = w.segs; kp.n_seg = (uint32_t)n_seg; kp.n_tiles = n_tiles; kp.n_frames = n_frames; kp.epoch = epoch;
-  kp.mats = h->mats_dev; kp.crop = h->crop;
+  kp.segs = w.segs; kp.n_seg = (uint32_t)n_seg; kp.n_tiles = plan.n_tiles; kp.n_frames = n_frames; kp.epoch = epoch;
+  kp.tiles_per_seg = plan.tiles_per_seg; kp.tile_seg = w.tile_seg;
+  kp.crop = h->crop;
   kp.surv_xyzi = w.surv_xyzi; kp.surv_src = w.surv_src;
   kp.ctrl = reinterpret_cast<Ctrl*>(w.meta + w.ml.off_ctrl);
   kp.acc = reinterpret_cast<FrameAcc*>(w.meta + w.ml.off_acc);
   kp.frame_surv_start = reinterpret_cast<uint32_t*>(w.meta + w.ml.off_fstart);
   kp.seg_surv_start = reinterpret_cast<uint32_t*>(w.meta + w.ml.off_segstart);
   kp.lb = w.lb_k1;
-  CM_CUDA(h, launch_transform_crop(kp, staged, st));
+  kp.trace = w.trace_k1;
+  CM_CUDA(h, launch_transform_crop(kp, plan.tile_points, plan.mode, plan.staged_smem, st));
   ++w.launches;
   CM_CUDA(h, cudaEventRecord(w.ev[EV_K1], st));
   if (!with_voxel) return CM_OK;
@@ -412,11 +482,15 @@ int run_pipeline(cm_handle_t h, Workspace& w, const cm_segment_t* segs, int n_se
 }
 
 // D2H of the control block of the last run + decode into stats / frame info. Blocks.
-int fetch_report(cm_handle_t h, Workspace& w) {
+int fetch_report(cm_handle_t h, Workspace& w, cudaEvent_t already_copied = nullptr) {
   if (!w.has_run) return fail(h, CM_E_INVALID, "nothing has run on this handle");
   if (w.report_valid) return CM_OK;
-  CM_CUDA(h, cudaMemcpyAsync(w.report, w.meta, w.ml.total, cudaMemcpyDeviceToHost, w.stream));
-  CM_CUDA(h, cudaStreamSynchronize(w.stream));
+  if (already_copied) {
+    CM_CUDA(h, cudaEventSynchronize(already_copied));  // the run enqueued the report copy itself
+  } else {
+    CM_CUDA(h, cudaMemcpyAsync(w.report, w.meta, w.ml.total, cudaMemcpyDeviceToHost, w.stream));
+    CM_CUDA(h, cudaStreamSynchronize(w.stream));
+  }
   const Ctrl* ctrl = reinterpret_cast<const Ctrl*>(w.report + w.ml.off_ctrl);
   const FrameAcc* acc = reinterpret_cast<const FrameAcc*>(w.report + w.ml.off_acc);
   const SortInfo* si = reinterpret_cast<const SortInfo*>(w.report + w.ml.off_info);
@@ -572,7 +646,7 @@ int wait_impl(cm_handle_t h, int64_t ticket, cm_frame_out_t* out, uint64_t* used
   if (!sl) return fail(h, CM_E_INVALID, "unknown ticket %lld", (long long)ticket);
   Workspace& w = sl->ws;
   h->last = &w;
-  int rc = fetch_report(h, w);
+  int rc = fetch_report(h, w, sl->done);
   sl->busy = false;
   if (rc != CM_OK) return rc;
   if (used_mask) *used_mask = sl->used_mask;
@@ -678,16 +752,12 @@ int cm_create(const cm_config_t* cfg, cm_handle_t* out) {
     float* m = h->mats_host + s * 12;
     for (int k = 0; k < 12; ++k) m[k] = (k % 5 == 0) ? 1.f : 0.f;  // identity rows
   }
-  if (cudaMalloc(reinterpret_cast<void**>(&h->mats_dev), sizeof(h->mats_host)) != cudaSuccess ||
-      cudaMemcpy(h->mats_dev, h->mats_host, sizeof(h->mats_host), cudaMemcpyHostToDevice) != cudaSuccess) {
-    delete h;
-    return CM_E_CUDA;
-  }
   // defaults = getROI with Parameter.h:31-35 (z [-0.5, 3], y +-5, x [-15, 60]) and Parameter.h:27-28 (0.1 m, 2 points)
   h->crop.n_pass = 3;
   h->crop.pass[0] = PassDev{2, -0.5f, 3.0f, 0};
   h->crop.pass[1] = PassDev{1, -10.0f / 2, 10.0f / 2, 0};
   h->crop.pass[2] = PassDev{0, -15.0f, 75.0f - 15.0f, 0};
+  derive_crop_box(h->crop);
   *out = h;
   return CM_OK;
 }
@@ -705,7 +775,6 @@ int cm_destroy(cm_handle_t h) {
     if (sl.done) cudaEventDestroy(sl.done);
   }
   for (auto& s : h->sensor_stream) if (s) cudaStreamDestroy(s);
-  cudaFree(h->mats_dev);
   delete h;
   return CM_OK;
 }
@@ -717,8 +786,6 @@ int cm_set_extrinsic(cm_handle_t h, int sensor, const float* m16, int col_major)
   float* m = h->mats_host + sensor * 12;
   for (int r = 0; r < 3; ++r)
     for (int c = 0; c < 4; ++c) m[r * 4 + c] = col_major ? m16[c * 4 + r] : m16[r * 4 + c];
-  CM_CUDA(h, cudaSetDevice(h->device));
-  CM_CUDA(h, cudaMemcpy(h->mats_dev + sensor * 12, m, 12 * sizeof(float), cudaMemcpyHostToDevice));
   return CM_OK;
 }
 
@@ -754,6 +821,7 @@ int cm_set_crop(cm_handle_t h, int n_pass, const cm_pass_t* passes) {
     if (passes[k].axis < 0 || passes[k].axis > 3) return fail(h, CM_E_INVALID, "pass %d: axis must be 0..3", k);
   h->crop.n_pass = n_pass;
   for (int k = 0; k < n_pass; ++k) h->crop.pass[k] = PassDev{passes[k].axis, passes[k].lo, passes[k].hi, passes[k].negative ? 1 : 0};
+  derive_crop_box(h->crop);
   return CM_OK;
 }
 
@@ -936,6 +1004,23 @@ int cm_stage_ms(cm_handle_t h, const char* stage, float* ms) {
   if (which < 0) return fail(h, CM_E_INVALID, "unknown stage '%s'", stage);
   *ms = h->stage_ms[which];
   return rc;
+}
+
+int cm_debug_trace(cm_handle_t h, int which, uint64_t* out, int64_t capacity, int64_t* n) {
+  if (!h || !n) return CM_E_INVALID;
+  std::lock_guard<std::mutex> lk(h->mu);
+  if (!h->last) return fail(h, CM_E_INVALID, "nothing has run on this handle");
+  Workspace& w = *h->last;
+  const unsigned long long* src = which == 0 ? w.trace_k1 : w.trace_sort;
+  const size_t cnt = which == 0 ? w.trace_k1_n : w.trace_sort_n;
+  *n = (int64_t)cnt;
+  if (!src) { *n = 0; return CM_OK; }
+  if (!out) return CM_OK;
+  if (capacity < (int64_t)cnt) return fail(h, CM_E_CAPACITY, "trace capacity");
+  CM_CUDA(h, cudaSetDevice(h->device));
+  CM_CUDA(h, cudaDeviceSynchronize());
+  CM_CUDA(h, cudaMemcpy(out, src, cnt * 8, cudaMemcpyDeviceToHost));
+  return CM_OK;
 }
 
 int cm_dev_alloc(cm_handle_t h, void** p, size_t bytes) {

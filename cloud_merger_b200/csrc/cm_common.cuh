@@ -31,7 +31,7 @@ enum SegMode : uint32_t {
 };
 #define CM_MAX_STAGED_STEP 96
 
-struct SegDev {
+struct SegDev {  // 128 bytes: one descriptor read per tile
   const uint8_t* data;
   uint32_t n_points;
   uint32_t tile_begin;      // first K1 tile of this segment (every segment owns >= 1 tile)
@@ -44,7 +44,10 @@ struct SegDev {
   uint32_t first_of_frame;
   uint32_t mode;
   uint32_t pad_;
+  float m[12];              // the sensor's extrinsic, rows 0..2 of the 4x4, row-major
+  uint32_t pad2_[4];
 };
+static_assert(sizeof(SegDev) == 128, "SegDev must stay 128 bytes");
 
 struct PassDev {
   int32_t axis;
@@ -55,6 +58,12 @@ struct PassDev {
 struct CropDev {
   int32_t n_pass;
   PassDev pass[8];
+  // When every pass is a plain (non-negative) window with non-NaN limits the chain collapses to one box:
+  // keep <=> lo[a] <= v[a] <= hi[a] for a = x, y, z (limits default to +-FLT_MAX, which also rejects non-finite
+  // coordinates exactly like PassThrough does) and, if use_i, for the intensity field.
+  int32_t is_box;
+  int32_t use_i;
+  float lo[4], hi[4];
 };
 
 // ---- per-run control block; zeroed by one memset at the start of every run --------------------------------------
@@ -153,30 +162,45 @@ __device__ __forceinline__ unsigned long long lb_pack(uint32_t epoch, uint32_t f
 
 // Spin until the word belongs to this epoch and carries a flag. Returns the word; on watchdog expiry raises the
 // device error and returns an "inclusive 0" word so that every waiter drains.
-__device__ __forceinline__ unsigned long long lb_wait(volatile unsigned long long* p, uint32_t epoch, uint32_t* err) {
+__device__ __forceinline__ unsigned long long ld_relaxed_u64(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_relaxed_u64(unsigned long long* p, unsigned long long v) {
+  asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+
+__device__ __forceinline__ bool lb_ready(unsigned long long w, uint32_t epoch) {
+  const uint32_t hi = (uint32_t)(w >> 32);
+  return (hi >> 2) == epoch && (hi & 3u) != 0u;
+}
+
+// Spin until the word belongs to this epoch and carries a flag. Returns the word; on watchdog expiry raises the
+// device error and returns an "inclusive 0" word so that every waiter drains.
+__device__ __forceinline__ unsigned long long lb_wait(unsigned long long* p, uint32_t epoch, uint32_t* err) {
   uint32_t spins = 0;
   while (true) {
-    unsigned long long w = *p;
-    uint32_t hi = (uint32_t)(w >> 32);
-    if ((hi >> 2) == epoch && (hi & 3u) != 0u) return w;
+    const unsigned long long w = ld_relaxed_u64(p);
+    if (lb_ready(w, epoch)) return w;
     if (++spins > CM_SPIN_LIMIT) {
       atomicExch(err, (uint32_t)CM_DEV_E_INTERNAL);
       return lb_pack(epoch, CM_LB_INCL, 0u);
     }
-    __nanosleep(40);
+    if (spins > 64) __nanosleep(20);
   }
 }
 
 // Exclusive prefix of `agg` over all tiles before `tile`. Must be called by one full warp (all 32 lanes);
 // every lane returns the prefix.
-__device__ __forceinline__ uint32_t lb_exclusive_warp(volatile unsigned long long* st, uint32_t tile, uint32_t agg,
+__device__ __forceinline__ uint32_t lb_exclusive_warp(unsigned long long* st, uint32_t tile, uint32_t agg,
                                                       uint32_t epoch, uint32_t* err) {
   const uint32_t lane = lane_id();
   if (tile == 0) {
-    if (lane == 0) st[0] = lb_pack(epoch, CM_LB_INCL, agg);
+    if (lane == 0) st_relaxed_u64(st, lb_pack(epoch, CM_LB_INCL, agg));
     return 0u;
   }
-  if (lane == 0) st[tile] = lb_pack(epoch, CM_LB_AGG, agg);
+  if (lane == 0) st_relaxed_u64(st + tile, lb_pack(epoch, CM_LB_AGG, agg));
   uint32_t excl = 0;
   long long base = (long long)tile - 1;
   while (true) {
@@ -193,26 +217,81 @@ __device__ __forceinline__ uint32_t lb_exclusive_warp(volatile unsigned long lon
     if (incl) break;
     base -= 32;
   }
-  if (lane == 0) st[tile] = lb_pack(epoch, CM_LB_INCL, excl + agg);
+  if (lane == 0) st_relaxed_u64(st + tile, lb_pack(epoch, CM_LB_INCL, excl + agg));
   return excl;
 }
 
-// Per-thread variant used by the radix pass: thread d walks back over tiles for its own digit d.
-__device__ __forceinline__ uint32_t lb_exclusive_digit(volatile unsigned long long* st, uint32_t tile, uint32_t d,
-                                                       uint32_t agg, uint32_t epoch, uint32_t* err) {
-  volatile unsigned long long* mine = st + (size_t)tile * CM_RADIX + d;
+// Block-wide variant: every warp of the CTA inspects its own 32-tile window in the same round trip, so one step covers
+// WARPS*32 predecessors (a whole generation of co-resident tiles) instead of 32. Must be called by all threads of the
+// block; contains __syncthreads. `scratch` holds 2*WARPS+1 uint32. Returns the exclusive prefix in every thread.
+template <int WARPS>
+__device__ __forceinline__ uint32_t lb_exclusive_block(unsigned long long* st, uint32_t tile, uint32_t agg, uint32_t epoch,
+                                                       uint32_t* err, uint32_t* scratch) {
+  const uint32_t lane = lane_id(), warp = threadIdx.x >> 5;
   if (tile == 0) {
-    *mine = lb_pack(epoch, CM_LB_INCL, agg);
+    if (threadIdx.x == 0) st_relaxed_u64(st, lb_pack(epoch, CM_LB_INCL, agg));
     return 0u;
   }
-  *mine = lb_pack(epoch, CM_LB_AGG, agg);
+  if (threadIdx.x == 0) st_relaxed_u64(st + tile, lb_pack(epoch, CM_LB_AGG, agg));
   uint32_t excl = 0;
-  for (long long j = (long long)tile - 1; j >= 0; --j) {
-    const unsigned long long w = lb_wait(st + (size_t)j * CM_RADIX + d, epoch, err);
-    excl += (uint32_t)w;
-    if ((((uint32_t)(w >> 32)) & 3u) == CM_LB_INCL) break;
+  long long base = (long long)tile - 1;
+  while (true) {
+    const long long idx = base - (long long)(warp * 32u + lane);
+    uint32_t flag = CM_LB_INCL, val = 0;
+    if (idx >= 0) {
+      const unsigned long long w = lb_wait(st + idx, epoch, err);
+      flag = ((uint32_t)(w >> 32)) & 3u;
+      val = (uint32_t)w;
+    }
+    const uint32_t incl = __ballot_sync(0xFFFFFFFFu, flag == CM_LB_INCL);
+    const int first = incl ? (__ffs(incl) - 1) : 32;
+    const uint32_t part = warp_sum_u32(((int)lane <= first) ? val : 0u);
+    if (lane == 0) { scratch[warp] = part; scratch[WARPS + warp] = incl ? 1u : 0u; }
+    __syncthreads();
+    bool found = false;
+#pragma unroll
+    for (int w = 0; w < WARPS; ++w) {
+      if (!found) {
+        excl += scratch[w];
+        found = scratch[WARPS + w] != 0u;
+      }
+    }
+    __syncthreads();
+    if (found) break;
+    base -= (long long)WARPS * 32;
   }
-  *mine = lb_pack(epoch, CM_LB_INCL, excl + agg);
+  if (threadIdx.x == 0) st_relaxed_u64(st + tile, lb_pack(epoch, CM_LB_INCL, excl + agg));
+  return excl;
+}
+
+// Per-digit variant used by the radix pass, split in two so that the aggregate can be published early and the walk
+// done late: thread d walks back over tiles for its own digit d, eight tiles per round trip (independent loads).
+__device__ __forceinline__ void lb_digit_publish(unsigned long long* st, uint32_t tile, uint32_t d, uint32_t agg,
+                                                 uint32_t epoch) {
+  st_relaxed_u64(st + (size_t)tile * CM_RADIX + d, lb_pack(epoch, tile == 0 ? CM_LB_INCL : CM_LB_AGG, agg));
+}
+__device__ __forceinline__ uint32_t lb_digit_walk(unsigned long long* st, uint32_t tile, uint32_t d, uint32_t agg,
+                                                  uint32_t epoch, uint32_t* err) {
+  if (tile == 0) return 0u;
+  constexpr int W = 8;
+  uint32_t excl = 0;
+  long long j = (long long)tile - 1;
+  bool done = false;
+  while (!done && j >= 0) {
+    unsigned long long w[W];
+#pragma unroll
+    for (int k = 0; k < W; ++k) w[k] = (j - k >= 0) ? ld_relaxed_u64(st + (size_t)(j - k) * CM_RADIX + d) : 0ull;
+#pragma unroll
+    for (int k = 0; k < W; ++k) {
+      if (done || j - k < 0) continue;
+      unsigned long long v = w[k];
+      if (!lb_ready(v, epoch)) v = lb_wait(st + (size_t)(j - k) * CM_RADIX + d, epoch, err);
+      excl += (uint32_t)v;
+      if ((((uint32_t)(v >> 32)) & 3u) == CM_LB_INCL) done = true;
+    }
+    j -= W;
+  }
+  st_relaxed_u64(st + (size_t)tile * CM_RADIX + d, lb_pack(epoch, CM_LB_INCL, excl + agg));
   return excl;
 }
 

@@ -1,18 +1,22 @@
 // cm_kernels.h -- launch interface between the C-ABI host layer (cm_api.cu) and the sm_100a kernels.
 #pragma once
 
+#include <algorithm>
+
 #include "cm_common.cuh"
 
 namespace cm {
 
 // ---- K1: fused unpack + transform + crop + stable compaction (cm_transform_crop.cu) ---------------------------------
+#define K1_BIG_BATCH_POINTS (1u << 21)
 struct K1Params {
   const SegDev* segs;
   uint32_t n_seg;
   uint32_t n_tiles;
   uint32_t n_frames;
   uint32_t epoch;
-  const float* mats;  // [sensor][12], row-major 3x4
+  uint32_t tiles_per_seg;    // > 0: every segment owns exactly this many tiles (segment = tile / tiles_per_seg)
+  const uint32_t* tile_seg;  // otherwise: segment of every tile
   CropDev crop;
   float4* surv_xyzi;
   uint32_t* surv_src;  // may be null
@@ -21,9 +25,14 @@ struct K1Params {
   uint32_t* frame_surv_start;  // [n_frames + 1]
   uint32_t* seg_surv_start;    // [n_seg]
   unsigned long long* lb;      // [n_tiles]
+  unsigned long long* trace;   // debug: 8 clock64 stamps per tile, or null
 };
-uint32_t k1_tile_points();
-cudaError_t launch_transform_crop(const K1Params& p, uint32_t staged_smem_bytes, cudaStream_t stream);
+uint32_t k1_tile_points(int64_t total_points);
+uint32_t k1_min_tile_points();
+uint32_t k1_staged_smem(uint32_t tile_points, uint32_t max_step);
+// mode: SEG_PACKED16 / SEG_PCL32 when every segment of the launch has that layout, anything else = generic kernel
+cudaError_t launch_transform_crop(const K1Params& p, uint32_t tile_points, int mode, uint32_t staged_smem_bytes,
+                                  cudaStream_t stream);
 
 // ---- VoxelGrid front/back ends (cm_voxel.cu) ---------------------------------------------------------------------
 struct VoxelParams {
@@ -52,6 +61,8 @@ struct VoxelParams {
   void* out_xyzi;
   uint32_t* out_count;
   unsigned long long* out_idx;
+  unsigned long long* trace;         // debug: 8 clock64 stamps per tile of the traced kernel, or null
+  uint32_t trace_pass;               // which sort pass writes the trace
 };
 
 // bounding box of n packed points (used when VoxelGrid runs on a cloud that did not come out of K1)
@@ -67,6 +78,5 @@ uint32_t centroid_tile_items();
 
 // per-device one-time kernel attribute setup (opt-in shared memory sizes)
 cudaError_t configure_device_kernels();
-uint32_t k1_max_staged_smem();
 
 }  // namespace cm

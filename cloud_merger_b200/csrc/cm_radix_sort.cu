@@ -4,7 +4,7 @@
 // from the reference's voxelgrid(), pc_preprocessing_main.cpp:168-177). No CUB / Thrust.
 //
 // One launch per 8-bit digit. The digit histograms of all passes were produced up front by k_voxel_key_hist, so a pass
-// is a single sweep: each CTA takes a tile (dynamic id), ranks its keys by digit (warp match-any, stable), obtains for
+// is a single sweep: each CTA takes a tile (dynamic id), ranks its keys by digit (ballot-based match, stable), obtains for
 // each of the 256 digits the number of equal-digit keys in all earlier tiles with a decoupled look-back, and scatters
 // keys and values to their final place of this pass through shared memory so that global stores are digit-contiguous.
 // The number of passes is decided on the device (SortInfo.num_passes, from the significant key bits); a pass beyond it
@@ -32,12 +32,12 @@ struct SortCfg<unsigned long long> {
 };
 
 template <typename KeyT>
-__global__ void __launch_bounds__(RS_THREADS) k_onesweep_pass(const VoxelParams p, const int pass) {
+__global__ void __launch_bounds__(RS_THREADS, 3) k_onesweep_pass(const VoxelParams p, const int pass) {
   constexpr int IPT = SortCfg<KeyT>::IPT;
   constexpr int TILE = RS_THREADS * IPT;
   constexpr int WARP_ITEMS = 32 * IPT;
 
-  __shared__ uint32_t s_warp_hist[RS_WARPS][CM_RADIX + 1];  // [..][256] is the bin of out-of-range items
+  __shared__ uint32_t s_warp_hist[RS_WARPS][CM_RADIX];
   __shared__ uint32_t s_bin_start[CM_RADIX];                 // first position of digit d inside the sorted tile
   __shared__ uint32_t s_scatter[CM_RADIX];                   // global position of sorted-tile position 0 of digit d, minus s_bin_start
   __shared__ uint32_t s_scan[9];
@@ -45,6 +45,7 @@ __global__ void __launch_bounds__(RS_THREADS) k_onesweep_pass(const VoxelParams 
   __shared__ __align__(16) KeyT s_keys[TILE];
   __shared__ uint32_t s_vals[TILE];
 
+  const long long tr0 = clock64();
   const SortInfo si = *p.info;
   if ((uint32_t)pass >= si.num_passes) return;
   const uint32_t M = si.n_keys;
@@ -52,11 +53,13 @@ __global__ void __launch_bounds__(RS_THREADS) k_onesweep_pass(const VoxelParams 
 
   const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
   if (tid == 0) s_tile = atomicAdd(&p.ctrl->tile_counter[1 + pass], 1u);
-  for (uint32_t i = tid; i < RS_WARPS * (CM_RADIX + 1); i += RS_THREADS) (&s_warp_hist[0][0])[i] = 0;
+  for (uint32_t i = tid; i < RS_WARPS * CM_RADIX; i += RS_THREADS) (&s_warp_hist[0][0])[i] = 0;
   __syncthreads();
   const uint32_t tile = s_tile;
   if (tile >= n_tiles) return;
 
+#define RS_TRACE(i) do { if (p.trace && p.trace_pass == (uint32_t)pass && tid == 0) p.trace[(size_t)tile * 8 + (i)] = (unsigned long long)(clock64() - tr0); } while (0)
+  RS_TRACE(0);
   const bool odd = (pass & 1) != 0;
   const KeyT* __restrict__ in_keys = reinterpret_cast<const KeyT*>(odd ? p.keys_b : p.keys_a);
   KeyT* __restrict__ out_keys = reinterpret_cast<KeyT*>(odd ? p.keys_a : p.keys_b);
@@ -76,24 +79,50 @@ __global__ void __launch_bounds__(RS_THREADS) k_onesweep_pass(const VoxelParams 
     key[i] = (li < n_here) ? in_keys[tile_base + li] : (KeyT)0;
   }
 
-  // ---- stable rank of every key among the keys of its digit inside the warp -----------------------------------------
-  uint32_t rank[IPT];
+  // values ride along; issue their loads now so the latency hides behind the ranking (pass 0: value = own position)
+  uint32_t val[IPT];
 #pragma unroll
   for (int i = 0; i < IPT; ++i) {
     const uint32_t li = item0 + 32 * i;
-    const uint32_t d = (li < n_here) ? ((uint32_t)(key[i] >> shift) & (CM_RADIX - 1)) : (uint32_t)CM_RADIX;
-    const uint32_t peers = __match_any_sync(0xFFFFFFFFu, d);
-    const int leader = __ffs(peers) - 1;
+    val[i] = (pass == 0) ? (tile_base + li) : ((li < n_here) ? in_vals[tile_base + li] : 0u);
+  }
+
+  RS_TRACE(1);
+  // ---- stable rank of every key among the keys of its digit inside the warp -----------------------------------------
+  // peers = lanes holding the same digit, found with one ballot per digit bit (constant time; __match_any_sync costs
+  // one round per distinct value, i.e. up to 32 rounds on the low, uniformly distributed digits)
+  uint32_t peers[IPT];
+#pragma unroll
+  for (int i = 0; i < IPT; ++i) {
+    const uint32_t li = item0 + 32 * i;
+    const bool valid = li < n_here;
+    const uint32_t d = (uint32_t)(key[i] >> shift) & (CM_RADIX - 1);
+    uint32_t pm = __ballot_sync(0xFFFFFFFFu, valid);
+#pragma unroll
+    for (int b = 0; b < CM_RADIX_BITS; ++b) {
+      const bool bit = (d >> b) & 1u;
+      const uint32_t m = __ballot_sync(0xFFFFFFFFu, bit);
+      pm &= bit ? m : ~m;
+    }
+    peers[i] = valid ? pm : 0u;
+  }
+  uint32_t rank[IPT];
+#pragma unroll
+  for (int i = 0; i < IPT; ++i) {
+    const uint32_t d = (uint32_t)(key[i] >> shift) & (CM_RADIX - 1);
+    const uint32_t pm = peers[i];
+    const int leader = pm ? (__ffs(pm) - 1) : (int)lane;
     uint32_t prev = 0;
-    if ((int)lane == leader) {
+    if (pm && (int)lane == leader) {
       prev = s_warp_hist[warp][d];
-      s_warp_hist[warp][d] = prev + (uint32_t)__popc(peers);
+      s_warp_hist[warp][d] = prev + (uint32_t)__popc(pm);
     }
     prev = __shfl_sync(0xFFFFFFFFu, prev, leader);
-    rank[i] = prev + (uint32_t)__popc(peers & lanemask_lt());
+    rank[i] = prev + (uint32_t)__popc(pm & lanemask_lt());
     __syncwarp();
   }
   __syncthreads();
+  RS_TRACE(2);
 
   // ---- per digit: prefix over warps, tile count, position in the sorted tile, global base, look-back ------------------
   uint32_t cnt = 0;
@@ -109,34 +138,33 @@ __global__ void __launch_bounds__(RS_THREADS) k_onesweep_pass(const VoxelParams 
   const uint32_t bin_start = block_excl_scan_256(cnt, s_scan, &tot);
   const uint32_t gcount = (tid < CM_RADIX) ? p.hist[pass * CM_RADIX + tid] : 0u;
   const uint32_t gbase = block_excl_scan_256(gcount, s_scan, &tot);
+  RS_TRACE(3);
+  const uint32_t epoch = p.epoch + 1u + (uint32_t)pass;
   if (tid < CM_RADIX) {
-    const uint32_t before = lb_exclusive_digit(p.lb_sort, tile, tid, cnt, p.epoch + 1u + (uint32_t)pass, &p.ctrl->error);
+    lb_digit_publish(p.lb_sort, tile, tid, cnt, epoch);  // aggregate out early ...
     s_bin_start[tid] = bin_start;
-    s_scatter[tid] = gbase + before - bin_start;  // modulo 2^32
   }
   __syncthreads();
 
-  // ---- keys into sorted-tile order in shared memory -----------------------------------------------------------------
+  // ---- keys and values into sorted-tile order in shared memory ---------------------------------------------------------
 #pragma unroll
   for (int i = 0; i < IPT; ++i) {
     const uint32_t li = item0 + 32 * i;
     if (li < n_here) {
       const uint32_t d = (uint32_t)(key[i] >> shift) & (CM_RADIX - 1);
       const uint32_t pos = s_bin_start[d] + s_warp_hist[warp][d] + rank[i];
-      rank[i] = pos;
       s_keys[pos] = key[i];
+      s_vals[pos] = val[i];
     }
   }
-  // values travel the same way (pass 0: the value is the key's own position)
-#pragma unroll
-  for (int i = 0; i < IPT; ++i) {
-    const uint32_t li = item0 + 32 * i;
-    if (li < n_here) {
-      const uint32_t v = (pass == 0) ? (tile_base + li) : in_vals[tile_base + li];
-      s_vals[rank[i]] = v;
-    }
+  RS_TRACE(4);
+  // ... and the walk over the predecessors late, when most of them have published
+  if (tid < CM_RADIX) {
+    const uint32_t before = lb_digit_walk(p.lb_sort, tile, tid, cnt, epoch, &p.ctrl->error);
+    s_scatter[tid] = gbase + before - bin_start;  // modulo 2^32
   }
   __syncthreads();
+  RS_TRACE(5);
 
   // ---- scatter: consecutive threads write consecutive addresses inside each digit's run ------------------------------
 #pragma unroll
@@ -150,6 +178,7 @@ __global__ void __launch_bounds__(RS_THREADS) k_onesweep_pass(const VoxelParams 
       out_vals[dst] = s_vals[pos];
     }
   }
+  RS_TRACE(6);
 }
 
 }  // namespace

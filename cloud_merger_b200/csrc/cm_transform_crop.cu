@@ -11,16 +11,18 @@
 // Roofline: HBM. Algorithmic bytes per launch = sum(n_points * point_step) + survivors * (16 + 4).
 // Arithmetic is kept bit-identical to the PCL 1.8.1 CPU build: x' = ((m00*x + m01*y) + m02*z) + m03 with every
 // multiply and add rounded separately (__fmul_rn/__fadd_rn are never contracted into FMA).
+//
+// Structure: one tile per CTA, tile id = blockIdx.x (CTAs of a 1-D grid are dispatched in index order, the property
+// CUB's single-pass scan relies on as well; the look-back has a watchdog should that ever not hold). The kernel is
+// specialised at compile time on the record layout (16-byte packed, 32-byte PCL, generic) and on the crop kind (one
+// box vs. a general chain), which keeps the per-point instruction count low enough to stay memory-bound.
 #include "cm_kernels.h"
 
 namespace cm {
 
 namespace {
 
-constexpr int K1_THREADS = 256;
-constexpr int K1_IPT = 8;
-constexpr int K1_TILE = K1_THREADS * K1_IPT;  // 2048 points
-constexpr int K1_WARPS = K1_THREADS / 32;
+constexpr int MODE_GENERIC = -1;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -61,7 +63,7 @@ __device__ __forceinline__ float ldg_f32_bytes(const uint8_t* p) {
   return __uint_as_float(v);
 }
 
-// One pcl::PassThrough stage on an already finite point (PCL 1.8.1 applyFilterIndices).
+// One pcl::PassThrough stage on a point whose x, y, z are finite (PCL 1.8.1 applyFilterIndices).
 __device__ __forceinline__ bool pass_keeps(const PassDev& ps, float x, float y, float z, float it) {
   const float v = ps.axis == 0 ? x : (ps.axis == 1 ? y : (ps.axis == 2 ? z : it));
   if (!finite_f32(v)) return false;
@@ -69,54 +71,46 @@ __device__ __forceinline__ bool pass_keeps(const PassDev& ps, float x, float y, 
   return !(v >= ps.lo && v <= ps.hi);
 }
 
-}  // namespace
-
-__global__ void __launch_bounds__(K1_THREADS) k_transform_crop(const K1Params p) {
+template <int THREADS, int IPT, int MODE, bool BOX>
+__global__ void __launch_bounds__(THREADS, (THREADS >= 512 ? 2 : 4)) k_transform_crop(const K1Params p) {
+  constexpr int TILE = THREADS * IPT;
+  constexpr int WARPS = THREADS / 32;
   extern __shared__ __align__(16) uint8_t stage[];
-  __shared__ uint32_t s_tile, s_seg, s_tile_excl;
-  __shared__ uint32_t s_warp_tot[K1_WARPS], s_warp_inv[K1_WARPS];
-  __shared__ float s_mm[K1_WARPS][6];
+  __shared__ uint32_t s_lb[2 * WARPS + 1];
+  __shared__ uint32_t s_warp_tot[WARPS], s_warp_inv[WARPS];
+  __shared__ float s_mm[WARPS][6];
   __shared__ __align__(8) unsigned long long s_bar;
 
   const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+  const uint32_t tile = blockIdx.x;
+  const long long tr0 = clock64();
+#define K1_TRACE(i) do { if (p.trace && tid == 0) p.trace[(size_t)tile * 8 + (i)] = (unsigned long long)(clock64() - tr0); } while (0)
 
-  if (tid == 0) s_tile = atomicAdd(&p.ctrl->tile_counter[0], 1u);
-  __syncthreads();
-  const uint32_t tile = s_tile;
+  // which segment owns this tile: uniform batches by division, others through the host-built table
+  const uint32_t seg_id = p.tiles_per_seg ? (tile / p.tiles_per_seg) : __ldg(p.tile_seg + tile);
+  const SegDev* __restrict__ sg = p.segs + seg_id;  // one 128-byte line: the first touch brings all of it
+  const uint8_t* data = sg->data;
+  const uint32_t seg_points = sg->n_points, tile_begin = sg->tile_begin;
+  const uint32_t pt0 = (tile - tile_begin) * TILE;
+  const uint32_t n_here = seg_points > pt0 ? min((uint32_t)TILE, seg_points - pt0) : 0u;
 
-  // which segment owns this tile (segments are few: one parallel probe)
-  for (uint32_t s = tid; s < p.n_seg; s += K1_THREADS) {
-    const uint32_t tb = p.segs[s].tile_begin;
-    const uint32_t te = (s + 1 < p.n_seg) ? p.segs[s + 1].tile_begin : p.n_tiles;
-    if (tb <= tile && tile < te) s_seg = s;
-  }
-  __syncthreads();
-  const uint32_t seg_id = s_seg;
-  const SegDev sg = p.segs[seg_id];
-  const uint32_t pt0 = (tile - sg.tile_begin) * K1_TILE;
-  const uint32_t n_here = sg.n_points > pt0 ? min((uint32_t)K1_TILE, sg.n_points - pt0) : 0u;
-
-  float m[12];
-#pragma unroll
-  for (int k = 0; k < 12; ++k) m[k] = __ldg(p.mats + sg.sensor * 12 + k);
-
-  float x[K1_IPT], y[K1_IPT], z[K1_IPT], it[K1_IPT];
-  const uint32_t li0 = warp * (32 * K1_IPT) + lane;  // local index of item 0; item i is li0 + 32*i
+  float x[IPT], y[IPT], z[IPT], it[IPT];
+  const uint32_t li0 = warp * (32 * IPT) + lane;  // local index of item 0; item i is li0 + 32*i
 
   // ---- unpack -------------------------------------------------------------------------------------------------
-  if (sg.mode == SEG_PACKED16) {
-    const uint8_t* base = sg.data + (size_t)pt0 * 16;
+  if (MODE == (int)SEG_PACKED16) {
+    const uint8_t* base = data + (size_t)pt0 * 16;
 #pragma unroll
-    for (int i = 0; i < K1_IPT; ++i) {
+    for (int i = 0; i < IPT; ++i) {
       const uint32_t li = li0 + 32 * i;
       float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
       if (li < n_here) v = ldg_stream_f4(base + (size_t)li * 16);
       x[i] = v.x; y[i] = v.y; z[i] = v.z; it[i] = v.w;
     }
-  } else if (sg.mode == SEG_PCL32) {
-    const uint8_t* base = sg.data + (size_t)pt0 * 32;
+  } else if (MODE == (int)SEG_PCL32) {
+    const uint8_t* base = data + (size_t)pt0 * 32;
 #pragma unroll
-    for (int i = 0; i < K1_IPT; ++i) {
+    for (int i = 0; i < IPT; ++i) {
       const uint32_t li = li0 + 32 * i;
       float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
       float w = 0.f;
@@ -126,105 +120,150 @@ __global__ void __launch_bounds__(K1_THREADS) k_transform_crop(const K1Params p)
       }
       x[i] = v.x; y[i] = v.y; z[i] = v.z; it[i] = w;
     }
-  } else if (sg.mode == SEG_ALIGNED4) {
-    const uint8_t* base = sg.data + (size_t)pt0 * sg.point_step;
+  } else {
+    const uint32_t mode = sg->mode;
+    const int step = sg->point_step, ox = sg->off_x, oy = sg->off_y, oz = sg->off_z, oi = sg->off_i;
+    const uint8_t* base = data + (size_t)pt0 * step;
+    if (mode == SEG_PACKED16) {
 #pragma unroll
-    for (int i = 0; i < K1_IPT; ++i) {
-      const uint32_t li = li0 + 32 * i;
-      x[i] = y[i] = z[i] = it[i] = 0.f;
-      if (li < n_here) {
-        const uint8_t* r = base + (size_t)li * sg.point_step;
-        x[i] = ldg_stream_f1(r + sg.off_x);
-        y[i] = ldg_stream_f1(r + sg.off_y);
-        z[i] = ldg_stream_f1(r + sg.off_z);
-        if (sg.off_i >= 0) it[i] = ldg_stream_f1(r + sg.off_i);
+      for (int i = 0; i < IPT; ++i) {
+        const uint32_t li = li0 + 32 * i;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (li < n_here) v = ldg_stream_f4(base + (size_t)li * 16);
+        x[i] = v.x; y[i] = v.y; z[i] = v.z; it[i] = v.w;
       }
-    }
-  } else if (sg.mode == SEG_STAGED) {
-    // raw tile bytes -> shared memory with one TMA bulk copy (16-byte multiple) + a < 16-byte tail by plain loads
-    const uint32_t bytes = n_here * (uint32_t)sg.point_step;
-    const uint32_t bulk = bytes & ~15u;
-    const uint8_t* src = sg.data + (size_t)pt0 * sg.point_step;
-    if (tid == 0) mbar_init(&s_bar, 1);
-    __syncthreads();
-    if (tid == 0 && bulk) {
-      mbar_arrive_expect_tx(&s_bar, bulk);
-      bulk_g2s(stage, src, bulk, &s_bar);
-    }
-    for (uint32_t b = bulk + tid; b < bytes; b += K1_THREADS) stage[b] = src[b];
-    if (bulk) {
-      uint32_t spins = 0;
-      while (!mbar_try_wait(&s_bar, 0)) {
-        if (++spins > CM_SPIN_LIMIT) {
-          atomicExch(&p.ctrl->error, (uint32_t)CM_DEV_E_INTERNAL);
-          break;
+    } else if (mode == SEG_PCL32) {
+#pragma unroll
+      for (int i = 0; i < IPT; ++i) {
+        const uint32_t li = li0 + 32 * i;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        float w = 0.f;
+        if (li < n_here) {
+          v = ldg_stream_f4(base + (size_t)li * 32);
+          w = ldg_stream_f1(base + (size_t)li * 32 + 16);
+        }
+        x[i] = v.x; y[i] = v.y; z[i] = v.z; it[i] = w;
+      }
+    } else if (mode == SEG_ALIGNED4) {
+#pragma unroll
+      for (int i = 0; i < IPT; ++i) {
+        const uint32_t li = li0 + 32 * i;
+        x[i] = y[i] = z[i] = it[i] = 0.f;
+        if (li < n_here) {
+          const uint8_t* r = base + (size_t)li * step;
+          x[i] = ldg_stream_f1(r + ox);
+          y[i] = ldg_stream_f1(r + oy);
+          z[i] = ldg_stream_f1(r + oz);
+          if (oi >= 0) it[i] = ldg_stream_f1(r + oi);
+        }
+      }
+    } else if (mode == SEG_STAGED) {
+      // raw tile bytes -> shared memory with one TMA bulk copy (16-byte multiple) + a < 16-byte tail by plain loads
+      const uint32_t bytes = n_here * (uint32_t)step;
+      const uint32_t bulk = bytes & ~15u;
+      if (tid == 0) mbar_init(&s_bar, 1);
+      __syncthreads();
+      if (tid == 0 && bulk) {
+        mbar_arrive_expect_tx(&s_bar, bulk);
+        bulk_g2s(stage, base, bulk, &s_bar);
+      }
+      for (uint32_t b = bulk + tid; b < bytes; b += THREADS) stage[b] = base[b];
+      if (bulk) {
+        uint32_t spins = 0;
+        while (!mbar_try_wait(&s_bar, 0)) {
+          if (++spins > CM_SPIN_LIMIT) {
+            atomicExch(&p.ctrl->error, (uint32_t)CM_DEV_E_INTERNAL);
+            break;
+          }
+        }
+      }
+      __syncthreads();
+#pragma unroll
+      for (int i = 0; i < IPT; ++i) {
+        const uint32_t li = li0 + 32 * i;
+        x[i] = y[i] = z[i] = it[i] = 0.f;
+        if (li < n_here) {
+          const uint32_t r = li * (uint32_t)step;
+          x[i] = lds_f32_unaligned(stage, r + ox);
+          y[i] = lds_f32_unaligned(stage, r + oy);
+          z[i] = lds_f32_unaligned(stage, r + oz);
+          if (oi >= 0) it[i] = lds_f32_unaligned(stage, r + oi);
+        }
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < IPT; ++i) {
+        const uint32_t li = li0 + 32 * i;
+        x[i] = y[i] = z[i] = it[i] = 0.f;
+        if (li < n_here) {
+          const uint8_t* r = base + (size_t)li * step;
+          x[i] = ldg_f32_bytes(r + ox);
+          y[i] = ldg_f32_bytes(r + oy);
+          z[i] = ldg_f32_bytes(r + oz);
+          if (oi >= 0) it[i] = ldg_f32_bytes(r + oi);
         }
       }
     }
-    __syncthreads();
-#pragma unroll
-    for (int i = 0; i < K1_IPT; ++i) {
-      const uint32_t li = li0 + 32 * i;
-      x[i] = y[i] = z[i] = it[i] = 0.f;
-      if (li < n_here) {
-        const uint32_t r = li * (uint32_t)sg.point_step;
-        x[i] = lds_f32_unaligned(stage, r + sg.off_x);
-        y[i] = lds_f32_unaligned(stage, r + sg.off_y);
-        z[i] = lds_f32_unaligned(stage, r + sg.off_z);
-        if (sg.off_i >= 0) it[i] = lds_f32_unaligned(stage, r + sg.off_i);
-      }
-    }
-  } else {
-    const uint8_t* base = sg.data + (size_t)pt0 * sg.point_step;
-#pragma unroll
-    for (int i = 0; i < K1_IPT; ++i) {
-      const uint32_t li = li0 + 32 * i;
-      x[i] = y[i] = z[i] = it[i] = 0.f;
-      if (li < n_here) {
-        const uint8_t* r = base + (size_t)li * sg.point_step;
-        x[i] = ldg_f32_bytes(r + sg.off_x);
-        y[i] = ldg_f32_bytes(r + sg.off_y);
-        z[i] = ldg_f32_bytes(r + sg.off_z);
-        if (sg.off_i >= 0) it[i] = ldg_f32_bytes(r + sg.off_i);
-      }
-    }
   }
+  K1_TRACE(0);
+
+  float m[12];
+#pragma unroll
+  for (int k = 0; k < 12; ++k) m[k] = sg->m[k];
+  const bool dense = sg->is_dense != 0;
 
   // ---- transform + crop predicate + in-warp ranks ------------------------------------------------------------------
-  uint32_t keep_bits = 0;            // bit i: item i survives
-  uint32_t rank_in_warp[K1_IPT];     // exclusive rank of item i among the warp's survivors
-  uint32_t warp_run = 0, inv_run = 0;
+  uint32_t keep_bits = 0;   // bit i: item i survives
+  uint32_t ballots[IPT];    // warp-uniform
+  uint32_t inv_run = 0;
   float mn0 = 3.402823466e+38f, mn1 = mn0, mn2 = mn0, mx0 = -mn0, mx1 = -mn0, mx2 = -mn0;
-  const int n_pass = p.crop.n_pass;
 #pragma unroll
-  for (int i = 0; i < K1_IPT; ++i) {
+  for (int i = 0; i < IPT; ++i) {
     const uint32_t li = li0 + 32 * i;
     const bool in_range = li < n_here;
-    const bool fin_in = finite_f32(x[i]) && finite_f32(y[i]) && finite_f32(z[i]);
-    if (sg.is_dense || fin_in) {
-      const float a = x[i], b = y[i], c = z[i];
+    const float a = x[i], b = y[i], c = z[i];
+    bool keep;
+    if (BOX) {
+      // a non-finite input coordinate makes every output row non-finite, and the box rejects those, so the
+      // "leave invalid points of a non-dense cloud untransformed" rule needs no special case here
       x[i] = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(m[0], a), __fmul_rn(m[1], b)), __fmul_rn(m[2], c)), m[3]);
       y[i] = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(m[4], a), __fmul_rn(m[5], b)), __fmul_rn(m[6], c)), m[7]);
       z[i] = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(m[8], a), __fmul_rn(m[9], b)), __fmul_rn(m[10], c)), m[11]);
+      keep = in_range && x[i] >= p.crop.lo[0] && x[i] <= p.crop.hi[0] && y[i] >= p.crop.lo[1] && y[i] <= p.crop.hi[1] &&
+             z[i] >= p.crop.lo[2] && z[i] <= p.crop.hi[2];
+      if (p.crop.use_i) keep = keep && it[i] >= p.crop.lo[3] && it[i] <= p.crop.hi[3];
+      if (keep) {
+        mn0 = fminf(mn0, x[i]); mx0 = fmaxf(mx0, x[i]);
+        mn1 = fminf(mn1, y[i]); mx1 = fmaxf(mx1, y[i]);
+        mn2 = fminf(mn2, z[i]); mx2 = fmaxf(mx2, z[i]);
+      }
+    } else {
+      const bool fin_in = finite_f32(a) && finite_f32(b) && finite_f32(c);
+      if (dense || fin_in) {
+        x[i] = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(m[0], a), __fmul_rn(m[1], b)), __fmul_rn(m[2], c)), m[3]);
+        y[i] = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(m[4], a), __fmul_rn(m[5], b)), __fmul_rn(m[6], c)), m[7]);
+        z[i] = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(m[8], a), __fmul_rn(m[9], b)), __fmul_rn(m[10], c)), m[11]);
+      }
+      const bool fin = finite_f32(x[i]) && finite_f32(y[i]) && finite_f32(z[i]);
+      keep = in_range;
+      const int n_pass = p.crop.n_pass;
+      if (n_pass > 0) {
+        keep = keep && fin;
+        for (int k = 0; k < n_pass; ++k) keep = keep && pass_keeps(p.crop.pass[k], x[i], y[i], z[i], it[i]);
+      }
+      if (keep && fin) {
+        mn0 = fminf(mn0, x[i]); mx0 = fmaxf(mx0, x[i]);
+        mn1 = fminf(mn1, y[i]); mx1 = fmaxf(mx1, y[i]);
+        mn2 = fminf(mn2, z[i]); mx2 = fmaxf(mx2, z[i]);
+      }
+      inv_run += __popc(__ballot_sync(0xFFFFFFFFu, keep && !fin));
     }
-    const bool fin = finite_f32(x[i]) && finite_f32(y[i]) && finite_f32(z[i]);
-    bool keep = in_range;
-    if (n_pass > 0) {
-      keep = keep && fin;
-      for (int k = 0; k < n_pass; ++k) keep = keep && pass_keeps(p.crop.pass[k], x[i], y[i], z[i], it[i]);
-    }
-    if (keep && fin) {
-      mn0 = fminf(mn0, x[i]); mx0 = fmaxf(mx0, x[i]);
-      mn1 = fminf(mn1, y[i]); mx1 = fmaxf(mx1, y[i]);
-      mn2 = fminf(mn2, z[i]); mx2 = fmaxf(mx2, z[i]);
-    }
-    const uint32_t ballot = __ballot_sync(0xFFFFFFFFu, keep);
-    const uint32_t inv_ballot = __ballot_sync(0xFFFFFFFFu, keep && !fin);
-    rank_in_warp[i] = warp_run + __popc(ballot & lanemask_lt());
-    warp_run += __popc(ballot);
-    inv_run += __popc(inv_ballot);
+    ballots[i] = __ballot_sync(0xFFFFFFFFu, keep);
     keep_bits |= (keep ? 1u : 0u) << i;
   }
+  uint32_t warp_run = 0;
+#pragma unroll
+  for (int i = 0; i < IPT; ++i) warp_run += __popc(ballots[i]);
 
   // ---- bounding box of the survivors (pcl::getMinMax3D) ----------------------------------------------------------------
 #pragma unroll
@@ -239,70 +278,99 @@ __global__ void __launch_bounds__(K1_THREADS) k_transform_crop(const K1Params p)
     s_mm[warp][0] = mn0; s_mm[warp][1] = mn1; s_mm[warp][2] = mn2;
     s_mm[warp][3] = mx0; s_mm[warp][4] = mx1; s_mm[warp][5] = mx2;
   }
+  K1_TRACE(1);
   __syncthreads();
+  K1_TRACE(2);
 
-  // ---- tile prefix by decoupled look-back (warp 0) ---------------------------------------------------------------------
-  if (warp == 0) {
-    uint32_t tot = 0, inv = 0;
+  // ---- tile prefix by decoupled look-back (all warps look back at once: one step covers WARPS*32 tiles) ------------------
+  uint32_t tot = 0, inv = 0;
 #pragma unroll
-    for (int w = 0; w < K1_WARPS; ++w) { tot += s_warp_tot[w]; inv += s_warp_inv[w]; }
-    const uint32_t excl = lb_exclusive_warp(p.lb, tile, tot, p.epoch, &p.ctrl->error);
-    if (lane == 0) {
-      s_tile_excl = excl;
-      if (tile == sg.tile_begin) {
-        p.seg_surv_start[seg_id] = excl;
-        if (sg.first_of_frame) p.frame_surv_start[sg.frame] = excl;
-      }
-      if (tile == p.n_tiles - 1) p.frame_surv_start[p.n_frames] = excl + tot;
-      if (inv) {
-        atomicAdd(&p.acc[sg.frame].n_invalid, inv);
-        atomicOr(&p.ctrl->has_invalid, 1u);
-      }
-      if (tot > inv) {  // at least one finite survivor: fold the tile's box into the frame's
-        float a0 = s_mm[0][0], a1 = s_mm[0][1], a2 = s_mm[0][2], b0 = s_mm[0][3], b1 = s_mm[0][4], b2 = s_mm[0][5];
+  for (int w = 0; w < WARPS; ++w) { tot += s_warp_tot[w]; inv += s_warp_inv[w]; }
+  const uint32_t excl = lb_exclusive_block<WARPS>(p.lb, tile, tot, p.epoch, &p.ctrl->error, s_lb);
+  K1_TRACE(3);
+  if (tid == 0) {
+    const uint32_t frame = sg->frame;
+    if (tile == tile_begin) {
+      p.seg_surv_start[seg_id] = excl;
+      if (sg->first_of_frame) p.frame_surv_start[frame] = excl;
+    }
+    if (tile == p.n_tiles - 1) p.frame_surv_start[p.n_frames] = excl + tot;
+    if (inv) {
+      atomicAdd(&p.acc[frame].n_invalid, inv);
+      atomicOr(&p.ctrl->has_invalid, 1u);
+    }
+    if (tot > inv) {  // at least one finite survivor: fold the tile's box into the frame's
+      float a0 = s_mm[0][0], a1 = s_mm[0][1], a2 = s_mm[0][2], b0 = s_mm[0][3], b1 = s_mm[0][4], b2 = s_mm[0][5];
 #pragma unroll
-        for (int w = 1; w < K1_WARPS; ++w) {
-          a0 = fminf(a0, s_mm[w][0]); a1 = fminf(a1, s_mm[w][1]); a2 = fminf(a2, s_mm[w][2]);
-          b0 = fmaxf(b0, s_mm[w][3]); b1 = fmaxf(b1, s_mm[w][4]); b2 = fmaxf(b2, s_mm[w][5]);
-        }
-        FrameAcc* fa = p.acc + sg.frame;
-        atomicMax(&fa->nmin_enc[0], ~f32_order_enc(__float_as_uint(a0)));
-        atomicMax(&fa->nmin_enc[1], ~f32_order_enc(__float_as_uint(a1)));
-        atomicMax(&fa->nmin_enc[2], ~f32_order_enc(__float_as_uint(a2)));
-        atomicMax(&fa->max_enc[0], f32_order_enc(__float_as_uint(b0)));
-        atomicMax(&fa->max_enc[1], f32_order_enc(__float_as_uint(b1)));
-        atomicMax(&fa->max_enc[2], f32_order_enc(__float_as_uint(b2)));
+      for (int w = 1; w < WARPS; ++w) {
+        a0 = fminf(a0, s_mm[w][0]); a1 = fminf(a1, s_mm[w][1]); a2 = fminf(a2, s_mm[w][2]);
+        b0 = fmaxf(b0, s_mm[w][3]); b1 = fmaxf(b1, s_mm[w][4]); b2 = fmaxf(b2, s_mm[w][5]);
       }
+      FrameAcc* fa = p.acc + frame;
+      atomicMax(&fa->nmin_enc[0], ~f32_order_enc(__float_as_uint(a0)));
+      atomicMax(&fa->nmin_enc[1], ~f32_order_enc(__float_as_uint(a1)));
+      atomicMax(&fa->nmin_enc[2], ~f32_order_enc(__float_as_uint(a2)));
+      atomicMax(&fa->max_enc[0], f32_order_enc(__float_as_uint(b0)));
+      atomicMax(&fa->max_enc[1], f32_order_enc(__float_as_uint(b1)));
+      atomicMax(&fa->max_enc[2], f32_order_enc(__float_as_uint(b2)));
     }
   }
-  __syncthreads();
+  K1_TRACE(4);
 
   // ---- write survivors at their final, order-preserving position ----------------------------------------------------
-  uint32_t warp_excl = s_tile_excl;
-  for (uint32_t w = 0; w < warp; ++w) warp_excl += s_warp_tot[w];
-  const uint32_t src0 = sg.src_base + pt0;
+  uint32_t pos = excl;
+  for (uint32_t w = 0; w < warp; ++w) pos += s_warp_tot[w];
+  const uint32_t src0 = sg->src_base + pt0 + li0;
+  const uint32_t lt = lanemask_lt();
 #pragma unroll
-  for (int i = 0; i < K1_IPT; ++i) {
+  for (int i = 0; i < IPT; ++i) {
     if (keep_bits & (1u << i)) {
-      const uint32_t pos = warp_excl + rank_in_warp[i];
-      p.surv_xyzi[pos] = make_float4(x[i], y[i], z[i], it[i]);
-      if (p.surv_src) p.surv_src[pos] = src0 + li0 + 32 * i;
+      const uint32_t q = pos + __popc(ballots[i] & lt);
+      p.surv_xyzi[q] = make_float4(x[i], y[i], z[i], it[i]);
+      if (p.surv_src) p.surv_src[q] = src0 + 32 * i;
     }
+    pos += __popc(ballots[i]);
   }
+  K1_TRACE(5);
 }
 
-uint32_t k1_tile_points() { return K1_TILE; }
+template <int THREADS, int IPT>
+cudaError_t launch_cfg(const K1Params& p, int mode, bool box, uint32_t smem, cudaStream_t stream) {
+#define CM_K1_LAUNCH(MODE, BOX) k_transform_crop<THREADS, IPT, MODE, BOX><<<p.n_tiles, THREADS, smem, stream>>>(p)
+  if (mode == (int)SEG_PACKED16) { if (box) CM_K1_LAUNCH((int)SEG_PACKED16, true); else CM_K1_LAUNCH((int)SEG_PACKED16, false); }
+  else if (mode == (int)SEG_PCL32) { if (box) CM_K1_LAUNCH((int)SEG_PCL32, true); else CM_K1_LAUNCH((int)SEG_PCL32, false); }
+  else { if (box) CM_K1_LAUNCH(MODE_GENERIC, true); else CM_K1_LAUNCH(MODE_GENERIC, false); }
+#undef CM_K1_LAUNCH
+  return cudaGetLastError();
+}
 
-uint32_t k1_max_staged_smem() { return (uint32_t)K1_TILE * CM_MAX_STAGED_STEP + 16u; }
+}  // namespace
+
+// Two tile shapes: large batches use 4096-point tiles (fewer, fatter links in the look-back chain), single frames use
+// 1024-point tiles so that a 128k-point cloud still spreads over the whole chip.
+uint32_t k1_tile_points(int64_t total_points) { return total_points >= (int64_t)K1_BIG_BATCH_POINTS ? 4096u : 1024u; }
+uint32_t k1_min_tile_points() { return 1024u; }
+uint32_t k1_staged_smem(uint32_t tile_points, uint32_t max_step) { return tile_points * max_step + 16u; }
 
 cudaError_t configure_device_kernels() {
-  return cudaFuncSetAttribute(k_transform_crop, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k1_max_staged_smem());
+  const int big = 200 * 1024;  // the host falls back to 1024-point tiles when a staged layout needs more
+  const int small = (int)k1_staged_smem(1024u, CM_MAX_STAGED_STEP);
+  cudaError_t e;
+  e = cudaFuncSetAttribute(k_transform_crop<512, 8, MODE_GENERIC, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
+  if (e != cudaSuccess) return e;
+  e = cudaFuncSetAttribute(k_transform_crop<512, 8, MODE_GENERIC, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
+  if (e != cudaSuccess) return e;
+  e = cudaFuncSetAttribute(k_transform_crop<256, 4, MODE_GENERIC, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, small);
+  if (e != cudaSuccess) return e;
+  return cudaFuncSetAttribute(k_transform_crop<256, 4, MODE_GENERIC, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, small);
 }
 
-cudaError_t launch_transform_crop(const K1Params& p, uint32_t staged_smem_bytes, cudaStream_t stream) {
+cudaError_t launch_transform_crop(const K1Params& p, uint32_t tile_points, int mode, uint32_t staged_smem_bytes,
+                                  cudaStream_t stream) {
   if (p.n_tiles == 0) return cudaSuccess;
-  k_transform_crop<<<p.n_tiles, K1_THREADS, staged_smem_bytes, stream>>>(p);
-  return cudaGetLastError();
+  const bool box = p.crop.is_box != 0;
+  if (tile_points == 4096u) return launch_cfg<512, 8>(p, mode, box, staged_smem_bytes, stream);
+  return launch_cfg<256, 4>(p, mode, box, staged_smem_bytes, stream);
 }
 
 }  // namespace cm

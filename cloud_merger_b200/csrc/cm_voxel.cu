@@ -260,8 +260,9 @@ __global__ void __launch_bounds__(VX_THREADS) k_voxel_key_hist(const VoxelParams
 // own order is unspecified because std::sort is unstable). centroid = sum / (float)n with an IEEE division.
 template <typename KeyT>
 __global__ void __launch_bounds__(VX_THREADS) k_voxel_centroid(const VoxelParams p) {
-  __shared__ uint32_t s_tile, s_excl;
+  __shared__ uint32_t s_tile;
   __shared__ uint32_t s_scan[9];
+  __shared__ uint32_t s_lb[2 * (VX_THREADS / 32) + 1];
   const uint32_t tid = threadIdx.x;
   const uint32_t F = p.n_frames;
   const uint32_t M = p.frame_surv_start[F];
@@ -307,14 +308,8 @@ __global__ void __launch_bounds__(VX_THREADS) k_voxel_centroid(const VoxelParams
 
   uint32_t total;
   const uint32_t excl_thread = block_excl_scan_256(cnt, s_scan, &total);
-  if (tid < 32) {
-    const uint32_t e = lb_exclusive_warp(p.lb_cent, tile, total, p.epoch + 9u, &p.ctrl->error);
-    if (tid == 0) {
-      s_excl = e;
-      if (tile == n_tiles - 1) p.ctrl->total_voxels = e + total;
-    }
-  }
-  __syncthreads();
+  const uint32_t tile_excl = lb_exclusive_block<VX_THREADS / 32>(p.lb_cent, tile, total, p.epoch + 9u, &p.ctrl->error, s_lb);
+  if (tid == 0 && tile == n_tiles - 1) p.ctrl->total_voxels = tile_excl + total;
 
   // per-frame voxel counts: one atomic per tile unless the tile straddles frames
   bool per_head_count = false;
@@ -331,7 +326,7 @@ __global__ void __launch_bounds__(VX_THREADS) k_voxel_centroid(const VoxelParams
     }
   }
 
-  uint32_t slot = s_excl + excl_thread;
+  uint32_t slot = tile_excl + excl_thread;
 #pragma unroll
   for (int j = 0; j < CE_IPT; ++j) {
     if (!(passbits & (1u << j))) continue;

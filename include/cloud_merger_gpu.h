@@ -223,6 +223,10 @@ CM_API int64_t cm_launch_count(cm_handle_t h);
 CM_API int cm_set_profiling(cm_handle_t h, int on);
 CM_API int cm_stage_ms(cm_handle_t h, const char* stage, float* ms);
 
+/* Debug only: with the environment variable CM_TRACE=1 set at creation, the transform_crop kernel (which = 0) and one
+ * radix pass (which = 1, pass CM_TRACE_PASS) record 8 clock64 stamps per tile; this copies them out. */
+CM_API int cm_debug_trace(cm_handle_t h, int which, uint64_t* out, int64_t capacity, int64_t* n);
+
 /* ---- small device-memory helpers so that non-CUDA callers (ctypes, cgo, JNI) can stage data ---- */
 CM_API int cm_dev_alloc(cm_handle_t h, void** p, size_t bytes);
 CM_API int cm_dev_free(cm_handle_t h, void* p);
