@@ -305,8 +305,8 @@ def main():
     stage_ms = {k: v / args.steps for k, v in stage_acc.items()}
     algo = {
         "transform_crop": pts_step * 16 + M * 20,
-        "key_hist": M * (16 + kb),
-        "sort": M * (2 * (kb + 4) * P - 4),
+        "key_hist": M * (16 + kb + 4),
+        "sort": M * (2 * (kb + 4) * P),
         "centroid": M * (kb + 4 + 16) + V * 28,
     }
     stages = {}

@@ -51,7 +51,8 @@ class CmFrameInfo(C.Structure):
 
 
 class CmDeviceOut(C.Structure):
-    _fields_ = [("survivor_xyzi", C.c_void_p), ("survivor_src", C.c_void_p), ("sorted_key", C.c_void_p),
+    _fields_ = [("survivor_xyzi", C.c_void_p), ("survivor_src", C.c_void_p), ("survivor_slot", C.c_void_p),
+                ("slot_xyzi", C.c_void_p), ("sorted_key", C.c_void_p),
                 ("sorted_point", C.c_void_p), ("voxel_xyzi", C.c_void_p), ("voxel_count", C.c_void_p),
                 ("voxel_idx", C.c_void_p), ("key_bytes", C.c_int32), ("key_idx_bits", C.c_int32)]
 

@@ -339,6 +339,7 @@ class CloudMerger:
         res = dict(stats=st, frames=self.frame_info(), key_bytes=o.key_bytes, key_idx_bits=o.key_idx_bits)
         res["survivor_xyzi"] = self.download(o.survivor_xyzi, np.float32, m * 4).reshape(m, 4) if o.survivor_xyzi else None
         res["survivor_src"] = self.download(o.survivor_src, np.uint32, m) if o.survivor_src else None
+        res["survivor_slot"] = self.download(o.survivor_slot, np.uint32, m) if o.survivor_slot else None
         if o.voxel_xyzi:
             step_f = self.out_point_step // 4
             vx = self.download(o.voxel_xyzi, np.float32, v * step_f).reshape(v, step_f)
@@ -349,7 +350,14 @@ class CloudMerger:
             if want_sorted:
                 kd = np.uint32 if o.key_bytes == 4 else np.uint64
                 res["sorted_key"] = self.download(o.sorted_key, kd, m).astype(np.uint64)
-                res["sorted_point"] = self.download(o.sorted_point, np.uint32, m)
+                slot = self.download(o.sorted_point, np.uint32, m)
+                res["sorted_slot"] = slot
+                if res["survivor_slot"] is not None and m:   # slot -> dense survivor index
+                    inv = np.full(int(res["survivor_slot"].max()) + 1, 0xFFFFFFFF, np.uint32)
+                    inv[res["survivor_slot"]] = np.arange(m, dtype=np.uint32)
+                    res["sorted_point"] = inv[slot]
+                else:
+                    res["sorted_point"] = slot
         return res
 
 

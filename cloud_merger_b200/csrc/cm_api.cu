@@ -60,8 +60,18 @@ struct Workspace {
   uint32_t* surv_src = nullptr;
   void *keys_a = nullptr, *keys_b = nullptr;
   uint32_t *vals_a = nullptr, *vals_b = nullptr;
-  unsigned long long *lb_k1 = nullptr, *lb_sort = nullptr, *lb_cent = nullptr;
+  TileRec* tile_rec = nullptr;          // [lb_k1_n] K1 tile records
+  uint32_t* cent_count = nullptr;       // [lb_cent_n]
+  unsigned long long* lb_sort = nullptr;
   size_t lb_k1_n = 0, lb_sort_n = 0, lb_cent_n = 0;
+  void* tmp_xyzi = nullptr;             // tile-local voxel records before compaction
+  uint32_t* tmp_count = nullptr;
+  unsigned long long* tmp_idx = nullptr;
+  float4* dense_xyzi = nullptr;         // dense merged cloud, allocated and filled on request only
+  uint32_t* dense_src = nullptr;
+  uint32_t* dense_slot = nullptr;
+  bool dense_valid = false;
+  uint32_t n_k1_tiles = 0;
   void* out_xyzi = nullptr;
   uint32_t* out_count = nullptr;
   unsigned long long* out_idx = nullptr;
@@ -160,7 +170,9 @@ void ws_free(Workspace& w) {
   if (!w.ready) return;
   cudaFree(w.meta); cudaFreeHost(w.report); cudaFree(w.segs); cudaFree(w.tile_seg); cudaFree(w.surv_xyzi); cudaFree(w.surv_src);
   cudaFree(w.keys_a); cudaFree(w.keys_b); cudaFree(w.vals_a); cudaFree(w.vals_b);
-  cudaFree(w.lb_k1); cudaFree(w.lb_sort); cudaFree(w.lb_cent);
+  cudaFree(w.tile_rec); cudaFree(w.lb_sort); cudaFree(w.cent_count);
+  cudaFree(w.tmp_xyzi); cudaFree(w.tmp_count); cudaFree(w.tmp_idx);
+  cudaFree(w.dense_xyzi); cudaFree(w.dense_src); cudaFree(w.dense_slot);
   cudaFree(w.out_xyzi); cudaFree(w.out_count); cudaFree(w.out_idx);
   cudaFree(w.trace_k1); cudaFree(w.trace_sort);
   for (auto& e : w.ev) if (e) cudaEventDestroy(e);
@@ -188,12 +200,14 @@ int ws_alloc(cm_handle_t h, Workspace& w, uint32_t points, uint32_t frames, uint
   const uint32_t st = std::min(sort_tile_items(4), sort_tile_items(8));
   w.lb_sort_n = (np / st + 2) * CM_RADIX;
   w.lb_cent_n = np / centroid_tile_items() + 2;
-  CM_CUDA(h, dev_alloc(&w.lb_k1, w.lb_k1_n));
+  CM_CUDA(h, dev_alloc(&w.tile_rec, w.lb_k1_n));
   CM_CUDA(h, dev_alloc(&w.lb_sort, w.lb_sort_n));
-  CM_CUDA(h, dev_alloc(&w.lb_cent, w.lb_cent_n));
-  CM_CUDA(h, cudaMemset(w.lb_k1, 0, w.lb_k1_n * 8));
+  CM_CUDA(h, dev_alloc(&w.cent_count, w.lb_cent_n));
   CM_CUDA(h, cudaMemset(w.lb_sort, 0, w.lb_sort_n * 8));
-  CM_CUDA(h, cudaMemset(w.lb_cent, 0, w.lb_cent_n * 8));
+  const size_t nt = np + centroid_tile_items();
+  CM_CUDA(h, cudaMalloc(&w.tmp_xyzi, nt * 16));
+  CM_CUDA(h, dev_alloc(&w.tmp_count, nt));
+  CM_CUDA(h, dev_alloc(&w.tmp_idx, nt));
   CM_CUDA(h, cudaMalloc(&w.out_xyzi, np * (size_t)out_step));
   CM_CUDA(h, dev_alloc(&w.out_count, np));
   CM_CUDA(h, dev_alloc(&w.out_idx, np));
@@ -214,8 +228,7 @@ uint32_t next_epoch(cm_handle_t h) {
   if ((uint64_t)(h->run_counter + 2) * 16ull >= (1ull << 30)) {
     auto clear = [](Workspace& w) {
       if (!w.ready) return;
-      cudaMemset(w.lb_k1, 0, w.lb_k1_n * 8); cudaMemset(w.lb_sort, 0, w.lb_sort_n * 8);
-      cudaMemset(w.lb_cent, 0, w.lb_cent_n * 8);
+      cudaMemset(w.lb_sort, 0, w.lb_sort_n * 8);
     };
     cudaDeviceSynchronize();
     clear(h->batch);
@@ -294,7 +307,10 @@ void fill_voxel_params(cm_handle_t h, Workspace& w, VoxelParams& vp, const float
   vp.info = reinterpret_cast<SortInfo*>(w.meta + w.ml.off_info);
   vp.hist = reinterpret_cast<uint32_t*>(w.meta + w.ml.off_hist);
   vp.keys_a = w.keys_a; vp.keys_b = w.keys_b; vp.vals_a = w.vals_a; vp.vals_b = w.vals_b;
-  vp.lb_sort = w.lb_sort; vp.lb_cent = w.lb_cent;
+  vp.lb_sort = w.lb_sort; vp.cent_count = w.cent_count;
+  vp.tmp_xyzi = w.tmp_xyzi; vp.tmp_count = w.tmp_count; vp.tmp_idx = w.tmp_idx;
+  vp.tile_rec = w.ran_k1 ? w.tile_rec : nullptr;
+  vp.n_k1_tiles = w.n_k1_tiles;
   vp.epoch = epoch;
   vp.max_passes = CM_MAX_SORT_PASSES;
   vp.out_xyzi = w.out_xyzi; vp.out_count = w.out_count; vp.out_idx = w.out_idx;
@@ -338,7 +354,7 @@ int run_voxel(cm_handle_t h, Workspace& w, VoxelParams& vp, cudaStream_t st) {
   }
   if (h->profiling) CM_CUDA(h, cudaEventRecord(w.ev[EV_SORT], st));
   CM_CUDA(h, launch_centroid(vp, st));
-  ++w.launches;
+  w.launches += CM_CENTROID_LAUNCHES;
   CM_CUDA(h, cudaEventRecord(w.ev[EV_CENT], st));
   w.ran_voxel = true;
   return CM_OK;
@@ -393,6 +409,7 @@ int build_segments(cm_handle_t h, Workspace& w, const cm_segment_t* segs, int n_
   if (max_step_staged && k1_staged_smem(T, max_step_staged) > 200u * 1024u) T = k1_min_tile_points();
   out.resize(n_seg);
   uint32_t tile = 0, frame = 0, src_base = 0;
+  uint64_t slot_base = 0;
   bool uniform = true;
   uint32_t tps = 0;
   for (int s = 0; s < n_seg; ++s) {
@@ -405,6 +422,7 @@ int build_segments(cm_handle_t h, Workspace& w, const cm_segment_t* segs, int n_
     d.n_points = (uint32_t)g.n_points;
     d.tile_begin = tile;
     d.src_base = src_base;
+    d.slot_base = (uint32_t)slot_base;
     d.frame = frame;
     d.point_step = g.layout.point_step;
     d.off_x = g.layout.off_x; d.off_y = g.layout.off_y; d.off_z = g.layout.off_z;
@@ -418,9 +436,11 @@ int build_segments(cm_handle_t h, Workspace& w, const cm_segment_t* segs, int n_
     if (s == 0) tps = nt; else if (nt != tps) uniform = false;
     tile += nt;
     src_base += d.n_points;
+    slot_base += d.n_points;
   }
   if (frame + 1 > w.cap_frames) return fail(h, CM_E_CAPACITY, "%u frames > capacity %u", frame + 1, w.cap_frames);
   if ((size_t)tile + 1 > w.lb_k1_n) return fail(h, CM_E_CAPACITY, "too many tiles");
+  if (slot_base > 0xFFFFFFF0ull) return fail(h, CM_E_CAPACITY, "batch too large");
   tile_seg.clear();
   if (!uniform) {
     tile_seg.resize(tile);
@@ -468,17 +488,35 @@ int run_pipeline(cm_handle_t h, Workspace& w, const cm_segment_t* segs, int n_se
   kp.surv_xyzi = w.surv_xyzi; kp.surv_src = w.surv_src;
   kp.ctrl = reinterpret_cast<Ctrl*>(w.meta + w.ml.off_ctrl);
   kp.acc = reinterpret_cast<FrameAcc*>(w.meta + w.ml.off_acc);
-  kp.frame_surv_start = reinterpret_cast<uint32_t*>(w.meta + w.ml.off_fstart);
-  kp.seg_surv_start = reinterpret_cast<uint32_t*>(w.meta + w.ml.off_segstart);
-  kp.lb = w.lb_k1;
+  kp.tile_rec = w.tile_rec;
   kp.trace = w.trace_k1;
+  w.n_k1_tiles = plan.n_tiles;
+  w.dense_valid = false;
   CM_CUDA(h, launch_transform_crop(kp, plan.tile_points, plan.mode, plan.staged_smem, st));
-  ++w.launches;
+  CM_CUDA(h, launch_tile_scan(w.tile_rec, plan.n_tiles, w.segs, (uint32_t)n_seg, n_frames,
+                              reinterpret_cast<uint32_t*>(w.meta + w.ml.off_fstart),
+                              reinterpret_cast<uint32_t*>(w.meta + w.ml.off_segstart), st));
+  w.launches += 2;
   CM_CUDA(h, cudaEventRecord(w.ev[EV_K1], st));
   if (!with_voxel) return CM_OK;
   VoxelParams vp;
   fill_voxel_params(h, w, vp, w.surv_xyzi, n_frames, (uint32_t)total, epoch);
   return run_voxel(h, w, vp, st);
+}
+
+// Dense copy of the merged cropped cloud of the last K1 run (allocated on first use).
+int materialize_dense(cm_handle_t h, Workspace& w) {
+  if (!w.ran_k1 || w.dense_valid) return CM_OK;
+  const size_t np = std::max<uint32_t>(w.cap_points, 1);
+  if (!w.dense_xyzi) {
+    CM_CUDA(h, dev_alloc(&w.dense_xyzi, np));
+    CM_CUDA(h, dev_alloc(&w.dense_src, np));
+    CM_CUDA(h, dev_alloc(&w.dense_slot, np));
+  }
+  CM_CUDA(h, launch_compact_survivors(w.tile_rec, w.n_k1_tiles, w.surv_xyzi, w.surv_src, w.dense_xyzi, w.dense_src,
+                                      w.dense_slot, w.stream));
+  w.dense_valid = true;
+  return CM_OK;
 }
 
 // D2H of the control block of the last run + decode into stats / frame info. Blocks.
@@ -664,14 +702,18 @@ int wait_impl(cm_handle_t h, int64_t ticket, cm_frame_out_t* out, uint64_t* used
     return fail(h, CM_E_CAPACITY, "survivor_capacity %lld < %lld survivors", (long long)out->survivor_capacity, (long long)out->n_survivors);
   cudaStream_t st = sl->stream;
   const size_t nv = (size_t)out->n_voxels, ns = (size_t)out->n_survivors;
+  if ((out->survivor_xyzi || out->survivor_src || pcl_refuses) && ns) {
+    rc = materialize_dense(h, w);
+    if (rc != CM_OK) return rc;
+  }
   if (pcl_refuses) {
     if (out->voxel_xyzi && nv) {
       if (w.out_step == 16) {
-        CM_CUDA(h, cudaMemcpyAsync(out->voxel_xyzi, w.surv_xyzi, nv * 16, cudaMemcpyDeviceToHost, st));
+        CM_CUDA(h, cudaMemcpyAsync(out->voxel_xyzi, w.dense_xyzi, nv * 16, cudaMemcpyDeviceToHost, st));
       } else {
         // expand packed survivors into pcl::PointXYZI records on the host side of the copy
         std::vector<float> tmp(nv * 4);
-        CM_CUDA(h, cudaMemcpyAsync(tmp.data(), w.surv_xyzi, nv * 16, cudaMemcpyDeviceToHost, st));
+        CM_CUDA(h, cudaMemcpyAsync(tmp.data(), w.dense_xyzi, nv * 16, cudaMemcpyDeviceToHost, st));
         CM_CUDA(h, cudaStreamSynchronize(st));
         float* o = static_cast<float*>(out->voxel_xyzi);
         for (size_t i = 0; i < nv; ++i) {
@@ -687,8 +729,8 @@ int wait_impl(cm_handle_t h, int64_t ticket, cm_frame_out_t* out, uint64_t* used
     if (out->voxel_count && nv) CM_CUDA(h, cudaMemcpyAsync(out->voxel_count, w.out_count, nv * 4, cudaMemcpyDeviceToHost, st));
     if (out->voxel_idx && nv) CM_CUDA(h, cudaMemcpyAsync(out->voxel_idx, w.out_idx, nv * 8, cudaMemcpyDeviceToHost, st));
   }
-  if (out->survivor_xyzi && ns) CM_CUDA(h, cudaMemcpyAsync(out->survivor_xyzi, w.surv_xyzi, ns * 16, cudaMemcpyDeviceToHost, st));
-  if (out->survivor_src && ns) CM_CUDA(h, cudaMemcpyAsync(out->survivor_src, w.surv_src, ns * 4, cudaMemcpyDeviceToHost, st));
+  if (out->survivor_xyzi && ns) CM_CUDA(h, cudaMemcpyAsync(out->survivor_xyzi, w.dense_xyzi, ns * 16, cudaMemcpyDeviceToHost, st));
+  if (out->survivor_src && ns) CM_CUDA(h, cudaMemcpyAsync(out->survivor_src, w.dense_src, ns * 4, cudaMemcpyDeviceToHost, st));
   CM_CUDA(h, cudaStreamSynchronize(st));
   return CM_OK;
 }
@@ -922,7 +964,7 @@ int cm_dev_voxelgrid(cm_handle_t h, const float* xyzi_dev, int64_t n_points, int
   const uint32_t epoch = next_epoch(h);
   w.has_run = true; w.report_valid = false; w.profiled = h->profiling;
   w.n_frames = 1; w.n_segs = 0; w.points_in = n_points; w.launches = 0;
-  w.ran_k1 = false; w.ran_voxel = false; w.stream = st;
+  w.ran_k1 = false; w.ran_voxel = false; w.stream = st; w.n_k1_tiles = 0; w.dense_valid = false;
   w.voxel_pts = reinterpret_cast<const float4*>(xyzi_dev);
   h->last = &w;
   CM_CUDA(h, cudaEventRecord(w.ev[EV_START], st));
@@ -957,8 +999,18 @@ int cm_get_device_out(cm_handle_t h, cm_device_out_t* out) {
   Workspace& w = *h->last;
   int rc = fetch_report(h, w);
   memset(out, 0, sizeof(*out));
-  out->survivor_xyzi = reinterpret_cast<const float*>(w.voxel_pts);
-  out->survivor_src = w.ran_k1 ? w.surv_src : nullptr;
+  if (w.ran_k1) {
+    int rc2 = materialize_dense(h, w);
+    if (rc2 != CM_OK) return rc2;
+    CM_CUDA(h, cudaStreamSynchronize(w.stream));
+    out->survivor_xyzi = reinterpret_cast<const float*>(w.dense_xyzi);
+    out->survivor_src = w.dense_src;
+    out->survivor_slot = w.dense_slot;
+    out->slot_xyzi = reinterpret_cast<const float*>(w.surv_xyzi);
+  } else {
+    out->survivor_xyzi = reinterpret_cast<const float*>(w.voxel_pts);
+    out->slot_xyzi = out->survivor_xyzi;
+  }
   if (w.ran_voxel) {
     const bool odd = (h->stats.sort_passes & 1) != 0;
     out->sorted_key = odd ? w.keys_b : w.keys_a;

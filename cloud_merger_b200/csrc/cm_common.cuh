@@ -2,8 +2,10 @@
 //
 // Conventions
 //  * one "run" = one batch of F frames x S sensors = n_seg segments, processed by a fixed sequence of launches;
-//  * every kernel that needs an order-preserving prefix across CTAs uses a single-pass decoupled look-back over
-//    tiles whose ids are handed out by an atomic counter (forward progress does not depend on CTA dispatch order);
+//  * the streaming kernels (transform_crop, centroid) compact tile-locally and leave one count per tile; a one-CTA scan
+//    turns the counts into dense offsets, so they carry no inter-CTA dependency. Only the radix passes need an
+//    order-preserving prefix across CTAs while the data moves: a single-pass decoupled look-back over tiles whose ids
+//    are handed out by an atomic counter (forward progress does not depend on CTA dispatch order);
 //  * look-back words carry an epoch, so the state arrays never need clearing between runs;
 //  * all spin loops have a watchdog: a stuck wait raises CM_E_INTERNAL in the control block instead of hanging the GPU.
 #pragma once
@@ -36,6 +38,7 @@ struct SegDev {  // 128 bytes: one descriptor read per tile
   uint32_t n_points;
   uint32_t tile_begin;      // first K1 tile of this segment (every segment owns >= 1 tile)
   uint32_t src_base;        // index of this segment's point 0 in its frame's un-cropped concatenation
+  uint32_t slot_base;       // index of this segment's point 0 in the batch's un-cropped concatenation
   uint32_t frame;
   int32_t point_step;
   int32_t off_x, off_y, off_z, off_i;
@@ -45,7 +48,7 @@ struct SegDev {  // 128 bytes: one descriptor read per tile
   uint32_t mode;
   uint32_t pad_;
   float m[12];              // the sensor's extrinsic, rows 0..2 of the 4x4, row-major
-  uint32_t pad2_[4];
+  uint32_t pad2_[3];
 };
 static_assert(sizeof(SegDev) == 128, "SegDev must stay 128 bytes");
 
@@ -64,6 +67,14 @@ struct CropDev {
   int32_t is_box;
   int32_t use_i;
   float lo[4], hi[4];
+};
+
+// ---- one record per K1 tile: where the tile's survivors sit (tile-local compaction) and where they belong densely ----
+struct TileRec {
+  uint32_t count;   // survivors of this tile; they occupy slots [slot0, slot0 + count)
+  uint32_t slot0;   // = position of the tile's first input point in the batch's un-cropped concatenation
+  uint32_t frame;
+  uint32_t dense0;  // exclusive prefix of count over all earlier tiles (filled by k_tile_scan)
 };
 
 // ---- per-run control block; zeroed by one memset at the start of every run --------------------------------------

@@ -22,9 +22,7 @@ struct K1Params {
   uint32_t* surv_src;  // may be null
   Ctrl* ctrl;
   FrameAcc* acc;
-  uint32_t* frame_surv_start;  // [n_frames + 1]
-  uint32_t* seg_surv_start;    // [n_seg]
-  unsigned long long* lb;      // [n_tiles]
+  TileRec* tile_rec;           // [n_tiles] out: count / slot0 / frame of every tile
   unsigned long long* trace;   // debug: 8 clock64 stamps per tile, or null
 };
 uint32_t k1_tile_points(int64_t total_points);
@@ -34,9 +32,20 @@ uint32_t k1_staged_smem(uint32_t tile_points, uint32_t max_step);
 cudaError_t launch_transform_crop(const K1Params& p, uint32_t tile_points, int mode, uint32_t staged_smem_bytes,
                                   cudaStream_t stream);
 
+// One CTA: exclusive prefix of TileRec.count -> TileRec.dense0, frame_surv_start[f] (first tile of each frame),
+// frame_surv_start[n_frames] = total, seg_surv_start[s].
+cudaError_t launch_tile_scan(TileRec* tile_rec, uint32_t n_tiles, const SegDev* segs, uint32_t n_seg, uint32_t n_frames,
+                             uint32_t* frame_surv_start, uint32_t* seg_surv_start, cudaStream_t stream);
+// Dense copy of the merged cropped cloud (xyzi + source index + slot of every survivor), on request only.
+cudaError_t launch_compact_survivors(const TileRec* tile_rec, uint32_t n_tiles, const float4* slot_xyzi,
+                                     const uint32_t* slot_src, float4* dense_xyzi, uint32_t* dense_src,
+                                     uint32_t* dense_slot, cudaStream_t stream);
+
 // ---- VoxelGrid front/back ends (cm_voxel.cu) ---------------------------------------------------------------------
 struct VoxelParams {
-  const float4* pts;                 // survivors (packed xyzi)
+  const float4* pts;                 // survivors by slot (tile-locally compacted), or a plain dense cloud
+  const TileRec* tile_rec;           // K1's tile records; null = pts is dense (slot == index, one frame)
+  uint32_t n_k1_tiles;
   const uint32_t* frame_surv_start;  // [n_frames + 1]; [n_frames] = number of points M
   uint32_t n_frames;
   uint32_t max_points;               // host-side upper bound of M (sizes the grids)
@@ -55,7 +64,10 @@ struct VoxelParams {
   uint32_t* vals_a;
   uint32_t* vals_b;
   unsigned long long* lb_sort;       // [sort tiles][256]
-  unsigned long long* lb_cent;       // [centroid tiles]
+  uint32_t* cent_count;              // [centroid tiles] voxels emitted per tile, then their exclusive prefix
+  void* tmp_xyzi;                    // tile-local voxel outputs before compaction
+  uint32_t* tmp_count;
+  unsigned long long* tmp_idx;
   uint32_t epoch;                    // epochs epoch+1 .. epoch+8 are used by the sort passes, epoch+9 by the centroid pass
   uint32_t max_passes;               // how many pass launches the host enqueues
   void* out_xyzi;
@@ -71,7 +83,8 @@ cudaError_t launch_minmax(const float4* pts, uint32_t n, Ctrl* ctrl, FrameAcc* a
 cudaError_t launch_grid_setup(const VoxelParams& p, cudaStream_t stream);
 cudaError_t launch_key_hist(const VoxelParams& p, cudaStream_t stream);
 cudaError_t launch_sort_pass(const VoxelParams& p, int pass, cudaStream_t stream);
-cudaError_t launch_centroid(const VoxelParams& p, cudaStream_t stream);
+cudaError_t launch_centroid(const VoxelParams& p, cudaStream_t stream);        // 3 launches: centroid, scan, compact
+#define CM_CENTROID_LAUNCHES 3
 
 uint32_t sort_tile_items(uint32_t key_bytes);
 uint32_t centroid_tile_items();

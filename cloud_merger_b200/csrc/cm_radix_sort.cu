@@ -10,7 +10,7 @@
 // The number of passes is decided on the device (SortInfo.num_passes, from the significant key bits); a pass beyond it
 // returns immediately, and every kernel derives the ping-pong buffer it reads from the pass number.
 //
-// Roofline: HBM. Algorithmic bytes per pass = n * 2 * (key_bytes + 4), minus 4 n in pass 0 whose values are implicit.
+// Roofline: HBM. Algorithmic bytes per pass = n * 2 * (key_bytes + 4).
 #include "cm_kernels.h"
 
 namespace cm {
@@ -38,6 +38,7 @@ __global__ void __launch_bounds__(RS_THREADS, 3) k_onesweep_pass(const VoxelPara
   constexpr int WARP_ITEMS = 32 * IPT;
 
   __shared__ uint32_t s_warp_hist[RS_WARPS][CM_RADIX];
+  __shared__ uint32_t s_cnt[CM_RADIX];                       // early per-tile digit counts
   __shared__ uint32_t s_bin_start[CM_RADIX];                 // first position of digit d inside the sorted tile
   __shared__ uint32_t s_scatter[CM_RADIX];                   // global position of sorted-tile position 0 of digit d, minus s_bin_start
   __shared__ uint32_t s_scan[9];
@@ -54,6 +55,7 @@ __global__ void __launch_bounds__(RS_THREADS, 3) k_onesweep_pass(const VoxelPara
   const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
   if (tid == 0) s_tile = atomicAdd(&p.ctrl->tile_counter[1 + pass], 1u);
   for (uint32_t i = tid; i < RS_WARPS * CM_RADIX; i += RS_THREADS) (&s_warp_hist[0][0])[i] = 0;
+  if (tid < CM_RADIX) s_cnt[tid] = 0;
   __syncthreads();
   const uint32_t tile = s_tile;
   if (tile >= n_tiles) return;
@@ -79,12 +81,12 @@ __global__ void __launch_bounds__(RS_THREADS, 3) k_onesweep_pass(const VoxelPara
     key[i] = (li < n_here) ? in_keys[tile_base + li] : (KeyT)0;
   }
 
-  // values ride along; issue their loads now so the latency hides behind the ranking (pass 0: value = own position)
+  // values ride along; issue their loads now so the latency hides behind the ranking
   uint32_t val[IPT];
 #pragma unroll
   for (int i = 0; i < IPT; ++i) {
     const uint32_t li = item0 + 32 * i;
-    val[i] = (pass == 0) ? (tile_base + li) : ((li < n_here) ? in_vals[tile_base + li] : 0u);
+    val[i] = (li < n_here) ? in_vals[tile_base + li] : 0u;
   }
 
   RS_TRACE(1);
@@ -106,6 +108,19 @@ __global__ void __launch_bounds__(RS_THREADS, 3) k_onesweep_pass(const VoxelPara
     }
     peers[i] = valid ? pm : 0u;
   }
+  // ---- early counts: the tile's digit histogram goes out before the (longer) ranking, so that by the time this tile
+  // walks back over its predecessors they have all published theirs (the ranking time becomes slack for stragglers)
+#pragma unroll
+  for (int i = 0; i < IPT; ++i) {
+    const uint32_t pm = peers[i];
+    if (pm && (int)lane == __ffs(pm) - 1) atomicAdd(&s_cnt[(uint32_t)(key[i] >> shift) & (CM_RADIX - 1)], (uint32_t)__popc(pm));
+  }
+  __syncthreads();
+  const uint32_t epoch = p.epoch + 1u + (uint32_t)pass;
+  const uint32_t cnt = (tid < CM_RADIX) ? s_cnt[tid] : 0u;
+  if (tid < CM_RADIX) lb_digit_publish(p.lb_sort, tile, tid, cnt, epoch);
+  RS_TRACE(2);
+
   uint32_t rank[IPT];
 #pragma unroll
   for (int i = 0; i < IPT; ++i) {
@@ -122,29 +137,24 @@ __global__ void __launch_bounds__(RS_THREADS, 3) k_onesweep_pass(const VoxelPara
     __syncwarp();
   }
   __syncthreads();
-  RS_TRACE(2);
 
-  // ---- per digit: prefix over warps, tile count, position in the sorted tile, global base, look-back ------------------
-  uint32_t cnt = 0;
+  // ---- per digit: prefix over warps, position in the sorted tile, global base ------------------------------------------
   if (tid < CM_RADIX) {
+    uint32_t run = 0;
 #pragma unroll
     for (int w = 0; w < RS_WARPS; ++w) {
       const uint32_t t = s_warp_hist[w][tid];
-      s_warp_hist[w][tid] = cnt;
-      cnt += t;
+      s_warp_hist[w][tid] = run;
+      run += t;
     }
   }
   uint32_t tot;
   const uint32_t bin_start = block_excl_scan_256(cnt, s_scan, &tot);
   const uint32_t gcount = (tid < CM_RADIX) ? p.hist[pass * CM_RADIX + tid] : 0u;
   const uint32_t gbase = block_excl_scan_256(gcount, s_scan, &tot);
-  RS_TRACE(3);
-  const uint32_t epoch = p.epoch + 1u + (uint32_t)pass;
-  if (tid < CM_RADIX) {
-    lb_digit_publish(p.lb_sort, tile, tid, cnt, epoch);  // aggregate out early ...
-    s_bin_start[tid] = bin_start;
-  }
+  if (tid < CM_RADIX) s_bin_start[tid] = bin_start;
   __syncthreads();
+  RS_TRACE(3);
 
   // ---- keys and values into sorted-tile order in shared memory ---------------------------------------------------------
 #pragma unroll
@@ -158,7 +168,7 @@ __global__ void __launch_bounds__(RS_THREADS, 3) k_onesweep_pass(const VoxelPara
     }
   }
   RS_TRACE(4);
-  // ... and the walk over the predecessors late, when most of them have published
+  // ---- the walk over the predecessors, late ------------------------------------------------------------------------------
   if (tid < CM_RADIX) {
     const uint32_t before = lb_digit_walk(p.lb_sort, tile, tid, cnt, epoch, &p.ctrl->error);
     s_scatter[tid] = gbase + before - bin_start;  // modulo 2^32

@@ -12,10 +12,14 @@
 // Arithmetic is kept bit-identical to the PCL 1.8.1 CPU build: x' = ((m00*x + m01*y) + m02*z) + m03 with every
 // multiply and add rounded separately (__fmul_rn/__fadd_rn are never contracted into FMA).
 //
-// Structure: one tile per CTA, tile id = blockIdx.x (CTAs of a 1-D grid are dispatched in index order, the property
-// CUB's single-pass scan relies on as well; the look-back has a watchdog should that ever not hold). The kernel is
-// specialised at compile time on the record layout (16-byte packed, 32-byte PCL, generic) and on the crop kind (one
+// Structure: one tile per CTA and no dependency between CTAs: a tile compacts its survivors, in input order, to the
+// head of its own slot range [slot0, slot0 + count) and leaves a 16-byte TileRec; the one-CTA k_tile_scan then turns the
+// counts into dense offsets (frame starts, totals), and the VoxelGrid kernels address survivors by slot. A dense copy of
+// the merged cloud is produced by k_compact_survivors only when a caller asks for it. The kernel is specialised at
+// compile time on the record layout (16-byte packed, 32-byte PCL, generic) and on the crop kind (one
 // box vs. a general chain), which keeps the per-point instruction count low enough to stay memory-bound.
+#include <cstdlib>
+
 #include "cm_kernels.h"
 
 namespace cm {
@@ -76,7 +80,6 @@ __global__ void __launch_bounds__(THREADS, (THREADS >= 512 ? 2 : 4)) k_transform
   constexpr int TILE = THREADS * IPT;
   constexpr int WARPS = THREADS / 32;
   extern __shared__ __align__(16) uint8_t stage[];
-  __shared__ uint32_t s_lb[2 * WARPS + 1];
   __shared__ uint32_t s_warp_tot[WARPS], s_warp_inv[WARPS];
   __shared__ float s_mm[WARPS][6];
   __shared__ __align__(8) unsigned long long s_bar;
@@ -282,19 +285,21 @@ __global__ void __launch_bounds__(THREADS, (THREADS >= 512 ? 2 : 4)) k_transform
   __syncthreads();
   K1_TRACE(2);
 
-  // ---- tile prefix by decoupled look-back (all warps look back at once: one step covers WARPS*32 tiles) ------------------
-  uint32_t tot = 0, inv = 0;
+  // ---- tile-local compaction: positions inside the tile's own slot range; the dense offset comes from k_tile_scan -----
+  uint32_t tot = 0, inv = 0, pos = 0;
 #pragma unroll
-  for (int w = 0; w < WARPS; ++w) { tot += s_warp_tot[w]; inv += s_warp_inv[w]; }
-  const uint32_t excl = lb_exclusive_block<WARPS>(p.lb, tile, tot, p.epoch, &p.ctrl->error, s_lb);
-  K1_TRACE(3);
+  for (int w = 0; w < WARPS; ++w) {
+    const uint32_t c = s_warp_tot[w];
+    if ((uint32_t)w < warp) pos += c;
+    tot += c;
+    inv += s_warp_inv[w];
+  }
+  const uint32_t slot0 = sg->slot_base + pt0;
   if (tid == 0) {
     const uint32_t frame = sg->frame;
-    if (tile == tile_begin) {
-      p.seg_surv_start[seg_id] = excl;
-      if (sg->first_of_frame) p.frame_surv_start[frame] = excl;
-    }
-    if (tile == p.n_tiles - 1) p.frame_surv_start[p.n_frames] = excl + tot;
+    TileRec rec;
+    rec.count = tot; rec.slot0 = slot0; rec.frame = frame; rec.dense0 = 0;
+    *reinterpret_cast<uint4*>(p.tile_rec + tile) = *reinterpret_cast<const uint4*>(&rec);
     if (inv) {
       atomicAdd(&p.acc[frame].n_invalid, inv);
       atomicOr(&p.ctrl->has_invalid, 1u);
@@ -315,11 +320,10 @@ __global__ void __launch_bounds__(THREADS, (THREADS >= 512 ? 2 : 4)) k_transform
       atomicMax(&fa->max_enc[2], f32_order_enc(__float_as_uint(b2)));
     }
   }
-  K1_TRACE(4);
+  K1_TRACE(3);
 
-  // ---- write survivors at their final, order-preserving position ----------------------------------------------------
-  uint32_t pos = excl;
-  for (uint32_t w = 0; w < warp; ++w) pos += s_warp_tot[w];
+  // ---- write the survivors, in input order, at the head of the tile's slot range -----------------------------------------
+  pos += slot0;
   const uint32_t src0 = sg->src_base + pt0 + li0;
   const uint32_t lt = lanemask_lt();
 #pragma unroll
@@ -348,7 +352,11 @@ cudaError_t launch_cfg(const K1Params& p, int mode, bool box, uint32_t smem, cud
 
 // Two tile shapes: large batches use 4096-point tiles (fewer, fatter links in the look-back chain), single frames use
 // 1024-point tiles so that a 128k-point cloud still spreads over the whole chip.
-uint32_t k1_tile_points(int64_t total_points) { return total_points >= (int64_t)K1_BIG_BATCH_POINTS ? 4096u : 1024u; }
+uint32_t k1_tile_points(int64_t total_points) {
+  static const int forced = getenv("CM_K1_TILE") ? atoi(getenv("CM_K1_TILE")) : 0;  // debug override
+  if (forced == 1024 || forced == 4096) return (uint32_t)forced;
+  return total_points >= (int64_t)K1_BIG_BATCH_POINTS ? 4096u : 1024u;
+}
 uint32_t k1_min_tile_points() { return 1024u; }
 uint32_t k1_staged_smem(uint32_t tile_points, uint32_t max_step) { return tile_points * max_step + 16u; }
 

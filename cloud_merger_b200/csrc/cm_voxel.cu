@@ -19,18 +19,29 @@ namespace {
 
 constexpr int VX_THREADS = 256;
 constexpr int KH_IPT = 8;
-constexpr int KH_TILE = VX_THREADS * KH_IPT;  // 2048 points per key/hist tile
+constexpr int KH_TILE = VX_THREADS * KH_IPT;  // 2048 points per min/max tile
+constexpr int KH_DENSE_TILE = 4096;           // virtual tile of the key kernel when the input is a plain dense cloud
+constexpr int SCAN_THREADS = 1024;
 constexpr int CE_IPT = 4;
 constexpr int CE_TILE = VX_THREADS * CE_IPT;  // 1024 sorted items per centroid tile
 
-// largest f in [0, n_frames) with fstart[f] <= idx
-__device__ __forceinline__ uint32_t find_frame(const uint32_t* __restrict__ fstart, uint32_t n_frames, uint32_t idx) {
-  uint32_t lo = 0, hi = n_frames - 1;
-  while (lo < hi) {
-    const uint32_t mid = (lo + hi + 1) >> 1;
-    if (__ldg(fstart + mid) <= idx) lo = mid; else hi = mid - 1;
+// Exclusive scan of one value per thread over a 1024-thread block. Returns the exclusive prefix; *total = block sum.
+__device__ __forceinline__ uint32_t block_excl_scan_1024(uint32_t v, uint32_t* scratch /* 33 words */, uint32_t* total) {
+  const uint32_t tid = threadIdx.x, lane = tid & 31u, w = tid >> 5;
+  const uint32_t incl = warp_incl_scan_u32(v);
+  if (lane == 31) scratch[w] = incl;
+  __syncthreads();
+  if (w == 0) {
+    const uint32_t t = scratch[lane];
+    const uint32_t ti = warp_incl_scan_u32(t);
+    scratch[lane] = ti - t;
+    if (lane == 31) scratch[32] = ti;
   }
-  return lo;
+  __syncthreads();
+  const uint32_t res = incl - v + scratch[w];
+  *total = scratch[32];
+  __syncthreads();
+  return res;
 }
 
 }  // namespace
@@ -92,6 +103,71 @@ __global__ void __launch_bounds__(VX_THREADS) k_minmax(const float4* __restrict_
     if (blockIdx.x == 0) {
       frame_surv_start[0] = 0;
       frame_surv_start[1] = n;
+    }
+  }
+}
+
+// ---- one CTA: dense offsets of the K1 tiles, frame / segment starts, total ------------------------------------------------
+__global__ void __launch_bounds__(SCAN_THREADS) k_tile_scan(TileRec* __restrict__ rec, uint32_t n_tiles,
+                                                           const SegDev* __restrict__ segs, uint32_t n_seg,
+                                                           uint32_t n_frames, uint32_t* frame_surv_start,
+                                                           uint32_t* seg_surv_start) {
+  __shared__ uint32_t s_scr[33];
+  const uint32_t tid = threadIdx.x;
+  const uint32_t chunk = (n_tiles + SCAN_THREADS - 1) / SCAN_THREADS;
+  const uint32_t b = min(n_tiles, tid * chunk), e = min(n_tiles, b + chunk);
+  uint32_t sum = 0;
+  for (uint32_t i = b; i < e; ++i) sum += rec[i].count;
+  uint32_t total;
+  uint32_t run = block_excl_scan_1024(sum, s_scr, &total);
+  for (uint32_t i = b; i < e; ++i) {
+    const uint32_t c = rec[i].count;
+    rec[i].dense0 = run;
+    run += c;
+  }
+  __syncthreads();  // dense0 of every tile is visible to the block
+  for (uint32_t s = tid; s < n_seg; s += SCAN_THREADS) {
+    const uint32_t d0 = rec[segs[s].tile_begin].dense0;
+    seg_surv_start[s] = d0;
+    if (segs[s].first_of_frame) frame_surv_start[segs[s].frame] = d0;
+  }
+  if (tid == 0) frame_surv_start[n_frames] = total;
+}
+
+// ---- one CTA: in-place exclusive scan of n counters (+ total) ----------------------------------------------------------
+__global__ void __launch_bounds__(SCAN_THREADS) k_scan_u32(uint32_t* __restrict__ v, const uint32_t* n_ptr, uint32_t per,
+                                                          uint32_t n_max, uint32_t* total_out) {
+  __shared__ uint32_t s_scr[33];
+  const uint32_t tid = threadIdx.x;
+  // n = ceil(*n_ptr / per): the number of live counters is only known on the device
+  const uint32_t n = min(n_max, (*n_ptr + per - 1) / per);
+  const uint32_t chunk = (n + SCAN_THREADS - 1) / SCAN_THREADS;
+  const uint32_t b = min(n, tid * chunk), e = min(n, b + chunk);
+  uint32_t sum = 0;
+  for (uint32_t i = b; i < e; ++i) sum += v[i];
+  uint32_t total;
+  uint32_t run = block_excl_scan_1024(sum, s_scr, &total);
+  for (uint32_t i = b; i < e; ++i) {
+    const uint32_t c = v[i];
+    v[i] = run;
+    run += c;
+  }
+  if (tid == 0) *total_out = total;
+}
+
+// ---- dense copy of the merged cropped cloud, on request ---------------------------------------------------------------------
+__global__ void __launch_bounds__(VX_THREADS) k_compact_survivors(const TileRec* __restrict__ rec, uint32_t n_tiles,
+                                                                 const float4* __restrict__ slot_xyzi,
+                                                                 const uint32_t* __restrict__ slot_src,
+                                                                 float4* __restrict__ dense_xyzi,
+                                                                 uint32_t* __restrict__ dense_src,
+                                                                 uint32_t* __restrict__ dense_slot) {
+  for (uint32_t t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+    const TileRec r = rec[t];
+    for (uint32_t j = threadIdx.x; j < r.count; j += VX_THREADS) {
+      dense_xyzi[r.dense0 + j] = slot_xyzi[r.slot0 + j];
+      if (dense_src) dense_src[r.dense0 + j] = slot_src[r.slot0 + j];
+      if (dense_slot) dense_slot[r.dense0 + j] = r.slot0 + j;
     }
   }
 }
@@ -181,6 +257,8 @@ __global__ void __launch_bounds__(VX_THREADS) k_grid_setup(const VoxelParams p) 
 }
 
 // ---- voxel key per point + the digit histograms of every radix pass -----------------------------------------------------
+// Walks the K1 tiles: tile t contributes rec.count survivors read from slots [slot0, slot0+count) and written densely at
+// [dense0, dense0+count): key = (frame << idx_bits) | idx, value = slot (what the centroid pass gathers by).
 template <typename KeyT>
 __global__ void __launch_bounds__(VX_THREADS) k_voxel_key_hist(const VoxelParams p) {
   __shared__ uint32_t s_hist[CM_MAX_SORT_PASSES][CM_RADIX];
@@ -192,31 +270,32 @@ __global__ void __launch_bounds__(VX_THREADS) k_voxel_key_hist(const VoxelParams
   const uint32_t M = p.frame_surv_start[F];
   const SortInfo si = *p.info;
   const uint32_t n_pass = si.num_passes, idx_bits = si.idx_bits;
-  const uint32_t n_tiles = (M + KH_TILE - 1) / KH_TILE;
+  const bool dense = p.tile_rec == nullptr;
+  const uint32_t n_tiles = dense ? (M + KH_DENSE_TILE - 1) / KH_DENSE_TILE : p.n_k1_tiles;
   KeyT* __restrict__ keys = reinterpret_cast<KeyT*>(p.keys_a);
+  uint32_t* __restrict__ vals = p.vals_a;
   const unsigned long long sentinel = (unsigned long long)F << idx_bits;
   const float inv0 = p.inv_leaf[0], inv1 = p.inv_leaf[1], inv2 = p.inv_leaf[2];
 
   for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-    const uint32_t base = tile * KH_TILE;
-    const uint32_t last = min(base + KH_TILE, M) - 1;
-    uint32_t f_lo = 0, f_hi = 0;
-    if (F > 1) {
-      f_lo = find_frame(p.frame_surv_start, F, base);
-      f_hi = find_frame(p.frame_surv_start, F, last);
+    TileRec r;
+    if (dense) {
+      r.slot0 = tile * KH_DENSE_TILE; r.dense0 = r.slot0; r.frame = 0;
+      r.count = min((uint32_t)KH_DENSE_TILE, M - r.slot0);
+    } else {
+      const uint4 q = __ldg(reinterpret_cast<const uint4*>(p.tile_rec + tile));
+      r.count = q.x; r.slot0 = q.y; r.frame = q.z; r.dense0 = q.w;
     }
-    GridDev g = p.grid[f_lo];
-    uint32_t f_cur = f_lo;
-#pragma unroll
-    for (int i = 0; i < KH_IPT; ++i) {
-      const uint32_t idx = base + i * VX_THREADS + tid;
-      const bool valid = idx < M;
+    if (r.count == 0) continue;
+    const GridDev g = p.grid[r.frame];
+    const unsigned long long fbits = (unsigned long long)r.frame << idx_bits;
+    const uint32_t rounds = (r.count + VX_THREADS - 1) / VX_THREADS;
+    for (uint32_t it = 0; it < rounds; ++it) {
+      const uint32_t j = it * VX_THREADS + tid;
+      const bool valid = j < r.count;
       unsigned long long key = 0;
       if (valid) {
-        const float4 v = ldg_stream_f4(p.pts + idx);
-        uint32_t f = f_cur;
-        while (f < f_hi && idx >= __ldg(p.frame_surv_start + f + 1)) ++f;
-        if (f != f_cur) { g = p.grid[f]; f_cur = f; }
+        const float4 v = ldg_stream_f4(p.pts + r.slot0 + j);
         if (finite_f32(v.x) && finite_f32(v.y) && finite_f32(v.z)) {
           // PCL: ijk = (int)(floor(x * inv) - (float)min_b); here in integers (identical below 2^24 cells)
           const long long i0 = (long long)(int)floorf(__fmul_rn(v.x, inv0)) - (long long)g.min_b[0];
@@ -224,11 +303,12 @@ __global__ void __launch_bounds__(VX_THREADS) k_voxel_key_hist(const VoxelParams
           const long long i2 = (long long)(int)floorf(__fmul_rn(v.z, inv2)) - (long long)g.min_b[2];
           const unsigned long long cell =
               (unsigned long long)i0 + (unsigned long long)i1 * g.mul1 + (unsigned long long)i2 * g.mul2;
-          key = ((unsigned long long)f << idx_bits) | cell;
+          key = fbits | cell;
         } else {
           key = sentinel;
         }
-        keys[idx] = (KeyT)key;
+        keys[r.dense0 + j] = (KeyT)key;
+        vals[r.dense0 + j] = r.slot0 + j;
       }
       // digit histograms; a warp whose valid lanes all share the digit adds once
       const uint32_t vmask = __ballot_sync(0xFFFFFFFFu, valid);
@@ -258,18 +338,21 @@ __global__ void __launch_bounds__(VX_THREADS) k_voxel_key_hist(const VoxelParams
 // The radix sort is stable and started from ascending point order, so inside a run the points are in ascending index
 // order: the float accumulation below is sequential in that order (one valid order of PCL's CentroidPoint loop, whose
 // own order is unspecified because std::sort is unstable). centroid = sum / (float)n with an IEEE division.
+//
+// Every thread first gathers the points of its own four sorted items (independent loads, all in flight together) and
+// parks them with their keys in shared memory; the thread that owns the head of a run then walks the run in shared
+// memory, so the dependent chain per element is a shared-memory read, not two global round trips. Only the part of a
+// run that continues past the tile is read from global memory.
 template <typename KeyT>
 __global__ void __launch_bounds__(VX_THREADS) k_voxel_centroid(const VoxelParams p) {
-  __shared__ uint32_t s_tile;
   __shared__ uint32_t s_scan[9];
-  __shared__ uint32_t s_lb[2 * (VX_THREADS / 32) + 1];
+  __shared__ __align__(16) float4 s_pts[CE_TILE];
+  __shared__ __align__(16) KeyT s_keys[CE_TILE + 1];
   const uint32_t tid = threadIdx.x;
   const uint32_t F = p.n_frames;
   const uint32_t M = p.frame_surv_start[F];
   const uint32_t n_tiles = (M + CE_TILE - 1) / CE_TILE;
-  if (tid == 0) s_tile = atomicAdd(&p.ctrl->tile_counter[9], 1u);
-  __syncthreads();
-  const uint32_t tile = s_tile;
+  const uint32_t tile = blockIdx.x;
   if (tile >= n_tiles) return;
 
   const SortInfo si = *p.info;
@@ -282,18 +365,32 @@ __global__ void __launch_bounds__(VX_THREADS) k_voxel_centroid(const VoxelParams
   const uint32_t m_req = p.min_points > 1u ? p.min_points : 1u;
 
   const uint32_t tile_base = tile * CE_TILE;
-  const uint32_t base = tile_base + tid * CE_IPT;
+  const uint32_t tile_n = min((uint32_t)CE_TILE, M - tile_base);
+  const uint32_t loc = tid * CE_IPT;           // tile-local index of this thread's first item
+  const uint32_t base = tile_base + loc;
   KeyT k[CE_IPT];
+  uint32_t v[CE_IPT];
 #pragma unroll
-  for (int j = 0; j < CE_IPT; ++j) k[j] = (base + j < M) ? keys[base + j] : (KeyT)0;
+  for (int j = 0; j < CE_IPT; ++j) {
+    const bool in = loc + j < tile_n;
+    k[j] = in ? keys[base + j] : (KeyT)0;
+    v[j] = in ? vals[base + j] : 0u;
+  }
   KeyT prev = (KeyT)0;
-  if (base > 0 && base < M) prev = keys[base - 1];
+  if (base > 0 && loc < tile_n) prev = keys[base - 1];
+#pragma unroll
+  for (int j = 0; j < CE_IPT; ++j) {
+    if (loc + j < tile_n) {
+      s_pts[loc + j] = __ldg(p.pts + v[j]);
+      s_keys[loc + j] = k[j];
+    }
+  }
 
   uint32_t passbits = 0, cnt = 0;
 #pragma unroll
   for (int j = 0; j < CE_IPT; ++j) {
     const uint32_t i = base + j;
-    if (i < M) {
+    if (loc + j < tile_n) {
       const bool head = (i == 0) || (k[j] != (j == 0 ? prev : k[j - 1]));
       if (head) {
         bool ok = (unsigned long long)k[j] < limit;
@@ -307,18 +404,17 @@ __global__ void __launch_bounds__(VX_THREADS) k_voxel_centroid(const VoxelParams
   }
 
   uint32_t total;
-  const uint32_t excl_thread = block_excl_scan_256(cnt, s_scan, &total);
-  const uint32_t tile_excl = lb_exclusive_block<VX_THREADS / 32>(p.lb_cent, tile, total, p.epoch + 9u, &p.ctrl->error, s_lb);
-  if (tid == 0 && tile == n_tiles - 1) p.ctrl->total_voxels = tile_excl + total;
+  const uint32_t excl_thread = block_excl_scan_256(cnt, s_scan, &total);  // also orders the shared-memory staging
+  // tile-local output: this tile's voxels go to tmp[tile_base + rank]; k_scan_u32 + k_compact_voxels make them dense
+  if (tid == 0) p.cent_count[tile] = total;
 
   // per-frame voxel counts: one atomic per tile unless the tile straddles frames
   bool per_head_count = false;
   if (F == 1) {
     if (tid == 0 && total) atomicAdd(&p.acc[0].voxel_count, total);
   } else {
-    const uint32_t tile_last = min(tile_base + CE_TILE, M) - 1;
-    const unsigned long long f_first = (unsigned long long)keys[tile_base] >> idx_bits;
-    const unsigned long long f_last = (unsigned long long)keys[tile_last] >> idx_bits;
+    const unsigned long long f_first = (unsigned long long)s_keys[0] >> idx_bits;
+    const unsigned long long f_last = (unsigned long long)s_keys[tile_n - 1] >> idx_bits;
     if (f_first == f_last) {
       if (tid == 0 && total && f_first < F) atomicAdd(&p.acc[f_first].voxel_count, total);
     } else {
@@ -326,37 +422,61 @@ __global__ void __launch_bounds__(VX_THREADS) k_voxel_centroid(const VoxelParams
     }
   }
 
-  uint32_t slot = tile_excl + excl_thread;
+  uint32_t slot = tile_base + excl_thread;
 #pragma unroll
   for (int j = 0; j < CE_IPT; ++j) {
     if (!(passbits & (1u << j))) continue;
     const KeyT key = k[j];
-    uint32_t q = base + j;
+    uint32_t q = loc + j;
     float sx = 0.f, sy = 0.f, sz = 0.f, sw = 0.f;
     uint32_t n = 0;
-    do {
-      const uint32_t v = __ldg(vals + q);
-      const float4 pt = __ldg(p.pts + v);
+    do {  // the part of the run inside this tile: shared memory
+      const float4 pt = s_pts[q];
       sx = __fadd_rn(sx, pt.x); sy = __fadd_rn(sy, pt.y); sz = __fadd_rn(sz, pt.z); sw = __fadd_rn(sw, pt.w);
       ++n; ++q;
-    } while (q < M && keys[q] == key);
+    } while (q < tile_n && s_keys[q] == key);
+    if (q == tile_n) {  // the run may continue in the following tiles: global memory
+      uint32_t g = tile_base + tile_n;
+      while (g < M && keys[g] == key) {
+        const float4 pt = __ldg(p.pts + __ldg(vals + g));
+        sx = __fadd_rn(sx, pt.x); sy = __fadd_rn(sy, pt.y); sz = __fadd_rn(sz, pt.z); sw = __fadd_rn(sw, pt.w);
+        ++n; ++g;
+      }
+    }
     const float nf = (float)n;
     const float cx = __fdiv_rn(sx, nf), cy = __fdiv_rn(sy, nf), cz = __fdiv_rn(sz, nf);
     const float ci = p.downsample_all ? __fdiv_rn(sw, nf) : 0.f;
-    if (p.out_step == 32) {
-      float4* o = reinterpret_cast<float4*>(reinterpret_cast<uint8_t*>(p.out_xyzi) + (size_t)slot * 32);
-      o[0] = make_float4(cx, cy, cz, 1.0f);
-      o[1] = make_float4(ci, 0.f, 0.f, 0.f);
-    } else {
-      reinterpret_cast<float4*>(p.out_xyzi)[slot] = make_float4(cx, cy, cz, ci);
-    }
-    p.out_count[slot] = n;
-    p.out_idx[slot] = (unsigned long long)key & idx_mask;
+    reinterpret_cast<float4*>(p.tmp_xyzi)[slot] = make_float4(cx, cy, cz, ci);
+    p.tmp_count[slot] = n;
+    p.tmp_idx[slot] = (unsigned long long)key & idx_mask;
     if (per_head_count) {
       const unsigned long long f = (unsigned long long)key >> idx_bits;
       if (f < F) atomicAdd(&p.acc[f].voxel_count, 1u);
     }
     ++slot;
+  }
+}
+
+// ---- tile-local voxel records -> dense, ordered output ----------------------------------------------------------------------
+__global__ void __launch_bounds__(VX_THREADS) k_compact_voxels(const VoxelParams p) {
+  const uint32_t M = p.frame_surv_start[p.n_frames];
+  const uint32_t n_tiles = (M + CE_TILE - 1) / CE_TILE;
+  for (uint32_t t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+    const uint32_t d0 = p.cent_count[t];  // exclusive prefix after k_scan_u32
+    const uint32_t d1 = (t + 1 < n_tiles) ? p.cent_count[t + 1] : p.ctrl->total_voxels;
+    const uint32_t src0 = t * CE_TILE;
+    for (uint32_t j = threadIdx.x; j < d1 - d0; j += VX_THREADS) {
+      const float4 c = reinterpret_cast<const float4*>(p.tmp_xyzi)[src0 + j];
+      if (p.out_step == 32) {
+        float4* o = reinterpret_cast<float4*>(reinterpret_cast<uint8_t*>(p.out_xyzi) + (size_t)(d0 + j) * 32);
+        o[0] = make_float4(c.x, c.y, c.z, 1.0f);
+        o[1] = make_float4(c.w, 0.f, 0.f, 0.f);
+      } else {
+        reinterpret_cast<float4*>(p.out_xyzi)[d0 + j] = c;
+      }
+      p.out_count[d0 + j] = p.tmp_count[src0 + j];
+      p.out_idx[d0 + j] = p.tmp_idx[src0 + j];
+    }
   }
 }
 
@@ -373,13 +493,28 @@ cudaError_t launch_minmax(const float4* pts, uint32_t n, Ctrl* ctrl, FrameAcc* a
   return cudaGetLastError();
 }
 
+cudaError_t launch_tile_scan(TileRec* tile_rec, uint32_t n_tiles, const SegDev* segs, uint32_t n_seg, uint32_t n_frames,
+                             uint32_t* frame_surv_start, uint32_t* seg_surv_start, cudaStream_t stream) {
+  k_tile_scan<<<1, SCAN_THREADS, 0, stream>>>(tile_rec, n_tiles, segs, n_seg, n_frames, frame_surv_start, seg_surv_start);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_compact_survivors(const TileRec* tile_rec, uint32_t n_tiles, const float4* slot_xyzi,
+                                     const uint32_t* slot_src, float4* dense_xyzi, uint32_t* dense_src,
+                                     uint32_t* dense_slot, cudaStream_t stream) {
+  if (n_tiles == 0) return cudaSuccess;
+  k_compact_survivors<<<persistent_grid(n_tiles), VX_THREADS, 0, stream>>>(tile_rec, n_tiles, slot_xyzi, slot_src,
+                                                                            dense_xyzi, dense_src, dense_slot);
+  return cudaGetLastError();
+}
+
 cudaError_t launch_grid_setup(const VoxelParams& p, cudaStream_t stream) {
   k_grid_setup<<<1, VX_THREADS, 0, stream>>>(p);
   return cudaGetLastError();
 }
 
 cudaError_t launch_key_hist(const VoxelParams& p, cudaStream_t stream) {
-  const uint32_t tiles = (p.max_points + KH_TILE - 1) / KH_TILE;
+  const uint32_t tiles = p.tile_rec ? p.n_k1_tiles : (p.max_points + KH_DENSE_TILE - 1) / KH_DENSE_TILE;
   if (p.key_bytes == 4)
     k_voxel_key_hist<uint32_t><<<persistent_grid(tiles), VX_THREADS, 0, stream>>>(p);
   else
@@ -394,6 +529,12 @@ cudaError_t launch_centroid(const VoxelParams& p, cudaStream_t stream) {
     k_voxel_centroid<uint32_t><<<tiles, VX_THREADS, 0, stream>>>(p);
   else
     k_voxel_centroid<unsigned long long><<<tiles, VX_THREADS, 0, stream>>>(p);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return e;
+  k_scan_u32<<<1, SCAN_THREADS, 0, stream>>>(p.cent_count, p.frame_surv_start + p.n_frames, CE_TILE, tiles, &p.ctrl->total_voxels);
+  e = cudaGetLastError();
+  if (e != cudaSuccess) return e;
+  k_compact_voxels<<<persistent_grid(tiles), VX_THREADS, 0, stream>>>(p);
   return cudaGetLastError();
 }
 

@@ -122,10 +122,12 @@ typedef struct {
 
 /* ---- device-resident outputs of the last batch run on a handle (valid until the next run) ---- */
 typedef struct {
-  const float* survivor_xyzi;    /* [survivors][4] merged + cropped cloud, transform applied (concat order) */
+  const float* survivor_xyzi;    /* [survivors][4] merged + cropped cloud, transform applied (concat order); dense copy made by this call */
   const uint32_t* survivor_src;  /* [survivors] index of each survivor in its frame's un-cropped concatenation */
+  const uint32_t* survivor_slot; /* [survivors] slot of each survivor (NULL when the cloud never went through the crop: slot == index) */
+  const float* slot_xyzi;        /* the kernels' own layout: survivors compacted tile by tile, addressed by slot */
   const void* sorted_key;        /* [survivors] voxel keys ascending (uint32 or uint64, see key_bytes) */
-  const uint32_t* sorted_point;  /* [survivors] survivor index belonging to sorted_key[i] (voxel membership) */
+  const uint32_t* sorted_point;  /* [survivors] SLOT of the point belonging to sorted_key[i] (voxel membership) */
   const void* voxel_xyzi;        /* [voxels] centroids, out_point_step bytes each */
   const uint32_t* voxel_count;   /* [voxels] points per voxel */
   const uint64_t* voxel_idx;     /* [voxels] PCL's voxel index idx = i + j*div_x + k*div_x*div_y (64-bit) */

@@ -26,7 +26,7 @@ for _ in range(4):
     cm.run_batch(segs); cm.sync()
 st = cm.stats()
 print("survivors", st.survivors, "voxels", st.voxels_out, "gpu_ms", st.gpu_ms)
-for which, name, labels in ((0, "transform_crop", ["seg+desc", "load+xform+rank", "sync1", "lookback(w0)", "sync2", "stores"]),
+for which, name, labels in ((0, "transform_crop", ["desc+load", "xform+rank", "sync1", "rec+minmax", "(unused)", "stores"]),
                             (1, "onesweep pass", ["setup", "load issue", "rank+sync", "scans", "lookback+sync", "place+sync", "scatter"])):
     nn = C.c_int64()
     cm._check(cm._lib.cm_debug_trace(cm._h, which, None, 0, C.byref(nn)))
@@ -37,6 +37,8 @@ for which, name, labels in ((0, "transform_crop", ["seg+desc", "load+xform+rank"
     print("%s: %d tiles traced" % (name, len(t)))
     prev = np.zeros(len(t), np.int64)
     for i, lab in enumerate(labels):
+        if lab == "(unused)":
+            continue
         d = t[:, i] - prev
         prev = t[:, i]
         print("   %-18s median %7d  p90 %7d  mean %7d cycles" % (lab, np.median(d), np.percentile(d, 90), d.mean()))
