@@ -166,6 +166,9 @@ __device__ __forceinline__ float ldg_stream_f1(const void* p) {
 #define CM_LB_AGG 1u
 #define CM_LB_INCL 2u
 #define CM_SPIN_LIMIT (1u << 22)
+#ifndef CM_WALK_W
+#define CM_WALK_W 24  // tiles per round trip of the per-digit walk: must exceed (round-trip latency / tile issue interval)
+#endif
 
 __device__ __forceinline__ unsigned long long lb_pack(uint32_t epoch, uint32_t flag, uint32_t value) {
   return ((unsigned long long)(epoch * 4u + flag) << 32) | (unsigned long long)value;
@@ -177,6 +180,17 @@ __device__ __forceinline__ unsigned long long ld_relaxed_u64(const unsigned long
   unsigned long long v;
   asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
   return v;
+}
+// Weak load served by L2 (L1 bypassed), so it observes other SMs' stores, and -- unlike the strong load above, which the
+// hardware completes one at a time per thread (measured: ~300 cycles each, back to back) -- several can be in flight.
+// Used for the batched window reads of the look-back; the spin on a single word keeps the strong load.
+__device__ __forceinline__ unsigned long long ld_cg_u64(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.global.cg.u64 %0, [%1];" : "=l"(v) : "l"(p));
+  return v;
+}
+__device__ __forceinline__ void st_cg_u64(unsigned long long* p, unsigned long long v) {
+  asm volatile("st.global.cg.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
 __device__ __forceinline__ void st_relaxed_u64(unsigned long long* p, unsigned long long v) {
   asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
@@ -199,6 +213,21 @@ __device__ __forceinline__ unsigned long long lb_wait(unsigned long long* p, uin
       return lb_pack(epoch, CM_LB_INCL, 0u);
     }
     if (spins > 64) __nanosleep(20);
+  }
+}
+
+// Spin until the word of this epoch carries the INCLUSIVE flag (written by the scanner CTAs of the radix pass).
+__device__ __forceinline__ uint32_t lb_wait_inclusive(unsigned long long* p, uint32_t epoch, uint32_t* err) {
+  uint32_t spins = 0;
+  while (true) {
+    const unsigned long long w = ld_relaxed_u64(p);
+    const uint32_t hi = (uint32_t)(w >> 32);
+    if ((hi >> 2) == epoch && (hi & 3u) == CM_LB_INCL) return (uint32_t)w;
+    if (++spins > CM_SPIN_LIMIT) {
+      atomicExch(err, (uint32_t)CM_DEV_E_INTERNAL);
+      return 0u;
+    }
+    if (spins > 16) __nanosleep(40);
   }
 }
 
@@ -277,33 +306,81 @@ __device__ __forceinline__ uint32_t lb_exclusive_block(unsigned long long* st, u
 
 // Per-digit variant used by the radix pass, split in two so that the aggregate can be published early and the walk
 // done late: thread d walks back over tiles for its own digit d, eight tiles per round trip (independent loads).
-__device__ __forceinline__ void lb_digit_publish(unsigned long long* st, uint32_t tile, uint32_t d, uint32_t agg,
-                                                 uint32_t epoch) {
-  st_relaxed_u64(st + (size_t)tile * CM_RADIX + d, lb_pack(epoch, tile == 0 ? CM_LB_INCL : CM_LB_AGG, agg));
+// Returns true (and *excl) when the predecessor's inclusive prefix was already there, in which case this tile's own
+// inclusive prefix is published at once instead of a bare aggregate.
+__device__ __forceinline__ bool lb_digit_publish(unsigned long long* st, uint32_t tile, uint32_t d, uint32_t agg,
+                                                 uint32_t epoch, uint32_t* excl) {
+  unsigned long long* mine = st + (size_t)tile * CM_RADIX + d;
+  if (tile == 0) {
+    st_relaxed_u64(mine, lb_pack(epoch, CM_LB_INCL, agg));
+    *excl = 0;
+    return true;
+  }
+  const unsigned long long w = ld_relaxed_u64(mine - CM_RADIX);
+  if (lb_ready(w, epoch) && (((uint32_t)(w >> 32)) & 3u) == CM_LB_INCL) {
+    *excl = (uint32_t)w;
+    st_relaxed_u64(mine, lb_pack(epoch, CM_LB_INCL, (uint32_t)w + agg));
+    return true;
+  }
+  st_relaxed_u64(mine, lb_pack(epoch, CM_LB_AGG, agg));
+  return false;
 }
 __device__ __forceinline__ uint32_t lb_digit_walk(unsigned long long* st, uint32_t tile, uint32_t d, uint32_t agg,
-                                                  uint32_t epoch, uint32_t* err) {
+                                                  uint32_t epoch, uint32_t* err, unsigned long long* dbg = nullptr) {
   if (tile == 0) return 0u;
-  constexpr int W = 8;
-  uint32_t excl = 0;
-  long long j = (long long)tile - 1;
-  bool done = false;
+  constexpr int W = CM_WALK_W;
+  uint32_t excl = 0, dbg_steps = 0, dbg_wait = 0;
+  long long j = (long long)tile;  // the first batch starts with this tile's own word: a pusher may have completed it
+  bool done = false, first = true;
   while (!done && j >= 0) {
     unsigned long long w[W];
 #pragma unroll
-    for (int k = 0; k < W; ++k) w[k] = (j - k >= 0) ? ld_relaxed_u64(st + (size_t)(j - k) * CM_RADIX + d) : 0ull;
+    for (int k = 0; k < W; ++k) w[k] = (j - k >= 0) ? ld_cg_u64(st + (size_t)(j - k) * CM_RADIX + d) : 0ull;
 #pragma unroll
     for (int k = 0; k < W; ++k) {
       if (done || j - k < 0) continue;
       unsigned long long v = w[k];
-      if (!lb_ready(v, epoch)) v = lb_wait(st + (size_t)(j - k) * CM_RADIX + d, epoch, err);
+      if (first && k == 0) {  // own word: inclusive already => exclusive = inclusive - aggregate
+        if (lb_ready(v, epoch) && (((uint32_t)(v >> 32)) & 3u) == CM_LB_INCL) {
+          if (dbg) *dbg = 0;
+          return (uint32_t)v - agg;
+        }
+        continue;
+      }
+      ++dbg_steps;
+      if (!lb_ready(v, epoch)) { ++dbg_wait; v = lb_wait(st + (size_t)(j - k) * CM_RADIX + d, epoch, err); }
       excl += (uint32_t)v;
       if ((((uint32_t)(v >> 32)) & 3u) == CM_LB_INCL) done = true;
     }
+    first = false;
     j -= W;
   }
   st_relaxed_u64(st + (size_t)tile * CM_RADIX + d, lb_pack(epoch, CM_LB_INCL, excl + agg));
+  if (dbg) *dbg = ((unsigned long long)dbg_steps << 32) | dbg_wait;
   return excl;
+}
+// Forward push: a tile that knows its inclusive prefix completes, on their behalf, the inclusive prefixes of the tiles
+// right after it that have already published an aggregate (the value is the one the owner would compute itself, so the
+// duplicate store is benign). Every tile does this for a bounded number of successors, batch-loading their words, so the
+// inclusive frontier is carried forward cooperatively and the walks of later tiles stop after one round trip.
+__device__ __forceinline__ void lb_digit_push(unsigned long long* st, uint32_t tile, uint32_t n_tiles, uint32_t d,
+                                              uint32_t incl, uint32_t epoch, uint32_t max_rounds) {
+  constexpr int W = 16;
+  uint32_t run = incl;
+  uint32_t j = tile + 1;
+  for (uint32_t r = 0; r < max_rounds && j < n_tiles; ++r, j += W) {
+    unsigned long long w[W];
+#pragma unroll
+    for (int k = 0; k < W; ++k) w[k] = (j + k < n_tiles) ? ld_cg_u64(st + (size_t)(j + k) * CM_RADIX + d) : 0ull;
+#pragma unroll
+    for (int k = 0; k < W; ++k) {
+      if (j + k >= n_tiles) return;
+      const unsigned long long v = w[k];
+      if (!lb_ready(v, epoch) || (((uint32_t)(v >> 32)) & 3u) == CM_LB_INCL) return;
+      run += (uint32_t)v;
+      st_relaxed_u64(st + (size_t)(j + k) * CM_RADIX + d, lb_pack(epoch, CM_LB_INCL, run));
+    }
+  }
 }
 
 // Exclusive scan over 256 values held one per thread by threads 0..255 of a block with >= 256 threads.

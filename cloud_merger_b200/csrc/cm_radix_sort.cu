@@ -4,8 +4,8 @@
 // from the reference's voxelgrid(), pc_preprocessing_main.cpp:168-177). No CUB / Thrust.
 //
 // One launch per 8-bit digit. The digit histograms of all passes were produced up front by k_voxel_key_hist, so a pass
-// is a single sweep: each CTA takes a tile (dynamic id), ranks its keys by digit (ballot-based match, stable), obtains for
-// each of the 256 digits the number of equal-digit keys in all earlier tiles with a decoupled look-back, and scatters
+// is a single sweep: each CTA takes a tile, ranks its keys by digit (ballot-based match, stable), obtains for
+// each of the 256 digits the number of equal-digit keys in all earlier tiles (chained scan; see "scanner CTAs"), and scatters
 // keys and values to their final place of this pass through shared memory so that global stores are digit-contiguous.
 // The number of passes is decided on the device (SortInfo.num_passes, from the significant key bits); a pass beyond it
 // returns immediately, and every kernel derives the ping-pong buffer it reads from the pass number.
@@ -31,6 +31,61 @@ struct SortCfg<unsigned long long> {
   static constexpr int IPT = 12;
 };
 
+// ---- scanner CTAs -------------------------------------------------------------------------------------------------------
+// The first RS_SCANNERS CTAs of a pass do not sort: scanner h owns 64 digits and walks the tile rows in order, four
+// threads per digit, 32 rows per round trip: it waits until the rows' aggregates are published, and rewrites every row
+// with the inclusive prefix. A worker tile then reads exactly one row -- its predecessor's inclusive prefix -- instead
+// of walking back over every tile in flight (that walk, 256 digits x dozens of rows per tile, cost as much L2 bandwidth
+// as the keys themselves). Scanners are CTAs 0..3 of the grid, i.e. resident before any worker; workers publish their
+// aggregate before they wait, so the pair cannot deadlock.
+constexpr int RS_SCANNERS = 4;
+constexpr int RS_SCAN_ROWS = 8;  // rows per thread per round trip (x4 threads per digit = 32 rows)
+
+__device__ __forceinline__ void scanner_load(unsigned long long (&w)[RS_SCAN_ROWS], const unsigned long long* st,
+                                             uint32_t r0, uint32_t n_tiles, uint32_t d) {
+#pragma unroll
+  for (int k = 0; k < RS_SCAN_ROWS; ++k) w[k] = (r0 + k < n_tiles) ? ld_cg_u64(st + (size_t)(r0 + k) * CM_RADIX + d) : 0ull;
+}
+
+__device__ __forceinline__ void scanner_cta(unsigned long long* st, uint32_t n_tiles, uint32_t epoch, uint32_t* err) {
+  const uint32_t tid = threadIdx.x;
+  const uint32_t d = blockIdx.x * (CM_RADIX / RS_SCANNERS) + (tid >> 2);  // digit
+  const uint32_t q = tid & 3u;                                            // which quarter of the 32-row batch
+  uint32_t run = 0;                                                       // inclusive prefix of everything before the batch
+  unsigned long long w[RS_SCAN_ROWS], wn[RS_SCAN_ROWS];
+  scanner_load(w, st, q * RS_SCAN_ROWS, n_tiles, d);
+  for (uint32_t t0 = 0; t0 < n_tiles; t0 += 4 * RS_SCAN_ROWS) {
+    const uint32_t r0 = t0 + q * RS_SCAN_ROWS;
+    scanner_load(wn, st, r0 + 4 * RS_SCAN_ROWS, n_tiles, d);  // next batch in flight while this one is processed
+    uint32_t v[RS_SCAN_ROWS];
+    uint32_t sum = 0;
+#pragma unroll
+    for (int k = 0; k < RS_SCAN_ROWS; ++k) {
+      v[k] = 0;
+      if (r0 + k < n_tiles) {
+        unsigned long long x = w[k];
+        if (!lb_ready(x, epoch)) x = lb_wait(st + (size_t)(r0 + k) * CM_RADIX + d, epoch, err);
+        v[k] = (uint32_t)x;
+      }
+      sum += v[k];
+      v[k] = sum;  // inclusive within this thread's rows
+    }
+    // inclusive prefix of `sum` over the 4 threads of the digit (lanes 4g .. 4g+3)
+    uint32_t incl = sum;
+    uint32_t o = __shfl_up_sync(0xFFFFFFFFu, incl, 1, 4);
+    if (q >= 1) incl += o;
+    o = __shfl_up_sync(0xFFFFFFFFu, incl, 2, 4);
+    if (q >= 2) incl += o;
+    const uint32_t base = run + incl - sum;
+#pragma unroll
+    for (int k = 0; k < RS_SCAN_ROWS; ++k)
+      if (r0 + k < n_tiles) st_cg_u64(st + (size_t)(r0 + k) * CM_RADIX + d, lb_pack(epoch, CM_LB_INCL, base + v[k]));
+    run += __shfl_sync(0xFFFFFFFFu, incl, 3, 4);  // batch total
+#pragma unroll
+    for (int k = 0; k < RS_SCAN_ROWS; ++k) w[k] = wn[k];
+  }
+}
+
 template <typename KeyT>
 __global__ void __launch_bounds__(RS_THREADS, 3) k_onesweep_pass(const VoxelParams p, const int pass) {
   constexpr int IPT = SortCfg<KeyT>::IPT;
@@ -42,7 +97,6 @@ __global__ void __launch_bounds__(RS_THREADS, 3) k_onesweep_pass(const VoxelPara
   __shared__ uint32_t s_bin_start[CM_RADIX];                 // first position of digit d inside the sorted tile
   __shared__ uint32_t s_scatter[CM_RADIX];                   // global position of sorted-tile position 0 of digit d, minus s_bin_start
   __shared__ uint32_t s_scan[9];
-  __shared__ uint32_t s_tile;
   __shared__ __align__(16) KeyT s_keys[TILE];
   __shared__ uint32_t s_vals[TILE];
 
@@ -53,12 +107,19 @@ __global__ void __launch_bounds__(RS_THREADS, 3) k_onesweep_pass(const VoxelPara
   const uint32_t n_tiles = (M + TILE - 1) / TILE;
 
   const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
-  if (tid == 0) s_tile = atomicAdd(&p.ctrl->tile_counter[1 + pass], 1u);
+  // tile id = blockIdx.x: CTAs of a 1-D grid are dispatched in index order (what CUB's single-pass scan relies on too;
+  // the look-back watchdog covers the case that this ever fails to hold)
+  const uint32_t epoch = p.epoch + 1u + (uint32_t)pass;
+  if (blockIdx.x < RS_SCANNERS) {
+    scanner_cta(p.lb_sort, n_tiles, epoch, &p.ctrl->error);
+    return;
+  }
+  const uint32_t tile = blockIdx.x - RS_SCANNERS;
+  if (tile >= n_tiles) return;
+  const uint32_t gcount = (tid < CM_RADIX) ? p.hist[pass * CM_RADIX + tid] : 0u;  // needed late: fetch it now
   for (uint32_t i = tid; i < RS_WARPS * CM_RADIX; i += RS_THREADS) (&s_warp_hist[0][0])[i] = 0;
   if (tid < CM_RADIX) s_cnt[tid] = 0;
   __syncthreads();
-  const uint32_t tile = s_tile;
-  if (tile >= n_tiles) return;
 
 #define RS_TRACE(i) do { if (p.trace && p.trace_pass == (uint32_t)pass && tid == 0) p.trace[(size_t)tile * 8 + (i)] = (unsigned long long)(clock64() - tr0); } while (0)
   RS_TRACE(0);
@@ -116,9 +177,8 @@ __global__ void __launch_bounds__(RS_THREADS, 3) k_onesweep_pass(const VoxelPara
     if (pm && (int)lane == __ffs(pm) - 1) atomicAdd(&s_cnt[(uint32_t)(key[i] >> shift) & (CM_RADIX - 1)], (uint32_t)__popc(pm));
   }
   __syncthreads();
-  const uint32_t epoch = p.epoch + 1u + (uint32_t)pass;
   const uint32_t cnt = (tid < CM_RADIX) ? s_cnt[tid] : 0u;
-  if (tid < CM_RADIX) lb_digit_publish(p.lb_sort, tile, tid, cnt, epoch);
+  if (tid < CM_RADIX) st_relaxed_u64(p.lb_sort + (size_t)tile * CM_RADIX + tid, lb_pack(epoch, CM_LB_AGG, cnt));
   RS_TRACE(2);
 
   uint32_t rank[IPT];
@@ -150,7 +210,6 @@ __global__ void __launch_bounds__(RS_THREADS, 3) k_onesweep_pass(const VoxelPara
   }
   uint32_t tot;
   const uint32_t bin_start = block_excl_scan_256(cnt, s_scan, &tot);
-  const uint32_t gcount = (tid < CM_RADIX) ? p.hist[pass * CM_RADIX + tid] : 0u;
   const uint32_t gbase = block_excl_scan_256(gcount, s_scan, &tot);
   if (tid < CM_RADIX) s_bin_start[tid] = bin_start;
   __syncthreads();
@@ -168,9 +227,10 @@ __global__ void __launch_bounds__(RS_THREADS, 3) k_onesweep_pass(const VoxelPara
     }
   }
   RS_TRACE(4);
-  // ---- the walk over the predecessors, late ------------------------------------------------------------------------------
+  // ---- one row from the scanners: the inclusive prefix of the previous tile ------------------------------------------------
   if (tid < CM_RADIX) {
-    const uint32_t before = lb_digit_walk(p.lb_sort, tile, tid, cnt, epoch, &p.ctrl->error);
+    const uint32_t before =
+        tile == 0 ? 0u : lb_wait_inclusive(p.lb_sort + (size_t)(tile - 1) * CM_RADIX + tid, epoch, &p.ctrl->error);
     s_scatter[tid] = gbase + before - bin_start;  // modulo 2^32
   }
   __syncthreads();
@@ -202,9 +262,9 @@ cudaError_t launch_sort_pass(const VoxelParams& p, int pass, cudaStream_t stream
   const uint32_t tiles = (p.max_points + tile - 1) / tile;
   if (tiles == 0) return cudaSuccess;
   if (p.key_bytes == 4)
-    k_onesweep_pass<uint32_t><<<tiles, RS_THREADS, 0, stream>>>(p, pass);
+    k_onesweep_pass<uint32_t><<<tiles + RS_SCANNERS, RS_THREADS, 0, stream>>>(p, pass);
   else
-    k_onesweep_pass<unsigned long long><<<tiles, RS_THREADS, 0, stream>>>(p, pass);
+    k_onesweep_pass<unsigned long long><<<tiles + RS_SCANNERS, RS_THREADS, 0, stream>>>(p, pass);
   return cudaGetLastError();
 }
 

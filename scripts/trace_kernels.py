@@ -43,4 +43,8 @@ for which, name, labels in ((0, "transform_crop", ["desc+load", "xform+rank", "s
         prev = t[:, i]
         print("   %-18s median %7d  p90 %7d  mean %7d cycles" % (lab, np.median(d), np.percentile(d, 90), d.mean()))
     print("   %-18s median %7d  p90 %7d" % ("TOTAL", np.median(t[:, len(labels) - 1]), np.percentile(t[:, len(labels) - 1], 90)))
+    if which == 1:
+        steps, waits = t[:, 7] >> 32, t[:, 7] & 0xFFFFFFFF
+        print("   walk (digit 3): tiles traversed median %d p90 %d max %d; not-ready words median %d p90 %d" % (
+            np.median(steps), np.percentile(steps, 90), steps.max(), np.median(waits), np.percentile(waits, 90)))
 cm.close()
