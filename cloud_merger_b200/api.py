@@ -163,6 +163,15 @@ class CloudMerger:
         self._check(self._lib.cm_set_voxel(self._h, leaf.ctypes.data_as(C.POINTER(C.c_float)), int(min_points),
                                            int(downsample_all)))
 
+    def set_voxel_bounds(self, min3=None, max3=None):
+        """Bounding box of the whole (partitioned) cloud for the next dev_voxelgrid calls; None switches it off."""
+        if min3 is None or max3 is None:
+            self._check(self._lib.cm_set_voxel_bounds(self._h, None, None))
+            return
+        a = (C.c_float * 3)(*[float(np.float32(v)) for v in min3])
+        b = (C.c_float * 3)(*[float(np.float32(v)) for v in max3])
+        self._check(self._lib.cm_set_voxel_bounds(self._h, a, b))
+
     def set_overflow_mode(self, pcl_like: bool):
         self._check(self._lib.cm_set_overflow_mode(self._h, int(pcl_like)))
 

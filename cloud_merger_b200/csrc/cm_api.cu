@@ -126,6 +126,8 @@ struct cm_handle_s {
   uint32_t downsample_all = 1;
   int overflow_mode = 0;
   bool profiling = false;
+  bool have_bounds = false;   // externally supplied bounding box for cm_dev_voxelgrid (partitioned giant cloud)
+  float bounds_min[3] = {0, 0, 0}, bounds_max[3] = {0, 0, 0};
   // run bookkeeping
   uint32_t run_counter = 0;
   Workspace batch;          // device-resident batch path
@@ -881,6 +883,18 @@ int cm_set_voxel(cm_handle_t h, const float* leaf3, int min_points, int downsamp
   return CM_OK;
 }
 
+int cm_set_voxel_bounds(cm_handle_t h, const float* min3, const float* max3) {
+  if (!h) return CM_E_INVALID;
+  std::lock_guard<std::mutex> lk(h->mu);
+  if (!min3 || !max3) { h->have_bounds = false; return CM_OK; }
+  for (int k = 0; k < 3; ++k) {
+    if (!std::isfinite(min3[k]) || !std::isfinite(max3[k]) || min3[k] > max3[k]) return fail(h, CM_E_INVALID, "bad bounds");
+    h->bounds_min[k] = min3[k]; h->bounds_max[k] = max3[k];
+  }
+  h->have_bounds = true;
+  return CM_OK;
+}
+
 int cm_set_overflow_mode(cm_handle_t h, int mode) {
   if (!h || (mode != 0 && mode != 1)) return CM_E_INVALID;
   h->overflow_mode = mode;
@@ -973,6 +987,10 @@ int cm_dev_voxelgrid(cm_handle_t h, const float* xyzi_dev, int64_t n_points, int
   fill_voxel_params(h, w, vp, w.voxel_pts, 1, (uint32_t)n_points, epoch);
   CM_CUDA(h, launch_minmax(w.voxel_pts, (uint32_t)n_points, vp.ctrl, vp.acc, const_cast<uint32_t*>(vp.frame_surv_start), st));
   ++w.launches;
+  if (h->have_bounds) {
+    CM_CUDA(h, launch_seed_bounds(vp.acc, h->bounds_min, h->bounds_max, st));
+    ++w.launches;
+  }
   CM_CUDA(h, cudaEventRecord(w.ev[EV_K1], st));
   return run_voxel(h, w, vp, st);
 }

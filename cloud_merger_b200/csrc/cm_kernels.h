@@ -80,6 +80,7 @@ struct VoxelParams {
 // bounding box of n packed points (used when VoxelGrid runs on a cloud that did not come out of K1)
 cudaError_t launch_minmax(const float4* pts, uint32_t n, Ctrl* ctrl, FrameAcc* acc, uint32_t* frame_surv_start,
                           cudaStream_t stream);
+cudaError_t launch_seed_bounds(FrameAcc* acc, const float* mn, const float* mx, cudaStream_t stream);
 cudaError_t launch_grid_setup(const VoxelParams& p, cudaStream_t stream);
 cudaError_t launch_key_hist(const VoxelParams& p, cudaStream_t stream);
 cudaError_t launch_sort_pass(const VoxelParams& p, int pass, cudaStream_t stream);

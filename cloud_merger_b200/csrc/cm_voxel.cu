@@ -172,6 +172,18 @@ __global__ void __launch_bounds__(VX_THREADS) k_compact_survivors(const TileRec*
   }
 }
 
+// ---- fold externally supplied bounds (the all-reduced bounding box of a cloud partitioned over several GPUs) into frame 0 --
+__global__ void k_seed_bounds(FrameAcc* acc, float mn0, float mn1, float mn2, float mx0, float mx1, float mx2) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) {
+    atomicMax(&acc->nmin_enc[0], ~f32_order_enc(__float_as_uint(mn0)));
+    atomicMax(&acc->nmin_enc[1], ~f32_order_enc(__float_as_uint(mn1)));
+    atomicMax(&acc->nmin_enc[2], ~f32_order_enc(__float_as_uint(mn2)));
+    atomicMax(&acc->max_enc[0], f32_order_enc(__float_as_uint(mx0)));
+    atomicMax(&acc->max_enc[1], f32_order_enc(__float_as_uint(mx1)));
+    atomicMax(&acc->max_enc[2], f32_order_enc(__float_as_uint(mx2)));
+  }
+}
+
 // ---- grid per frame + sort plan (one block) -----------------------------------------------------------------------
 // PCL 1.8.1: min_b = floor(min_p * inv), max_b = floor(max_p * inv), div_b = max_b - min_b + 1, and the guard
 // dx*dy*dz > INT32_MAX with d = (int64)((max_p - min_p) * inv) + 1.
@@ -490,6 +502,11 @@ cudaError_t launch_minmax(const float4* pts, uint32_t n, Ctrl* ctrl, FrameAcc* a
                           cudaStream_t stream) {
   const uint32_t tiles = (n + KH_TILE - 1) / KH_TILE;
   k_minmax<<<persistent_grid(tiles), VX_THREADS, 0, stream>>>(pts, n, ctrl, acc, frame_surv_start);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_seed_bounds(FrameAcc* acc, const float* mn, const float* mx, cudaStream_t stream) {
+  k_seed_bounds<<<1, 32, 0, stream>>>(acc, mn[0], mn[1], mn[2], mx[0], mx[1], mx[2]);
   return cudaGetLastError();
 }
 

@@ -171,6 +171,10 @@ CM_API int cm_set_crop(cm_handle_t h, int n_pass, const cm_pass_t* passes);
 /* cm_set_voxel replaces voxel_grid.setLeafSize / setDownsampleAllData / setMinimumPointsNumberPerVoxel
  * (pc_preprocessing_main.cpp:171-175). Defaults: leaf 0.1, min_points 2, downsample_all 1 (Parameter.h:27-28). */
 CM_API int cm_set_voxel(cm_handle_t h, const float* leaf3, int min_points, int downsample_all);
+/* Single-giant-cloud mode (one cloud partitioned by voxel-key range over several GPUs): the bounding box pcl::getMinMax3D
+ * would find on the WHOLE cloud, all-reduced by the caller. The next cm_dev_voxelgrid calls fold it into the local box, so
+ * every rank builds the same grid (same min_b / div_b / voxel indices). NULL, NULL switches it off. */
+CM_API int cm_set_voxel_bounds(cm_handle_t h, const float* min3, const float* max3);
 /* PCL 1.8.1 returns the input cloud unchanged when dx*dy*dz > INT32_MAX. mode 0 (default): keep going with the 64-bit
  * key and report it in cm_frame_info_t.pcl_overflow; mode 1: behave like PCL (the frame's output is its cropped cloud). */
 CM_API int cm_set_overflow_mode(cm_handle_t h, int mode);

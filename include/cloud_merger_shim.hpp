@@ -1,0 +1,348 @@
+// cloud_merger_shim.hpp -- header-only C++ host layer over the C ABI (cloud_merger_gpu.h) that re-creates the reference's
+// own function surface for the merge hot path, so a maintainer can swap the PCL calls for the GPU path without touching
+// the ROS node shell:
+//
+//   reference (pc_preprocessing_main.h:80-88, CloudFusionNode.h:59,145,276)      here (namespace cloud_merger)
+//   pcl_ros::transformPointCloud(const Cloud&, Cloud&, const tf::Transform&)  ->  transformPointCloud(in, out, Transform)
+//   void getROI(const Cloud::Ptr, Cloud::Ptr)                                 ->  getROI(in, out)
+//   void getCloudPart(const Cloud::Ptr, Cloud::Ptr, float length, float dev)  ->  getCloudPart(in, out, length, deviation)
+//   void fusePointclouds(Cloud::Ptr no_ground, Cloud::Ptr ground)             ->  FusedFrame::fuse (+ operator+= kept)
+//   void voxelgrid(const Cloud::Ptr, Cloud::Ptr)                              ->  voxelgrid(in, out)
+//   callbackX(const Cloud input) ... main loop fuse + voxelgrid               ->  FusedFrame::onCloud / fuseAndVoxel
+//
+// Cloud = pcl::PointCloud<pcl::PointXYZI> when PCL is present; otherwise the layout-compatible stand-ins below (PCL is
+// not installed in the build image, so the tests use the stand-ins; the record layout -- 32 bytes, x y z at 0 4 8,
+// pad 1.0f at 12, intensity at 16 -- is PCL's own, which makes every copy in and out a memcpy).
+//
+// Error behaviour mirrors the reference: the functions are void; on a GPU / capacity error they leave the output empty
+// and report through last_error() (PCL itself only PCL_WARNs). No CPU fallback exists.
+#ifndef CLOUD_MERGER_SHIM_HPP_
+#define CLOUD_MERGER_SHIM_HPP_
+
+#include <cstdint>
+#include <cstring>
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "cloud_merger_gpu.h"
+
+#if defined(__has_include)
+#if __has_include(<pcl/point_cloud.h>) && __has_include(<pcl/point_types.h>) && !defined(CM_SHIM_NO_PCL)
+#include <pcl/point_cloud.h>
+#include <pcl/point_types.h>
+#define CM_SHIM_HAVE_PCL 1
+#endif
+#endif
+
+namespace cloud_merger {
+
+#ifdef CM_SHIM_HAVE_PCL
+using PointXYZI = pcl::PointXYZI;
+using Cloud = pcl::PointCloud<pcl::PointXYZI>;
+inline uint64_t stamp_of(const Cloud& c) { return c.header.stamp; }
+inline void set_stamp(Cloud& c, uint64_t s) { c.header.stamp = s; }
+#else
+// pcl::PointXYZI (point_types.hpp): PCL_ADD_POINT4D + intensity, 16-byte aligned, sizeof == 32.
+struct alignas(16) PointXYZI {
+  float x = 0.f, y = 0.f, z = 0.f, data3 = 1.f;
+  float intensity = 0.f, data_c1 = 0.f, data_c2 = 0.f, data_c3 = 0.f;
+};
+static_assert(sizeof(PointXYZI) == 32, "PointXYZI must match pcl::PointXYZI");
+// the members of pcl::PointCloud<PointT> the reference touches
+template <typename PointT>
+struct PointCloudT {
+  struct Header {
+    uint64_t stamp = 0;
+    std::string frame_id;
+  } header;
+  std::vector<PointT> points;
+  uint32_t width = 0, height = 0;
+  bool is_dense = true;
+  using Ptr = std::shared_ptr<PointCloudT<PointT>>;
+  size_t size() const { return points.size(); }
+  // pcl::PointCloud::operator+= (PCL 1.8.1): append, newest stamp, width = size, height = 1, is_dense = AND
+  PointCloudT& operator+=(const PointCloudT& rhs) {
+    if (rhs.header.stamp > header.stamp) header.stamp = rhs.header.stamp;
+    points.insert(points.end(), rhs.points.begin(), rhs.points.end());
+    width = static_cast<uint32_t>(points.size());
+    height = 1;
+    is_dense = rhs.is_dense && is_dense;
+    return *this;
+  }
+};
+using Cloud = PointCloudT<PointXYZI>;
+inline uint64_t stamp_of(const Cloud& c) { return c.header.stamp; }
+inline void set_stamp(Cloud& c, uint64_t s) { c.header.stamp = s; }
+#endif
+
+// tf::Transform as the reference builds it: tf::Transform(stf.getRotation(), stf.getOrigin()) (pc_preprocessing_main.cpp:320)
+struct Transform {
+  double q[4] = {0, 0, 0, 1};  // quaternion x y z w
+  double origin[3] = {0, 0, 0};
+};
+
+// Parameter.h:27-35 (pcl_preprocessing) -- the reference's compile-time constants
+struct Params {
+  float voxel_size = 0.1f;
+  int points_per_voxel = 2;
+  float roi_width = 10.0f, roi_length = 75.0f, roi_mid = 15.0f, roi_z_min = -0.5f, roi_z_max = 3.0f;
+};
+
+inline cm_layout_t pcl_layout(bool is_dense) {
+  cm_layout_t l;
+  l.point_step = 32; l.off_x = 0; l.off_y = 4; l.off_z = 8; l.off_intensity = 16; l.is_dense = is_dense ? 1 : 0;
+  return l;
+}
+
+// One GPU context shared by the drop-in functions. Capacity = largest single cloud / fused frame it will be handed.
+class Context {
+ public:
+  explicit Context(int64_t max_points_per_cloud = 1 << 20, int max_sensors = 6, int device = 0, Params p = Params())
+      : params_(p), max_points_(max_points_per_cloud), max_sensors_(max_sensors) {
+    cm_config_t cfg;
+    std::memset(&cfg, 0, sizeof(cfg));
+    cfg.device = device;
+    cfg.max_sensors = max_sensors;
+    cfg.max_points_per_sensor = max_points_per_cloud;
+    cfg.max_point_step = 32;
+    cfg.frames_in_flight = 2;
+    cfg.max_batch_points = max_points_per_cloud * max_sensors;
+    cfg.max_batch_frames = 1;
+    cfg.out_point_step = 32;  // pcl::PointXYZI records straight out of the kernels
+    rc_ = cm_create(&cfg, &h_);
+    if (rc_ != CM_OK) { h_ = nullptr; err_ = cm_strerror(rc_); }
+  }
+  ~Context() {
+    if (h_) {
+      if (dev_in_) cm_dev_free(h_, dev_in_);
+      cm_destroy(h_);
+    }
+  }
+  Context(const Context&) = delete;
+  Context& operator=(const Context&) = delete;
+
+  bool ok() const { return h_ != nullptr; }
+  cm_handle_t handle() const { return h_; }
+  const Params& params() const { return params_; }
+  const std::string& last_error() const { return err_; }
+  int last_status() const { return rc_; }
+
+  // transform + crop of ONE host cloud (stage entry cm_dev_transform_crop); out keeps input order.
+  bool transform_crop(const Cloud& in, Cloud& out, const float* m16_row_major, int n_pass, const cm_pass_t* passes) {
+    if (!check(h_ ? CM_OK : CM_E_NO_DEVICE)) return clear(out);
+    const int64_t n = static_cast<int64_t>(in.points.size());
+    if (n > max_points_) { rc_ = CM_E_CAPACITY; err_ = "cloud larger than the context capacity"; return clear(out); }
+    if (!stage_in(in.points.data(), n)) return clear(out);
+    if (!check(cm_set_extrinsic(h_, 0, m16_row_major, 0)) || !check(cm_set_crop(h_, n_pass, passes))) return clear(out);
+    cm_segment_t seg;
+    seg.data = dev_in_; seg.n_points = n; seg.layout = pcl_layout(in.is_dense); seg.sensor = 0; seg.frame = 0;
+    if (!check(cm_dev_transform_crop(h_, &seg, 1, nullptr))) return clear(out);
+    cm_stats_t st;
+    cm_device_out_t o;
+    if (!check(cm_get_stats(h_, &st)) || !check(cm_get_device_out(h_, &o))) return clear(out);
+    const size_t m = static_cast<size_t>(st.survivors);
+    tmp_.resize(m * 4);
+    if (m && !check(cm_memcpy_d2h(h_, tmp_.data(), o.survivor_xyzi, m * 16, nullptr))) return clear(out);
+    out.points.resize(m);
+    for (size_t i = 0; i < m; ++i) {
+      PointXYZI& p = out.points[i];
+      p = PointXYZI();
+      p.x = tmp_[i * 4 + 0]; p.y = tmp_[i * 4 + 1]; p.z = tmp_[i * 4 + 2]; p.intensity = tmp_[i * 4 + 3];
+    }
+    finish(out, in, n_pass > 0 ? true : in.is_dense);
+    return true;
+  }
+
+  // VoxelGrid of ONE host cloud (stage entry cm_dev_voxelgrid).
+  bool voxelgrid(const Cloud& in, Cloud& out) {
+    if (!check(h_ ? CM_OK : CM_E_NO_DEVICE)) return clear(out);
+    const int64_t n = static_cast<int64_t>(in.points.size());
+    if (n > max_points_ * max_sensors_) { rc_ = CM_E_CAPACITY; err_ = "cloud larger than the context capacity"; return clear(out); }
+    // the voxel stage reads packed xyzi
+    tmp_.resize(static_cast<size_t>(n) * 4);
+    for (int64_t i = 0; i < n; ++i) {
+      const PointXYZI& p = in.points[static_cast<size_t>(i)];
+      tmp_[i * 4 + 0] = p.x; tmp_[i * 4 + 1] = p.y; tmp_[i * 4 + 2] = p.z; tmp_[i * 4 + 3] = p.intensity;
+    }
+    if (!stage_in(tmp_.data(), n, 16)) return clear(out);
+    const float leaf[3] = {params_.voxel_size, params_.voxel_size, params_.voxel_size};
+    if (!check(cm_set_voxel(h_, leaf, params_.points_per_voxel, 1))) return clear(out);
+    if (!check(cm_dev_voxelgrid(h_, static_cast<const float*>(dev_in_), n, in.is_dense ? 1 : 0, nullptr))) return clear(out);
+    cm_stats_t st;
+    cm_device_out_t o;
+    if (!check(cm_get_stats(h_, &st)) || !check(cm_get_device_out(h_, &o))) return clear(out);
+    if (st.pcl_overflow) {  // PCL 1.8.1: "Leaf size is too small for the input dataset" -> output = input
+      out = in;
+      return true;
+    }
+    const size_t v = static_cast<size_t>(st.voxels_out);
+    out.points.resize(v);
+    if (v && !check(cm_memcpy_d2h(h_, out.points.data(), o.voxel_xyzi, v * 32, nullptr))) return clear(out);
+    finish(out, in, true);
+    return true;
+  }
+
+ private:
+  bool check(int rc) {
+    rc_ = rc;
+    if (rc != CM_OK) err_ = std::string(cm_strerror(rc)) + ": " + (h_ ? cm_last_error(h_) : "");
+    return rc == CM_OK;
+  }
+  static bool clear(Cloud& out) {
+    out.points.clear(); out.width = 0; out.height = 1;
+    return false;
+  }
+  static void finish(Cloud& out, const Cloud& in, bool dense) {
+    out.width = static_cast<uint32_t>(out.points.size());
+    out.height = 1;
+    out.is_dense = dense;
+    out.header = in.header;
+  }
+  bool stage_in(const void* host, int64_t n, int step = 32) {
+    const size_t need = static_cast<size_t>(max_points_) * max_sensors_ * 32 + 64;
+    if (!dev_in_ && !check(cm_dev_alloc(h_, &dev_in_, need))) return false;
+    if (n == 0) return true;
+    return check(cm_memcpy_h2d(h_, dev_in_, host, static_cast<size_t>(n) * step, nullptr));
+  }
+
+  Params params_;
+  int64_t max_points_;
+  int max_sensors_;
+  cm_handle_t h_ = nullptr;
+  void* dev_in_ = nullptr;
+  std::vector<float> tmp_;
+  std::string err_;
+  int rc_ = CM_OK;
+};
+
+inline void matrix_from_transform(const Transform& t, float* m16) {
+  // pcl_ros::transformPointCloud: Eigen::Quaternionf(q.w, q.x, q.y, q.z), Vector3f(origin), Eigen 3.3 toRotationMatrix
+  const float x = static_cast<float>(t.q[0]), y = static_cast<float>(t.q[1]), z = static_cast<float>(t.q[2]),
+              w = static_cast<float>(t.q[3]);
+  const float tx = 2.0f * x, ty = 2.0f * y, tz = 2.0f * z;
+  const float twx = tx * w, twy = ty * w, twz = tz * w, txx = tx * x, txy = ty * x, txz = tz * x;
+  const float tyy = ty * y, tyz = tz * y, tzz = tz * z;
+  const float m[16] = {1.0f - (tyy + tzz), txy - twz, txz + twy, static_cast<float>(t.origin[0]),
+                       txy + twz, 1.0f - (txx + tzz), tyz - twx, static_cast<float>(t.origin[1]),
+                       txz - twy, tyz + twx, 1.0f - (txx + tyy), static_cast<float>(t.origin[2]),
+                       0.f, 0.f, 0.f, 1.f};
+  std::memcpy(m16, m, sizeof(m));
+}
+
+// ---- the reference's functions, same names and argument meaning -------------------------------------------------------
+
+// pcl_ros::transformPointCloud(input, *cloud_ptr, transform) -- pc_preprocessing_main.cpp:322
+inline void transformPointCloud(Context& ctx, const Cloud& in, Cloud& out, const Transform& tf) {
+  float m[16];
+  matrix_from_transform(tf, m);
+  ctx.transform_crop(in, out, m, 0, nullptr);
+}
+
+// void getROI(const Cloud::Ptr cloud_ptr, Cloud::Ptr cloud_ROI_ptr) -- pc_preprocessing_main.cpp:20-40
+inline void getROI(Context& ctx, const Cloud::Ptr& cloud_ptr, const Cloud::Ptr& cloud_ROI_ptr) {
+  const Params& p = ctx.params();
+  const cm_pass_t passes[3] = {{2, p.roi_z_min, p.roi_z_max, 0},
+                               {1, -p.roi_width / 2, p.roi_width / 2, 0},
+                               {0, -p.roi_mid, p.roi_length - p.roi_mid, 0}};
+  const float eye[16] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1};
+  Cloud tmp;
+  ctx.transform_crop(*cloud_ptr, tmp, eye, 3, passes);
+  *cloud_ROI_ptr = tmp;
+}
+
+// void getCloudPart(const Cloud::Ptr, Cloud::Ptr, const float length, const float deviation) -- :49-59
+inline void getCloudPart(Context& ctx, const Cloud::Ptr& cloud_ptr, const Cloud::Ptr& cloud_part_ptr, const float length,
+                         const float deviation) {
+  const cm_pass_t pass = {0, deviation, deviation + length, 0};
+  const float eye[16] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1};
+  Cloud tmp;
+  ctx.transform_crop(*cloud_ptr, tmp, eye, 1, &pass);
+  *cloud_part_ptr = tmp;
+}
+
+// void voxelgrid(const Cloud::Ptr cloud_ptr, Cloud::Ptr voxel_cloud_ptr) -- :168-177
+inline void voxelgrid(Context& ctx, const Cloud::Ptr& cloud_ptr, const Cloud::Ptr& voxel_cloud_ptr) {
+  Cloud tmp;
+  ctx.voxelgrid(*cloud_ptr, tmp);
+  *voxel_cloud_ptr = tmp;
+}
+
+// ---- the fused per-frame flow: callbacks submit, the main loop merges ------------------------------------------------------
+// Replaces, together: callbackX (transform + getROI) -> globals + flags -> fusePointclouds -> voxelgrid
+// (pc_preprocessing_main.cpp:318-337, :131-177, main loop :574-578). One GPU pass per frame instead of ~20 CPU passes.
+class FusedFrame {
+ public:
+  FusedFrame(int n_sensors, int64_t max_points_per_sensor, uint64_t required_mask, int device = 0, Params p = Params())
+      : params_(p), n_sensors_(n_sensors), required_(required_mask), cap_(max_points_per_sensor * n_sensors) {
+    cm_config_t cfg;
+    std::memset(&cfg, 0, sizeof(cfg));
+    cfg.device = device; cfg.max_sensors = n_sensors; cfg.max_points_per_sensor = max_points_per_sensor;
+    cfg.max_point_step = 32; cfg.frames_in_flight = 2; cfg.max_batch_frames = 1; cfg.out_point_step = 32;
+    if (cm_create(&cfg, &h_) != CM_OK) h_ = nullptr;
+    if (h_) {
+      const cm_pass_t passes[3] = {{2, p.roi_z_min, p.roi_z_max, 0}, {1, -p.roi_width / 2, p.roi_width / 2, 0},
+                                   {0, -p.roi_mid, p.roi_length - p.roi_mid, 0}};
+      cm_set_crop(h_, 3, passes);
+      const float leaf[3] = {p.voxel_size, p.voxel_size, p.voxel_size};
+      cm_set_voxel(h_, leaf, p.points_per_voxel, 1);
+      cm_set_overflow_mode(h_, 1);  // behave like PCL when the leaf is too small
+    }
+  }
+  ~FusedFrame() { if (h_) cm_destroy(h_); }
+  FusedFrame(const FusedFrame&) = delete;
+  FusedFrame& operator=(const FusedFrame&) = delete;
+  bool ok() const { return h_ != nullptr; }
+  cm_handle_t handle() const { return h_; }
+
+  // once, after the TF lookup (pc_preprocessing_main.cpp:551-568)
+  void setTransform(int sensor, const Transform& tf) { if (h_) cm_set_extrinsic_tf(h_, sensor, tf.q, tf.origin); }
+
+  // body of callbackFrontRight ... callbackFrontMiddle: hands the raw cloud over; thread-safe per sensor
+  void onCloud(int sensor, const Cloud& input) {
+    if (!h_) return;
+    const cm_layout_t l = pcl_layout(input.is_dense);
+    if (cm_submit_cloud(h_, sensor, input.points.data(), static_cast<int64_t>(input.points.size()), &l, stamp_of(input)) == CM_OK)
+      seen_ |= 1ull << sensor;
+  }
+
+  // fusePointclouds + voxelgrid. Returns false (like the reference's flag gate, :134) until every required sensor has
+  // delivered; optional sensors are merged when present.
+  bool fuseAndVoxel(Cloud& fused, Cloud& voxel) {
+    if (!h_ || (seen_ & required_) != required_) return false;
+    fused.points.resize(static_cast<size_t>(cap_));
+    voxel.points.resize(static_cast<size_t>(cap_));
+    sx_.resize(static_cast<size_t>(cap_) * 4);
+    cm_frame_out_t o;
+    std::memset(&o, 0, sizeof(o));
+    o.voxel_xyzi = voxel.points.data(); o.voxel_capacity = cap_;
+    o.survivor_xyzi = sx_.data(); o.survivor_capacity = cap_;
+    uint64_t used = 0, stamp = 0;
+    const int rc = cm_merge_frame(h_, ~0ull, &o, &used, &stamp);
+    seen_ = 0;
+    if (rc != CM_OK) { fused.points.clear(); voxel.points.clear(); return false; }
+    fused.points.resize(static_cast<size_t>(o.n_survivors));
+    for (int64_t i = 0; i < o.n_survivors; ++i) {
+      PointXYZI& p = fused.points[static_cast<size_t>(i)];
+      p = PointXYZI();
+      p.x = sx_[i * 4 + 0]; p.y = sx_[i * 4 + 1]; p.z = sx_[i * 4 + 2]; p.intensity = sx_[i * 4 + 3];
+    }
+    voxel.points.resize(static_cast<size_t>(o.n_voxels));
+    for (Cloud* c : {&fused, &voxel}) {
+      c->width = static_cast<uint32_t>(c->points.size()); c->height = 1; c->is_dense = true; set_stamp(*c, stamp);
+    }
+    return true;
+  }
+
+ private:
+  Params params_;
+  int n_sensors_;
+  uint64_t required_, seen_ = 0;
+  int64_t cap_;
+  cm_handle_t h_ = nullptr;
+  std::vector<float> sx_;
+};
+
+}  // namespace cloud_merger
+
+#endif  // CLOUD_MERGER_SHIM_HPP_

@@ -61,11 +61,13 @@ def crop(xyzi: np.ndarray, passes) -> np.ndarray:
     return keep
 
 
-def voxelgrid(xyzi: np.ndarray, leaf, min_points: int = 0, downsample_all: bool = True, force64: bool = True):
+def voxelgrid(xyzi: np.ndarray, leaf, min_points: int = 0, downsample_all: bool = True, force64: bool = True,
+              bounds=None):
     """a8: pcl::VoxelGrid::applyFilter (PCL 1.8.1), reference voxelgrid pc_preprocessing_main.cpp:168-177.
 
     Returns dict(idx, count, centroid_f64, point_idx, min_b, max_b, div_b, pcl_overflow). Centroids are accumulated in
-    float64 in ascending point order (the tolerance anchor)."""
+    float64 in ascending point order (the tolerance anchor). bounds = (min_p, max_p) replaces the cloud's own bounding
+    box (used for a cloud that is one part of a larger, partitioned cloud)."""
     xyzi = np.asarray(xyzi, dtype=F32)
     n = len(xyzi)
     leaf = np.asarray(leaf, dtype=F32)
@@ -79,6 +81,9 @@ def voxelgrid(xyzi: np.ndarray, leaf, min_points: int = 0, downsample_all: bool 
     pts = xyzi[fin]
     min_p = pts[:, :3].min(axis=0).astype(F32)
     max_p = pts[:, :3].max(axis=0).astype(F32)
+    if bounds is not None:
+        min_p = np.minimum(min_p, np.asarray(bounds[0], F32))
+        max_p = np.maximum(max_p, np.asarray(bounds[1], F32))
     d = ((max_p - min_p).astype(F32) * inv).astype(F32)
     dxyz = [int(np.trunc(np.float64(v))) + 1 for v in d]
     res["pcl_overflow"] = (dxyz[0] * dxyz[1] * dxyz[2]) > INT32_MAX

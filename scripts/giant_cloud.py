@@ -1,0 +1,95 @@
+#!/usr/bin/env python
+"""BASELINE config 4: VoxelGrid of one aggregated map cloud partitioned over the GPUs of one box by voxel-key range, with
+one NCCL all-to-all (cloud_merger_b200/multi_gpu.py). Launch with torchrun (one rank per GPU) or plainly for one GPU.
+Prints one JSON line on rank 0. --check compares against the CPU oracle (small clouds only)."""
+import argparse
+import json
+import os
+import sys
+import time
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from cloud_merger_b200 import CloudMerger, multi_gpu, synth  # noqa: E402
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--points", type=int, default=100_000_000)
+    ap.add_argument("--leaf", type=float, default=0.02)
+    ap.add_argument("--min-points", type=int, default=1)
+    ap.add_argument("--iters", type=int, default=3)
+    ap.add_argument("--check", action="store_true")
+    a = ap.parse_args()
+    rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
+    local_rank = int(os.environ.get("LOCAL_RANK", 0))
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    n = a.points
+    lo, hi = rank * n // world, (rank + 1) * n // world
+    # every rank generates the same cloud chunk-wise and keeps its block (deterministic, no host exchange)
+    whole = synth.map_cloud(4, n)
+    local = torch.from_numpy(np.ascontiguousarray(whole[lo:hi])).cuda()
+    if not a.check:
+        whole = None
+    # capacity: a rank may receive more than its share
+    cap = int(min(n, (hi - lo) * 2 + 1024))
+    cm = CloudMerger(device=local_rank, max_batch_points=cap)
+    backend = multi_gpu.cuda_voxelgrid_backend(cm, a.leaf, a.min_points)
+    times, out = [], None
+    for it in range(a.iters + 1):
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        out = multi_gpu.giant_cloud_voxelgrid(local, [a.leaf] * 3, a.min_points, backend, rank, world)
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        if it:
+            times.append(time.perf_counter() - t0)
+    dt = float(np.median(times))
+    stats = torch.tensor([out["points_received"], out["points_sent_away"], len(out["idx"])], dtype=torch.int64, device="cuda")
+    if world > 1:
+        allv = [torch.zeros_like(stats) for _ in range(world)]
+        dist.all_gather(allv, stats)
+    else:
+        allv = [stats]
+    check = None
+    if a.check:
+        from oracle import cm_oracle_py as oracle
+        gathered = [None] * world
+        mine = (rank, out["idx"], out["count"], out["centroid"])
+        if world > 1:
+            dist.all_gather_object(gathered, mine)
+        else:
+            gathered = [mine]
+        if rank == 0:
+            gathered.sort(key=lambda t: t[0])
+            idx = np.concatenate([g[1] for g in gathered]); cnt = np.concatenate([g[2] for g in gathered])
+            cen = np.concatenate([g[3] for g in gathered])
+            o = oracle.voxelgrid(whole, [a.leaf] * 3, a.min_points, True, force64=True)
+            ok = len(idx) == o["n"] and (idx == o["idx"]).all() and (cnt == o["count"]).all()
+            rel = np.abs(cen - o["centroid_f64"]) / np.maximum(np.abs(o["centroid_f64"]), 1e-2)
+            ok = ok and rel.max() <= 1e-5
+            check = "ok" if ok else "MISMATCH"
+    if rank == 0:
+        sent = int(sum(int(v[1]) for v in allv))
+        print(json.dumps({"workload": "cfg4: %d-pt map cloud, VoxelGrid %.3f m, key-range partition + all-to-all" % (n, a.leaf),
+                          "n_gpus": world, "points": n, "voxels": int(sum(int(v[2]) for v in allv)), "ms": dt * 1e3,
+                          "mpoints_per_s": n / dt / 1e6, "points_exchanged": sent, "bytes_exchanged": sent * 16,
+                          "points_per_rank_after": [int(v[0]) for v in allv], "key_bits": out.get("key_bits"),
+                          "local_voxelgrid_ms": out.get("gpu_ms"), "check": check}))
+    cm.close()
+    if world > 1:
+        dist.destroy_process_group()
+    return 0 if check in (None, "ok") else 1
+
+
+if __name__ == "__main__":
+    sys.exit(main())

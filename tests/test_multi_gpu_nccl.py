@@ -1,0 +1,51 @@
+"""GPU tests of the giant-cloud mode: the CUDA backend behind multi_gpu.giant_cloud_voxelgrid (cm_set_voxel_bounds +
+cm_dev_voxelgrid), on one GPU always and on two ranks over NCCL when the box has two GPUs."""
+import json
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+from cloud_merger_b200 import CloudMerger, multi_gpu, synth
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_giant_backend_single_gpu(gpu_ok, oracle):
+    import torch
+    n, leaf, min_points = 400000, 0.1, 1
+    whole = synth.map_cloud(7, n, extent=(120.0, 120.0, 10.0), n_boxes=100)
+    whole[::1013, 1] = np.nan
+    with CloudMerger(max_batch_points=n) as cm:
+        pts = torch.from_numpy(whole).cuda()
+        out = multi_gpu.giant_cloud_voxelgrid(pts, [leaf] * 3, min_points,
+                                              multi_gpu.cuda_voxelgrid_backend(cm, leaf, min_points), 0, 1)
+    o = oracle.voxelgrid(whole, [leaf] * 3, min_points, True, force64=True, is_dense=False)
+    assert (out["idx"] == o["idx"]).all() and (out["count"] == o["count"]).all()
+    assert (out["centroid"].view(np.uint32) == o["centroid"].view(np.uint32)).all()
+    # bounds wider than the local cloud shift the grid origin exactly as a larger cloud would
+    with CloudMerger(max_batch_points=n) as cm:
+        cm.set_voxel(leaf, 1, True)
+        lo = whole[np.isfinite(whole[:, :3]).all(axis=1), :3].min(axis=0) - np.float32(3.3)
+        hi = whole[np.isfinite(whole[:, :3]).all(axis=1), :3].max(axis=0) + np.float32(1.7)
+        cm.set_voxel_bounds(lo, hi)
+        buf = cm.upload(whole)
+        cm.dev_voxelgrid(buf.ptr, n, False)
+        fi = cm.frame_info()[0]
+    inv = np.float32(1.0) / np.float32(leaf)
+    assert list(fi.min_b) == np.floor((lo * inv).astype(np.float32)).astype(int).tolist()
+
+
+def test_giant_cloud_two_ranks_nccl(gpu_ok):
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+                        "--master-addr", "127.0.0.1", "--master-port", "29617", os.path.join(ROOT, "scripts", "giant_cloud.py"),
+                        "--points", "2000000", "--leaf", "0.1", "--check"], capture_output=True, text=True, timeout=600, cwd=ROOT)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+    line = json.loads([l for l in r.stdout.splitlines() if l.startswith("{")][-1])
+    assert line["check"] == "ok" and line["n_gpus"] == 2
