@@ -235,6 +235,7 @@ def main():
         raise SystemExit("bench.py: no CUDA device (the product path has no CPU fallback)")
     torch.cuda.set_device(local_rank)
     if world > 1:
+        os.environ.setdefault("NCCL_DEBUG", "WARN")  # keep NCCL's version banner off stdout (one JSON line only)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
     def barrier():
