@@ -300,40 +300,57 @@ __global__ void __launch_bounds__(VX_THREADS) k_voxel_key_hist(const VoxelParams
     }
     if (r.count == 0) continue;
     const GridDev g = p.grid[r.frame];
-    const unsigned long long fbits = (unsigned long long)r.frame << idx_bits;
-    const uint32_t rounds = (r.count + VX_THREADS - 1) / VX_THREADS;
+    const KeyT fbits = (KeyT)((unsigned long long)r.frame << idx_bits);
+    const KeyT mul1 = (KeyT)g.mul1, mul2 = (KeyT)g.mul2;  // 32-bit arithmetic when the key is 32-bit
+    const int mb0 = g.min_b[0], mb1 = g.min_b[1], mb2 = g.min_b[2];
+    constexpr int U = 4;  // points per thread in flight
+    const uint32_t rounds = (r.count + U * VX_THREADS - 1) / (U * VX_THREADS);
     for (uint32_t it = 0; it < rounds; ++it) {
-      const uint32_t j = it * VX_THREADS + tid;
-      const bool valid = j < r.count;
-      unsigned long long key = 0;
-      if (valid) {
-        const float4 v = ldg_stream_f4(p.pts + r.slot0 + j);
-        if (finite_f32(v.x) && finite_f32(v.y) && finite_f32(v.z)) {
-          // PCL: ijk = (int)(floor(x * inv) - (float)min_b); here in integers (identical below 2^24 cells)
-          const long long i0 = (long long)(int)floorf(__fmul_rn(v.x, inv0)) - (long long)g.min_b[0];
-          const long long i1 = (long long)(int)floorf(__fmul_rn(v.y, inv1)) - (long long)g.min_b[1];
-          const long long i2 = (long long)(int)floorf(__fmul_rn(v.z, inv2)) - (long long)g.min_b[2];
-          const unsigned long long cell =
-              (unsigned long long)i0 + (unsigned long long)i1 * g.mul1 + (unsigned long long)i2 * g.mul2;
-          key = fbits | cell;
-        } else {
-          key = sentinel;
-        }
-        keys[r.dense0 + j] = (KeyT)key;
-        vals[r.dense0 + j] = r.slot0 + j;
+      float4 pv[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const uint32_t j = (it * U + u) * VX_THREADS + tid;
+        pv[u] = (j < r.count) ? ldg_stream_f4(p.pts + r.slot0 + j) : make_float4(0.f, 0.f, 0.f, 0.f);
       }
-      // digit histograms; a warp whose valid lanes all share the digit adds once
-      const uint32_t vmask = __ballot_sync(0xFFFFFFFFu, valid);
-      if (vmask) {
-        const int leader = __ffs(vmask) - 1;
-        for (uint32_t ps = 0; ps < n_pass; ++ps) {
-          const uint32_t d = (uint32_t)(key >> (ps * CM_RADIX_BITS)) & (CM_RADIX - 1);
-          const uint32_t dl = __shfl_sync(0xFFFFFFFFu, d, leader);
-          const bool uniform = __all_sync(0xFFFFFFFFu, !valid || d == dl);
-          if (uniform) {
-            if ((int)lane == leader) atomicAdd(&s_hist[ps][dl], (uint32_t)__popc(vmask));
-          } else if (valid) {
-            atomicAdd(&s_hist[ps][d], 1u);
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const uint32_t j = (it * U + u) * VX_THREADS + tid;
+        const bool valid = j < r.count;
+        const float4 v = pv[u];
+        KeyT key = 0;
+        if (valid) {
+          if (finite_f32(v.x) && finite_f32(v.y) && finite_f32(v.z)) {
+            // PCL: ijk = (int)(floor(x * inv) - (float)min_b); here in integers (identical below 2^24 cells)
+            const KeyT i0 = (KeyT)((int)floorf(__fmul_rn(v.x, inv0)) - mb0);
+            const KeyT i1 = (KeyT)((int)floorf(__fmul_rn(v.y, inv1)) - mb1);
+            const KeyT i2 = (KeyT)((int)floorf(__fmul_rn(v.z, inv2)) - mb2);
+            key = fbits | (KeyT)(i0 + i1 * mul1 + i2 * mul2);
+          } else {
+            key = (KeyT)sentinel;
+          }
+          keys[r.dense0 + j] = key;
+          vals[r.dense0 + j] = r.slot0 + j;
+        }
+        // digit histograms. Bits on which all valid lanes of the warp agree are found with two warp reductions; a digit
+        // made only of such bits (the frame bits, the high cell bits of a spatially coherent tile) is added once per warp.
+        const uint32_t vmask = __ballot_sync(0xFFFFFFFFu, valid);
+        if (vmask) {
+          const uint32_t klo = (uint32_t)key;
+          uint32_t diff_lo = __reduce_or_sync(0xFFFFFFFFu, valid ? klo : 0u) ^ __reduce_and_sync(0xFFFFFFFFu, valid ? klo : 0xFFFFFFFFu);
+          uint32_t diff_hi = 0;
+          if (sizeof(KeyT) == 8) {
+            const uint32_t khi = (uint32_t)((unsigned long long)key >> 32);
+            diff_hi = __reduce_or_sync(0xFFFFFFFFu, valid ? khi : 0u) ^ __reduce_and_sync(0xFFFFFFFFu, valid ? khi : 0xFFFFFFFFu);
+          }
+          const unsigned long long diff = ((unsigned long long)diff_hi << 32) | diff_lo;
+          const int leader = __ffs(vmask) - 1;
+          for (uint32_t ps = 0; ps < n_pass; ++ps) {
+            const uint32_t d = (uint32_t)((unsigned long long)key >> (ps * CM_RADIX_BITS)) & (CM_RADIX - 1);
+            if (((diff >> (ps * CM_RADIX_BITS)) & (CM_RADIX - 1)) == 0) {
+              if ((int)lane == leader) atomicAdd(&s_hist[ps][d], (uint32_t)__popc(vmask));
+            } else if (valid) {
+              atomicAdd(&s_hist[ps][d], 1u);
+            }
           }
         }
       }
@@ -388,12 +405,23 @@ __global__ void __launch_bounds__(VX_THREADS) k_voxel_centroid(const VoxelParams
     k[j] = in ? keys[base + j] : (KeyT)0;
     v[j] = in ? vals[base + j] : 0u;
   }
-  KeyT prev = (KeyT)0;
-  if (base > 0 && loc < tile_n) prev = keys[base - 1];
+  KeyT prev = (KeyT)0, next = (KeyT)0;
+  const bool has_prev = base > 0 && loc < tile_n;
+  const bool has_next = base + CE_IPT < M;
+  if (has_prev) prev = keys[base - 1];
+  if (has_next) next = keys[base + CE_IPT];
+  // With min_points <= 2 a point is needed only when its run survives the filter: every point for 1, a point with an
+  // equal neighbour for 2. Singleton voxels (most of a sparse lidar frame) are then never gathered.
 #pragma unroll
   for (int j = 0; j < CE_IPT; ++j) {
     if (loc + j < tile_n) {
-      s_pts[loc + j] = __ldg(p.pts + v[j]);
+      bool need = m_req != 2u;
+      if (!need) {
+        const bool eq_prev = (j == 0) ? (has_prev && prev == k[0]) : (k[j - 1] == k[j]);
+        const bool eq_next = (j == CE_IPT - 1) ? (has_next && next == k[j]) : (loc + j + 1 < tile_n ? k[j + 1] == k[j] : (base + j + 1 < M && keys[base + j + 1] == k[j]));
+        need = eq_prev || eq_next;
+      }
+      if (need) s_pts[loc + j] = __ldg(p.pts + v[j]);
       s_keys[loc + j] = k[j];
     }
   }
