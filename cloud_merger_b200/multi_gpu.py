@@ -123,17 +123,23 @@ def giant_cloud_voxelgrid(local_xyzi: torch.Tensor, leaf: Sequence[float], min_p
     Returns this rank's voxels (ascending idx; ranks hold ascending, disjoint key ranges) plus exchange statistics."""
     min_p, max_p, min_b, div_b = global_grid(local_xyzi, leaf, group)
     n_cells = int(div_b[0]) * int(div_b[1]) * int(div_b[2])
-    keys = voxel_keys(local_xyzi, leaf, min_b, div_b)
-    splitters = pick_splitters(keys, n_cells, world, group=group) if world > 1 else torch.zeros(0, dtype=torch.int64)
-    recv = exchange_by_key_range(local_xyzi, keys, splitters.to(keys.device), rank, world, group)
+    if world > 1:
+        keys = voxel_keys(local_xyzi, leaf, min_b, div_b)
+        splitters = pick_splitters(keys, n_cells, world, group=group).to(keys.device)
+        recv = exchange_by_key_range(local_xyzi, keys, splitters, rank, world, group)
+        dest = torch.searchsorted(splitters, keys, right=True)
+        sent_away = int(((dest != rank) & (keys >= 0)).sum().item())
+    else:
+        splitters, recv, sent_away = torch.zeros(0, dtype=torch.int64), local_xyzi, 0
     out = voxelgrid_local(recv, min_p, max_p)
-    out.update(points_received=int(recv.shape[0]), points_sent_away=int((torch.searchsorted(splitters.to(keys.device), keys, right=True) != rank).sum().item()) if world > 1 else 0,
-               min_b=min_b, div_b=div_b, splitters=splitters.cpu().numpy())
+    out.update(points_received=int(recv.shape[0]), points_sent_away=sent_away, min_b=min_b, div_b=div_b,
+               splitters=splitters.cpu().numpy())
     return out
 
 
-def cuda_voxelgrid_backend(merger, leaf, min_points: int):
-    """The product backend of giant_cloud_voxelgrid: the CUDA VoxelGrid of this package on the received points."""
+def cuda_voxelgrid_backend(merger, leaf, min_points: int, download: bool = True):
+    """The product backend of giant_cloud_voxelgrid: the CUDA VoxelGrid of this package on the received points.
+    download=False leaves the voxels on the device (cm_get_device_out) and returns only their number."""
     merger.set_voxel(leaf, min_points, True)
 
     def run(points: torch.Tensor, min_p: np.ndarray, max_p: np.ndarray) -> dict:
@@ -142,11 +148,15 @@ def cuda_voxelgrid_backend(merger, leaf, min_points: int):
         stream = torch.cuda.current_stream().cuda_stream
         merger.dev_voxelgrid(points.data_ptr(), int(points.shape[0]), True, stream=stream)
         st = merger.stats()
-        o = merger.device_out()
         v = int(st.voxels_out)
-        step_f = merger.out_point_step // 4
-        cen = merger.download(o.voxel_xyzi, np.float32, v * step_f).reshape(v, step_f)
-        return dict(idx=merger.download(o.voxel_idx, np.uint64, v).astype(np.int64),
-                    count=merger.download(o.voxel_count, np.uint32, v), centroid=cen[:, :4] if step_f == 4 else
-                    np.concatenate([cen[:, 0:3], cen[:, 4:5]], axis=1), gpu_ms=float(st.gpu_ms), key_bits=int(st.key_bits))
+        res = dict(n_voxels=v, gpu_ms=float(st.gpu_ms), key_bits=int(st.key_bits), idx=np.zeros(0, np.int64),
+                   count=np.zeros(0, np.uint32), centroid=np.zeros((0, 4), np.float32))
+        if download:
+            o = merger.device_out()
+            step_f = merger.out_point_step // 4
+            cen = merger.download(o.voxel_xyzi, np.float32, v * step_f).reshape(v, step_f)
+            res.update(idx=merger.download(o.voxel_idx, np.uint64, v).astype(np.int64),
+                       count=merger.download(o.voxel_count, np.uint32, v),
+                       centroid=cen[:, :4] if step_f == 4 else np.concatenate([cen[:, 0:3], cen[:, 4:5]], axis=1))
+        return res
     return run

@@ -40,7 +40,7 @@ def main():
     # capacity: a rank may receive more than its share
     cap = int(min(n, (hi - lo) * 2 + 1024))
     cm = CloudMerger(device=local_rank, max_batch_points=cap)
-    backend = multi_gpu.cuda_voxelgrid_backend(cm, a.leaf, a.min_points)
+    backend = multi_gpu.cuda_voxelgrid_backend(cm, a.leaf, a.min_points, download=a.check)
     times, out = [], None
     for it in range(a.iters + 1):
         if world > 1:
@@ -54,7 +54,7 @@ def main():
         if it:
             times.append(time.perf_counter() - t0)
     dt = float(np.median(times))
-    stats = torch.tensor([out["points_received"], out["points_sent_away"], len(out["idx"])], dtype=torch.int64, device="cuda")
+    stats = torch.tensor([out["points_received"], out["points_sent_away"], out["n_voxels"]], dtype=torch.int64, device="cuda")
     if world > 1:
         allv = [torch.zeros_like(stats) for _ in range(world)]
         dist.all_gather(allv, stats)

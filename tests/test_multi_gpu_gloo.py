@@ -66,7 +66,7 @@ def test_frame_sharding_world2():
 def _np_backend(leaf, min_points):
     def run(points, min_p, max_p):
         r = npo.voxelgrid(points.cpu().numpy(), leaf, min_points, True, True, bounds=(min_p, max_p))
-        return dict(idx=r["idx"], count=r["count"], centroid=r["centroid_f64"])
+        return dict(idx=r["idx"], count=r["count"], centroid=r["centroid_f64"], n_voxels=len(r["idx"]))
     return run
 
 
