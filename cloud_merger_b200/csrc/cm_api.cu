@@ -1031,8 +1031,17 @@ int cm_get_device_out(cm_handle_t h, cm_device_out_t* out) {
   }
   if (w.ran_voxel) {
     const bool odd = (h->stats.sort_passes & 1) != 0;
-    out->sorted_key = odd ? w.keys_b : w.keys_a;
-    out->sorted_point = odd ? w.vals_b : w.vals_a;
+    if (w.key_bytes == 4) {
+      // 32-bit keys are sorted as 8-byte (key, value) records: split them into the two arrays this struct promises
+      const uint32_t* n_ptr = reinterpret_cast<const uint32_t*>(w.meta + w.ml.off_fstart) + w.n_frames;
+      CM_CUDA(h, launch_split_records(odd ? w.keys_b : w.keys_a, w.vals_a, w.vals_b, n_ptr, (uint32_t)w.points_in, w.stream));
+      CM_CUDA(h, cudaStreamSynchronize(w.stream));
+      out->sorted_key = w.vals_a;
+      out->sorted_point = w.vals_b;
+    } else {
+      out->sorted_key = odd ? w.keys_b : w.keys_a;
+      out->sorted_point = odd ? w.vals_b : w.vals_a;
+    }
     out->voxel_xyzi = w.out_xyzi;
     out->voxel_count = w.out_count;
     out->voxel_idx = reinterpret_cast<const uint64_t*>(w.out_idx);

@@ -59,9 +59,9 @@ struct VoxelParams {
   GridDev* grid;                     // [n_frames]
   SortInfo* info;
   uint32_t* hist;                    // [CM_MAX_SORT_PASSES][256]
-  void* keys_a;                      // key buffers (ping-pong)
+  void* keys_a;                      // ping-pong: 64-bit keys, or 8-byte (key, value) records when key_bytes == 4
   void* keys_b;
-  uint32_t* vals_a;
+  uint32_t* vals_a;                  // values of 64-bit keys (unused by the record layout)
   uint32_t* vals_b;
   unsigned long long* lb_sort;       // [sort tiles][256]
   uint32_t* cent_count;              // [centroid tiles] voxels emitted per tile, then their exclusive prefix
@@ -84,6 +84,9 @@ cudaError_t launch_seed_bounds(FrameAcc* acc, const float* mn, const float* mx, 
 cudaError_t launch_grid_setup(const VoxelParams& p, cudaStream_t stream);
 cudaError_t launch_key_hist(const VoxelParams& p, cudaStream_t stream);
 cudaError_t launch_sort_pass(const VoxelParams& p, int pass, cudaStream_t stream);
+// 32-bit keys are sorted as 8-byte (key, value) records in keys_a/keys_b; this splits the first *n_ptr records into two arrays
+cudaError_t launch_split_records(const void* records, uint32_t* keys, uint32_t* vals, const uint32_t* n_ptr,
+                                 uint32_t max_points, cudaStream_t stream);
 cudaError_t launch_centroid(const VoxelParams& p, cudaStream_t stream);        // 3 launches: centroid, scan, compact
 #define CM_CENTROID_LAUNCHES 3
 

@@ -5,10 +5,18 @@
 //
 // One launch per 8-bit digit. The digit histograms of all passes were produced up front by k_voxel_key_hist, so a pass
 // is a single sweep: each CTA takes a tile, ranks its keys by digit (ballot-based match, stable), obtains for
-// each of the 256 digits the number of equal-digit keys in all earlier tiles (chained scan; see "scanner CTAs"), and scatters
-// keys and values to their final place of this pass through shared memory so that global stores are digit-contiguous.
-// The number of passes is decided on the device (SortInfo.num_passes, from the significant key bits); a pass beyond it
-// returns immediately, and every kernel derives the ping-pong buffer it reads from the pass number.
+// each of the 256 digits the global position of its first key of that digit (chained scan; see "scanner CTAs"), and
+// scatters keys and values to their final place of this pass through shared memory so that global stores are
+// digit-contiguous. The number of passes is decided on the device (SortInfo.num_passes, from the significant key bits); a
+// pass beyond it returns immediately, and every kernel derives the ping-pong buffer it reads from the pass number.
+//
+// Record layout in HBM: 32-bit keys travel as 8-byte (key, value) records in keys_a / keys_b (one 8-byte load and one
+// 8-byte store per item and pass, digit runs of 128 bytes on average); 64-bit keys travel as separate key and value
+// arrays (keys_*, vals_*).
+//
+// The kernel is instruction-issue bound before it is HBM bound, so the per-item instruction count is what was designed:
+//   load 1, digit 1, match 24 (R2P + 8 VOTE + 8 predicated NOT + 4 three-input OR), rank 8 (one LDS, one predicated STS
+//   on a warp-private counter row, one POPC), shared-memory placement 5, scatter 8  ~= 50 per item (was ~150).
 //
 // Roofline: HBM. Algorithmic bytes per pass = n * 2 * (key_bytes + 4).
 #include "cm_kernels.h"
@@ -32,58 +40,102 @@ struct SortCfg<unsigned long long> {
 };
 
 // ---- scanner CTAs -------------------------------------------------------------------------------------------------------
-// The first RS_SCANNERS CTAs of a pass do not sort: scanner h owns 64 digits and walks the tile rows in order, four
-// threads per digit, 32 rows per round trip: it waits until the rows' aggregates are published, and rewrites every row
-// with the inclusive prefix. A worker tile then reads exactly one row -- its predecessor's inclusive prefix -- instead
-// of walking back over every tile in flight (that walk, 256 digits x dozens of rows per tile, cost as much L2 bandwidth
-// as the keys themselves). Scanners are CTAs 0..3 of the grid, i.e. resident before any worker; workers publish their
-// aggregate before they wait, so the pair cannot deadlock.
-constexpr int RS_SCANNERS = 4;
-constexpr int RS_SCAN_ROWS = 8;  // rows per thread per round trip (x4 threads per digit = 32 rows)
+// The first RS_SCANNERS CTAs of a pass do not sort. Rows of 256 look-back words are indexed -1 .. n_tiles-1; worker
+// tile t publishes its 256 digit counts in row t, and needs, per digit, the global position of its first key of that
+// digit = (number of keys with a smaller digit in the whole input) + (keys of that digit in tiles < t). The scanners
+// produce exactly that number: scanner h owns 32 consecutive digits (one per lane), its warp q owns 8 rows of every
+// 64-row batch; it starts from the exclusive scan of the pass's global digit histogram (row -1), waits until the rows'
+// counts are published, and overwrites every row with the running inclusive sum. A worker then reads one row -- row
+// t-1 -- instead of walking back over every tile in flight (that walk, 256 digits x dozens of rows per tile, cost as much
+// L2 bandwidth as the keys themselves). Scanners are CTAs 0..7 of the grid, i.e. resident before any worker; workers
+// publish their counts before they wait, so the pair cannot deadlock.
+constexpr int RS_SCANNERS = 8;
+constexpr int RS_SCAN_DIGITS = CM_RADIX / RS_SCANNERS;  // 32: one digit per lane
+constexpr int RS_SCAN_ROWS = 8;                         // rows per warp per batch
+constexpr int RS_SCAN_BATCH = RS_SCAN_ROWS * RS_WARPS;  // 64 rows per round trip
+static_assert(RS_SCAN_DIGITS == 32, "one digit per lane");
 
-__device__ __forceinline__ void scanner_load(unsigned long long (&w)[RS_SCAN_ROWS], const unsigned long long* st,
+__device__ __forceinline__ void scanner_load(unsigned long long (&w)[RS_SCAN_ROWS], const unsigned long long* rows,
                                              uint32_t r0, uint32_t n_tiles, uint32_t d) {
 #pragma unroll
-  for (int k = 0; k < RS_SCAN_ROWS; ++k) w[k] = (r0 + k < n_tiles) ? ld_cg_u64(st + (size_t)(r0 + k) * CM_RADIX + d) : 0ull;
+  for (int k = 0; k < RS_SCAN_ROWS; ++k) w[k] = (r0 + k < n_tiles) ? ld_cg_u64(rows + (size_t)(r0 + k) * CM_RADIX + d) : 0ull;
 }
 
-__device__ __forceinline__ void scanner_cta(unsigned long long* st, uint32_t n_tiles, uint32_t epoch, uint32_t* err) {
-  const uint32_t tid = threadIdx.x;
-  const uint32_t d = blockIdx.x * (CM_RADIX / RS_SCANNERS) + (tid >> 2);  // digit
-  const uint32_t q = tid & 3u;                                            // which quarter of the 32-row batch
-  uint32_t run = 0;                                                       // inclusive prefix of everything before the batch
+__device__ __forceinline__ void scanner_cta(unsigned long long* rows /* row 0 */, uint32_t n_tiles, uint32_t epoch,
+                                            const uint32_t* hist /* this pass */, uint32_t* err, uint32_t* s_scan,
+                                            uint32_t* s_tot /* [2][RS_WARPS][32] */) {
+  const uint32_t tid = threadIdx.x, lane = tid & 31u, q = tid >> 5;
+  const uint32_t d = blockIdx.x * RS_SCAN_DIGITS + lane;  // digit
   unsigned long long w[RS_SCAN_ROWS], wn[RS_SCAN_ROWS];
-  scanner_load(w, st, q * RS_SCAN_ROWS, n_tiles, d);
-  for (uint32_t t0 = 0; t0 < n_tiles; t0 += 4 * RS_SCAN_ROWS) {
+  scanner_load(w, rows, q * RS_SCAN_ROWS, n_tiles, d);
+  // exclusive scan of the global digit histogram: where digit d starts in the output of this pass
+  uint32_t tot;
+  const uint32_t gb = block_excl_scan_256(hist[tid], s_scan, &tot);
+  s_tot[tid] = gb;
+  __syncthreads();
+  uint32_t run = s_tot[d];
+  __syncthreads();
+  if (q == 0) st_cg_u64(rows - CM_RADIX + d, lb_pack(epoch, CM_LB_INCL, run));  // row -1
+  uint32_t buf = 0;
+  for (uint32_t t0 = 0; t0 < n_tiles; t0 += RS_SCAN_BATCH, buf ^= 1u) {
     const uint32_t r0 = t0 + q * RS_SCAN_ROWS;
-    scanner_load(wn, st, r0 + 4 * RS_SCAN_ROWS, n_tiles, d);  // next batch in flight while this one is processed
+    scanner_load(wn, rows, r0 + RS_SCAN_BATCH, n_tiles, d);  // next batch in flight while this one is processed
     uint32_t v[RS_SCAN_ROWS];
     uint32_t sum = 0;
 #pragma unroll
     for (int k = 0; k < RS_SCAN_ROWS; ++k) {
-      v[k] = 0;
+      uint32_t c = 0;
       if (r0 + k < n_tiles) {
         unsigned long long x = w[k];
-        if (!lb_ready(x, epoch)) x = lb_wait(st + (size_t)(r0 + k) * CM_RADIX + d, epoch, err);
-        v[k] = (uint32_t)x;
+        if (!lb_ready(x, epoch)) x = lb_wait(rows + (size_t)(r0 + k) * CM_RADIX + d, epoch, err);
+        c = (uint32_t)x;
       }
-      sum += v[k];
-      v[k] = sum;  // inclusive within this thread's rows
+      sum += c;
+      v[k] = sum;  // inclusive within this warp's rows
     }
-    // inclusive prefix of `sum` over the 4 threads of the digit (lanes 4g .. 4g+3)
-    uint32_t incl = sum;
-    uint32_t o = __shfl_up_sync(0xFFFFFFFFu, incl, 1, 4);
-    if (q >= 1) incl += o;
-    o = __shfl_up_sync(0xFFFFFFFFu, incl, 2, 4);
-    if (q >= 2) incl += o;
-    const uint32_t base = run + incl - sum;
+    uint32_t* tb = s_tot + buf * (RS_WARPS * 32);
+    tb[q * 32 + lane] = sum;
+    __syncthreads();
+    uint32_t before = 0, total = 0;
+#pragma unroll
+    for (int u = 0; u < RS_WARPS; ++u) {
+      const uint32_t t = tb[u * 32 + lane];
+      if ((uint32_t)u < q) before += t;
+      total += t;
+    }
+    const uint32_t base = run + before;
 #pragma unroll
     for (int k = 0; k < RS_SCAN_ROWS; ++k)
-      if (r0 + k < n_tiles) st_cg_u64(st + (size_t)(r0 + k) * CM_RADIX + d, lb_pack(epoch, CM_LB_INCL, base + v[k]));
-    run += __shfl_sync(0xFFFFFFFFu, incl, 3, 4);  // batch total
+      if (r0 + k < n_tiles) st_cg_u64(rows + (size_t)(r0 + k) * CM_RADIX + d, lb_pack(epoch, CM_LB_INCL, base + v[k]));
+    run += total;
 #pragma unroll
     for (int k = 0; k < RS_SCAN_ROWS; ++k) w[k] = wn[k];
   }
+}
+
+// Which lanes of the warp hold a different value in bits 0..7 of x: bit j of the result is set iff lane j differs.
+// One ballot per bit; a lane whose bit is set complements the ballot, so the OR over bits marks the differing lanes.
+__device__ __forceinline__ uint32_t warp_diff8(uint32_t x) {
+  uint32_t t[8];
+#pragma unroll
+  for (int b = 0; b < 8; ++b) {
+    asm volatile(
+        "{\n .reg .pred p;\n .reg .b32 y;\n and.b32 y, %1, %2;\n setp.ne.u32 p, y, 0;\n"
+        " vote.sync.ballot.b32 %0, p, 0xffffffff;\n @p not.b32 %0, %0;\n}"
+        : "=r"(t[b])
+        : "r"(x), "r"(1u << b));
+  }
+  uint32_t a, c;
+  asm("lop3.b32 %0, %1, %2, %3, 0xFE;" : "=r"(a) : "r"(t[0]), "r"(t[1]), "r"(t[2]));
+  asm("lop3.b32 %0, %1, %2, %3, 0xFE;" : "=r"(c) : "r"(t[3]), "r"(t[4]), "r"(t[5]));
+  asm("lop3.b32 %0, %1, %2, %3, 0xFE;" : "=r"(a) : "r"(a), "r"(t[6]), "r"(t[7]));
+  return a | c;
+}
+
+__device__ __forceinline__ uint32_t lanemask_gt() {
+  uint32_t m;
+  asm("mov.u32 %0, %%lanemask_gt;" : "=r"(m));
+  return m;
 }
 
 template <typename KeyT>
@@ -91,14 +143,13 @@ __global__ void __launch_bounds__(RS_THREADS, 3) k_onesweep_pass(const VoxelPara
   constexpr int IPT = SortCfg<KeyT>::IPT;
   constexpr int TILE = RS_THREADS * IPT;
   constexpr int WARP_ITEMS = 32 * IPT;
+  constexpr bool AOS = sizeof(KeyT) == 4;  // (key, value) records of 8 bytes
 
-  __shared__ uint32_t s_warp_hist[RS_WARPS][CM_RADIX];
-  __shared__ uint32_t s_cnt[CM_RADIX];                       // early per-tile digit counts
-  __shared__ uint32_t s_bin_start[CM_RADIX];                 // first position of digit d inside the sorted tile
-  __shared__ uint32_t s_scatter[CM_RADIX];                   // global position of sorted-tile position 0 of digit d, minus s_bin_start
+  __shared__ uint32_t s_hist[RS_WARPS * CM_RADIX];  // per-warp digit counters, then per-warp first positions
+  __shared__ uint32_t s_scatter[CM_RADIX];          // global position of sorted-tile position 0 of digit d
   __shared__ uint32_t s_scan[9];
-  __shared__ __align__(16) KeyT s_keys[TILE];
-  __shared__ uint32_t s_vals[TILE];
+  __shared__ __align__(16) unsigned long long s_k[TILE];  // AOS: records (value << 32 | key); else keys
+  __shared__ uint32_t s_v[AOS ? 1 : TILE];
 
   const long long tr0 = clock64();
   const SortInfo si = *p.info;
@@ -106,149 +157,201 @@ __global__ void __launch_bounds__(RS_THREADS, 3) k_onesweep_pass(const VoxelPara
   const uint32_t M = si.n_keys;
   const uint32_t n_tiles = (M + TILE - 1) / TILE;
 
-  const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+  const uint32_t tid = threadIdx.x, lane = tid & 31u;
+  const uint32_t warp = __shfl_sync(0xFFFFFFFFu, tid >> 5, 0);  // provably warp-uniform
   // tile id = blockIdx.x: CTAs of a 1-D grid are dispatched in index order (what CUB's single-pass scan relies on too;
   // the look-back watchdog covers the case that this ever fails to hold)
   const uint32_t epoch = p.epoch + 1u + (uint32_t)pass;
+  unsigned long long* const rows = p.lb_sort + CM_RADIX;  // row -1 lives in front
   if (blockIdx.x < RS_SCANNERS) {
-    scanner_cta(p.lb_sort, n_tiles, epoch, &p.ctrl->error);
+    scanner_cta(rows, n_tiles, epoch, p.hist + pass * CM_RADIX, &p.ctrl->error, s_scan, s_hist);
     return;
   }
   const uint32_t tile = blockIdx.x - RS_SCANNERS;
   if (tile >= n_tiles) return;
-  const uint32_t gcount = (tid < CM_RADIX) ? p.hist[pass * CM_RADIX + tid] : 0u;  // needed late: fetch it now
-  for (uint32_t i = tid; i < RS_WARPS * CM_RADIX; i += RS_THREADS) (&s_warp_hist[0][0])[i] = 0;
-  if (tid < CM_RADIX) s_cnt[tid] = 0;
-  __syncthreads();
 
 #define RS_TRACE(i) do { if (p.trace && p.trace_pass == (uint32_t)pass && tid == 0) p.trace[(size_t)tile * 8 + (i)] = (unsigned long long)(clock64() - tr0); } while (0)
-  RS_TRACE(0);
   const bool odd = (pass & 1) != 0;
-  const KeyT* __restrict__ in_keys = reinterpret_cast<const KeyT*>(odd ? p.keys_b : p.keys_a);
-  KeyT* __restrict__ out_keys = reinterpret_cast<KeyT*>(odd ? p.keys_a : p.keys_b);
-  const uint32_t* __restrict__ in_vals = odd ? p.vals_b : p.vals_a;
-  uint32_t* __restrict__ out_vals = odd ? p.vals_a : p.vals_b;
   const uint32_t shift = (uint32_t)pass * CM_RADIX_BITS;
-
   const uint32_t tile_base = tile * TILE;
   const uint32_t n_here = min((uint32_t)TILE, M - tile_base);
+  const bool full = n_here == (uint32_t)TILE;
   const uint32_t item0 = warp * WARP_ITEMS + lane;  // tile-local index of item 0 of this thread; item i = item0 + 32 i
 
-  // ---- load keys (warp-striped, coalesced) -----------------------------------------------------------------------
+  // ---- load keys and values (warp-striped, coalesced). Slots past the end of a partial (last) tile get the all-ones
+  // key: digit 255 in every pass, and -- being the last items of the tile -- ranked after every real key of that digit,
+  // so they land at sorted-tile positions >= n_here and are simply not written back.
   KeyT key[IPT];
-#pragma unroll
-  for (int i = 0; i < IPT; ++i) {
-    const uint32_t li = item0 + 32 * i;
-    key[i] = (li < n_here) ? in_keys[tile_base + li] : (KeyT)0;
-  }
-
-  // values ride along; issue their loads now so the latency hides behind the ranking
   uint32_t val[IPT];
+  if (AOS) {
+    const uint2* __restrict__ in = reinterpret_cast<const uint2*>(odd ? p.keys_b : p.keys_a) + tile_base + item0;
+    if (full) {
 #pragma unroll
-  for (int i = 0; i < IPT; ++i) {
-    const uint32_t li = item0 + 32 * i;
-    val[i] = (li < n_here) ? in_vals[tile_base + li] : 0u;
-  }
-
-  RS_TRACE(1);
-  // ---- stable rank of every key among the keys of its digit inside the warp -----------------------------------------
-  // peers = lanes holding the same digit, found with one ballot per digit bit (constant time; __match_any_sync costs
-  // one round per distinct value, i.e. up to 32 rounds on the low, uniformly distributed digits)
-  uint32_t peers[IPT];
+      for (int i = 0; i < IPT; ++i) {
+        const uint2 r = in[32 * i];
+        key[i] = (KeyT)r.x;
+        val[i] = r.y;
+      }
+    } else {
 #pragma unroll
-  for (int i = 0; i < IPT; ++i) {
-    const uint32_t li = item0 + 32 * i;
-    const bool valid = li < n_here;
-    const uint32_t d = (uint32_t)(key[i] >> shift) & (CM_RADIX - 1);
-    uint32_t pm = __ballot_sync(0xFFFFFFFFu, valid);
-#pragma unroll
-    for (int b = 0; b < CM_RADIX_BITS; ++b) {
-      const bool bit = (d >> b) & 1u;
-      const uint32_t m = __ballot_sync(0xFFFFFFFFu, bit);
-      pm &= bit ? m : ~m;
+      for (int i = 0; i < IPT; ++i) {
+        uint2 r = make_uint2(0xFFFFFFFFu, 0u);
+        if (item0 + 32 * i < n_here) r = in[32 * i];
+        key[i] = (KeyT)r.x;
+        val[i] = r.y;
+      }
     }
-    peers[i] = valid ? pm : 0u;
-  }
-  // ---- early counts: the tile's digit histogram goes out before the (longer) ranking, so that by the time this tile
-  // walks back over its predecessors they have all published theirs (the ranking time becomes slack for stragglers)
+  } else {
+    const KeyT* __restrict__ in_keys = reinterpret_cast<const KeyT*>(odd ? p.keys_b : p.keys_a) + tile_base + item0;
+    const uint32_t* __restrict__ in_vals = (odd ? p.vals_b : p.vals_a) + tile_base + item0;
+    if (full) {
 #pragma unroll
-  for (int i = 0; i < IPT; ++i) {
-    const uint32_t pm = peers[i];
-    if (pm && (int)lane == __ffs(pm) - 1) atomicAdd(&s_cnt[(uint32_t)(key[i] >> shift) & (CM_RADIX - 1)], (uint32_t)__popc(pm));
+      for (int i = 0; i < IPT; ++i) key[i] = in_keys[32 * i];
+#pragma unroll
+      for (int i = 0; i < IPT; ++i) val[i] = in_vals[32 * i];
+    } else {
+#pragma unroll
+      for (int i = 0; i < IPT; ++i) key[i] = (item0 + 32 * i < n_here) ? in_keys[32 * i] : ~(KeyT)0;
+#pragma unroll
+      for (int i = 0; i < IPT; ++i) val[i] = (item0 + 32 * i < n_here) ? in_vals[32 * i] : 0u;
+    }
   }
-  __syncthreads();
-  const uint32_t cnt = (tid < CM_RADIX) ? s_cnt[tid] : 0u;
-  if (tid < CM_RADIX) st_relaxed_u64(p.lb_sort + (size_t)tile * CM_RADIX + tid, lb_pack(epoch, CM_LB_AGG, cnt));
-  RS_TRACE(2);
+  // the warp's own counter row
+  uint32_t* const wh = s_hist + warp * CM_RADIX;
+#pragma unroll
+  for (int k = 0; k < CM_RADIX / 32; ++k) wh[lane + 32 * k] = 0;
+  __syncwarp();
+  RS_TRACE(0);
 
+  // ---- stable rank of every key among the keys of its digit inside the warp ----------------------------------------
+  // peers = lanes holding the same digit (ballot match, constant time; __match_any_sync costs one round per distinct
+  // value). Every lane reads the digit's counter; the highest peer lane writes it back advanced by the peer count.
+  // Shared-memory accesses of one warp are performed in program order, __syncwarp keeps the compiler from reordering.
+  const uint32_t lt = lanemask_lt(), gt = lanemask_gt();
   uint32_t rank[IPT];
 #pragma unroll
   for (int i = 0; i < IPT; ++i) {
-    const uint32_t d = (uint32_t)(key[i] >> shift) & (CM_RADIX - 1);
-    const uint32_t pm = peers[i];
-    const int leader = pm ? (__ffs(pm) - 1) : (int)lane;
-    uint32_t prev = 0;
-    if (pm && (int)lane == leader) {
-      prev = s_warp_hist[warp][d];
-      s_warp_hist[warp][d] = prev + (uint32_t)__popc(pm);
-    }
-    prev = __shfl_sync(0xFFFFFFFFu, prev, leader);
-    rank[i] = prev + (uint32_t)__popc(pm & lanemask_lt());
+    const uint32_t ks = (uint32_t)(key[i] >> shift);
+    const uint32_t diff = warp_diff8(ks);
+    const uint32_t below = (uint32_t)__popc(~diff & lt);
+    volatile uint32_t* c = wh + (ks & (CM_RADIX - 1));
+    const uint32_t r = *c + below;
+    rank[i] = r;
+    if ((~diff & gt) == 0u) *c = r + 1u;
     __syncwarp();
   }
   __syncthreads();
+  RS_TRACE(1);
 
-  // ---- per digit: prefix over warps, position in the sorted tile, global base ------------------------------------------
-  if (tid < CM_RADIX) {
-    uint32_t run = 0;
+  // ---- per digit (one per thread): tile count -> published; prefix over digits and warps -> first positions ---------
+  {
+    uint32_t wc[RS_WARPS];
+    uint32_t cnt = 0;
 #pragma unroll
     for (int w = 0; w < RS_WARPS; ++w) {
-      const uint32_t t = s_warp_hist[w][tid];
-      s_warp_hist[w][tid] = run;
-      run += t;
+      wc[w] = s_hist[w * CM_RADIX + tid];
+      cnt += wc[w];
     }
+    const uint32_t real = (tid == CM_RADIX - 1) ? cnt - ((uint32_t)TILE - n_here) : cnt;
+    st_relaxed_u64(rows + (size_t)tile * CM_RADIX + tid, lb_pack(epoch, CM_LB_AGG, real));
+    RS_TRACE(2);
+    uint32_t tot;
+    const uint32_t bin_start = block_excl_scan_256(cnt, s_scan, &tot);
+    uint32_t run = bin_start;
+#pragma unroll
+    for (int w = 0; w < RS_WARPS; ++w) {
+      s_hist[w * CM_RADIX + tid] = run;
+      run += wc[w];
+    }
+    s_scatter[tid] = 0u - bin_start;  // completed below once the scanners have delivered the row
   }
-  uint32_t tot;
-  const uint32_t bin_start = block_excl_scan_256(cnt, s_scan, &tot);
-  const uint32_t gbase = block_excl_scan_256(gcount, s_scan, &tot);
-  if (tid < CM_RADIX) s_bin_start[tid] = bin_start;
   __syncthreads();
   RS_TRACE(3);
 
   // ---- keys and values into sorted-tile order in shared memory ---------------------------------------------------------
 #pragma unroll
   for (int i = 0; i < IPT; ++i) {
-    const uint32_t li = item0 + 32 * i;
-    if (li < n_here) {
-      const uint32_t d = (uint32_t)(key[i] >> shift) & (CM_RADIX - 1);
-      const uint32_t pos = s_bin_start[d] + s_warp_hist[warp][d] + rank[i];
-      s_keys[pos] = key[i];
-      s_vals[pos] = val[i];
+    const uint32_t ks = (uint32_t)(key[i] >> shift);
+    const uint32_t pos = wh[ks & (CM_RADIX - 1)] + rank[i];
+    if (AOS) {
+      s_k[pos] = ((unsigned long long)val[i] << 32) | (unsigned long long)key[i];
+    } else {
+      s_k[pos] = (unsigned long long)key[i];
+      s_v[pos] = val[i];
     }
   }
   RS_TRACE(4);
-  // ---- one row from the scanners: the inclusive prefix of the previous tile ------------------------------------------------
-  if (tid < CM_RADIX) {
-    const uint32_t before =
-        tile == 0 ? 0u : lb_wait_inclusive(p.lb_sort + (size_t)(tile - 1) * CM_RADIX + tid, epoch, &p.ctrl->error);
-    s_scatter[tid] = gbase + before - bin_start;  // modulo 2^32
+  // ---- one row from the scanners: where this tile's keys of digit d start in the output -------------------------------
+  {
+    const uint32_t first = lb_wait_inclusive(rows + ((long long)tile - 1) * CM_RADIX + tid, epoch, &p.ctrl->error);
+    s_scatter[tid] += first;  // modulo 2^32
   }
   __syncthreads();
   RS_TRACE(5);
 
   // ---- scatter: consecutive threads write consecutive addresses inside each digit's run ------------------------------
+  // (two copies of the loop: the one for full tiles carries no bounds checks, so its shared-memory loads batch up)
+  if (AOS) {
+    unsigned long long* __restrict__ out = reinterpret_cast<unsigned long long*>(odd ? p.keys_a : p.keys_b);
+    if (full) {
+      unsigned long long r[IPT];
 #pragma unroll
-  for (int j = 0; j < IPT; ++j) {
-    const uint32_t pos = j * RS_THREADS + tid;
-    if (pos < n_here) {
-      const KeyT kk = s_keys[pos];
-      const uint32_t d = (uint32_t)(kk >> shift) & (CM_RADIX - 1);
-      const uint32_t dst = s_scatter[d] + pos;
-      out_keys[dst] = kk;
-      out_vals[dst] = s_vals[pos];
+      for (int j = 0; j < IPT; ++j) r[j] = s_k[j * RS_THREADS + tid];
+#pragma unroll
+      for (int j = 0; j < IPT; ++j) {
+        const uint32_t dg = ((uint32_t)r[j] >> shift) & (CM_RADIX - 1);
+        out[s_scatter[dg] + (j * RS_THREADS + tid)] = r[j];
+      }
+    } else {
+      for (uint32_t pos = tid; pos < n_here; pos += RS_THREADS) {
+        const unsigned long long r = s_k[pos];
+        const uint32_t dg = ((uint32_t)r >> shift) & (CM_RADIX - 1);
+        out[s_scatter[dg] + pos] = r;
+      }
+    }
+  } else {
+    KeyT* __restrict__ out_keys = reinterpret_cast<KeyT*>(odd ? p.keys_a : p.keys_b);
+    uint32_t* __restrict__ out_vals = odd ? p.vals_a : p.vals_b;
+    if (full) {
+#pragma unroll
+      for (int j0 = 0; j0 < IPT; j0 += 4) {
+        unsigned long long kk[4];
+        uint32_t vv[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          kk[j] = s_k[(j0 + j) * RS_THREADS + tid];
+          vv[j] = s_v[(j0 + j) * RS_THREADS + tid];
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const uint32_t dg = (uint32_t)(kk[j] >> shift) & (CM_RADIX - 1);
+          const uint32_t dst = s_scatter[dg] + ((j0 + j) * RS_THREADS + tid);
+          out_keys[dst] = (KeyT)kk[j];
+          out_vals[dst] = vv[j];
+        }
+      }
+    } else {
+      for (uint32_t pos = tid; pos < n_here; pos += RS_THREADS) {
+        const unsigned long long kk = s_k[pos];
+        const uint32_t dg = (uint32_t)(kk >> shift) & (CM_RADIX - 1);
+        const uint32_t dst = s_scatter[dg] + pos;
+        out_keys[dst] = (KeyT)kk;
+        out_vals[dst] = s_v[pos];
+      }
     }
   }
   RS_TRACE(6);
+}
+
+// 32-bit keys leave the sort as 8-byte (key, value) records; callers that want two plain arrays get them from here.
+__global__ void __launch_bounds__(256) k_split_records(const uint2* __restrict__ rec, uint32_t* __restrict__ keys,
+                                                       uint32_t* __restrict__ vals, const uint32_t* n_ptr) {
+  const uint32_t n = *n_ptr;
+  for (uint32_t i = blockIdx.x * 256u + threadIdx.x; i < n; i += gridDim.x * 256u) {
+    const uint2 r = rec[i];
+    keys[i] = r.x;
+    vals[i] = r.y;
+  }
 }
 
 }  // namespace
@@ -265,6 +368,14 @@ cudaError_t launch_sort_pass(const VoxelParams& p, int pass, cudaStream_t stream
     k_onesweep_pass<uint32_t><<<tiles + RS_SCANNERS, RS_THREADS, 0, stream>>>(p, pass);
   else
     k_onesweep_pass<unsigned long long><<<tiles + RS_SCANNERS, RS_THREADS, 0, stream>>>(p, pass);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_split_records(const void* records, uint32_t* keys, uint32_t* vals, const uint32_t* n_ptr,
+                                 uint32_t max_points, cudaStream_t stream) {
+  if (max_points == 0) return cudaSuccess;
+  const uint32_t blocks = std::min<uint32_t>((max_points + 255u) / 256u, 148u * 8u);
+  k_split_records<<<blocks, 256, 0, stream>>>(reinterpret_cast<const uint2*>(records), keys, vals, n_ptr);
   return cudaGetLastError();
 }
 

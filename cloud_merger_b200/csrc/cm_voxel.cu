@@ -328,8 +328,12 @@ __global__ void __launch_bounds__(VX_THREADS) k_voxel_key_hist(const VoxelParams
           } else {
             key = (KeyT)sentinel;
           }
-          keys[r.dense0 + j] = key;
-          vals[r.dense0 + j] = r.slot0 + j;
+          if (sizeof(KeyT) == 4) {  // 32-bit keys travel as 8-byte (key, value) records
+            reinterpret_cast<uint2*>(p.keys_a)[r.dense0 + j] = make_uint2((uint32_t)key, r.slot0 + j);
+          } else {
+            keys[r.dense0 + j] = key;
+            vals[r.dense0 + j] = r.slot0 + j;
+          }
         }
         // digit histograms. Bits on which all valid lanes of the warp agree are found with two warp reductions; a digit
         // made only of such bits (the frame bits, the high cell bits of a spatially coherent tile) is added once per warp.
@@ -387,8 +391,17 @@ __global__ void __launch_bounds__(VX_THREADS) k_voxel_centroid(const VoxelParams
   const SortInfo si = *p.info;
   const uint32_t idx_bits = si.idx_bits;
   const bool odd = (si.num_passes & 1u) != 0u;
-  const KeyT* __restrict__ keys = reinterpret_cast<const KeyT*>(odd ? p.keys_b : p.keys_a);
+  // 32-bit keys arrive as 8-byte (key, value) records, 64-bit keys as two arrays
+  const void* __restrict__ sorted = odd ? p.keys_b : p.keys_a;
   const uint32_t* __restrict__ vals = odd ? p.vals_b : p.vals_a;
+  auto key_at = [&](uint32_t i) -> KeyT {
+    if constexpr (sizeof(KeyT) == 4) return (KeyT) reinterpret_cast<const uint2*>(sorted)[i].x;
+    else return reinterpret_cast<const KeyT*>(sorted)[i];
+  };
+  auto val_at = [&](uint32_t i) -> uint32_t {
+    if constexpr (sizeof(KeyT) == 4) return reinterpret_cast<const uint2*>(sorted)[i].y;
+    else return vals[i];
+  };
   const unsigned long long limit = (si.key_frames > F) ? ((unsigned long long)F << idx_bits) : ~0ull;
   const unsigned long long idx_mask = idx_bits >= 64 ? ~0ull : ((1ull << idx_bits) - 1ull);
   const uint32_t m_req = p.min_points > 1u ? p.min_points : 1u;
@@ -402,14 +415,20 @@ __global__ void __launch_bounds__(VX_THREADS) k_voxel_centroid(const VoxelParams
 #pragma unroll
   for (int j = 0; j < CE_IPT; ++j) {
     const bool in = loc + j < tile_n;
-    k[j] = in ? keys[base + j] : (KeyT)0;
-    v[j] = in ? vals[base + j] : 0u;
+    if constexpr (sizeof(KeyT) == 4) {
+      const uint2 r = in ? reinterpret_cast<const uint2*>(sorted)[base + j] : make_uint2(0u, 0u);
+      k[j] = (KeyT)r.x;
+      v[j] = r.y;
+    } else {
+      k[j] = in ? key_at(base + j) : (KeyT)0;
+      v[j] = in ? val_at(base + j) : 0u;
+    }
   }
   KeyT prev = (KeyT)0, next = (KeyT)0;
   const bool has_prev = base > 0 && loc < tile_n;
   const bool has_next = base + CE_IPT < M;
-  if (has_prev) prev = keys[base - 1];
-  if (has_next) next = keys[base + CE_IPT];
+  if (has_prev) prev = key_at(base - 1);
+  if (has_next) next = key_at(base + CE_IPT);
   // With min_points <= 2 a point is needed only when its run survives the filter: every point for 1, a point with an
   // equal neighbour for 2. Singleton voxels (most of a sparse lidar frame) are then never gathered.
 #pragma unroll
@@ -418,7 +437,7 @@ __global__ void __launch_bounds__(VX_THREADS) k_voxel_centroid(const VoxelParams
       bool need = m_req != 2u;
       if (!need) {
         const bool eq_prev = (j == 0) ? (has_prev && prev == k[0]) : (k[j - 1] == k[j]);
-        const bool eq_next = (j == CE_IPT - 1) ? (has_next && next == k[j]) : (loc + j + 1 < tile_n ? k[j + 1] == k[j] : (base + j + 1 < M && keys[base + j + 1] == k[j]));
+        const bool eq_next = (j == CE_IPT - 1) ? (has_next && next == k[j]) : (loc + j + 1 < tile_n ? k[j + 1] == k[j] : (base + j + 1 < M && key_at(base + j + 1) == k[j]));
         need = eq_prev || eq_next;
       }
       if (need) s_pts[loc + j] = __ldg(p.pts + v[j]);
@@ -436,7 +455,7 @@ __global__ void __launch_bounds__(VX_THREADS) k_voxel_centroid(const VoxelParams
         bool ok = (unsigned long long)k[j] < limit;
         if (ok && m_req > 1u) {
           const unsigned long long i2 = (unsigned long long)i + m_req - 1ull;
-          ok = i2 < (unsigned long long)M && keys[i2] == k[j];
+          ok = i2 < (unsigned long long)M && key_at((uint32_t)i2) == k[j];
         }
         if (ok) { passbits |= 1u << j; ++cnt; }
       }
@@ -477,8 +496,8 @@ __global__ void __launch_bounds__(VX_THREADS) k_voxel_centroid(const VoxelParams
     } while (q < tile_n && s_keys[q] == key);
     if (q == tile_n) {  // the run may continue in the following tiles: global memory
       uint32_t g = tile_base + tile_n;
-      while (g < M && keys[g] == key) {
-        const float4 pt = __ldg(p.pts + __ldg(vals + g));
+      while (g < M && key_at(g) == key) {
+        const float4 pt = __ldg(p.pts + val_at(g));
         sx = __fadd_rn(sx, pt.x); sy = __fadd_rn(sy, pt.y); sz = __fadd_rn(sz, pt.z); sw = __fadd_rn(sw, pt.w);
         ++n; ++g;
       }
