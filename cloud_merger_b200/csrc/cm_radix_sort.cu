@@ -19,12 +19,18 @@
 //   on a warp-private counter row, one POPC), shared-memory placement 5, scatter 8  ~= 50 per item (was ~150).
 //
 // Roofline: HBM. Algorithmic bytes per pass = n * 2 * (key_bytes + 4).
+#include <cstdio>
+#include <cstdlib>
+
 #include "cm_kernels.h"
 
 namespace cm {
 
 namespace {
 
+#ifndef RS_MIN_CTAS
+#define RS_MIN_CTAS 3
+#endif
 constexpr int RS_THREADS = 256;
 constexpr int RS_WARPS = RS_THREADS / 32;
 
@@ -36,80 +42,97 @@ struct SortCfg<uint32_t> {
 };
 template <>
 struct SortCfg<unsigned long long> {
-  static constexpr int IPT = 12;
+  static constexpr int IPT = 10;  // 2 x (20 + 10) KB of sorted-tile buffers: three CTAs per SM like the 32-bit variant
 };
 
 // ---- scanner CTAs -------------------------------------------------------------------------------------------------------
 // The first RS_SCANNERS CTAs of a pass do not sort. Rows of 256 look-back words are indexed -1 .. n_tiles-1; worker
 // tile t publishes its 256 digit counts in row t, and needs, per digit, the global position of its first key of that
 // digit = (number of keys with a smaller digit in the whole input) + (keys of that digit in tiles < t). The scanners
-// produce exactly that number: scanner h owns 32 consecutive digits (one per lane), its warp q owns 8 rows of every
-// 64-row batch; it starts from the exclusive scan of the pass's global digit histogram (row -1), waits until the rows'
-// counts are published, and overwrites every row with the running inclusive sum. A worker then reads one row -- row
-// t-1 -- instead of walking back over every tile in flight (that walk, 256 digits x dozens of rows per tile, cost as much
-// L2 bandwidth as the keys themselves). Scanners are CTAs 0..7 of the grid, i.e. resident before any worker; workers
-// publish their counts before they wait, so the pair cannot deadlock.
+// produce exactly that number and overwrite every row with it, so a worker reads one row -- row t-1 -- instead of
+// walking back over every tile in flight (that walk, 256 digits x dozens of rows per tile, cost as much L2 bandwidth as
+// the keys themselves).
+//
+// Scanner h owns 32 consecutive digits, one per lane. Its warps take 32-row batches round-robin (warp q: batches q,
+// q+8, ...) and work on them independently: poll the batch's rows (all loads of a round in flight together) until
+// every count is published, prefix them in registers -- and only then enter the serial part, a shared-memory hand-over
+// of the running sum from the warp of the previous batch (one 8-byte word per digit carrying the batch sequence
+// number; ~100 cycles per batch). So 256 rows are being collected at any time and the serial chain of a pass is
+// n_tiles/32 short hops, not n_tiles/64 global-memory round trips as in the first version (where a worker spent 43% of
+// its life waiting for its row). The running sum starts from the exclusive scan of the pass's global digit histogram
+// (row -1). Scanners are CTAs 0..7 of the grid, i.e. resident before any worker; workers publish their counts before
+// they wait, so the pair cannot deadlock.
 constexpr int RS_SCANNERS = 8;
 constexpr int RS_SCAN_DIGITS = CM_RADIX / RS_SCANNERS;  // 32: one digit per lane
-constexpr int RS_SCAN_ROWS = 8;                         // rows per warp per batch
-constexpr int RS_SCAN_BATCH = RS_SCAN_ROWS * RS_WARPS;  // 64 rows per round trip
+constexpr int RS_SCAN_ROWS = 32;                        // rows per batch (one warp)
+constexpr int RS_SCAN_GROUP = 16;                       // rows polled together
 static_assert(RS_SCAN_DIGITS == 32, "one digit per lane");
-
-__device__ __forceinline__ void scanner_load(unsigned long long (&w)[RS_SCAN_ROWS], const unsigned long long* rows,
-                                             uint32_t r0, uint32_t n_tiles, uint32_t d) {
-#pragma unroll
-  for (int k = 0; k < RS_SCAN_ROWS; ++k) w[k] = (r0 + k < n_tiles) ? ld_cg_u64(rows + (size_t)(r0 + k) * CM_RADIX + d) : 0ull;
-}
 
 __device__ __forceinline__ void scanner_cta(unsigned long long* rows /* row 0 */, uint32_t n_tiles, uint32_t epoch,
                                             const uint32_t* hist /* this pass */, uint32_t* err, uint32_t* s_scan,
-                                            uint32_t* s_tot /* [2][RS_WARPS][32] */) {
+                                            uint32_t* s_tmp /* >= 256 words */, unsigned long long* s_chain /* 32 */) {
   const uint32_t tid = threadIdx.x, lane = tid & 31u, q = tid >> 5;
   const uint32_t d = blockIdx.x * RS_SCAN_DIGITS + lane;  // digit
-  unsigned long long w[RS_SCAN_ROWS], wn[RS_SCAN_ROWS];
-  scanner_load(w, rows, q * RS_SCAN_ROWS, n_tiles, d);
   // exclusive scan of the global digit histogram: where digit d starts in the output of this pass
   uint32_t tot;
   const uint32_t gb = block_excl_scan_256(hist[tid], s_scan, &tot);
-  s_tot[tid] = gb;
+  s_tmp[tid] = gb;
   __syncthreads();
-  uint32_t run = s_tot[d];
+  if (q == 0) {
+    const uint32_t run0 = s_tmp[d];
+    st_cg_u64(rows - CM_RADIX + d, lb_pack(epoch, CM_LB_INCL, run0));  // row -1
+    s_chain[lane] = (unsigned long long)run0;                           // sequence number 0: the sum before batch 0
+  }
   __syncthreads();
-  if (q == 0) st_cg_u64(rows - CM_RADIX + d, lb_pack(epoch, CM_LB_INCL, run));  // row -1
-  uint32_t buf = 0;
-  for (uint32_t t0 = 0; t0 < n_tiles; t0 += RS_SCAN_BATCH, buf ^= 1u) {
-    const uint32_t r0 = t0 + q * RS_SCAN_ROWS;
-    scanner_load(wn, rows, r0 + RS_SCAN_BATCH, n_tiles, d);  // next batch in flight while this one is processed
-    uint32_t v[RS_SCAN_ROWS];
+  const uint32_t n_batches = (n_tiles + RS_SCAN_ROWS - 1) / RS_SCAN_ROWS;
+  volatile unsigned long long* chain = s_chain + lane;
+  for (uint32_t b = q; b < n_batches; b += RS_WARPS) {
+    const uint32_t r0 = b * RS_SCAN_ROWS;
+    unsigned long long* const base = rows + (size_t)r0 * CM_RADIX + d;
+    uint32_t c[RS_SCAN_ROWS];
+#pragma unroll
+    for (int g0 = 0; g0 < RS_SCAN_ROWS; g0 += RS_SCAN_GROUP) {
+      uint32_t spins = 0;
+      while (true) {
+        unsigned long long w[RS_SCAN_GROUP];
+#pragma unroll
+        for (int k = 0; k < RS_SCAN_GROUP; ++k)
+          w[k] = (r0 + g0 + k < n_tiles) ? ld_cg_u64(base + (size_t)(g0 + k) * CM_RADIX) : lb_pack(epoch, CM_LB_AGG, 0u);
+        bool all = true;
+#pragma unroll
+        for (int k = 0; k < RS_SCAN_GROUP; ++k) {
+          all = all && lb_ready(w[k], epoch);
+          c[g0 + k] = (uint32_t)w[k];
+        }
+        if (__all_sync(0xFFFFFFFFu, all)) break;
+        if (++spins > (CM_SPIN_LIMIT >> 4)) {  // watchdog: raise the device error and let everything drain
+          atomicExch(err, (uint32_t)CM_DEV_E_INTERNAL);
+          break;
+        }
+        if (spins > 8) __nanosleep(50);
+      }
+    }
     uint32_t sum = 0;
 #pragma unroll
     for (int k = 0; k < RS_SCAN_ROWS; ++k) {
-      uint32_t c = 0;
-      if (r0 + k < n_tiles) {
-        unsigned long long x = w[k];
-        if (!lb_ready(x, epoch)) x = lb_wait(rows + (size_t)(r0 + k) * CM_RADIX + d, epoch, err);
-        c = (uint32_t)x;
+      sum += c[k];
+      c[k] = sum;  // inclusive within the batch
+    }
+    // serial part: take the running sum from the previous batch's warp, pass it on
+    unsigned long long x = *chain;
+    uint32_t spins = 0;
+    while ((uint32_t)(x >> 32) != b) {
+      if (++spins > CM_SPIN_LIMIT) {
+        atomicExch(err, (uint32_t)CM_DEV_E_INTERNAL);
+        break;
       }
-      sum += c;
-      v[k] = sum;  // inclusive within this warp's rows
+      x = *chain;
     }
-    uint32_t* tb = s_tot + buf * (RS_WARPS * 32);
-    tb[q * 32 + lane] = sum;
-    __syncthreads();
-    uint32_t before = 0, total = 0;
-#pragma unroll
-    for (int u = 0; u < RS_WARPS; ++u) {
-      const uint32_t t = tb[u * 32 + lane];
-      if ((uint32_t)u < q) before += t;
-      total += t;
-    }
-    const uint32_t base = run + before;
+    const uint32_t run = (uint32_t)x;
+    *chain = ((unsigned long long)(b + 1u) << 32) | (unsigned long long)(run + sum);
 #pragma unroll
     for (int k = 0; k < RS_SCAN_ROWS; ++k)
-      if (r0 + k < n_tiles) st_cg_u64(rows + (size_t)(r0 + k) * CM_RADIX + d, lb_pack(epoch, CM_LB_INCL, base + v[k]));
-    run += total;
-#pragma unroll
-    for (int k = 0; k < RS_SCAN_ROWS; ++k) w[k] = wn[k];
+      if (r0 + k < n_tiles) st_cg_u64(base + (size_t)k * CM_RADIX, lb_pack(epoch, CM_LB_INCL, run + c[k]));
   }
 }
 
@@ -138,18 +161,29 @@ __device__ __forceinline__ uint32_t lanemask_gt() {
   return m;
 }
 
+// Shared memory of one worker CTA. The sorted-tile buffers are double: a CTA ranks and places tile B while the scanners
+// are still producing the row that tile A (placed in the other buffer) needs for its scatter -- see the kernel.
 template <typename KeyT>
-__global__ void __launch_bounds__(RS_THREADS, 3) k_onesweep_pass(const VoxelParams p, const int pass) {
+struct SortSmem {
+  static constexpr int IPT = SortCfg<KeyT>::IPT;
+  static constexpr int TILE = RS_THREADS * IPT;
+  static constexpr bool AOS = sizeof(KeyT) == 4;
+  unsigned long long k[2][TILE];       // AOS: records (value << 32 | key); else keys
+  uint32_t v[2][AOS ? 1 : TILE];       // values of 64-bit keys
+  uint32_t hist[RS_WARPS * CM_RADIX];  // per-warp digit counters, then per-warp first positions
+  uint32_t scatter[2][CM_RADIX];       // global position of sorted-tile position 0 of digit d
+  uint32_t scan[12];
+  uint32_t next_tile[2];               // written by thread 0 one iteration ahead (parity-indexed)
+};
+
+template <typename KeyT>
+__global__ void __launch_bounds__(RS_THREADS, RS_MIN_CTAS) k_onesweep_pass(const VoxelParams p, const int pass) {
   constexpr int IPT = SortCfg<KeyT>::IPT;
   constexpr int TILE = RS_THREADS * IPT;
   constexpr int WARP_ITEMS = 32 * IPT;
   constexpr bool AOS = sizeof(KeyT) == 4;  // (key, value) records of 8 bytes
-
-  __shared__ uint32_t s_hist[RS_WARPS * CM_RADIX];  // per-warp digit counters, then per-warp first positions
-  __shared__ uint32_t s_scatter[CM_RADIX];          // global position of sorted-tile position 0 of digit d
-  __shared__ uint32_t s_scan[9];
-  __shared__ __align__(16) unsigned long long s_k[TILE];  // AOS: records (value << 32 | key); else keys
-  __shared__ uint32_t s_v[AOS ? 1 : TILE];
+  extern __shared__ __align__(16) unsigned char s_raw[];
+  SortSmem<KeyT>& sm = *reinterpret_cast<SortSmem<KeyT>*>(s_raw);
 
   const long long tr0 = clock64();
   const SortInfo si = *p.info;
@@ -159,188 +193,231 @@ __global__ void __launch_bounds__(RS_THREADS, 3) k_onesweep_pass(const VoxelPara
 
   const uint32_t tid = threadIdx.x, lane = tid & 31u;
   const uint32_t warp = __shfl_sync(0xFFFFFFFFu, tid >> 5, 0);  // provably warp-uniform
-  // tile id = blockIdx.x: CTAs of a 1-D grid are dispatched in index order (what CUB's single-pass scan relies on too;
-  // the look-back watchdog covers the case that this ever fails to hold)
   const uint32_t epoch = p.epoch + 1u + (uint32_t)pass;
   unsigned long long* const rows = p.lb_sort + CM_RADIX;  // row -1 lives in front
+  uint32_t* const err = &p.ctrl->error;
+  // CTAs of a 1-D grid are dispatched in index order, so the scanners are resident before any worker can wait for them
+  // (and the grid never exceeds what the device holds at once); the watchdogs cover the case that this fails to hold.
   if (blockIdx.x < RS_SCANNERS) {
-    scanner_cta(rows, n_tiles, epoch, p.hist + pass * CM_RADIX, &p.ctrl->error, s_scan, s_hist);
+    scanner_cta(rows, n_tiles, epoch, p.hist + pass * CM_RADIX, err, sm.scan, sm.hist, &sm.k[0][0]);
     return;
   }
-  const uint32_t tile = blockIdx.x - RS_SCANNERS;
-  if (tile >= n_tiles) return;
 
-#define RS_TRACE(i) do { if (p.trace && p.trace_pass == (uint32_t)pass && tid == 0) p.trace[(size_t)tile * 8 + (i)] = (unsigned long long)(clock64() - tr0); } while (0)
+#define RS_TRACE(t, i, t0) do { if (p.trace && p.trace_pass == (uint32_t)pass && tid == 0) p.trace[(size_t)(t) * 8 + (i)] = (unsigned long long)(clock64() - (t0)); } while (0)
   const bool odd = (pass & 1) != 0;
   const uint32_t shift = (uint32_t)pass * CM_RADIX_BITS;
-  const uint32_t tile_base = tile * TILE;
-  const uint32_t n_here = min((uint32_t)TILE, M - tile_base);
-  const bool full = n_here == (uint32_t)TILE;
-  const uint32_t item0 = warp * WARP_ITEMS + lane;  // tile-local index of item 0 of this thread; item i = item0 + 32 i
-
-  // ---- load keys and values (warp-striped, coalesced). Slots past the end of a partial (last) tile get the all-ones
-  // key: digit 255 in every pass, and -- being the last items of the tile -- ranked after every real key of that digit,
-  // so they land at sorted-tile positions >= n_here and are simply not written back.
-  KeyT key[IPT];
-  uint32_t val[IPT];
-  if (AOS) {
-    const uint2* __restrict__ in = reinterpret_cast<const uint2*>(odd ? p.keys_b : p.keys_a) + tile_base + item0;
-    if (full) {
-#pragma unroll
-      for (int i = 0; i < IPT; ++i) {
-        const uint2 r = in[32 * i];
-        key[i] = (KeyT)r.x;
-        val[i] = r.y;
-      }
-    } else {
-#pragma unroll
-      for (int i = 0; i < IPT; ++i) {
-        uint2 r = make_uint2(0xFFFFFFFFu, 0u);
-        if (item0 + 32 * i < n_here) r = in[32 * i];
-        key[i] = (KeyT)r.x;
-        val[i] = r.y;
-      }
-    }
-  } else {
-    const KeyT* __restrict__ in_keys = reinterpret_cast<const KeyT*>(odd ? p.keys_b : p.keys_a) + tile_base + item0;
-    const uint32_t* __restrict__ in_vals = (odd ? p.vals_b : p.vals_a) + tile_base + item0;
-    if (full) {
-#pragma unroll
-      for (int i = 0; i < IPT; ++i) key[i] = in_keys[32 * i];
-#pragma unroll
-      for (int i = 0; i < IPT; ++i) val[i] = in_vals[32 * i];
-    } else {
-#pragma unroll
-      for (int i = 0; i < IPT; ++i) key[i] = (item0 + 32 * i < n_here) ? in_keys[32 * i] : ~(KeyT)0;
-#pragma unroll
-      for (int i = 0; i < IPT; ++i) val[i] = (item0 + 32 * i < n_here) ? in_vals[32 * i] : 0u;
-    }
-  }
-  // the warp's own counter row
-  uint32_t* const wh = s_hist + warp * CM_RADIX;
-#pragma unroll
-  for (int k = 0; k < CM_RADIX / 32; ++k) wh[lane + 32 * k] = 0;
-  __syncwarp();
-  RS_TRACE(0);
-
-  // ---- stable rank of every key among the keys of its digit inside the warp ----------------------------------------
-  // peers = lanes holding the same digit (ballot match, constant time; __match_any_sync costs one round per distinct
-  // value). Every lane reads the digit's counter; the highest peer lane writes it back advanced by the peer count.
-  // Shared-memory accesses of one warp are performed in program order, __syncwarp keeps the compiler from reordering.
   const uint32_t lt = lanemask_lt(), gt = lanemask_gt();
-  uint32_t rank[IPT];
-#pragma unroll
-  for (int i = 0; i < IPT; ++i) {
-    const uint32_t ks = (uint32_t)(key[i] >> shift);
-    const uint32_t diff = warp_diff8(ks);
-    const uint32_t below = (uint32_t)__popc(~diff & lt);
-    volatile uint32_t* c = wh + (ks & (CM_RADIX - 1));
-    const uint32_t r = *c + below;
-    rank[i] = r;
-    if ((~diff & gt) == 0u) *c = r + 1u;
-    __syncwarp();
-  }
-  __syncthreads();
-  RS_TRACE(1);
+  uint32_t* const wh = sm.hist + warp * CM_RADIX;  // the warp's own counter row
+  uint32_t* const counter = &p.ctrl->tile_counter[1 + pass];
 
-  // ---- per digit (one per thread): tile count -> published; prefix over digits and warps -> first positions ---------
-  {
-    uint32_t wc[RS_WARPS];
-    uint32_t cnt = 0;
-#pragma unroll
-    for (int w = 0; w < RS_WARPS; ++w) {
-      wc[w] = s_hist[w * CM_RADIX + tid];
-      cnt += wc[w];
-    }
-    const uint32_t real = (tid == CM_RADIX - 1) ? cnt - ((uint32_t)TILE - n_here) : cnt;
-    st_relaxed_u64(rows + (size_t)tile * CM_RADIX + tid, lb_pack(epoch, CM_LB_AGG, real));
-    RS_TRACE(2);
-    uint32_t tot;
-    const uint32_t bin_start = block_excl_scan_256(cnt, s_scan, &tot);
-    uint32_t run = bin_start;
-#pragma unroll
-    for (int w = 0; w < RS_WARPS; ++w) {
-      s_hist[w * CM_RADIX + tid] = run;
-      run += wc[w];
-    }
-    s_scatter[tid] = 0u - bin_start;  // completed below once the scanners have delivered the row
-  }
+  // Tiles are handed out by an atomic counter (forward progress never depends on which CTAs are resident). A CTA works
+  // on two tiles at a time, software-pipelined:  front(t1): load, rank, publish counts, place into buffer b1
+  //                                              back(t0):  wait for row t0-1 from the scanners, scatter buffer b0
+  // so the scanners' latency (poll + chain + store + our poll, ~4-6 thousand cycles) hides behind front(t1) instead of
+  // idling a third of the SM's warps as it did when a CTA handled one tile from start to end.
+  if (tid == 0) sm.next_tile[0] = atomicAdd(counter, 1u);
   __syncthreads();
-  RS_TRACE(3);
-
-  // ---- keys and values into sorted-tile order in shared memory ---------------------------------------------------------
+  uint32_t cur = sm.next_tile[0];
+  uint32_t prev = 0xFFFFFFFFu, prev_n = 0;
+  uint32_t buf = 0;  // also the parity of the iteration
+  long long tr_cur = tr0, tr_prev = tr0;
+  uint32_t claimed = 0xFFFFFFFFu;
+  while (true) {
+    tr_prev = tr_cur;
+    tr_cur = clock64();
+    const bool have = cur < n_tiles;
+    uint32_t n_here = 0;
+    if (have) {
+      // ================================= front(cur) ==========================================================
+      const uint32_t tile_base = cur * TILE;
+      n_here = min((uint32_t)TILE, M - tile_base);
+      const bool full = n_here == (uint32_t)TILE;
+      const uint32_t item0 = warp * WARP_ITEMS + lane;  // tile-local index of item 0 of this thread; item i = item0 + 32 i
+      // ---- load keys and values (warp-striped, coalesced). Slots past the end of a partial (last) tile get the
+      // all-ones key: digit 255 in every pass, and -- being the last items of the tile -- ranked after every real key
+      // of that digit, so they land at sorted-tile positions >= n_here and are simply not written back.
+      KeyT key[IPT];
+      uint32_t val[IPT];
+      if (AOS) {
+        const uint2* __restrict__ in = reinterpret_cast<const uint2*>(odd ? p.keys_b : p.keys_a) + tile_base + item0;
+        if (full) {
 #pragma unroll
-  for (int i = 0; i < IPT; ++i) {
-    const uint32_t ks = (uint32_t)(key[i] >> shift);
-    const uint32_t pos = wh[ks & (CM_RADIX - 1)] + rank[i];
-    if (AOS) {
-      s_k[pos] = ((unsigned long long)val[i] << 32) | (unsigned long long)key[i];
-    } else {
-      s_k[pos] = (unsigned long long)key[i];
-      s_v[pos] = val[i];
-    }
-  }
-  RS_TRACE(4);
-  // ---- one row from the scanners: where this tile's keys of digit d start in the output -------------------------------
-  {
-    const uint32_t first = lb_wait_inclusive(rows + ((long long)tile - 1) * CM_RADIX + tid, epoch, &p.ctrl->error);
-    s_scatter[tid] += first;  // modulo 2^32
-  }
-  __syncthreads();
-  RS_TRACE(5);
-
-  // ---- scatter: consecutive threads write consecutive addresses inside each digit's run ------------------------------
-  // (two copies of the loop: the one for full tiles carries no bounds checks, so its shared-memory loads batch up)
-  if (AOS) {
-    unsigned long long* __restrict__ out = reinterpret_cast<unsigned long long*>(odd ? p.keys_a : p.keys_b);
-    if (full) {
-      unsigned long long r[IPT];
+          for (int i = 0; i < IPT; ++i) {
+            const uint2 r = in[32 * i];
+            key[i] = (KeyT)r.x;
+            val[i] = r.y;
+          }
+        } else {
 #pragma unroll
-      for (int j = 0; j < IPT; ++j) r[j] = s_k[j * RS_THREADS + tid];
-#pragma unroll
-      for (int j = 0; j < IPT; ++j) {
-        const uint32_t dg = ((uint32_t)r[j] >> shift) & (CM_RADIX - 1);
-        out[s_scatter[dg] + (j * RS_THREADS + tid)] = r[j];
-      }
-    } else {
-      for (uint32_t pos = tid; pos < n_here; pos += RS_THREADS) {
-        const unsigned long long r = s_k[pos];
-        const uint32_t dg = ((uint32_t)r >> shift) & (CM_RADIX - 1);
-        out[s_scatter[dg] + pos] = r;
-      }
-    }
-  } else {
-    KeyT* __restrict__ out_keys = reinterpret_cast<KeyT*>(odd ? p.keys_a : p.keys_b);
-    uint32_t* __restrict__ out_vals = odd ? p.vals_a : p.vals_b;
-    if (full) {
-#pragma unroll
-      for (int j0 = 0; j0 < IPT; j0 += 4) {
-        unsigned long long kk[4];
-        uint32_t vv[4];
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          kk[j] = s_k[(j0 + j) * RS_THREADS + tid];
-          vv[j] = s_v[(j0 + j) * RS_THREADS + tid];
+          for (int i = 0; i < IPT; ++i) {
+            uint2 r = make_uint2(0xFFFFFFFFu, 0u);
+            if (item0 + 32 * i < n_here) r = in[32 * i];
+            key[i] = (KeyT)r.x;
+            val[i] = r.y;
+          }
         }
+      } else {
+        const KeyT* __restrict__ in_keys = reinterpret_cast<const KeyT*>(odd ? p.keys_b : p.keys_a) + tile_base + item0;
+        const uint32_t* __restrict__ in_vals = (odd ? p.vals_b : p.vals_a) + tile_base + item0;
+        if (full) {
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const uint32_t dg = (uint32_t)(kk[j] >> shift) & (CM_RADIX - 1);
-          const uint32_t dst = s_scatter[dg] + ((j0 + j) * RS_THREADS + tid);
-          out_keys[dst] = (KeyT)kk[j];
-          out_vals[dst] = vv[j];
+          for (int i = 0; i < IPT; ++i) key[i] = in_keys[32 * i];
+#pragma unroll
+          for (int i = 0; i < IPT; ++i) val[i] = in_vals[32 * i];
+        } else {
+#pragma unroll
+          for (int i = 0; i < IPT; ++i) key[i] = (item0 + 32 * i < n_here) ? in_keys[32 * i] : ~(KeyT)0;
+#pragma unroll
+          for (int i = 0; i < IPT; ++i) val[i] = (item0 + 32 * i < n_here) ? in_vals[32 * i] : 0u;
         }
       }
-    } else {
-      for (uint32_t pos = tid; pos < n_here; pos += RS_THREADS) {
-        const unsigned long long kk = s_k[pos];
-        const uint32_t dg = (uint32_t)(kk >> shift) & (CM_RADIX - 1);
-        const uint32_t dst = s_scatter[dg] + pos;
-        out_keys[dst] = (KeyT)kk;
-        out_vals[dst] = s_v[pos];
+#pragma unroll
+      for (int k = 0; k < CM_RADIX / 32; ++k) wh[lane + 32 * k] = 0;
+      __syncwarp();
+      RS_TRACE(cur, 0, tr_cur);
+
+      // ---- stable rank of every key among the keys of its digit inside the warp ------------------------------------
+      // peers = lanes holding the same digit (ballot match, constant time; __match_any_sync costs one round per
+      // distinct value). Every lane reads the digit's counter; the highest peer lane writes it back advanced by the
+      // peer count. Shared-memory accesses of one warp are performed in program order; __syncwarp keeps the compiler
+      // from reordering them.
+      uint32_t rank[IPT];
+#pragma unroll
+      for (int i = 0; i < IPT; ++i) {
+        const uint32_t ks = (uint32_t)(key[i] >> shift);
+        const uint32_t diff = warp_diff8(ks);
+        const uint32_t below = (uint32_t)__popc(~diff & lt);
+        volatile uint32_t* c = wh + (ks & (CM_RADIX - 1));
+        const uint32_t r = *c + below;
+        rank[i] = r;
+        if ((~diff & gt) == 0u) *c = r + 1u;
+        __syncwarp();
       }
+      __syncthreads();
+      RS_TRACE(cur, 1, tr_cur);
+
+      // ---- per digit (one per thread): tile count -> published; prefix over digits and warps -> first positions -----
+      {
+        uint32_t wc[RS_WARPS];
+        uint32_t cnt = 0;
+#pragma unroll
+        for (int w = 0; w < RS_WARPS; ++w) {
+          wc[w] = sm.hist[w * CM_RADIX + tid];
+          cnt += wc[w];
+        }
+        const uint32_t real = (tid == CM_RADIX - 1) ? cnt - ((uint32_t)TILE - n_here) : cnt;
+        st_relaxed_u64(rows + (size_t)cur * CM_RADIX + tid, lb_pack(epoch, CM_LB_AGG, real));
+        RS_TRACE(cur, 2, tr_cur);
+        uint32_t tot;
+        const uint32_t bin_start = block_excl_scan_256(cnt, sm.scan, &tot);
+        uint32_t run = bin_start;
+#pragma unroll
+        for (int w = 0; w < RS_WARPS; ++w) {
+          sm.hist[w * CM_RADIX + tid] = run;
+          run += wc[w];
+        }
+        sm.scatter[buf][tid] = 0u - bin_start;  // completed in back() once the scanners have delivered the row
+      }
+      __syncthreads();
+      RS_TRACE(cur, 3, tr_cur);
+
+      // ---- keys and values into sorted-tile order in shared memory -------------------------------------------------
+#pragma unroll
+      for (int i = 0; i < IPT; ++i) {
+        const uint32_t ks = (uint32_t)(key[i] >> shift);
+        const uint32_t pos = wh[ks & (CM_RADIX - 1)] + rank[i];
+        if (AOS) {
+          sm.k[buf][pos] = ((unsigned long long)val[i] << 32) | (unsigned long long)key[i];
+        } else {
+          sm.k[buf][pos] = (unsigned long long)key[i];
+          sm.v[buf][pos] = val[i];
+        }
+      }
+      RS_TRACE(cur, 4, tr_cur);
     }
+    if (prev != 0xFFFFFFFFu) {
+      // ================================= back(prev) ===========================================================
+      const uint32_t pb = buf ^ 1u;
+      RS_TRACE(prev, 7, tr_prev);
+      // ---- one row from the scanners: where this tile's keys of digit d start in the output ----------------------
+      {
+        const uint32_t first = lb_wait_inclusive(rows + ((long long)prev - 1) * CM_RADIX + tid, epoch, err);
+        sm.scatter[pb][tid] += first;  // modulo 2^32
+      }
+      __syncthreads();
+      RS_TRACE(prev, 5, tr_prev);
+      // Claim the next tile now, not earlier: a tile claimed long before its front() runs holds back the published
+      // frontier for every later tile. The result is only needed after the scatter below, so its latency is hidden.
+      if (tid == 0 && have) claimed = atomicAdd(counter, 1u);
+      // ---- scatter: consecutive threads write consecutive addresses inside each digit's run -----------------------
+      // (two copies of the loop: the one for full tiles carries no bounds checks, so its shared-memory loads batch up)
+      const bool pfull = prev_n == (uint32_t)TILE;
+      const unsigned long long* sk = sm.k[pb];
+      const uint32_t* ssc = sm.scatter[pb];
+      if (AOS) {
+        unsigned long long* __restrict__ out = reinterpret_cast<unsigned long long*>(odd ? p.keys_a : p.keys_b);
+        if (pfull) {
+          unsigned long long r[IPT];
+#pragma unroll
+          for (int j = 0; j < IPT; ++j) r[j] = sk[j * RS_THREADS + tid];
+#pragma unroll
+          for (int j = 0; j < IPT; ++j) {
+            const uint32_t dg = ((uint32_t)r[j] >> shift) & (CM_RADIX - 1);
+            out[ssc[dg] + (j * RS_THREADS + tid)] = r[j];
+          }
+        } else {
+          for (uint32_t pos = tid; pos < prev_n; pos += RS_THREADS) {
+            const unsigned long long r = sk[pos];
+            const uint32_t dg = ((uint32_t)r >> shift) & (CM_RADIX - 1);
+            out[ssc[dg] + pos] = r;
+          }
+        }
+      } else {
+        KeyT* __restrict__ out_keys = reinterpret_cast<KeyT*>(odd ? p.keys_a : p.keys_b);
+        uint32_t* __restrict__ out_vals = odd ? p.vals_a : p.vals_b;
+        const uint32_t* sv = sm.v[pb];
+        if (pfull) {
+#pragma unroll
+          for (int j0 = 0; j0 < IPT; j0 += 4) {
+            unsigned long long kk[4];
+            uint32_t vv[4];
+#pragma unroll
+            for (int j = 0; j < 4 && j0 + j < IPT; ++j) {
+              kk[j] = sk[(j0 + j) * RS_THREADS + tid];
+              vv[j] = sv[(j0 + j) * RS_THREADS + tid];
+            }
+#pragma unroll
+            for (int j = 0; j < 4 && j0 + j < IPT; ++j) {
+              const uint32_t dg = (uint32_t)(kk[j] >> shift) & (CM_RADIX - 1);
+              const uint32_t dst = ssc[dg] + ((j0 + j) * RS_THREADS + tid);
+              out_keys[dst] = (KeyT)kk[j];
+              out_vals[dst] = vv[j];
+            }
+          }
+        } else {
+          for (uint32_t pos = tid; pos < prev_n; pos += RS_THREADS) {
+            const unsigned long long kk = sk[pos];
+            const uint32_t dg = (uint32_t)(kk >> shift) & (CM_RADIX - 1);
+            const uint32_t dst = ssc[dg] + pos;
+            out_keys[dst] = (KeyT)kk;
+            out_vals[dst] = sv[pos];
+          }
+        }
+      }
+      RS_TRACE(prev, 6, tr_prev);
+    } else if (tid == 0 && have) {
+      claimed = atomicAdd(counter, 1u);  // first iteration: nothing to scatter yet
+    }
+    if (!have) break;
+    if (tid == 0) sm.next_tile[buf ^ 1u] = claimed;
+    prev = cur;
+    prev_n = n_here;
+    buf ^= 1u;
+    // Orders this iteration's shared-memory reads (placement reads of the counter rows, scatter reads of the other
+    // buffer) before the next iteration's writes, and makes next_tile (written long ago by thread 0) visible.
+    __syncthreads();
+    cur = sm.next_tile[buf];
   }
-  RS_TRACE(6);
 }
 
 // 32-bit keys leave the sort as 8-byte (key, value) records; callers that want two plain arrays get them from here.
@@ -360,14 +437,40 @@ uint32_t sort_tile_items(uint32_t key_bytes) {
   return key_bytes == 4 ? RS_THREADS * SortCfg<uint32_t>::IPT : RS_THREADS * SortCfg<unsigned long long>::IPT;
 }
 
+static int g_sort_ctas_per_sm[2] = {0, 0};
+
+cudaError_t configure_sort_kernels() {
+  if (g_sort_ctas_per_sm[0] > 0) return cudaSuccess;
+  cudaError_t e = cudaFuncSetAttribute(k_onesweep_pass<uint32_t>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)sizeof(SortSmem<uint32_t>));
+  if (e != cudaSuccess) return e;
+  e = cudaFuncSetAttribute(k_onesweep_pass<unsigned long long>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                           (int)sizeof(SortSmem<unsigned long long>));
+  if (e != cudaSuccess) return e;
+  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&g_sort_ctas_per_sm[0], k_onesweep_pass<uint32_t>, RS_THREADS,
+                                                    sizeof(SortSmem<uint32_t>));
+  if (e != cudaSuccess) return e;
+  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&g_sort_ctas_per_sm[1], k_onesweep_pass<unsigned long long>,
+                                                    RS_THREADS, sizeof(SortSmem<unsigned long long>));
+  if (getenv("CM_DEBUG")) fprintf(stderr, "[cm] sort pass: %d / %d CTAs per SM (32-bit / 64-bit keys), %zu / %zu B smem\n",
+                                 g_sort_ctas_per_sm[0], g_sort_ctas_per_sm[1], sizeof(SortSmem<uint32_t>), sizeof(SortSmem<unsigned long long>));
+  return e;
+}
+
 cudaError_t launch_sort_pass(const VoxelParams& p, int pass, cudaStream_t stream) {
   const uint32_t tile = sort_tile_items(p.key_bytes);
   const uint32_t tiles = (p.max_points + tile - 1) / tile;
   if (tiles == 0) return cudaSuccess;
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  // persistent workers: at most what the device holds at once (tiles are handed out by an atomic counter)
+  const int per_sm = std::max(1, g_sort_ctas_per_sm[p.key_bytes == 4 ? 0 : 1]);
+  const uint32_t workers = std::min<uint32_t>(tiles, (uint32_t)(sms * per_sm) - RS_SCANNERS);
   if (p.key_bytes == 4)
-    k_onesweep_pass<uint32_t><<<tiles + RS_SCANNERS, RS_THREADS, 0, stream>>>(p, pass);
+    k_onesweep_pass<uint32_t><<<workers + RS_SCANNERS, RS_THREADS, sizeof(SortSmem<uint32_t>), stream>>>(p, pass);
   else
-    k_onesweep_pass<unsigned long long><<<tiles + RS_SCANNERS, RS_THREADS, 0, stream>>>(p, pass);
+    k_onesweep_pass<unsigned long long><<<workers + RS_SCANNERS, RS_THREADS, sizeof(SortSmem<unsigned long long>), stream>>>(p, pass);
   return cudaGetLastError();
 }
 

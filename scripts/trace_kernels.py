@@ -27,7 +27,7 @@ for _ in range(4):
 st = cm.stats()
 print("survivors", st.survivors, "voxels", st.voxels_out, "gpu_ms", st.gpu_ms)
 for which, name, labels in ((0, "transform_crop", ["desc+load", "xform+rank", "sync1", "rec+minmax", "(unused)", "stores"]),
-                            (1, "onesweep pass", ["setup", "load issue", "rank+sync", "scans", "lookback+sync", "place+sync", "scatter"])):
+                            (1, "onesweep pass", ["setup+load issue", "match+rank+sync", "counts published", "scans+sync", "placement", "row wait+sync", "scatter"])):
     nn = C.c_int64()
     cm._check(cm._lib.cm_debug_trace(cm._h, which, None, 0, C.byref(nn)))
     buf = np.zeros(nn.value, np.uint64)
@@ -35,6 +35,15 @@ for which, name, labels in ((0, "transform_crop", ["desc+load", "xform+rank", "s
     t = buf.reshape(-1, 8).astype(np.int64)
     t = t[t[:, len(labels) - 1] > 0]
     print("%s: %d tiles traced" % (name, len(t)))
+    if which == 1:
+        # stamps 0..4 (front) and 5, 6, 7 (back) are relative to the iteration in which the tile's front ran; 7 = back begins
+        t = t[t[:, 6] > 0]
+        cols = [("setup+load issue", t[:, 0]), ("match+rank+sync", t[:, 1] - t[:, 0]), ("counts published", t[:, 2] - t[:, 1]),
+                ("scans+sync", t[:, 3] - t[:, 2]), ("placement", t[:, 4] - t[:, 3]), ("(next tile's front)", t[:, 7] - t[:, 4]),
+                ("row wait+sync", t[:, 5] - t[:, 7]), ("scatter", t[:, 6] - t[:, 5])]
+        for lab, d in cols:
+            print("   %-20s median %7d  p90 %7d  mean %7d cycles" % (lab, np.median(d), np.percentile(d, 90), d.mean()))
+        continue
     prev = np.zeros(len(t), np.int64)
     for i, lab in enumerate(labels):
         if lab == "(unused)":
@@ -43,8 +52,4 @@ for which, name, labels in ((0, "transform_crop", ["desc+load", "xform+rank", "s
         prev = t[:, i]
         print("   %-18s median %7d  p90 %7d  mean %7d cycles" % (lab, np.median(d), np.percentile(d, 90), d.mean()))
     print("   %-18s median %7d  p90 %7d" % ("TOTAL", np.median(t[:, len(labels) - 1]), np.percentile(t[:, len(labels) - 1], 90)))
-    if which == 1:
-        steps, waits = t[:, 7] >> 32, t[:, 7] & 0xFFFFFFFF
-        print("   walk (digit 3): tiles traversed median %d p90 %d max %d; not-ready words median %d p90 %d" % (
-            np.median(steps), np.percentile(steps, 90), steps.max(), np.median(waits), np.percentile(waits, 90)))
 cm.close()
