@@ -75,13 +75,21 @@ __device__ __forceinline__ bool pass_keeps(const PassDev& ps, float x, float y, 
   return !(v >= ps.lo && v <= ps.hi);
 }
 
-template <int THREADS, int IPT, int MODE, bool BOX>
+// BOX: 0 = general PassThrough chain, 1 = one x/y/z box, 2 = box that also windows the intensity
+// min/max folded only when `on` (predicated instructions, no branch, no select)
+__device__ __forceinline__ void minmax_if(bool on, float v, float& mn, float& mx) {
+  asm("{\n .reg .pred p;\n setp.ne.s32 p, %2, 0;\n @p min.f32 %0, %0, %3;\n @p max.f32 %1, %1, %3;\n}"
+      : "+f"(mn), "+f"(mx)
+      : "r"((int)on), "f"(v));
+}
+
+template <int THREADS, int IPT, int MODE, int BOX>
 __global__ void __launch_bounds__(THREADS, (THREADS >= 512 ? 2 : 4)) k_transform_crop(const K1Params p) {
   constexpr int TILE = THREADS * IPT;
   constexpr int WARPS = THREADS / 32;
   extern __shared__ __align__(16) uint8_t stage[];
   __shared__ uint32_t s_warp_tot[WARPS], s_warp_inv[WARPS];
-  __shared__ float s_mm[WARPS][6];
+  __shared__ uint32_t s_mm[WARPS][6];  // order-preserving encodings: ~enc(min) x3, enc(max) x3
   __shared__ __align__(8) unsigned long long s_bar;
 
   const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
@@ -101,27 +109,43 @@ __global__ void __launch_bounds__(THREADS, (THREADS >= 512 ? 2 : 4)) k_transform
   const uint32_t li0 = warp * (32 * IPT) + lane;  // local index of item 0; item i is li0 + 32*i
 
   // ---- unpack -------------------------------------------------------------------------------------------------
+  const bool full = n_here == (uint32_t)TILE;
   if (MODE == (int)SEG_PACKED16) {
-    const uint8_t* base = data + (size_t)pt0 * 16;
+    const uint8_t* base = data + ((size_t)pt0 + li0) * 16;
+    if (full) {  // no bounds checks: eight independent 16-byte loads at constant offsets
 #pragma unroll
-    for (int i = 0; i < IPT; ++i) {
-      const uint32_t li = li0 + 32 * i;
-      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (li < n_here) v = ldg_stream_f4(base + (size_t)li * 16);
-      x[i] = v.x; y[i] = v.y; z[i] = v.z; it[i] = v.w;
+      for (int i = 0; i < IPT; ++i) {
+        const float4 v = ldg_stream_f4(base + (size_t)i * (32 * 16));
+        x[i] = v.x; y[i] = v.y; z[i] = v.z; it[i] = v.w;
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < IPT; ++i) {
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (li0 + 32 * i < n_here) v = ldg_stream_f4(base + (size_t)i * (32 * 16));
+        x[i] = v.x; y[i] = v.y; z[i] = v.z; it[i] = v.w;
+      }
     }
   } else if (MODE == (int)SEG_PCL32) {
-    const uint8_t* base = data + (size_t)pt0 * 32;
+    const uint8_t* base = data + ((size_t)pt0 + li0) * 32;
+    if (full) {
 #pragma unroll
-    for (int i = 0; i < IPT; ++i) {
-      const uint32_t li = li0 + 32 * i;
-      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-      float w = 0.f;
-      if (li < n_here) {
-        v = ldg_stream_f4(base + (size_t)li * 32);
-        w = ldg_stream_f1(base + (size_t)li * 32 + 16);
+      for (int i = 0; i < IPT; ++i) {
+        const float4 v = ldg_stream_f4(base + (size_t)i * (32 * 32));
+        const float w = ldg_stream_f1(base + (size_t)i * (32 * 32) + 16);
+        x[i] = v.x; y[i] = v.y; z[i] = v.z; it[i] = w;
       }
-      x[i] = v.x; y[i] = v.y; z[i] = v.z; it[i] = w;
+    } else {
+#pragma unroll
+      for (int i = 0; i < IPT; ++i) {
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        float w = 0.f;
+        if (li0 + 32 * i < n_here) {
+          v = ldg_stream_f4(base + (size_t)i * (32 * 32));
+          w = ldg_stream_f1(base + (size_t)i * (32 * 32) + 16);
+        }
+        x[i] = v.x; y[i] = v.y; z[i] = v.z; it[i] = w;
+      }
     }
   } else {
     const uint32_t mode = sg->mode;
@@ -216,30 +240,27 @@ __global__ void __launch_bounds__(THREADS, (THREADS >= 512 ? 2 : 4)) k_transform
   const bool dense = sg->is_dense != 0;
 
   // ---- transform + crop predicate + in-warp ranks ------------------------------------------------------------------
+  // Branch-free per item: the bounding box is folded with predicated min/max, the box test is one predicate chain.
   uint32_t keep_bits = 0;   // bit i: item i survives
   uint32_t ballots[IPT];    // warp-uniform
   uint32_t inv_run = 0;
   float mn0 = 3.402823466e+38f, mn1 = mn0, mn2 = mn0, mx0 = -mn0, mx1 = -mn0, mx2 = -mn0;
+  const float lo0 = p.crop.lo[0], lo1 = p.crop.lo[1], lo2 = p.crop.lo[2], lo3 = p.crop.lo[3];
+  const float hi0 = p.crop.hi[0], hi1 = p.crop.hi[1], hi2 = p.crop.hi[2], hi3 = p.crop.hi[3];
 #pragma unroll
   for (int i = 0; i < IPT; ++i) {
-    const uint32_t li = li0 + 32 * i;
-    const bool in_range = li < n_here;
+    const bool in_range = full || (li0 + 32 * i < n_here);
     const float a = x[i], b = y[i], c = z[i];
-    bool keep;
+    bool keep, fold;
     if (BOX) {
       // a non-finite input coordinate makes every output row non-finite, and the box rejects those, so the
       // "leave invalid points of a non-dense cloud untransformed" rule needs no special case here
       x[i] = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(m[0], a), __fmul_rn(m[1], b)), __fmul_rn(m[2], c)), m[3]);
       y[i] = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(m[4], a), __fmul_rn(m[5], b)), __fmul_rn(m[6], c)), m[7]);
       z[i] = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(m[8], a), __fmul_rn(m[9], b)), __fmul_rn(m[10], c)), m[11]);
-      keep = in_range && x[i] >= p.crop.lo[0] && x[i] <= p.crop.hi[0] && y[i] >= p.crop.lo[1] && y[i] <= p.crop.hi[1] &&
-             z[i] >= p.crop.lo[2] && z[i] <= p.crop.hi[2];
-      if (p.crop.use_i) keep = keep && it[i] >= p.crop.lo[3] && it[i] <= p.crop.hi[3];
-      if (keep) {
-        mn0 = fminf(mn0, x[i]); mx0 = fmaxf(mx0, x[i]);
-        mn1 = fminf(mn1, y[i]); mx1 = fmaxf(mx1, y[i]);
-        mn2 = fminf(mn2, z[i]); mx2 = fmaxf(mx2, z[i]);
-      }
+      keep = in_range & (x[i] >= lo0) & (x[i] <= hi0) & (y[i] >= lo1) & (y[i] <= hi1) & (z[i] >= lo2) & (z[i] <= hi2);
+      if (BOX == 2) keep = keep & (it[i] >= lo3) & (it[i] <= hi3);
+      fold = keep;
     } else {
       const bool fin_in = finite_f32(a) && finite_f32(b) && finite_f32(c);
       if (dense || fin_in) {
@@ -254,13 +275,12 @@ __global__ void __launch_bounds__(THREADS, (THREADS >= 512 ? 2 : 4)) k_transform
         keep = keep && fin;
         for (int k = 0; k < n_pass; ++k) keep = keep && pass_keeps(p.crop.pass[k], x[i], y[i], z[i], it[i]);
       }
-      if (keep && fin) {
-        mn0 = fminf(mn0, x[i]); mx0 = fmaxf(mx0, x[i]);
-        mn1 = fminf(mn1, y[i]); mx1 = fmaxf(mx1, y[i]);
-        mn2 = fminf(mn2, z[i]); mx2 = fmaxf(mx2, z[i]);
-      }
+      fold = keep && fin;
       inv_run += __popc(__ballot_sync(0xFFFFFFFFu, keep && !fin));
     }
+    minmax_if(fold, x[i], mn0, mx0);
+    minmax_if(fold, y[i], mn1, mx1);
+    minmax_if(fold, z[i], mn2, mx2);
     ballots[i] = __ballot_sync(0xFFFFFFFFu, keep);
     keep_bits |= (keep ? 1u : 0u) << i;
   }
@@ -268,56 +288,53 @@ __global__ void __launch_bounds__(THREADS, (THREADS >= 512 ? 2 : 4)) k_transform
 #pragma unroll
   for (int i = 0; i < IPT; ++i) warp_run += __popc(ballots[i]);
 
-  // ---- bounding box of the survivors (pcl::getMinMax3D) ----------------------------------------------------------------
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
-    mn0 = fminf(mn0, __shfl_xor_sync(0xFFFFFFFFu, mn0, o)); mx0 = fmaxf(mx0, __shfl_xor_sync(0xFFFFFFFFu, mx0, o));
-    mn1 = fminf(mn1, __shfl_xor_sync(0xFFFFFFFFu, mn1, o)); mx1 = fmaxf(mx1, __shfl_xor_sync(0xFFFFFFFFu, mx1, o));
-    mn2 = fminf(mn2, __shfl_xor_sync(0xFFFFFFFFu, mn2, o)); mx2 = fmaxf(mx2, __shfl_xor_sync(0xFFFFFFFFu, mx2, o));
-  }
+  // ---- bounding box of the survivors (pcl::getMinMax3D): one integer max-reduction per bound on the order-preserving
+  // encodings (REDUX) instead of five shuffle rounds on six floats
+  const uint32_t e0 = __reduce_max_sync(0xFFFFFFFFu, ~f32_order_enc(__float_as_uint(mn0)));
+  const uint32_t e1 = __reduce_max_sync(0xFFFFFFFFu, ~f32_order_enc(__float_as_uint(mn1)));
+  const uint32_t e2 = __reduce_max_sync(0xFFFFFFFFu, ~f32_order_enc(__float_as_uint(mn2)));
+  const uint32_t e3 = __reduce_max_sync(0xFFFFFFFFu, f32_order_enc(__float_as_uint(mx0)));
+  const uint32_t e4 = __reduce_max_sync(0xFFFFFFFFu, f32_order_enc(__float_as_uint(mx1)));
+  const uint32_t e5 = __reduce_max_sync(0xFFFFFFFFu, f32_order_enc(__float_as_uint(mx2)));
   if (lane == 0) {
     s_warp_tot[warp] = warp_run;
     s_warp_inv[warp] = inv_run;
-    s_mm[warp][0] = mn0; s_mm[warp][1] = mn1; s_mm[warp][2] = mn2;
-    s_mm[warp][3] = mx0; s_mm[warp][4] = mx1; s_mm[warp][5] = mx2;
+    s_mm[warp][0] = e0; s_mm[warp][1] = e1; s_mm[warp][2] = e2;
+    s_mm[warp][3] = e3; s_mm[warp][4] = e4; s_mm[warp][5] = e5;
   }
   K1_TRACE(1);
   __syncthreads();
   K1_TRACE(2);
 
   // ---- tile-local compaction: positions inside the tile's own slot range; the dense offset comes from k_tile_scan -----
-  uint32_t tot = 0, inv = 0, pos = 0;
-#pragma unroll
-  for (int w = 0; w < WARPS; ++w) {
-    const uint32_t c = s_warp_tot[w];
-    if ((uint32_t)w < warp) pos += c;
-    tot += c;
-    inv += s_warp_inv[w];
+  // every warp scans the (<= 32) warp totals with shuffles: lane w holds warp w's count
+  uint32_t tot, inv, pos;
+  {
+    const uint32_t c = lane < (uint32_t)WARPS ? s_warp_tot[lane] : 0u;
+    const uint32_t incl = warp_incl_scan_u32(c);
+    pos = __shfl_sync(0xFFFFFFFFu, incl - c, warp);
+    tot = __shfl_sync(0xFFFFFFFFu, incl, 31);
+    inv = 0;
+    if (!BOX) inv = warp_sum_u32(lane < (uint32_t)WARPS ? s_warp_inv[lane] : 0u);
   }
   const uint32_t slot0 = sg->slot_base + pt0;
-  if (tid == 0) {
+  if (warp == 0) {
     const uint32_t frame = sg->frame;
-    TileRec rec;
-    rec.count = tot; rec.slot0 = slot0; rec.frame = frame; rec.dense0 = 0;
-    *reinterpret_cast<uint4*>(p.tile_rec + tile) = *reinterpret_cast<const uint4*>(&rec);
-    if (inv) {
-      atomicAdd(&p.acc[frame].n_invalid, inv);
-      atomicOr(&p.ctrl->has_invalid, 1u);
-    }
-    if (tot > inv) {  // at least one finite survivor: fold the tile's box into the frame's
-      float a0 = s_mm[0][0], a1 = s_mm[0][1], a2 = s_mm[0][2], b0 = s_mm[0][3], b1 = s_mm[0][4], b2 = s_mm[0][5];
-#pragma unroll
-      for (int w = 1; w < WARPS; ++w) {
-        a0 = fminf(a0, s_mm[w][0]); a1 = fminf(a1, s_mm[w][1]); a2 = fminf(a2, s_mm[w][2]);
-        b0 = fmaxf(b0, s_mm[w][3]); b1 = fmaxf(b1, s_mm[w][4]); b2 = fmaxf(b2, s_mm[w][5]);
+    if (lane == 0) {
+      TileRec rec;
+      rec.count = tot; rec.slot0 = slot0; rec.frame = frame; rec.dense0 = 0;
+      *reinterpret_cast<uint4*>(p.tile_rec + tile) = *reinterpret_cast<const uint4*>(&rec);
+      if (inv) {
+        atomicAdd(&p.acc[frame].n_invalid, inv);
+        atomicOr(&p.ctrl->has_invalid, 1u);
       }
+    }
+    if (tot > inv && lane < 6) {  // at least one finite survivor: fold the tile's box into the frame's (lane k: bound k)
+      uint32_t e = s_mm[0][lane];
+#pragma unroll
+      for (int w = 1; w < WARPS; ++w) e = max(e, s_mm[w][lane]);
       FrameAcc* fa = p.acc + frame;
-      atomicMax(&fa->nmin_enc[0], ~f32_order_enc(__float_as_uint(a0)));
-      atomicMax(&fa->nmin_enc[1], ~f32_order_enc(__float_as_uint(a1)));
-      atomicMax(&fa->nmin_enc[2], ~f32_order_enc(__float_as_uint(a2)));
-      atomicMax(&fa->max_enc[0], f32_order_enc(__float_as_uint(b0)));
-      atomicMax(&fa->max_enc[1], f32_order_enc(__float_as_uint(b1)));
-      atomicMax(&fa->max_enc[2], f32_order_enc(__float_as_uint(b2)));
+      atomicMax(lane < 3 ? &fa->nmin_enc[lane] : &fa->max_enc[lane - 3], e);
     }
   }
   K1_TRACE(3);
@@ -326,12 +343,13 @@ __global__ void __launch_bounds__(THREADS, (THREADS >= 512 ? 2 : 4)) k_transform
   pos += slot0;
   const uint32_t src0 = sg->src_base + pt0 + li0;
   const uint32_t lt = lanemask_lt();
+  const bool want_src = p.surv_src != nullptr;
 #pragma unroll
   for (int i = 0; i < IPT; ++i) {
     if (keep_bits & (1u << i)) {
       const uint32_t q = pos + __popc(ballots[i] & lt);
       p.surv_xyzi[q] = make_float4(x[i], y[i], z[i], it[i]);
-      if (p.surv_src) p.surv_src[q] = src0 + 32 * i;
+      if (want_src) p.surv_src[q] = src0 + 32 * i;
     }
     pos += __popc(ballots[i]);
   }
@@ -339,11 +357,13 @@ __global__ void __launch_bounds__(THREADS, (THREADS >= 512 ? 2 : 4)) k_transform
 }
 
 template <int THREADS, int IPT>
-cudaError_t launch_cfg(const K1Params& p, int mode, bool box, uint32_t smem, cudaStream_t stream) {
+cudaError_t launch_cfg(const K1Params& p, int mode, int box, uint32_t smem, cudaStream_t stream) {
 #define CM_K1_LAUNCH(MODE, BOX) k_transform_crop<THREADS, IPT, MODE, BOX><<<p.n_tiles, THREADS, smem, stream>>>(p)
-  if (mode == (int)SEG_PACKED16) { if (box) CM_K1_LAUNCH((int)SEG_PACKED16, true); else CM_K1_LAUNCH((int)SEG_PACKED16, false); }
-  else if (mode == (int)SEG_PCL32) { if (box) CM_K1_LAUNCH((int)SEG_PCL32, true); else CM_K1_LAUNCH((int)SEG_PCL32, false); }
-  else { if (box) CM_K1_LAUNCH(MODE_GENERIC, true); else CM_K1_LAUNCH(MODE_GENERIC, false); }
+#define CM_K1_BOX(MODE) do { if (box == 1) CM_K1_LAUNCH(MODE, 1); else if (box == 2) CM_K1_LAUNCH(MODE, 2); else CM_K1_LAUNCH(MODE, 0); } while (0)
+  if (mode == (int)SEG_PACKED16) CM_K1_BOX((int)SEG_PACKED16);
+  else if (mode == (int)SEG_PCL32) CM_K1_BOX((int)SEG_PCL32);
+  else CM_K1_BOX(MODE_GENERIC);
+#undef CM_K1_BOX
 #undef CM_K1_LAUNCH
   return cudaGetLastError();
 }
@@ -364,19 +384,23 @@ cudaError_t configure_device_kernels() {
   const int big = 200 * 1024;  // the host falls back to 1024-point tiles when a staged layout needs more
   const int small = (int)k1_staged_smem(1024u, CM_MAX_STAGED_STEP);
   cudaError_t e;
-  e = cudaFuncSetAttribute(k_transform_crop<512, 8, MODE_GENERIC, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
+  e = cudaFuncSetAttribute(k_transform_crop<512, 8, MODE_GENERIC, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
   if (e != cudaSuccess) return e;
-  e = cudaFuncSetAttribute(k_transform_crop<512, 8, MODE_GENERIC, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
+  e = cudaFuncSetAttribute(k_transform_crop<512, 8, MODE_GENERIC, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
   if (e != cudaSuccess) return e;
-  e = cudaFuncSetAttribute(k_transform_crop<256, 4, MODE_GENERIC, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, small);
+  e = cudaFuncSetAttribute(k_transform_crop<512, 8, MODE_GENERIC, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
   if (e != cudaSuccess) return e;
-  return cudaFuncSetAttribute(k_transform_crop<256, 4, MODE_GENERIC, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, small);
+  e = cudaFuncSetAttribute(k_transform_crop<256, 4, MODE_GENERIC, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, small);
+  if (e != cudaSuccess) return e;
+  e = cudaFuncSetAttribute(k_transform_crop<256, 4, MODE_GENERIC, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, small);
+  if (e != cudaSuccess) return e;
+  return cudaFuncSetAttribute(k_transform_crop<256, 4, MODE_GENERIC, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, small);
 }
 
 cudaError_t launch_transform_crop(const K1Params& p, uint32_t tile_points, int mode, uint32_t staged_smem_bytes,
                                   cudaStream_t stream) {
   if (p.n_tiles == 0) return cudaSuccess;
-  const bool box = p.crop.is_box != 0;
+  const int box = p.crop.is_box ? (p.crop.use_i ? 2 : 1) : 0;
   if (tile_points == 4096u) return launch_cfg<512, 8>(p, mode, box, staged_smem_bytes, stream);
   return launch_cfg<256, 4>(p, mode, box, staged_smem_bytes, stream);
 }
