@@ -22,8 +22,8 @@ constexpr int KH_IPT = 8;
 constexpr int KH_TILE = VX_THREADS * KH_IPT;  // 2048 points per min/max tile
 constexpr int KH_DENSE_TILE = 4096;           // virtual tile of the key kernel when the input is a plain dense cloud
 constexpr int SCAN_THREADS = 1024;
-constexpr int CE_IPT = 4;
-constexpr int CE_TILE = VX_THREADS * CE_IPT;  // 1024 sorted items per centroid tile
+constexpr int CE_IPT = 8;
+constexpr int CE_TILE = VX_THREADS * CE_IPT;  // 2048 sorted items per centroid tile
 
 // Exclusive scan of one value per thread over a 1024-thread block. Returns the exclusive prefix; *total = block sum.
 __device__ __forceinline__ uint32_t block_excl_scan_1024(uint32_t v, uint32_t* scratch /* 33 words */, uint32_t* total) {
@@ -372,16 +372,24 @@ __global__ void __launch_bounds__(VX_THREADS) k_voxel_key_hist(const VoxelParams
 // order: the float accumulation below is sequential in that order (one valid order of PCL's CentroidPoint loop, whose
 // own order is unspecified because std::sort is unstable). centroid = sum / (float)n with an IEEE division.
 //
-// Every thread first gathers the points of its own four sorted items (independent loads, all in flight together) and
-// parks them with their keys in shared memory; the thread that owns the head of a run then walks the run in shared
-// memory, so the dependent chain per element is a shared-memory read, not two global round trips. Only the part of a
-// run that continues past the tile is read from global memory.
+// Two phases per 2048-item tile, both with every lane busy:
+//   per item  (thread t owns items 8t .. 8t+7): records in with 16-byte loads, neighbour keys by shuffle, head-of-run
+//             and min-points flags as bit masks, the points of surviving runs gathered into shared memory (independent
+//             loads, all in flight together), one head bit per item into a shared bit array;
+//   per voxel (thread r owns the r-th surviving run of the tile, found through the block scan of the per-thread
+//             counts): end of run from the head bit array, sequential sum over shared memory (the part of a run that
+//             continues past the tile is read from global memory), division, coalesced tile-local output.
+// The first version did the per-voxel work in the thread that owned the head item: with ~1 surviving head per 8 items
+// the warp executed the whole epilogue (four divisions, stores, atomics) for a handful of active lanes at a time, and
+// the kernel issued 190 instructions per item.
 template <typename KeyT>
-__global__ void __launch_bounds__(VX_THREADS) k_voxel_centroid(const VoxelParams p) {
+__global__ void __launch_bounds__(VX_THREADS, 4) k_voxel_centroid(const VoxelParams p) {
+  constexpr bool REC = sizeof(KeyT) == 4;  // 8-byte (key, value) records
   __shared__ uint32_t s_scan[9];
   __shared__ __align__(16) float4 s_pts[CE_TILE];
-  __shared__ __align__(16) KeyT s_keys[CE_TILE + 1];
-  const uint32_t tid = threadIdx.x;
+  __shared__ uint32_t s_headw[CE_TILE / 32 + 1];  // bit i: item i starts a run; bit tile_n: sentinel
+  __shared__ unsigned short s_start[CE_TILE];     // tile-local position of the r-th surviving run
+  const uint32_t tid = threadIdx.x, lane = tid & 31u;
   const uint32_t F = p.n_frames;
   const uint32_t M = p.frame_surv_start[F];
   const uint32_t n_tiles = (M + CE_TILE - 1) / CE_TILE;
@@ -395,106 +403,146 @@ __global__ void __launch_bounds__(VX_THREADS) k_voxel_centroid(const VoxelParams
   const void* __restrict__ sorted = odd ? p.keys_b : p.keys_a;
   const uint32_t* __restrict__ vals = odd ? p.vals_b : p.vals_a;
   auto key_at = [&](uint32_t i) -> KeyT {
-    if constexpr (sizeof(KeyT) == 4) return (KeyT) reinterpret_cast<const uint2*>(sorted)[i].x;
+    if constexpr (REC) return (KeyT) reinterpret_cast<const uint2*>(sorted)[i].x;
     else return reinterpret_cast<const KeyT*>(sorted)[i];
   };
   auto val_at = [&](uint32_t i) -> uint32_t {
-    if constexpr (sizeof(KeyT) == 4) return reinterpret_cast<const uint2*>(sorted)[i].y;
+    if constexpr (REC) return reinterpret_cast<const uint2*>(sorted)[i].y;
     else return vals[i];
   };
-  const unsigned long long limit = (si.key_frames > F) ? ((unsigned long long)F << idx_bits) : ~0ull;
+  const bool has_sentinel = si.key_frames > F;  // non-finite points were keyed into an extra frame: never emitted
+  const unsigned long long limit = (unsigned long long)F << idx_bits;
   const unsigned long long idx_mask = idx_bits >= 64 ? ~0ull : ((1ull << idx_bits) - 1ull);
   const uint32_t m_req = p.min_points > 1u ? p.min_points : 1u;
 
   const uint32_t tile_base = tile * CE_TILE;
   const uint32_t tile_n = min((uint32_t)CE_TILE, M - tile_base);
-  const uint32_t loc = tid * CE_IPT;           // tile-local index of this thread's first item
+  const uint32_t loc = tid * CE_IPT;  // tile-local index of this thread's first item
   const uint32_t base = tile_base + loc;
+
+  // ---- per item -----------------------------------------------------------------------------------------------------
   KeyT k[CE_IPT];
   uint32_t v[CE_IPT];
+  if (base + CE_IPT <= M) {
+    if constexpr (REC) {
+      const uint4* src = reinterpret_cast<const uint4*>(reinterpret_cast<const uint2*>(sorted) + base);
 #pragma unroll
-  for (int j = 0; j < CE_IPT; ++j) {
-    const bool in = loc + j < tile_n;
-    if constexpr (sizeof(KeyT) == 4) {
-      const uint2 r = in ? reinterpret_cast<const uint2*>(sorted)[base + j] : make_uint2(0u, 0u);
-      k[j] = (KeyT)r.x;
-      v[j] = r.y;
+      for (int j = 0; j < CE_IPT; j += 2) {
+        const uint4 r = src[j / 2];
+        k[j] = (KeyT)r.x; v[j] = r.y; k[j + 1] = (KeyT)r.z; v[j + 1] = r.w;
+      }
     } else {
+      const ulonglong2* ks = reinterpret_cast<const ulonglong2*>(reinterpret_cast<const KeyT*>(sorted) + base);
+      const uint4* vs = reinterpret_cast<const uint4*>(vals + base);
+#pragma unroll
+      for (int j = 0; j < CE_IPT; j += 2) {
+        const ulonglong2 r = ks[j / 2];
+        k[j] = (KeyT)r.x; k[j + 1] = (KeyT)r.y;
+      }
+#pragma unroll
+      for (int j = 0; j < CE_IPT; j += 4) {
+        const uint4 r = vs[j / 4];
+        v[j] = r.x; v[j + 1] = r.y; v[j + 2] = r.z; v[j + 3] = r.w;
+      }
+    }
+  } else {
+#pragma unroll
+    for (int j = 0; j < CE_IPT; ++j) {
+      const bool in = base + j < M;
       k[j] = in ? key_at(base + j) : (KeyT)0;
       v[j] = in ? val_at(base + j) : 0u;
     }
   }
-  KeyT prev = (KeyT)0, next = (KeyT)0;
-  const bool has_prev = base > 0 && loc < tile_n;
-  const bool has_next = base + CE_IPT < M;
-  if (has_prev) prev = key_at(base - 1);
-  if (has_next) next = key_at(base + CE_IPT);
-  // With min_points <= 2 a point is needed only when its run survives the filter: every point for 1, a point with an
-  // equal neighbour for 2. Singleton voxels (most of a sparse lidar frame) are then never gathered.
+  // keys of the items just before and just after this thread's eight
+  KeyT prev = (KeyT)__shfl_up_sync(0xFFFFFFFFu, k[CE_IPT - 1], 1);
+  KeyT next = (KeyT)__shfl_down_sync(0xFFFFFFFFu, k[0], 1);
+  if (lane == 0 && base > 0 && base < M) prev = key_at(base - 1);
+  if (lane == 31 && base + CE_IPT < M) next = key_at(base + CE_IPT);
+  // eq bit j: item j exists and continues the run of item j-1 (bit CE_IPT: the item after this thread's last)
+  uint32_t eq = 0, valid = 0;
 #pragma unroll
   for (int j = 0; j < CE_IPT; ++j) {
-    if (loc + j < tile_n) {
-      bool need = m_req != 2u;
-      if (!need) {
-        const bool eq_prev = (j == 0) ? (has_prev && prev == k[0]) : (k[j - 1] == k[j]);
-        const bool eq_next = (j == CE_IPT - 1) ? (has_next && next == k[j]) : (loc + j + 1 < tile_n ? k[j + 1] == k[j] : (base + j + 1 < M && key_at(base + j + 1) == k[j]));
-        need = eq_prev || eq_next;
-      }
-      if (need) s_pts[loc + j] = __ldg(p.pts + v[j]);
-      s_keys[loc + j] = k[j];
-    }
+    const bool in = base + j < M;
+    const KeyT before = j == 0 ? prev : k[j - 1];
+    valid |= (in ? 1u : 0u) << j;
+    eq |= ((in && (base + j > 0) && k[j] == before) ? 1u : 0u) << j;
   }
-
-  uint32_t passbits = 0, cnt = 0;
+  eq |= ((base + CE_IPT < M && next == k[CE_IPT - 1]) ? 1u : 0u) << CE_IPT;
+  const uint32_t head = valid & ~eq;  // bits 0..7
+  // which heads survive the min-points filter, and which points are therefore needed
+  uint32_t pass = head, need = valid;
+  if (m_req == 2u) {
+    pass = head & (eq >> 1);          // the next item continues the run
+    need = valid & (eq | (eq >> 1));  // the item has an equal neighbour
+  } else if (m_req > 2u) {
+    pass = 0;
 #pragma unroll
-  for (int j = 0; j < CE_IPT; ++j) {
-    const uint32_t i = base + j;
-    if (loc + j < tile_n) {
-      const bool head = (i == 0) || (k[j] != (j == 0 ? prev : k[j - 1]));
-      if (head) {
-        bool ok = (unsigned long long)k[j] < limit;
-        if (ok && m_req > 1u) {
-          const unsigned long long i2 = (unsigned long long)i + m_req - 1ull;
-          ok = i2 < (unsigned long long)M && key_at((uint32_t)i2) == k[j];
-        }
-        if (ok) { passbits |= 1u << j; ++cnt; }
+    for (int j = 0; j < CE_IPT; ++j) {
+      if (head & (1u << j)) {
+        const unsigned long long i2 = (unsigned long long)base + j + m_req - 1ull;
+        if (i2 < (unsigned long long)M && key_at((uint32_t)i2) == k[j]) pass |= 1u << j;
       }
     }
   }
+  if (has_sentinel) {
+#pragma unroll
+    for (int j = 0; j < CE_IPT; ++j)
+      if ((unsigned long long)k[j] >= limit) pass &= ~(1u << j);
+  }
+#pragma unroll
+  for (int j = 0; j < CE_IPT; ++j)
+    if (need & (1u << j)) s_pts[loc + j] = __ldg(p.pts + v[j]);
+  reinterpret_cast<unsigned char*>(s_headw)[tid] = (unsigned char)head;  // bit position 8*tid + j == item loc + j
+  if (tid == 0) s_headw[CE_TILE / 32] = 0u;
+  const uint32_t cnt = (uint32_t)__popc(pass);
 
   uint32_t total;
   const uint32_t excl_thread = block_excl_scan_256(cnt, s_scan, &total);  // also orders the shared-memory staging
-  // tile-local output: this tile's voxels go to tmp[tile_base + rank]; k_scan_u32 + k_compact_voxels make them dense
-  if (tid == 0) p.cent_count[tile] = total;
+  {
+    uint32_t r = excl_thread, pm = pass;
+    while (pm) {
+      const uint32_t j = (uint32_t)__ffs(pm) - 1u;
+      pm &= pm - 1u;
+      s_start[r++] = (unsigned short)(loc + j);
+    }
+    if (tid == 0) {
+      atomicOr(&s_headw[tile_n >> 5], 1u << (tile_n & 31u));  // sentinel: every run ends at the end of the tile at the latest
+      p.cent_count[tile] = total;  // this tile's voxels go to tmp[tile_base + r]; k_scan_u32 + k_compact_voxels make them dense
+    }
+  }
+  __syncthreads();
 
   // per-frame voxel counts: one atomic per tile unless the tile straddles frames
-  bool per_head_count = false;
+  bool per_voxel_count = false;
   if (F == 1) {
     if (tid == 0 && total) atomicAdd(&p.acc[0].voxel_count, total);
   } else {
-    const unsigned long long f_first = (unsigned long long)s_keys[0] >> idx_bits;
-    const unsigned long long f_last = (unsigned long long)s_keys[tile_n - 1] >> idx_bits;
+    const unsigned long long f_first = (unsigned long long)key_at(tile_base) >> idx_bits;
+    const unsigned long long f_last = (unsigned long long)key_at(tile_base + tile_n - 1) >> idx_bits;
     if (f_first == f_last) {
       if (tid == 0 && total && f_first < F) atomicAdd(&p.acc[f_first].voxel_count, total);
     } else {
-      per_head_count = true;
+      per_voxel_count = true;
     }
   }
 
-  uint32_t slot = tile_base + excl_thread;
-#pragma unroll
-  for (int j = 0; j < CE_IPT; ++j) {
-    if (!(passbits & (1u << j))) continue;
-    const KeyT key = k[j];
-    uint32_t q = loc + j;
+  // ---- per voxel ----------------------------------------------------------------------------------------------------
+  for (uint32_t r = tid; r < total; r += VX_THREADS) {
+    const uint32_t s0 = s_start[r];
+    const KeyT key = key_at(tile_base + s0);
+    // end of the run inside the tile: the next head bit after s0 (the sentinel at tile_n bounds the search)
+    uint32_t q = s0 + 1u;
+    uint32_t w = q >> 5;
+    uint32_t bits = s_headw[w] & (0xFFFFFFFFu << (q & 31u));
+    while (bits == 0u) bits = s_headw[++w];
+    const uint32_t end = (w << 5) + (uint32_t)__ffs(bits) - 1u;
     float sx = 0.f, sy = 0.f, sz = 0.f, sw = 0.f;
-    uint32_t n = 0;
-    do {  // the part of the run inside this tile: shared memory
+    for (q = s0; q < end; ++q) {
       const float4 pt = s_pts[q];
       sx = __fadd_rn(sx, pt.x); sy = __fadd_rn(sy, pt.y); sz = __fadd_rn(sz, pt.z); sw = __fadd_rn(sw, pt.w);
-      ++n; ++q;
-    } while (q < tile_n && s_keys[q] == key);
-    if (q == tile_n) {  // the run may continue in the following tiles: global memory
+    }
+    uint32_t n = end - s0;
+    if (end == tile_n) {  // the run may continue in the following tiles: global memory
       uint32_t g = tile_base + tile_n;
       while (g < M && key_at(g) == key) {
         const float4 pt = __ldg(p.pts + val_at(g));
@@ -505,14 +553,14 @@ __global__ void __launch_bounds__(VX_THREADS) k_voxel_centroid(const VoxelParams
     const float nf = (float)n;
     const float cx = __fdiv_rn(sx, nf), cy = __fdiv_rn(sy, nf), cz = __fdiv_rn(sz, nf);
     const float ci = p.downsample_all ? __fdiv_rn(sw, nf) : 0.f;
+    const uint32_t slot = tile_base + r;
     reinterpret_cast<float4*>(p.tmp_xyzi)[slot] = make_float4(cx, cy, cz, ci);
     p.tmp_count[slot] = n;
     p.tmp_idx[slot] = (unsigned long long)key & idx_mask;
-    if (per_head_count) {
+    if (per_voxel_count) {
       const unsigned long long f = (unsigned long long)key >> idx_bits;
       if (f < F) atomicAdd(&p.acc[f].voxel_count, 1u);
     }
-    ++slot;
   }
 }
 
