@@ -271,21 +271,21 @@ __global__ void __launch_bounds__(VX_THREADS) k_grid_setup(const VoxelParams p) 
 // ---- voxel key per point + the digit histograms of every radix pass -----------------------------------------------------
 // Walks the K1 tiles: tile t contributes rec.count survivors read from slots [slot0, slot0+count) and written densely at
 // [dense0, dense0+count): key = (frame << idx_bits) | idx, value = slot (what the centroid pass gathers by).
-template <typename KeyT>
-__global__ void __launch_bounds__(VX_THREADS) k_voxel_key_hist(const VoxelParams p) {
-  __shared__ uint32_t s_hist[CM_MAX_SORT_PASSES][CM_RADIX];
-  const uint32_t tid = threadIdx.x, lane = tid & 31u;
-  for (uint32_t i = tid; i < CM_MAX_SORT_PASSES * CM_RADIX; i += VX_THREADS) (&s_hist[0][0])[i] = 0;
-  __syncthreads();
-
+// Histograms: one shared-memory increment per key and pass. The hardware aggregates lanes that hit the same counter
+// (SASS ATOMS.POPC.INC), so neither the warp-uniform high digits nor the scattered low digits need software matching.
+// CHECK: non-finite survivors are possible (no crop pass configured) and get the sentinel frame; any PassThrough stage
+// rejects them, so the common instantiation carries no finite tests.
+template <typename KeyT, bool CHECK>
+__device__ __forceinline__ void key_hist_tiles(const VoxelParams& p, uint32_t (*s_hist)[CM_RADIX], const SortInfo& si,
+                                               uint32_t M) {
+  const uint32_t tid = threadIdx.x;
   const uint32_t F = p.n_frames;
-  const uint32_t M = p.frame_surv_start[F];
-  const SortInfo si = *p.info;
   const uint32_t n_pass = si.num_passes, idx_bits = si.idx_bits;
   const bool dense = p.tile_rec == nullptr;
   const uint32_t n_tiles = dense ? (M + KH_DENSE_TILE - 1) / KH_DENSE_TILE : p.n_k1_tiles;
   KeyT* __restrict__ keys = reinterpret_cast<KeyT*>(p.keys_a);
   uint32_t* __restrict__ vals = p.vals_a;
+  uint2* __restrict__ recs = reinterpret_cast<uint2*>(p.keys_a);
   const unsigned long long sentinel = (unsigned long long)F << idx_bits;
   const float inv0 = p.inv_leaf[0], inv1 = p.inv_leaf[1], inv2 = p.inv_leaf[2];
 
@@ -299,69 +299,69 @@ __global__ void __launch_bounds__(VX_THREADS) k_voxel_key_hist(const VoxelParams
       r.count = q.x; r.slot0 = q.y; r.frame = q.z; r.dense0 = q.w;
     }
     if (r.count == 0) continue;
-    const GridDev g = p.grid[r.frame];
+    const GridDev* __restrict__ g = p.grid + r.frame;
     const KeyT fbits = (KeyT)((unsigned long long)r.frame << idx_bits);
-    const KeyT mul1 = (KeyT)g.mul1, mul2 = (KeyT)g.mul2;  // 32-bit arithmetic when the key is 32-bit
-    const int mb0 = g.min_b[0], mb1 = g.min_b[1], mb2 = g.min_b[2];
+    const KeyT mul1 = (KeyT)g->mul1, mul2 = (KeyT)g->mul2;  // 32-bit arithmetic when the key is 32-bit
+    const int mb0 = g->min_b[0], mb1 = g->min_b[1], mb2 = g->min_b[2];
+    const float4* __restrict__ src = p.pts + r.slot0;
     constexpr int U = 4;  // points per thread in flight
-    const uint32_t rounds = (r.count + U * VX_THREADS - 1) / (U * VX_THREADS);
-    for (uint32_t it = 0; it < rounds; ++it) {
+    for (uint32_t j0 = 0; j0 < r.count; j0 += U * VX_THREADS) {
+      const bool whole = j0 + U * VX_THREADS <= r.count;
       float4 pv[U];
+      if (whole) {
 #pragma unroll
-      for (int u = 0; u < U; ++u) {
-        const uint32_t j = (it * U + u) * VX_THREADS + tid;
-        pv[u] = (j < r.count) ? ldg_stream_f4(p.pts + r.slot0 + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int u = 0; u < U; ++u) pv[u] = ldg_stream_f4(src + j0 + u * VX_THREADS + tid);
+      } else {
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          const uint32_t j = j0 + u * VX_THREADS + tid;
+          pv[u] = (j < r.count) ? ldg_stream_f4(src + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
       }
 #pragma unroll
       for (int u = 0; u < U; ++u) {
-        const uint32_t j = (it * U + u) * VX_THREADS + tid;
-        const bool valid = j < r.count;
+        const uint32_t j = j0 + u * VX_THREADS + tid;
+        if (!whole && j >= r.count) continue;
         const float4 v = pv[u];
-        KeyT key = 0;
-        if (valid) {
-          if (finite_f32(v.x) && finite_f32(v.y) && finite_f32(v.z)) {
-            // PCL: ijk = (int)(floor(x * inv) - (float)min_b); here in integers (identical below 2^24 cells)
-            const KeyT i0 = (KeyT)((int)floorf(__fmul_rn(v.x, inv0)) - mb0);
-            const KeyT i1 = (KeyT)((int)floorf(__fmul_rn(v.y, inv1)) - mb1);
-            const KeyT i2 = (KeyT)((int)floorf(__fmul_rn(v.z, inv2)) - mb2);
-            key = fbits | (KeyT)(i0 + i1 * mul1 + i2 * mul2);
-          } else {
-            key = (KeyT)sentinel;
-          }
-          if (sizeof(KeyT) == 4) {  // 32-bit keys travel as 8-byte (key, value) records
-            reinterpret_cast<uint2*>(p.keys_a)[r.dense0 + j] = make_uint2((uint32_t)key, r.slot0 + j);
-          } else {
-            keys[r.dense0 + j] = key;
-            vals[r.dense0 + j] = r.slot0 + j;
-          }
+        // PCL: ijk = (int)(floor(x * inv) - (float)min_b); here in integers (identical below 2^24 cells)
+        const KeyT i0 = (KeyT)(__float2int_rd(__fmul_rn(v.x, inv0)) - mb0);
+        const KeyT i1 = (KeyT)(__float2int_rd(__fmul_rn(v.y, inv1)) - mb1);
+        const KeyT i2 = (KeyT)(__float2int_rd(__fmul_rn(v.z, inv2)) - mb2);
+        KeyT key = fbits | (KeyT)(i0 + i1 * mul1 + i2 * mul2);
+        if (CHECK && !(finite_f32(v.x) && finite_f32(v.y) && finite_f32(v.z))) key = (KeyT)sentinel;
+        if (sizeof(KeyT) == 4) {  // 32-bit keys travel as 8-byte (key, value) records
+          recs[r.dense0 + j] = make_uint2((uint32_t)key, r.slot0 + j);
+        } else {
+          keys[r.dense0 + j] = key;
+          vals[r.dense0 + j] = r.slot0 + j;
         }
-        // digit histograms. Bits on which all valid lanes of the warp agree are found with two warp reductions; a digit
-        // made only of such bits (the frame bits, the high cell bits of a spatially coherent tile) is added once per warp.
-        const uint32_t vmask = __ballot_sync(0xFFFFFFFFu, valid);
-        if (vmask) {
-          const uint32_t klo = (uint32_t)key;
-          uint32_t diff_lo = __reduce_or_sync(0xFFFFFFFFu, valid ? klo : 0u) ^ __reduce_and_sync(0xFFFFFFFFu, valid ? klo : 0xFFFFFFFFu);
-          uint32_t diff_hi = 0;
-          if (sizeof(KeyT) == 8) {
-            const uint32_t khi = (uint32_t)((unsigned long long)key >> 32);
-            diff_hi = __reduce_or_sync(0xFFFFFFFFu, valid ? khi : 0u) ^ __reduce_and_sync(0xFFFFFFFFu, valid ? khi : 0xFFFFFFFFu);
-          }
-          const unsigned long long diff = ((unsigned long long)diff_hi << 32) | diff_lo;
-          const int leader = __ffs(vmask) - 1;
-          for (uint32_t ps = 0; ps < n_pass; ++ps) {
-            const uint32_t d = (uint32_t)((unsigned long long)key >> (ps * CM_RADIX_BITS)) & (CM_RADIX - 1);
-            if (((diff >> (ps * CM_RADIX_BITS)) & (CM_RADIX - 1)) == 0) {
-              if ((int)lane == leader) atomicAdd(&s_hist[ps][d], (uint32_t)__popc(vmask));
-            } else if (valid) {
-              atomicAdd(&s_hist[ps][d], 1u);
-            }
-          }
+        if (sizeof(KeyT) == 4) {
+#pragma unroll
+          for (uint32_t ps = 0; ps < 4; ++ps)
+            if (ps < n_pass) atomicAdd(&s_hist[ps][((uint32_t)key >> (ps * CM_RADIX_BITS)) & (CM_RADIX - 1)], 1u);
+        } else {
+#pragma unroll
+          for (uint32_t ps = 0; ps < CM_MAX_SORT_PASSES; ++ps)
+            if (ps < n_pass)
+              atomicAdd(&s_hist[ps][(uint32_t)((unsigned long long)key >> (ps * CM_RADIX_BITS)) & (CM_RADIX - 1)], 1u);
         }
       }
     }
   }
+}
+
+template <typename KeyT>
+__global__ void __launch_bounds__(VX_THREADS) k_voxel_key_hist(const VoxelParams p) {
+  __shared__ uint32_t s_hist[CM_MAX_SORT_PASSES][CM_RADIX];
+  const uint32_t tid = threadIdx.x;
+  for (uint32_t i = tid; i < CM_MAX_SORT_PASSES * CM_RADIX; i += VX_THREADS) (&s_hist[0][0])[i] = 0;
   __syncthreads();
-  for (uint32_t i = tid; i < n_pass * CM_RADIX; i += VX_THREADS) {
+  const uint32_t M = p.frame_surv_start[p.n_frames];
+  const SortInfo si = *p.info;
+  if (si.key_frames > p.n_frames) key_hist_tiles<KeyT, true>(p, s_hist, si, M);
+  else key_hist_tiles<KeyT, false>(p, s_hist, si, M);
+  __syncthreads();
+  for (uint32_t i = tid; i < si.num_passes * CM_RADIX; i += VX_THREADS) {
     const uint32_t c = (&s_hist[0][0])[i];
     if (c) atomicAdd(p.hist + i, c);
   }
