@@ -112,11 +112,12 @@ def load() -> C.CDLL:
     global _LIB
     if _LIB is not None:
         return _LIB
-    if not os.path.exists(LIB_PATH):
+    path = os.environ.get("CM_LIB_PATH") or LIB_PATH  # CM_LIB_PATH: a differently tuned build of the same library (experiments)
+    if not os.path.exists(path):
         raise RuntimeError(
             "cloud_merger_b200: %s is missing. Build it with `python -m cloud_merger_b200.build` "
-            "(nvcc, sm_100a). There is no CPU fallback." % LIB_PATH)
-    lib = C.CDLL(LIB_PATH)
+            "(nvcc, sm_100a). There is no CPU fallback." % path)
+    lib = C.CDLL(path)
     for name, (res, args) in SYMBOLS.items():
         fn = getattr(lib, name)  # AttributeError if the library does not export a declared symbol
         fn.restype = res

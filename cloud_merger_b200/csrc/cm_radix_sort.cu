@@ -28,21 +28,37 @@ namespace cm {
 
 namespace {
 
-#ifndef RS_MIN_CTAS
-#define RS_MIN_CTAS 3
+// Shape of a worker CTA (overridable for experiments): threads, keys per thread (32-bit / 64-bit keys), CTAs per SM.
+// Measured on B200, cfg2 batch, ms for the four passes: 256x16x3 0.311-0.323, 512x8x2 0.352, 320x14x2 0.324, 384x12x2 0.302;
+// publishing the digit counts before the ranking (RS_EARLY_COUNT) cost more than the shorter row wait returned (0.32).
+#ifndef RS_THREADS_CFG
+#define RS_THREADS_CFG 384
 #endif
-constexpr int RS_THREADS = 256;
+#ifndef RS_IPT32
+#define RS_IPT32 12
+#endif
+#ifndef RS_IPT64
+#define RS_IPT64 8
+#endif
+#ifndef RS_MIN_CTAS
+#define RS_MIN_CTAS 2
+#endif
+#ifndef RS_EARLY_COUNT
+#define RS_EARLY_COUNT 0
+#endif
+constexpr int RS_THREADS = RS_THREADS_CFG;
+static_assert(RS_THREADS >= CM_RADIX && RS_THREADS % 32 == 0, "one thread per digit is needed");
 constexpr int RS_WARPS = RS_THREADS / 32;
 
 template <typename KeyT>
 struct SortCfg;
 template <>
 struct SortCfg<uint32_t> {
-  static constexpr int IPT = 16;
+  static constexpr int IPT = RS_IPT32;
 };
 template <>
 struct SortCfg<unsigned long long> {
-  static constexpr int IPT = 10;  // 2 x (20 + 10) KB of sorted-tile buffers: three CTAs per SM like the 32-bit variant
+  static constexpr int IPT = RS_IPT64;
 };
 
 // ---- scanner CTAs -------------------------------------------------------------------------------------------------------
@@ -65,7 +81,7 @@ struct SortCfg<unsigned long long> {
 constexpr int RS_SCANNERS = 8;
 constexpr int RS_SCAN_DIGITS = CM_RADIX / RS_SCANNERS;  // 32: one digit per lane
 constexpr int RS_SCAN_ROWS = 32;                        // rows per batch (one warp)
-constexpr int RS_SCAN_GROUP = 16;                       // rows polled together
+constexpr int RS_SCAN_GROUP = RS_THREADS >= 512 ? 8 : 16;  // rows polled together (register budget of the CTA shape)
 static_assert(RS_SCAN_DIGITS == 32, "one digit per lane");
 
 __device__ __forceinline__ void scanner_cta(unsigned long long* rows /* row 0 */, uint32_t n_tiles, uint32_t epoch,
@@ -75,8 +91,8 @@ __device__ __forceinline__ void scanner_cta(unsigned long long* rows /* row 0 */
   const uint32_t d = blockIdx.x * RS_SCAN_DIGITS + lane;  // digit
   // exclusive scan of the global digit histogram: where digit d starts in the output of this pass
   uint32_t tot;
-  const uint32_t gb = block_excl_scan_256(hist[tid], s_scan, &tot);
-  s_tmp[tid] = gb;
+  const uint32_t gb = block_excl_scan_256(tid < CM_RADIX ? hist[tid] : 0u, s_scan, &tot);
+  if (tid < CM_RADIX) s_tmp[tid] = gb;
   __syncthreads();
   if (q == 0) {
     const uint32_t run0 = s_tmp[d];
@@ -173,6 +189,7 @@ struct SortSmem {
   uint32_t hist[RS_WARPS * CM_RADIX];  // per-warp digit counters, then per-warp first positions
   uint32_t scatter[2][CM_RADIX];       // global position of sorted-tile position 0 of digit d
   uint32_t scan[12];
+  uint32_t cnt[CM_RADIX];              // RS_EARLY_COUNT: the tile's digit counts, taken before the ranking
   uint32_t next_tile[2];               // written by thread 0 one iteration ahead (parity-indexed)
 };
 
@@ -216,6 +233,7 @@ __global__ void __launch_bounds__(RS_THREADS, RS_MIN_CTAS) k_onesweep_pass(const
   // so the scanners' latency (poll + chain + store + our poll, ~4-6 thousand cycles) hides behind front(t1) instead of
   // idling a third of the SM's warps as it did when a CTA handled one tile from start to end.
   if (tid == 0) sm.next_tile[0] = atomicAdd(counter, 1u);
+  if (RS_EARLY_COUNT && tid < CM_RADIX) sm.cnt[tid] = 0;
   __syncthreads();
   uint32_t cur = sm.next_tile[0];
   uint32_t prev = 0xFFFFFFFFu, prev_n = 0;
@@ -275,6 +293,19 @@ __global__ void __launch_bounds__(RS_THREADS, RS_MIN_CTAS) k_onesweep_pass(const
       for (int k = 0; k < CM_RADIX / 32; ++k) wh[lane + 32 * k] = 0;
       __syncwarp();
       RS_TRACE(cur, 0, tr_cur);
+      if (RS_EARLY_COUNT) {
+        // The tile's digit counts go out before the (long) ranking: one hardware-aggregated shared-memory increment per
+        // key (ATOMS.POPC.INC). The later a tile publishes, the longer every tile after it waits for its row.
+#pragma unroll
+        for (int i = 0; i < IPT; ++i) atomicAdd(&sm.cnt[(uint32_t)(key[i] >> shift) & (CM_RADIX - 1)], 1u);
+        __syncthreads();
+        if (RS_THREADS == CM_RADIX || tid < CM_RADIX) {
+          const uint32_t c = sm.cnt[tid];
+          sm.cnt[tid] = 0;  // for the next tile (no increments can follow in this iteration)
+          const uint32_t real = (tid == CM_RADIX - 1) ? c - ((uint32_t)TILE - n_here) : c;
+          st_relaxed_u64(rows + (size_t)cur * CM_RADIX + tid, lb_pack(epoch, CM_LB_AGG, real));
+        }
+      }
 
       // ---- stable rank of every key among the keys of its digit inside the warp ------------------------------------
       // peers = lanes holding the same digit (ballot match, constant time; __match_any_sync costs one round per
@@ -298,25 +329,32 @@ __global__ void __launch_bounds__(RS_THREADS, RS_MIN_CTAS) k_onesweep_pass(const
 
       // ---- per digit (one per thread): tile count -> published; prefix over digits and warps -> first positions -----
       {
+        const bool dt = RS_THREADS == CM_RADIX || tid < CM_RADIX;  // digit threads
         uint32_t wc[RS_WARPS];
         uint32_t cnt = 0;
+        if (dt) {
 #pragma unroll
-        for (int w = 0; w < RS_WARPS; ++w) {
-          wc[w] = sm.hist[w * CM_RADIX + tid];
-          cnt += wc[w];
+          for (int w = 0; w < RS_WARPS; ++w) {
+            wc[w] = sm.hist[w * CM_RADIX + tid];
+            cnt += wc[w];
+          }
+          if (!RS_EARLY_COUNT) {
+            const uint32_t real = (tid == CM_RADIX - 1) ? cnt - ((uint32_t)TILE - n_here) : cnt;
+            st_relaxed_u64(rows + (size_t)cur * CM_RADIX + tid, lb_pack(epoch, CM_LB_AGG, real));
+          }
         }
-        const uint32_t real = (tid == CM_RADIX - 1) ? cnt - ((uint32_t)TILE - n_here) : cnt;
-        st_relaxed_u64(rows + (size_t)cur * CM_RADIX + tid, lb_pack(epoch, CM_LB_AGG, real));
         RS_TRACE(cur, 2, tr_cur);
         uint32_t tot;
         const uint32_t bin_start = block_excl_scan_256(cnt, sm.scan, &tot);
-        uint32_t run = bin_start;
+        if (dt) {
+          uint32_t run = bin_start;
 #pragma unroll
-        for (int w = 0; w < RS_WARPS; ++w) {
-          sm.hist[w * CM_RADIX + tid] = run;
-          run += wc[w];
+          for (int w = 0; w < RS_WARPS; ++w) {
+            sm.hist[w * CM_RADIX + tid] = run;
+            run += wc[w];
+          }
+          sm.scatter[buf][tid] = 0u - bin_start;  // completed in back() once the scanners have delivered the row
         }
-        sm.scatter[buf][tid] = 0u - bin_start;  // completed in back() once the scanners have delivered the row
       }
       __syncthreads();
       RS_TRACE(cur, 3, tr_cur);
@@ -340,7 +378,7 @@ __global__ void __launch_bounds__(RS_THREADS, RS_MIN_CTAS) k_onesweep_pass(const
       const uint32_t pb = buf ^ 1u;
       RS_TRACE(prev, 7, tr_prev);
       // ---- one row from the scanners: where this tile's keys of digit d start in the output ----------------------
-      {
+      if (RS_THREADS == CM_RADIX || tid < CM_RADIX) {
         const uint32_t first = lb_wait_inclusive(rows + ((long long)prev - 1) * CM_RADIX + tid, epoch, err);
         sm.scatter[pb][tid] += first;  // modulo 2^32
       }
