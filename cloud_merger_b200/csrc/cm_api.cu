@@ -322,7 +322,7 @@ void fill_voxel_params(cm_handle_t h, Workspace& w, VoxelParams& vp, const float
 }
 
 // VoxelGrid stages on vp.pts. bounded: the crop box bounds the key width, so no device round trip is needed.
-int run_voxel(cm_handle_t h, Workspace& w, VoxelParams& vp, cudaStream_t st) {
+int run_voxel(cm_handle_t h, Workspace& w, VoxelParams& vp, cudaStream_t st, bool scan_k1_tiles = false) {
   unsigned long long cells = 0;
   const bool bounded = w.ran_k1 && crop_cell_bound(h, &cells);
   if (bounded) {
@@ -333,7 +333,11 @@ int run_voxel(cm_handle_t h, Workspace& w, VoxelParams& vp, cudaStream_t st) {
     vp.key_bytes = 8;
     vp.max_passes = CM_MAX_SORT_PASSES;
   }
-  CM_CUDA(h, launch_grid_setup(vp, st));
+  if (scan_k1_tiles)
+    CM_CUDA(h, launch_grid_setup(vp, st, w.tile_rec, w.n_k1_tiles, w.segs, w.n_segs,
+                                 reinterpret_cast<uint32_t*>(w.meta + w.ml.off_segstart)));
+  else
+    CM_CUDA(h, launch_grid_setup(vp, st));
   ++w.launches;
   if (h->profiling) CM_CUDA(h, cudaEventRecord(w.ev[EV_GRID], st));
   if (!bounded) {
@@ -495,15 +499,19 @@ int run_pipeline(cm_handle_t h, Workspace& w, const cm_segment_t* segs, int n_se
   w.n_k1_tiles = plan.n_tiles;
   w.dense_valid = false;
   CM_CUDA(h, launch_transform_crop(kp, plan.tile_points, plan.mode, plan.staged_smem, st));
-  CM_CUDA(h, launch_tile_scan(w.tile_rec, plan.n_tiles, w.segs, (uint32_t)n_seg, n_frames,
-                              reinterpret_cast<uint32_t*>(w.meta + w.ml.off_fstart),
-                              reinterpret_cast<uint32_t*>(w.meta + w.ml.off_segstart), st));
-  w.launches += 2;
+  ++w.launches;
+  if (!with_voxel) {
+    CM_CUDA(h, launch_tile_scan(w.tile_rec, plan.n_tiles, w.segs, (uint32_t)n_seg, n_frames,
+                                reinterpret_cast<uint32_t*>(w.meta + w.ml.off_fstart),
+                                reinterpret_cast<uint32_t*>(w.meta + w.ml.off_segstart), st));
+    ++w.launches;
+    CM_CUDA(h, cudaEventRecord(w.ev[EV_K1], st));
+    return CM_OK;
+  }
   CM_CUDA(h, cudaEventRecord(w.ev[EV_K1], st));
-  if (!with_voxel) return CM_OK;
   VoxelParams vp;
   fill_voxel_params(h, w, vp, w.surv_xyzi, n_frames, (uint32_t)total, epoch);
-  return run_voxel(h, w, vp, st);
+  return run_voxel(h, w, vp, st, true);  // the tile scan rides in the grid-setup launch
 }
 
 // Dense copy of the merged cropped cloud of the last K1 run (allocated on first use).

@@ -81,7 +81,9 @@ struct VoxelParams {
 cudaError_t launch_minmax(const float4* pts, uint32_t n, Ctrl* ctrl, FrameAcc* acc, uint32_t* frame_surv_start,
                           cudaStream_t stream);
 cudaError_t launch_seed_bounds(FrameAcc* acc, const float* mn, const float* mx, cudaStream_t stream);
-cudaError_t launch_grid_setup(const VoxelParams& p, cudaStream_t stream);
+// one CTA; when scan_rec is given it first does launch_tile_scan's work (K1 tile counts -> dense offsets, frame / segment starts)
+cudaError_t launch_grid_setup(const VoxelParams& p, cudaStream_t stream, TileRec* scan_rec = nullptr, uint32_t scan_tiles = 0,
+                              const SegDev* segs = nullptr, uint32_t n_seg = 0, uint32_t* seg_surv_start = nullptr);
 cudaError_t launch_key_hist(const VoxelParams& p, cudaStream_t stream);
 cudaError_t launch_sort_pass(const VoxelParams& p, int pass, cudaStream_t stream);
 // 32-bit keys are sorted as 8-byte (key, value) records in keys_a/keys_b; this splits the first *n_ptr records into two arrays

@@ -108,22 +108,37 @@ __global__ void __launch_bounds__(VX_THREADS) k_minmax(const float4* __restrict_
 }
 
 // ---- one CTA: dense offsets of the K1 tiles, frame / segment starts, total ------------------------------------------------
-__global__ void __launch_bounds__(SCAN_THREADS) k_tile_scan(TileRec* __restrict__ rec, uint32_t n_tiles,
-                                                           const SegDev* __restrict__ segs, uint32_t n_seg,
-                                                           uint32_t n_frames, uint32_t* frame_surv_start,
-                                                           uint32_t* seg_surv_start) {
-  __shared__ uint32_t s_scr[33];
+__device__ __forceinline__ void tile_scan_body(TileRec* __restrict__ rec, uint32_t n_tiles, const SegDev* __restrict__ segs,
+                                               uint32_t n_seg, uint32_t n_frames, uint32_t* frame_surv_start,
+                                               uint32_t* seg_surv_start, uint32_t* s_scr /* 33 words */) {
   const uint32_t tid = threadIdx.x;
   const uint32_t chunk = (n_tiles + SCAN_THREADS - 1) / SCAN_THREADS;
   const uint32_t b = min(n_tiles, tid * chunk), e = min(n_tiles, b + chunk);
+  // a single CTA is latency-bound: the counts of a thread's chunk are fetched eight at a time (independent loads) and,
+  // for chunks of up to eight tiles (batches of up to 8192 tiles), kept in registers for the second sweep
+  constexpr int W = 8;
+  uint32_t c[W];
   uint32_t sum = 0;
-  for (uint32_t i = b; i < e; ++i) sum += rec[i].count;
+  for (uint32_t i0 = b; i0 < e; i0 += W) {
+#pragma unroll
+    for (int k = 0; k < W; ++k) c[k] = (i0 + k < e) ? rec[i0 + k].count : 0u;
+#pragma unroll
+    for (int k = 0; k < W; ++k) sum += c[k];
+  }
   uint32_t total;
   uint32_t run = block_excl_scan_1024(sum, s_scr, &total);
-  for (uint32_t i = b; i < e; ++i) {
-    const uint32_t c = rec[i].count;
-    rec[i].dense0 = run;
-    run += c;
+  if (chunk <= (uint32_t)W) {
+#pragma unroll
+    for (int k = 0; k < W; ++k) {
+      if (b + k < e) rec[b + k].dense0 = run;
+      run += c[k];
+    }
+  } else {
+    for (uint32_t i = b; i < e; ++i) {
+      const uint32_t cc = rec[i].count;
+      rec[i].dense0 = run;
+      run += cc;
+    }
   }
   __syncthreads();  // dense0 of every tile is visible to the block
   for (uint32_t s = tid; s < n_seg; s += SCAN_THREADS) {
@@ -132,6 +147,14 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_tile_scan(TileRec* __restrict_
     if (segs[s].first_of_frame) frame_surv_start[segs[s].frame] = d0;
   }
   if (tid == 0) frame_surv_start[n_frames] = total;
+}
+
+__global__ void __launch_bounds__(SCAN_THREADS) k_tile_scan(TileRec* __restrict__ rec, uint32_t n_tiles,
+                                                           const SegDev* __restrict__ segs, uint32_t n_seg,
+                                                           uint32_t n_frames, uint32_t* frame_surv_start,
+                                                           uint32_t* seg_surv_start) {
+  __shared__ uint32_t s_scr[33];
+  tile_scan_body(rec, n_tiles, segs, n_seg, n_frames, frame_surv_start, seg_surv_start, s_scr);
 }
 
 // ---- one CTA: in-place exclusive scan of n counters (+ total) ----------------------------------------------------------
@@ -187,12 +210,24 @@ __global__ void k_seed_bounds(FrameAcc* acc, float mn0, float mn1, float mn2, fl
 // ---- grid per frame + sort plan (one block) -----------------------------------------------------------------------
 // PCL 1.8.1: min_b = floor(min_p * inv), max_b = floor(max_p * inv), div_b = max_b - min_b + 1, and the guard
 // dx*dy*dz > INT32_MAX with d = (int64)((max_p - min_p) * inv) + 1.
-__global__ void __launch_bounds__(VX_THREADS) k_grid_setup(const VoxelParams p) {
+// When the survivors come out of K1 the same CTA first turns the K1 tile counts into dense offsets (tile_scan_body):
+// one launch and one dependent-launch gap less on the critical path.
+struct TileScanArgs {
+  TileRec* rec;
+  uint32_t n_tiles;
+  const SegDev* segs;
+  uint32_t n_seg;
+  uint32_t* seg_surv_start;
+};
+__global__ void __launch_bounds__(SCAN_THREADS) k_grid_setup(const VoxelParams p, const TileScanArgs ts) {
   __shared__ uint32_t s_maxbits;
+  __shared__ uint32_t s_scr[33];
   const uint32_t tid = threadIdx.x;
   if (tid == 0) s_maxbits = 0;
+  if (ts.rec) tile_scan_body(ts.rec, ts.n_tiles, ts.segs, ts.n_seg, p.n_frames, const_cast<uint32_t*>(p.frame_surv_start),
+                             ts.seg_surv_start, s_scr);
   __syncthreads();
-  for (uint32_t f = tid; f < p.n_frames; f += VX_THREADS) {
+  for (uint32_t f = tid; f < p.n_frames; f += SCAN_THREADS) {
     const FrameAcc a = p.acc[f];
     GridDev g;
     g.pcl_overflow = 0;
@@ -620,8 +655,11 @@ cudaError_t launch_compact_survivors(const TileRec* tile_rec, uint32_t n_tiles, 
   return cudaGetLastError();
 }
 
-cudaError_t launch_grid_setup(const VoxelParams& p, cudaStream_t stream) {
-  k_grid_setup<<<1, VX_THREADS, 0, stream>>>(p);
+cudaError_t launch_grid_setup(const VoxelParams& p, cudaStream_t stream, TileRec* scan_rec, uint32_t scan_tiles,
+                              const SegDev* segs, uint32_t n_seg, uint32_t* seg_surv_start) {
+  TileScanArgs ts;
+  ts.rec = scan_rec; ts.n_tiles = scan_tiles; ts.segs = segs; ts.n_seg = n_seg; ts.seg_surv_start = seg_surv_start;
+  k_grid_setup<<<1, SCAN_THREADS, 0, stream>>>(p, ts);
   return cudaGetLastError();
 }
 
