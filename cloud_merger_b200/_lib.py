@@ -20,6 +20,19 @@ class CmPass(C.Structure):
     _fields_ = [("axis", C.c_int32), ("lo", C.c_float), ("hi", C.c_float), ("negative", C.c_int32)]
 
 
+CM_MAX_ZONES = 16
+CM_MAX_ZONE_PASSES = 4
+
+
+class CmZone(C.Structure):
+    _fields_ = [("n_pass", C.c_int32), ("pass_", CmPass * CM_MAX_ZONE_PASSES)]
+
+
+class CmZoneOut(C.Structure):
+    _fields_ = [("xyzi", C.c_void_p), ("src", C.c_void_p), ("begin", C.c_int64 * (CM_MAX_ZONES + 1)),
+                ("n_zones", C.c_int32), ("reserved", C.c_int32)]
+
+
 class CmLayout(C.Structure):
     _fields_ = [("point_step", C.c_int32), ("off_x", C.c_int32), ("off_y", C.c_int32), ("off_z", C.c_int32),
                 ("off_intensity", C.c_int32), ("is_dense", C.c_int32)]
@@ -90,6 +103,10 @@ SYMBOLS = {
     "cm_run_batch": (C.c_int, [_H, C.POINTER(CmSegment), C.c_int, C.c_void_p]),
     "cm_dev_transform_crop": (C.c_int, [_H, C.POINTER(CmSegment), C.c_int, C.c_void_p]),
     "cm_dev_voxelgrid": (C.c_int, [_H, C.c_void_p, C.c_int64, C.c_int, C.c_void_p]),
+    "cm_set_zones": (C.c_int, [_H, C.c_int, C.POINTER(CmZone)]),
+    "cm_dev_zone_split": (C.c_int, [_H, C.c_void_p, C.c_int64, C.c_void_p]),
+    "cm_get_zone_out": (C.c_int, [_H, C.POINTER(CmZoneOut)]),
+    "cm_zone_split": (C.c_int, [_H, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_int64, C.POINTER(C.c_int64)]),
     "cm_sync": (C.c_int, [_H]),
     "cm_get_stats": (C.c_int, [_H, C.POINTER(CmStats)]),
     "cm_get_device_out": (C.c_int, [_H, C.POINTER(CmDeviceOut)]),

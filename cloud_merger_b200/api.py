@@ -12,7 +12,8 @@ from typing import Iterable, List, Optional, Sequence, Tuple
 import numpy as np
 
 from . import _lib
-from ._lib import (CmConfig, CmDeviceOut, CmFrameInfo, CmFrameOut, CmLayout, CmPass, CmSegment, CmStats)
+from ._lib import (CM_MAX_ZONES, CM_MAX_ZONE_PASSES, CmConfig, CmDeviceOut, CmFrameInfo, CmFrameOut, CmLayout, CmPass,
+                   CmSegment, CmStats, CmZone, CmZoneOut)
 
 # ---- layouts the reference's sensors produce ------------------------------------------------------
 LAYOUT_PACKED16 = dict(point_step=16, off_x=0, off_y=4, off_z=8, off_intensity=12)   # float4 x y z intensity
@@ -157,6 +158,48 @@ class CloudMerger:
         for i, (axis, lo, hi, neg) in enumerate(passes):
             arr[i] = CmPass(int(axis), float(np.float32(lo)), float(np.float32(hi)), int(neg))
         self._check(self._lib.cm_set_crop(self._h, len(passes), arr))
+
+    # -- zone slicing: getCloudPart x5 + the z windows of removeGround in one pass (pc_preprocessing_main.cpp:49-92, 228-312)
+    def set_zones(self, zones: Sequence[Sequence[Tuple[int, float, float, int]]]):
+        """zones: one PassThrough chain [(axis, lo, hi, negative), ...] per zone (<= 16 zones of <= 4 stages)."""
+        zones = [list(z) for z in zones]
+        arr = (CmZone * max(len(zones), 1))()
+        for zi, chain in enumerate(zones):
+            if len(chain) > CM_MAX_ZONE_PASSES:
+                raise ValueError("a zone takes at most %d stages" % CM_MAX_ZONE_PASSES)
+            arr[zi].n_pass = len(chain)
+            for k, (axis, lo, hi, neg) in enumerate(chain):
+                arr[zi].pass_[k] = CmPass(int(axis), float(np.float32(lo)), float(np.float32(hi)), int(neg))
+        self._check(self._lib.cm_set_zones(self._h, len(zones), arr))
+        self._n_zones = len(zones)
+
+    def dev_zone_split(self, xyzi_ptr: int = 0, n_points: int = 0, stream: int = 0):
+        """Device form; xyzi_ptr = 0 splits the merged cropped cloud of the last transform_crop / run_batch."""
+        self._check(self._lib.cm_dev_zone_split(self._h, C.c_void_p(xyzi_ptr or None), C.c_int64(n_points),
+                                                C.c_void_p(stream or None)))
+
+    def zone_out(self):
+        """(list of (xyzi [n,4] float32, src [n] uint32) per zone) of the last device zone split, downloaded."""
+        zo = CmZoneOut()
+        self._check(self._lib.cm_get_zone_out(self._h, C.byref(zo)))
+        total = int(zo.begin[zo.n_zones])
+        xyzi = self.download(zo.xyzi, np.float32, total * 4).reshape(-1, 4) if total else np.zeros((0, 4), np.float32)
+        src = self.download(zo.src, np.uint32, total) if total else np.zeros(0, np.uint32)
+        return [(xyzi[zo.begin[z]:zo.begin[z + 1]], src[zo.begin[z]:zo.begin[z + 1]]) for z in range(zo.n_zones)]
+
+    def zone_split(self, xyzi: np.ndarray, capacity: Optional[int] = None):
+        """Host-buffer form: returns the same per-zone list for a [n,4] float32 cloud in host memory."""
+        a = np.ascontiguousarray(xyzi, np.float32).reshape(-1, 4)
+        n = len(a)
+        cap = int(capacity if capacity is not None else 2 * max(n, 1))
+        ox = np.empty((max(cap, 1), 4), np.float32)
+        osrc = np.empty(max(cap, 1), np.uint32)
+        begin = (C.c_int64 * (CM_MAX_ZONES + 1))()
+        self._check(self._lib.cm_zone_split(self._h, a.ctypes.data_as(C.c_void_p), C.c_int64(n),
+                                            ox.ctypes.data_as(C.c_void_p), osrc.ctypes.data_as(C.c_void_p),
+                                            C.c_int64(cap), begin))
+        nz = self._n_zones
+        return [(ox[begin[z]:begin[z + 1]].copy(), osrc[begin[z]:begin[z + 1]].copy()) for z in range(nz)]
 
     def set_voxel(self, leaf, min_points: int = 2, downsample_all: bool = True):
         leaf = np.broadcast_to(np.asarray(leaf, np.float32), (3,)).copy()

@@ -135,6 +135,21 @@ struct cm_handle_s {
   std::vector<cm_frame_info_t> frame_info;
   cm_stats_t stats{};
   float stage_ms[EV_COUNT]{};
+  // zone slicing (allocated on first use)
+  ZoneSet zones{};
+  struct ZoneWs {
+    size_t cap_points = 0, cap_out = 0;
+    unsigned short* mask = nullptr;
+    uint32_t *tile_count = nullptr, *tile_offset = nullptr, *zone_begin = nullptr, *overflow = nullptr;
+    float4* out_xyzi = nullptr;
+    uint32_t* out_src = nullptr;
+    float4* in_stage = nullptr;  // host-buffer form: the uploaded cloud
+    uint32_t* report = nullptr;  // pinned: zone_begin[CM_MAX_ZONES + 1] + overflow
+    cudaStream_t stream = nullptr;
+    bool ran = false;
+    int64_t launches = 0;
+    ZoneParams last{};           // the last split, so that its scatter can be repeated after the outputs grew
+  } zw;
   // host path
   std::vector<Slot> slots;
   std::vector<cudaStream_t> sensor_stream;
@@ -827,6 +842,12 @@ int cm_destroy(cm_handle_t h) {
     if (sl.done) cudaEventDestroy(sl.done);
   }
   for (auto& s : h->sensor_stream) if (s) cudaStreamDestroy(s);
+  {
+    auto& z = h->zw;
+    cudaFree(z.mask); cudaFree(z.tile_count); cudaFree(z.tile_offset); cudaFree(z.zone_begin); cudaFree(z.overflow);
+    cudaFree(z.out_xyzi); cudaFree(z.out_src); cudaFree(z.in_stage);
+    if (z.report) cudaFreeHost(z.report);
+  }
   delete h;
   return CM_OK;
 }
@@ -1001,6 +1022,156 @@ int cm_dev_voxelgrid(cm_handle_t h, const float* xyzi_dev, int64_t n_points, int
   }
   CM_CUDA(h, cudaEventRecord(w.ev[EV_K1], st));
   return run_voxel(h, w, vp, st);
+}
+
+// ---- zone slicing ---------------------------------------------------------------------------------------------------------
+int cm_set_zones(cm_handle_t h, int n_zones, const cm_zone_t* zones) {
+  if (!h || n_zones < 0 || n_zones > CM_MAX_ZONES || (n_zones > 0 && !zones)) return CM_E_INVALID;
+  std::lock_guard<std::mutex> lk(h->mu);
+  ZoneSet zs{};
+  zs.n_zones = n_zones;
+  for (int z = 0; z < n_zones; ++z) {
+    if (zones[z].n_pass < 0 || zones[z].n_pass > CM_MAX_ZONE_PASSES) return fail(h, CM_E_INVALID, "zone %d: bad n_pass", z);
+    zs.zone[z].n_pass = zones[z].n_pass;
+    for (int k = 0; k < zones[z].n_pass; ++k) {
+      const cm_pass_t& ps = zones[z].pass[k];
+      if (ps.axis < 0 || ps.axis > 3) return fail(h, CM_E_INVALID, "zone %d pass %d: bad axis", z, k);
+      zs.zone[z].pass[k].axis = ps.axis; zs.zone[z].pass[k].lo = ps.lo; zs.zone[z].pass[k].hi = ps.hi;
+      zs.zone[z].pass[k].negative = ps.negative ? 1 : 0;
+    }
+  }
+  h->zones = zs;
+  return CM_OK;
+}
+
+namespace {
+void zone_ws_free(cm_handle_s::ZoneWs& z) {
+  cudaFree(z.mask); cudaFree(z.tile_count); cudaFree(z.tile_offset); cudaFree(z.zone_begin); cudaFree(z.overflow);
+  cudaFree(z.out_xyzi); cudaFree(z.out_src); cudaFree(z.in_stage);
+  if (z.report) cudaFreeHost(z.report);
+  z = cm_handle_s::ZoneWs();
+}
+
+// capacity: the input may hold up to `points`; the zones together up to twice that (boundary duplicates are rare, but
+// zones are free to overlap)
+int zone_ws_ensure(cm_handle_t h, size_t points) {
+  cm_handle_s::ZoneWs& z = h->zw;
+  const size_t want = std::max<size_t>({points, (size_t)h->cfg.max_batch_points, (size_t)1});
+  if (z.cap_points >= want) return CM_OK;
+  zone_ws_free(z);
+  const size_t tiles = want / zone_tile_points() + 2;
+  CM_CUDA(h, dev_alloc(&z.mask, want));
+  CM_CUDA(h, dev_alloc(&z.tile_count, tiles * CM_MAX_ZONES));
+  CM_CUDA(h, dev_alloc(&z.tile_offset, tiles * CM_MAX_ZONES));
+  CM_CUDA(h, dev_alloc(&z.zone_begin, (size_t)CM_MAX_ZONES + 2));
+  CM_CUDA(h, dev_alloc(&z.overflow, (size_t)1));
+  z.cap_out = 2 * want;
+  CM_CUDA(h, dev_alloc(&z.out_xyzi, z.cap_out));
+  CM_CUDA(h, dev_alloc(&z.out_src, z.cap_out));
+  CM_CUDA(h, cudaMallocHost(reinterpret_cast<void**>(&z.report), sizeof(uint32_t) * (CM_MAX_ZONES + 2)));
+  z.cap_points = want;
+  return CM_OK;
+}
+
+int zone_run(cm_handle_t h, const float4* pts, int64_t n_points, cudaStream_t st) {
+  cm_handle_s::ZoneWs& z = h->zw;
+  if (h->zones.n_zones <= 0) return fail(h, CM_E_INVALID, "no zones configured (cm_set_zones)");
+  if (n_points < 0 || n_points > 0xFFFFFFF0ll) return fail(h, CM_E_INVALID, "bad n_points");
+  int rc = zone_ws_ensure(h, (size_t)n_points);
+  if (rc != CM_OK) return rc;
+  ZoneParams zp;
+  zp.pts = pts; zp.n_points = (uint32_t)n_points;
+  zp.n_tiles = (uint32_t)((n_points + zone_tile_points() - 1) / zone_tile_points());
+  zp.zones = h->zones;
+  zp.mask = z.mask; zp.tile_count = z.tile_count; zp.tile_offset = z.tile_offset; zp.zone_begin = z.zone_begin;
+  zp.overflow = z.overflow; zp.out_capacity = (uint32_t)std::min<size_t>(z.cap_out, 0xFFFFFFF0u);
+  zp.out_xyzi = z.out_xyzi; zp.out_src = z.out_src;
+  CM_CUDA(h, cudaMemsetAsync(z.overflow, 0, sizeof(uint32_t), st));
+  CM_CUDA(h, launch_zone_split(zp, st));
+  CM_CUDA(h, cudaMemcpyAsync(z.report, z.zone_begin, sizeof(uint32_t) * (CM_MAX_ZONES + 1), cudaMemcpyDeviceToHost, st));
+  CM_CUDA(h, cudaMemcpyAsync(z.report + CM_MAX_ZONES + 1, z.overflow, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+  z.stream = st; z.ran = true; z.launches = zp.n_tiles ? CM_ZONE_LAUNCHES : 1; z.last = zp;
+  return CM_OK;
+}
+}  // namespace
+
+int cm_dev_zone_split(cm_handle_t h, const float* xyzi_dev, int64_t n_points, void* stream) {
+  if (!h) return CM_E_INVALID;
+  std::lock_guard<std::mutex> lk(h->mu);
+  CM_CUDA(h, cudaSetDevice(h->device));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (xyzi_dev) {
+    if (reinterpret_cast<uintptr_t>(xyzi_dev) & 15u) return fail(h, CM_E_INVALID, "xyzi_dev must be 16-byte aligned");
+    return zone_run(h, reinterpret_cast<const float4*>(xyzi_dev), n_points, st);
+  }
+  // the merged cropped cloud of the last transform_crop run (what getROI hands to getCloudPart)
+  if (!h->last || !h->last->ran_k1) return fail(h, CM_E_INVALID, "no transform_crop result on this handle");
+  Workspace& w = *h->last;
+  int rc = fetch_report(h, w);
+  if (rc != CM_OK) return rc;
+  rc = materialize_dense(h, w);
+  if (rc != CM_OK) return rc;
+  CM_CUDA(h, cudaStreamSynchronize(w.stream));
+  return zone_run(h, w.dense_xyzi, h->stats.survivors, st);
+}
+
+int cm_get_zone_out(cm_handle_t h, cm_zone_out_t* out) {
+  if (!h || !out) return CM_E_INVALID;
+  std::lock_guard<std::mutex> lk(h->mu);
+  cm_handle_s::ZoneWs& z = h->zw;
+  if (!z.ran) return fail(h, CM_E_INVALID, "no zone split has run on this handle");
+  CM_CUDA(h, cudaSetDevice(h->device));
+  CM_CUDA(h, cudaStreamSynchronize(z.stream));
+  if (z.report[CM_MAX_ZONES + 1] && (size_t)z.report[CM_MAX_ZONES + 1] <= 0xFFFFFFF0u) {
+    // Overlapping zones hold more points together than the output arrays were sized for (twice the input): grow them to
+    // the size the scan found and repeat the scatter. The input cloud must still be where it was.
+    const size_t need = z.report[CM_MAX_ZONES + 1];
+    cudaFree(z.out_xyzi); cudaFree(z.out_src);
+    z.out_xyzi = nullptr; z.out_src = nullptr; z.cap_out = 0;
+    CM_CUDA(h, dev_alloc(&z.out_xyzi, need));
+    CM_CUDA(h, dev_alloc(&z.out_src, need));
+    z.cap_out = need;
+    z.last.out_xyzi = z.out_xyzi; z.last.out_src = z.out_src; z.last.out_capacity = (uint32_t)need;
+    CM_CUDA(h, cudaMemsetAsync(z.overflow, 0, sizeof(uint32_t), z.stream));
+    CM_CUDA(h, launch_zone_scatter(z.last, z.stream));
+    CM_CUDA(h, cudaStreamSynchronize(z.stream));
+    z.report[CM_MAX_ZONES + 1] = 0;
+    ++z.launches;
+  }
+  memset(out, 0, sizeof(*out));
+  out->n_zones = h->zones.n_zones;
+  for (int k = 0; k <= h->zones.n_zones; ++k) out->begin[k] = z.report[k];
+  out->xyzi = reinterpret_cast<const float*>(z.out_xyzi);
+  out->src = z.out_src;
+  if (z.report[CM_MAX_ZONES + 1])
+    return fail(h, CM_E_CAPACITY, "the zones hold %u points together, capacity is %zu", z.report[CM_MAX_ZONES + 1], z.cap_out);
+  return CM_OK;
+}
+
+int cm_zone_split(cm_handle_t h, const float* xyzi_host, int64_t n_points, float* out_xyzi, uint32_t* out_src,
+                  int64_t capacity, int64_t* out_begin) {
+  if (!h || !out_begin || n_points < 0 || (n_points > 0 && !xyzi_host)) return CM_E_INVALID;
+  cm_zone_out_t zo;
+  {
+    std::lock_guard<std::mutex> lk(h->mu);
+    CM_CUDA(h, cudaSetDevice(h->device));
+    int rc = zone_ws_ensure(h, (size_t)n_points);
+    if (rc != CM_OK) return rc;
+    cm_handle_s::ZoneWs& z = h->zw;
+    if (!z.in_stage) CM_CUDA(h, dev_alloc(&z.in_stage, z.cap_points));
+    CM_CUDA(h, cudaMemcpyAsync(z.in_stage, xyzi_host, (size_t)n_points * 16, cudaMemcpyHostToDevice, nullptr));
+    rc = zone_run(h, z.in_stage, n_points, nullptr);
+    if (rc != CM_OK) return rc;
+  }
+  int rc = cm_get_zone_out(h, &zo);
+  for (int k = 0; k <= zo.n_zones; ++k) out_begin[k] = zo.begin[k];
+  if (rc != CM_OK) return rc;
+  const int64_t total = zo.begin[zo.n_zones];
+  if (total > capacity) return fail(h, CM_E_CAPACITY, "the zones hold %lld points, caller capacity %lld", (long long)total, (long long)capacity);
+  std::lock_guard<std::mutex> lk(h->mu);
+  if (out_xyzi && total) CM_CUDA(h, cudaMemcpy(out_xyzi, zo.xyzi, (size_t)total * 16, cudaMemcpyDeviceToHost));
+  if (out_src && total) CM_CUDA(h, cudaMemcpy(out_src, zo.src, (size_t)total * 4, cudaMemcpyDeviceToHost));
+  return CM_OK;
 }
 
 int cm_sync(cm_handle_t h) {

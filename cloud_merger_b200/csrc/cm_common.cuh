@@ -69,6 +69,18 @@ struct CropDev {
   float lo[4], hi[4];
 };
 
+// ---- zone slicing (cm_zones.cu): several PassThrough chains evaluated in one pass ---------------------------------------
+#define CM_MAX_ZONES 16
+#define CM_MAX_ZONE_PASSES 4
+struct ZoneDev {
+  int32_t n_pass;
+  PassDev pass[CM_MAX_ZONE_PASSES];
+};
+struct ZoneSet {
+  int32_t n_zones;
+  ZoneDev zone[CM_MAX_ZONES];
+};
+
 // ---- one record per K1 tile: where the tile's survivors sit (tile-local compaction) and where they belong densely ----
 struct TileRec {
   uint32_t count;   // survivors of this tile; they occupy slots [slot0, slot0 + count)

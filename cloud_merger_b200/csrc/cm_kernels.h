@@ -92,6 +92,26 @@ cudaError_t launch_split_records(const void* records, uint32_t* keys, uint32_t* 
 cudaError_t launch_centroid(const VoxelParams& p, cudaStream_t stream);        // 3 launches: centroid, scan, compact
 #define CM_CENTROID_LAUNCHES 3
 
+// ---- zone slicing: multi-output PassThrough compaction (cm_zones.cu) -------------------------------------------------------
+struct ZoneParams {
+  const float4* pts;         // n packed xyzi points
+  uint32_t n_points;
+  uint32_t n_tiles;          // ceil(n_points / zone_tile_points())
+  ZoneSet zones;
+  unsigned short* mask;      // [n_points] zone membership of every point
+  uint32_t* tile_count;      // [n_zones][n_tiles]
+  uint32_t* tile_offset;     // [n_zones][n_tiles] where the tile's points of the zone start in the output
+  uint32_t* zone_begin;      // [n_zones + 1] zone z occupies [zone_begin[z], zone_begin[z+1]) of the output
+  uint32_t* overflow;        // set to the needed size when the zones together exceed out_capacity
+  uint32_t out_capacity;
+  float4* out_xyzi;
+  uint32_t* out_src;         // index of every output point in the input cloud
+};
+uint32_t zone_tile_points();
+cudaError_t launch_zone_split(const ZoneParams& p, cudaStream_t stream);  // 3 launches
+cudaError_t launch_zone_scatter(const ZoneParams& p, cudaStream_t stream);  // the last of them again, after out_* grew
+#define CM_ZONE_LAUNCHES 3
+
 uint32_t sort_tile_items(uint32_t key_bytes);
 uint32_t centroid_tile_items();
 

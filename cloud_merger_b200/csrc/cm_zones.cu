@@ -1,0 +1,201 @@
+// cm_zones.cu -- zone slicing: several PassThrough chains evaluated in ONE pass over a cloud, one order-preserving
+// compacted output per chain (multi-output stream compaction) for sm_100a.
+//
+// Replaces the per-sensor sequences of the reference that run pcl::PassThrough over the same cloud again and again
+// (paths relative to timspilak/cloud_merger):
+//   * getCloudPart x5 per sensor, each followed by the two z windows of removeGround
+//     (pcl_preprocessing/src/pc_preprocessing_main.cpp:49-59, 80-92, 228-312): 15 PassThrough runs + copies per cloud;
+//   * filter_ROI_R's three x ranges and remove_ground's two z windows (my_cloud_fusion/src/CloudFusionNode.h:145-216).
+// A "zone" is a chain of up to CM_MAX_ZONE_PASSES PassThrough stages (inclusive float window, non-finite rejected,
+// `negative` keeps the outside; chained stages AND together). Zones may overlap (the reference's x windows share their
+// end points: a point exactly on a boundary is copied into both neighbours) and need not cover the cloud (the z windows
+// leave the gap (z_max_g, z_max_g + 0.01)). Inside every zone the points keep their input order, like PassThrough.
+//
+// Three launches: k_zone_count (membership mask per point + per-tile counts per zone), k_zone_scan (one CTA: zone starts
+// and per-tile offsets), k_zone_scatter (ranks from warp ballots -> points and source indices to their final place).
+// Roofline: HBM. Algorithmic bytes = n * (16 read + 2 mask written + 16 + 2 read again) + sum(zone sizes) * (16 + 4).
+#include "cm_kernels.h"
+
+namespace cm {
+
+namespace {
+
+constexpr int ZN_THREADS = 256;
+constexpr int ZN_IPT = 4;
+constexpr int ZN_TILE = ZN_THREADS * ZN_IPT;  // 1024 points per tile
+constexpr int ZN_WARPS = ZN_THREADS / 32;
+
+__device__ __forceinline__ bool zone_pass_keeps(const PassDev& ps, const float4& v) {
+  const float f = ps.axis == 0 ? v.x : (ps.axis == 1 ? v.y : (ps.axis == 2 ? v.z : v.w));
+  if (!finite_f32(f)) return false;
+  if (!ps.negative) return !(f < ps.lo || f > ps.hi);
+  return !(f >= ps.lo && f <= ps.hi);
+}
+
+// membership of one point: bit z set iff every stage of zone z keeps it (PCL 1.8.1 PassThrough::applyFilterIndices:
+// a point with a non-finite x, y or z passes no stage). A zone without stages is no filter at all: it keeps every point.
+__device__ __forceinline__ uint32_t zone_mask(const ZoneSet& zs, const float4& v) {
+  const bool fin = finite_f32(v.x) && finite_f32(v.y) && finite_f32(v.z);
+  uint32_t m = 0;
+  for (int z = 0; z < zs.n_zones; ++z) {
+    const int np = zs.zone[z].n_pass;
+    bool keep = fin || np == 0;
+    for (int k = 0; k < np; ++k) keep = keep && zone_pass_keeps(zs.zone[z].pass[k], v);
+    m |= (keep ? 1u : 0u) << z;
+  }
+  return m;
+}
+
+__global__ void __launch_bounds__(ZN_THREADS) k_zone_count(const ZoneParams p) {
+  __shared__ uint32_t s_cnt[CM_MAX_ZONES];
+  const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+  const uint32_t n = p.n_points;
+  const uint32_t tile = blockIdx.x;
+  if (tid < CM_MAX_ZONES) s_cnt[tid] = 0;
+  __syncthreads();
+  const uint32_t base = tile * ZN_TILE + warp * (32 * ZN_IPT) + lane;
+  float4 v[ZN_IPT];
+#pragma unroll
+  for (int i = 0; i < ZN_IPT; ++i) {
+    const uint32_t g = base + 32 * i;
+    v[i] = g < n ? ldg_stream_f4(p.pts + g) : make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  uint32_t cnt_z = 0;  // lane z accumulates the warp's count for zone z
+#pragma unroll
+  for (int i = 0; i < ZN_IPT; ++i) {
+    const uint32_t g = base + 32 * i;
+    const uint32_t m = g < n ? zone_mask(p.zones, v[i]) : 0u;
+    if (g < n) p.mask[g] = (unsigned short)m;
+    for (int z = 0; z < p.zones.n_zones; ++z) {
+      const uint32_t b = __ballot_sync(0xFFFFFFFFu, (m >> z) & 1u);
+      if ((int)lane == z) cnt_z += (uint32_t)__popc(b);
+    }
+  }
+  if ((int)lane < p.zones.n_zones && cnt_z) atomicAdd(&s_cnt[lane], cnt_z);
+  __syncthreads();
+  if ((int)tid < p.zones.n_zones) p.tile_count[(size_t)tid * p.n_tiles + tile] = s_cnt[tid];  // zone-major
+}
+
+// one CTA: zone z starts where zone z-1 ends; inside a zone the tiles follow each other
+__global__ void __launch_bounds__(1024) k_zone_scan(const ZoneParams p) {
+  __shared__ uint32_t s_scr[33];
+  __shared__ uint32_t s_run;
+  const uint32_t tid = threadIdx.x, lane = tid & 31u, w = tid >> 5;
+  const uint32_t total_items = p.n_tiles * (uint32_t)p.zones.n_zones;  // zone-major: index = z * n_tiles + tile
+  if (tid == 0) s_run = 0;
+  __syncthreads();
+  for (uint32_t i0 = 0; i0 < total_items; i0 += 1024u * 8u) {
+    uint32_t c[8];
+    uint32_t sum = 0;
+    const uint32_t b = i0 + tid * 8u;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      c[k] = (b + k < total_items) ? p.tile_count[b + k] : 0u;
+      sum += c[k];
+    }
+    // block exclusive scan of `sum` over 1024 threads
+    const uint32_t incl = warp_incl_scan_u32(sum);
+    if (lane == 31) s_scr[w] = incl;
+    __syncthreads();
+    if (w == 0) {
+      const uint32_t t = s_scr[lane];
+      const uint32_t ti = warp_incl_scan_u32(t);
+      s_scr[lane] = ti - t;
+      if (lane == 31) s_scr[32] = ti;
+    }
+    __syncthreads();
+    uint32_t run = s_run + s_scr[w] + incl - sum;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      if (b + k < total_items) {
+        p.tile_offset[b + k] = run;
+        if ((b + k) % p.n_tiles == 0u) p.zone_begin[(b + k) / p.n_tiles] = run;
+      }
+      run += c[k];
+    }
+    __syncthreads();
+    if (tid == 0) s_run += s_scr[32];
+    __syncthreads();
+  }
+  if (tid == 0) {
+    const uint32_t total = s_run;
+    p.zone_begin[p.zones.n_zones] = total;
+    if (p.n_tiles == 0)
+      for (int z = 0; z < p.zones.n_zones; ++z) p.zone_begin[z] = 0;
+    if (total > p.out_capacity) *p.overflow = total;  // the scatter kernel then writes nothing
+  }
+}
+
+__global__ void __launch_bounds__(ZN_THREADS) k_zone_scatter(const ZoneParams p) {
+  __shared__ uint32_t s_wcnt[ZN_WARPS][CM_MAX_ZONES];
+  const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+  if (*p.overflow) return;
+  const uint32_t n = p.n_points;
+  const uint32_t tile = blockIdx.x;
+  const int nz = p.zones.n_zones;
+  const uint32_t base = tile * ZN_TILE + warp * (32 * ZN_IPT) + lane;
+  float4 v[ZN_IPT];
+  uint32_t m[ZN_IPT];
+#pragma unroll
+  for (int i = 0; i < ZN_IPT; ++i) {
+    const uint32_t g = base + 32 * i;
+    m[i] = g < n ? (uint32_t)p.mask[g] : 0u;
+    v[i] = (g < n && m[i]) ? ldg_stream_f4(p.pts + g) : make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  // the warp's count per zone (lane z holds zone z), for the prefix over the warps of the tile
+  uint32_t cnt_z = 0;
+#pragma unroll
+  for (int i = 0; i < ZN_IPT; ++i)
+    for (int z = 0; z < nz; ++z) {
+      const uint32_t b = __ballot_sync(0xFFFFFFFFu, (m[i] >> z) & 1u);
+      if ((int)lane == z) cnt_z += (uint32_t)__popc(b);
+    }
+  if ((int)lane < CM_MAX_ZONES) s_wcnt[warp][lane] = cnt_z;
+  __syncthreads();
+  const uint32_t lt = lanemask_lt();
+  for (int z = 0; z < nz; ++z) {
+    uint32_t pos = p.tile_offset[(size_t)z * p.n_tiles + tile];
+    for (uint32_t w2 = 0; w2 < warp; ++w2) pos += s_wcnt[w2][z];
+#pragma unroll
+    for (int i = 0; i < ZN_IPT; ++i) {
+      const bool in = (m[i] >> z) & 1u;
+      const uint32_t b = __ballot_sync(0xFFFFFFFFu, in);
+      if (in) {
+        const uint32_t q = pos + (uint32_t)__popc(b & lt);
+        p.out_xyzi[q] = v[i];
+        p.out_src[q] = base + 32 * i;
+      }
+      pos += (uint32_t)__popc(b);
+    }
+  }
+}
+
+}  // namespace
+
+uint32_t zone_tile_points() { return ZN_TILE; }
+
+// Only the last stage again (the counts and offsets of the previous launch_zone_split are still in place): used after
+// the output arrays had to grow.
+cudaError_t launch_zone_scatter(const ZoneParams& p, cudaStream_t stream) {
+  if (!p.n_tiles) return cudaSuccess;
+  k_zone_scatter<<<p.n_tiles, ZN_THREADS, 0, stream>>>(p);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_zone_split(const ZoneParams& p, cudaStream_t stream) {
+  if (p.n_tiles) {
+    k_zone_count<<<p.n_tiles, ZN_THREADS, 0, stream>>>(p);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+  }
+  k_zone_scan<<<1, 1024, 0, stream>>>(p);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return e;
+  if (p.n_tiles) {
+    k_zone_scatter<<<p.n_tiles, ZN_THREADS, 0, stream>>>(p);
+    e = cudaGetLastError();
+  }
+  return e;
+}
+
+}  // namespace cm

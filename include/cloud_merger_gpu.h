@@ -63,6 +63,29 @@ typedef struct {
   int32_t negative;
 } cm_pass_t;
 
+/* ---- zone slicing: several PassThrough chains over ONE cloud, one ordered output per chain ----
+ * Replaces the getCloudPart x5 + z-window sequences the reference runs per sensor cloud in proceedFront / proceedRear /
+ * proceedTop / proceedLivox (pc_preprocessing_main.cpp:49-59, 80-92, 228-312: one PassThrough on "x" for
+ * [deviation, deviation + length], then "z" for [z_min_g, z_max_g] and for [z_max_g + 0.01, roi_z_max]), filter_ROI_R's
+ * three x ranges (CloudFusionNode.h:145-190) and remove_ground's two z windows (:201-216). A zone is a chain of up to
+ * CM_MAX_ZONE_PASSES stages; zones may overlap (a point on a shared window end lands in both, as in the reference) and
+ * need not cover the cloud; inside a zone the points keep their input order; a zone without stages keeps every point. */
+#define CM_MAX_ZONES 16
+#define CM_MAX_ZONE_PASSES 4
+typedef struct {
+  int32_t n_pass;
+  cm_pass_t pass[CM_MAX_ZONE_PASSES];
+} cm_zone_t;
+
+/* device-resident result of the last zone split on a handle (valid until the next one) */
+typedef struct {
+  const float* xyzi;                  /* [begin[n_zones]][4] zone 0's points, then zone 1's, ... */
+  const uint32_t* src;                /* index of each output point in the input cloud */
+  int64_t begin[CM_MAX_ZONES + 1];    /* zone z = [begin[z], begin[z+1]) */
+  int32_t n_zones;
+  int32_t reserved;
+} cm_zone_out_t;
+
 /* ---- layout of one incoming sensor cloud ----
  * Replaces: the sensor_msgs/PointCloud2 -> pcl::PointCloud<pcl::PointXYZI> deserialisation done by the pcl_ros
  * subscriber (pc_preprocessing_main.cpp:520-525, CloudFusionNode.h:51-56): data[], point_step and the byte offsets of the
@@ -217,6 +240,17 @@ CM_API int cm_run_batch(cm_handle_t h, const cm_segment_t* segments, int n_segme
  *  cm_dev_voxelgrid: VoxelGrid only on n packed float4 xyzi points already on the device (== voxelgrid()). */
 CM_API int cm_dev_transform_crop(cm_handle_t h, const cm_segment_t* segments, int n_segments, void* stream);
 CM_API int cm_dev_voxelgrid(cm_handle_t h, const float* xyzi_dev, int64_t n_points, int is_dense, void* stream);
+/* Zone slicing (see cm_zone_t). cm_set_zones configures the chains; cm_dev_zone_split runs them over n packed float4
+ * xyzi points on the device -- or, with xyzi_dev == NULL, over the merged cropped cloud of the handle's last
+ * cm_dev_transform_crop / cm_run_batch (== getROI's output, the input of getCloudPart in the reference);
+ * cm_get_zone_out waits and returns the device arrays. cm_zone_split is the host-buffer form (H2D, split, D2H):
+ * out_begin receives n_zones + 1 offsets; returns CM_E_CAPACITY (and the needed size in out_begin[n_zones]) when the
+ * zones together do not fit `capacity` points. */
+CM_API int cm_set_zones(cm_handle_t h, int n_zones, const cm_zone_t* zones);
+CM_API int cm_dev_zone_split(cm_handle_t h, const float* xyzi_dev, int64_t n_points, void* stream);
+CM_API int cm_get_zone_out(cm_handle_t h, cm_zone_out_t* out);
+CM_API int cm_zone_split(cm_handle_t h, const float* xyzi_host, int64_t n_points, float* out_xyzi, uint32_t* out_src,
+                         int64_t capacity, int64_t* out_begin);
 /* Blocks until the last run on the handle finished, then reports. */
 CM_API int cm_sync(cm_handle_t h);
 CM_API int cm_get_stats(cm_handle_t h, cm_stats_t* out);

@@ -6,6 +6,7 @@
 //   pcl_ros::transformPointCloud(const Cloud&, Cloud&, const tf::Transform&)  ->  transformPointCloud(in, out, Transform)
 //   void getROI(const Cloud::Ptr, Cloud::Ptr)                                 ->  getROI(in, out)
 //   void getCloudPart(const Cloud::Ptr, Cloud::Ptr, float length, float dev)  ->  getCloudPart(in, out, length, deviation)
+//   proceedX: getCloudPart x5 + the z windows of removeGround                 ->  getCloudPartsZSplit (one GPU pass)
 //   void fusePointclouds(Cloud::Ptr no_ground, Cloud::Ptr ground)             ->  FusedFrame::fuse (+ operator+= kept)
 //   void voxelgrid(const Cloud::Ptr, Cloud::Ptr)                              ->  voxelgrid(in, out)
 //   callbackX(const Cloud input) ... main loop fuse + voxelgrid               ->  FusedFrame::onCloud / fuseAndVoxel
@@ -183,6 +184,41 @@ class Context {
     return true;
   }
 
+  // Zone slicing of ONE host cloud (cm_zone_split): one ordered output cloud per PassThrough chain, one GPU pass.
+  bool zone_split(const Cloud& in, const std::vector<cm_zone_t>& zones, std::vector<Cloud>& out) {
+    out.assign(zones.size(), Cloud());
+    if (!check(h_ ? CM_OK : CM_E_NO_DEVICE)) return false;
+    const int64_t n = static_cast<int64_t>(in.points.size());
+    tmp_.resize(static_cast<size_t>(n) * 4);
+    for (int64_t i = 0; i < n; ++i) {
+      const PointXYZI& p = in.points[static_cast<size_t>(i)];
+      tmp_[i * 4 + 0] = p.x; tmp_[i * 4 + 1] = p.y; tmp_[i * 4 + 2] = p.z; tmp_[i * 4 + 3] = p.intensity;
+    }
+    if (!check(cm_set_zones(h_, static_cast<int>(zones.size()), zones.data()))) return false;
+    int64_t begin[CM_MAX_ZONES + 1] = {0};
+    int64_t cap = 2 * n + 16;
+    zone_xyzi_.resize(static_cast<size_t>(cap) * 4);
+    int rc = cm_zone_split(h_, tmp_.data(), n, zone_xyzi_.data(), nullptr, cap, begin);
+    if (rc == CM_E_CAPACITY && begin[zones.size()] > cap) {  // heavily overlapping zones: the needed size came back
+      cap = begin[zones.size()];
+      zone_xyzi_.resize(static_cast<size_t>(cap) * 4);
+      rc = cm_zone_split(h_, tmp_.data(), n, zone_xyzi_.data(), nullptr, cap, begin);
+    }
+    if (!check(rc)) return false;
+    for (size_t z = 0; z < zones.size(); ++z) {
+      Cloud& c = out[z];
+      const size_t b = static_cast<size_t>(begin[z]), e = static_cast<size_t>(begin[z + 1]);
+      c.points.resize(e - b);
+      for (size_t i = b; i < e; ++i) {
+        PointXYZI& p = c.points[i - b];
+        p = PointXYZI();
+        p.x = zone_xyzi_[i * 4 + 0]; p.y = zone_xyzi_[i * 4 + 1]; p.z = zone_xyzi_[i * 4 + 2]; p.intensity = zone_xyzi_[i * 4 + 3];
+      }
+      finish(c, in, zones[z].n_pass > 0 ? true : in.is_dense);
+    }
+    return true;
+  }
+
  private:
   bool check(int rc) {
     rc_ = rc;
@@ -211,7 +247,7 @@ class Context {
   int max_sensors_;
   cm_handle_t h_ = nullptr;
   void* dev_in_ = nullptr;
-  std::vector<float> tmp_;
+  std::vector<float> tmp_, zone_xyzi_;
   std::string err_;
   int rc_ = CM_OK;
 };
@@ -259,6 +295,36 @@ inline void getCloudPart(Context& ctx, const Cloud::Ptr& cloud_ptr, const Cloud:
   Cloud tmp;
   ctx.transform_crop(*cloud_ptr, tmp, eye, 1, &pass);
   *cloud_part_ptr = tmp;
+}
+
+// The zone loop of proceedFront / proceedRear / proceedTop / proceedLivox (:228-312): for every part
+//   getCloudPart(cloud_ROI_ptr, part, length, deviation);                                      -- x in [dev, dev + length]
+//   removeGround(part, ...) { zpass [z_min_ground, z_max_ground]  -> ground_part_ptr;          -- :80-92, the input of RANSAC
+//                             zpass2 [z_max_ground + 0.01, roi_z_max] -> no_ground_part_ptr }  -- appended after RANSAC
+// i.e. 3 PassThrough runs + copies per part on the CPU; here all parts and both z windows come out of ONE GPU pass.
+// z_min_ground is -z_max_ground at every call site of the reference. `z_max_ground + 0.01` is a double sum narrowed to
+// float by setFilterLimits(const float&, const float&), exactly as in the reference.
+struct ZonePart {
+  float length, deviation, z_max_ground;
+};
+inline void getCloudPartsZSplit(Context& ctx, const Cloud::Ptr& cloud_ROI_ptr, const std::vector<ZonePart>& parts,
+                                const float roi_z_max, std::vector<Cloud::Ptr>& ground_part_ptrs,
+                                std::vector<Cloud::Ptr>& no_ground_part_ptrs) {
+  std::vector<cm_zone_t> zones(parts.size() * 2);
+  for (size_t k = 0; k < parts.size(); ++k) {
+    const ZonePart& pt = parts[k];
+    const cm_pass_t x = {0, pt.deviation, pt.deviation + pt.length, 0};
+    const float z_lo2 = static_cast<float>(pt.z_max_ground + 0.01);
+    zones[2 * k].n_pass = 2; zones[2 * k].pass[0] = x; zones[2 * k].pass[1] = cm_pass_t{2, -pt.z_max_ground, pt.z_max_ground, 0};
+    zones[2 * k + 1].n_pass = 2; zones[2 * k + 1].pass[0] = x; zones[2 * k + 1].pass[1] = cm_pass_t{2, z_lo2, roi_z_max, 0};
+  }
+  std::vector<Cloud> out;
+  ctx.zone_split(*cloud_ROI_ptr, zones, out);
+  ground_part_ptrs.clear(); no_ground_part_ptrs.clear();
+  for (size_t k = 0; k < parts.size(); ++k) {
+    ground_part_ptrs.push_back(Cloud::Ptr(new Cloud(out[2 * k])));
+    no_ground_part_ptrs.push_back(Cloud::Ptr(new Cloud(out[2 * k + 1])));
+  }
 }
 
 // void voxelgrid(const Cloud::Ptr cloud_ptr, Cloud::Ptr voxel_cloud_ptr) -- :168-177

@@ -71,6 +71,24 @@ def passthrough(xyzi: np.ndarray, axis: int, lo: float, hi: float, negative: boo
     return idx[:k].copy()
 
 
+def zone_split(xyzi: np.ndarray, zones) -> list:
+    """The reference's per-zone sequence, literally: for every zone run its PassThrough stages one after the other, each
+    on the cloud the previous one copied out (getCloudPart followed by the z window of removeGround,
+    pc_preprocessing_main.cpp:49-59, 80-92). zones: list of chains [(axis, lo, hi, negative), ...].
+    Returns, per zone, (xyzi [k,4], src [k] = indices into the input cloud, in input order)."""
+    xyzi = np.ascontiguousarray(xyzi, np.float32).reshape(-1, 4)
+    out = []
+    for chain in zones:
+        cur = xyzi
+        src = np.arange(len(xyzi), dtype=np.int64)
+        for (axis, lo, hi, neg) in chain:
+            keep = passthrough(cur, int(axis), float(np.float32(lo)), float(np.float32(hi)), bool(neg)).astype(np.int64)
+            cur = np.ascontiguousarray(cur[keep])
+            src = src[keep]
+        out.append((cur, src.astype(np.uint32)))
+    return out
+
+
 def voxelgrid(xyzi: np.ndarray, leaf, min_points: int = 0, downsample_all: bool = True, force64: bool = True,
               is_dense: bool = True) -> dict:
     xyzi = np.ascontiguousarray(xyzi, np.float32)

@@ -142,6 +142,26 @@ int main() {
     const std::vector<float> part_o = oracle_passes(roi_o, {{0, -prm.roi_mid + 11.0f, -prm.roi_mid + 11.0f + 30.0f, 0}});
     expect_cloud(*part, part_o, part_o.size() / 4, "getCloudPart");
     CHECK(part->points.size() > 100 && part->points.size() < roi_ptr->points.size(), "getCloudPart is a proper slice");
+    // proceedFront's zone loop: getCloudPart x5, each followed by the two z windows of removeGround (:228-270, :80-92)
+    {
+      const float rm = prm.roi_mid;
+      const std::vector<ZonePart> parts = {{30.0f, -rm + 11.0f + 8.0f + 15.0f + 11.0f, 2.5f}, {11.0f, -rm + 11.0f + 8.0f + 15.0f, 2.0f},
+                                           {15.0f, -rm + 11.0f + 8.0f, 1.5f}, {8.0f, -rm + 11.0f, 0.3f}, {11.0f, -rm, 0.5f}};
+      std::vector<Cloud::Ptr> ground_parts, no_ground_parts;
+      getCloudPartsZSplit(ctx, roi_ptr, parts, prm.roi_z_max, ground_parts, no_ground_parts);
+      CHECK(ground_parts.size() == parts.size() && no_ground_parts.size() == parts.size(), "zone split: %s", ctx.last_error().c_str());
+      size_t total = 0;
+      for (size_t k = 0; k < parts.size() && k < ground_parts.size(); ++k) {
+        const cmo_pass_t x = {0, parts[k].deviation, parts[k].deviation + parts[k].length, 0};
+        const std::vector<float> g_o = oracle_passes(roi_o, {x, {2, -parts[k].z_max_ground, parts[k].z_max_ground, 0}});
+        const std::vector<float> n_o = oracle_passes(roi_o, {x, {2, static_cast<float>(parts[k].z_max_ground + 0.01), prm.roi_z_max, 0}});
+        expect_cloud(*ground_parts[k], g_o, g_o.size() / 4, "zone ground part");
+        expect_cloud(*no_ground_parts[k], n_o, n_o.size() / 4, "zone no-ground part");
+        total += g_o.size() / 4 + n_o.size() / 4;
+      }
+      CHECK(total > roi_ptr->points.size() / 2 && total <= roi_ptr->points.size() + 16, "zones cover most of the ROI cloud (%zu of %zu)",
+            total, roi_ptr->points.size());
+    }
     // fusePointclouds: *no_ground_ptr = first; *no_ground_ptr += rest
     if (s == 0) *fused = *roi_ptr; else *fused += *roi_ptr;
     fused_oracle.insert(fused_oracle.end(), roi_o.begin(), roi_o.end());

@@ -65,3 +65,26 @@ def assert_centroids_close(g, o_f64, what=""):
         i = np.argmax(err - tol)
         raise AssertionError("%s: centroid off by %g (tol %g) at flat index %d" % (what, err.flat[i], tol.flat[i], i))
     return float((err / np.maximum(np.abs(o), 1e-2)).max()) if err.size else 0.0
+
+
+def reference_front_zones():
+    """The ten PassThrough chains proceedFront runs on one ROI-cropped cloud (pc_preprocessing_main.cpp:228-270 with
+    pcl_preprocessing/src/Parameter.h:31-55): five x windows [deviation, deviation + length] (float arithmetic), each
+    followed by the ground window z in [-zg, zg] and the no-ground window z in [zg + 0.01, roi_z_max] -- the `+ 0.01` is
+    a double addition narrowed to float by setFilterLimits (removeGround, :80-92)."""
+    f32 = np.float32
+    roi_mid, roi_z_max = f32(15), f32(3.0)
+    front, mid, mid2, veh, rear = f32(30.0), f32(15.0), f32(11.0), f32(8.0), f32(11)
+    parts = [  # (length, deviation, z_max_ground)
+        (front, -roi_mid + rear + veh + mid + mid2, f32(2.5)),
+        (mid2, -roi_mid + rear + veh + mid, f32(2.0)),
+        (mid, -roi_mid + rear + veh, f32(1.5)),
+        (veh, -roi_mid + rear, f32(0.3)),
+        (rear, -roi_mid, f32(0.5)),
+    ]
+    zones = []
+    for length, dev, zg in parts:
+        x_pass = (0, float(f32(dev)), float(f32(dev) + f32(length)), 0)
+        zones.append([x_pass, (2, float(-zg), float(zg), 0)])
+        zones.append([x_pass, (2, float(f32(np.float64(zg) + 0.01)), float(roi_z_max), 0)])
+    return zones

@@ -206,3 +206,37 @@ def test_threads_do_not_change_results(oracle):
     b = oracle.merge_frame(cds, synth.ROI_BOX, [0.1] * 3, 2, threads=6)
     assert (a["idx"] == b["idx"]).all() and (a["survivor_src"] == b["survivor_src"]).all()
     assert_bit_equal(a["centroid"], b["centroid"], "threads")
+
+
+def test_zone_split_oracle_against_numpy_masks(oracle):
+    """The oracle's literal replay of getCloudPart + z windows (PassThrough after PassThrough, each on the copied cloud)
+    against an independent restatement: one boolean mask per zone on the original cloud, float32 compares."""
+    from helpers import reference_front_zones
+    rng = np.random.default_rng(3)
+    n = 20000
+    cloud = np.column_stack([rng.uniform(-16, 61, n), rng.uniform(-6, 6, n), rng.uniform(-1, 3.5, n),
+                             rng.uniform(0, 255, n)]).astype(np.float32)
+    cloud[::97, 0] = np.float32(19.0)   # shared window end
+    cloud[::101, 2] = np.nan
+    cloud[::103, 1] = np.inf
+    cloud[::107, 3] = np.nan            # only an intensity stage may reject these
+    zones = reference_front_zones() + [[(3, 10.0, 20.0, 0)], [(1, -1.0, 1.0, 1)], []]
+    got = oracle.zone_split(cloud, zones)
+    fin = np.isfinite(cloud[:, :3]).all(axis=1)
+    for z, chain in enumerate(zones):
+        keep = fin.copy() if chain else np.ones(n, bool)  # no stage = no filter
+        for (axis, lo, hi, neg) in chain:
+            v = cloud[:, axis]
+            lo, hi = np.float32(lo), np.float32(hi)
+            with np.errstate(invalid="ignore"):
+                inside = (v >= lo) & (v <= hi)
+            keep &= np.isfinite(v) & (~inside if neg else inside)
+        want = np.nonzero(keep)[0]
+        assert (got[z][1] == want).all(), "zone %d" % z
+        assert (got[z][0].view(np.uint32) == cloud[want].view(np.uint32)).all()
+    # the reference's windows: x = 19 sits in both neighbours, the 0.01 gap above z_max_ground belongs to nobody
+    on_edge = np.nonzero(fin & (cloud[:, 0] == np.float32(19.0)))[0]
+    in_mid2 = np.union1d(got[2][1], got[3][1])
+    in_mid = np.union1d(got[4][1], got[5][1])
+    zwin = lambda i, zg: (cloud[i, 2] >= -zg) & (cloud[i, 2] <= zg) | (cloud[i, 2] >= np.float32(np.float64(np.float32(zg)) + 0.01)) & (cloud[i, 2] <= 3.0)
+    assert set(on_edge[zwin(on_edge, np.float32(2.0))]) <= set(in_mid2) and set(on_edge[zwin(on_edge, np.float32(1.5))]) <= set(in_mid)
