@@ -59,17 +59,48 @@ def peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks + throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    """SM clock + throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe). The timed region of this
+    workload lasts milliseconds, so the primary source is an NVML polling thread (one sample per ~2 ms); nvidia-smi -lms
+    (one sample per 100 ms at best) runs beside it as the recipe's own view and is merged in."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
 
-    def __init__(self, gpu_index: int):
+    def __init__(self, gpu_index: int, uuid: str = ""):
         self.gpu = gpu_index
+        self.uuid = uuid
         self.rows = []
         self.proc = None
+        self.nv = []        # (sm_mhz, reasons bitmask)
+        self.nv_max = None
+        self._stop = threading.Event()
+        self._thr = None
+
+    def _nvml_loop(self):
+        try:
+            import pynvml as nv
+            nv.nvmlInit()
+            h = None
+            if self.uuid:
+                for cand in (self.uuid, "GPU-" + self.uuid):
+                    try:
+                        h = nv.nvmlDeviceGetHandleByUUID(cand.encode() if isinstance(cand, str) else cand)
+                        break
+                    except Exception:
+                        h = None
+            if h is None:
+                h = nv.nvmlDeviceGetHandleByIndex(self.gpu)
+            self.nv_max = float(nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM))
+            get_reasons = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or nv.nvmlDeviceGetCurrentClocksThrottleReasons
+            while not self._stop.is_set():
+                self.nv.append((float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)), int(get_reasons(h))))
+                time.sleep(0.002)
+        except Exception:
+            pass
 
     def start(self):
+        self._thr = threading.Thread(target=self._nvml_loop, daemon=True)
+        self._thr.start()
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q,
                                           "--format=csv,noheader,nounits", "-lms", "100"],
@@ -83,10 +114,22 @@ class ClockSampler:
             self.rows.append([c.strip() for c in line.split(",")])
 
     def stop(self):
+        self._stop.set()
+        if self._thr:
+            self._thr.join(timeout=1.0)
         if self.proc:
             time.sleep(0.15)
             self.proc.terminate()
         sm, mx, reasons = [], [], set()
+        # NVML bit masks: 0x8 hw_slowdown, 0x40 hw_thermal_slowdown, 0x20 sw_thermal_slowdown, 0x4 sw_power_cap
+        for clk, bits in self.nv:
+            sm.append(clk)
+            for name, bit in (("hw_slowdown", 0x8), ("hw_thermal_slowdown", 0x40), ("sw_thermal_slowdown", 0x20), ("sw_power_cap", 0x4)):
+                if bits & bit:
+                    reasons.add(name)
+        if self.nv_max:
+            mx.append(self.nv_max)
+        n_nvml = len(sm)
         for r in self.rows:
             try:
                 sm.append(float(r[1])); mx.append(float(r[2]))
@@ -97,7 +140,19 @@ class ClockSampler:
                     reasons.add(name)
         if not sm:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
-        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
+        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons),
+                "samples": len(sm), "source": "nvml x%d + nvidia-smi x%d" % (n_nvml, len(sm) - n_nvml)}
+
+
+def dram_traffic(kernel: str, workload: str, frames: int):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of `kernel`, from the committed `ncu --set full` capture of
+    this same workload (profiles/traffic.json, written by scripts/ncu_traffic.py); None when no capture matches."""
+    try:
+        d = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+        e = d.get("%s/%d" % (workload, frames), {}).get(kernel)
+        return int(e["bytes_per_launch"]) if e else None
+    except Exception:
+        return None
 
 
 def workload_spec(name: str, frames: int):
@@ -235,7 +290,9 @@ def main():
         raise SystemExit("bench.py: no CUDA device (the product path has no CPU fallback)")
     torch.cuda.set_device(local_rank)
     if world > 1:
-        os.environ.setdefault("NCCL_DEBUG", "WARN")  # keep NCCL's version banner off stdout (one JSON line only)
+        # one JSON line on stdout: NCCL's banner / debug lines (NCCL_DEBUG may be preset on the box) go to stderr
+        os.environ.setdefault("NCCL_DEBUG", "WARN")
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
     def barrier():
@@ -276,7 +333,11 @@ def main():
     if st.device_error:
         raise SystemExit("device error %d" % st.device_error)
 
-    sampler = ClockSampler(local_rank)
+    try:
+        gpu_uuid = str(torch.cuda.get_device_properties(torch.cuda.current_device()).uuid)
+    except Exception:
+        gpu_uuid = ""
+    sampler = ClockSampler(local_rank, gpu_uuid)
     barrier()
     sampler.start()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -329,10 +390,11 @@ def main():
     dom_ms_launch = stage_ms[dom] / dom_launches
     dom_bytes_launch = algo[dom] / dom_launches
     achieved = dom_bytes_launch / (dom_ms_launch * 1e-3) / 1e9 if dom_ms_launch > 0 else 0.0
-    roofline = {"bound": "hbm", "kernel": {"transform_crop": "k_transform_crop", "key_hist": "k_voxel_key_hist",
-                                           "sort": "k_onesweep_pass", "centroid": "k_voxel_centroid"}[dom],
+    roof_kernel = {"transform_crop": "k_transform_crop", "key_hist": "k_voxel_key_hist", "sort": "k_onesweep_pass",
+                   "centroid": "k_voxel_centroid"}[dom]
+    roofline = {"bound": "hbm", "kernel": roof_kernel,
                 "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4),
-                "traffic": None, "peak_source": peak_src, "launch_ms": round(dom_ms_launch, 4),
+                "traffic": dram_traffic(roof_kernel, args.workload, F), "peak_source": peak_src, "launch_ms": round(dom_ms_launch, 4),
                 "algorithmic_bytes_per_launch": int(dom_bytes_launch), "share_of_step": round(stage_ms[dom] / ms_step, 3)}
 
     # ---- end to end through the host C-ABI path, pinned host buffers, H2D + D2H inside the timed region -----------------

@@ -1040,6 +1040,23 @@ int cm_set_zones(cm_handle_t h, int n_zones, const cm_zone_t* zones) {
       zs.zone[z].pass[k].negative = ps.negative ? 1 : 0;
     }
   }
+  // box form of every chain that allows it (see ZoneDev)
+  const float fmax = std::numeric_limits<float>::max();
+  zs.all_box = n_zones > 0 ? 1 : 0;
+  for (int z = 0; z < n_zones; ++z) {
+    ZoneDev& zd = zs.zone[z];
+    zd.is_box = zd.n_pass > 0 ? 1 : 0;
+    zd.use_i = 0;
+    for (int a = 0; a < 4; ++a) { zd.lo[a] = -fmax; zd.hi[a] = fmax; }
+    for (int k = 0; k < zd.n_pass; ++k) {
+      const PassDev& ps = zd.pass[k];
+      if (ps.negative || !(ps.lo == ps.lo) || !(ps.hi == ps.hi)) { zd.is_box = 0; break; }
+      zd.lo[ps.axis] = std::max(zd.lo[ps.axis], ps.lo);
+      zd.hi[ps.axis] = std::min(zd.hi[ps.axis], ps.hi);
+      if (ps.axis == 3) zd.use_i = 1;
+    }
+    if (!zd.is_box) zs.all_box = 0;
+  }
   h->zones = zs;
   return CM_OK;
 }

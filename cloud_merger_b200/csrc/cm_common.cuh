@@ -75,9 +75,15 @@ struct CropDev {
 struct ZoneDev {
   int32_t n_pass;
   PassDev pass[CM_MAX_ZONE_PASSES];
+  // When every stage is a plain (non-negative) window with non-NaN limits the chain is one box, like CropDev:
+  // keep <=> lo[a] <= v[a] <= hi[a] for x, y, z (defaults +-FLT_MAX also reject non-finite coordinates) and, if use_i,
+  // for the intensity.
+  int32_t is_box, use_i;
+  float lo[4], hi[4];
 };
 struct ZoneSet {
   int32_t n_zones;
+  int32_t all_box;  // every zone has at least one stage and is a box: the kernels take the compare-only path
   ZoneDev zone[CM_MAX_ZONES];
 };
 

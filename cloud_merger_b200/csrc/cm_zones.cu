@@ -34,9 +34,21 @@ __device__ __forceinline__ bool zone_pass_keeps(const PassDev& ps, const float4&
 
 // membership of one point: bit z set iff every stage of zone z keeps it (PCL 1.8.1 PassThrough::applyFilterIndices:
 // a point with a non-finite x, y or z passes no stage). A zone without stages is no filter at all: it keeps every point.
+// BOX: every zone is a box (ZoneSet.all_box): six compares per zone, non-finite coordinates fail them by themselves.
+template <bool BOX>
 __device__ __forceinline__ uint32_t zone_mask(const ZoneSet& zs, const float4& v) {
-  const bool fin = finite_f32(v.x) && finite_f32(v.y) && finite_f32(v.z);
   uint32_t m = 0;
+  if (BOX) {
+    for (int z = 0; z < zs.n_zones; ++z) {
+      const ZoneDev& zd = zs.zone[z];
+      bool keep = (v.x >= zd.lo[0]) & (v.x <= zd.hi[0]) & (v.y >= zd.lo[1]) & (v.y <= zd.hi[1]) & (v.z >= zd.lo[2]) &
+                  (v.z <= zd.hi[2]);
+      if (zd.use_i) keep = keep & (v.w >= zd.lo[3]) & (v.w <= zd.hi[3]);
+      m |= (keep ? 1u : 0u) << z;
+    }
+    return m;
+  }
+  const bool fin = finite_f32(v.x) && finite_f32(v.y) && finite_f32(v.z);
   for (int z = 0; z < zs.n_zones; ++z) {
     const int np = zs.zone[z].n_pass;
     bool keep = fin || np == 0;
@@ -46,6 +58,7 @@ __device__ __forceinline__ uint32_t zone_mask(const ZoneSet& zs, const float4& v
   return m;
 }
 
+template <bool BOX>
 __global__ void __launch_bounds__(ZN_THREADS) k_zone_count(const ZoneParams p) {
   __shared__ uint32_t s_cnt[CM_MAX_ZONES];
   const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
@@ -64,7 +77,7 @@ __global__ void __launch_bounds__(ZN_THREADS) k_zone_count(const ZoneParams p) {
 #pragma unroll
   for (int i = 0; i < ZN_IPT; ++i) {
     const uint32_t g = base + 32 * i;
-    const uint32_t m = g < n ? zone_mask(p.zones, v[i]) : 0u;
+    const uint32_t m = g < n ? zone_mask<BOX>(p.zones, v[i]) : 0u;
     if (g < n) p.mask[g] = (unsigned short)m;
     for (int z = 0; z < p.zones.n_zones; ++z) {
       const uint32_t b = __ballot_sync(0xFFFFFFFFu, (m >> z) & 1u);
@@ -184,7 +197,8 @@ cudaError_t launch_zone_scatter(const ZoneParams& p, cudaStream_t stream) {
 
 cudaError_t launch_zone_split(const ZoneParams& p, cudaStream_t stream) {
   if (p.n_tiles) {
-    k_zone_count<<<p.n_tiles, ZN_THREADS, 0, stream>>>(p);
+    if (p.zones.all_box) k_zone_count<true><<<p.n_tiles, ZN_THREADS, 0, stream>>>(p);
+    else k_zone_count<false><<<p.n_tiles, ZN_THREADS, 0, stream>>>(p);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
   }
