@@ -95,6 +95,8 @@ SYMBOLS = {
     "cm_set_overflow_mode": (C.c_int, [_H, C.c_int]),
     "cm_submit_cloud": (C.c_int, [_H, C.c_int, C.c_void_p, C.c_int64, C.POINTER(CmLayout), C.c_uint64]),
     "cm_submit_cloud_pinned": (C.c_int, [_H, C.c_int, C.c_void_p, C.c_int64, C.POINTER(CmLayout), C.c_uint64]),
+    "cm_submit_clouds_pinned": (C.c_int, [_H, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_void_p), C.POINTER(C.c_int64),
+                                          C.POINTER(CmLayout), C.POINTER(C.c_uint64)]),
     "cm_merge_frame": (C.c_int, [_H, C.c_uint64, C.POINTER(CmFrameOut), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
     "cm_merge_frame_async": (C.c_int, [_H, C.c_uint64, C.POINTER(C.c_int64)]),
     "cm_wait_frame": (C.c_int, [_H, C.c_int64, C.POINTER(CmFrameOut), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),

@@ -233,6 +233,33 @@ class CloudMerger:
         fn = self._lib.cm_submit_cloud_pinned if pinned else self._lib.cm_submit_cloud
         self._check(fn(self._h, sensor, ptr, n_points, C.byref(layout), C.c_uint64(stamp)))
 
+    def submit_clouds_pinned(self, sensors: Sequence[int], addresses: Sequence[int], n_points: Sequence[int],
+                             layouts: Sequence[CmLayout], stamps: Optional[Sequence[int]] = None):
+        """All page-locked clouds of a frame in one call (cm_submit_clouds_pinned): host-adjacent clouds of consecutive
+        sensors go over PCIe as one copy. addresses are raw host addresses."""
+        k = len(sensors)
+        a_s = (C.c_int * k)(*[int(x) for x in sensors])
+        a_d = (C.c_void_p * k)(*[int(x) for x in addresses])
+        a_n = (C.c_int64 * k)(*[int(x) for x in n_points])
+        a_l = (CmLayout * k)(*layouts)
+        a_t = (C.c_uint64 * k)(*[int(x) for x in (stamps if stamps is not None else [0] * k)])
+        self._check(self._lib.cm_submit_clouds_pinned(self._h, k, a_s, a_d, a_n, a_l, a_t))
+
+    def prepared_frame_submit(self, sensors, addresses, n_points, layouts, stamp: int = 0):
+        """The argument arrays of submit_clouds_pinned built once, for callers that replay the same buffers every frame;
+        returns a zero-argument callable."""
+        k = len(sensors)
+        a_s = (C.c_int * k)(*[int(x) for x in sensors])
+        a_d = (C.c_void_p * k)(*[int(x) for x in addresses])
+        a_n = (C.c_int64 * k)(*[int(x) for x in n_points])
+        a_l = (CmLayout * k)(*layouts)
+        a_t = (C.c_uint64 * k)(*([int(stamp)] * k))
+        fn, h, chk = self._lib.cm_submit_clouds_pinned, self._h, self._check
+
+        def go():
+            chk(fn(h, k, a_s, a_d, a_n, a_l, a_t))
+        return go
+
     def merge_frame_async(self, sensor_mask: int = (1 << 64) - 1) -> int:
         t = C.c_int64()
         self._check(self._lib.cm_merge_frame_async(self._h, C.c_uint64(sensor_mask), C.byref(t)))

@@ -92,6 +92,7 @@ struct Workspace {
 
 struct SensorState {
   bool submitted = false;
+  uint8_t* dev = nullptr;  // where this submission's records sit in the slot's raw buffer
   int64_t n_points = 0;
   cm_layout_t layout{};
   uint64_t stamp = 0;
@@ -666,7 +667,7 @@ int submit_impl(cm_handle_t h, int sensor, const void* data, int64_t n_points, c
     }
   }
   CM_CUDA(h, cudaEventRecord(ss.copied, st));
-  ss.submitted = true; ss.n_points = n_points; ss.layout = *layout; ss.stamp = stamp;
+  ss.submitted = true; ss.n_points = n_points; ss.layout = *layout; ss.stamp = stamp; ss.dev = dst;
   return CM_OK;
 }
 
@@ -682,7 +683,7 @@ int merge_async_impl(cm_handle_t h, uint64_t mask, int64_t* ticket) {
     SensorState& ss = sl.sensor[s];
     if (!ss.submitted) continue;
     cm_segment_t g;
-    g.data = sl.raw_dev + (size_t)s * h->slot_stride;
+    g.data = ss.dev;
     g.n_points = ss.n_points; g.layout = ss.layout; g.sensor = s; g.frame = 0;
     segs.push_back(g);
     used |= 1ull << s;
@@ -943,6 +944,50 @@ int cm_submit_cloud(cm_handle_t h, int sensor, const void* data, int64_t n_point
 int cm_submit_cloud_pinned(cm_handle_t h, int sensor, const void* data, int64_t n_points, const cm_layout_t* layout,
                            uint64_t stamp) {
   return submit_impl(h, sensor, data, n_points, layout, stamp, true);
+}
+
+int cm_submit_clouds_pinned(cm_handle_t h, int count, const int* sensors, const void* const* data, const int64_t* n_points,
+                            const cm_layout_t* layouts, const uint64_t* stamps) {
+  if (!h || count < 0 || (count > 0 && (!sensors || !data || !n_points || !layouts))) return CM_E_INVALID;
+  std::lock_guard<std::mutex> lk(h->mu);
+  CM_CUDA(h, cudaSetDevice(h->device));
+  int rc = ensure_host_path(h);
+  if (rc != CM_OK) return rc;
+  Slot& sl = h->slots[h->fill];
+  if (sl.busy) return fail(h, CM_E_CAPACITY, "all %d frame slots are in flight: call cm_wait_frame first", h->cfg.frames_in_flight);
+  for (int i = 0; i < count; ++i) {
+    if (sensors[i] < 0 || sensors[i] >= h->cfg.max_sensors) return fail(h, CM_E_INVALID, "sensor %d out of range", sensors[i]);
+    if (!layout_ok(layouts[i])) return fail(h, CM_E_INVALID, "cloud %d: bad layout", i);
+    if (n_points[i] < 0 || (n_points[i] > 0 && !data[i])) return fail(h, CM_E_INVALID, "cloud %d: bad cloud", i);
+    if (n_points[i] > h->cfg.max_points_per_sensor) return fail(h, CM_E_CAPACITY, "cloud %d: %lld points > max_points_per_sensor", i, (long long)n_points[i]);
+    if (layouts[i].point_step > h->cfg.max_point_step) return fail(h, CM_E_CAPACITY, "cloud %d: point_step %d > max_point_step", i, layouts[i].point_step);
+  }
+  // Clouds that follow each other in host memory, belong to consecutive sensor ids and are 16-byte multiples travel as ONE
+  // copy (a 2 MB copy reaches ~50 GB/s over PCIe 5 x16, an 8 MB one ~54): they are laid out back to back from the first
+  // sensor's region of the slot, which only ever covers regions of the run's own members.
+  int i = 0;
+  while (i < count) {
+    size_t run_bytes = (size_t)n_points[i] * (size_t)layouts[i].point_step;
+    int j = i + 1;
+    while (j < count && sensors[j] == sensors[j - 1] + 1 && run_bytes % 16 == 0 && run_bytes > 0 &&
+           static_cast<const uint8_t*>(data[j]) == static_cast<const uint8_t*>(data[i]) + run_bytes) {
+      run_bytes += (size_t)n_points[j] * (size_t)layouts[j].point_step;
+      ++j;
+    }
+    uint8_t* dst = sl.raw_dev + (size_t)sensors[i] * h->slot_stride;
+    cudaStream_t st = h->sensor_stream[sensors[i]];
+    if (run_bytes) CM_CUDA(h, cudaMemcpyAsync(dst, data[i], run_bytes, cudaMemcpyHostToDevice, st));
+    size_t off = 0;
+    for (int k = i; k < j; ++k) {
+      SensorState& ss = sl.sensor[sensors[k]];
+      CM_CUDA(h, cudaEventRecord(ss.copied, st));
+      ss.submitted = true; ss.n_points = n_points[k]; ss.layout = layouts[k]; ss.stamp = stamps ? stamps[k] : 0;
+      ss.dev = dst + off;
+      off += (size_t)n_points[k] * (size_t)layouts[k].point_step;
+    }
+    i = j;
+  }
+  return CM_OK;
 }
 
 int cm_merge_frame_async(cm_handle_t h, uint64_t sensor_mask, int64_t* ticket) {

@@ -213,6 +213,11 @@ CM_API int cm_submit_cloud(cm_handle_t h, int sensor, const void* data, int64_t 
  * belongs to has been waited for: the copy goes straight from the caller's memory, with no staging memcpy. */
 CM_API int cm_submit_cloud_pinned(cm_handle_t h, int sensor, const void* data, int64_t n_points,
                                   const cm_layout_t* layout, uint64_t stamp);
+/* Several page-locked clouds of one frame at once (a rosbag replay, or a driver that delivers all sensors together):
+ * the same as `count` calls of cm_submit_cloud_pinned, except that clouds which follow each other in host memory and
+ * belong to consecutive sensor ids are copied with one transfer. stamps may be NULL. */
+CM_API int cm_submit_clouds_pinned(cm_handle_t h, int count, const int* sensors, const void* const* data,
+                                   const int64_t* n_points, const cm_layout_t* layouts, const uint64_t* stamps);
 /* cm_merge_frame replaces fusePointclouds + voxelgrid (pc_preprocessing_main.cpp:131-177, main loop :574-578):
  * merges the latest cloud of every sensor in sensor_mask (bit s = sensor s, concat order = ascending sensor id),
  * crops, voxel-filters and copies the results into the caller's buffers. Blocks until the results are on the host.

@@ -316,6 +316,43 @@ def test_pipelined_frames_and_optional_sensor(gpu_ok, oracle):
             assert_bit_equal(r.voxel_xyzi, o["centroid"], "frame %d" % f)
 
 
+def test_submit_clouds_pinned_matches_single_submits(gpu_ok, oracle):
+    """cm_submit_clouds_pinned == one cm_submit_cloud_pinned per cloud, whether or not the clouds are adjacent in host
+    memory (adjacent clouds of consecutive sensors travel as one copy), with ragged sizes and a skipped sensor id."""
+    from cloud_merger_b200 import host_alloc
+    S, cap = 4, 16 * 512
+    sizes = [cap, cap - 37 * 16 // 16, 1234, cap]
+    passes, leaf, mp = [(2, -0.5, 3.0, 0), (0, -15.0, 60.0, 0)], 0.1, 2
+    arena, addr = host_alloc(S * cap * 16 + 4096)
+    clouds, addrs, off = [], [], 0
+    for s in range(S):
+        c = synth.lidar_cloud(555, s, 0, 16, 512)[:sizes[s]]
+        if s == 3:
+            off += 256  # a gap: the last cloud is not adjacent to its predecessor
+        arena[off:off + c.nbytes] = c.view(np.uint8).reshape(-1)
+        clouds.append(c); addrs.append(addr + off)
+        off += c.nbytes
+    with CloudMerger(max_sensors=6, max_points_per_sensor=cap, frames_in_flight=2) as cm:
+        ids = [0, 1, 2, 4]  # sensor 3 is never submitted: 0-1-2 form one run, 4 stands alone (and is not adjacent anyway)
+        for s, sid in enumerate(ids):
+            cm.set_extrinsic(sid, synth.extrinsic(s, S))
+        cm.set_crop(passes); cm.set_voxel(leaf, mp, True)
+        cm.submit_clouds_pinned(ids, addrs, sizes, [make_layout()] * S, stamps=[7, 8, 9, 10])
+        got = cm.merge_frame(capacity=S * cap)
+        for s, sid in enumerate(ids):
+            cm.submit_cloud(sid, clouds[s], sizes[s], make_layout(), stamp=7 + s)
+        ref = cm.merge_frame(capacity=S * cap)
+        mats = [cm.get_extrinsic(sid) for sid in ids]
+    assert got.stamp == ref.stamp == 10
+    assert (got.survivor_src == ref.survivor_src).all() and len(got.survivor_src) > 1000
+    assert_bit_equal(got.survivor_xyzi, ref.survivor_xyzi, "survivors")
+    assert (got.voxel_idx == ref.voxel_idx).all() and (got.voxel_count == ref.voxel_count).all()
+    assert_bit_equal(got.voxel_xyzi, ref.voxel_xyzi, "centroids")
+    o = oracle.merge_frame([cloud_dict(c, m) for c, m in zip(clouds, mats)], passes, [leaf] * 3, mp, True, True)
+    assert (got.survivor_src == o["survivor_src"]).all()
+    assert (got.voxel_idx.astype(np.int64) == o["idx"]).all()
+
+
 def test_pcl_overflow_modes(gpu_ok, oracle):
     """Leaf too small for the extent: PCL 1.8.1 returns the input unchanged (mode 1); the default carries on in 64 bits."""
     p = synth.uniform_cloud(8, 5000, extent=(300.0, 300.0, 20.0))
