@@ -43,7 +43,7 @@ def parse_args():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
-    ap.add_argument("--latency", action="store_true", help="also report single-frame p50/p99 latency")
+    ap.add_argument("--no-latency", action="store_true", help="skip the single-frame p50/p99 latency measurement")
     return ap.parse_args()
 
 
@@ -470,7 +470,7 @@ def main():
 
     # ---- single-frame latency (resident inputs) -----------------------------------------------------------------------
     latency = None
-    if args.latency and rank == 0:
+    if not args.no_latency and rank == 0:
         one = cm.make_segments(items[:S])
         lat = []
         for i in range(220):
@@ -481,6 +481,19 @@ def main():
         lat.sort()
         latency = {"p50_ms": lat[len(lat) // 2], "p99_ms": lat[int(len(lat) * 0.99)], "frames": len(lat),
                    "what": "device time of one resident frame, first to last kernel"}
+        if not args.no_e2e:
+            # the same through the host path, nothing else in flight: page-locked clouds in -> voxels in host memory
+            hl = []
+            for i in range(120):
+                f = i % F
+                t0 = time.perf_counter()
+                submit[f]()
+                cm.wait_frame_into(cm.merge_frame_async(), ring[0][0])
+                if i >= 20:
+                    hl.append((time.perf_counter() - t0) * 1e3)
+            hl.sort()
+            latency.update({"host_p50_ms": hl[len(hl) // 2], "host_p99_ms": hl[int(len(hl) * 0.99)],
+                            "host_what": "wall time of one frame through cm_submit_clouds_pinned + merge + wait (8 MB in, voxels out)"})
 
     # ---- CPU baseline on this box's host cores (rank 0, N = 1 only) ------------------------------------------------------
     cpu = None

@@ -215,8 +215,7 @@ int ws_alloc(cm_handle_t h, Workspace& w, uint32_t points, uint32_t frames, uint
   // every segment owns at least one K1 tile
   w.lb_k1_n = np / k1_min_tile_points() + segs + 2;
   CM_CUDA(h, dev_alloc(&w.tile_seg, w.lb_k1_n));
-  const uint32_t st = std::min(sort_tile_items(4), sort_tile_items(8));
-  w.lb_sort_n = (np / st + 2) * CM_RADIX;
+  w.lb_sort_n = sort_lookback_rows((uint32_t)np) * CM_RADIX;
   w.lb_cent_n = np / centroid_tile_items() + 2;
   CM_CUDA(h, dev_alloc(&w.tile_rec, w.lb_k1_n));
   CM_CUDA(h, dev_alloc(&w.lb_sort, w.lb_sort_n));

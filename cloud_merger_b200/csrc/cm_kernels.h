@@ -112,7 +112,8 @@ cudaError_t launch_zone_split(const ZoneParams& p, cudaStream_t stream);  // 3 l
 cudaError_t launch_zone_scatter(const ZoneParams& p, cudaStream_t stream);  // the last of them again, after out_* grew
 #define CM_ZONE_LAUNCHES 3
 
-uint32_t sort_tile_items(uint32_t key_bytes);
+uint32_t sort_tile_items(uint32_t key_bytes, uint32_t max_points);
+size_t sort_lookback_rows(uint32_t capacity);
 uint32_t centroid_tile_items();
 
 // per-device one-time kernel attribute setup (opt-in shared memory sizes)

@@ -179,9 +179,8 @@ __device__ __forceinline__ uint32_t lanemask_gt() {
 
 // Shared memory of one worker CTA. The sorted-tile buffers are double: a CTA ranks and places tile B while the scanners
 // are still producing the row that tile A (placed in the other buffer) needs for its scatter -- see the kernel.
-template <typename KeyT>
+template <typename KeyT, int IPT>
 struct SortSmem {
-  static constexpr int IPT = SortCfg<KeyT>::IPT;
   static constexpr int TILE = RS_THREADS * IPT;
   static constexpr bool AOS = sizeof(KeyT) == 4;
   unsigned long long k[2][TILE];       // AOS: records (value << 32 | key); else keys
@@ -193,14 +192,13 @@ struct SortSmem {
   uint32_t next_tile[2];               // written by thread 0 one iteration ahead (parity-indexed)
 };
 
-template <typename KeyT>
+template <typename KeyT, int IPT>
 __global__ void __launch_bounds__(RS_THREADS, RS_MIN_CTAS) k_onesweep_pass(const VoxelParams p, const int pass) {
-  constexpr int IPT = SortCfg<KeyT>::IPT;
   constexpr int TILE = RS_THREADS * IPT;
   constexpr int WARP_ITEMS = 32 * IPT;
   constexpr bool AOS = sizeof(KeyT) == 4;  // (key, value) records of 8 bytes
   extern __shared__ __align__(16) unsigned char s_raw[];
-  SortSmem<KeyT>& sm = *reinterpret_cast<SortSmem<KeyT>*>(s_raw);
+  SortSmem<KeyT, IPT>& sm = *reinterpret_cast<SortSmem<KeyT, IPT>*>(s_raw);
 
   const long long tr0 = clock64();
   const SortInfo si = *p.info;
@@ -471,45 +469,76 @@ __global__ void __launch_bounds__(256) k_split_records(const uint2* __restrict__
 
 }  // namespace
 
-uint32_t sort_tile_items(uint32_t key_bytes) {
+// Two tile sizes per key width. A single frame (a few hundred thousand keys) cut into 4608-key tiles would occupy a third
+// of the SMs with one long tile each; 1536-key tiles spread it over the chip and shorten the critical path of a pass.
+constexpr int RS_IPT_SMALL = 4;
+constexpr uint32_t RS_SMALL_LIMIT = 148u * 2u * RS_THREADS * RS_IPT32;  // up to ~1.4 M keys: the small tile
+
+static bool sort_uses_small_tile(uint32_t max_points) { return max_points <= RS_SMALL_LIMIT; }
+
+uint32_t sort_tile_items(uint32_t key_bytes, uint32_t max_points) {
+  if (sort_uses_small_tile(max_points)) return RS_THREADS * RS_IPT_SMALL;
   return key_bytes == 4 ? RS_THREADS * SortCfg<uint32_t>::IPT : RS_THREADS * SortCfg<unsigned long long>::IPT;
 }
 
-static int g_sort_ctas_per_sm[2] = {0, 0};
+// rows of look-back words a workspace of `capacity` points needs (+1 for row -1, +1 spare)
+size_t sort_lookback_rows(uint32_t capacity) {
+  const uint32_t small_part = std::min(capacity, RS_SMALL_LIMIT);
+  const size_t rows_small = small_part / (RS_THREADS * RS_IPT_SMALL) + 1;
+  const size_t rows_big = capacity / (RS_THREADS * std::min<int>(SortCfg<uint32_t>::IPT, SortCfg<unsigned long long>::IPT)) + 1;
+  return std::max(rows_small, rows_big) + 2;
+}
+
+namespace {
+template <typename KeyT, int IPT>
+struct PassLaunch {
+  static inline int ctas_per_sm = 0;
+  static cudaError_t configure() {
+    cudaError_t e = cudaFuncSetAttribute(k_onesweep_pass<KeyT, IPT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)sizeof(SortSmem<KeyT, IPT>));
+    if (e != cudaSuccess) return e;
+    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, k_onesweep_pass<KeyT, IPT>, RS_THREADS,
+                                                         sizeof(SortSmem<KeyT, IPT>));
+  }
+  static cudaError_t launch(const VoxelParams& p, int pass, int sms, cudaStream_t stream) {
+    const uint32_t tile = RS_THREADS * IPT;
+    const uint32_t tiles = (p.max_points + tile - 1) / tile;
+    if (tiles == 0) return cudaSuccess;
+    // persistent workers: at most what the device holds at once (tiles are handed out by an atomic counter)
+    const uint32_t workers = std::min<uint32_t>(tiles, (uint32_t)(sms * std::max(1, ctas_per_sm)) - RS_SCANNERS);
+    k_onesweep_pass<KeyT, IPT><<<workers + RS_SCANNERS, RS_THREADS, sizeof(SortSmem<KeyT, IPT>), stream>>>(p, pass);
+    return cudaGetLastError();
+  }
+};
+bool g_sort_configured = false;
+}  // namespace
 
 cudaError_t configure_sort_kernels() {
-  if (g_sort_ctas_per_sm[0] > 0) return cudaSuccess;
-  cudaError_t e = cudaFuncSetAttribute(k_onesweep_pass<uint32_t>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       (int)sizeof(SortSmem<uint32_t>));
+  if (g_sort_configured) return cudaSuccess;
+  cudaError_t e = PassLaunch<uint32_t, SortCfg<uint32_t>::IPT>::configure();
+  if (e == cudaSuccess) e = PassLaunch<unsigned long long, SortCfg<unsigned long long>::IPT>::configure();
+  if (e == cudaSuccess) e = PassLaunch<uint32_t, RS_IPT_SMALL>::configure();
+  if (e == cudaSuccess) e = PassLaunch<unsigned long long, RS_IPT_SMALL>::configure();
   if (e != cudaSuccess) return e;
-  e = cudaFuncSetAttribute(k_onesweep_pass<unsigned long long>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                           (int)sizeof(SortSmem<unsigned long long>));
-  if (e != cudaSuccess) return e;
-  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&g_sort_ctas_per_sm[0], k_onesweep_pass<uint32_t>, RS_THREADS,
-                                                    sizeof(SortSmem<uint32_t>));
-  if (e != cudaSuccess) return e;
-  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&g_sort_ctas_per_sm[1], k_onesweep_pass<unsigned long long>,
-                                                    RS_THREADS, sizeof(SortSmem<unsigned long long>));
-  if (getenv("CM_DEBUG")) fprintf(stderr, "[cm] sort pass: %d / %d CTAs per SM (32-bit / 64-bit keys), %zu / %zu B smem\n",
-                                 g_sort_ctas_per_sm[0], g_sort_ctas_per_sm[1], sizeof(SortSmem<uint32_t>), sizeof(SortSmem<unsigned long long>));
-  return e;
+  if (getenv("CM_DEBUG"))
+    fprintf(stderr, "[cm] sort pass CTAs per SM: %d / %d (32 / 64-bit keys), small tile %d / %d\n",
+            PassLaunch<uint32_t, SortCfg<uint32_t>::IPT>::ctas_per_sm,
+            PassLaunch<unsigned long long, SortCfg<unsigned long long>::IPT>::ctas_per_sm,
+            PassLaunch<uint32_t, RS_IPT_SMALL>::ctas_per_sm, PassLaunch<unsigned long long, RS_IPT_SMALL>::ctas_per_sm);
+  g_sort_configured = true;
+  return cudaSuccess;
 }
 
 cudaError_t launch_sort_pass(const VoxelParams& p, int pass, cudaStream_t stream) {
-  const uint32_t tile = sort_tile_items(p.key_bytes);
-  const uint32_t tiles = (p.max_points + tile - 1) / tile;
-  if (tiles == 0) return cudaSuccess;
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  // persistent workers: at most what the device holds at once (tiles are handed out by an atomic counter)
-  const int per_sm = std::max(1, g_sort_ctas_per_sm[p.key_bytes == 4 ? 0 : 1]);
-  const uint32_t workers = std::min<uint32_t>(tiles, (uint32_t)(sms * per_sm) - RS_SCANNERS);
+  const bool small = sort_uses_small_tile(p.max_points);
   if (p.key_bytes == 4)
-    k_onesweep_pass<uint32_t><<<workers + RS_SCANNERS, RS_THREADS, sizeof(SortSmem<uint32_t>), stream>>>(p, pass);
-  else
-    k_onesweep_pass<unsigned long long><<<workers + RS_SCANNERS, RS_THREADS, sizeof(SortSmem<unsigned long long>), stream>>>(p, pass);
-  return cudaGetLastError();
+    return small ? PassLaunch<uint32_t, RS_IPT_SMALL>::launch(p, pass, sms, stream)
+                 : PassLaunch<uint32_t, SortCfg<uint32_t>::IPT>::launch(p, pass, sms, stream);
+  return small ? PassLaunch<unsigned long long, RS_IPT_SMALL>::launch(p, pass, sms, stream)
+               : PassLaunch<unsigned long long, SortCfg<unsigned long long>::IPT>::launch(p, pass, sms, stream);
 }
 
 cudaError_t launch_split_records(const void* records, uint32_t* keys, uint32_t* vals, const uint32_t* n_ptr,
