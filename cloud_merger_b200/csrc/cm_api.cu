@@ -63,6 +63,7 @@ struct Workspace {
   TileRec* tile_rec = nullptr;          // [lb_k1_n] K1 tile records
   uint32_t* cent_count = nullptr;       // [lb_cent_n]
   unsigned long long* lb_sort = nullptr;
+  uint32_t* epoch_dev = nullptr;        // run epoch of the look-back words (device-resident, see VoxelParams)
   size_t lb_k1_n = 0, lb_sort_n = 0, lb_cent_n = 0;
   void* tmp_xyzi = nullptr;             // tile-local voxel records before compaction
   uint32_t* tmp_count = nullptr;
@@ -86,6 +87,7 @@ struct Workspace {
   uint32_t key_bytes = 8, max_passes = 8;
   const float4* voxel_pts = nullptr;  // points the voxel stage read (survivors or the caller's cloud)
   bool ran_k1 = false, ran_voxel = false;
+  bool capturing = false;  // the run is being captured into a graph: its timing events are recorded around the graph launch instead
   int64_t launches = 0;
   cudaStream_t stream = nullptr;
 };
@@ -109,6 +111,12 @@ struct Slot {
   int64_t ticket = -1;
   bool busy = false;
   uint64_t used_mask = 0, stamp = 0;
+  // The launch sequence of a frame, captured once per configuration and replayed as a CUDA graph: a frame of the host
+  // path is ~12 stream operations on half a million points, and enqueueing them one by one costs more host time than
+  // the GPU needs to run them. graph_seen: configuration of the previous frame (run the plain way, which also uploads
+  // the segment table); graph_key: configuration the instantiated graph belongs to.
+  cudaGraphExec_t graph = nullptr;
+  std::string graph_key, graph_seen;
 };
 
 }  // namespace
@@ -158,6 +166,7 @@ struct cm_handle_s {
   int fill = 0;
   int64_t ticket_counter = 0;
   bool host_ready = false;
+  bool use_graph = true;  // CM_NO_GRAPH=1 switches the frame graphs off
 };
 
 namespace {
@@ -188,7 +197,7 @@ void ws_free(Workspace& w) {
   if (!w.ready) return;
   cudaFree(w.meta); cudaFreeHost(w.report); cudaFree(w.segs); cudaFree(w.tile_seg); cudaFree(w.surv_xyzi); cudaFree(w.surv_src);
   cudaFree(w.keys_a); cudaFree(w.keys_b); cudaFree(w.vals_a); cudaFree(w.vals_b);
-  cudaFree(w.tile_rec); cudaFree(w.lb_sort); cudaFree(w.cent_count);
+  cudaFree(w.tile_rec); cudaFree(w.lb_sort); cudaFree(w.cent_count); cudaFree(w.epoch_dev);
   cudaFree(w.tmp_xyzi); cudaFree(w.tmp_count); cudaFree(w.tmp_idx);
   cudaFree(w.dense_xyzi); cudaFree(w.dense_src); cudaFree(w.dense_slot);
   cudaFree(w.out_xyzi); cudaFree(w.out_count); cudaFree(w.out_idx);
@@ -221,6 +230,8 @@ int ws_alloc(cm_handle_t h, Workspace& w, uint32_t points, uint32_t frames, uint
   CM_CUDA(h, dev_alloc(&w.lb_sort, w.lb_sort_n));
   CM_CUDA(h, dev_alloc(&w.cent_count, w.lb_cent_n));
   CM_CUDA(h, cudaMemset(w.lb_sort, 0, w.lb_sort_n * 8));
+  CM_CUDA(h, dev_alloc(&w.epoch_dev, (size_t)1));
+  CM_CUDA(h, cudaMemset(w.epoch_dev, 0, sizeof(uint32_t)));
   const size_t nt = np + centroid_tile_items();
   CM_CUDA(h, cudaMalloc(&w.tmp_xyzi, nt * 16));
   CM_CUDA(h, dev_alloc(&w.tmp_count, nt));
@@ -238,22 +249,6 @@ int ws_alloc(cm_handle_t h, Workspace& w, uint32_t points, uint32_t frames, uint
   }
   w.ready = true;
   return CM_OK;
-}
-
-uint32_t next_epoch(cm_handle_t h) {
-  // epochs are 30-bit; a run uses 16 of them. On wrap the look-back arrays are cleared.
-  if ((uint64_t)(h->run_counter + 2) * 16ull >= (1ull << 30)) {
-    auto clear = [](Workspace& w) {
-      if (!w.ready) return;
-      cudaMemset(w.lb_sort, 0, w.lb_sort_n * 8);
-    };
-    cudaDeviceSynchronize();
-    clear(h->batch);
-    for (auto& s : h->slots) clear(s.ws);
-    h->run_counter = 0;
-  }
-  ++h->run_counter;
-  return h->run_counter * 16u;
 }
 
 uint32_t seg_mode(const cm_layout_t& L) {
@@ -308,7 +303,7 @@ bool crop_cell_bound(cm_handle_t h, unsigned long long* cells) {
 }
 
 void fill_voxel_params(cm_handle_t h, Workspace& w, VoxelParams& vp, const float4* pts, uint32_t n_frames,
-                       uint32_t max_points, uint32_t epoch) {
+                       uint32_t max_points) {
   vp.pts = pts;
   vp.frame_surv_start = reinterpret_cast<uint32_t*>(w.meta + w.ml.off_fstart);
   vp.n_frames = n_frames;
@@ -328,7 +323,8 @@ void fill_voxel_params(cm_handle_t h, Workspace& w, VoxelParams& vp, const float
   vp.tmp_xyzi = w.tmp_xyzi; vp.tmp_count = w.tmp_count; vp.tmp_idx = w.tmp_idx;
   vp.tile_rec = w.ran_k1 ? w.tile_rec : nullptr;
   vp.n_k1_tiles = w.n_k1_tiles;
-  vp.epoch = epoch;
+  vp.epoch_dev = w.epoch_dev;
+  vp.lb_sort_words = (uint32_t)std::min<size_t>(w.lb_sort_n, 0xFFFFFFFFu);
   vp.max_passes = CM_MAX_SORT_PASSES;
   vp.out_xyzi = w.out_xyzi; vp.out_count = w.out_count; vp.out_idx = w.out_idx;
   vp.trace = w.trace_sort;
@@ -376,7 +372,7 @@ int run_voxel(cm_handle_t h, Workspace& w, VoxelParams& vp, cudaStream_t st, boo
   if (h->profiling) CM_CUDA(h, cudaEventRecord(w.ev[EV_SORT], st));
   CM_CUDA(h, launch_centroid(vp, st));
   w.launches += CM_CENTROID_LAUNCHES;
-  CM_CUDA(h, cudaEventRecord(w.ev[EV_CENT], st));
+  if (!w.capturing) CM_CUDA(h, cudaEventRecord(w.ev[EV_CENT], st));
   w.ran_voxel = true;
   return CM_OK;
 }
@@ -493,17 +489,16 @@ int run_pipeline(cm_handle_t h, Workspace& w, const cm_segment_t* segs, int n_se
   }
   const uint32_t n_frames = plan.n_frames;
   const int64_t total = plan.total_points;
-  const uint32_t epoch = next_epoch(h);
   w.has_run = true; w.report_valid = false; w.profiled = h->profiling;
   w.n_frames = n_frames; w.n_segs = (uint32_t)n_seg; w.points_in = total; w.launches = 0;
   w.ran_k1 = true; w.ran_voxel = false; w.stream = st;
   w.voxel_pts = w.surv_xyzi;
   h->last = &w;
 
-  CM_CUDA(h, cudaEventRecord(w.ev[EV_START], st));
+  if (!w.capturing) CM_CUDA(h, cudaEventRecord(w.ev[EV_START], st));
   CM_CUDA(h, cudaMemsetAsync(w.meta, 0, w.ml.zero_bytes, st));
   K1Params kp;
-  kp.segs = w.segs; kp.n_seg = (uint32_t)n_seg; kp.n_tiles = plan.n_tiles; kp.n_frames = n_frames; kp.epoch = epoch;
+  kp.segs = w.segs; kp.n_seg = (uint32_t)n_seg; kp.n_tiles = plan.n_tiles; kp.n_frames = n_frames; kp.epoch = 0;
   kp.tiles_per_seg = plan.tiles_per_seg; kp.tile_seg = w.tile_seg;
   kp.crop = h->crop;
   kp.surv_xyzi = w.surv_xyzi; kp.surv_src = w.surv_src;
@@ -523,9 +518,9 @@ int run_pipeline(cm_handle_t h, Workspace& w, const cm_segment_t* segs, int n_se
     CM_CUDA(h, cudaEventRecord(w.ev[EV_K1], st));
     return CM_OK;
   }
-  CM_CUDA(h, cudaEventRecord(w.ev[EV_K1], st));
+  if (!w.capturing) CM_CUDA(h, cudaEventRecord(w.ev[EV_K1], st));
   VoxelParams vp;
-  fill_voxel_params(h, w, vp, w.surv_xyzi, n_frames, (uint32_t)total, epoch);
+  fill_voxel_params(h, w, vp, w.surv_xyzi, n_frames, (uint32_t)total);
   return run_voxel(h, w, vp, st, true);  // the tile scan rides in the grid-setup launch
 }
 
@@ -589,6 +584,7 @@ int fetch_report(cm_handle_t h, Workspace& w, cudaEvent_t already_copied = nullp
   const int last_ev = w.ran_voxel ? EV_CENT : EV_K1;
   float ms = 0.f;
   if (cudaEventElapsedTime(&ms, w.ev[EV_START], w.ev[last_ev]) == cudaSuccess) s.gpu_ms = ms;
+  else cudaGetLastError();  // a failed query must not surface later as the result of an unrelated launch
   for (auto& v : h->stage_ms) v = -1.f;
   h->stage_ms[EV_START] = s.gpu_ms;
   if (w.profiled) {
@@ -690,9 +686,64 @@ int merge_async_impl(cm_handle_t h, uint64_t mask, int64_t* ticket) {
     CM_CUDA(h, cudaStreamWaitEvent(sl.stream, ss.copied, 0));
   }
   if (segs.empty()) return fail(h, CM_E_NOT_READY, "no submitted cloud for any sensor in the mask");
-  rc = run_pipeline(h, sl.ws, segs.data(), (int)segs.size(), sl.stream, true);
-  if (rc != CM_OK) return rc;
-  CM_CUDA(h, cudaMemcpyAsync(sl.ws.report, sl.ws.meta, sl.ws.ml.total, cudaMemcpyDeviceToHost, sl.stream));
+  // ---- replay / capture / plain enqueue ---------------------------------------------------------------------------------
+  unsigned long long cells = 0;
+  bool graphable = h->use_graph && !h->profiling && crop_cell_bound(h, &cells);  // an unbounded grid needs a host round trip
+  std::string key;
+  if (graphable) {
+    key.assign(reinterpret_cast<const char*>(segs.data()), segs.size() * sizeof(cm_segment_t));
+    for (const cm_segment_t& g : segs) key.append(reinterpret_cast<const char*>(h->mats_host + g.sensor * 12), 12 * sizeof(float));
+    key.append(reinterpret_cast<const char*>(&h->crop), sizeof(h->crop));
+    key.append(reinterpret_cast<const char*>(h->inv_leaf), sizeof(h->inv_leaf));
+    key.append(reinterpret_cast<const char*>(&h->min_points), sizeof(h->min_points));
+    key.append(reinterpret_cast<const char*>(&h->downsample_all), sizeof(h->downsample_all));
+  }
+  bool launched = false;
+  if (graphable && sl.graph && sl.graph_key == key) {
+    Workspace& w = sl.ws;  // same configuration as the captured frame: every host-side field of the run is unchanged
+    w.has_run = true; w.report_valid = false; w.dense_valid = false; w.stream = sl.stream;
+    h->last = &w;
+    CM_CUDA(h, cudaEventRecord(w.ev[EV_START], sl.stream));
+    CM_CUDA(h, cudaGraphLaunch(sl.graph, sl.stream));
+    CM_CUDA(h, cudaEventRecord(w.ev[EV_CENT], sl.stream));
+    launched = true;
+  } else if (graphable && sl.graph_seen == key) {
+    // second frame with this configuration (its segment table is already on the device): capture, instantiate, launch
+    if (sl.graph) { cudaGraphExecDestroy(sl.graph); sl.graph = nullptr; sl.graph_key.clear(); }
+    cudaGraph_t g = nullptr;
+    if (cudaStreamBeginCapture(sl.stream, cudaStreamCaptureModeRelaxed) == cudaSuccess) {
+      sl.ws.capturing = true;
+      rc = run_pipeline(h, sl.ws, segs.data(), (int)segs.size(), sl.stream, true);
+      sl.ws.capturing = false;
+      cudaError_t ce = cudaSuccess;
+      if (rc == CM_OK) ce = cudaMemcpyAsync(sl.ws.report, sl.ws.meta, sl.ws.ml.total, cudaMemcpyDeviceToHost, sl.stream);
+      const cudaError_t ee = cudaStreamEndCapture(sl.stream, &g);
+      if (rc == CM_OK && ce == cudaSuccess && ee == cudaSuccess && g &&
+          cudaGraphInstantiate(&sl.graph, g, 0) == cudaSuccess) {
+        sl.graph_key = key;
+        cudaGraphDestroy(g);
+        CM_CUDA(h, cudaEventRecord(sl.ws.ev[EV_START], sl.stream));
+        CM_CUDA(h, cudaGraphLaunch(sl.graph, sl.stream));
+        CM_CUDA(h, cudaEventRecord(sl.ws.ev[EV_CENT], sl.stream));
+        launched = true;
+      } else {
+        if (g) cudaGraphDestroy(g);
+        sl.graph = nullptr;
+        h->use_graph = false;  // not capturable here: stay on the plain path
+        cudaGetLastError();
+      }
+    } else {
+      h->use_graph = false;
+      cudaGetLastError();
+    }
+  }
+  if (!launched) {
+    if (sl.graph && sl.graph_key != key) { cudaGraphExecDestroy(sl.graph); sl.graph = nullptr; sl.graph_key.clear(); }
+    rc = run_pipeline(h, sl.ws, segs.data(), (int)segs.size(), sl.stream, true);
+    if (rc != CM_OK) return rc;
+    CM_CUDA(h, cudaMemcpyAsync(sl.ws.report, sl.ws.meta, sl.ws.ml.total, cudaMemcpyDeviceToHost, sl.stream));
+    sl.graph_seen = key;
+  }
   CM_CUDA(h, cudaEventRecord(sl.done, sl.stream));
   for (int s = 0; s < h->cfg.max_sensors; ++s)
     if ((used >> s) & 1ull) sl.sensor[s].submitted = false;
@@ -815,6 +866,7 @@ int cm_create(const cm_config_t* cfg, cm_handle_t* out) {
   h->device = c.device;
   if (cudaSetDevice(h->device) != cudaSuccess) { delete h; return CM_E_CUDA; }
   if (configure_device_kernels() != cudaSuccess || configure_sort_kernels() != cudaSuccess) { delete h; return CM_E_CUDA; }
+  if (getenv("CM_NO_GRAPH")) h->use_graph = false;
   for (int s = 0; s < CM_MAX_SENSORS; ++s) {
     float* m = h->mats_host + s * 12;
     for (int k = 0; k < 12; ++k) m[k] = (k % 5 == 0) ? 1.f : 0.f;  // identity rows
@@ -838,6 +890,7 @@ int cm_destroy(cm_handle_t h) {
     ws_free(sl.ws);
     cudaFree(sl.raw_dev); cudaFreeHost(sl.raw_pinned);
     for (auto& ss : sl.sensor) if (ss.copied) cudaEventDestroy(ss.copied);
+    if (sl.graph) cudaGraphExecDestroy(sl.graph);
     if (sl.stream) cudaStreamDestroy(sl.stream);
     if (sl.done) cudaEventDestroy(sl.done);
   }
@@ -1048,7 +1101,6 @@ int cm_dev_voxelgrid(cm_handle_t h, const float* xyzi_dev, int64_t n_points, int
   if (n_points < 0 || n_points > (int64_t)w.cap_points) return fail(h, CM_E_CAPACITY, "%lld points > capacity %u", (long long)n_points, w.cap_points);
   if (n_points > 0 && (!xyzi_dev || (reinterpret_cast<uintptr_t>(xyzi_dev) & 15u))) return fail(h, CM_E_INVALID, "xyzi_dev must be 16-byte aligned");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  const uint32_t epoch = next_epoch(h);
   w.has_run = true; w.report_valid = false; w.profiled = h->profiling;
   w.n_frames = 1; w.n_segs = 0; w.points_in = n_points; w.launches = 0;
   w.ran_k1 = false; w.ran_voxel = false; w.stream = st; w.n_k1_tiles = 0; w.dense_valid = false;
@@ -1057,7 +1109,7 @@ int cm_dev_voxelgrid(cm_handle_t h, const float* xyzi_dev, int64_t n_points, int
   CM_CUDA(h, cudaEventRecord(w.ev[EV_START], st));
   CM_CUDA(h, cudaMemsetAsync(w.meta, 0, w.ml.zero_bytes, st));
   VoxelParams vp;
-  fill_voxel_params(h, w, vp, w.voxel_pts, 1, (uint32_t)n_points, epoch);
+  fill_voxel_params(h, w, vp, w.voxel_pts, 1, (uint32_t)n_points);
   CM_CUDA(h, launch_minmax(w.voxel_pts, (uint32_t)n_points, vp.ctrl, vp.acc, const_cast<uint32_t*>(vp.frame_surv_start), st));
   ++w.launches;
   if (h->have_bounds) {

@@ -68,7 +68,10 @@ struct VoxelParams {
   void* tmp_xyzi;                    // tile-local voxel outputs before compaction
   uint32_t* tmp_count;
   unsigned long long* tmp_idx;
-  uint32_t epoch;                    // epochs epoch+1 .. epoch+8 are used by the sort passes, epoch+9 by the centroid pass
+  uint32_t* epoch_dev;               // device-resident run epoch: advanced by 16 in k_grid_setup, read by the sort passes
+                                     // (pass p tags its look-back words with *epoch_dev + 1 + p), so no kernel argument
+                                     // changes from run to run and a captured launch sequence can be replayed as a graph
+  uint32_t lb_sort_words;            // size of lb_sort, for the clear on epoch wrap-around
   uint32_t max_passes;               // how many pass launches the host enqueues
   void* out_xyzi;
   uint32_t* out_count;

@@ -208,7 +208,7 @@ __global__ void __launch_bounds__(RS_THREADS, RS_MIN_CTAS) k_onesweep_pass(const
 
   const uint32_t tid = threadIdx.x, lane = tid & 31u;
   const uint32_t warp = __shfl_sync(0xFFFFFFFFu, tid >> 5, 0);  // provably warp-uniform
-  const uint32_t epoch = p.epoch + 1u + (uint32_t)pass;
+  const uint32_t epoch = *p.epoch_dev + 1u + (uint32_t)pass;
   unsigned long long* const rows = p.lb_sort + CM_RADIX;  // row -1 lives in front
   uint32_t* const err = &p.ctrl->error;
   // CTAs of a 1-D grid are dispatched in index order, so the scanners are resident before any worker can wait for them

@@ -276,6 +276,15 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_grid_setup(const VoxelParams p
     p.grid[f] = g;
   }
   __syncthreads();
+  // the run epoch of the look-back words (30 bits): on wrap-around clear the words and start over
+  {
+    const uint32_t e = *p.epoch_dev;
+    const bool wrap = e + 64u >= (1u << 30);
+    if (wrap)
+      for (uint32_t i = tid; i < p.lb_sort_words; i += SCAN_THREADS) p.lb_sort[i] = 0ull;
+    __syncthreads();
+    if (tid == 0) *p.epoch_dev = wrap ? 16u : e + 16u;
+  }
   if (tid == 0) {
     const uint32_t key_frames = p.n_frames + (p.ctrl->has_invalid ? 1u : 0u);
     const uint32_t frame_bits = key_frames <= 1u ? 0u : (uint32_t)(32 - __clz((int)(key_frames - 1u)));
