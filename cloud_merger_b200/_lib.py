@@ -109,6 +109,9 @@ SYMBOLS = {
     "cm_dev_zone_split": (C.c_int, [_H, C.c_void_p, C.c_int64, C.c_void_p]),
     "cm_get_zone_out": (C.c_int, [_H, C.POINTER(CmZoneOut)]),
     "cm_zone_split": (C.c_int, [_H, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_int64, C.POINTER(C.c_int64)]),
+    "cm_dev_radius_outlier": (C.c_int, [_H, C.c_void_p, C.c_int64, C.c_double, C.c_int, C.c_int, C.c_void_p]),
+    "cm_radius_outlier": (C.c_int, [_H, C.c_void_p, C.c_int64, C.c_double, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
+                                    C.c_int64, C.POINTER(C.c_int64)]),
     "cm_sync": (C.c_int, [_H]),
     "cm_get_stats": (C.c_int, [_H, C.POINTER(CmStats)]),
     "cm_get_device_out": (C.c_int, [_H, C.POINTER(CmDeviceOut)]),

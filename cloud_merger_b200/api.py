@@ -201,6 +201,30 @@ class CloudMerger:
         nz = self._n_zones
         return [(ox[begin[z]:begin[z + 1]].copy(), osrc[begin[z]:begin[z + 1]].copy()) for z in range(nz)]
 
+    # -- radius outlier removal: outlierRemoval() of the reference (pc_preprocessing_main.cpp:184-192) ----------------------
+    def dev_radius_outlier(self, xyzi_ptr: int, n_points: int, radius: float, min_neighbors: int = 1,
+                           negative: bool = False, stream: int = 0):
+        """Device form; fetch the survivors with radius_outlier_out()."""
+        self._check(self._lib.cm_dev_radius_outlier(self._h, C.c_void_p(xyzi_ptr or None), C.c_int64(n_points),
+                                                    C.c_double(radius), int(min_neighbors), int(negative),
+                                                    C.c_void_p(stream or None)))
+
+    def radius_outlier_out(self):
+        """(xyzi [k,4], idx [k]) of the last device radius outlier removal."""
+        return self.zone_out()[0]
+
+    def radius_outlier(self, xyzi: np.ndarray, radius: float, min_neighbors: int = 1, negative: bool = False):
+        """Host-buffer form: (xyzi [k,4] float32, idx [k] uint32 indices into the input, ascending)."""
+        a = np.ascontiguousarray(xyzi, np.float32).reshape(-1, 4)
+        n = len(a)
+        ox = np.empty((max(n, 1), 4), np.float32)
+        oi = np.empty(max(n, 1), np.uint32)
+        k = C.c_int64()
+        self._check(self._lib.cm_radius_outlier(self._h, a.ctypes.data_as(C.c_void_p), C.c_int64(n), C.c_double(radius),
+                                                int(min_neighbors), int(negative), ox.ctypes.data_as(C.c_void_p),
+                                                oi.ctypes.data_as(C.c_void_p), C.c_int64(n), C.byref(k)))
+        return ox[:k.value].copy(), oi[:k.value].copy()
+
     def set_voxel(self, leaf, min_points: int = 2, downsample_all: bool = True):
         leaf = np.broadcast_to(np.asarray(leaf, np.float32), (3,)).copy()
         self._check(self._lib.cm_set_voxel(self._h, leaf.ctypes.data_as(C.POINTER(C.c_float)), int(min_points),

@@ -158,6 +158,7 @@ struct cm_handle_s {
     bool ran = false;
     int64_t launches = 0;
     ZoneParams last{};           // the last split, so that its scatter can be repeated after the outputs grew
+    int n_zones_run = 0;         // zones of the last split (1 for a radius outlier removal)
   } zw;
   // host path
   std::vector<Slot> slots;
@@ -333,7 +334,8 @@ void fill_voxel_params(cm_handle_t h, Workspace& w, VoxelParams& vp, const float
 }
 
 // VoxelGrid stages on vp.pts. bounded: the crop box bounds the key width, so no device round trip is needed.
-int run_voxel(cm_handle_t h, Workspace& w, VoxelParams& vp, cudaStream_t st, bool scan_k1_tiles = false) {
+int run_voxel(cm_handle_t h, Workspace& w, VoxelParams& vp, cudaStream_t st, bool scan_k1_tiles = false,
+              bool with_centroid = true) {
   unsigned long long cells = 0;
   const bool bounded = w.ran_k1 && crop_cell_bound(h, &cells);
   if (bounded) {
@@ -370,6 +372,10 @@ int run_voxel(cm_handle_t h, Workspace& w, VoxelParams& vp, cudaStream_t st, boo
     ++w.launches;
   }
   if (h->profiling) CM_CUDA(h, cudaEventRecord(w.ev[EV_SORT], st));
+  if (!with_centroid) {  // the caller only wants the points sorted by cell (radius outlier removal)
+    w.ran_voxel = false;
+    return CM_OK;
+  }
   CM_CUDA(h, launch_centroid(vp, st));
   w.launches += CM_CENTROID_LAUNCHES;
   if (!w.capturing) CM_CUDA(h, cudaEventRecord(w.ev[EV_CENT], st));
@@ -1186,9 +1192,9 @@ int zone_ws_ensure(cm_handle_t h, size_t points) {
   return CM_OK;
 }
 
-int zone_run(cm_handle_t h, const float4* pts, int64_t n_points, cudaStream_t st) {
+int zone_run(cm_handle_t h, const float4* pts, int64_t n_points, cudaStream_t st, bool mask_given = false) {
   cm_handle_s::ZoneWs& z = h->zw;
-  if (h->zones.n_zones <= 0) return fail(h, CM_E_INVALID, "no zones configured (cm_set_zones)");
+  if (!mask_given && h->zones.n_zones <= 0) return fail(h, CM_E_INVALID, "no zones configured (cm_set_zones)");
   if (n_points < 0 || n_points > 0xFFFFFFF0ll) return fail(h, CM_E_INVALID, "bad n_points");
   int rc = zone_ws_ensure(h, (size_t)n_points);
   if (rc != CM_OK) return rc;
@@ -1196,6 +1202,12 @@ int zone_run(cm_handle_t h, const float4* pts, int64_t n_points, cudaStream_t st
   zp.pts = pts; zp.n_points = (uint32_t)n_points;
   zp.n_tiles = (uint32_t)((n_points + zone_tile_points() - 1) / zone_tile_points());
   zp.zones = h->zones;
+  zp.mask_given = mask_given ? 1u : 0u;
+  if (mask_given) {  // one output: the points whose flag is set
+    zp.zones = ZoneSet{};
+    zp.zones.n_zones = 1;
+  }
+  z.n_zones_run = zp.zones.n_zones;
   zp.mask = z.mask; zp.tile_count = z.tile_count; zp.tile_offset = z.tile_offset; zp.zone_begin = z.zone_begin;
   zp.overflow = z.overflow; zp.out_capacity = (uint32_t)std::min<size_t>(z.cap_out, 0xFFFFFFF0u);
   zp.out_xyzi = z.out_xyzi; zp.out_src = z.out_src;
@@ -1252,8 +1264,8 @@ int cm_get_zone_out(cm_handle_t h, cm_zone_out_t* out) {
     ++z.launches;
   }
   memset(out, 0, sizeof(*out));
-  out->n_zones = h->zones.n_zones;
-  for (int k = 0; k <= h->zones.n_zones; ++k) out->begin[k] = z.report[k];
+  out->n_zones = z.n_zones_run;
+  for (int k = 0; k <= z.n_zones_run; ++k) out->begin[k] = z.report[k];
   out->xyzi = reinterpret_cast<const float*>(z.out_xyzi);
   out->src = z.out_src;
   if (z.report[CM_MAX_ZONES + 1])
@@ -1284,6 +1296,93 @@ int cm_zone_split(cm_handle_t h, const float* xyzi_host, int64_t n_points, float
   std::lock_guard<std::mutex> lk(h->mu);
   if (out_xyzi && total) CM_CUDA(h, cudaMemcpy(out_xyzi, zo.xyzi, (size_t)total * 16, cudaMemcpyDeviceToHost));
   if (out_src && total) CM_CUDA(h, cudaMemcpy(out_src, zo.src, (size_t)total * 4, cudaMemcpyDeviceToHost));
+  return CM_OK;
+}
+
+// ---- radius outlier removal ---------------------------------------------------------------------------------------------
+namespace {
+int radius_outlier_run(cm_handle_t h, const float4* pts, int64_t n_points, double radius, int min_neighbors, int negative,
+                       cudaStream_t st) {
+  if (!(radius > 0.0) || min_neighbors < 0) return fail(h, CM_E_INVALID, "radius must be > 0 and min_neighbors >= 0");
+  int rc = ensure_batch_ws(h);
+  if (rc != CM_OK) return rc;
+  Workspace& w = h->batch;
+  if (n_points < 0 || n_points > (int64_t)w.cap_points) return fail(h, CM_E_CAPACITY, "%lld points > capacity %u", (long long)n_points, w.cap_points);
+  rc = zone_ws_ensure(h, (size_t)n_points);
+  if (rc != CM_OK) return rc;
+  // cells a little wider than the radius: two points closer than the radius are then at most one cell apart on every
+  // axis even after the float rounding of x * (1 / cell) (valid below 2^14 cells from the origin, checked on the device)
+  const float cell = (float)radius * 1.00390625f;
+  w.has_run = true; w.report_valid = false; w.profiled = false;
+  w.n_frames = 1; w.n_segs = 0; w.points_in = n_points; w.launches = 0;
+  w.ran_k1 = false; w.ran_voxel = false; w.stream = st; w.n_k1_tiles = 0; w.dense_valid = false;
+  w.voxel_pts = pts;
+  h->last = &w;
+  CM_CUDA(h, cudaEventRecord(w.ev[EV_START], st));
+  CM_CUDA(h, cudaMemsetAsync(w.meta, 0, w.ml.zero_bytes, st));
+  VoxelParams vp;
+  fill_voxel_params(h, w, vp, pts, 1, (uint32_t)n_points);
+  for (int k = 0; k < 3; ++k) vp.inv_leaf[k] = 1.0f / cell;
+  CM_CUDA(h, launch_minmax(pts, (uint32_t)n_points, vp.ctrl, vp.acc, const_cast<uint32_t*>(vp.frame_surv_start), st));
+  ++w.launches;
+  CM_CUDA(h, cudaEventRecord(w.ev[EV_K1], st));
+  rc = run_voxel(h, w, vp, st, false, false);  // keys + sort only
+  if (rc != CM_OK) return rc;
+  vp.key_bytes = w.key_bytes;
+  RorParams rp;
+  rp.r2 = (float)(radius * radius);
+  rp.min_pts = (uint32_t)min_neighbors;
+  rp.negative = negative ? 1u : 0u;
+  rp.mask = h->zw.mask;
+  if (n_points) CM_CUDA(h, cudaMemsetAsync(h->zw.mask, 0, (size_t)n_points * sizeof(unsigned short), st));
+  CM_CUDA(h, launch_radius_count(vp, rp, st));
+  ++w.launches;
+  CM_CUDA(h, cudaEventRecord(w.ev[EV_CENT], st));
+  return zone_run(h, pts, n_points, st, true);
+}
+}  // namespace
+
+int cm_dev_radius_outlier(cm_handle_t h, const float* xyzi_dev, int64_t n_points, double radius, int min_neighbors,
+                          int negative, void* stream) {
+  if (!h) return CM_E_INVALID;
+  std::lock_guard<std::mutex> lk(h->mu);
+  CM_CUDA(h, cudaSetDevice(h->device));
+  if (n_points > 0 && (!xyzi_dev || (reinterpret_cast<uintptr_t>(xyzi_dev) & 15u))) return fail(h, CM_E_INVALID, "xyzi_dev must be 16-byte aligned");
+  return radius_outlier_run(h, reinterpret_cast<const float4*>(xyzi_dev), n_points, radius, min_neighbors, negative,
+                            static_cast<cudaStream_t>(stream));
+}
+
+int cm_radius_outlier(cm_handle_t h, const float* xyzi_host, int64_t n_points, double radius, int min_neighbors,
+                      int negative, float* out_xyzi, uint32_t* out_idx, int64_t capacity, int64_t* n_out) {
+  if (!h || !n_out || n_points < 0 || (n_points > 0 && !xyzi_host)) return CM_E_INVALID;
+  cm_zone_out_t zo;
+  {
+    std::lock_guard<std::mutex> lk(h->mu);
+    CM_CUDA(h, cudaSetDevice(h->device));
+    int rc = zone_ws_ensure(h, (size_t)n_points);
+    if (rc != CM_OK) return rc;
+    cm_handle_s::ZoneWs& z = h->zw;
+    if (!z.in_stage) CM_CUDA(h, dev_alloc(&z.in_stage, z.cap_points));
+    CM_CUDA(h, cudaMemcpyAsync(z.in_stage, xyzi_host, (size_t)n_points * 16, cudaMemcpyHostToDevice, nullptr));
+    rc = radius_outlier_run(h, z.in_stage, n_points, radius, min_neighbors, negative, nullptr);
+    if (rc != CM_OK) return rc;
+  }
+  int rc = cm_get_zone_out(h, &zo);
+  *n_out = zo.begin[1];
+  if (rc != CM_OK) return rc;
+  {
+    std::lock_guard<std::mutex> lk(h->mu);
+    // device-side errors of the key / sort stage (e.g. the radius is too small for the extent of the cloud)
+    uint32_t dev_err = 0;
+    Workspace& w = h->batch;
+    CM_CUDA(h, cudaMemcpy(&dev_err, &reinterpret_cast<Ctrl*>(w.meta + w.ml.off_ctrl)->error, sizeof(dev_err), cudaMemcpyDeviceToHost));
+    if (dev_err == CM_DEV_E_KEY_RANGE) return fail(h, CM_E_KEY_RANGE, "radius too small for the extent of the cloud (cell grid exceeds the key range)");
+    if (dev_err) return fail(h, CM_E_INTERNAL, "device error %u", dev_err);
+    const int64_t total = zo.begin[1];
+    if (total > capacity) return fail(h, CM_E_CAPACITY, "%lld points kept, caller capacity %lld", (long long)total, (long long)capacity);
+    if (out_xyzi && total) CM_CUDA(h, cudaMemcpy(out_xyzi, zo.xyzi, (size_t)total * 16, cudaMemcpyDeviceToHost));
+    if (out_idx && total) CM_CUDA(h, cudaMemcpy(out_idx, zo.src, (size_t)total * 4, cudaMemcpyDeviceToHost));
+  }
   return CM_OK;
 }
 

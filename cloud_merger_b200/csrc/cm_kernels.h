@@ -102,6 +102,7 @@ struct ZoneParams {
   uint32_t n_tiles;          // ceil(n_points / zone_tile_points())
   ZoneSet zones;
   unsigned short* mask;      // [n_points] zone membership of every point
+  uint32_t mask_given;       // the masks were produced by another kernel (radius outlier removal): only count them
   uint32_t* tile_count;      // [n_zones][n_tiles]
   uint32_t* tile_offset;     // [n_zones][n_tiles] where the tile's points of the zone start in the output
   uint32_t* zone_begin;      // [n_zones + 1] zone z occupies [zone_begin[z], zone_begin[z+1]) of the output
@@ -110,6 +111,15 @@ struct ZoneParams {
   float4* out_xyzi;
   uint32_t* out_src;         // index of every output point in the input cloud
 };
+// ---- radius outlier removal on the sorted cell keys (cm_outlier.cu) -------------------------------------------------------
+struct RorParams {
+  float r2;              // (float)(radius * radius): FLANN counts squared distances strictly below it
+  uint32_t min_pts;      // keep iff count (the point itself included) > min_pts
+  uint32_t negative;
+  unsigned short* mask;  // [n_points] keep flag per input point (cleared by the caller)
+};
+cudaError_t launch_radius_count(const VoxelParams& p, const RorParams& r, cudaStream_t stream);
+
 uint32_t zone_tile_points();
 cudaError_t launch_zone_split(const ZoneParams& p, cudaStream_t stream);  // 3 launches
 cudaError_t launch_zone_scatter(const ZoneParams& p, cudaStream_t stream);  // the last of them again, after out_* grew

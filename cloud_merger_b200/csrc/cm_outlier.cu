@@ -1,0 +1,96 @@
+// cm_outlier.cu -- pcl::RadiusOutlierRemoval on the sorted cell keys for sm_100a.
+//
+// Replaces outlierRemoval() of the reference (pcl_preprocessing/src/pc_preprocessing_main.cpp:184-192, called from
+// removeGround :119; parameters Parameter.h:23-24: radius 0.15 m, min_neighbor 1): PCL 1.8.1 builds a FLANN kd-tree over the
+// cloud and, for every point, counts the points strictly inside the radius (the point itself included); a point is kept iff
+// that count exceeds min_pts (`negative` inverts).
+//
+// Here the cloud goes through the VoxelGrid front end with a cell edge slightly above the radius (keys + onesweep sort:
+// points of one cell become one run, cells of one x-row neighbours in key order), and every point then counts inside the
+// 3 x 3 rows of cells around its own: nine binary searches for the row segments [x-1, x+1], a walk over each segment
+// with the squared distance in FLANN's float order ((dx*dx + dy*dy) + dz*dz, never fused), and an early exit as soon as
+// the count decides the outcome. The keep flags go to the zone-slicing mask array, whose scan + scatter kernels then
+// compact the survivors in input order (cm_zones.cu).
+//
+// Roofline: HBM/L2 for the gathers; algorithmic bytes ~ n * (8 record + 16 point) * (neighbours visited).
+#include "cm_kernels.h"
+
+namespace cm {
+
+namespace {
+
+constexpr int ROR_THREADS = 256;
+
+template <typename KeyT>
+__global__ void __launch_bounds__(ROR_THREADS) k_ror_count(const VoxelParams p, const RorParams r) {
+  constexpr bool REC = sizeof(KeyT) == 4;
+  const uint32_t M = p.frame_surv_start[p.n_frames];
+  const uint32_t i = blockIdx.x * ROR_THREADS + threadIdx.x;
+  if (i >= M) return;
+  const SortInfo si = *p.info;
+  const bool odd = (si.num_passes & 1u) != 0u;
+  const void* __restrict__ sorted = odd ? p.keys_b : p.keys_a;
+  const uint32_t* __restrict__ vals = odd ? p.vals_b : p.vals_a;
+  auto key_at = [&](uint32_t j) -> unsigned long long {
+    if constexpr (REC) return reinterpret_cast<const uint2*>(sorted)[j].x;
+    else return reinterpret_cast<const unsigned long long*>(sorted)[j];
+  };
+  auto val_at = [&](uint32_t j) -> uint32_t {
+    if constexpr (REC) return reinterpret_cast<const uint2*>(sorted)[j].y;
+    else return vals[j];
+  };
+  const uint32_t idx_bits = si.idx_bits;
+  const unsigned long long limit = idx_bits >= 64 ? ~0ull : (1ull << idx_bits);  // keys of frame >= 1: non-finite points
+  const unsigned long long key = key_at(i);
+  if (si.key_frames > 1u && key >= limit) return;  // never kept (the mask array was cleared)
+  const GridDev g = p.grid[0];
+  // the cell margin (see the host side) only covers |coordinate / cell| < 2^14
+  if (i == 0) {
+    int worst = 0;
+    for (int a = 0; a < 3; ++a) worst = max(worst, max(abs(g.min_b[a]), abs(g.max_b[a])));
+    if (worst >= (1 << 14)) atomicExch(&p.ctrl->error, (uint32_t)CM_DEV_E_KEY_RANGE);
+  }
+  const unsigned long long d0 = (unsigned long long)g.div_b[0], d1 = (unsigned long long)g.div_b[1],
+                           d2 = (unsigned long long)g.div_b[2];
+  const unsigned long long c0 = key % d0, t = key / d0, c1 = t % d1, c2 = t / d1;
+  const uint32_t me = val_at(i);
+  const float4 q = __ldg(p.pts + me);
+  const unsigned long long x_lo = c0 > 0 ? c0 - 1 : 0, x_hi = c0 + 1 < d0 ? c0 + 1 : d0 - 1;
+  uint32_t cnt = 0;
+  const uint32_t need = r.min_pts + 1u;  // the outcome is decided once this many neighbours were seen
+  for (int dz = -1; dz <= 1 && cnt < need; ++dz) {
+    if ((dz < 0 && c2 == 0) || (dz > 0 && c2 + 1 >= d2)) continue;
+    for (int dy = -1; dy <= 1 && cnt < need; ++dy) {
+      if ((dy < 0 && c1 == 0) || (dy > 0 && c1 + 1 >= d1)) continue;
+      const unsigned long long row = ((c2 + dz) * d1 + (c1 + dy)) * d0;
+      const unsigned long long k_lo = row + x_lo, k_hi = row + x_hi;
+      // lower bound of k_lo in the sorted keys
+      uint32_t lo = 0, hi = M;
+      while (lo < hi) {
+        const uint32_t mid = (lo + hi) >> 1;
+        if (key_at(mid) < k_lo) lo = mid + 1; else hi = mid;
+      }
+      for (uint32_t j = lo; j < M && cnt < need; ++j) {
+        if (key_at(j) > k_hi) break;
+        const float4 d = __ldg(p.pts + val_at(j));
+        const float ex = __fsub_rn(q.x, d.x), ey = __fsub_rn(q.y, d.y), ez = __fsub_rn(q.z, d.z);
+        const float acc = __fadd_rn(__fadd_rn(__fmul_rn(ex, ex), __fmul_rn(ey, ey)), __fmul_rn(ez, ez));
+        if (acc < r.r2) ++cnt;
+      }
+    }
+  }
+  const bool inlier = cnt > r.min_pts;
+  if (inlier != (r.negative != 0u)) r.mask[me] = 1;
+}
+
+}  // namespace
+
+cudaError_t launch_radius_count(const VoxelParams& p, const RorParams& r, cudaStream_t stream) {
+  if (p.max_points == 0) return cudaSuccess;
+  const uint32_t blocks = (p.max_points + ROR_THREADS - 1) / ROR_THREADS;
+  if (p.key_bytes == 4) k_ror_count<uint32_t><<<blocks, ROR_THREADS, 0, stream>>>(p, r);
+  else k_ror_count<unsigned long long><<<blocks, ROR_THREADS, 0, stream>>>(p, r);
+  return cudaGetLastError();
+}
+
+}  // namespace cm

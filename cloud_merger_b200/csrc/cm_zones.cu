@@ -58,7 +58,7 @@ __device__ __forceinline__ uint32_t zone_mask(const ZoneSet& zs, const float4& v
   return m;
 }
 
-template <bool BOX>
+template <bool BOX, bool GIVEN>
 __global__ void __launch_bounds__(ZN_THREADS) k_zone_count(const ZoneParams p) {
   __shared__ uint32_t s_cnt[CM_MAX_ZONES];
   const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
@@ -71,14 +71,21 @@ __global__ void __launch_bounds__(ZN_THREADS) k_zone_count(const ZoneParams p) {
 #pragma unroll
   for (int i = 0; i < ZN_IPT; ++i) {
     const uint32_t g = base + 32 * i;
-    v[i] = g < n ? ldg_stream_f4(p.pts + g) : make_float4(0.f, 0.f, 0.f, 0.f);
+    v[i] = (!GIVEN && g < n) ? ldg_stream_f4(p.pts + g) : make_float4(0.f, 0.f, 0.f, 0.f);
   }
   uint32_t cnt_z = 0;  // lane z accumulates the warp's count for zone z
 #pragma unroll
   for (int i = 0; i < ZN_IPT; ++i) {
     const uint32_t g = base + 32 * i;
-    const uint32_t m = g < n ? zone_mask<BOX>(p.zones, v[i]) : 0u;
-    if (g < n) p.mask[g] = (unsigned short)m;
+    uint32_t m = 0;
+    if (g < n) {
+      if (GIVEN) {
+        m = p.mask[g];
+      } else {
+        m = zone_mask<BOX>(p.zones, v[i]);
+        p.mask[g] = (unsigned short)m;
+      }
+    }
     for (int z = 0; z < p.zones.n_zones; ++z) {
       const uint32_t b = __ballot_sync(0xFFFFFFFFu, (m >> z) & 1u);
       if ((int)lane == z) cnt_z += (uint32_t)__popc(b);
@@ -197,8 +204,9 @@ cudaError_t launch_zone_scatter(const ZoneParams& p, cudaStream_t stream) {
 
 cudaError_t launch_zone_split(const ZoneParams& p, cudaStream_t stream) {
   if (p.n_tiles) {
-    if (p.zones.all_box) k_zone_count<true><<<p.n_tiles, ZN_THREADS, 0, stream>>>(p);
-    else k_zone_count<false><<<p.n_tiles, ZN_THREADS, 0, stream>>>(p);
+    if (p.mask_given) k_zone_count<false, true><<<p.n_tiles, ZN_THREADS, 0, stream>>>(p);
+    else if (p.zones.all_box) k_zone_count<true, false><<<p.n_tiles, ZN_THREADS, 0, stream>>>(p);
+    else k_zone_count<false, false><<<p.n_tiles, ZN_THREADS, 0, stream>>>(p);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
   }

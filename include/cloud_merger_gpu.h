@@ -256,6 +256,19 @@ CM_API int cm_dev_zone_split(cm_handle_t h, const float* xyzi_dev, int64_t n_poi
 CM_API int cm_get_zone_out(cm_handle_t h, cm_zone_out_t* out);
 CM_API int cm_zone_split(cm_handle_t h, const float* xyzi_host, int64_t n_points, float* out_xyzi, uint32_t* out_src,
                          int64_t capacity, int64_t* out_begin);
+/* Radius outlier removal. Replaces outlierRemoval() (pc_preprocessing_main.cpp:184-192, called from removeGround :119):
+ * pcl::RadiusOutlierRemoval<pcl::PointXYZI> with setRadiusSearch(radius), setMinNeighborsInRadius(min_neighbors),
+ * keep_organized false (Parameter.h:23-24: 0.15 m, 1). PCL 1.8.1 keeps a point iff MORE than min_neighbors points -- the
+ * point itself included -- lie strictly inside the radius (float squared distances, FLANN's order); negative != 0 keeps
+ * the others. Non-finite points are never kept. Survivors keep their input order.
+ *  cm_dev_radius_outlier: n packed float4 xyzi points on the device; results through cm_get_zone_out (one zone: xyzi +
+ *      the index of every survivor in the input). Uses the handle's batch workspace (the previous run's device outputs
+ *      are overwritten).
+ *  cm_radius_outlier: host buffers in and out; *n_out receives the number of survivors (also on CM_E_CAPACITY). */
+CM_API int cm_dev_radius_outlier(cm_handle_t h, const float* xyzi_dev, int64_t n_points, double radius,
+                                 int min_neighbors, int negative, void* stream);
+CM_API int cm_radius_outlier(cm_handle_t h, const float* xyzi_host, int64_t n_points, double radius, int min_neighbors,
+                             int negative, float* out_xyzi, uint32_t* out_idx, int64_t capacity, int64_t* n_out);
 /* Blocks until the last run on the handle finished, then reports. */
 CM_API int cm_sync(cm_handle_t h);
 CM_API int cm_get_stats(cm_handle_t h, cm_stats_t* out);

@@ -8,6 +8,7 @@
 //   void getCloudPart(const Cloud::Ptr, Cloud::Ptr, float length, float dev)  ->  getCloudPart(in, out, length, deviation)
 //   proceedX: getCloudPart x5 + the z windows of removeGround                 ->  getCloudPartsZSplit (one GPU pass)
 //   void fusePointclouds(Cloud::Ptr no_ground, Cloud::Ptr ground)             ->  FusedFrame::fuse (+ operator+= kept)
+//   void outlierRemoval(Cloud::Ptr)                                           ->  outlierRemoval(cloud)
 //   void voxelgrid(const Cloud::Ptr, Cloud::Ptr)                              ->  voxelgrid(in, out)
 //   callbackX(const Cloud input) ... main loop fuse + voxelgrid               ->  FusedFrame::onCloud / fuseAndVoxel
 //
@@ -88,6 +89,8 @@ struct Params {
   float voxel_size = 0.1f;
   int points_per_voxel = 2;
   float roi_width = 10.0f, roi_length = 75.0f, roi_mid = 15.0f, roi_z_min = -0.5f, roi_z_max = 3.0f;
+  float radius = 0.15f;      // outlier removal: radius [m] and minimum number of neighbours (Parameter.h:23-24)
+  float min_neighbor = 1;
 };
 
 inline cm_layout_t pcl_layout(bool is_dense) {
@@ -181,6 +184,32 @@ class Context {
     out.points.resize(v);
     if (v && !check(cm_memcpy_d2h(h_, out.points.data(), o.voxel_xyzi, v * 32, nullptr))) return clear(out);
     finish(out, in, true);
+    return true;
+  }
+
+  // Radius outlier removal of ONE host cloud (cm_radius_outlier); out keeps input order.
+  bool radius_outlier(const Cloud& in, Cloud& out, double radius, int min_neighbors) {
+    if (!check(h_ ? CM_OK : CM_E_NO_DEVICE)) return clear(out);
+    const int64_t n = static_cast<int64_t>(in.points.size());
+    if (n > max_points_ * max_sensors_) { rc_ = CM_E_CAPACITY; err_ = "cloud larger than the context capacity"; return clear(out); }
+    tmp_.resize(static_cast<size_t>(n) * 4);
+    for (int64_t i = 0; i < n; ++i) {
+      const PointXYZI& p = in.points[static_cast<size_t>(i)];
+      tmp_[i * 4 + 0] = p.x; tmp_[i * 4 + 1] = p.y; tmp_[i * 4 + 2] = p.z; tmp_[i * 4 + 3] = p.intensity;
+    }
+    zone_xyzi_.resize(static_cast<size_t>(n) * 4 + 4);
+    int64_t kept = 0;
+    if (!check(cm_radius_outlier(h_, tmp_.data(), n, radius, min_neighbors, 0, zone_xyzi_.data(), nullptr, n, &kept)))
+      return clear(out);
+    Cloud res;
+    res.points.resize(static_cast<size_t>(kept));
+    for (size_t i = 0; i < static_cast<size_t>(kept); ++i) {
+      PointXYZI& p = res.points[i];
+      p = PointXYZI();
+      p.x = zone_xyzi_[i * 4 + 0]; p.y = zone_xyzi_[i * 4 + 1]; p.z = zone_xyzi_[i * 4 + 2]; p.intensity = zone_xyzi_[i * 4 + 3];
+    }
+    finish(res, in, true);
+    out = res;
     return true;
   }
 
@@ -325,6 +354,14 @@ inline void getCloudPartsZSplit(Context& ctx, const Cloud::Ptr& cloud_ROI_ptr, c
     ground_part_ptrs.push_back(Cloud::Ptr(new Cloud(out[2 * k])));
     no_ground_part_ptrs.push_back(Cloud::Ptr(new Cloud(out[2 * k + 1])));
   }
+}
+
+// void outlierRemoval(Cloud::Ptr cloud_ptr) -- :184-192: pcl::RadiusOutlierRemoval, radius / min_neighbor of Parameter.h:23-24,
+// filtering the cloud in place.
+inline void outlierRemoval(Context& ctx, const Cloud::Ptr& cloud_ptr) {
+  Cloud tmp;
+  ctx.radius_outlier(*cloud_ptr, tmp, static_cast<double>(ctx.params().radius), static_cast<int>(ctx.params().min_neighbor));
+  *cloud_ptr = tmp;
 }
 
 // void voxelgrid(const Cloud::Ptr cloud_ptr, Cloud::Ptr voxel_cloud_ptr) -- :168-177

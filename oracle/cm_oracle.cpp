@@ -11,6 +11,7 @@
 #include "cm_oracle.h"
 
 #include <algorithm>
+#include <array>
 #include <cfloat>
 #include <cmath>
 #include <cstring>
@@ -452,6 +453,67 @@ void cmo_tf_to_matrix(const double* q, const double* t, float* m) {
   m[0] = 1.0f - (tyy + tzz); m[1] = txy - twz;          m[2] = txz + twy;           m[3] = static_cast<float>(t[0]);
   m[4] = txy + twz;          m[5] = 1.0f - (txx + tzz); m[6] = tyz - twx;           m[7] = static_cast<float>(t[1]);
   m[8] = txz - twy;          m[9] = tyz + twx;          m[10] = 1.0f - (txx + tyy); m[11] = static_cast<float>(t[2]);
+}
+
+/* pcl::RadiusOutlierRemoval<PointXYZI>::applyFilterIndices of PCL 1.8.1 (filters/impl/radius_outlier_removal.hpp), as
+ * configured by the reference's outlierRemoval() (pc_preprocessing_main.cpp:184-192: setRadiusSearch(radius),
+ * setMinNeighborsInRadius(min_neighbor), keep_organized false; Parameter.h:23-24 radius 0.15, min_neighbor 1):
+ *   k = searcher_->radiusSearch(point, search_radius_, ...)   -- k counts the query point itself
+ *   outlier  <=>  (!negative && k <= min_pts) || (negative && k > min_pts)
+ * The search is pcl::search::KdTree -> pcl::KdTreeFLANN (FLANN 1.8/1.9, L2_Simple<float>): a point is inside the radius
+ * iff its squared distance, accumulated in float as ((0 + dx*dx) + dy*dy) + dz*dz with dx = query - data, is strictly
+ * smaller than (float)(radius * radius) (radius is a double in PCL; RadiusResultSet::addPoint tests dist < radius).
+ * The kd-tree only prunes; it does not change which points are counted, so an exhaustive count over a cell grid whose
+ * cells are two radii wide gives the same k. Non-finite points are never kept (PCL requires a dense cloud here; the
+ * reference applies the filter to PassThrough/ExtractIndices output, which is dense).
+ * Writes the indices of the kept points in input order; returns how many. */
+int64_t cmo_radius_outlier(const float* xyzi, int64_t n, double radius, int32_t min_pts, int32_t negative,
+                           int32_t* out_indices) {
+  const float r2 = static_cast<float>(radius * radius);
+  const double cell = radius > 0.0 ? 2.0 * radius : 1.0;
+  /* grid over the finite points (double arithmetic: only a pruning structure, with a full cell of slack) */
+  std::vector<int64_t> order;
+  std::vector<std::array<int64_t, 3>> cell_of(static_cast<size_t>(n));
+  std::vector<char> fin(static_cast<size_t>(n), 0);
+  for (int64_t i = 0; i < n; ++i) {
+    const float* p = xyzi + i * 4;
+    if (std::isfinite(p[0]) && std::isfinite(p[1]) && std::isfinite(p[2])) {
+      fin[i] = 1;
+      for (int a = 0; a < 3; ++a) cell_of[i][a] = static_cast<int64_t>(std::floor(static_cast<double>(p[a]) / cell));
+      order.push_back(i);
+    }
+  }
+  std::sort(order.begin(), order.end(), [&](int64_t a, int64_t b) {
+    if (cell_of[a] != cell_of[b]) return cell_of[a] < cell_of[b];
+    return a < b;
+  });
+  auto find_cell = [&](const std::array<int64_t, 3>& c) {
+    return std::lower_bound(order.begin(), order.end(), c,
+                            [&](int64_t idx, const std::array<int64_t, 3>& key) { return cell_of[idx] < key; });
+  };
+  int64_t kept = 0;
+  for (int64_t i = 0; i < n; ++i) {
+    if (!fin[i]) continue;
+    const float* q = xyzi + i * 4;
+    int64_t k = 0;
+    for (int64_t dz = -1; dz <= 1; ++dz)
+      for (int64_t dy = -1; dy <= 1; ++dy)
+        for (int64_t dx = -1; dx <= 1; ++dx) {
+          const std::array<int64_t, 3> c = {cell_of[i][0] + dx, cell_of[i][1] + dy, cell_of[i][2] + dz};
+          for (auto it = find_cell(c); it != order.end() && cell_of[*it] == c; ++it) {
+            const float* d = xyzi + (*it) * 4;
+            float acc = 0.0f;
+            for (int a = 0; a < 3; ++a) {
+              const float diff = q[a] - d[a];
+              acc += diff * diff;
+            }
+            if (acc < r2) ++k;
+          }
+        }
+    const bool outlier = (!negative && k <= min_pts) || (negative && k > min_pts);
+    if (!outlier) out_indices[kept++] = static_cast<int32_t>(i);
+  }
+  return kept;
 }
 
 const char* cmo_version(void) { return "cm_oracle 1 (PCL 1.8.1 restatement; parity unpinned)"; }

@@ -94,6 +94,12 @@ int64_t cmo_merge_frame(const cmo_cloud_t* clouds, int32_t n_clouds, const cmo_p
                         float* out_xyzi, double* out_xyzi_f64, uint32_t* out_count, int64_t* out_idx,
                         int64_t* point_idx, int32_t* grid, int32_t* flags);
 
+/* pcl::RadiusOutlierRemoval<PointXYZI> (pc_preprocessing_main.cpp:184-192, called from removeGround :119): keeps a
+ * point iff more than min_pts points (itself included) lie strictly inside `radius` (float squared distance, FLANN
+ * L2_Simple order); negative inverts. Writes the kept indices in input order, returns how many. */
+int64_t cmo_radius_outlier(const float* xyzi, int64_t n, double radius, int32_t min_pts, int32_t negative,
+                           int32_t* out_indices);
+
 /* Eigen 3.3.4 Quaternionf::toRotationMatrix + Translation, as pcl_ros builds the Affine3f from a tf::Transform
  * (double quaternion xyzw + origin narrowed to float). Writes 12 floats row-major. Host glue, kept here so the tests can
  * pin it too. */

@@ -39,6 +39,7 @@ def lib() -> C.CDLL:
         L = C.CDLL(build())
         L.cmo_version.restype = C.c_char_p
         L.cmo_passthrough.restype = C.c_int64
+        L.cmo_radius_outlier.restype = C.c_int64
         L.cmo_voxelgrid.restype = C.c_int64
         L.cmo_merge_frame.restype = C.c_int64
         _LIB = L
@@ -68,6 +69,14 @@ def passthrough(xyzi: np.ndarray, axis: int, lo: float, hi: float, negative: boo
     xyzi = np.ascontiguousarray(xyzi, np.float32)
     idx = np.empty(len(xyzi), np.int32)
     k = lib().cmo_passthrough(_p(xyzi), C.c_int64(len(xyzi)), axis, C.c_float(lo), C.c_float(hi), int(negative), _p(idx))
+    return idx[:k].copy()
+
+
+def radius_outlier(xyzi: np.ndarray, radius: float, min_pts: int, negative: bool = False) -> np.ndarray:
+    """pcl::RadiusOutlierRemoval as configured by outlierRemoval() (pc_preprocessing_main.cpp:184-192): indices kept."""
+    xyzi = np.ascontiguousarray(xyzi, np.float32).reshape(-1, 4)
+    idx = np.empty(max(len(xyzi), 1), np.int32)
+    k = lib().cmo_radius_outlier(_p(xyzi), C.c_int64(len(xyzi)), C.c_double(radius), int(min_pts), int(negative), _p(idx))
     return idx[:k].copy()
 
 

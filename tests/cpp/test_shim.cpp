@@ -162,6 +162,18 @@ int main() {
       CHECK(total > roi_ptr->points.size() / 2 && total <= roi_ptr->points.size() + 16, "zones cover most of the ROI cloud (%zu of %zu)",
             total, roi_ptr->points.size());
     }
+    // outlierRemoval(cloud_ptr) on a copy of the ROI cloud (in the reference it runs on the RANSAC outliers, :119)
+    {
+      Cloud::Ptr filtered(new Cloud(*roi_ptr));
+      outlierRemoval(ctx, filtered);
+      const int64_t n_roi = static_cast<int64_t>(roi_o.size() / 4);
+      std::vector<int32_t> keep(static_cast<size_t>(n_roi) + 1);
+      const int64_t k = cmo_radius_outlier(roi_o.data(), n_roi, static_cast<double>(prm.radius), static_cast<int32_t>(prm.min_neighbor), 0, keep.data());
+      std::vector<float> want(static_cast<size_t>(k) * 4);
+      for (int64_t i = 0; i < k; ++i) std::memcpy(&want[i * 4], &roi_o[static_cast<size_t>(keep[i]) * 4], 16);
+      expect_cloud(*filtered, want, static_cast<size_t>(k), "outlierRemoval");
+      CHECK(k > 100 && k < n_roi, "outlierRemoval removes some but not all points (%lld of %lld kept)", (long long)k, (long long)n_roi);
+    }
     // fusePointclouds: *no_ground_ptr = first; *no_ground_ptr += rest
     if (s == 0) *fused = *roi_ptr; else *fused += *roi_ptr;
     fused_oracle.insert(fused_oracle.end(), roi_o.begin(), roi_o.end());

@@ -1,0 +1,91 @@
+"""GPU parity tests (-m gpu) of the radius outlier removal (outlierRemoval() of the reference,
+pc_preprocessing_main.cpp:184-192: pcl::RadiusOutlierRemoval, radius 0.15 m, min_neighbor 1) through the C ABI against
+the oracle's restatement of PCL 1.8.1 + FLANN (count of points strictly inside the radius, the point itself included,
+float squared distances; keep iff count > min_pts). Bar: bit-exact survivor set, order and coordinates."""
+import numpy as np
+import pytest
+
+from cloud_merger_b200 import ROI_PASSES, CloudMerger, CloudMergerError, _lib, synth
+
+from helpers import assert_bit_equal
+
+pytestmark = pytest.mark.gpu
+
+RADIUS = float(np.float32(0.15))  # `const float radius = 0.15;` widened to the double setRadiusSearch takes (Parameter.h:23)
+
+
+def _roi_cloud(oracle, seed, rings, az, sensor=0):
+    cur = oracle.transform(synth.lidar_cloud(seed, sensor, 0, rings, az), synth.extrinsic(sensor, 4)[:3].reshape(-1))
+    for (axis, lo, hi, neg) in ROI_PASSES:
+        cur = np.ascontiguousarray(cur[oracle.passthrough(cur, axis, lo, hi, bool(neg))])
+    return cur
+
+
+@pytest.mark.parametrize("rings,az,min_pts,negative", [(16, 256, 1, False), (64, 1024, 1, False), (64, 1024, 3, False),
+                                                       (32, 512, 2, True)])
+def test_radius_outlier_matches_oracle(gpu_ok, oracle, rings, az, min_pts, negative):
+    cloud = _roi_cloud(oracle, 4300, rings, az)
+    want = oracle.radius_outlier(cloud, RADIUS, min_pts, negative)
+    assert 0 < len(want) < len(cloud)
+    with CloudMerger(max_sensors=1, max_points_per_sensor=len(cloud), max_batch_points=len(cloud)) as cm:
+        gx, gi = cm.radius_outlier(cloud, RADIUS, min_pts, negative)
+        assert len(gi) == len(want) and (gi == want).all(), "survivor set / order differs"
+        assert_bit_equal(gx, cloud[want], "survivor coordinates")
+        buf = cm.upload(cloud)
+        cm.dev_radius_outlier(buf.ptr, len(cloud), RADIUS, min_pts, negative)
+        dx, di = cm.radius_outlier_out()
+        assert (di == want).all()
+        assert_bit_equal(dx, cloud[want], "device form coordinates")
+
+
+def test_radius_outlier_boundaries_and_invalid(gpu_ok, oracle):
+    """Distances right at the radius (strictly-inside rule, float arithmetic), pairs that straddle cell borders, duplicate
+    points, non-finite points (never kept, never counted), clouds of 0 / 1 / 2 points."""
+    f32 = np.float32
+    r = RADIUS
+    rows = []
+    rng = np.random.default_rng(21)
+    for k in range(400):  # pairs at distance r * (1 +- a few ulp) along random directions, anywhere in the ROI
+        c = np.array([rng.uniform(-15, 60), rng.uniform(-5, 5), rng.uniform(-0.5, 3.0)])
+        d = rng.normal(size=3); d /= np.linalg.norm(d)
+        s = r * (1.0 + (k % 9 - 4) * 2.0 ** -23)
+        rows.append(c); rows.append(c + d * s)
+    pts = np.array(rows, np.float64)
+    cloud = np.column_stack([pts, np.arange(len(pts))]).astype(np.float32)
+    extra = np.array([[1.0, 1.0, 1.0, 0.0], [1.0, 1.0, 1.0, 1.0],                 # duplicates: each other's neighbour
+                      [np.nan, 0.0, 0.0, 2.0], [0.0, np.inf, 0.0, 3.0],           # non-finite
+                      [40.0, 4.0, 2.0, 4.0]], np.float32)                         # isolated
+    cloud = np.concatenate([cloud, extra])
+    for min_pts, neg in ((1, False), (1, True), (0, False)):
+        want = oracle.radius_outlier(cloud, r, min_pts, neg)
+        with CloudMerger(max_sensors=1, max_points_per_sensor=len(cloud), max_batch_points=len(cloud)) as cm:
+            gx, gi = cm.radius_outlier(cloud, r, min_pts, neg)
+        assert len(gi) == len(want) and (gi == want).all(), "min_pts %d negative %s" % (min_pts, neg)
+        assert_bit_equal(gx, cloud[want], "coordinates")
+    # both sides of the strict rule must be present in the data, otherwise the test proves nothing
+    k1 = set(oracle.radius_outlier(cloud[:800], r, 1, False).tolist())
+    assert 0 < len(k1) < 800
+    with CloudMerger(max_sensors=1, max_points_per_sensor=16, max_batch_points=16) as cm:
+        for n in (0, 1, 2):
+            c = np.array([[0, 0, 0, 1], [0.1, 0, 0, 2]], np.float32)[:n]
+            gx, gi = cm.radius_outlier(c, r, 1)
+            assert gi.tolist() == oracle.radius_outlier(c, r, 1).tolist()
+        with pytest.raises(CloudMergerError):
+            cm.radius_outlier(np.zeros((4, 4), np.float32), 0.0, 1)
+
+
+def test_radius_outlier_properties_full_size(gpu_ok):
+    """Size-independent checks on 1 Mi points: the result is a subsequence of the input (order, bit-exact coordinates);
+    the filter is monotone in min_pts; with a negative filter the two outputs partition the finite points."""
+    n = 1 << 20
+    rng = np.random.default_rng(33)
+    cloud = np.column_stack([rng.uniform(-15, 60, n), rng.uniform(-5, 5, n), rng.uniform(-0.5, 3, n),
+                             rng.uniform(0, 255, n)]).astype(np.float32)
+    with CloudMerger(max_sensors=1, max_points_per_sensor=n, max_batch_points=n) as cm:
+        x1, i1 = cm.radius_outlier(cloud, RADIUS, 1)
+        x3, i3 = cm.radius_outlier(cloud, RADIUS, 3)
+        xn, in_ = cm.radius_outlier(cloud, RADIUS, 1, negative=True)
+    assert (np.diff(i1.astype(np.int64)) > 0).all() and (np.diff(in_.astype(np.int64)) > 0).all()
+    assert_bit_equal(x1, cloud[i1], "kept coordinates")
+    assert set(i3.tolist()) <= set(i1.tolist()) and 0 < len(i3) < len(i1) < n
+    assert len(i1) + len(in_) == n and len(np.intersect1d(i1, in_)) == 0

@@ -240,3 +240,28 @@ def test_zone_split_oracle_against_numpy_masks(oracle):
     in_mid = np.union1d(got[4][1], got[5][1])
     zwin = lambda i, zg: (cloud[i, 2] >= -zg) & (cloud[i, 2] <= zg) | (cloud[i, 2] >= np.float32(np.float64(np.float32(zg)) + 0.01)) & (cloud[i, 2] <= 3.0)
     assert set(on_edge[zwin(on_edge, np.float32(2.0))]) <= set(in_mid2) and set(on_edge[zwin(on_edge, np.float32(1.5))]) <= set(in_mid)
+
+
+def test_radius_outlier_oracle_against_brute_force(oracle):
+    """The grid-accelerated C++ restatement of pcl::RadiusOutlierRemoval (PCL 1.8.1 + FLANN L2_Simple) against an O(n^2)
+    numpy count in the same float32 operation order: strictly inside the radius, the point itself counted, keep iff
+    count > min_pts; negative inverts; non-finite points are neither kept nor counted."""
+    rng = np.random.default_rng(9)
+    n = 2500
+    x = np.column_stack([rng.uniform(0, 5, n), rng.uniform(0, 3, n), rng.uniform(0, 1, n), rng.uniform(0, 1, n)]).astype(np.float32)
+    x[::211, 1] = np.nan
+    r = float(np.float32(0.15))
+    r2 = np.float32(r * r)
+    fin = np.isfinite(x[:, :3]).all(axis=1)
+    d = x[:, None, :3] - x[None, :, :3]
+    with np.errstate(invalid="ignore"):
+        acc = (d[..., 0] * d[..., 0]).astype(np.float32)
+        acc = (acc + (d[..., 1] * d[..., 1]).astype(np.float32)).astype(np.float32)
+        acc = (acc + (d[..., 2] * d[..., 2]).astype(np.float32)).astype(np.float32)
+        inside = (acc < r2) & fin[None, :] & fin[:, None]
+    k = inside.sum(axis=1)
+    for min_pts in (0, 1, 2, 4):
+        for neg in (False, True):
+            want = np.nonzero(fin & ((k <= min_pts) if neg else (k > min_pts)))[0]
+            got = oracle.radius_outlier(x, r, min_pts, neg)
+            assert len(got) == len(want) and (got == want).all(), (min_pts, neg)
