@@ -150,6 +150,7 @@ struct cm_handle_s {
     size_t cap_points = 0, cap_out = 0;
     unsigned short* mask = nullptr;
     uint32_t *tile_count = nullptr, *tile_offset = nullptr, *zone_begin = nullptr, *overflow = nullptr;
+    uint32_t* zone_total = nullptr;  // [CM_MAX_ZONES] + the scan ticket behind it
     float4* out_xyzi = nullptr;
     uint32_t* out_src = nullptr;
     float4* in_stage = nullptr;  // host-buffer form: the uploaded cloud
@@ -904,6 +905,7 @@ int cm_destroy(cm_handle_t h) {
   {
     auto& z = h->zw;
     cudaFree(z.mask); cudaFree(z.tile_count); cudaFree(z.tile_offset); cudaFree(z.zone_begin); cudaFree(z.overflow);
+    cudaFree(z.zone_total);
     cudaFree(z.out_xyzi); cudaFree(z.out_src); cudaFree(z.in_stage);
     if (z.report) cudaFreeHost(z.report);
   }
@@ -1166,6 +1168,7 @@ int cm_set_zones(cm_handle_t h, int n_zones, const cm_zone_t* zones) {
 namespace {
 void zone_ws_free(cm_handle_s::ZoneWs& z) {
   cudaFree(z.mask); cudaFree(z.tile_count); cudaFree(z.tile_offset); cudaFree(z.zone_begin); cudaFree(z.overflow);
+  cudaFree(z.zone_total);
   cudaFree(z.out_xyzi); cudaFree(z.out_src); cudaFree(z.in_stage);
   if (z.report) cudaFreeHost(z.report);
   z = cm_handle_s::ZoneWs();
@@ -1184,6 +1187,8 @@ int zone_ws_ensure(cm_handle_t h, size_t points) {
   CM_CUDA(h, dev_alloc(&z.tile_offset, tiles * CM_MAX_ZONES));
   CM_CUDA(h, dev_alloc(&z.zone_begin, (size_t)CM_MAX_ZONES + 2));
   CM_CUDA(h, dev_alloc(&z.overflow, (size_t)1));
+  CM_CUDA(h, dev_alloc(&z.zone_total, (size_t)CM_MAX_ZONES + 2));
+  CM_CUDA(h, cudaMemset(z.zone_total, 0, sizeof(uint32_t) * (CM_MAX_ZONES + 2)));
   z.cap_out = 2 * want;
   CM_CUDA(h, dev_alloc(&z.out_xyzi, z.cap_out));
   CM_CUDA(h, dev_alloc(&z.out_src, z.cap_out));
@@ -1209,6 +1214,7 @@ int zone_run(cm_handle_t h, const float4* pts, int64_t n_points, cudaStream_t st
   }
   z.n_zones_run = zp.zones.n_zones;
   zp.mask = z.mask; zp.tile_count = z.tile_count; zp.tile_offset = z.tile_offset; zp.zone_begin = z.zone_begin;
+  zp.zone_total = z.zone_total; zp.scan_ticket = z.zone_total + CM_MAX_ZONES;
   zp.overflow = z.overflow; zp.out_capacity = (uint32_t)std::min<size_t>(z.cap_out, 0xFFFFFFF0u);
   zp.out_xyzi = z.out_xyzi; zp.out_src = z.out_src;
   CM_CUDA(h, cudaMemsetAsync(z.overflow, 0, sizeof(uint32_t), st));

@@ -104,7 +104,9 @@ struct ZoneParams {
   unsigned short* mask;      // [n_points] zone membership of every point
   uint32_t mask_given;       // the masks were produced by another kernel (radius outlier removal): only count them
   uint32_t* tile_count;      // [n_zones][n_tiles]
-  uint32_t* tile_offset;     // [n_zones][n_tiles] where the tile's points of the zone start in the output
+  uint32_t* tile_offset;     // [n_zones][n_tiles] where the tile's points of the zone start, relative to the zone's start
+  uint32_t* zone_total;      // [n_zones] points per zone
+  uint32_t* scan_ticket;     // counts the zone CTAs of k_zone_scan that have finished (self-resetting)
   uint32_t* zone_begin;      // [n_zones + 1] zone z occupies [zone_begin[z], zone_begin[z+1]) of the output
   uint32_t* overflow;        // set to the needed size when the zones together exceed out_capacity
   uint32_t out_capacity;

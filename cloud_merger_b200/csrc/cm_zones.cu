@@ -11,8 +11,8 @@
 // end points: a point exactly on a boundary is copied into both neighbours) and need not cover the cloud (the z windows
 // leave the gap (z_max_g, z_max_g + 0.01)). Inside every zone the points keep their input order, like PassThrough.
 //
-// Three launches: k_zone_count (membership mask per point + per-tile counts per zone), k_zone_scan (one CTA: zone starts
-// and per-tile offsets), k_zone_scatter (ranks from warp ballots -> points and source indices to their final place).
+// Three launches: k_zone_count (membership mask per point + per-tile counts per zone), k_zone_scan (one CTA per zone:
+// per-tile offsets; the last CTA to finish lays the zones out one after the other), k_zone_scatter (ranks from warp ballots -> points and source indices to their final place).
 // Roofline: HBM. Algorithmic bytes = n * (16 read + 2 mask written + 16 + 2 read again) + sum(zone sizes) * (16 + 4).
 #include "cm_kernels.h"
 
@@ -34,21 +34,9 @@ __device__ __forceinline__ bool zone_pass_keeps(const PassDev& ps, const float4&
 
 // membership of one point: bit z set iff every stage of zone z keeps it (PCL 1.8.1 PassThrough::applyFilterIndices:
 // a point with a non-finite x, y or z passes no stage). A zone without stages is no filter at all: it keeps every point.
-// BOX: every zone is a box (ZoneSet.all_box): six compares per zone, non-finite coordinates fail them by themselves.
-template <bool BOX>
-__device__ __forceinline__ uint32_t zone_mask(const ZoneSet& zs, const float4& v) {
-  uint32_t m = 0;
-  if (BOX) {
-    for (int z = 0; z < zs.n_zones; ++z) {
-      const ZoneDev& zd = zs.zone[z];
-      bool keep = (v.x >= zd.lo[0]) & (v.x <= zd.hi[0]) & (v.y >= zd.lo[1]) & (v.y <= zd.hi[1]) & (v.z >= zd.lo[2]) &
-                  (v.z <= zd.hi[2]);
-      if (zd.use_i) keep = keep & (v.w >= zd.lo[3]) & (v.w <= zd.hi[3]);
-      m |= (keep ? 1u : 0u) << z;
-    }
-    return m;
-  }
+__device__ __forceinline__ uint32_t zone_mask_chain(const ZoneSet& zs, const float4& v) {
   const bool fin = finite_f32(v.x) && finite_f32(v.y) && finite_f32(v.z);
+  uint32_t m = 0;
   for (int z = 0; z < zs.n_zones; ++z) {
     const int np = zs.zone[z].n_pass;
     bool keep = fin || np == 0;
@@ -57,14 +45,40 @@ __device__ __forceinline__ uint32_t zone_mask(const ZoneSet& zs, const float4& v
   }
   return m;
 }
+// Every zone is a box (ZoneSet.all_box): lo / hi of x, y, z, intensity sit in shared memory as two float4 per zone
+// (+-FLT_MAX where a zone has no stage on an axis; the intensity test is skipped through no_i_mask for zones without an
+// intensity stage, so that a NaN intensity only matters where PCL would look at it): two 16-byte broadcast loads and
+// eight compares per zone.
+__device__ __forceinline__ uint32_t zone_mask_box(const float4* s_lo, const float4* s_hi, int n_zones, uint32_t no_i_mask,
+                                                  const float4& v) {
+  uint32_t m = 0;
+  for (int z = 0; z < n_zones; ++z) {
+    const float4 lo = s_lo[z], hi = s_hi[z];
+    const bool keep = (v.x >= lo.x) & (v.x <= hi.x) & (v.y >= lo.y) & (v.y <= hi.y) & (v.z >= lo.z) & (v.z <= hi.z);
+    const bool keep_i = (v.w >= lo.w) & (v.w <= hi.w);
+    m |= ((keep ? 1u : 0u) & ((keep_i ? 1u : 0u) | (no_i_mask >> z))) << z;
+  }
+  return m;
+}
 
 template <bool BOX, bool GIVEN>
 __global__ void __launch_bounds__(ZN_THREADS) k_zone_count(const ZoneParams p) {
   __shared__ uint32_t s_cnt[CM_MAX_ZONES];
+  __shared__ __align__(16) float4 s_lo[CM_MAX_ZONES], s_hi[CM_MAX_ZONES];
   const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
   const uint32_t n = p.n_points;
   const uint32_t tile = blockIdx.x;
-  if (tid < CM_MAX_ZONES) s_cnt[tid] = 0;
+  if (tid < CM_MAX_ZONES) {
+    s_cnt[tid] = 0;
+    if (BOX && (int)tid < p.zones.n_zones) {
+      const ZoneDev& zd = p.zones.zone[tid];
+      s_lo[tid] = make_float4(zd.lo[0], zd.lo[1], zd.lo[2], zd.lo[3]);
+      s_hi[tid] = make_float4(zd.hi[0], zd.hi[1], zd.hi[2], zd.hi[3]);
+    }
+  }
+  uint32_t no_i_mask = 0;  // bit z: zone z has no intensity stage
+  if (BOX)
+    for (int z = 0; z < p.zones.n_zones; ++z) no_i_mask |= (p.zones.zone[z].use_i ? 0u : 1u) << z;
   __syncthreads();
   const uint32_t base = tile * ZN_TILE + warp * (32 * ZN_IPT) + lane;
   float4 v[ZN_IPT];
@@ -73,7 +87,6 @@ __global__ void __launch_bounds__(ZN_THREADS) k_zone_count(const ZoneParams p) {
     const uint32_t g = base + 32 * i;
     v[i] = (!GIVEN && g < n) ? ldg_stream_f4(p.pts + g) : make_float4(0.f, 0.f, 0.f, 0.f);
   }
-  uint32_t cnt_z = 0;  // lane z accumulates the warp's count for zone z
 #pragma unroll
   for (int i = 0; i < ZN_IPT; ++i) {
     const uint32_t g = base + 32 * i;
@@ -82,38 +95,43 @@ __global__ void __launch_bounds__(ZN_THREADS) k_zone_count(const ZoneParams p) {
       if (GIVEN) {
         m = p.mask[g];
       } else {
-        m = zone_mask<BOX>(p.zones, v[i]);
+        m = BOX ? zone_mask_box(s_lo, s_hi, p.zones.n_zones, no_i_mask, v[i]) : zone_mask_chain(p.zones, v[i]);
         p.mask[g] = (unsigned short)m;
       }
     }
-    for (int z = 0; z < p.zones.n_zones; ++z) {
-      const uint32_t b = __ballot_sync(0xFFFFFFFFu, (m >> z) & 1u);
-      if ((int)lane == z) cnt_z += (uint32_t)__popc(b);
+    // one shared-memory increment per zone the point belongs to (usually one); lanes of a warp that hit the same zone
+    // are aggregated by the hardware (ATOMS.POPC.INC)
+    while (m) {
+      const uint32_t z = (uint32_t)__ffs(m) - 1u;
+      m &= m - 1u;
+      atomicAdd(&s_cnt[z], 1u);
     }
   }
-  if ((int)lane < p.zones.n_zones && cnt_z) atomicAdd(&s_cnt[lane], cnt_z);
   __syncthreads();
   if ((int)tid < p.zones.n_zones) p.tile_count[(size_t)tid * p.n_tiles + tile] = s_cnt[tid];  // zone-major
 }
 
-// one CTA: zone z starts where zone z-1 ends; inside a zone the tiles follow each other
+// One CTA per zone: exclusive scan of the zone's tile counts (offsets relative to the zone's start) and the zone total;
+// the CTA that finishes last turns the totals into zone starts (zone z starts where zone z-1 ends).
 __global__ void __launch_bounds__(1024) k_zone_scan(const ZoneParams p) {
   __shared__ uint32_t s_scr[33];
-  __shared__ uint32_t s_run;
+  __shared__ uint32_t s_run, s_last;
   const uint32_t tid = threadIdx.x, lane = tid & 31u, w = tid >> 5;
-  const uint32_t total_items = p.n_tiles * (uint32_t)p.zones.n_zones;  // zone-major: index = z * n_tiles + tile
+  const uint32_t z = blockIdx.x;
+  const uint32_t nt = p.n_tiles;
+  const uint32_t* cnt = p.tile_count + (size_t)z * nt;
+  uint32_t* off = p.tile_offset + (size_t)z * nt;
   if (tid == 0) s_run = 0;
   __syncthreads();
-  for (uint32_t i0 = 0; i0 < total_items; i0 += 1024u * 8u) {
+  for (uint32_t i0 = 0; i0 < nt; i0 += 1024u * 8u) {
     uint32_t c[8];
     uint32_t sum = 0;
     const uint32_t b = i0 + tid * 8u;
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
-      c[k] = (b + k < total_items) ? p.tile_count[b + k] : 0u;
+      c[k] = (b + k < nt) ? cnt[b + k] : 0u;
       sum += c[k];
     }
-    // block exclusive scan of `sum` over 1024 threads
     const uint32_t incl = warp_incl_scan_u32(sum);
     if (lane == 31) s_scr[w] = incl;
     __syncthreads();
@@ -127,10 +145,7 @@ __global__ void __launch_bounds__(1024) k_zone_scan(const ZoneParams p) {
     uint32_t run = s_run + s_scr[w] + incl - sum;
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
-      if (b + k < total_items) {
-        p.tile_offset[b + k] = run;
-        if ((b + k) % p.n_tiles == 0u) p.zone_begin[(b + k) / p.n_tiles] = run;
-      }
+      if (b + k < nt) off[b + k] = run;
       run += c[k];
     }
     __syncthreads();
@@ -138,11 +153,21 @@ __global__ void __launch_bounds__(1024) k_zone_scan(const ZoneParams p) {
     __syncthreads();
   }
   if (tid == 0) {
-    const uint32_t total = s_run;
-    p.zone_begin[p.zones.n_zones] = total;
-    if (p.n_tiles == 0)
-      for (int z = 0; z < p.zones.n_zones; ++z) p.zone_begin[z] = 0;
-    if (total > p.out_capacity) *p.overflow = total;  // the scatter kernel then writes nothing
+    p.zone_total[z] = s_run;
+    __threadfence();
+    s_last = atomicAdd(p.scan_ticket, 1u) == gridDim.x - 1u ? 1u : 0u;
+  }
+  __syncthreads();
+  if (s_last && tid == 0) {
+    __threadfence();
+    uint32_t run = 0;
+    for (uint32_t k = 0; k < gridDim.x; ++k) {
+      p.zone_begin[k] = run;
+      run += reinterpret_cast<volatile uint32_t*>(p.zone_total)[k];
+    }
+    p.zone_begin[gridDim.x] = run;
+    if (run > p.out_capacity) *p.overflow = run;  // the scatter kernel then writes nothing
+    *p.scan_ticket = 0;                           // ready for the next split
   }
 }
 
@@ -162,19 +187,25 @@ __global__ void __launch_bounds__(ZN_THREADS) k_zone_scatter(const ZoneParams p)
     m[i] = g < n ? (uint32_t)p.mask[g] : 0u;
     v[i] = (g < n && m[i]) ? ldg_stream_f4(p.pts + g) : make_float4(0.f, 0.f, 0.f, 0.f);
   }
-  // the warp's count per zone (lane z holds zone z), for the prefix over the warps of the tile
-  uint32_t cnt_z = 0;
+  // zones present in this warp's rows (lidar clouds are spatially coherent: usually one or two of them), and the warp's
+  // count per zone (lane z holds zone z) for the prefix over the warps of the tile
+  uint32_t present = 0;
 #pragma unroll
-  for (int i = 0; i < ZN_IPT; ++i)
-    for (int z = 0; z < nz; ++z) {
-      const uint32_t b = __ballot_sync(0xFFFFFFFFu, (m[i] >> z) & 1u);
-      if ((int)lane == z) cnt_z += (uint32_t)__popc(b);
-    }
+  for (int i = 0; i < ZN_IPT; ++i) present |= __reduce_or_sync(0xFFFFFFFFu, m[i]);
+  uint32_t cnt_z = 0;
+  for (uint32_t zs = present; zs; zs &= zs - 1u) {
+    const uint32_t z = (uint32_t)__ffs(zs) - 1u;
+    uint32_t c = 0;
+#pragma unroll
+    for (int i = 0; i < ZN_IPT; ++i) c += (uint32_t)__popc(__ballot_sync(0xFFFFFFFFu, (m[i] >> z) & 1u));
+    if (lane == z) cnt_z = c;
+  }
   if ((int)lane < CM_MAX_ZONES) s_wcnt[warp][lane] = cnt_z;
   __syncthreads();
   const uint32_t lt = lanemask_lt();
-  for (int z = 0; z < nz; ++z) {
-    uint32_t pos = p.tile_offset[(size_t)z * p.n_tiles + tile];
+  for (uint32_t zs = present; zs; zs &= zs - 1u) {
+    const uint32_t z = (uint32_t)__ffs(zs) - 1u;
+    uint32_t pos = p.zone_begin[z] + p.tile_offset[(size_t)z * p.n_tiles + tile];
     for (uint32_t w2 = 0; w2 < warp; ++w2) pos += s_wcnt[w2][z];
 #pragma unroll
     for (int i = 0; i < ZN_IPT; ++i) {
@@ -210,7 +241,7 @@ cudaError_t launch_zone_split(const ZoneParams& p, cudaStream_t stream) {
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
   }
-  k_zone_scan<<<1, 1024, 0, stream>>>(p);
+  k_zone_scan<<<p.zones.n_zones, 1024, 0, stream>>>(p);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return e;
   if (p.n_tiles) {
