@@ -291,12 +291,34 @@ def run_reference(args):
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line))
+    emit(line)
     return 0
+
+
+_REAL_STDOUT = None
+
+
+def guard_stdout():
+    """The contract is ONE JSON line on stdout. Libraries print there too (NCCL's version banner at NCCL_DEBUG=WARN, for
+    one), so file descriptor 1 is pointed at stderr for the whole run and the line is written to the saved descriptor."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line: dict):
+    data = (json.dumps(line) + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(data.decode()); sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, data)
 
 
 def main():
     args = parse_args()
+    guard_stdout()
     if args.impl == "reference":
         return run_reference(args)
 
@@ -312,9 +334,6 @@ def main():
         raise SystemExit("bench.py: no CUDA device (the product path has no CPU fallback)")
     torch.cuda.set_device(local_rank)
     if world > 1:
-        # one JSON line on stdout: NCCL's banner / debug lines (NCCL_DEBUG may be preset on the box) go to stderr
-        os.environ.setdefault("NCCL_DEBUG", "WARN")
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
     def barrier():
@@ -521,7 +540,7 @@ def main():
         }
         if latency:
             line["latency"] = latency
-        print(json.dumps(line))
+        emit(line)
     cm.close()
     if world > 1:
         dist.destroy_process_group()

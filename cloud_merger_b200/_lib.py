@@ -112,6 +112,12 @@ SYMBOLS = {
     "cm_dev_radius_outlier": (C.c_int, [_H, C.c_void_p, C.c_int64, C.c_double, C.c_int, C.c_int, C.c_void_p]),
     "cm_radius_outlier": (C.c_int, [_H, C.c_void_p, C.c_int64, C.c_double, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
                                     C.c_int64, C.POINTER(C.c_int64)]),
+    "cm_dev_bounds": (C.c_int, [_H, C.c_void_p, C.c_int64, C.POINTER(C.c_float), C.POINTER(C.c_float), C.POINTER(C.c_int64),
+                                C.c_void_p]),
+    "cm_dev_key_histogram": (C.c_int, [_H, C.c_void_p, C.c_int64, C.POINTER(C.c_float), C.POINTER(C.c_float), C.c_int,
+                                       C.c_void_p, C.POINTER(C.c_uint64), C.c_void_p]),
+    "cm_dev_route_by_key": (C.c_int, [_H, C.c_void_p, C.c_int64, C.POINTER(C.c_float), C.POINTER(C.c_float),
+                                      C.POINTER(C.c_uint64), C.c_int, C.c_int, C.c_void_p]),
     "cm_sync": (C.c_int, [_H]),
     "cm_get_stats": (C.c_int, [_H, C.POINTER(CmStats)]),
     "cm_get_device_out": (C.c_int, [_H, C.POINTER(CmDeviceOut)]),
@@ -124,6 +130,7 @@ SYMBOLS = {
     "cm_dev_free": (C.c_int, [_H, C.c_void_p]),
     "cm_memcpy_h2d": (C.c_int, [_H, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
     "cm_memcpy_d2h": (C.c_int, [_H, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
+    "cm_memcpy_d2d": (C.c_int, [_H, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
 }
 
 _LIB = None

@@ -225,6 +225,42 @@ class CloudMerger:
                                                 oi.ctypes.data_as(C.c_void_p), C.c_int64(n), C.byref(k)))
         return ox[:k.value].copy(), oi[:k.value].copy()
 
+    # -- giant-cloud mode: device-side pieces of the voxel-key range partition (BASELINE config 4) -------------------------
+    def dev_bounds(self, xyzi_ptr: int, n_points: int, stream: int = 0):
+        """pcl::getMinMax3D of n packed points on the device -> (min[3], max[3] float32, number of finite points)."""
+        mn, mx = (C.c_float * 3)(), (C.c_float * 3)()
+        nf = C.c_int64()
+        self._check(self._lib.cm_dev_bounds(self._h, C.c_void_p(xyzi_ptr or None), C.c_int64(n_points), mn, mx,
+                                            C.byref(nf), C.c_void_p(stream or None)))
+        return np.array(mn, np.float32), np.array(mx, np.float32), nf.value
+
+    def dev_key_histogram(self, xyzi_ptr: int, n_points: int, min_p, max_p, bins: int, hist_ptr: int, stream: int = 0) -> int:
+        """Histogram of the PCL voxel index on the grid of the box [min_p, max_p] into `bins` uint64 device counters;
+        returns the key width of a bin."""
+        mn = (C.c_float * 3)(*[float(v) for v in min_p]); mx = (C.c_float * 3)(*[float(v) for v in max_p])
+        width = C.c_uint64()
+        self._check(self._lib.cm_dev_key_histogram(self._h, C.c_void_p(xyzi_ptr or None), C.c_int64(n_points), mn, mx,
+                                                   int(bins), C.c_void_p(hist_ptr), C.byref(width), C.c_void_p(stream or None)))
+        return int(width.value)
+
+    def dev_route_by_key(self, xyzi_ptr: int, n_points: int, min_p, max_p, splitters, invalid_part: int, stream: int = 0):
+        """Groups the points by key range (len(splitters) + 1 parts); fetch the device arrays with zone_out_raw()."""
+        mn = (C.c_float * 3)(*[float(v) for v in min_p]); mx = (C.c_float * 3)(*[float(v) for v in max_p])
+        sp = [int(v) for v in splitters]
+        arr = (C.c_uint64 * max(len(sp), 1))(*sp)
+        self._check(self._lib.cm_dev_route_by_key(self._h, C.c_void_p(xyzi_ptr or None), C.c_int64(n_points), mn, mx, arr,
+                                                  len(sp) + 1, int(invalid_part), C.c_void_p(stream or None)))
+
+    def zone_out_raw(self):
+        """(device pointer of the grouped xyzi, device pointer of the source indices, begin offsets) of the last split."""
+        zo = CmZoneOut()
+        self._check(self._lib.cm_get_zone_out(self._h, C.byref(zo)))
+        return zo.xyzi, zo.src, [int(zo.begin[k]) for k in range(zo.n_zones + 1)]
+
+    def memcpy_d2d(self, dst_ptr: int, src_ptr: int, nbytes: int, stream: int = 0):
+        self._check(self._lib.cm_memcpy_d2d(self._h, C.c_void_p(dst_ptr), C.c_void_p(src_ptr), C.c_size_t(nbytes),
+                                            C.c_void_p(stream or None)))
+
     def set_voxel(self, leaf, min_points: int = 2, downsample_all: bool = True):
         leaf = np.broadcast_to(np.asarray(leaf, np.float32), (3,)).copy()
         self._check(self._lib.cm_set_voxel(self._h, leaf.ctypes.data_as(C.POINTER(C.c_float)), int(min_points),

@@ -1197,7 +1197,8 @@ int zone_ws_ensure(cm_handle_t h, size_t points) {
   return CM_OK;
 }
 
-int zone_run(cm_handle_t h, const float4* pts, int64_t n_points, cudaStream_t st, bool mask_given = false) {
+int zone_run(cm_handle_t h, const float4* pts, int64_t n_points, cudaStream_t st, bool mask_given = false,
+             int given_zones = 1) {
   cm_handle_s::ZoneWs& z = h->zw;
   if (!mask_given && h->zones.n_zones <= 0) return fail(h, CM_E_INVALID, "no zones configured (cm_set_zones)");
   if (n_points < 0 || n_points > 0xFFFFFFF0ll) return fail(h, CM_E_INVALID, "bad n_points");
@@ -1210,7 +1211,7 @@ int zone_run(cm_handle_t h, const float4* pts, int64_t n_points, cudaStream_t st
   zp.mask_given = mask_given ? 1u : 0u;
   if (mask_given) {  // one output: the points whose flag is set
     zp.zones = ZoneSet{};
-    zp.zones.n_zones = 1;
+    zp.zones.n_zones = given_zones;
   }
   z.n_zones_run = zp.zones.n_zones;
   zp.mask = z.mask; zp.tile_count = z.tile_count; zp.tile_offset = z.tile_offset; zp.zone_begin = z.zone_begin;
@@ -1302,6 +1303,102 @@ int cm_zone_split(cm_handle_t h, const float* xyzi_host, int64_t n_points, float
   std::lock_guard<std::mutex> lk(h->mu);
   if (out_xyzi && total) CM_CUDA(h, cudaMemcpy(out_xyzi, zo.xyzi, (size_t)total * 16, cudaMemcpyDeviceToHost));
   if (out_src && total) CM_CUDA(h, cudaMemcpy(out_src, zo.src, (size_t)total * 4, cudaMemcpyDeviceToHost));
+  return CM_OK;
+}
+
+// ---- giant-cloud mode: bounding box, key histogram, routing by key range ------------------------------------------------
+namespace {
+// PCL's grid (VoxelGrid::applyFilter, float32) on a bounding box, with the handle's leaf
+int route_grid(cm_handle_t h, const float* min3, const float* max3, RouteGrid* g, unsigned long long* cells) {
+  long long div[3];
+  for (int k = 0; k < 3; ++k) {
+    g->inv[k] = h->inv_leaf[k];
+    const float fmn = std::floor(min3[k] * h->inv_leaf[k]), fmx = std::floor(max3[k] * h->inv_leaf[k]);
+    if (!(std::fabs(fmn) < 1073741824.f) || !(std::fabs(fmx) < 1073741824.f) || fmx < fmn)
+      return fail(h, CM_E_KEY_RANGE, "bounding box outside the key range");
+    g->min_b[k] = (long long)fmn;
+    div[k] = (long long)fmx - (long long)fmn + 1;
+    if (div[k] > (1ll << 21)) return fail(h, CM_E_KEY_RANGE, "more than 2^21 cells on an axis");
+  }
+  g->div0 = div[0];
+  g->div01 = div[0] * div[1];
+  if (cells) *cells = (unsigned long long)div[0] * (unsigned long long)div[1] * (unsigned long long)div[2];
+  return CM_OK;
+}
+}  // namespace
+
+int cm_dev_bounds(cm_handle_t h, const float* xyzi_dev, int64_t n_points, float* min3, float* max3, int64_t* n_finite,
+                  void* stream) {
+  if (!h || !min3 || !max3 || n_points < 0 || n_points > 0xFFFFFFF0ll) return CM_E_INVALID;
+  std::lock_guard<std::mutex> lk(h->mu);
+  CM_CUDA(h, cudaSetDevice(h->device));
+  int rc = ensure_batch_ws(h);
+  if (rc != CM_OK) return rc;
+  Workspace& w = h->batch;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  CM_CUDA(h, cudaMemsetAsync(w.meta, 0, w.ml.zero_bytes, st));
+  Ctrl* ctrl = reinterpret_cast<Ctrl*>(w.meta + w.ml.off_ctrl);
+  FrameAcc* acc = reinterpret_cast<FrameAcc*>(w.meta + w.ml.off_acc);
+  CM_CUDA(h, launch_minmax(reinterpret_cast<const float4*>(xyzi_dev), (uint32_t)n_points, ctrl, acc,
+                           reinterpret_cast<uint32_t*>(w.meta + w.ml.off_fstart), st));
+  FrameAcc a;
+  CM_CUDA(h, cudaMemcpyAsync(&a, acc, sizeof(a), cudaMemcpyDeviceToHost, st));
+  CM_CUDA(h, cudaStreamSynchronize(st));
+  const bool empty = a.max_enc[0] == 0u && a.nmin_enc[0] == 0u;
+  for (int k = 0; k < 3; ++k) {
+    uint32_t lo = f32_order_dec(~a.nmin_enc[k]), hi = f32_order_dec(a.max_enc[k]);
+    float flo, fhi;
+    memcpy(&flo, &lo, 4); memcpy(&fhi, &hi, 4);
+    min3[k] = empty ? std::numeric_limits<float>::max() : flo;
+    max3[k] = empty ? -std::numeric_limits<float>::max() : fhi;
+  }
+  if (n_finite) *n_finite = n_points - (int64_t)a.n_invalid;
+  return CM_OK;
+}
+
+int cm_dev_key_histogram(cm_handle_t h, const float* xyzi_dev, int64_t n_points, const float* min3, const float* max3,
+                         int bins, uint64_t* hist_dev, uint64_t* out_bin_width, void* stream) {
+  if (!h || !min3 || !max3 || !hist_dev || bins <= 0 || n_points < 0 || n_points > 0xFFFFFFF0ll) return CM_E_INVALID;
+  std::lock_guard<std::mutex> lk(h->mu);
+  CM_CUDA(h, cudaSetDevice(h->device));
+  RouteGrid g;
+  unsigned long long cells = 0;
+  int rc = route_grid(h, min3, max3, &g, &cells);
+  if (rc != CM_OK) return rc;
+  const unsigned long long width = std::max<unsigned long long>(1ull, (cells + (unsigned long long)bins - 1ull) / (unsigned long long)bins);
+  if (out_bin_width) *out_bin_width = width;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  CM_CUDA(h, cudaMemsetAsync(hist_dev, 0, sizeof(uint64_t) * (size_t)bins, st));
+  CM_CUDA(h, launch_route_hist(reinterpret_cast<const float4*>(xyzi_dev), (uint32_t)n_points, g, width, (uint32_t)bins,
+                               reinterpret_cast<unsigned long long*>(hist_dev), st));
+  return CM_OK;
+}
+
+int cm_dev_route_by_key(cm_handle_t h, const float* xyzi_dev, int64_t n_points, const float* min3, const float* max3,
+                        const uint64_t* splitters, int n_parts, int invalid_part, void* stream) {
+  if (!h || !min3 || !max3 || n_parts < 1 || n_parts > CM_MAX_ZONES || (n_parts > 1 && !splitters) || invalid_part < 0 ||
+      invalid_part >= n_parts || n_points < 0 || n_points > 0xFFFFFFF0ll)
+    return CM_E_INVALID;
+  std::lock_guard<std::mutex> lk(h->mu);
+  CM_CUDA(h, cudaSetDevice(h->device));
+  if (n_points > 0 && (!xyzi_dev || (reinterpret_cast<uintptr_t>(xyzi_dev) & 15u))) return fail(h, CM_E_INVALID, "xyzi_dev must be 16-byte aligned");
+  RouteGrid g;
+  int rc = route_grid(h, min3, max3, &g, nullptr);
+  if (rc != CM_OK) return rc;
+  rc = zone_ws_ensure(h, (size_t)n_points);
+  if (rc != CM_OK) return rc;
+  RouteSplit sp{};
+  sp.n_parts = n_parts; sp.invalid_part = (uint32_t)invalid_part;
+  for (int k = 0; k + 1 < n_parts; ++k) sp.splitter[k] = splitters[k];
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  CM_CUDA(h, launch_route_mask(reinterpret_cast<const float4*>(xyzi_dev), (uint32_t)n_points, g, sp, h->zw.mask, st));
+  return zone_run(h, reinterpret_cast<const float4*>(xyzi_dev), n_points, st, true, n_parts);
+}
+
+int cm_memcpy_d2d(cm_handle_t h, void* dst_dev, const void* src_dev, size_t bytes, void* stream) {
+  if (!h) return CM_E_INVALID;
+  CM_CUDA(h, cudaSetDevice(h->device));
+  if (bytes) CM_CUDA(h, cudaMemcpyAsync(dst_dev, src_dev, bytes, cudaMemcpyDeviceToDevice, static_cast<cudaStream_t>(stream)));
   return CM_OK;
 }
 

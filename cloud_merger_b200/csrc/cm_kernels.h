@@ -122,6 +122,22 @@ struct RorParams {
 };
 cudaError_t launch_radius_count(const VoxelParams& p, const RorParams& r, cudaStream_t stream);
 
+// ---- giant-cloud mode: routing by voxel-key range (cm_route.cu) ----------------------------------------------------------
+struct RouteGrid {  // PCL's grid on the GLOBAL bounding box
+  float inv[3];
+  long long min_b[3];
+  long long div0, div01;  // div_x, div_x * div_y
+};
+struct RouteSplit {
+  int32_t n_parts;                           // <= CM_MAX_ZONES
+  uint32_t invalid_part;                     // where non-finite points go (the local rank)
+  unsigned long long splitter[CM_MAX_ZONES];  // part r owns voxel indices in [splitter[r-1], splitter[r])
+};
+cudaError_t launch_route_hist(const float4* pts, uint32_t n, const RouteGrid& g, unsigned long long width, uint32_t bins,
+                              unsigned long long* hist, cudaStream_t stream);
+cudaError_t launch_route_mask(const float4* pts, uint32_t n, const RouteGrid& g, const RouteSplit& sp, unsigned short* mask,
+                              cudaStream_t stream);
+// bounding box of n packed points into acc (frame 0), as launch_minmax does for the VoxelGrid-only entry
 uint32_t zone_tile_points();
 cudaError_t launch_zone_split(const ZoneParams& p, cudaStream_t stream);  // 3 launches
 cudaError_t launch_zone_scatter(const ZoneParams& p, cudaStream_t stream);  // the last of them again, after out_* grew

@@ -10,10 +10,12 @@ Two modes:
   runs the ordinary single-GPU VoxelGrid. Concatenating the rank outputs in rank order is the global PCL order.
 
 The per-rank compute is injected as a callable so that the same orchestration runs on NCCL with the CUDA library and,
-in the CPU tests, on gloo with a checker backend.
+in the CPU tests, on gloo with a checker backend; with a CudaRouter the routing steps (bounding box, key histogram,
+grouping by destination) run on this package's kernels too and torch only carries the collectives.
 """
 from __future__ import annotations
 
+import sys
 from typing import Callable, List, Optional, Sequence, Tuple
 
 import numpy as np
@@ -115,12 +117,92 @@ def exchange_by_key_range(local_xyzi: torch.Tensor, keys: torch.Tensor, splitter
     return recv
 
 
+class CudaRouter:
+    """The routing steps of giant_cloud_voxelgrid on this package's CUDA kernels instead of torch ops: bounding box
+    (cm_dev_bounds), coarse key histogram (cm_dev_key_histogram), grouping by destination (cm_dev_route_by_key, the
+    zone-slicing count / scan / scatter). torch only carries the collectives. The leaf must have been set on the merger
+    (cm_set_voxel) -- cuda_voxelgrid_backend does that."""
+
+    def __init__(self, merger, bins: int = 1 << 14):
+        self.m = merger
+        self.bins = bins
+
+    def global_grid(self, local_xyzi: torch.Tensor, leaf: Sequence[float], group=None):
+        stream = torch.cuda.current_stream().cuda_stream
+        mn, mx, _ = self.m.dev_bounds(local_xyzi.data_ptr(), int(local_xyzi.shape[0]), stream=stream)
+        if dist.is_initialized() and dist.get_world_size(group) > 1:
+            t = torch.tensor(np.concatenate([mn, -mx]), device=local_xyzi.device)  # one MIN all-reduce for both bounds
+            dist.all_reduce(t, op=dist.ReduceOp.MIN, group=group)
+            t = t.cpu().numpy()
+            mn, mx = t[:3].astype(F32), (-t[3:]).astype(F32)
+        inv = (F32(1.0) / np.asarray(leaf, F32)).astype(F32)
+        min_b = np.floor((mn * inv).astype(F32)).astype(np.int64)
+        max_b = np.floor((mx * inv).astype(F32)).astype(np.int64)
+        return mn, mx, min_b, max_b - min_b + 1
+
+    def exchange(self, local_xyzi: torch.Tensor, min_p, max_p, rank: int, world: int, group=None):
+        """histogram -> all-reduce -> splitters -> group by destination -> one all-to-all. Returns (received points,
+        points sent to other ranks, splitters). With CM_GIANT_TRACE=1 rank 0 prints a per-step time breakdown."""
+        import os
+        import time
+        trace = os.environ.get("CM_GIANT_TRACE") and rank == 0
+        marks = []
+
+        def mark(name):
+            if trace:
+                torch.cuda.synchronize()
+                marks.append((name, time.perf_counter()))
+        mark("start")
+        dev = local_xyzi.device
+        n = int(local_xyzi.shape[0])
+        stream = torch.cuda.current_stream().cuda_stream
+        hist = torch.empty(self.bins, dtype=torch.int64, device=dev)
+        width = self.m.dev_key_histogram(local_xyzi.data_ptr(), n, min_p, max_p, self.bins, hist.data_ptr(), stream=stream)
+        mark("key histogram")
+        dist.all_reduce(hist, group=group)
+        cum = torch.cumsum(hist, dim=0)
+        total = int(cum[-1].item())
+        targets = torch.tensor([total * r // world for r in range(1, world)], device=dev, dtype=torch.int64)
+        cut_bins = torch.searchsorted(cum, targets, right=False) + 1
+        splitters = (cut_bins.clamp_(0, self.bins) * width).to(torch.int64)
+        sp = splitters.cpu().tolist()
+        mark("all-reduce + splitters")
+        self.m.dev_route_by_key(local_xyzi.data_ptr(), n, min_p, max_p, sp, rank, stream=stream)
+        xyzi_ptr, _, begin = self.m.zone_out_raw()
+        mark("group by destination")
+        send = torch.empty((begin[-1], 4), dtype=torch.float32, device=dev)
+        self.m.memcpy_d2d(send.data_ptr(), xyzi_ptr, begin[-1] * 16, stream=stream)
+        mark("copy to send buffer")
+        sc = [begin[r + 1] - begin[r] for r in range(world)]
+        send_counts = torch.tensor(sc, dtype=torch.int64, device=dev)
+        recv_counts = torch.empty_like(send_counts)
+        dist.all_to_all_single(recv_counts, send_counts, group=group)
+        rc = recv_counts.tolist()
+        recv = torch.empty((int(sum(rc)), 4), dtype=torch.float32, device=dev)
+        mark("counts exchange")
+        dist.all_to_all_single(recv, send, output_split_sizes=rc, input_split_sizes=sc, group=group)
+        mark("all-to-all")
+        if trace:
+            print("[giant] " + ", ".join("%s %.2f ms" % (b[0], (b[1] - a[1]) * 1e3) for a, b in zip(marks, marks[1:])), file=sys.stderr)
+        return recv, n - sc[rank], splitters
+
+
 def giant_cloud_voxelgrid(local_xyzi: torch.Tensor, leaf: Sequence[float], min_points: int,
                           voxelgrid_local: Callable[[torch.Tensor, np.ndarray, np.ndarray], dict], rank: int, world: int,
-                          group=None) -> dict:
+                          group=None, router: Optional[CudaRouter] = None) -> dict:
     """VoxelGrid of one cloud spread over `world` ranks. `voxelgrid_local(points, min_p, max_p) -> dict(idx, count,
     centroid)` is the single-GPU VoxelGrid run with the GLOBAL bounding box (cm_set_voxel_bounds + cm_dev_voxelgrid).
     Returns this rank's voxels (ascending idx; ranks hold ascending, disjoint key ranges) plus exchange statistics."""
+    if router is not None:  # the product path: CUDA kernels of this package, torch for the collectives only
+        min_p, max_p, min_b, div_b = router.global_grid(local_xyzi, leaf, group)
+        if world > 1:
+            recv, sent_away, splitters = router.exchange(local_xyzi, min_p, max_p, rank, world, group)
+        else:
+            splitters, recv, sent_away = torch.zeros(0, dtype=torch.int64), local_xyzi, 0
+        out = voxelgrid_local(recv, min_p, max_p)
+        out.update(points_received=int(recv.shape[0]), points_sent_away=sent_away, min_b=min_b, div_b=div_b,
+                   splitters=splitters.cpu().numpy())
+        return out
     min_p, max_p, min_b, div_b = global_grid(local_xyzi, leaf, group)
     n_cells = int(div_b[0]) * int(div_b[1]) * int(div_b[2])
     if world > 1:

@@ -269,6 +269,23 @@ CM_API int cm_dev_radius_outlier(cm_handle_t h, const float* xyzi_dev, int64_t n
                                  int min_neighbors, int negative, void* stream);
 CM_API int cm_radius_outlier(cm_handle_t h, const float* xyzi_host, int64_t n_points, double radius, int min_neighbors,
                              int negative, float* out_xyzi, uint32_t* out_idx, int64_t capacity, int64_t* n_out);
+/* ---- single giant cloud over several GPUs (BASELINE config 4): device-side pieces of the voxel-key range partition ----
+ * The reference has no counterpart (one process). Every rank holds a block of the cloud; all ranks must build the SAME
+ * voxel grid, a voxel must not straddle ranks, and the rank outputs concatenated in rank order must be PCL's order:
+ *  cm_dev_bounds         pcl::getMinMax3D of the local block (blocking; the caller all-reduces min / max);
+ *  cm_dev_key_histogram  histogram (uint64 bins on the device, equal key width, *out_bin_width) of the PCL voxel index
+ *                        idx = i + j*div_x + k*div_x*div_y on the grid of the GLOBAL box (the caller all-reduces it and
+ *                        cuts it into balanced key ranges);
+ *  cm_dev_route_by_key   groups the local points by destination: part r owns idx in [splitters[r-1], splitters[r])
+ *                        (n_parts - 1 splitters; non-finite points go to invalid_part); source order is kept inside a
+ *                        part. Results through cm_get_zone_out (zone r = the send buffer for rank r).
+ * The owning rank then runs cm_set_voxel_bounds + cm_dev_voxelgrid on what it received. Leaf = cm_set_voxel. */
+CM_API int cm_dev_bounds(cm_handle_t h, const float* xyzi_dev, int64_t n_points, float* min3, float* max3,
+                         int64_t* n_finite, void* stream);
+CM_API int cm_dev_key_histogram(cm_handle_t h, const float* xyzi_dev, int64_t n_points, const float* min3,
+                                const float* max3, int bins, uint64_t* hist_dev, uint64_t* out_bin_width, void* stream);
+CM_API int cm_dev_route_by_key(cm_handle_t h, const float* xyzi_dev, int64_t n_points, const float* min3,
+                               const float* max3, const uint64_t* splitters, int n_parts, int invalid_part, void* stream);
 /* Blocks until the last run on the handle finished, then reports. */
 CM_API int cm_sync(cm_handle_t h);
 CM_API int cm_get_stats(cm_handle_t h, cm_stats_t* out);
@@ -290,6 +307,7 @@ CM_API int cm_dev_alloc(cm_handle_t h, void** p, size_t bytes);
 CM_API int cm_dev_free(cm_handle_t h, void* p);
 CM_API int cm_memcpy_h2d(cm_handle_t h, void* dst_dev, const void* src_host, size_t bytes, void* stream);
 CM_API int cm_memcpy_d2h(cm_handle_t h, void* dst_host, const void* src_dev, size_t bytes, void* stream);
+CM_API int cm_memcpy_d2d(cm_handle_t h, void* dst_dev, const void* src_dev, size_t bytes, void* stream);
 
 #ifdef __cplusplus
 }

@@ -18,6 +18,10 @@ from cloud_merger_b200 import CloudMerger, multi_gpu, synth  # noqa: E402
 
 
 def main():
+    # one JSON line on stdout: whatever libraries print there (NCCL's version banner) goes to stderr instead
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--points", type=int, default=100_000_000)
     ap.add_argument("--leaf", type=float, default=0.02)
@@ -41,13 +45,14 @@ def main():
     cap = int(min(n, (hi - lo) * 2 + 1024))
     cm = CloudMerger(device=local_rank, max_batch_points=cap)
     backend = multi_gpu.cuda_voxelgrid_backend(cm, a.leaf, a.min_points, download=a.check)
+    router = multi_gpu.CudaRouter(cm)
     times, out = [], None
     for it in range(a.iters + 1):
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
         t0 = time.perf_counter()
-        out = multi_gpu.giant_cloud_voxelgrid(local, [a.leaf] * 3, a.min_points, backend, rank, world)
+        out = multi_gpu.giant_cloud_voxelgrid(local, [a.leaf] * 3, a.min_points, backend, rank, world, router=router)
         torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
@@ -80,11 +85,11 @@ def main():
             check = "ok" if ok else "MISMATCH"
     if rank == 0:
         sent = int(sum(int(v[1]) for v in allv))
-        print(json.dumps({"workload": "cfg4: %d-pt map cloud, VoxelGrid %.3f m, key-range partition + all-to-all" % (n, a.leaf),
+        os.write(real_stdout, (json.dumps({"workload": "cfg4: %d-pt map cloud, VoxelGrid %.3f m, key-range partition + all-to-all" % (n, a.leaf),
                           "n_gpus": world, "points": n, "voxels": int(sum(int(v[2]) for v in allv)), "ms": dt * 1e3,
                           "mpoints_per_s": n / dt / 1e6, "points_exchanged": sent, "bytes_exchanged": sent * 16,
                           "points_per_rank_after": [int(v[0]) for v in allv], "key_bits": out.get("key_bits"),
-                          "local_voxelgrid_ms": out.get("gpu_ms"), "check": check}))
+                          "local_voxelgrid_ms": out.get("gpu_ms"), "check": check}) + "\n").encode())
     cm.close()
     if world > 1:
         dist.destroy_process_group()

@@ -39,6 +39,42 @@ def test_giant_backend_single_gpu(gpu_ok, oracle):
     assert list(fi.min_b) == np.floor((lo * inv).astype(np.float32)).astype(int).tolist()
 
 
+def test_cuda_router_pieces_single_gpu(gpu_ok):
+    """The device-side routing steps against the torch formulation they replace: bounding box, key histogram and the
+    grouping by key range (membership, source order inside a part, non-finite points to the local part)."""
+    import torch
+    n, leaf = 300000, 0.1
+    whole = synth.map_cloud(9, n, extent=(100.0, 80.0, 8.0), n_boxes=80)
+    whole[::997, 0] = np.nan
+    whole[5::1999, 2] = np.inf
+    pts = torch.from_numpy(whole).cuda()
+    with CloudMerger(max_batch_points=n) as cm:
+        cm.set_voxel(leaf, 1, True)
+        router = multi_gpu.CudaRouter(cm, bins=4096)
+        mn, mx, min_b, div_b = router.global_grid(pts, [leaf] * 3)
+        t_mn, t_mx, t_min_b, t_div_b = multi_gpu.global_grid(pts, [leaf] * 3)
+        assert (mn.view(np.uint32) == t_mn.view(np.uint32)).all() and (mx.view(np.uint32) == t_mx.view(np.uint32)).all()
+        assert (min_b == t_min_b).all() and (div_b == t_div_b).all()
+        keys = multi_gpu.voxel_keys(pts, [leaf] * 3, min_b, div_b)
+        n_cells = int(div_b[0]) * int(div_b[1]) * int(div_b[2])
+        hist = torch.zeros(4096, dtype=torch.int64, device="cuda")
+        width = cm.dev_key_histogram(pts.data_ptr(), n, mn, mx, 4096, hist.data_ptr())
+        assert width == max(1, -(-n_cells // 4096))
+        want_hist = torch.bincount((keys[keys >= 0] // width).clamp_(0, 4095), minlength=4096)
+        assert torch.equal(hist, want_hist)
+        parts, me = 5, 2
+        splitters = [n_cells * r // parts for r in range(1, parts)]
+        cm.dev_route_by_key(pts.data_ptr(), n, mn, mx, splitters, me)
+        got = cm.zone_out()
+        dest = torch.searchsorted(torch.tensor(splitters, device="cuda"), keys, right=True)
+        dest = torch.where(keys < 0, torch.full_like(dest, me), dest).cpu().numpy()
+        assert len(got) == parts and sum(len(s) for _, s in got) == n
+        for r in range(parts):
+            want = np.nonzero(dest == r)[0]
+            assert (got[r][1] == want).all(), "part %d" % r
+            assert (got[r][0].view(np.uint32) == whole[want].view(np.uint32)).all()
+
+
 def test_giant_cloud_two_ranks_nccl(gpu_ok):
     import torch
     if torch.cuda.device_count() < 2:
