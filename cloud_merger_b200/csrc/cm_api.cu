@@ -505,7 +505,7 @@ int run_pipeline(cm_handle_t h, Workspace& w, const cm_segment_t* segs, int n_se
   if (!w.capturing) CM_CUDA(h, cudaEventRecord(w.ev[EV_START], st));
   CM_CUDA(h, cudaMemsetAsync(w.meta, 0, w.ml.zero_bytes, st));
   K1Params kp;
-  kp.segs = w.segs; kp.n_seg = (uint32_t)n_seg; kp.n_tiles = plan.n_tiles; kp.n_frames = n_frames; kp.epoch = 0;
+  kp.segs = w.segs; kp.n_seg = (uint32_t)n_seg; kp.n_tiles = plan.n_tiles; kp.n_frames = n_frames;
   kp.tiles_per_seg = plan.tiles_per_seg; kp.tile_seg = w.tile_seg;
   kp.crop = h->crop;
   kp.surv_xyzi = w.surv_xyzi; kp.surv_src = w.surv_src;

@@ -2,11 +2,12 @@
 //
 // Conventions
 //  * one "run" = one batch of F frames x S sensors = n_seg segments, processed by a fixed sequence of launches;
-//  * the streaming kernels (transform_crop, centroid) compact tile-locally and leave one count per tile; a one-CTA scan
-//    turns the counts into dense offsets, so they carry no inter-CTA dependency. Only the radix passes need an
-//    order-preserving prefix across CTAs while the data moves: a single-pass decoupled look-back over tiles whose ids
-//    are handed out by an atomic counter (forward progress does not depend on CTA dispatch order);
-//  * look-back words carry an epoch, so the state arrays never need clearing between runs;
+//  * the streaming kernels (transform_crop, centroid, zone slicing) compact tile-locally and leave one count per tile; a
+//    small scan kernel turns the counts into dense offsets, so they carry no inter-CTA dependency. Only the radix passes
+//    need an order-preserving prefix across CTAs while the data moves: workers publish per-tile digit counts, scanner CTAs
+//    turn them into running sums (cm_radix_sort.cu); tiles are handed out by an atomic counter, so forward progress does
+//    not depend on which CTAs are resident;
+//  * look-back words carry an epoch (device-resident, advanced once per run), so the arrays never need clearing;
 //  * all spin loops have a watchdog: a stuck wait raises CM_E_INTERNAL in the control block instead of hanging the GPU.
 #pragma once
 
@@ -104,7 +105,7 @@ struct FrameAcc {
 };
 
 struct Ctrl {
-  uint32_t tile_counter[12];  // [0] transform_crop, [1..8] sort passes, [9] centroid, [10] minmax
+  uint32_t tile_counter[12];  // [1 + p]: next tile of radix pass p (the persistent workers claim tiles here); others unused
   uint32_t error;             // CM_DEV_E_*
   uint32_t total_voxels;
   uint32_t has_invalid;
@@ -184,16 +185,11 @@ __device__ __forceinline__ float ldg_stream_f1(const void* p) {
 #define CM_LB_AGG 1u
 #define CM_LB_INCL 2u
 #define CM_SPIN_LIMIT (1u << 22)
-#ifndef CM_WALK_W
-#define CM_WALK_W 24  // tiles per round trip of the per-digit walk: must exceed (round-trip latency / tile issue interval)
-#endif
 
 __device__ __forceinline__ unsigned long long lb_pack(uint32_t epoch, uint32_t flag, uint32_t value) {
   return ((unsigned long long)(epoch * 4u + flag) << 32) | (unsigned long long)value;
 }
 
-// Spin until the word belongs to this epoch and carries a flag. Returns the word; on watchdog expiry raises the
-// device error and returns an "inclusive 0" word so that every waiter drains.
 __device__ __forceinline__ unsigned long long ld_relaxed_u64(const unsigned long long* p) {
   unsigned long long v;
   asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
@@ -219,21 +215,6 @@ __device__ __forceinline__ bool lb_ready(unsigned long long w, uint32_t epoch) {
   return (hi >> 2) == epoch && (hi & 3u) != 0u;
 }
 
-// Spin until the word belongs to this epoch and carries a flag. Returns the word; on watchdog expiry raises the
-// device error and returns an "inclusive 0" word so that every waiter drains.
-__device__ __forceinline__ unsigned long long lb_wait(unsigned long long* p, uint32_t epoch, uint32_t* err) {
-  uint32_t spins = 0;
-  while (true) {
-    const unsigned long long w = ld_relaxed_u64(p);
-    if (lb_ready(w, epoch)) return w;
-    if (++spins > CM_SPIN_LIMIT) {
-      atomicExch(err, (uint32_t)CM_DEV_E_INTERNAL);
-      return lb_pack(epoch, CM_LB_INCL, 0u);
-    }
-    if (spins > 64) __nanosleep(20);
-  }
-}
-
 // Spin until the word of this epoch carries the INCLUSIVE flag (written by the scanner CTAs of the radix pass).
 __device__ __forceinline__ uint32_t lb_wait_inclusive(unsigned long long* p, uint32_t epoch, uint32_t* err) {
   uint32_t spins = 0;
@@ -246,158 +227,6 @@ __device__ __forceinline__ uint32_t lb_wait_inclusive(unsigned long long* p, uin
       return 0u;
     }
     if (spins > 16) __nanosleep(40);
-  }
-}
-
-// Exclusive prefix of `agg` over all tiles before `tile`. Must be called by one full warp (all 32 lanes);
-// every lane returns the prefix.
-__device__ __forceinline__ uint32_t lb_exclusive_warp(unsigned long long* st, uint32_t tile, uint32_t agg,
-                                                      uint32_t epoch, uint32_t* err) {
-  const uint32_t lane = lane_id();
-  if (tile == 0) {
-    if (lane == 0) st_relaxed_u64(st, lb_pack(epoch, CM_LB_INCL, agg));
-    return 0u;
-  }
-  if (lane == 0) st_relaxed_u64(st + tile, lb_pack(epoch, CM_LB_AGG, agg));
-  uint32_t excl = 0;
-  long long base = (long long)tile - 1;
-  while (true) {
-    const long long idx = base - (long long)lane;
-    uint32_t flag = CM_LB_INCL, val = 0;
-    if (idx >= 0) {
-      const unsigned long long w = lb_wait(st + idx, epoch, err);
-      flag = ((uint32_t)(w >> 32)) & 3u;
-      val = (uint32_t)w;
-    }
-    const uint32_t incl = __ballot_sync(0xFFFFFFFFu, flag == CM_LB_INCL);
-    const int first = incl ? (__ffs(incl) - 1) : 32;
-    excl += warp_sum_u32(((int)lane <= first) ? val : 0u);
-    if (incl) break;
-    base -= 32;
-  }
-  if (lane == 0) st_relaxed_u64(st + tile, lb_pack(epoch, CM_LB_INCL, excl + agg));
-  return excl;
-}
-
-// Block-wide variant: every warp of the CTA inspects its own 32-tile window in the same round trip, so one step covers
-// WARPS*32 predecessors (a whole generation of co-resident tiles) instead of 32. Must be called by all threads of the
-// block; contains __syncthreads. `scratch` holds 2*WARPS+1 uint32. Returns the exclusive prefix in every thread.
-template <int WARPS>
-__device__ __forceinline__ uint32_t lb_exclusive_block(unsigned long long* st, uint32_t tile, uint32_t agg, uint32_t epoch,
-                                                       uint32_t* err, uint32_t* scratch) {
-  const uint32_t lane = lane_id(), warp = threadIdx.x >> 5;
-  if (tile == 0) {
-    if (threadIdx.x == 0) st_relaxed_u64(st, lb_pack(epoch, CM_LB_INCL, agg));
-    return 0u;
-  }
-  if (threadIdx.x == 0) st_relaxed_u64(st + tile, lb_pack(epoch, CM_LB_AGG, agg));
-  uint32_t excl = 0;
-  long long base = (long long)tile - 1;
-  while (true) {
-    const long long idx = base - (long long)(warp * 32u + lane);
-    uint32_t flag = CM_LB_INCL, val = 0;
-    if (idx >= 0) {
-      const unsigned long long w = lb_wait(st + idx, epoch, err);
-      flag = ((uint32_t)(w >> 32)) & 3u;
-      val = (uint32_t)w;
-    }
-    const uint32_t incl = __ballot_sync(0xFFFFFFFFu, flag == CM_LB_INCL);
-    const int first = incl ? (__ffs(incl) - 1) : 32;
-    const uint32_t part = warp_sum_u32(((int)lane <= first) ? val : 0u);
-    if (lane == 0) { scratch[warp] = part; scratch[WARPS + warp] = incl ? 1u : 0u; }
-    __syncthreads();
-    bool found = false;
-#pragma unroll
-    for (int w = 0; w < WARPS; ++w) {
-      if (!found) {
-        excl += scratch[w];
-        found = scratch[WARPS + w] != 0u;
-      }
-    }
-    __syncthreads();
-    if (found) break;
-    base -= (long long)WARPS * 32;
-  }
-  if (threadIdx.x == 0) st_relaxed_u64(st + tile, lb_pack(epoch, CM_LB_INCL, excl + agg));
-  return excl;
-}
-
-// Per-digit variant used by the radix pass, split in two so that the aggregate can be published early and the walk
-// done late: thread d walks back over tiles for its own digit d, eight tiles per round trip (independent loads).
-// Returns true (and *excl) when the predecessor's inclusive prefix was already there, in which case this tile's own
-// inclusive prefix is published at once instead of a bare aggregate.
-__device__ __forceinline__ bool lb_digit_publish(unsigned long long* st, uint32_t tile, uint32_t d, uint32_t agg,
-                                                 uint32_t epoch, uint32_t* excl) {
-  unsigned long long* mine = st + (size_t)tile * CM_RADIX + d;
-  if (tile == 0) {
-    st_relaxed_u64(mine, lb_pack(epoch, CM_LB_INCL, agg));
-    *excl = 0;
-    return true;
-  }
-  const unsigned long long w = ld_relaxed_u64(mine - CM_RADIX);
-  if (lb_ready(w, epoch) && (((uint32_t)(w >> 32)) & 3u) == CM_LB_INCL) {
-    *excl = (uint32_t)w;
-    st_relaxed_u64(mine, lb_pack(epoch, CM_LB_INCL, (uint32_t)w + agg));
-    return true;
-  }
-  st_relaxed_u64(mine, lb_pack(epoch, CM_LB_AGG, agg));
-  return false;
-}
-__device__ __forceinline__ uint32_t lb_digit_walk(unsigned long long* st, uint32_t tile, uint32_t d, uint32_t agg,
-                                                  uint32_t epoch, uint32_t* err, unsigned long long* dbg = nullptr) {
-  if (tile == 0) return 0u;
-  constexpr int W = CM_WALK_W;
-  uint32_t excl = 0, dbg_steps = 0, dbg_wait = 0;
-  long long j = (long long)tile;  // the first batch starts with this tile's own word: a pusher may have completed it
-  bool done = false, first = true;
-  while (!done && j >= 0) {
-    unsigned long long w[W];
-#pragma unroll
-    for (int k = 0; k < W; ++k) w[k] = (j - k >= 0) ? ld_cg_u64(st + (size_t)(j - k) * CM_RADIX + d) : 0ull;
-#pragma unroll
-    for (int k = 0; k < W; ++k) {
-      if (done || j - k < 0) continue;
-      unsigned long long v = w[k];
-      if (first && k == 0) {  // own word: inclusive already => exclusive = inclusive - aggregate
-        if (lb_ready(v, epoch) && (((uint32_t)(v >> 32)) & 3u) == CM_LB_INCL) {
-          if (dbg) *dbg = 0;
-          return (uint32_t)v - agg;
-        }
-        continue;
-      }
-      ++dbg_steps;
-      if (!lb_ready(v, epoch)) { ++dbg_wait; v = lb_wait(st + (size_t)(j - k) * CM_RADIX + d, epoch, err); }
-      excl += (uint32_t)v;
-      if ((((uint32_t)(v >> 32)) & 3u) == CM_LB_INCL) done = true;
-    }
-    first = false;
-    j -= W;
-  }
-  st_relaxed_u64(st + (size_t)tile * CM_RADIX + d, lb_pack(epoch, CM_LB_INCL, excl + agg));
-  if (dbg) *dbg = ((unsigned long long)dbg_steps << 32) | dbg_wait;
-  return excl;
-}
-// Forward push: a tile that knows its inclusive prefix completes, on their behalf, the inclusive prefixes of the tiles
-// right after it that have already published an aggregate (the value is the one the owner would compute itself, so the
-// duplicate store is benign). Every tile does this for a bounded number of successors, batch-loading their words, so the
-// inclusive frontier is carried forward cooperatively and the walks of later tiles stop after one round trip.
-__device__ __forceinline__ void lb_digit_push(unsigned long long* st, uint32_t tile, uint32_t n_tiles, uint32_t d,
-                                              uint32_t incl, uint32_t epoch, uint32_t max_rounds) {
-  constexpr int W = 16;
-  uint32_t run = incl;
-  uint32_t j = tile + 1;
-  for (uint32_t r = 0; r < max_rounds && j < n_tiles; ++r, j += W) {
-    unsigned long long w[W];
-#pragma unroll
-    for (int k = 0; k < W; ++k) w[k] = (j + k < n_tiles) ? ld_cg_u64(st + (size_t)(j + k) * CM_RADIX + d) : 0ull;
-#pragma unroll
-    for (int k = 0; k < W; ++k) {
-      if (j + k >= n_tiles) return;
-      const unsigned long long v = w[k];
-      if (!lb_ready(v, epoch) || (((uint32_t)(v >> 32)) & 3u) == CM_LB_INCL) return;
-      run += (uint32_t)v;
-      st_relaxed_u64(st + (size_t)(j + k) * CM_RADIX + d, lb_pack(epoch, CM_LB_INCL, run));
-    }
   }
 }
 

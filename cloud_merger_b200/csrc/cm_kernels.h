@@ -14,7 +14,6 @@ struct K1Params {
   uint32_t n_seg;
   uint32_t n_tiles;
   uint32_t n_frames;
-  uint32_t epoch;
   uint32_t tiles_per_seg;    // > 0: every segment owns exactly this many tiles (segment = tile / tiles_per_seg)
   const uint32_t* tile_seg;  // otherwise: segment of every tile
   CropDev crop;
