@@ -22,6 +22,9 @@ constexpr int KH_IPT = 8;
 constexpr int KH_TILE = VX_THREADS * KH_IPT;  // 2048 points per min/max tile
 constexpr int KH_DENSE_TILE = 4096;           // virtual tile of the key kernel when the input is a plain dense cloud
 constexpr int SCAN_THREADS = 1024;
+#ifndef CE_MIN_CTAS
+#define CE_MIN_CTAS 4
+#endif
 constexpr int CE_IPT = 8;
 constexpr int CE_TILE = VX_THREADS * CE_IPT;  // 2048 sorted items per centroid tile
 
@@ -427,7 +430,7 @@ __global__ void __launch_bounds__(VX_THREADS) k_voxel_key_hist(const VoxelParams
 // the warp executed the whole epilogue (four divisions, stores, atomics) for a handful of active lanes at a time, and
 // the kernel issued 190 instructions per item.
 template <typename KeyT>
-__global__ void __launch_bounds__(VX_THREADS, 4) k_voxel_centroid(const VoxelParams p) {
+__global__ void __launch_bounds__(VX_THREADS, CE_MIN_CTAS) k_voxel_centroid(const VoxelParams p) {
   constexpr bool REC = sizeof(KeyT) == 4;  // 8-byte (key, value) records
   __shared__ uint32_t s_scan[9];
   __shared__ __align__(16) float4 s_pts[CE_TILE];
