@@ -316,6 +316,45 @@ def test_pipelined_frames_and_optional_sensor(gpu_ok, oracle):
             assert_bit_equal(r.voxel_xyzi, o["centroid"], "frame %d" % f)
 
 
+def test_concurrent_sensor_callbacks_and_frame_graphs(gpu_ok, oracle):
+    """The reference runs its six sensor callbacks on ros::AsyncSpinner(6) and fuses on the main thread
+    (pc_preprocessing_main.cpp:513, :574-578): cm_submit_cloud from one thread per sensor, concurrently, then the merge.
+    Twelve frames of the same shape also take the host path through its plain / captured / replayed-graph stages; every
+    frame must match the oracle."""
+    import threading
+    S, rings, az = 6, 16, 128
+    n = rings * az
+    passes, leaf, mp = synth.ROI_BOX, 0.1, 2
+    with CloudMerger(max_sensors=S, max_points_per_sensor=n, frames_in_flight=2) as cm:
+        mats = [synth.extrinsic(s, S) for s in range(S)]
+        for s in range(S):
+            cm.set_extrinsic(s, mats[s])
+        cm.set_crop(passes)
+        cm.set_voxel(leaf, mp, True)
+        for f in range(12):
+            clouds = [synth.lidar_cloud(77, s, f, rings, az) for s in range(S)]
+            errs = []
+
+            def callback(s):
+                try:
+                    cm.submit_cloud(s, clouds[s], n, make_layout(), stamp=100 + f)
+                except Exception as e:  # noqa: BLE001
+                    errs.append(e)
+            th = [threading.Thread(target=callback, args=(s,)) for s in range(S)]
+            for t in th:
+                t.start()
+            for t in th:
+                t.join()
+            assert not errs, errs
+            r = cm.merge_frame(capacity=S * n)
+            o = oracle.merge_frame([cloud_dict(c, m[:3]) for c, m in zip(clouds, mats)], passes, [leaf] * 3, mp, True, True)
+            assert r.used_mask == (1 << S) - 1 and r.stamp == 100 + f
+            assert (r.survivor_src == o["survivor_src"]).all(), "frame %d" % f
+            assert_bit_equal(r.survivor_xyzi, o["survivor_xyzi"], "frame %d survivors" % f)
+            assert (r.voxel_idx.astype(np.int64) == o["idx"]).all() and (r.voxel_count == o["count"]).all(), "frame %d" % f
+            assert_bit_equal(r.voxel_xyzi, o["centroid"], "frame %d centroids" % f)
+
+
 def test_submit_clouds_pinned_matches_single_submits(gpu_ok, oracle):
     """cm_submit_clouds_pinned == one cm_submit_cloud_pinned per cloud, whether or not the clouds are adjacent in host
     memory (adjacent clouds of consecutive sensors travel as one copy), with ragged sizes and a skipped sensor id."""
