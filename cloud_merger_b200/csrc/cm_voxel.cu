@@ -22,6 +22,9 @@ constexpr int KH_IPT = 8;
 constexpr int KH_TILE = VX_THREADS * KH_IPT;  // 2048 points per min/max tile
 constexpr int KH_DENSE_TILE = 4096;           // virtual tile of the key kernel when the input is a plain dense cloud
 constexpr int SCAN_THREADS = 1024;
+#ifndef KH_UNROLL
+#define KH_UNROLL 8
+#endif
 #ifndef CE_MIN_CTAS
 #define CE_MIN_CTAS 4
 #endif
@@ -351,7 +354,7 @@ __device__ __forceinline__ void key_hist_tiles(const VoxelParams& p, uint32_t (*
     const KeyT mul1 = (KeyT)g->mul1, mul2 = (KeyT)g->mul2;  // 32-bit arithmetic when the key is 32-bit
     const int mb0 = g->min_b[0], mb1 = g->min_b[1], mb2 = g->min_b[2];
     const float4* __restrict__ src = p.pts + r.slot0;
-    constexpr int U = 4;  // points per thread in flight
+    constexpr int U = KH_UNROLL;  // points per thread in flight
     for (uint32_t j0 = 0; j0 < r.count; j0 += U * VX_THREADS) {
       const bool whole = j0 + U * VX_THREADS <= r.count;
       float4 pv[U];
