@@ -33,6 +33,20 @@ class CmZoneOut(C.Structure):
                 ("n_zones", C.c_int32), ("reserved", C.c_int32)]
 
 
+class CmPlaneCfg(C.Structure):
+    _fields_ = [("distance_threshold", C.c_double), ("probability", C.c_double), ("max_iterations", C.c_int32),
+                ("optimize", C.c_int32), ("seed", C.c_uint32), ("sum_order", C.c_int32)]
+
+
+class CmPlane(C.Structure):
+    _fields_ = [("found", C.c_int32), ("iterations", C.c_int32), ("draws", C.c_int32), ("best_count", C.c_int32),
+                ("sample", C.c_int32 * 3), ("reserved", C.c_int32), ("coeff_ransac", C.c_float * 4),
+                ("coeff", C.c_float * 4), ("n_inliers", C.c_int64)]
+
+
+CM_SUM4_SSE2, CM_SUM4_SSE3, CM_SUM4_SCALAR = 0, 1, 2
+
+
 class CmLayout(C.Structure):
     _fields_ = [("point_step", C.c_int32), ("off_x", C.c_int32), ("off_y", C.c_int32), ("off_z", C.c_int32),
                 ("off_intensity", C.c_int32), ("is_dense", C.c_int32)]
@@ -112,6 +126,9 @@ SYMBOLS = {
     "cm_dev_radius_outlier": (C.c_int, [_H, C.c_void_p, C.c_int64, C.c_double, C.c_int, C.c_int, C.c_void_p]),
     "cm_radius_outlier": (C.c_int, [_H, C.c_void_p, C.c_int64, C.c_double, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
                                     C.c_int64, C.POINTER(C.c_int64)]),
+    "cm_dev_plane_ransac": (C.c_int, [_H, C.c_void_p, C.c_int64, C.POINTER(CmPlaneCfg), C.POINTER(CmPlane), C.c_void_p]),
+    "cm_plane_ransac": (C.c_int, [_H, C.c_void_p, C.c_int64, C.POINTER(CmPlaneCfg), C.POINTER(CmPlane), C.c_void_p,
+                                  C.c_void_p, C.c_int64, C.POINTER(C.c_int64)]),
     "cm_dev_bounds": (C.c_int, [_H, C.c_void_p, C.c_int64, C.POINTER(C.c_float), C.POINTER(C.c_float), C.POINTER(C.c_int64),
                                 C.c_void_p]),
     "cm_dev_key_histogram": (C.c_int, [_H, C.c_void_p, C.c_int64, C.POINTER(C.c_float), C.POINTER(C.c_float), C.c_int,

@@ -225,6 +225,48 @@ class CloudMerger:
                                                 oi.ctypes.data_as(C.c_void_p), C.c_int64(n), C.byref(k)))
         return ox[:k.value].copy(), oi[:k.value].copy()
 
+    # -- RANSAC ground plane (pcl::SACSegmentation of removeGround, pc_preprocessing_main.cpp:95-117) ------------------------
+    @staticmethod
+    def _plane_cfg(distance_threshold, probability, max_iterations, optimize, seed, sum_order):
+        return _lib.CmPlaneCfg(float(distance_threshold), float(probability), int(max_iterations), int(bool(optimize)),
+                               int(seed), int(sum_order))
+
+    @staticmethod
+    def _plane_dict(pl) -> dict:
+        return {"found": bool(pl.found), "iterations": int(pl.iterations), "draws": int(pl.draws),
+                "best_count": int(pl.best_count), "sample": np.array(pl.sample, np.int32),
+                "coeff_ransac": np.array(pl.coeff_ransac, np.float32), "coeff": np.array(pl.coeff, np.float32),
+                "n_inliers": int(pl.n_inliers)}
+
+    def dev_plane_ransac(self, xyzi_ptr: int, n_points: int, distance_threshold: float, probability: float = 0.99,
+                         max_iterations: int = 1000, optimize: bool = True, seed: int = 12345, sum_order: int = 0,
+                         stream: int = 0) -> dict:
+        """Device form; the ground / no-ground clouds are zones 0 / 1 of zone_out()."""
+        cfg = self._plane_cfg(distance_threshold, probability, max_iterations, optimize, seed, sum_order)
+        pl = _lib.CmPlane()
+        self._check(self._lib.cm_dev_plane_ransac(self._h, C.c_void_p(xyzi_ptr or None), C.c_int64(n_points), C.byref(cfg),
+                                                  C.byref(pl), C.c_void_p(stream or None)))
+        return self._plane_dict(pl)
+
+    def plane_ransac(self, xyzi: np.ndarray, distance_threshold: float, probability: float = 0.99,
+                     max_iterations: int = 1000, optimize: bool = True, seed: int = 12345, sum_order: int = 0) -> dict:
+        """Host-buffer form. Adds "ground" and "rest": (xyzi [k,4] float32, idx [k] uint32 into the input, ascending)."""
+        a = np.ascontiguousarray(xyzi, np.float32).reshape(-1, 4)
+        n = len(a)
+        cfg = self._plane_cfg(distance_threshold, probability, max_iterations, optimize, seed, sum_order)
+        pl = _lib.CmPlane()
+        ox = np.empty((max(n, 1), 4), np.float32)
+        oi = np.empty(max(n, 1), np.uint32)
+        begin = (C.c_int64 * 3)()
+        self._check(self._lib.cm_plane_ransac(self._h, a.ctypes.data_as(C.c_void_p), C.c_int64(n), C.byref(cfg), C.byref(pl),
+                                              ox.ctypes.data_as(C.c_void_p), oi.ctypes.data_as(C.c_void_p), C.c_int64(n),
+                                              begin))
+        r = self._plane_dict(pl)
+        b = list(begin)
+        r["ground"] = (ox[b[0]:b[1]].copy(), oi[b[0]:b[1]].copy())
+        r["rest"] = (ox[b[1]:b[2]].copy(), oi[b[1]:b[2]].copy())
+        return r
+
     # -- giant-cloud mode: device-side pieces of the voxel-key range partition (BASELINE config 4) -------------------------
     def dev_bounds(self, xyzi_ptr: int, n_points: int, stream: int = 0):
         """pcl::getMinMax3D of n packed points on the device -> (min[3], max[3] float32, number of finite points)."""

@@ -11,13 +11,14 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(HERE, "build")
 LIB = os.path.join(HERE, "libcloud_merger_gpu.so")
-SOURCES = ["cm_transform_crop.cu", "cm_voxel.cu", "cm_radix_sort.cu", "cm_zones.cu", "cm_outlier.cu", "cm_route.cu", "cm_api.cu"]
+SOURCES = ["cm_transform_crop.cu", "cm_voxel.cu", "cm_radix_sort.cu", "cm_zones.cu", "cm_outlier.cu", "cm_route.cu", "cm_plane.cu", "cm_api.cu"]
 HEADERS = ["cm_common.cuh", "cm_kernels.h", os.path.join("..", "..", "include", "cloud_merger_gpu.h")]
 
 NVCC_FLAGS = [
     "-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
     "--fmad=false",  # parity: PCL's CPU build has no FMA; the kernels also use __fmul_rn/__fadd_rn explicitly
-    "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden", "-Xptxas", "-v", "-Xcudafe", "--diag_suppress=177",
+    "-Xcompiler", "-fPIC", "-Xcompiler", "-ffp-contract=off",  # host side of the plane refit: no FMA either
+     "-Xcompiler", "-fvisibility=hidden", "-Xptxas", "-v", "-Xcudafe", "--diag_suppress=177",
 ]
 
 

@@ -15,7 +15,9 @@
 #include <limits>
 #include <mutex>
 #include <new>
+#include <random>
 #include <string>
+#include <unordered_map>
 #include <vector>
 
 #include "../../include/cloud_merger_gpu.h"
@@ -161,6 +163,18 @@ struct cm_handle_s {
     ZoneParams last{};           // the last split, so that its scatter can be repeated after the outputs grew
     int n_zones_run = 0;         // zones of the last split (1 for a radius outlier removal)
   } zw;
+  // RANSAC ground plane (allocated on first use): one batch of draws and its scores, device + pinned mirrors
+  struct PlaneWs {
+    size_t cap_draws = 0;
+    int32_t* samples_dev = nullptr;  // [cap_draws][3]
+    int32_t* counts_dev = nullptr;   // [cap_draws] counts, then [cap_draws] good flags
+    float4* models_dev = nullptr;    // [cap_draws]
+    float* acc_dev = nullptr;        // [10] running sums + count
+    int32_t* samples_pin = nullptr;
+    int32_t* counts_pin = nullptr;
+    float4* models_pin = nullptr;
+    float* acc_pin = nullptr;
+  } pw;
   // host path
   std::vector<Slot> slots;
   std::vector<cudaStream_t> sensor_stream;
@@ -908,6 +922,12 @@ int cm_destroy(cm_handle_t h) {
     cudaFree(z.zone_total);
     cudaFree(z.out_xyzi); cudaFree(z.out_src); cudaFree(z.in_stage);
     if (z.report) cudaFreeHost(z.report);
+    auto& q = h->pw;
+    cudaFree(q.samples_dev); cudaFree(q.counts_dev); cudaFree(q.models_dev); cudaFree(q.acc_dev);
+    if (q.samples_pin) cudaFreeHost(q.samples_pin);
+    if (q.counts_pin) cudaFreeHost(q.counts_pin);
+    if (q.models_pin) cudaFreeHost(q.models_pin);
+    if (q.acc_pin) cudaFreeHost(q.acc_pin);
   }
   delete h;
   return CM_OK;
@@ -1247,9 +1267,16 @@ int cm_dev_zone_split(cm_handle_t h, const float* xyzi_dev, int64_t n_points, vo
   return zone_run(h, w.dense_xyzi, h->stats.survivors, st);
 }
 
+namespace {
+int zone_out_locked(cm_handle_t h, cm_zone_out_t* out);
+}
 int cm_get_zone_out(cm_handle_t h, cm_zone_out_t* out) {
   if (!h || !out) return CM_E_INVALID;
   std::lock_guard<std::mutex> lk(h->mu);
+  return zone_out_locked(h, out);
+}
+namespace {
+int zone_out_locked(cm_handle_t h, cm_zone_out_t* out) {
   cm_handle_s::ZoneWs& z = h->zw;
   if (!z.ran) return fail(h, CM_E_INVALID, "no zone split has run on this handle");
   CM_CUDA(h, cudaSetDevice(h->device));
@@ -1279,6 +1306,7 @@ int cm_get_zone_out(cm_handle_t h, cm_zone_out_t* out) {
     return fail(h, CM_E_CAPACITY, "the zones hold %u points together, capacity is %zu", z.report[CM_MAX_ZONES + 1], z.cap_out);
   return CM_OK;
 }
+}  // namespace
 
 int cm_zone_split(cm_handle_t h, const float* xyzi_host, int64_t n_points, float* out_xyzi, uint32_t* out_src,
                   int64_t capacity, int64_t* out_begin) {
@@ -1486,6 +1514,265 @@ int cm_radius_outlier(cm_handle_t h, const float* xyzi_host, int64_t n_points, d
     if (out_xyzi && total) CM_CUDA(h, cudaMemcpy(out_xyzi, zo.xyzi, (size_t)total * 16, cudaMemcpyDeviceToHost));
     if (out_idx && total) CM_CUDA(h, cudaMemcpy(out_idx, zo.src, (size_t)total * 4, cudaMemcpyDeviceToHost));
   }
+  return CM_OK;
+}
+
+// ---- RANSAC ground plane --------------------------------------------------------------------------------------------------
+namespace {
+constexpr size_t PLANE_FIRST_BATCH = 256;  // PCL's stopping rule usually ends within a few iterations on a ground zone
+constexpr size_t PLANE_BATCH = 1024;
+
+int plane_ws_ensure(cm_handle_t h) {
+  cm_handle_s::PlaneWs& q = h->pw;
+  if (q.cap_draws) return CM_OK;
+  CM_CUDA(h, dev_alloc(&q.samples_dev, PLANE_BATCH * 3));
+  CM_CUDA(h, dev_alloc(&q.counts_dev, PLANE_BATCH * 2));
+  CM_CUDA(h, dev_alloc(&q.models_dev, PLANE_BATCH));
+  CM_CUDA(h, dev_alloc(&q.acc_dev, (size_t)16));
+  CM_CUDA(h, cudaMallocHost(reinterpret_cast<void**>(&q.samples_pin), PLANE_BATCH * 3 * sizeof(int32_t)));
+  CM_CUDA(h, cudaMallocHost(reinterpret_cast<void**>(&q.counts_pin), PLANE_BATCH * 2 * sizeof(int32_t)));
+  CM_CUDA(h, cudaMallocHost(reinterpret_cast<void**>(&q.models_pin), PLANE_BATCH * sizeof(float4)));
+  CM_CUDA(h, cudaMallocHost(reinterpret_cast<void**>(&q.acc_pin), 16 * sizeof(float)));
+  q.cap_draws = PLANE_BATCH;
+  return CM_OK;
+}
+
+// SampleConsensusModel::shuffled_indices_ without the O(n) array: only the entries a swap has touched are stored
+struct ShuffledIndices {
+  std::unordered_map<int64_t, int32_t> moved;
+  int32_t get(int64_t i) const {
+    auto it = moved.find(i);
+    return it == moved.end() ? (int32_t)i : it->second;
+  }
+  void swap(int64_t a, int64_t b) {
+    if (a == b) return;
+    const int32_t va = get(a), vb = get(b);
+    moved[a] = vb;
+    moved[b] = va;
+  }
+};
+
+// Eigen's 4-wide float reduction in the order of the build PCL came from (cm_plane_cfg_t::sum_order)
+float sum4_host(float l0, float l1, float l2, float l3, int order) {
+  if (order == CM_SUM4_SSE2) return (l0 + l2) + (l1 + l3);
+  if (order == CM_SUM4_SSE3) return (l0 + l1) + (l2 + l3);
+  return ((l0 + l1) + l2) + l3;
+}
+
+// pcl::computeRoots2 (common/impl/eigen.hpp): roots of x^2 - b x + c, with the zero root in front
+void plane_roots2(float b, float c, float* roots) {
+  roots[0] = 0.0f;
+  float d = (float)(b * b - 4.0 * c);
+  if (d < 0.0) d = 0.0f;
+  const float sd = std::sqrt(d);
+  roots[2] = 0.5f * (b + sd);
+  roots[1] = 0.5f * (b - sd);
+}
+
+// pcl::computeRoots for a symmetric 3x3 float matrix given as xx xy xz yy yz zz; ascending roots
+void plane_roots3(const float* a, float* roots) {
+  const float xx = a[0], xy = a[1], xz = a[2], yy = a[3], yz = a[4], zz = a[5];
+  const float c0 = xx * yy * zz + 2.0f * xy * xz * yz - xx * yz * yz - yy * xz * xz - zz * xy * xy;
+  const float c1 = xx * yy - xy * xy + xx * zz - xz * xz + yy * zz - yz * yz;
+  const float c2 = xx + yy + zz;
+  if (std::fabs(c0) < std::numeric_limits<float>::epsilon()) return plane_roots2(c2, c1, roots);
+  const float inv3 = (float)(1.0 / 3.0), sqrt3 = std::sqrt(3.0f);
+  const float c2_3 = c2 * inv3;
+  float a_3 = (c1 - c2 * c2_3) * inv3;
+  if (a_3 > 0.0f) a_3 = 0.0f;
+  const float half_b = 0.5f * (c0 + c2_3 * (2.0f * c2_3 * c2_3 - c1));
+  float q = half_b * half_b + a_3 * a_3 * a_3;
+  if (q > 0.0f) q = 0.0f;
+  const float rho = std::sqrt(-a_3);
+  const float theta = std::atan2(std::sqrt(-q), half_b) * inv3;
+  const float ct = std::cos(theta), sn = std::sin(theta);
+  roots[0] = c2_3 + 2.0f * rho * ct;
+  roots[1] = c2_3 - rho * (ct + sqrt3 * sn);
+  roots[2] = c2_3 - rho * (ct - sqrt3 * sn);
+  if (roots[0] >= roots[1]) std::swap(roots[0], roots[1]);
+  if (roots[1] >= roots[2]) {
+    std::swap(roots[1], roots[2]);
+    if (roots[0] >= roots[1]) std::swap(roots[0], roots[1]);
+  }
+  if (roots[0] <= 0.0f) plane_roots2(c2, c1, roots);
+}
+
+// SampleConsensusModelPlane::optimizeModelCoefficients after the running sums: mean, covariance, pcl::eigen33's
+// eigenvector of the smallest eigenvalue, d = -n . centroid. sums = xx xy xz yy yz zz x y z (PCL-order float sums).
+void plane_refit(const float* sums, uint32_t count, int order, float* coeff) {
+  float m[9];
+  const float cnt = (float)count;
+  for (int i = 0; i < 9; ++i) m[i] = sums[i] / cnt;
+  float cov[6] = {m[0] - m[6] * m[6], m[1] - m[6] * m[7], m[2] - m[6] * m[8],
+                  m[3] - m[7] * m[7], m[4] - m[7] * m[8], m[5] - m[8] * m[8]};
+  float scale = 0.0f;
+  for (int i = 0; i < 6; ++i) scale = std::max(scale, std::fabs(cov[i]));
+  if (scale <= std::numeric_limits<float>::min()) scale = 1.0f;
+  for (int i = 0; i < 6; ++i) cov[i] = cov[i] / scale;
+  float roots[3];
+  plane_roots3(cov, roots);
+  const float r0[3] = {cov[0] - roots[0], cov[1], cov[2]};
+  const float r1[3] = {cov[1], cov[3] - roots[0], cov[4]};
+  const float r2[3] = {cov[2], cov[4], cov[5] - roots[0]};
+  auto cross = [](const float* u, const float* v, float* o) {
+    o[0] = u[1] * v[2] - u[2] * v[1];
+    o[1] = u[2] * v[0] - u[0] * v[2];
+    o[2] = u[0] * v[1] - u[1] * v[0];
+  };
+  float v01[3], v02[3], v12[3];
+  cross(r0, r1, v01); cross(r0, r2, v02); cross(r1, r2, v12);
+  auto len2 = [](const float* u) { return u[0] * u[0] + u[1] * u[1] + u[2] * u[2]; };
+  const float l01 = len2(v01), l02 = len2(v02), l12 = len2(v12);
+  const float* pick; float len;
+  if (l01 >= l02 && l01 >= l12) { pick = v01; len = l01; }
+  else if (l02 >= l01 && l02 >= l12) { pick = v02; len = l02; }
+  else { pick = v12; len = l12; }
+  const float nrm = std::sqrt(len);
+  for (int i = 0; i < 3; ++i) coeff[i] = pick[i] / nrm;
+  coeff[3] = -1.0f * sum4_host(coeff[0] * m[6], coeff[1] * m[7], coeff[2] * m[8], 0.0f * 1.0f, order);
+}
+
+int plane_ransac_run(cm_handle_t h, const float4* pts, int64_t n_points, const cm_plane_cfg_t& cfg, cm_plane_t* out,
+                     cudaStream_t st) {
+  if (n_points < 0 || n_points > 0x7FFFFFF0ll) return fail(h, CM_E_INVALID, "bad n_points");
+  if (cfg.max_iterations < 0 || cfg.sum_order < 0 || cfg.sum_order > 2) return fail(h, CM_E_INVALID, "bad plane settings");
+  int rc = zone_ws_ensure(h, (size_t)n_points);
+  if (rc != CM_OK) return rc;
+  rc = plane_ws_ensure(h);
+  if (rc != CM_OK) return rc;
+  cm_handle_s::PlaneWs& q = h->pw;
+  memset(out, 0, sizeof(*out));
+  out->sample[0] = out->sample[1] = out->sample[2] = -1;
+  // PCL compares the float distance with the double threshold: the smallest float >= threshold decides the same way
+  float thr = (float)cfg.distance_threshold;
+  if ((double)thr < cfg.distance_threshold) thr = std::nextafter(thr, std::numeric_limits<float>::infinity());
+  const uint32_t n = (uint32_t)n_points;
+  int64_t launches = 0;
+
+  // RandomSampleConsensus::computeModel over the draw stream of SampleConsensusModel::getSamples
+  bool found = false;
+  if (n >= 3) {
+    std::mt19937 engine(cfg.seed);
+    ShuffledIndices shuffled;
+    int iterations = 0, draws = 0, bad_run = 0;
+    long long best = -(long long)std::numeric_limits<int>::max();
+    double k = 1.0;
+    const double log_probability = std::log(1.0 - cfg.probability);
+    const double one_over_indices = 1.0 / (double)n;
+    bool stop = false;
+    size_t batch = PLANE_FIRST_BATCH;
+    while (!stop && iterations < k) {
+      for (size_t d = 0; d < batch; ++d) {
+        for (int64_t i = 0; i < 3; ++i) {
+          const uint64_t r = (uint64_t)((uint32_t)engine() >> 1);  // boost::uniform_int<>(0, INT_MAX) on mt19937
+          shuffled.swap(i, i + (int64_t)(r % (uint64_t)(n - i)));
+        }
+        for (int64_t i = 0; i < 3; ++i) q.samples_pin[3 * d + i] = shuffled.get(i);
+      }
+      PlaneParams pp;
+      pp.pts = pts; pp.n_points = n; pp.samples = q.samples_dev; pp.n_draws = (uint32_t)batch;
+      pp.threshold = thr; pp.sum_order = (uint32_t)cfg.sum_order;
+      pp.models = q.models_dev; pp.counts = q.counts_dev; pp.good = q.counts_dev + q.cap_draws;
+      CM_CUDA(h, cudaMemcpyAsync(q.samples_dev, q.samples_pin, batch * 3 * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+      CM_CUDA(h, cudaMemsetAsync(q.counts_dev, 0, q.cap_draws * 2 * sizeof(int32_t), st));
+      CM_CUDA(h, launch_plane_score(pp, st));
+      ++launches;
+      CM_CUDA(h, cudaMemcpyAsync(q.counts_pin, q.counts_dev, q.cap_draws * 2 * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+      CM_CUDA(h, cudaMemcpyAsync(q.models_pin, q.models_dev, batch * sizeof(float4), cudaMemcpyDeviceToHost, st));
+      CM_CUDA(h, cudaStreamSynchronize(st));
+      const int32_t* counts = q.counts_pin;
+      const int32_t* good = q.counts_pin + q.cap_draws;
+      for (size_t d = 0; d < batch && !stop && iterations < k; ++d) {
+        ++draws;
+        if (!good[d]) {  // getSamples draws again; after max_sample_checks_ (1000) failures in a row it gives up
+          if (++bad_run == 1000) stop = true;
+          continue;
+        }
+        bad_run = 0;
+        if ((long long)counts[d] > best) {
+          best = counts[d];
+          found = true;
+          out->best_count = counts[d];
+          for (int i = 0; i < 3; ++i) out->sample[i] = q.samples_pin[3 * d + i];
+          const float4 c = q.models_pin[d];
+          out->coeff_ransac[0] = c.x; out->coeff_ransac[1] = c.y; out->coeff_ransac[2] = c.z; out->coeff_ransac[3] = c.w;
+          const double w = (double)best * one_over_indices;
+          double p_no_outliers = 1.0 - std::pow(w, 3.0);
+          p_no_outliers = std::max(std::numeric_limits<double>::epsilon(), p_no_outliers);
+          p_no_outliers = std::min(1.0 - std::numeric_limits<double>::epsilon(), p_no_outliers);
+          k = log_probability / std::log(p_no_outliers);
+        }
+        ++iterations;
+        if (iterations > cfg.max_iterations) stop = true;
+      }
+      batch = PLANE_BATCH;
+    }
+    out->iterations = iterations;
+    out->draws = draws;
+  }
+  out->found = found ? 1 : 0;
+  memcpy(out->coeff, out->coeff_ransac, sizeof(out->coeff));
+
+  // selectWithinDistance + the two ExtractIndices passes: zone 0 = inliers, zone 1 = the rest, both in input order
+  cm_zone_out_t zo;
+  CM_CUDA(h, launch_plane_select(pts, n, out->coeff_ransac, thr, (uint32_t)cfg.sum_order, found, h->zw.mask, st));
+  ++launches;
+  rc = zone_run(h, pts, n_points, st, true, 2);
+  if (rc != CM_OK) return rc;
+  launches += h->zw.launches;
+  if (found && cfg.optimize) {
+    CM_CUDA(h, launch_plane_moments(h->zw.out_xyzi, h->zw.zone_begin + 1, q.acc_dev, st));
+    ++launches;
+    CM_CUDA(h, cudaMemcpyAsync(q.acc_pin, q.acc_dev, 10 * sizeof(float), cudaMemcpyDeviceToHost, st));
+    CM_CUDA(h, cudaStreamSynchronize(st));
+    uint32_t n_in;
+    memcpy(&n_in, q.acc_pin + 9, sizeof(n_in));
+    if (n_in >= 4) {
+      plane_refit(q.acc_pin, n_in, cfg.sum_order, out->coeff);
+      CM_CUDA(h, launch_plane_select(pts, n, out->coeff, thr, (uint32_t)cfg.sum_order, true, h->zw.mask, st));
+      ++launches;
+      rc = zone_run(h, pts, n_points, st, true, 2);
+      if (rc != CM_OK) return rc;
+      launches += h->zw.launches;
+    }
+  }
+  rc = zone_out_locked(h, &zo);
+  if (rc != CM_OK) return rc;
+  h->zw.launches = launches;
+  out->n_inliers = zo.begin[1];
+  return CM_OK;
+}
+}  // namespace
+
+int cm_dev_plane_ransac(cm_handle_t h, const float* xyzi_dev, int64_t n_points, const cm_plane_cfg_t* cfg, cm_plane_t* out,
+                        void* stream) {
+  if (!h || !cfg || !out) return CM_E_INVALID;
+  std::lock_guard<std::mutex> lk(h->mu);
+  CM_CUDA(h, cudaSetDevice(h->device));
+  if (n_points > 0 && (!xyzi_dev || (reinterpret_cast<uintptr_t>(xyzi_dev) & 15u))) return fail(h, CM_E_INVALID, "xyzi_dev must be 16-byte aligned");
+  return plane_ransac_run(h, reinterpret_cast<const float4*>(xyzi_dev), n_points, *cfg, out, static_cast<cudaStream_t>(stream));
+}
+
+int cm_plane_ransac(cm_handle_t h, const float* xyzi_host, int64_t n_points, const cm_plane_cfg_t* cfg, cm_plane_t* out,
+                    float* out_xyzi, uint32_t* out_idx, int64_t capacity, int64_t* out_begin) {
+  if (!h || !cfg || !out || !out_begin || n_points < 0 || (n_points > 0 && !xyzi_host)) return CM_E_INVALID;
+  std::lock_guard<std::mutex> lk(h->mu);
+  CM_CUDA(h, cudaSetDevice(h->device));
+  int rc = zone_ws_ensure(h, (size_t)n_points);
+  if (rc != CM_OK) return rc;
+  cm_handle_s::ZoneWs& z = h->zw;
+  if (!z.in_stage) CM_CUDA(h, dev_alloc(&z.in_stage, z.cap_points));
+  CM_CUDA(h, cudaMemcpyAsync(z.in_stage, xyzi_host, (size_t)n_points * 16, cudaMemcpyHostToDevice, nullptr));
+  rc = plane_ransac_run(h, z.in_stage, n_points, *cfg, out, nullptr);
+  if (rc != CM_OK) return rc;
+  cm_zone_out_t zo;
+  rc = zone_out_locked(h, &zo);
+  for (int k = 0; k <= 2; ++k) out_begin[k] = zo.begin[k];
+  if (rc != CM_OK) return rc;
+  const int64_t total = zo.begin[2];
+  if (total > capacity) return fail(h, CM_E_CAPACITY, "%lld points, caller capacity %lld", (long long)total, (long long)capacity);
+  if (out_xyzi && total) CM_CUDA(h, cudaMemcpy(out_xyzi, zo.xyzi, (size_t)total * 16, cudaMemcpyDeviceToHost));
+  if (out_idx && total) CM_CUDA(h, cudaMemcpy(out_idx, zo.src, (size_t)total * 4, cudaMemcpyDeviceToHost));
   return CM_OK;
 }
 

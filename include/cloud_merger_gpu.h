@@ -86,6 +86,30 @@ typedef struct {
   int32_t reserved;
 } cm_zone_out_t;
 
+/* RANSAC ground plane: the pcl::SACSegmentation settings of removeGround() (pc_preprocessing_main.cpp:95-108) */
+#define CM_SUM4_SSE2 0   /* Eigen packet reductions as an SSE2 build does them: (l0+l2)+(l1+l3) */
+#define CM_SUM4_SSE3 1   /* SSE3 and later (haddps): (l0+l1)+(l2+l3) */
+#define CM_SUM4_SCALAR 2 /* no vectorisation: ((l0+l1)+l2)+l3 */
+typedef struct {
+  double distance_threshold; /* seg.setDistanceThreshold (Parameter.h:40: 0.3f) */
+  double probability;        /* seg.setProbability (Parameter.h:41: 0.99f) */
+  int32_t max_iterations;    /* seg.setMaxIterations (Parameter.h:38: 1000) */
+  int32_t optimize;          /* seg.setOptimizeCoefficients (true in the reference) */
+  uint32_t seed;             /* 12345 = PCL's sampler (SampleConsensusModel with random == false) */
+  int32_t sum_order;         /* CM_SUM4_* */
+} cm_plane_cfg_t;
+typedef struct {
+  int32_t found;        /* 0: segment() failed (fewer than 3 points / no good sample): no inliers */
+  int32_t iterations;   /* RandomSampleConsensus iterations_ at exit */
+  int32_t draws;        /* three-index draws taken from the sampler (>= iterations: bad samples are redrawn) */
+  int32_t best_count;   /* inliers of the RANSAC model */
+  int32_t sample[3];    /* the three point indices it was fitted through */
+  int32_t reserved;
+  float coeff_ransac[4]; /* sac_->getModelCoefficients */
+  float coeff[4];        /* what segment() returns: the least-squares refit when optimize != 0 */
+  int64_t n_inliers;     /* inliers->indices.size() */
+} cm_plane_t;
+
 /* ---- layout of one incoming sensor cloud ----
  * Replaces: the sensor_msgs/PointCloud2 -> pcl::PointCloud<pcl::PointXYZI> deserialisation done by the pcl_ros
  * subscriber (pc_preprocessing_main.cpp:520-525, CloudFusionNode.h:51-56): data[], point_step and the byte offsets of the
@@ -269,6 +293,21 @@ CM_API int cm_dev_radius_outlier(cm_handle_t h, const float* xyzi_dev, int64_t n
                                  int min_neighbors, int negative, void* stream);
 CM_API int cm_radius_outlier(cm_handle_t h, const float* xyzi_host, int64_t n_points, double radius, int min_neighbors,
                              int negative, float* out_xyzi, uint32_t* out_idx, int64_t capacity, int64_t* n_out);
+/* RANSAC ground plane. Replaces the pcl::SACSegmentation + pcl::ExtractIndices block of removeGround()
+ * (pc_preprocessing_main.cpp:95-117): SACMODEL_PLANE, SAC_RANSAC (setAxis / setEpsAngle are ignored by that model, as in
+ * PCL). The three-index draws are PCL 1.8.1's -- boost::mt19937 seeded with cfg->seed, uniform_int<>(0, INT_MAX), the
+ * partial shuffle of drawIndexSample -- and are scored on the GPU a batch at a time; the host applies PCL's stopping rule
+ * to the batch in draw order, so model, iteration count and inliers are those of PCL's sequential loop. With optimize the
+ * least-squares refit follows (float running sums in inlier order as computeMeanAndCovarianceMatrix forms them, pcl::eigen33
+ * on the host) and the inliers are selected again.
+ *  cm_dev_plane_ransac: n packed float4 xyzi points on the device; blocks until the model is known. Results: *out, and
+ *      through cm_get_zone_out two zones in input order -- zone 0 the inliers (ground_cloud), zone 1 the rest
+ *      (no_ground_cloud before outlierRemoval), src = index in the input.
+ *  cm_plane_ransac: host buffers; out_begin receives 3 offsets (inliers = [0, out_begin[1]), rest up to out_begin[2]). */
+CM_API int cm_dev_plane_ransac(cm_handle_t h, const float* xyzi_dev, int64_t n_points, const cm_plane_cfg_t* cfg,
+                               cm_plane_t* out, void* stream);
+CM_API int cm_plane_ransac(cm_handle_t h, const float* xyzi_host, int64_t n_points, const cm_plane_cfg_t* cfg,
+                           cm_plane_t* out, float* out_xyzi, uint32_t* out_idx, int64_t capacity, int64_t* out_begin);
 /* ---- single giant cloud over several GPUs (BASELINE config 4): device-side pieces of the voxel-key range partition ----
  * The reference has no counterpart (one process). Every rank holds a block of the cloud; all ranks must build the SAME
  * voxel grid, a voxel must not straddle ranks, and the rank outputs concatenated in rank order must be PCL's order:

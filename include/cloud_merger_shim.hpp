@@ -9,6 +9,8 @@
 //   proceedX: getCloudPart x5 + the z windows of removeGround                 ->  getCloudPartsZSplit (one GPU pass)
 //   void fusePointclouds(Cloud::Ptr no_ground, Cloud::Ptr ground)             ->  FusedFrame::fuse (+ operator+= kept)
 //   void outlierRemoval(Cloud::Ptr)                                           ->  outlierRemoval(cloud)
+//   void removeGround(cloud, no_ground, ground, z_min, z_max, max_angle)      ->  removeGround(...) (z windows + RANSAC
+//                                                                                 plane + ExtractIndices + outlierRemoval)
 //   void voxelgrid(const Cloud::Ptr, Cloud::Ptr)                              ->  voxelgrid(in, out)
 //   callbackX(const Cloud input) ... main loop fuse + voxelgrid               ->  FusedFrame::onCloud / fuseAndVoxel
 //
@@ -91,6 +93,11 @@ struct Params {
   float roi_width = 10.0f, roi_length = 75.0f, roi_mid = 15.0f, roi_z_min = -0.5f, roi_z_max = 3.0f;
   float radius = 0.15f;      // outlier removal: radius [m] and minimum number of neighbours (Parameter.h:23-24)
   float min_neighbor = 1;
+  // RANSAC ground plane (Parameter.h:38-42); sum_order: the instruction set the PCL binary being replaced was built for
+  int max_iterations = 1000;
+  float distance_threshold = 0.3f;
+  float prob = 0.99f;
+  int sum_order = CM_SUM4_SSE2;
 };
 
 inline cm_layout_t pcl_layout(bool is_dense) {
@@ -210,6 +217,45 @@ class Context {
     }
     finish(res, in, true);
     out = res;
+    return true;
+  }
+
+  // RANSAC ground plane of ONE host cloud (cm_plane_ransac): pcl::SACSegmentation (SACMODEL_PLANE, SAC_RANSAC, optimize
+  // on) + the two pcl::ExtractIndices passes; ground = the inliers, no_ground = the rest, both in input order.
+  bool plane_ransac(const Cloud& in, Cloud& ground, Cloud& no_ground, cm_plane_t* model = nullptr) {
+    clear(ground); clear(no_ground);
+    if (!check(h_ ? CM_OK : CM_E_NO_DEVICE)) return false;
+    const int64_t n = static_cast<int64_t>(in.points.size());
+    if (n > max_points_ * max_sensors_) { rc_ = CM_E_CAPACITY; err_ = "cloud larger than the context capacity"; return false; }
+    tmp_.resize(static_cast<size_t>(n) * 4);
+    for (int64_t i = 0; i < n; ++i) {
+      const PointXYZI& p = in.points[static_cast<size_t>(i)];
+      tmp_[i * 4 + 0] = p.x; tmp_[i * 4 + 1] = p.y; tmp_[i * 4 + 2] = p.z; tmp_[i * 4 + 3] = p.intensity;
+    }
+    cm_plane_cfg_t cfg;
+    cfg.distance_threshold = static_cast<double>(params_.distance_threshold);
+    cfg.probability = static_cast<double>(params_.prob);
+    cfg.max_iterations = params_.max_iterations;
+    cfg.optimize = 1;
+    cfg.seed = 12345u;
+    cfg.sum_order = params_.sum_order;
+    cm_plane_t pl;
+    int64_t begin[3] = {0, 0, 0};
+    zone_xyzi_.resize(static_cast<size_t>(n) * 4 + 4);
+    if (!check(cm_plane_ransac(h_, tmp_.data(), n, &cfg, &pl, zone_xyzi_.data(), nullptr, n, begin))) return false;
+    if (model) *model = pl;
+    Cloud* outs[2] = {&ground, &no_ground};
+    for (int z = 0; z < 2; ++z) {
+      Cloud& c = *outs[z];
+      const size_t b = static_cast<size_t>(begin[z]), e = static_cast<size_t>(begin[z + 1]);
+      c.points.resize(e - b);
+      for (size_t i = b; i < e; ++i) {
+        PointXYZI& p = c.points[i - b];
+        p = PointXYZI();
+        p.x = zone_xyzi_[i * 4 + 0]; p.y = zone_xyzi_[i * 4 + 1]; p.z = zone_xyzi_[i * 4 + 2]; p.intensity = zone_xyzi_[i * 4 + 3];
+      }
+      finish(c, in, in.is_dense);
+    }
     return true;
   }
 
@@ -362,6 +408,26 @@ inline void outlierRemoval(Context& ctx, const Cloud::Ptr& cloud_ptr) {
   Cloud tmp;
   ctx.radius_outlier(*cloud_ptr, tmp, static_cast<double>(ctx.params().radius), static_cast<int>(ctx.params().min_neighbor));
   *cloud_ptr = tmp;
+}
+
+// void removeGround(cloud, no_ground, ground, z_min_ground, z_max_ground, max_angle) -- :71-122, the whole function: the two
+// z windows (one zone-slicing pass), the RANSAC plane on the lower one + ExtractIndices, outlierRemoval of what is not
+// ground, and the points above the window appended. max_angle is accepted and unused, as in the reference (SACMODEL_PLANE
+// ignores setAxis / setEpsAngle).
+inline void removeGround(Context& ctx, const Cloud::Ptr& cloud_ptr, const Cloud::Ptr& no_ground_cloud_ptr,
+                         const Cloud::Ptr& ground_cloud_ptr, const float z_min_ground, const float z_max_ground,
+                         const float /*max_angle*/) {
+  std::vector<cm_zone_t> zones(2);
+  zones[0].n_pass = 1; zones[0].pass[0] = cm_pass_t{2, z_min_ground, z_max_ground, 0};
+  zones[1].n_pass = 1; zones[1].pass[0] = cm_pass_t{2, static_cast<float>(z_max_ground + 0.01), ctx.params().roi_z_max, 0};
+  std::vector<Cloud> parts;
+  ctx.zone_split(*cloud_ptr, zones, parts);
+  Cloud ground, no_ground;
+  ctx.plane_ransac(parts[0], ground, no_ground);
+  *ground_cloud_ptr = ground;
+  *no_ground_cloud_ptr = no_ground;
+  outlierRemoval(ctx, no_ground_cloud_ptr);
+  *no_ground_cloud_ptr += parts[1];
 }
 
 // void voxelgrid(const Cloud::Ptr cloud_ptr, Cloud::Ptr voxel_cloud_ptr) -- :168-177

@@ -516,6 +516,292 @@ int64_t cmo_radius_outlier(const float* xyzi, int64_t n, double radius, int32_t 
   return kept;
 }
 
+/* ---- RANSAC ground plane: pcl::SACSegmentation<PointXYZI> with SACMODEL_PLANE / SAC_RANSAC --------------------------
+ * Reference call site: pc_preprocessing_main.cpp:95-117 (setOptimizeCoefficients(true), setMaxIterations(1000),
+ * setDistanceThreshold(0.3f), setProbability(0.99f); setAxis / setEpsAngle are set there but SACMODEL_PLANE ignores
+ * them), followed by pcl::ExtractIndices with the inliers (negative and positive). Parameters: Parameter.h:38-42.
+ * Restated from PCL 1.8.1 (sample_consensus/{sac_model.h, impl/sac_model_plane.hpp, impl/ransac.hpp},
+ * segmentation/impl/sac_segmentation.hpp, common/impl/{centroid,eigen}.hpp), Eigen 3.3.4 and Boost.Random:
+ *
+ *  sampler   SampleConsensusModel with random == false seeds boost::mt19937 with 12345 and draws through
+ *            boost::uniform_int<>(0, INT_MAX), which maps the 32-bit engine output to out >> 1. drawIndexSample swaps
+ *            shuffled_indices_[i] with shuffled_indices_[i + rnd() % (n - i)] for i = 0, 1, 2 (the array persists over
+ *            the draws of one segment() call) and takes the first three entries. getSamples repeats the draw (at most
+ *            max_sample_checks_ = 1000 times) until isSampleGood: ((p1-p0)/(p2-p0)) has unequal x, y, z quotients.
+ *  model     cross product of (p1-p0) and (p2-p0), Eigen 3.3 normalize() (divides by sqrt(squaredNorm) iff that is > 0),
+ *            d = -1 * dot(n, p0).
+ *  score     countWithinDistance: |dot((a,b,c,d), (x,y,z,1))| < threshold, strict.
+ *  loop      RandomSampleConsensus::computeModel: k = log(1 - p) / log(1 - w^3) is lowered at every new best model,
+ *            the loop ends when iterations >= k or iterations > max_iterations.
+ *  refine    optimizeModelCoefficients: float running sums of xx, xy, xz, yy, yz, zz, x, y, z over the inliers in index
+ *            order, / n, covariance = E[ab] - E[a]E[b], pcl::eigen33 (closed-form smallest eigenvalue in float, eigenvector
+ *            from the largest row cross product), d = -1 * dot(n, centroid); then selectWithinDistance once more.
+ *
+ * The 4-wide float dot products / squared norms are Eigen packet reductions whose order depends on the instruction set
+ * PCL was built for; sum_order selects it: 0 = SSE2 (movehl + shuffle): (l0+l2)+(l1+l3); 1 = SSE3 (haddps):
+ * (l0+l1)+(l2+l3); 2 = scalar: ((l0+l1)+l2)+l3. */
+namespace {
+struct Mt19937 {
+  uint32_t s[624];
+  int at;
+  explicit Mt19937(uint32_t seed) {
+    s[0] = seed;
+    for (int i = 1; i < 624; ++i) s[i] = 1812433253u * (s[i - 1] ^ (s[i - 1] >> 30)) + static_cast<uint32_t>(i);
+    at = 624;
+  }
+  void refill() {
+    for (int i = 0; i < 624; ++i) {
+      const uint32_t y = (s[i] & 0x80000000u) | (s[(i + 1) % 624] & 0x7fffffffu);
+      s[i] = s[(i + 397) % 624] ^ (y >> 1) ^ ((y & 1u) ? 0x9908b0dfu : 0u);
+    }
+    at = 0;
+  }
+  uint32_t next() {
+    if (at >= 624) refill();
+    uint32_t y = s[at++];
+    y ^= y >> 11;
+    y ^= (y << 7) & 0x9d2c5680u;
+    y ^= (y << 15) & 0xefc60000u;
+    y ^= y >> 18;
+    return y;
+  }
+};
+
+inline float sum4(float l0, float l1, float l2, float l3, int order) {
+  if (order == 0) return (l0 + l2) + (l1 + l3);
+  if (order == 1) return (l0 + l1) + (l2 + l3);
+  return ((l0 + l1) + l2) + l3;
+}
+
+inline bool plane_sample_good(const float* p0, const float* p1, const float* p2) {
+  float q[3];
+  for (int a = 0; a < 3; ++a) q[a] = (p1[a] - p0[a]) / (p2[a] - p0[a]);
+  return (q[0] != q[1]) || (q[2] != q[1]);
+}
+
+inline void plane_from_sample(const float* p0, const float* p1, const float* p2, int order, float* c) {
+  float u[3], v[3];
+  for (int a = 0; a < 3; ++a) { u[a] = p1[a] - p0[a]; v[a] = p2[a] - p0[a]; }
+  c[0] = u[1] * v[2] - u[2] * v[1];
+  c[1] = u[2] * v[0] - u[0] * v[2];
+  c[2] = u[0] * v[1] - u[1] * v[0];
+  c[3] = 0.0f;
+  const float z = sum4(c[0] * c[0], c[1] * c[1], c[2] * c[2], c[3] * c[3], order);
+  if (z > 0.0f) {
+    const float nrm = std::sqrt(z);
+    for (int a = 0; a < 4; ++a) c[a] = c[a] / nrm;
+  }
+  c[3] = -1.0f * sum4(c[0] * p0[0], c[1] * p0[1], c[2] * p0[2], c[3] * 1.0f, order);
+}
+
+inline float plane_distance(const float* c, const float* p, int order) {
+  return std::fabs(sum4(c[0] * p[0], c[1] * p[1], c[2] * p[2], c[3] * 1.0f, order));
+}
+
+/* pcl::computeRoots2 / computeRoots / eigen33 (smallest eigenvalue form), Scalar = float */
+void roots2(float b, float c, float* r) {
+  r[0] = 0.0f;
+  float d = static_cast<float>(b * b - 4.0 * c);
+  if (d < 0.0) d = 0.0f;
+  const float sd = std::sqrt(d);
+  r[2] = 0.5f * (b + sd);
+  r[1] = 0.5f * (b - sd);
+}
+
+void roots3(const float m[3][3], float* r) {
+  const float c0 = m[0][0] * m[1][1] * m[2][2] + 2.0f * m[0][1] * m[0][2] * m[1][2] - m[0][0] * m[1][2] * m[1][2] -
+                   m[1][1] * m[0][2] * m[0][2] - m[2][2] * m[0][1] * m[0][1];
+  const float c1 = m[0][0] * m[1][1] - m[0][1] * m[0][1] + m[0][0] * m[2][2] - m[0][2] * m[0][2] + m[1][1] * m[2][2] -
+                   m[1][2] * m[1][2];
+  const float c2 = m[0][0] + m[1][1] + m[2][2];
+  if (std::fabs(c0) < std::numeric_limits<float>::epsilon()) {
+    roots2(c2, c1, r);
+    return;
+  }
+  const float s_inv3 = static_cast<float>(1.0 / 3.0);
+  const float s_sqrt3 = std::sqrt(3.0f);
+  const float c2_over_3 = c2 * s_inv3;
+  float a_over_3 = (c1 - c2 * c2_over_3) * s_inv3;
+  if (a_over_3 > 0.0f) a_over_3 = 0.0f;
+  const float half_b = 0.5f * (c0 + c2_over_3 * (2.0f * c2_over_3 * c2_over_3 - c1));
+  float q = half_b * half_b + a_over_3 * a_over_3 * a_over_3;
+  if (q > 0.0f) q = 0.0f;
+  const float rho = std::sqrt(-a_over_3);
+  const float theta = std::atan2(std::sqrt(-q), half_b) * s_inv3;
+  const float cos_theta = std::cos(theta);
+  const float sin_theta = std::sin(theta);
+  r[0] = c2_over_3 + 2.0f * rho * cos_theta;
+  r[1] = c2_over_3 - rho * (cos_theta + s_sqrt3 * sin_theta);
+  r[2] = c2_over_3 - rho * (cos_theta - s_sqrt3 * sin_theta);
+  if (r[0] >= r[1]) std::swap(r[0], r[1]);
+  if (r[1] >= r[2]) {
+    std::swap(r[1], r[2]);
+    if (r[0] >= r[1]) std::swap(r[0], r[1]);
+  }
+  if (r[0] <= 0.0f) roots2(c2, c1, r);
+}
+
+void smallest_eigenvector(const float cov[3][3], float* vec) {
+  float scale = 0.0f;
+  for (int i = 0; i < 3; ++i)
+    for (int j = 0; j < 3; ++j) scale = std::max(scale, std::fabs(cov[i][j]));
+  if (scale <= std::numeric_limits<float>::min()) scale = 1.0f;
+  float m[3][3];
+  for (int i = 0; i < 3; ++i)
+    for (int j = 0; j < 3; ++j) m[i][j] = cov[i][j] / scale;
+  float r[3];
+  roots3(m, r);
+  for (int i = 0; i < 3; ++i) m[i][i] -= r[0];
+  auto cross = [](const float* a, const float* b, float* o) {
+    o[0] = a[1] * b[2] - a[2] * b[1];
+    o[1] = a[2] * b[0] - a[0] * b[2];
+    o[2] = a[0] * b[1] - a[1] * b[0];
+  };
+  float v1[3], v2[3], v3[3];
+  cross(m[0], m[1], v1);
+  cross(m[0], m[2], v2);
+  cross(m[1], m[2], v3);
+  auto sq = [](const float* a) { return a[0] * a[0] + a[1] * a[1] + a[2] * a[2]; };
+  const float l1 = sq(v1), l2 = sq(v2), l3 = sq(v3);
+  const float* best = v3;
+  float len = l3;
+  if (l1 >= l2 && l1 >= l3) { best = v1; len = l1; }
+  else if (l2 >= l1 && l2 >= l3) { best = v2; len = l2; }
+  const float s = std::sqrt(len);
+  for (int a = 0; a < 3; ++a) vec[a] = best[a] / s;
+}
+}  // namespace
+
+/* Known-answer hook for the sampler: the i-th output (0-based) of mt19937 seeded with `seed`. */
+uint32_t cmo_mt19937_at(uint32_t seed, int64_t i) {
+  Mt19937 g(seed);
+  uint32_t v = 0;
+  for (int64_t k = 0; k <= i; ++k) v = g.next();
+  return v;
+}
+
+/* Scores one externally given sample (three indices): coeff[4], returns the inlier count or -1 for a bad sample. */
+int64_t cmo_plane_score(const float* xyzi, int64_t n, const int32_t* sample, double threshold, int32_t sum_order,
+                        float* coeff) {
+  const float *p0 = xyzi + 4 * static_cast<int64_t>(sample[0]), *p1 = xyzi + 4 * static_cast<int64_t>(sample[1]),
+              *p2 = xyzi + 4 * static_cast<int64_t>(sample[2]);
+  if (!plane_sample_good(p0, p1, p2)) return -1;
+  plane_from_sample(p0, p1, p2, sum_order, coeff);
+  int64_t cnt = 0;
+  for (int64_t i = 0; i < n; ++i)
+    if (plane_distance(coeff, xyzi + 4 * i, sum_order) < threshold) ++cnt;
+  return cnt;
+}
+
+/* The whole segment() call. out_info: [0] found, [1] iterations, [2] draws taken from the sampler, [3] inlier count of
+ * the best RANSAC model, [4..6] its sample. coeff_ransac / coeff_out: the RANSAC model and what segment() returns
+ * (refined when optimize != 0). out_inliers [n]: the final inlier indices, ascending. Returns their number (0 when no
+ * model was found). */
+int64_t cmo_plane_ransac(const float* xyzi, int64_t n, double threshold, double probability, int32_t max_iterations,
+                         int32_t optimize, uint32_t seed, int32_t sum_order, int32_t* out_info, float* coeff_ransac,
+                         float* coeff_out, int32_t* out_inliers) {
+  int32_t info[7] = {0, 0, 0, 0, -1, -1, -1};
+  auto finish = [&](int64_t k) {
+    if (out_info) std::memcpy(out_info, info, sizeof(info));
+    return k;
+  };
+  if (n < 3) return finish(0);
+  std::vector<int32_t> shuffled(static_cast<size_t>(n));
+  for (int64_t i = 0; i < n; ++i) shuffled[i] = static_cast<int32_t>(i);
+  Mt19937 rng(seed);
+  int iterations = 0, draws = 0;
+  int64_t best = -std::numeric_limits<int>::max();
+  double k = 1.0;
+  const double log_probability = std::log(1.0 - probability);
+  const double one_over_indices = 1.0 / static_cast<double>(n);
+  float best_c[4] = {0, 0, 0, 0};
+  bool have = false;
+  while (iterations < k) {
+    int32_t sel[3];
+    bool got = false;
+    for (int check = 0; check < 1000 && !got; ++check) {
+      for (int64_t i = 0; i < 3; ++i) {
+        const int32_t r = static_cast<int32_t>(rng.next() >> 1);
+        std::swap(shuffled[i], shuffled[i + static_cast<int64_t>(static_cast<uint64_t>(r) % static_cast<uint64_t>(n - i))]);
+      }
+      ++draws;
+      sel[0] = shuffled[0]; sel[1] = shuffled[1]; sel[2] = shuffled[2];
+      got = plane_sample_good(xyzi + 4 * static_cast<int64_t>(sel[0]), xyzi + 4 * static_cast<int64_t>(sel[1]),
+                              xyzi + 4 * static_cast<int64_t>(sel[2]));
+    }
+    if (!got) break;
+    float c[4];
+    plane_from_sample(xyzi + 4 * static_cast<int64_t>(sel[0]), xyzi + 4 * static_cast<int64_t>(sel[1]),
+                      xyzi + 4 * static_cast<int64_t>(sel[2]), sum_order, c);
+    int64_t cnt = 0;
+    for (int64_t i = 0; i < n; ++i)
+      if (plane_distance(c, xyzi + 4 * i, sum_order) < threshold) ++cnt;
+    if (cnt > best) {
+      best = cnt;
+      have = true;
+      std::memcpy(best_c, c, sizeof(c));
+      info[3] = static_cast<int32_t>(cnt);
+      info[4] = sel[0]; info[5] = sel[1]; info[6] = sel[2];
+      const double w = static_cast<double>(best) * one_over_indices;
+      double p_no_outliers = 1.0 - std::pow(w, 3.0);
+      p_no_outliers = std::max(std::numeric_limits<double>::epsilon(), p_no_outliers);
+      p_no_outliers = std::min(1.0 - std::numeric_limits<double>::epsilon(), p_no_outliers);
+      k = log_probability / std::log(p_no_outliers);
+    }
+    ++iterations;
+    if (iterations > max_iterations) break;
+  }
+  info[1] = iterations;
+  info[2] = draws;
+  if (!have) return finish(0);
+  info[0] = 1;
+  if (coeff_ransac) std::memcpy(coeff_ransac, best_c, sizeof(best_c));
+  std::vector<int32_t> inl;
+  auto select = [&](const float* c) {
+    inl.clear();
+    for (int64_t i = 0; i < n; ++i)
+      if (plane_distance(c, xyzi + 4 * i, sum_order) < threshold) inl.push_back(static_cast<int32_t>(i));
+  };
+  select(best_c);
+  float fin_c[4];
+  std::memcpy(fin_c, best_c, sizeof(fin_c));
+  if (optimize) {
+    if (inl.size() >= 4) {
+      float acc[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+      for (int32_t i : inl) {
+        const float* p = xyzi + 4 * static_cast<int64_t>(i);
+        acc[0] += p[0] * p[0];
+        acc[1] += p[0] * p[1];
+        acc[2] += p[0] * p[2];
+        acc[3] += p[1] * p[1];
+        acc[4] += p[1] * p[2];
+        acc[5] += p[2] * p[2];
+        acc[6] += p[0];
+        acc[7] += p[1];
+        acc[8] += p[2];
+      }
+      const float cnt = static_cast<float>(inl.size());
+      for (int a = 0; a < 9; ++a) acc[a] = acc[a] / cnt;
+      float cov[3][3];
+      cov[0][0] = acc[0] - acc[6] * acc[6];
+      cov[0][1] = acc[1] - acc[6] * acc[7];
+      cov[0][2] = acc[2] - acc[6] * acc[8];
+      cov[1][1] = acc[3] - acc[7] * acc[7];
+      cov[1][2] = acc[4] - acc[7] * acc[8];
+      cov[2][2] = acc[5] - acc[8] * acc[8];
+      cov[1][0] = cov[0][1]; cov[2][0] = cov[0][2]; cov[2][1] = cov[1][2];
+      float v[3];
+      smallest_eigenvector(cov, v);
+      fin_c[0] = v[0]; fin_c[1] = v[1]; fin_c[2] = v[2];
+      fin_c[3] = -1.0f * sum4(v[0] * acc[6], v[1] * acc[7], v[2] * acc[8], 0.0f * 1.0f, sum_order);
+    }
+    select(fin_c);
+  }
+  if (coeff_out) std::memcpy(coeff_out, fin_c, sizeof(fin_c));
+  if (out_inliers) std::memcpy(out_inliers, inl.data(), inl.size() * sizeof(int32_t));
+  return finish(static_cast<int64_t>(inl.size()));
+}
+
 const char* cmo_version(void) { return "cm_oracle 1 (PCL 1.8.1 restatement; parity unpinned)"; }
 
 }  // extern "C"

@@ -100,6 +100,20 @@ int64_t cmo_merge_frame(const cmo_cloud_t* clouds, int32_t n_clouds, const cmo_p
 int64_t cmo_radius_outlier(const float* xyzi, int64_t n, double radius, int32_t min_pts, int32_t negative,
                            int32_t* out_indices);
 
+/* RANSAC ground plane: pcl::SACSegmentation<PointXYZI>, SACMODEL_PLANE + SAC_RANSAC, as removeGround() configures it
+ * (pc_preprocessing_main.cpp:95-108; Parameter.h:38-42), restated from PCL 1.8.1 / Eigen 3.3.4 / Boost.Random (see the
+ * block comment in cm_oracle.cpp). sum_order: order of Eigen's 4-wide float reductions, 0 = SSE2, 1 = SSE3, 2 = scalar.
+ *  cmo_mt19937_at     i-th output of the sampler's engine (known-answer hook);
+ *  cmo_plane_score    one externally given sample: coefficients + inlier count (-1: rejected by isSampleGood);
+ *  cmo_plane_ransac   the whole segment() call; out_info[7] = found, iterations, draws, best count, best sample[3];
+ *                     out_inliers = the indices pcl::ExtractIndices is then given (ascending). Returns their number. */
+uint32_t cmo_mt19937_at(uint32_t seed, int64_t i);
+int64_t cmo_plane_score(const float* xyzi, int64_t n, const int32_t* sample, double threshold, int32_t sum_order,
+                        float* coeff);
+int64_t cmo_plane_ransac(const float* xyzi, int64_t n, double threshold, double probability, int32_t max_iterations,
+                         int32_t optimize, uint32_t seed, int32_t sum_order, int32_t* out_info, float* coeff_ransac,
+                         float* coeff_out, int32_t* out_inliers);
+
 /* Eigen 3.3.4 Quaternionf::toRotationMatrix + Translation, as pcl_ros builds the Affine3f from a tf::Transform
  * (double quaternion xyzw + origin narrowed to float). Writes 12 floats row-major. Host glue, kept here so the tests can
  * pin it too. */

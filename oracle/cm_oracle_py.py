@@ -80,6 +80,40 @@ def radius_outlier(xyzi: np.ndarray, radius: float, min_pts: int, negative: bool
     return idx[:k].copy()
 
 
+def mt19937_at(seed: int, i: int) -> int:
+    f = lib().cmo_mt19937_at
+    f.restype = C.c_uint32
+    return int(f(C.c_uint32(seed), C.c_int64(i)))
+
+
+def plane_score(xyzi: np.ndarray, sample, threshold: float, sum_order: int = 0):
+    """One RANSAC hypothesis (three point indices): (coefficients [4] float32, inlier count or -1 for a bad sample)."""
+    xyzi = np.ascontiguousarray(xyzi, np.float32).reshape(-1, 4)
+    smp = np.ascontiguousarray(sample, np.int32)
+    coeff = np.zeros(4, np.float32)
+    f = lib().cmo_plane_score
+    f.restype = C.c_int64
+    k = f(_p(xyzi), C.c_int64(len(xyzi)), _p(smp), C.c_double(threshold), int(sum_order), _p(coeff))
+    return coeff, int(k)
+
+
+def plane_ransac(xyzi: np.ndarray, threshold: float, probability: float = 0.99, max_iterations: int = 1000,
+                 optimize: bool = True, seed: int = 12345, sum_order: int = 0) -> dict:
+    """pcl::SACSegmentation (SACMODEL_PLANE, SAC_RANSAC) as removeGround() runs it (pc_preprocessing_main.cpp:95-108)."""
+    xyzi = np.ascontiguousarray(xyzi, np.float32).reshape(-1, 4)
+    n = len(xyzi)
+    info = np.zeros(7, np.int32)
+    c_r = np.zeros(4, np.float32)
+    c_o = np.zeros(4, np.float32)
+    inl = np.empty(max(n, 1), np.int32)
+    f = lib().cmo_plane_ransac
+    f.restype = C.c_int64
+    k = f(_p(xyzi), C.c_int64(n), C.c_double(threshold), C.c_double(probability), int(max_iterations), int(bool(optimize)),
+          C.c_uint32(seed), int(sum_order), _p(info), _p(c_r), _p(c_o), _p(inl))
+    return {"found": bool(info[0]), "iterations": int(info[1]), "draws": int(info[2]), "best_count": int(info[3]),
+            "sample": info[4:7].copy(), "coeff_ransac": c_r, "coeff": c_o, "inliers": inl[:k].copy()}
+
+
 def zone_split(xyzi: np.ndarray, zones) -> list:
     """The reference's per-zone sequence, literally: for every zone run its PassThrough stages one after the other, each
     on the cloud the previous one copied out (getCloudPart followed by the z window of removeGround,

@@ -139,3 +139,83 @@ def merge_frame(clouds, passes, leaf, min_points=0, downsample_all=True, force64
     sx = np.concatenate(surv) if surv else np.zeros((0, 4), F32)
     ss = np.concatenate(src).astype(np.uint32) if src else np.zeros(0, np.uint32)
     return dict(survivor_xyzi=sx, survivor_src=ss, voxel=voxelgrid(sx, leaf, min_points, downsample_all, force64))
+
+
+# ---- RANSAC ground plane (pcl::SACSegmentation, SACMODEL_PLANE + SAC_RANSAC; pc_preprocessing_main.cpp:95-108) ------------
+def _sum4(l0, l1, l2, l3, order: int):
+    """Eigen's 4-wide float reduction: 0 = SSE2 (l0+l2)+(l1+l3), 1 = SSE3 (l0+l1)+(l2+l3), 2 = scalar ((l0+l1)+l2)+l3."""
+    l0, l1, l2, l3 = (np.asarray(v, F32) for v in (l0, l1, l2, l3))
+    if order == 0:
+        return ((l0 + l2).astype(F32) + (l1 + l3).astype(F32)).astype(F32)
+    if order == 1:
+        return ((l0 + l1).astype(F32) + (l2 + l3).astype(F32)).astype(F32)
+    return (((l0 + l1).astype(F32) + l2).astype(F32) + l3).astype(F32)
+
+
+def plane_of_sample(p0, p1, p2, order: int = 0):
+    """isSampleGood + computeModelCoefficients of SampleConsensusModelPlane: (good, coefficients[4] float32)."""
+    p0, p1, p2 = (np.asarray(v, F32)[:3] for v in (p0, p1, p2))
+    with np.errstate(all="ignore"):
+        u = (p1 - p0).astype(F32)
+        v = (p2 - p0).astype(F32)
+        q = (u / v).astype(F32)
+        good = bool(q[0] != q[1]) or bool(q[2] != q[1])
+        c = np.zeros(4, F32)
+        c[0] = F32(F32(u[1] * v[2]) - F32(u[2] * v[1]))
+        c[1] = F32(F32(u[2] * v[0]) - F32(u[0] * v[2]))
+        c[2] = F32(F32(u[0] * v[1]) - F32(u[1] * v[0]))
+        z = _sum4(c[0] * c[0], c[1] * c[1], c[2] * c[2], c[3] * c[3], order)
+        if z > 0:
+            c = (c / np.sqrt(z, dtype=F32)).astype(F32)
+        c[3] = F32(-1.0) * _sum4(c[0] * p0[0], c[1] * p0[1], c[2] * p0[2], c[3] * F32(1.0), order)
+    return good, c
+
+
+def plane_inlier_mask(xyzi: np.ndarray, c: np.ndarray, threshold: float, order: int = 0) -> np.ndarray:
+    """countWithinDistance / selectWithinDistance: |dot(c, (x, y, z, 1))| < threshold (float distance, double threshold)."""
+    x = np.asarray(xyzi, F32)
+    with np.errstate(all="ignore"):
+        d = np.abs(_sum4(c[0] * x[:, 0], c[1] * x[:, 1], c[2] * x[:, 2], np.broadcast_to(c[3], x[:, 0].shape), order))
+        return d.astype(np.float64) < float(threshold)
+
+
+def plane_ransac(xyzi: np.ndarray, threshold: float, probability: float = 0.99, max_iterations: int = 1000,
+                 seed: int = 12345, order: int = 0) -> dict:
+    """RandomSampleConsensus::computeModel with PCL's sampler (mt19937(seed) >> 1, partial shuffle); no refit."""
+    x = np.ascontiguousarray(xyzi, F32).reshape(-1, 4)
+    n = len(x)
+    out = {"found": False, "iterations": 0, "draws": 0, "best_count": 0, "sample": np.full(3, -1, np.int32), "coeff": np.zeros(4, F32)}
+    if n < 3:
+        return out
+    raw = np.random.RandomState(seed)._bit_generator  # init_genrand(seed), as boost::mt19937::seed(value)
+    shuffled = np.arange(n, dtype=np.int64)
+    iterations, draws, best, k = 0, 0, -INT32_MAX, 1.0
+    log_p = np.log(1.0 - probability)
+    while iterations < k:
+        got = False
+        for _ in range(1000):
+            for i in range(3):
+                r = int(raw.random_raw()) >> 1
+                j = i + r % (n - i)
+                shuffled[i], shuffled[j] = shuffled[j], shuffled[i]
+            draws += 1
+            sel = shuffled[:3].copy()
+            good, c = plane_of_sample(x[sel[0]], x[sel[1]], x[sel[2]], order)
+            if good:
+                got = True
+                break
+        if not got:
+            break
+        cnt = int(plane_inlier_mask(x, c, threshold, order).sum())
+        if cnt > best:
+            best = cnt
+            out.update(found=True, best_count=cnt, sample=sel.astype(np.int32), coeff=c.copy())
+            w = best / n
+            p_no = 1.0 - w ** 3.0
+            p_no = min(max(np.finfo(np.float64).eps, p_no), 1.0 - np.finfo(np.float64).eps)
+            k = log_p / np.log(p_no)
+        iterations += 1
+        if iterations > max_iterations:
+            break
+    out.update(iterations=iterations, draws=draws)
+    return out

@@ -174,6 +174,43 @@ int main() {
       expect_cloud(*filtered, want, static_cast<size_t>(k), "outlierRemoval");
       CHECK(k > 100 && k < n_roi, "outlierRemoval removes some but not all points (%lld of %lld kept)", (long long)k, (long long)n_roi);
     }
+    // removeGround(cloud, no_ground, ground, z_min, z_max, max_angle) -- :71-122 -- on the whole ROI cloud of this sensor
+    {
+      Cloud::Ptr no_ground(new Cloud), ground(new Cloud);
+      const float zg = 0.4f;
+      removeGround(ctx, roi_ptr, no_ground, ground, -zg, zg, 0.05f);
+      const int64_t n_roi = static_cast<int64_t>(roi_o.size() / 4);
+      std::vector<int32_t> idx(static_cast<size_t>(n_roi) + 1);
+      auto gather = [&](const std::vector<float>& src, const int32_t* ix, int64_t k) {
+        std::vector<float> o(static_cast<size_t>(k) * 4);
+        for (int64_t i = 0; i < k; ++i) std::memcpy(&o[i * 4], &src[static_cast<size_t>(ix[i]) * 4], 16);
+        return o;
+      };
+      int64_t k = cmo_passthrough(roi_o.data(), n_roi, 2, -zg, zg, 0, idx.data());
+      const std::vector<float> low = gather(roi_o, idx.data(), k);
+      k = cmo_passthrough(roi_o.data(), n_roi, 2, static_cast<float>(zg + 0.01), prm.roi_z_max, 0, idx.data());
+      const std::vector<float> high = gather(roi_o, idx.data(), k);
+      const int64_t n_low = static_cast<int64_t>(low.size() / 4);
+      std::vector<int32_t> inl(static_cast<size_t>(n_low) + 1);
+      int32_t info[7];
+      const int64_t n_in = cmo_plane_ransac(low.data(), n_low, static_cast<double>(prm.distance_threshold), static_cast<double>(prm.prob),
+                                            prm.max_iterations, 1, 12345u, prm.sum_order, info, nullptr, nullptr, inl.data());
+      const std::vector<float> want_ground = gather(low, inl.data(), n_in);
+      std::vector<int32_t> rest;
+      for (int64_t i = 0, j = 0; i < n_low; ++i) {
+        if (j < n_in && inl[static_cast<size_t>(j)] == i) { ++j; continue; }
+        rest.push_back(static_cast<int32_t>(i));
+      }
+      const std::vector<float> not_ground = gather(low, rest.data(), static_cast<int64_t>(rest.size()));
+      std::vector<int32_t> keep(rest.size() + 1);
+      const int64_t kk = cmo_radius_outlier(not_ground.data(), static_cast<int64_t>(rest.size()), static_cast<double>(prm.radius),
+                                            static_cast<int32_t>(prm.min_neighbor), 0, keep.data());
+      std::vector<float> want_ng = gather(not_ground, keep.data(), kk);
+      want_ng.insert(want_ng.end(), high.begin(), high.end());
+      expect_cloud(*ground, want_ground, static_cast<size_t>(n_in), "removeGround ground");
+      expect_cloud(*no_ground, want_ng, want_ng.size() / 4, "removeGround no_ground");
+      CHECK(info[0] == 1 && n_in > 50 && n_in < n_low, "removeGround found a plane (%lld of %lld inliers)", (long long)n_in, (long long)n_low);
+    }
     // fusePointclouds: *no_ground_ptr = first; *no_ground_ptr += rest
     if (s == 0) *fused = *roi_ptr; else *fused += *roi_ptr;
     fused_oracle.insert(fused_oracle.end(), roi_o.begin(), roi_o.end());

@@ -1,0 +1,112 @@
+"""GPU parity tests (-m gpu) of the RANSAC ground plane (the pcl::SACSegmentation + pcl::ExtractIndices block of
+removeGround(), pc_preprocessing_main.cpp:95-117; Parameter.h:38-42) through the C ABI against the oracle's restatement of
+PCL 1.8.1 (sampler, model, stopping rule, least-squares refit). Bar: the same draw stream, model, iteration count and
+inlier set as PCL's sequential loop -- bit-exact coefficients, indices and coordinates."""
+import numpy as np
+import pytest
+
+from cloud_merger_b200 import CloudMerger
+
+from helpers import assert_bit_equal
+
+pytestmark = pytest.mark.gpu
+
+THR = float(np.float32(0.3))     # `const float distance_threshold = 0.3;` widened to setDistanceThreshold's double
+PROB = float(np.float32(0.99))   # `const float prob = 0.99;`
+
+
+def ground_scene(seed, n, ground_frac=0.7, slope=0.02, noise=0.03):
+    rng = np.random.default_rng(seed)
+    g = int(n * ground_frac)
+    pts = np.zeros((n, 4), np.float32)
+    pts[:, 0] = rng.uniform(-30, 30, n)
+    pts[:, 1] = rng.uniform(-10, 10, n)
+    pts[:g, 2] = -1.8 + slope * pts[:g, 0] + rng.normal(0, noise, g)
+    pts[g:, 2] = rng.uniform(-1.5, 1.0, n - g)
+    pts[:, 3] = rng.uniform(0, 255, n)
+    return pts[rng.permutation(n)]
+
+
+def same_floats(a, b):
+    """Bit equality, except that any NaN equals any NaN (x86 and the GPU produce different NaN payloads)."""
+    a, b = np.asarray(a, np.float32), np.asarray(b, np.float32)
+    return bool(((a.view(np.uint32) == b.view(np.uint32)) | (np.isnan(a) & np.isnan(b))).all())
+
+
+def check(cm, oracle, cloud, thr=THR, prob=PROB, max_it=1000, optimize=True, seed=12345, order=0, device_form=False):
+    want = oracle.plane_ransac(cloud, thr, prob, max_it, optimize, seed, order)
+    if device_form:
+        buf = cm.upload(cloud)
+        got = cm.dev_plane_ransac(buf.ptr, len(cloud), thr, prob, max_it, optimize, seed, order)
+        zones = cm.zone_out()
+        got["ground"], got["rest"] = zones[0], zones[1]
+    else:
+        got = cm.plane_ransac(cloud, thr, prob, max_it, optimize, seed, order)
+    for key in ("found", "iterations", "draws", "best_count"):
+        assert got[key] == want[key], (key, got[key], want[key])
+    assert (got["sample"] == want["sample"]).all()
+    assert same_floats(got["coeff_ransac"], want["coeff_ransac"]), (got["coeff_ransac"], want["coeff_ransac"])
+    assert same_floats(got["coeff"], want["coeff"]), (got["coeff"], want["coeff"])
+    gx, gi = got["ground"]
+    rx, ri = got["rest"]
+    assert got["n_inliers"] == len(want["inliers"]) == len(gi)
+    assert (gi == want["inliers"]).all(), "inlier set / order differs"
+    rest = np.setdiff1d(np.arange(len(cloud)), want["inliers"])
+    assert len(ri) == len(rest) and (ri == rest).all(), "ExtractIndices(negative) set / order differs"
+    assert_bit_equal(gx, cloud[want["inliers"]], "ground coordinates")
+    assert_bit_equal(rx, cloud[rest], "no-ground coordinates")
+    return want
+
+
+@pytest.mark.parametrize("order", [0, 1, 2])
+@pytest.mark.parametrize("optimize", [False, True])
+def test_plane_ransac_matches_oracle(gpu_ok, oracle, order, optimize):
+    with CloudMerger(max_sensors=1, max_points_per_sensor=60000, max_batch_points=60000) as cm:
+        for seed, n, frac in ((1, 50000, 0.8), (2, 20000, 0.45), (3, 777, 0.7), (4, 5, 1.0), (5, 4, 1.0), (6, 3, 1.0)):
+            w = check(cm, oracle, ground_scene(seed, n, frac), optimize=optimize, order=order)
+            assert w["found"]
+        check(cm, oracle, ground_scene(7, 30000, 0.8), optimize=optimize, order=order, device_form=True)
+
+
+def test_plane_ransac_long_runs_and_caps(gpu_ok, oracle):
+    """More hypotheses than one batch holds (the stopping rule needs several hundred iterations), the iteration cap, other
+    seeds, a threshold that is not a float."""
+    with CloudMerger(max_sensors=1, max_points_per_sensor=40000, max_batch_points=40000) as cm:
+        weak = ground_scene(11, 30000, 0.12)
+        w = check(cm, oracle, weak, prob=0.999999)
+        assert w["iterations"] > 300
+        w = check(cm, oracle, weak, prob=0.999999999, max_it=1500)
+        assert w["iterations"] > 1024
+        w = check(cm, oracle, weak, prob=0.999999, max_it=100)
+        assert w["iterations"] == 101
+        rng = np.random.default_rng(5)
+        blob = rng.uniform(-20, 20, (20000, 4)).astype(np.float32)
+        w = check(cm, oracle, blob, thr=0.05, max_it=1000)
+        assert w["iterations"] == 1001
+        for seed in (1, 99, 2**31 + 7):
+            check(cm, oracle, ground_scene(12, 10000, 0.6), seed=seed)
+        check(cm, oracle, ground_scene(13, 10000, 0.6), thr=0.3)   # the double 0.3, not 0.3f
+        check(cm, oracle, ground_scene(13, 10000, 0.6), thr=0.0)   # nothing is strictly inside 0
+        check(cm, oracle, ground_scene(14, 10000, 0.6, noise=0.0), thr=1e-6)
+
+
+def test_plane_ransac_degenerate_inputs(gpu_ok, oracle):
+    """Fewer than three points, collinear clouds (every draw rejected, getSamples gives up after 1000), duplicate points,
+    non-finite points (never inliers; they stay in the no-ground cloud as ExtractIndices(negative) leaves them)."""
+    with CloudMerger(max_sensors=1, max_points_per_sensor=4096, max_batch_points=4096) as cm:
+        for n in (0, 1, 2):
+            w = check(cm, oracle, ground_scene(20, 8, 1.0)[:n])
+            assert not w["found"]
+        t = np.arange(50, dtype=np.float32)
+        line = np.column_stack([t, 2 * t, 4 * t, t]).astype(np.float32)
+        w = check(cm, oracle, line)
+        assert not w["found"] and w["draws"] == 1000
+        dup = np.repeat(ground_scene(21, 40, 1.0), 5, axis=0)   # coincident sample points: zero normal, Eigen 3.3 normalize
+        check(cm, oracle, dup)
+        check(cm, oracle, np.repeat(np.array([[1, 2, 3, 4]], np.float32), 30, axis=0))
+        bad = ground_scene(22, 3000, 0.8)
+        bad[::97, 0] = np.nan
+        bad[5::131, 2] = np.inf
+        check(cm, oracle, bad)
+        with pytest.raises(Exception):
+            cm.plane_ransac(bad, THR, sum_order=7)

@@ -265,3 +265,82 @@ def test_radius_outlier_oracle_against_brute_force(oracle):
             want = np.nonzero(fin & ((k <= min_pts) if neg else (k > min_pts)))[0]
             got = oracle.radius_outlier(x, r, min_pts, neg)
             assert len(got) == len(want) and (got == want).all(), (min_pts, neg)
+
+
+# ---- RANSAC ground plane (pcl::SACSegmentation; pc_preprocessing_main.cpp:95-108) -----------------------------------------
+def _ground_scene(seed, n, ground_frac=0.7, slope=0.02, noise=0.03):
+    rng = np.random.default_rng(seed)
+    g = int(n * ground_frac)
+    pts = np.zeros((n, 4), np.float32)
+    pts[:, 0] = rng.uniform(-30, 30, n)
+    pts[:, 1] = rng.uniform(-10, 10, n)
+    pts[:g, 2] = -1.8 + slope * pts[:g, 0] + rng.normal(0, noise, g)
+    pts[g:, 2] = rng.uniform(-1.5, 1.0, n - g)
+    pts[:, 3] = rng.uniform(0, 255, n)
+    return pts[rng.permutation(n)]
+
+
+def test_plane_sampler_engine_known_answers(oracle):
+    """The sampler's engine is mt19937: the C++ standard's known answer (10000th output of the default seed 5489 is
+    4123659995) and numpy's init_genrand seeding for the seed PCL uses."""
+    assert oracle.mt19937_at(5489, 9999) == 4123659995
+    raw = np.random.RandomState(12345)._bit_generator.random_raw(1000)
+    for i in (0, 1, 623, 624, 999):
+        assert oracle.mt19937_at(12345, i) == int(raw[i])
+
+
+@pytest.mark.parametrize("order", [0, 1, 2])
+def test_plane_score_against_numpy(oracle, order):
+    from oracle import np_oracle
+    x = _ground_scene(3, 4000)
+    rng = np.random.default_rng(8)
+    thr = float(np.float32(0.3))
+    for _ in range(25):
+        smp = rng.choice(len(x), 3, replace=False).astype(np.int32)
+        good, c = np_oracle.plane_of_sample(x[smp[0]], x[smp[1]], x[smp[2]], order)
+        got_c, got_k = oracle.plane_score(x, smp, thr, order)
+        assert good and got_k == int(np_oracle.plane_inlier_mask(x, c, thr, order).sum())
+        assert got_c.tobytes() == c.tobytes()
+    # collinear sample (equal quotients on all axes) and coincident points are rejected
+    line = np.array([[0, 0, 0, 0], [1, 2, 4, 0], [2, 4, 8, 0], [5, 1, 1, 0]], np.float32)
+    assert oracle.plane_score(line, np.array([0, 1, 2], np.int32), thr, order)[1] == -1
+    assert oracle.plane_score(line, np.array([0, 1, 3], np.int32), thr, order)[1] >= 3
+
+
+@pytest.mark.parametrize("order", [0, 2])
+def test_plane_ransac_against_numpy_and_recovers_the_ground(oracle, order):
+    from oracle import np_oracle
+    for seed, n, frac in ((1, 3000, 0.7), (2, 1500, 0.35), (3, 64, 0.8)):
+        x = _ground_scene(seed, n, frac)
+        thr = float(np.float32(0.3))
+        want = np_oracle.plane_ransac(x, thr, float(np.float32(0.99)), 1000, 12345, order)
+        got = oracle.plane_ransac(x, thr, float(np.float32(0.99)), 1000, optimize=False, seed=12345, sum_order=order)
+        assert got["found"] and want["found"]
+        assert (got["iterations"], got["draws"], got["best_count"]) == (want["iterations"], want["draws"], want["best_count"])
+        assert (got["sample"] == want["sample"]).all() and got["coeff_ransac"].tobytes() == want["coeff"].tobytes()
+        mask = np_oracle.plane_inlier_mask(x, want["coeff"], thr, order)
+        assert (got["inliers"] == np.nonzero(mask)[0]).all()
+        # the least-squares refit tightens the plane: it must be close to the generating plane z = -1.8 + 0.02 x
+        ref = oracle.plane_ransac(x, thr, float(np.float32(0.99)), 1000, optimize=True, seed=12345, sum_order=order)
+        c = ref["coeff"] * np.sign(ref["coeff"][2])
+        truth = np.array([-0.02, 0.0, 1.0, 1.8]) / np.sqrt(1 + 0.02 ** 2)
+        if frac >= 0.7 and n >= 1000:
+            assert np.abs(c - truth).max() < 2e-2
+        assert abs(float(np.linalg.norm(c[:3])) - 1.0) < 1e-4
+
+
+def test_plane_ransac_degenerate_inputs(oracle):
+    thr = 0.3
+    for n in (0, 1, 2):
+        r = oracle.plane_ransac(np.zeros((n, 4), np.float32), thr)
+        assert not r["found"] and len(r["inliers"]) == 0
+    # all points on one line: every draw is rejected, getSamples gives up after 1000 of them
+    t = np.arange(50, dtype=np.float32)
+    line = np.column_stack([t, 2 * t, 4 * t, t]).astype(np.float32)
+    r = oracle.plane_ransac(line, thr)
+    assert not r["found"] and r["iterations"] == 0 and r["draws"] == 1000
+    # the iteration cap: a cloud without a dominant plane runs until iterations > max_iterations
+    rng = np.random.default_rng(5)
+    blob = rng.uniform(-20, 20, (4000, 4)).astype(np.float32)
+    r = oracle.plane_ransac(blob, 0.05, 0.99, 40)
+    assert r["found"] and r["iterations"] == 41
