@@ -44,6 +44,5 @@ for n, frac, prob, label in ((20000, 0.7, PROB, "zone"), (200000, 0.7, PROB, "wh
     cpu_ms = (time.perf_counter() - t0) * 1e3
     same = (r["iterations"], r["best_count"], r["n_inliers"]) == (w["iterations"], w["best_count"], len(w["inliers"]))
     print(json.dumps({"op": "plane_ransac", "case": label, "points": n, "iterations": r["iterations"], "inliers": r["n_inliers"],
-                      "gpu_ms": round(ms, 4), "cpu_port_ms": round(cpu_ms, 3), "same_result_as_cpu": bool(same),
-                      "launches": cm.launch_count() if hasattr(cm, "launch_count") else None}))
+                      "gpu_ms": round(ms, 4), "cpu_port_ms": round(cpu_ms, 3), "same_result_as_cpu": bool(same)}))
     cm.close()
