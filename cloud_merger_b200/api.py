@@ -248,6 +248,45 @@ class CloudMerger:
                                                   C.byref(pl), C.c_void_p(stream or None)))
         return self._plane_dict(pl)
 
+    def dev_plane_ransac_multi(self, xyzi_ptr: int, begin, distance_threshold: float, probability: float = 0.99,
+                               max_iterations: int = 1000, optimize: bool = True, seed: int = 12345, sum_order: int = 0,
+                               stream: int = 0) -> list:
+        """Independent plane searches over the consecutive clouds [begin[k], begin[k+1]) of one device array in one pass;
+        zone_out() then holds zone 2k = inliers of cloud k, zone 2k + 1 = its other points."""
+        b = (C.c_int64 * len(begin))(*[int(v) for v in begin])
+        k = len(begin) - 1
+        cfg = self._plane_cfg(distance_threshold, probability, max_iterations, optimize, seed, sum_order)
+        pl = (_lib.CmPlane * max(k, 1))()
+        self._check(self._lib.cm_dev_plane_ransac_multi(self._h, C.c_void_p(xyzi_ptr or None), b, k, C.byref(cfg), pl,
+                                                        C.c_void_p(stream or None)))
+        return [self._plane_dict(pl[i]) for i in range(k)]
+
+    def plane_ransac_multi(self, clouds, distance_threshold: float, probability: float = 0.99, max_iterations: int = 1000,
+                           optimize: bool = True, seed: int = 12345, sum_order: int = 0) -> list:
+        """Host-buffer form of dev_plane_ransac_multi: one dict per cloud with "ground" / "rest" as in plane_ransac
+        (indices relative to the cloud)."""
+        arrs = [np.ascontiguousarray(c, np.float32).reshape(-1, 4) for c in clouds]
+        k = len(arrs)
+        begin = np.concatenate([[0], np.cumsum([len(a) for a in arrs])]).astype(np.int64)
+        n = int(begin[-1])
+        allpts = np.ascontiguousarray(np.concatenate(arrs)) if n else np.zeros((0, 4), np.float32)
+        cfg = self._plane_cfg(distance_threshold, probability, max_iterations, optimize, seed, sum_order)
+        pl = (_lib.CmPlane * max(k, 1))()
+        ox = np.empty((max(n, 1), 4), np.float32)
+        oi = np.empty(max(n, 1), np.uint32)
+        ob = (C.c_int64 * (2 * k + 1))()
+        b = (C.c_int64 * (k + 1))(*[int(v) for v in begin])
+        self._check(self._lib.cm_plane_ransac_multi(self._h, allpts.ctypes.data_as(C.c_void_p), b, k, C.byref(cfg), pl,
+                                                    ox.ctypes.data_as(C.c_void_p), oi.ctypes.data_as(C.c_void_p), C.c_int64(n), ob))
+        res = []
+        for c in range(k):
+            r = self._plane_dict(pl[c])
+            g0, g1, g2 = ob[2 * c], ob[2 * c + 1], ob[2 * c + 2]
+            r["ground"] = (ox[g0:g1].copy(), (oi[g0:g1].astype(np.int64) - begin[c]).astype(np.uint32))
+            r["rest"] = (ox[g1:g2].copy(), (oi[g1:g2].astype(np.int64) - begin[c]).astype(np.uint32))
+            res.append(r)
+        return res
+
     def plane_ransac(self, xyzi: np.ndarray, distance_threshold: float, probability: float = 0.99,
                      max_iterations: int = 1000, optimize: bool = True, seed: int = 12345, sum_order: int = 0) -> dict:
         """Host-buffer form. Adds "ground" and "rest": (xyzi [k,4] float32, idx [k] uint32 into the input, ascending)."""

@@ -7,6 +7,7 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <chrono>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
@@ -1519,36 +1520,58 @@ int cm_radius_outlier(cm_handle_t h, const float* xyzi_host, int64_t n_points, d
 
 // ---- RANSAC ground plane --------------------------------------------------------------------------------------------------
 namespace {
-constexpr size_t PLANE_FIRST_BATCH = 256;  // PCL's stopping rule usually ends within a few iterations on a ground zone
-constexpr size_t PLANE_BATCH = 1024;
+constexpr size_t PLANE_FIRST_BATCH = 32;   // PCL's stopping rule usually ends within ~10 iterations on a ground zone;
+constexpr size_t PLANE_SECOND_BATCH = 256;  // the host draws (and the GPU scores) no further ahead than this
+constexpr size_t PLANE_BATCH = 1024;  // draws per cloud and batch
 
 int plane_ws_ensure(cm_handle_t h) {
   cm_handle_s::PlaneWs& q = h->pw;
   if (q.cap_draws) return CM_OK;
-  CM_CUDA(h, dev_alloc(&q.samples_dev, PLANE_BATCH * 3));
-  CM_CUDA(h, dev_alloc(&q.counts_dev, PLANE_BATCH * 2));
-  CM_CUDA(h, dev_alloc(&q.models_dev, PLANE_BATCH));
-  CM_CUDA(h, dev_alloc(&q.acc_dev, (size_t)16));
-  CM_CUDA(h, cudaMallocHost(reinterpret_cast<void**>(&q.samples_pin), PLANE_BATCH * 3 * sizeof(int32_t)));
-  CM_CUDA(h, cudaMallocHost(reinterpret_cast<void**>(&q.counts_pin), PLANE_BATCH * 2 * sizeof(int32_t)));
-  CM_CUDA(h, cudaMallocHost(reinterpret_cast<void**>(&q.models_pin), PLANE_BATCH * sizeof(float4)));
-  CM_CUDA(h, cudaMallocHost(reinterpret_cast<void**>(&q.acc_pin), 16 * sizeof(float)));
-  q.cap_draws = PLANE_BATCH;
+  const size_t draws = PLANE_BATCH * CM_MAX_PLANE_CLOUDS;
+  CM_CUDA(h, dev_alloc(&q.samples_dev, draws * 3));
+  CM_CUDA(h, dev_alloc(&q.counts_dev, draws * 2));
+  CM_CUDA(h, dev_alloc(&q.models_dev, draws));
+  CM_CUDA(h, dev_alloc(&q.acc_dev, (size_t)16 * CM_MAX_PLANE_CLOUDS));
+  CM_CUDA(h, cudaMallocHost(reinterpret_cast<void**>(&q.samples_pin), draws * 3 * sizeof(int32_t)));
+  CM_CUDA(h, cudaMallocHost(reinterpret_cast<void**>(&q.counts_pin), draws * 2 * sizeof(int32_t)));
+  CM_CUDA(h, cudaMallocHost(reinterpret_cast<void**>(&q.models_pin), draws * sizeof(float4)));
+  CM_CUDA(h, cudaMallocHost(reinterpret_cast<void**>(&q.acc_pin), 16 * CM_MAX_PLANE_CLOUDS * sizeof(float)));
+  q.cap_draws = draws;
   return CM_OK;
 }
 
-// SampleConsensusModel::shuffled_indices_ without the O(n) array: only the entries a swap has touched are stored
+// SampleConsensusModel::shuffled_indices_ without the O(n) array: only the entries a swap has touched are stored, in a
+// small open-addressing table (three swaps per draw; identity everywhere else)
 struct ShuffledIndices {
-  std::unordered_map<int64_t, int32_t> moved;
-  int32_t get(int64_t i) const {
-    auto it = moved.find(i);
-    return it == moved.end() ? (int32_t)i : it->second;
+  std::vector<uint32_t> key;  // position + 1 (0 = empty)
+  std::vector<int32_t> val;
+  size_t used = 0, mask = 0;
+  ShuffledIndices() { rehash(256); }
+  void rehash(size_t cap) {
+    std::vector<uint32_t> ok; std::vector<int32_t> ov;
+    ok.swap(key); ov.swap(val);
+    key.assign(cap, 0u); val.assign(cap, 0);
+    mask = cap - 1; used = 0;
+    for (size_t i = 0; i < ok.size(); ++i) if (ok[i]) *slot(ok[i] - 1) = ov[i];
+  }
+  // the value cell of position `pos`, created with the identity value if absent
+  int32_t* slot(uint32_t pos) {
+    size_t i = ((size_t)pos * 0x9E3779B1u) & mask;
+    while (key[i] && key[i] != pos + 1) i = (i + 1) & mask;
+    if (!key[i]) { key[i] = pos + 1; val[i] = (int32_t)pos; ++used; }
+    return &val[i];
+  }
+  int32_t get(int64_t pos) const {
+    size_t i = ((size_t)(uint32_t)pos * 0x9E3779B1u) & mask;
+    while (key[i] && key[i] != (uint32_t)pos + 1) i = (i + 1) & mask;
+    return key[i] ? val[i] : (int32_t)pos;
   }
   void swap(int64_t a, int64_t b) {
     if (a == b) return;
-    const int32_t va = get(a), vb = get(b);
-    moved[a] = vb;
-    moved[b] = va;
+    if ((used + 2) * 2 > mask + 1) rehash((mask + 1) * 2);
+    int32_t* pa = slot((uint32_t)a);
+    int32_t* pb = slot((uint32_t)b);
+    std::swap(*pa, *pb);
   }
 };
 
@@ -1632,117 +1655,195 @@ void plane_refit(const float* sums, uint32_t count, int order, float* coeff) {
   coeff[3] = -1.0f * sum4_host(coeff[0] * m[6], coeff[1] * m[7], coeff[2] * m[8], 0.0f * 1.0f, order);
 }
 
-int plane_ransac_run(cm_handle_t h, const float4* pts, int64_t n_points, const cm_plane_cfg_t& cfg, cm_plane_t* out,
-                     cudaStream_t st) {
-  if (n_points < 0 || n_points > 0x7FFFFFF0ll) return fail(h, CM_E_INVALID, "bad n_points");
+// RandomSampleConsensus::computeModel of one cloud, fed batch by batch
+struct PlaneSearch {
+  uint32_t n = 0;
+  std::mt19937 engine;
+  ShuffledIndices shuffled;
+  int iterations = 0, draws = 0, bad_run = 0;
+  long long best = -(long long)std::numeric_limits<int>::max();
+  double k = 1.0, one_over_indices = 0.0;
+  bool stop = false, found = false;
+  bool running() const { return n >= 3 && !stop && iterations < k; }
+};
+
+// clouds = the ranges [begin[k], begin[k+1]) of pts; out[n_clouds]; output zones 2k = inliers, 2k + 1 = rest of cloud k
+int plane_ransac_run(cm_handle_t h, const float4* pts, const int64_t* begin, int n_clouds, const cm_plane_cfg_t& cfg,
+                     cm_plane_t* out, cudaStream_t st) {
+  if (n_clouds < 1 || n_clouds > CM_MAX_PLANE_CLOUDS) return fail(h, CM_E_INVALID, "1 .. %d clouds per call", CM_MAX_PLANE_CLOUDS);
+  if (begin[0] != 0) return fail(h, CM_E_INVALID, "begin[0] must be 0");
+  for (int c = 0; c < n_clouds; ++c)
+    if (begin[c + 1] < begin[c]) return fail(h, CM_E_INVALID, "begin must not decrease");
+  const int64_t n_points = begin[n_clouds];
+  if (n_points > 0x7FFFFFF0ll) return fail(h, CM_E_INVALID, "bad n_points");
   if (cfg.max_iterations < 0 || cfg.sum_order < 0 || cfg.sum_order > 2) return fail(h, CM_E_INVALID, "bad plane settings");
   int rc = zone_ws_ensure(h, (size_t)n_points);
   if (rc != CM_OK) return rc;
   rc = plane_ws_ensure(h);
   if (rc != CM_OK) return rc;
   cm_handle_s::PlaneWs& q = h->pw;
-  memset(out, 0, sizeof(*out));
-  out->sample[0] = out->sample[1] = out->sample[2] = -1;
   // PCL compares the float distance with the double threshold: the smallest float >= threshold decides the same way
   float thr = (float)cfg.distance_threshold;
   if ((double)thr < cfg.distance_threshold) thr = std::nextafter(thr, std::numeric_limits<float>::infinity());
-  const uint32_t n = (uint32_t)n_points;
   int64_t launches = 0;
 
-  // RandomSampleConsensus::computeModel over the draw stream of SampleConsensusModel::getSamples
-  bool found = false;
-  if (n >= 3) {
-    std::mt19937 engine(cfg.seed);
-    ShuffledIndices shuffled;
-    int iterations = 0, draws = 0, bad_run = 0;
-    long long best = -(long long)std::numeric_limits<int>::max();
-    double k = 1.0;
-    const double log_probability = std::log(1.0 - cfg.probability);
-    const double one_over_indices = 1.0 / (double)n;
-    bool stop = false;
-    size_t batch = PLANE_FIRST_BATCH;
-    while (!stop && iterations < k) {
+  PlaneParams pp{};
+  pp.pts = pts; pp.n_clouds = (uint32_t)n_clouds; pp.draw_stride = (uint32_t)PLANE_BATCH;
+  pp.threshold = thr; pp.sum_order = (uint32_t)cfg.sum_order;
+  pp.samples = q.samples_dev; pp.models = q.models_dev; pp.counts = q.counts_dev; pp.good = q.counts_dev + q.cap_draws;
+  std::vector<PlaneSearch> search((size_t)n_clouds);
+  // CM_PLANE_TRACE=1: where the wall time of a call goes (host draws / scoring round trips / select + refit), to stderr
+  static const bool trace = getenv("CM_PLANE_TRACE") != nullptr;
+  auto now = [] { return std::chrono::steady_clock::now(); };
+  auto us = [](std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b) {
+    return std::chrono::duration<double, std::micro>(b - a).count();
+  };
+  double t_draw = 0, t_score = 0, t_walk = 0;
+  int rounds = 0;
+  const auto t_begin = now();
+  for (int c = 0; c <= n_clouds; ++c) pp.begin[c] = (uint32_t)begin[c];
+  for (int c = 0; c < n_clouds; ++c) {
+    PlaneSearch& s = search[(size_t)c];
+    s.n = (uint32_t)(begin[c + 1] - begin[c]);
+    s.engine.seed(cfg.seed);
+    s.one_over_indices = s.n ? 1.0 / (double)s.n : 0.0;
+    memset(&out[c], 0, sizeof(out[c]));
+    out[c].sample[0] = out[c].sample[1] = out[c].sample[2] = -1;
+  }
+  const double log_probability = std::log(1.0 - cfg.probability);
+
+  // the draw streams of SampleConsensusModel::getSamples, scored a batch at a time
+  size_t batch = PLANE_FIRST_BATCH;
+  for (;;) {
+    bool any = false;
+    const auto t0 = now();
+    for (int c = 0; c < n_clouds; ++c) {
+      PlaneSearch& s = search[(size_t)c];
+      pp.n_draws[c] = 0;
+      if (!s.running()) continue;
+      any = true;
+      pp.n_draws[c] = (uint32_t)batch;
+      int32_t* smp = q.samples_pin + 3 * (size_t)c * PLANE_BATCH;
       for (size_t d = 0; d < batch; ++d) {
         for (int64_t i = 0; i < 3; ++i) {
-          const uint64_t r = (uint64_t)((uint32_t)engine() >> 1);  // boost::uniform_int<>(0, INT_MAX) on mt19937
-          shuffled.swap(i, i + (int64_t)(r % (uint64_t)(n - i)));
+          const uint64_t r = (uint64_t)((uint32_t)s.engine() >> 1);  // boost::uniform_int<>(0, INT_MAX) on mt19937
+          s.shuffled.swap(i, i + (int64_t)(r % (uint64_t)(s.n - i)));
         }
-        for (int64_t i = 0; i < 3; ++i) q.samples_pin[3 * d + i] = shuffled.get(i);
+        for (int64_t i = 0; i < 3; ++i) smp[3 * d + i] = s.shuffled.get(i);
       }
-      PlaneParams pp;
-      pp.pts = pts; pp.n_points = n; pp.samples = q.samples_dev; pp.n_draws = (uint32_t)batch;
-      pp.threshold = thr; pp.sum_order = (uint32_t)cfg.sum_order;
-      pp.models = q.models_dev; pp.counts = q.counts_dev; pp.good = q.counts_dev + q.cap_draws;
-      CM_CUDA(h, cudaMemcpyAsync(q.samples_dev, q.samples_pin, batch * 3 * sizeof(int32_t), cudaMemcpyHostToDevice, st));
-      CM_CUDA(h, cudaMemsetAsync(q.counts_dev, 0, q.cap_draws * 2 * sizeof(int32_t), st));
-      CM_CUDA(h, launch_plane_score(pp, st));
-      ++launches;
-      CM_CUDA(h, cudaMemcpyAsync(q.counts_pin, q.counts_dev, q.cap_draws * 2 * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
-      CM_CUDA(h, cudaMemcpyAsync(q.models_pin, q.models_dev, batch * sizeof(float4), cudaMemcpyDeviceToHost, st));
-      CM_CUDA(h, cudaStreamSynchronize(st));
-      const int32_t* counts = q.counts_pin;
-      const int32_t* good = q.counts_pin + q.cap_draws;
-      for (size_t d = 0; d < batch && !stop && iterations < k; ++d) {
-        ++draws;
+    }
+    if (!any) break;
+    const auto t1 = now();
+    const size_t used = (size_t)(n_clouds - 1) * PLANE_BATCH + batch;  // the per-draw arrays up to the last cloud's batch
+    CM_CUDA(h, cudaMemcpyAsync(q.samples_dev, q.samples_pin, used * 3 * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+    CM_CUDA(h, cudaMemsetAsync(q.counts_dev, 0, used * sizeof(int32_t), st));
+    CM_CUDA(h, launch_plane_score(pp, st));
+    ++launches;
+    CM_CUDA(h, cudaMemcpyAsync(q.counts_pin, q.counts_dev, used * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    CM_CUDA(h, cudaMemcpyAsync(q.counts_pin + q.cap_draws, q.counts_dev + q.cap_draws, used * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    CM_CUDA(h, cudaMemcpyAsync(q.models_pin, q.models_dev, used * sizeof(float4), cudaMemcpyDeviceToHost, st));
+    CM_CUDA(h, cudaStreamSynchronize(st));
+    const auto t2 = now();
+    for (int c = 0; c < n_clouds; ++c) {
+      PlaneSearch& s = search[(size_t)c];
+      const size_t n_draws = pp.n_draws[c], off = (size_t)c * PLANE_BATCH;
+      const int32_t* counts = q.counts_pin + off;
+      const int32_t* good = q.counts_pin + q.cap_draws + off;
+      for (size_t d = 0; d < n_draws && s.running(); ++d) {
+        ++s.draws;
         if (!good[d]) {  // getSamples draws again; after max_sample_checks_ (1000) failures in a row it gives up
-          if (++bad_run == 1000) stop = true;
+          if (++s.bad_run == 1000) s.stop = true;
           continue;
         }
-        bad_run = 0;
-        if ((long long)counts[d] > best) {
-          best = counts[d];
-          found = true;
-          out->best_count = counts[d];
-          for (int i = 0; i < 3; ++i) out->sample[i] = q.samples_pin[3 * d + i];
-          const float4 c = q.models_pin[d];
-          out->coeff_ransac[0] = c.x; out->coeff_ransac[1] = c.y; out->coeff_ransac[2] = c.z; out->coeff_ransac[3] = c.w;
-          const double w = (double)best * one_over_indices;
+        s.bad_run = 0;
+        if ((long long)counts[d] > s.best) {
+          s.best = counts[d];
+          s.found = true;
+          out[c].best_count = counts[d];
+          for (int i = 0; i < 3; ++i) out[c].sample[i] = q.samples_pin[3 * (off + d) + i];
+          const float4 m = q.models_pin[off + d];
+          out[c].coeff_ransac[0] = m.x; out[c].coeff_ransac[1] = m.y; out[c].coeff_ransac[2] = m.z; out[c].coeff_ransac[3] = m.w;
+          const double w = (double)s.best * s.one_over_indices;
           double p_no_outliers = 1.0 - std::pow(w, 3.0);
           p_no_outliers = std::max(std::numeric_limits<double>::epsilon(), p_no_outliers);
           p_no_outliers = std::min(1.0 - std::numeric_limits<double>::epsilon(), p_no_outliers);
-          k = log_probability / std::log(p_no_outliers);
+          s.k = log_probability / std::log(p_no_outliers);
         }
-        ++iterations;
-        if (iterations > cfg.max_iterations) stop = true;
+        ++s.iterations;
+        if (s.iterations > cfg.max_iterations) s.stop = true;
       }
-      batch = PLANE_BATCH;
     }
-    out->iterations = iterations;
-    out->draws = draws;
+    batch = batch == PLANE_FIRST_BATCH ? PLANE_SECOND_BATCH : PLANE_BATCH;
+    t_draw += us(t0, t1); t_score += us(t1, t2); t_walk += us(t2, now());
+    ++rounds;
   }
-  out->found = found ? 1 : 0;
-  memcpy(out->coeff, out->coeff_ransac, sizeof(out->coeff));
+  const auto t_search = now();
 
-  // selectWithinDistance + the two ExtractIndices passes: zone 0 = inliers, zone 1 = the rest, both in input order
-  cm_zone_out_t zo;
-  CM_CUDA(h, launch_plane_select(pts, n, out->coeff_ransac, thr, (uint32_t)cfg.sum_order, found, h->zw.mask, st));
+  // what follows the search: zone 2k = inliers of cloud k, zone 2k + 1 = its other points
+  PlaneSelect ps{};
+  ps.pts = pts; ps.n_clouds = (uint32_t)n_clouds; ps.threshold = thr; ps.mask = h->zw.mask;
+  for (int c = 0; c <= n_clouds; ++c) ps.begin[c] = (uint32_t)begin[c];
+  bool any_found = false;
+  for (int c = 0; c < n_clouds; ++c) {
+    const PlaneSearch& s = search[(size_t)c];
+    out[c].found = s.found ? 1 : 0;
+    out[c].iterations = s.iterations;
+    out[c].draws = s.draws;
+    memcpy(out[c].coeff, out[c].coeff_ransac, sizeof(out[c].coeff));
+    ps.found[c] = s.found ? 1u : 0u;
+    ps.coeff[c] = make_float4(out[c].coeff[0], out[c].coeff[1], out[c].coeff[2], out[c].coeff[3]);
+    any_found = any_found || s.found;
+  }
+  if (any_found && cfg.optimize) {
+    // optimizeModelCoefficients on the inliers of the RANSAC model: the running sums on the device, the 3 x 3 part here
+    CM_CUDA(h, launch_plane_moments(ps, (uint32_t)cfg.sum_order, q.acc_dev, st));
+    ++launches;
+    CM_CUDA(h, cudaMemcpyAsync(q.acc_pin, q.acc_dev, (size_t)16 * n_clouds * sizeof(float), cudaMemcpyDeviceToHost, st));
+    CM_CUDA(h, cudaStreamSynchronize(st));
+    for (int c = 0; c < n_clouds; ++c) {
+      uint32_t n_in;
+      memcpy(&n_in, q.acc_pin + 16 * c + 9, sizeof(n_in));
+#ifdef CM_PLANE_CYCLES
+      if (trace) {
+        uint32_t cyc[2];
+        memcpy(cyc, q.acc_pin + 16 * c + 10, sizeof(cyc));
+        fprintf(stderr, "[cm plane] cloud %d: moments kernel %u cycles, adding warp busy %u cycles, %u inliers\n", c, cyc[0], cyc[1], n_in);
+      }
+#endif
+      if (!search[(size_t)c].found || n_in < 4) continue;  // below 4 inliers PCL keeps the RANSAC model
+      plane_refit(q.acc_pin + 16 * c, n_in, cfg.sum_order, out[c].coeff);
+      ps.coeff[c] = make_float4(out[c].coeff[0], out[c].coeff[1], out[c].coeff[2], out[c].coeff[3]);
+    }
+  }
+  // selectWithinDistance with the final model + the two ExtractIndices passes
+  CM_CUDA(h, launch_plane_select(ps, (uint32_t)cfg.sum_order, st));
   ++launches;
-  rc = zone_run(h, pts, n_points, st, true, 2);
+  rc = zone_run(h, pts, n_points, st, true, 2 * n_clouds);
   if (rc != CM_OK) return rc;
   launches += h->zw.launches;
-  if (found && cfg.optimize) {
-    CM_CUDA(h, launch_plane_moments(h->zw.out_xyzi, h->zw.zone_begin + 1, q.acc_dev, st));
-    ++launches;
-    CM_CUDA(h, cudaMemcpyAsync(q.acc_pin, q.acc_dev, 10 * sizeof(float), cudaMemcpyDeviceToHost, st));
-    CM_CUDA(h, cudaStreamSynchronize(st));
-    uint32_t n_in;
-    memcpy(&n_in, q.acc_pin + 9, sizeof(n_in));
-    if (n_in >= 4) {
-      plane_refit(q.acc_pin, n_in, cfg.sum_order, out->coeff);
-      CM_CUDA(h, launch_plane_select(pts, n, out->coeff, thr, (uint32_t)cfg.sum_order, true, h->zw.mask, st));
-      ++launches;
-      rc = zone_run(h, pts, n_points, st, true, 2);
-      if (rc != CM_OK) return rc;
-      launches += h->zw.launches;
-    }
-  }
+  cm_zone_out_t zo;
   rc = zone_out_locked(h, &zo);
   if (rc != CM_OK) return rc;
   h->zw.launches = launches;
-  out->n_inliers = zo.begin[1];
+  for (int c = 0; c < n_clouds; ++c) out[c].n_inliers = zo.begin[2 * c + 1] - zo.begin[2 * c];
+  if (trace)
+    fprintf(stderr, "[cm plane] clouds %d points %lld: %d scoring rounds (host draws %.1f us, GPU round trips %.1f us, stopping rule %.1f us), "
+            "refit + select + compaction %.1f us, total %.1f us, %lld launches\n", n_clouds, (long long)n_points, rounds, t_draw, t_score,
+            t_walk, us(t_search, now()), us(t_begin, now()), (long long)launches);
   return CM_OK;
 }
 }  // namespace
+
+int cm_dev_plane_ransac_multi(cm_handle_t h, const float* xyzi_dev, const int64_t* begin, int n_clouds,
+                              const cm_plane_cfg_t* cfg, cm_plane_t* out, void* stream) {
+  if (!h || !cfg || !out || !begin) return CM_E_INVALID;
+  std::lock_guard<std::mutex> lk(h->mu);
+  CM_CUDA(h, cudaSetDevice(h->device));
+  if (n_clouds >= 1 && n_clouds <= CM_MAX_PLANE_CLOUDS && begin[n_clouds] > 0 &&
+      (!xyzi_dev || (reinterpret_cast<uintptr_t>(xyzi_dev) & 15u)))
+    return fail(h, CM_E_INVALID, "xyzi_dev must be 16-byte aligned");
+  return plane_ransac_run(h, reinterpret_cast<const float4*>(xyzi_dev), begin, n_clouds, *cfg, out, static_cast<cudaStream_t>(stream));
+}
 
 int cm_dev_plane_ransac(cm_handle_t h, const float* xyzi_dev, int64_t n_points, const cm_plane_cfg_t* cfg, cm_plane_t* out,
                         void* stream) {
@@ -1750,30 +1851,42 @@ int cm_dev_plane_ransac(cm_handle_t h, const float* xyzi_dev, int64_t n_points, 
   std::lock_guard<std::mutex> lk(h->mu);
   CM_CUDA(h, cudaSetDevice(h->device));
   if (n_points > 0 && (!xyzi_dev || (reinterpret_cast<uintptr_t>(xyzi_dev) & 15u))) return fail(h, CM_E_INVALID, "xyzi_dev must be 16-byte aligned");
-  return plane_ransac_run(h, reinterpret_cast<const float4*>(xyzi_dev), n_points, *cfg, out, static_cast<cudaStream_t>(stream));
+  if (n_points < 0) return fail(h, CM_E_INVALID, "bad n_points");
+  const int64_t begin[2] = {0, n_points};
+  return plane_ransac_run(h, reinterpret_cast<const float4*>(xyzi_dev), begin, 1, *cfg, out, static_cast<cudaStream_t>(stream));
 }
 
-int cm_plane_ransac(cm_handle_t h, const float* xyzi_host, int64_t n_points, const cm_plane_cfg_t* cfg, cm_plane_t* out,
-                    float* out_xyzi, uint32_t* out_idx, int64_t capacity, int64_t* out_begin) {
-  if (!h || !cfg || !out || !out_begin || n_points < 0 || (n_points > 0 && !xyzi_host)) return CM_E_INVALID;
+int cm_plane_ransac_multi(cm_handle_t h, const float* xyzi_host, const int64_t* begin, int n_clouds, const cm_plane_cfg_t* cfg,
+                          cm_plane_t* out, float* out_xyzi, uint32_t* out_idx, int64_t capacity, int64_t* out_begin) {
+  if (!h || !cfg || !out || !out_begin || !begin) return CM_E_INVALID;
   std::lock_guard<std::mutex> lk(h->mu);
   CM_CUDA(h, cudaSetDevice(h->device));
+  if (n_clouds < 1 || n_clouds > CM_MAX_PLANE_CLOUDS) return fail(h, CM_E_INVALID, "1 .. %d clouds per call", CM_MAX_PLANE_CLOUDS);
+  const int64_t n_points = begin[n_clouds];
+  if (n_points < 0 || (n_points > 0 && !xyzi_host)) return fail(h, CM_E_INVALID, "bad input");
   int rc = zone_ws_ensure(h, (size_t)n_points);
   if (rc != CM_OK) return rc;
   cm_handle_s::ZoneWs& z = h->zw;
   if (!z.in_stage) CM_CUDA(h, dev_alloc(&z.in_stage, z.cap_points));
-  CM_CUDA(h, cudaMemcpyAsync(z.in_stage, xyzi_host, (size_t)n_points * 16, cudaMemcpyHostToDevice, nullptr));
-  rc = plane_ransac_run(h, z.in_stage, n_points, *cfg, out, nullptr);
+  if (n_points) CM_CUDA(h, cudaMemcpyAsync(z.in_stage, xyzi_host, (size_t)n_points * 16, cudaMemcpyHostToDevice, nullptr));
+  rc = plane_ransac_run(h, z.in_stage, begin, n_clouds, *cfg, out, nullptr);
   if (rc != CM_OK) return rc;
   cm_zone_out_t zo;
   rc = zone_out_locked(h, &zo);
-  for (int k = 0; k <= 2; ++k) out_begin[k] = zo.begin[k];
+  for (int k = 0; k <= 2 * n_clouds; ++k) out_begin[k] = zo.begin[k];
   if (rc != CM_OK) return rc;
-  const int64_t total = zo.begin[2];
+  const int64_t total = zo.begin[2 * n_clouds];
   if (total > capacity) return fail(h, CM_E_CAPACITY, "%lld points, caller capacity %lld", (long long)total, (long long)capacity);
   if (out_xyzi && total) CM_CUDA(h, cudaMemcpy(out_xyzi, zo.xyzi, (size_t)total * 16, cudaMemcpyDeviceToHost));
   if (out_idx && total) CM_CUDA(h, cudaMemcpy(out_idx, zo.src, (size_t)total * 4, cudaMemcpyDeviceToHost));
   return CM_OK;
+}
+
+int cm_plane_ransac(cm_handle_t h, const float* xyzi_host, int64_t n_points, const cm_plane_cfg_t* cfg, cm_plane_t* out,
+                    float* out_xyzi, uint32_t* out_idx, int64_t capacity, int64_t* out_begin) {
+  if (n_points < 0) return CM_E_INVALID;
+  const int64_t begin[2] = {0, n_points};
+  return cm_plane_ransac_multi(h, xyzi_host, begin, 1, cfg, out, out_xyzi, out_idx, capacity, out_begin);
 }
 
 int cm_sync(cm_handle_t h) {

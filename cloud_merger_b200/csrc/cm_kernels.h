@@ -122,23 +122,34 @@ struct RorParams {
 cudaError_t launch_radius_count(const VoxelParams& p, const RorParams& r, cudaStream_t stream);
 
 // ---- RANSAC ground plane (cm_plane.cu) --------------------------------------------------------------------------------------
-struct PlaneParams {
-  const float4* pts;       // n packed xyzi points
-  uint32_t n_points;
-  const int32_t* samples;  // [n_draws][3] point indices of every draw
-  uint32_t n_draws;
+#define CM_MAX_PLANE_CLOUDS (CM_MAX_ZONES / 2)
+struct PlaneParams {  // one batch of draws for up to CM_MAX_PLANE_CLOUDS independent clouds
+  const float4* pts;                         // the clouds, one after the other
+  uint32_t n_clouds;
+  uint32_t begin[CM_MAX_PLANE_CLOUDS + 1];   // cloud k = pts[begin[k] .. begin[k+1])
+  uint32_t n_draws[CM_MAX_PLANE_CLOUDS];     // draws of cloud k in this batch (0: the cloud is finished)
+  uint32_t draw_stride;                      // per-draw arrays: cloud k owns [k * draw_stride, (k+1) * draw_stride)
   float threshold;         // smallest float >= the double threshold: |d| < threshold decides like PCL's float-vs-double test
   uint32_t sum_order;      // order of Eigen's 4-wide reductions: 0 SSE2 (l0+l2)+(l1+l3), 1 SSE3 (l0+l1)+(l2+l3), 2 scalar
-  float4* models;          // [n_draws] plane of every draw
-  int32_t* counts;         // [n_draws] inliers of every draw (cleared by the caller)
-  int32_t* good;           // [n_draws] isSampleGood
+  const int32_t* samples;  // [draw][3] point indices (relative to the cloud's first point)
+  float4* models;          // [draw] plane of every draw
+  int32_t* counts;         // [draw] inliers of every draw (cleared by the caller)
+  int32_t* good;           // [draw] isSampleGood
+};
+struct PlaneSelect {
+  const float4* pts;
+  uint32_t n_clouds;
+  uint32_t begin[CM_MAX_PLANE_CLOUDS + 1];
+  uint32_t found[CM_MAX_PLANE_CLOUDS];       // 0: segment() failed for this cloud, no inliers
+  float4 coeff[CM_MAX_PLANE_CLOUDS];
+  float threshold;
+  unsigned short* mask;    // bit 2k: inlier of cloud k, bit 2k + 1: its other points
 };
 cudaError_t launch_plane_score(const PlaneParams& p, cudaStream_t stream);
-// inlier (bit 0) / rest (bit 1) flags of every point; found == false: everything is rest
-cudaError_t launch_plane_select(const float4* pts, uint32_t n, const float* coeff, float threshold, uint32_t sum_order,
-                                bool found, unsigned short* mask, cudaStream_t stream);
-// PCL-order float sums xx xy xz yy yz zz x y z over inliers[0 .. *n_inliers_dev) -> out[0..8], out[9] = the count's bits
-cudaError_t launch_plane_moments(const float4* inliers, const uint32_t* n_inliers_dev, float* out, cudaStream_t stream);
+cudaError_t launch_plane_select(const PlaneSelect& q, uint32_t sum_order, cudaStream_t stream);
+// PCL-order float sums xx xy xz yy yz zz x y z over the inliers of every cloud's model (index order) ->
+// out[16 k + 0..8], out[16 k + 9] = the inlier count's bits
+cudaError_t launch_plane_moments(const PlaneSelect& q, uint32_t sum_order, float* out, cudaStream_t stream);
 
 // ---- giant-cloud mode: routing by voxel-key range (cm_route.cu) ----------------------------------------------------------
 struct RouteGrid {  // PCL's grid on the GLOBAL bounding box

@@ -306,6 +306,17 @@ CM_API int cm_radius_outlier(cm_handle_t h, const float* xyzi_host, int64_t n_po
  *  cm_plane_ransac: host buffers; out_begin receives 3 offsets (inliers = [0, out_begin[1]), rest up to out_begin[2]). */
 CM_API int cm_dev_plane_ransac(cm_handle_t h, const float* xyzi_dev, int64_t n_points, const cm_plane_cfg_t* cfg,
                                cm_plane_t* out, void* stream);
+/* Several independent plane searches in one pass (the ground zones of one sensor cloud: five RANSACs per proceedX,
+ * pc_preprocessing_main.cpp:228-312): cloud k = the points [begin[k], begin[k+1]) of xyzi_dev (begin[0] == 0),
+ * n_clouds <= CM_MAX_ZONES / 2. Every batch of hypotheses, the selection and the refit cover all clouds at once, so the
+ * call costs about as much as one search. out[n_clouds]; cm_get_zone_out then holds 2 * n_clouds zones: zone 2k = the
+ * inliers of cloud k, zone 2k + 1 = its other points (src = index in xyzi_dev, i.e. begin[k] + index in the cloud). */
+CM_API int cm_dev_plane_ransac_multi(cm_handle_t h, const float* xyzi_dev, const int64_t* begin, int n_clouds,
+                                     const cm_plane_cfg_t* cfg, cm_plane_t* out, void* stream);
+/* host-buffer form of the above: out_begin receives 2 * n_clouds + 1 offsets into out_xyzi / out_idx */
+CM_API int cm_plane_ransac_multi(cm_handle_t h, const float* xyzi_host, const int64_t* begin, int n_clouds,
+                                 const cm_plane_cfg_t* cfg, cm_plane_t* out, float* out_xyzi, uint32_t* out_idx,
+                                 int64_t capacity, int64_t* out_begin);
 CM_API int cm_plane_ransac(cm_handle_t h, const float* xyzi_host, int64_t n_points, const cm_plane_cfg_t* cfg,
                            cm_plane_t* out, float* out_xyzi, uint32_t* out_idx, int64_t capacity, int64_t* out_begin);
 /* ---- single giant cloud over several GPUs (BASELINE config 4): device-side pieces of the voxel-key range partition ----

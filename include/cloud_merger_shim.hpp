@@ -9,6 +9,7 @@
 //   proceedX: getCloudPart x5 + the z windows of removeGround                 ->  getCloudPartsZSplit (one GPU pass)
 //   void fusePointclouds(Cloud::Ptr no_ground, Cloud::Ptr ground)             ->  FusedFrame::fuse (+ operator+= kept)
 //   void outlierRemoval(Cloud::Ptr)                                           ->  outlierRemoval(cloud)
+//   proceedX after getROI: 5 x (getCloudPart + removeGround), appended          ->  proceedZones(ctx, roi, parts, no_ground, ground)
 //   void removeGround(cloud, no_ground, ground, z_min, z_max, max_angle)      ->  removeGround(...) (z windows + RANSAC
 //                                                                                 plane + ExtractIndices + outlierRemoval)
 //   void voxelgrid(const Cloud::Ptr, Cloud::Ptr)                              ->  voxelgrid(in, out)
@@ -220,18 +221,25 @@ class Context {
     return true;
   }
 
-  // RANSAC ground plane of ONE host cloud (cm_plane_ransac): pcl::SACSegmentation (SACMODEL_PLANE, SAC_RANSAC, optimize
-  // on) + the two pcl::ExtractIndices passes; ground = the inliers, no_ground = the rest, both in input order.
-  bool plane_ransac(const Cloud& in, Cloud& ground, Cloud& no_ground, cm_plane_t* model = nullptr) {
-    clear(ground); clear(no_ground);
+  // RANSAC ground plane of several host clouds in one pass (cm_plane_ransac_multi; at most CM_MAX_ZONES / 2 clouds): per
+  // cloud pcl::SACSegmentation (SACMODEL_PLANE, SAC_RANSAC, optimize on) + the two pcl::ExtractIndices passes;
+  // ground[k] = the inliers of in[k], no_ground[k] = its other points, both in input order.
+  bool plane_ransac_multi(const std::vector<const Cloud*>& in, std::vector<Cloud>& ground, std::vector<Cloud>& no_ground,
+                          std::vector<cm_plane_t>* models = nullptr) {
+    const size_t k = in.size();
+    ground.assign(k, Cloud()); no_ground.assign(k, Cloud());
     if (!check(h_ ? CM_OK : CM_E_NO_DEVICE)) return false;
-    const int64_t n = static_cast<int64_t>(in.points.size());
-    if (n > max_points_ * max_sensors_) { rc_ = CM_E_CAPACITY; err_ = "cloud larger than the context capacity"; return false; }
-    tmp_.resize(static_cast<size_t>(n) * 4);
-    for (int64_t i = 0; i < n; ++i) {
-      const PointXYZI& p = in.points[static_cast<size_t>(i)];
-      tmp_[i * 4 + 0] = p.x; tmp_[i * 4 + 1] = p.y; tmp_[i * 4 + 2] = p.z; tmp_[i * 4 + 3] = p.intensity;
-    }
+    std::vector<int64_t> begin(k + 1, 0);
+    for (size_t c = 0; c < k; ++c) begin[c + 1] = begin[c] + static_cast<int64_t>(in[c]->points.size());
+    const int64_t n = begin[k];
+    if (n > max_points_ * max_sensors_) { rc_ = CM_E_CAPACITY; err_ = "clouds larger than the context capacity"; return false; }
+    tmp_.resize(static_cast<size_t>(n) * 4 + 4);
+    for (size_t c = 0; c < k; ++c)
+      for (size_t i = 0; i < in[c]->points.size(); ++i) {
+        const PointXYZI& p = in[c]->points[i];
+        float* o = &tmp_[(static_cast<size_t>(begin[c]) + i) * 4];
+        o[0] = p.x; o[1] = p.y; o[2] = p.z; o[3] = p.intensity;
+      }
     cm_plane_cfg_t cfg;
     cfg.distance_threshold = static_cast<double>(params_.distance_threshold);
     cfg.probability = static_cast<double>(params_.prob);
@@ -239,24 +247,34 @@ class Context {
     cfg.optimize = 1;
     cfg.seed = 12345u;
     cfg.sum_order = params_.sum_order;
-    cm_plane_t pl;
-    int64_t begin[3] = {0, 0, 0};
+    std::vector<cm_plane_t> pl(k);
+    std::vector<int64_t> ob(2 * k + 1, 0);
     zone_xyzi_.resize(static_cast<size_t>(n) * 4 + 4);
-    if (!check(cm_plane_ransac(h_, tmp_.data(), n, &cfg, &pl, zone_xyzi_.data(), nullptr, n, begin))) return false;
-    if (model) *model = pl;
-    Cloud* outs[2] = {&ground, &no_ground};
-    for (int z = 0; z < 2; ++z) {
-      Cloud& c = *outs[z];
-      const size_t b = static_cast<size_t>(begin[z]), e = static_cast<size_t>(begin[z + 1]);
+    if (!check(cm_plane_ransac_multi(h_, tmp_.data(), begin.data(), static_cast<int>(k), &cfg, pl.data(), zone_xyzi_.data(),
+                                     nullptr, n, ob.data())))
+      return false;
+    if (models) *models = pl;
+    for (size_t z = 0; z < 2 * k; ++z) {
+      Cloud& c = (z & 1) ? no_ground[z / 2] : ground[z / 2];
+      const size_t b = static_cast<size_t>(ob[z]), e = static_cast<size_t>(ob[z + 1]);
       c.points.resize(e - b);
       for (size_t i = b; i < e; ++i) {
         PointXYZI& p = c.points[i - b];
         p = PointXYZI();
         p.x = zone_xyzi_[i * 4 + 0]; p.y = zone_xyzi_[i * 4 + 1]; p.z = zone_xyzi_[i * 4 + 2]; p.intensity = zone_xyzi_[i * 4 + 3];
       }
-      finish(c, in, in.is_dense);
+      finish(c, *in[z / 2], in[z / 2]->is_dense);
     }
     return true;
+  }
+  // one cloud
+  bool plane_ransac(const Cloud& in, Cloud& ground, Cloud& no_ground, cm_plane_t* model = nullptr) {
+    std::vector<Cloud> g, r;
+    std::vector<cm_plane_t> m;
+    const bool ok = plane_ransac_multi({&in}, g, r, &m);
+    if (ok) { ground = g[0]; no_ground = r[0]; if (model) *model = m[0]; }
+    else { clear(ground); clear(no_ground); }
+    return ok;
   }
 
   // Zone slicing of ONE host cloud (cm_zone_split): one ordered output cloud per PassThrough chain, one GPU pass.
@@ -428,6 +446,29 @@ inline void removeGround(Context& ctx, const Cloud::Ptr& cloud_ptr, const Cloud:
   *no_ground_cloud_ptr = no_ground;
   outlierRemoval(ctx, no_ground_cloud_ptr);
   *no_ground_cloud_ptr += parts[1];
+}
+
+// proceedFront / proceedRear / proceedTop / proceedLivox after getROI -- :228-312: per zone getCloudPart + removeGround,
+// results appended zone after zone. Here: one zone-slicing pass for all x and z windows, one multi-cloud RANSAC pass for
+// all ground windows, then per zone outlierRemoval of what is not ground and the points above the window appended.
+inline void proceedZones(Context& ctx, const Cloud::Ptr& cloud_ROI_ptr, const std::vector<ZonePart>& parts,
+                         const Cloud::Ptr& no_ground_ptr, const Cloud::Ptr& ground_ptr) {
+  std::vector<Cloud::Ptr> ground_part, upper_part;
+  getCloudPartsZSplit(ctx, cloud_ROI_ptr, parts, ctx.params().roi_z_max, ground_part, upper_part);
+  std::vector<const Cloud*> in;
+  for (const Cloud::Ptr& g : ground_part) in.push_back(g.get());
+  std::vector<Cloud> ground, rest;
+  ctx.plane_ransac_multi(in, ground, rest);
+  Cloud no_ground_all, ground_all;
+  for (size_t k = 0; k < parts.size(); ++k) {
+    Cloud::Ptr ng(new Cloud(rest[k]));
+    outlierRemoval(ctx, ng);
+    *ng += *upper_part[k];
+    if (k == 0) { no_ground_all = *ng; ground_all = ground[k]; }
+    else { no_ground_all += *ng; ground_all += ground[k]; }
+  }
+  *no_ground_ptr = no_ground_all;
+  *ground_ptr = ground_all;
 }
 
 // void voxelgrid(const Cloud::Ptr cloud_ptr, Cloud::Ptr voxel_cloud_ptr) -- :168-177

@@ -7,7 +7,7 @@ srcs=${@:-cm_radix_sort.cu}
 root=$(cd "$(dirname "$0")/.." && pwd)
 mkdir -p "$root/variants/obj_$name"
 objs=""
-for s in cm_transform_crop.cu cm_voxel.cu cm_radix_sort.cu cm_zones.cu cm_outlier.cu cm_route.cu cm_api.cu; do
+for s in cm_transform_crop.cu cm_voxel.cu cm_radix_sort.cu cm_zones.cu cm_outlier.cu cm_route.cu cm_plane.cu cm_api.cu; do
   o="$root/cloud_merger_b200/build/${s%.cu}.o"
   for v in $srcs; do
     if [ "$v" == "$s" ]; then

@@ -46,3 +46,31 @@ for n, frac, prob, label in ((20000, 0.7, PROB, "zone"), (200000, 0.7, PROB, "wh
     print(json.dumps({"op": "plane_ransac", "case": label, "points": n, "iterations": r["iterations"], "inliers": r["n_inliers"],
                       "gpu_ms": round(ms, 4), "cpu_port_ms": round(cpu_ms, 3), "same_result_as_cpu": bool(same)}))
     cm.close()
+
+# five ground zones of one sensor cloud in one call (proceedX runs five removeGround in a row) vs five single calls
+sizes = (30000, 11000, 15000, 8000, 20000)
+clouds = [ground_scene(10 + i, n, 0.75) for i, n in enumerate(sizes)]
+begin = np.concatenate([[0], np.cumsum(sizes)]).astype(np.int64)
+allpts = np.ascontiguousarray(np.concatenate(clouds))
+cm = CloudMerger(max_sensors=1, max_points_per_sensor=len(allpts), max_batch_points=len(allpts))
+buf = cm.upload(allpts)
+for _ in range(3):
+    cm.dev_plane_ransac_multi(buf.ptr, begin, THR, PROB)
+steps = 20
+t0 = time.perf_counter()
+for _ in range(steps):
+    res = cm.dev_plane_ransac_multi(buf.ptr, begin, THR, PROB)
+multi_ms = (time.perf_counter() - t0) * 1e3 / steps
+t0 = time.perf_counter()
+for _ in range(steps):
+    for k in range(len(sizes)):
+        cm.dev_plane_ransac(buf.ptr + int(begin[k]) * 16, sizes[k], THR, PROB)
+single_ms = (time.perf_counter() - t0) * 1e3 / steps
+t0 = time.perf_counter()
+want = [oracle.plane_ransac(c, THR, PROB) for c in clouds]
+cpu_ms = (time.perf_counter() - t0) * 1e3
+same = all(r["iterations"] == w["iterations"] and r["n_inliers"] == len(w["inliers"]) for r, w in zip(res, want))
+print(json.dumps({"op": "plane_ransac_multi", "case": "5 ground zones of one sensor cloud", "points": int(begin[-1]),
+                  "iterations": [r["iterations"] for r in res], "gpu_ms_one_call": round(multi_ms, 4),
+                  "gpu_ms_five_calls": round(single_ms, 4), "cpu_port_ms": round(cpu_ms, 3), "same_result_as_cpu": bool(same)}))
+cm.close()

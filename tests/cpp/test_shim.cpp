@@ -161,6 +161,31 @@ int main() {
       }
       CHECK(total > roi_ptr->points.size() / 2 && total <= roi_ptr->points.size() + 16, "zones cover most of the ROI cloud (%zu of %zu)",
             total, roi_ptr->points.size());
+      // proceedX after getROI (:228-312): per zone getCloudPart + removeGround, appended zone after zone
+      Cloud::Ptr ng_all(new Cloud), g_all(new Cloud);
+      proceedZones(ctx, roi_ptr, parts, ng_all, g_all);
+      std::vector<float> want_g, want_ng;
+      for (size_t k = 0; k < parts.size(); ++k) {
+        const cmo_pass_t x = {0, parts[k].deviation, parts[k].deviation + parts[k].length, 0};
+        const std::vector<float> low = oracle_passes(roi_o, {x, {2, -parts[k].z_max_ground, parts[k].z_max_ground, 0}});
+        const std::vector<float> high = oracle_passes(roi_o, {x, {2, static_cast<float>(parts[k].z_max_ground + 0.01), prm.roi_z_max, 0}});
+        const int64_t n_low = static_cast<int64_t>(low.size() / 4);
+        std::vector<int32_t> inl(static_cast<size_t>(n_low) + 1);
+        const int64_t n_in = cmo_plane_ransac(low.data(), n_low, static_cast<double>(prm.distance_threshold), static_cast<double>(prm.prob),
+                                              prm.max_iterations, 1, 12345u, prm.sum_order, nullptr, nullptr, nullptr, inl.data());
+        std::vector<float> rest;
+        for (int64_t i = 0, j = 0; i < n_low; ++i) {
+          if (j < n_in && inl[static_cast<size_t>(j)] == i) { want_g.insert(want_g.end(), &low[i * 4], &low[i * 4] + 4); ++j; }
+          else rest.insert(rest.end(), &low[i * 4], &low[i * 4] + 4);
+        }
+        const int64_t n_rest = static_cast<int64_t>(rest.size() / 4);
+        std::vector<int32_t> keep(static_cast<size_t>(n_rest) + 1);
+        const int64_t kk = cmo_radius_outlier(rest.data(), n_rest, static_cast<double>(prm.radius), static_cast<int32_t>(prm.min_neighbor), 0, keep.data());
+        for (int64_t i = 0; i < kk; ++i) want_ng.insert(want_ng.end(), &rest[static_cast<size_t>(keep[i]) * 4], &rest[static_cast<size_t>(keep[i]) * 4] + 4);
+        want_ng.insert(want_ng.end(), high.begin(), high.end());
+      }
+      expect_cloud(*g_all, want_g, want_g.size() / 4, "proceedZones ground");
+      expect_cloud(*ng_all, want_ng, want_ng.size() / 4, "proceedZones no_ground");
     }
     // outlierRemoval(cloud_ptr) on a copy of the ROI cloud (in the reference it runs on the RANSAC outliers, :119)
     {

@@ -110,3 +110,53 @@ def test_plane_ransac_degenerate_inputs(gpu_ok, oracle):
         check(cm, oracle, bad)
         with pytest.raises(Exception):
             cm.plane_ransac(bad, THR, sum_order=7)
+
+
+def test_plane_ransac_multi_equals_separate_searches(gpu_ok, oracle):
+    """Five ground zones of one sensor cloud in one call (what a proceedX of the reference runs one after the other,
+    pc_preprocessing_main.cpp:228-312) -- every cloud must come out exactly as its own search: different sizes, one empty,
+    one below three points, one collinear, one that needs several batches."""
+    t = np.arange(40, dtype=np.float32)
+    clouds = [ground_scene(31, 20000, 0.8), ground_scene(32, 3000, 0.5), np.zeros((0, 4), np.float32),
+              ground_scene(33, 9000, 0.12), ground_scene(34, 2, 1.0), np.column_stack([t, 2 * t, 4 * t, t]).astype(np.float32),
+              ground_scene(35, 12345, 0.65), ground_scene(36, 513, 0.9)]
+    begin = np.concatenate([[0], np.cumsum([len(c) for c in clouds])]).astype(np.int64)
+    allpts = np.ascontiguousarray(np.concatenate(clouds))
+    with CloudMerger(max_sensors=1, max_points_per_sensor=len(allpts), max_batch_points=len(allpts)) as cm:
+        buf = cm.upload(allpts)
+        for prob, optimize, order in ((PROB, True, 0), (0.999999, True, 1), (PROB, False, 2)):
+            got = cm.dev_plane_ransac_multi(buf.ptr, begin, THR, prob, 1000, optimize, 12345, order)
+            zones = cm.zone_out()
+            assert len(zones) == 2 * len(clouds)
+            for k, cloud in enumerate(clouds):
+                want = oracle.plane_ransac(cloud, THR, prob, 1000, optimize, 12345, order)
+                g = got[k]
+                for key in ("found", "iterations", "draws", "best_count"):
+                    assert g[key] == want[key], (k, key, g[key], want[key])
+                assert (g["sample"] == want["sample"]).all()
+                assert same_floats(g["coeff_ransac"], want["coeff_ransac"]) and same_floats(g["coeff"], want["coeff"])
+                gx, gi = zones[2 * k]
+                rx, ri = zones[2 * k + 1]
+                assert g["n_inliers"] == len(want["inliers"]) == len(gi)
+                assert (gi.astype(np.int64) - begin[k] == want["inliers"]).all()
+                rest = np.setdiff1d(np.arange(len(cloud)), want["inliers"])
+                assert (ri.astype(np.int64) - begin[k] == rest).all()
+                assert_bit_equal(gx, cloud[want["inliers"]], "ground coordinates")
+                assert_bit_equal(rx, cloud[rest], "no-ground coordinates")
+        with pytest.raises(Exception):
+            cm.dev_plane_ransac_multi(buf.ptr, np.arange(10, dtype=np.int64), THR)   # nine clouds
+
+
+def test_plane_ransac_multi_host_form(gpu_ok, oracle):
+    clouds = [ground_scene(41, 7000, 0.8), ground_scene(42, 100, 0.9), np.zeros((0, 4), np.float32), ground_scene(43, 2500, 0.4)]
+    with CloudMerger(max_sensors=1, max_points_per_sensor=16384, max_batch_points=16384) as cm:
+        got = cm.plane_ransac_multi(clouds, THR, PROB)
+        for cloud, g in zip(clouds, got):
+            want = oracle.plane_ransac(cloud, THR, PROB)
+            assert (g["found"], g["iterations"], g["draws"]) == (want["found"], want["iterations"], want["draws"])
+            assert same_floats(g["coeff"], want["coeff"])
+            assert (g["ground"][1] == want["inliers"]).all()
+            rest = np.setdiff1d(np.arange(len(cloud)), want["inliers"])
+            assert (g["rest"][1] == rest).all()
+            assert_bit_equal(g["ground"][0], cloud[want["inliers"]], "ground coordinates")
+            assert_bit_equal(g["rest"][0], cloud[rest], "no-ground coordinates")
