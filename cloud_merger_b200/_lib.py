@@ -126,6 +126,10 @@ SYMBOLS = {
     "cm_dev_radius_outlier": (C.c_int, [_H, C.c_void_p, C.c_int64, C.c_double, C.c_int, C.c_int, C.c_void_p]),
     "cm_radius_outlier": (C.c_int, [_H, C.c_void_p, C.c_int64, C.c_double, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
                                     C.c_int64, C.POINTER(C.c_int64)]),
+    "cm_dev_radius_outlier_multi": (C.c_int, [_H, C.c_void_p, C.POINTER(C.c_int64), C.c_int, C.c_double, C.c_int, C.c_int,
+                                              C.c_void_p]),
+    "cm_radius_outlier_multi": (C.c_int, [_H, C.c_void_p, C.POINTER(C.c_int64), C.c_int, C.c_double, C.c_int, C.c_int,
+                                          C.c_void_p, C.c_void_p, C.c_int64, C.POINTER(C.c_int64)]),
     "cm_dev_plane_ransac": (C.c_int, [_H, C.c_void_p, C.c_int64, C.POINTER(CmPlaneCfg), C.POINTER(CmPlane), C.c_void_p]),
     "cm_dev_plane_ransac_multi": (C.c_int, [_H, C.c_void_p, C.POINTER(C.c_int64), C.c_int, C.POINTER(CmPlaneCfg),
                                             C.POINTER(CmPlane), C.c_void_p]),

@@ -225,6 +225,31 @@ class CloudMerger:
                                                 oi.ctypes.data_as(C.c_void_p), C.c_int64(n), C.byref(k)))
         return ox[:k.value].copy(), oi[:k.value].copy()
 
+    def dev_radius_outlier_multi(self, xyzi_ptr: int, begin, radius: float, min_neighbors: int = 1, negative: bool = False,
+                                 stream: int = 0):
+        """Independent clouds [begin[k], begin[k+1]) of one device array in one pass; zone k of zone_out() = survivors of
+        cloud k (needs max_batch_frames >= number of clouds)."""
+        b = (C.c_int64 * len(begin))(*[int(v) for v in begin])
+        self._check(self._lib.cm_dev_radius_outlier_multi(self._h, C.c_void_p(xyzi_ptr or None), b, len(begin) - 1,
+                                                          C.c_double(radius), int(min_neighbors), int(negative),
+                                                          C.c_void_p(stream or None)))
+
+    def radius_outlier_multi(self, clouds, radius: float, min_neighbors: int = 1, negative: bool = False) -> list:
+        """Host-buffer form: per cloud (xyzi [k,4], idx [k] into that cloud)."""
+        arrs = [np.ascontiguousarray(c, np.float32).reshape(-1, 4) for c in clouds]
+        k = len(arrs)
+        begin = np.concatenate([[0], np.cumsum([len(a) for a in arrs])]).astype(np.int64)
+        n = int(begin[-1])
+        allpts = np.ascontiguousarray(np.concatenate(arrs)) if n else np.zeros((0, 4), np.float32)
+        ox = np.empty((max(n, 1), 4), np.float32)
+        oi = np.empty(max(n, 1), np.uint32)
+        ob = (C.c_int64 * (k + 1))()
+        b = (C.c_int64 * (k + 1))(*[int(v) for v in begin])
+        self._check(self._lib.cm_radius_outlier_multi(self._h, allpts.ctypes.data_as(C.c_void_p), b, k, C.c_double(radius),
+                                                      int(min_neighbors), int(negative), ox.ctypes.data_as(C.c_void_p),
+                                                      oi.ctypes.data_as(C.c_void_p), C.c_int64(n), ob))
+        return [(ox[ob[c]:ob[c + 1]].copy(), (oi[ob[c]:ob[c + 1]].astype(np.int64) - begin[c]).astype(np.uint32)) for c in range(k)]
+
     # -- RANSAC ground plane (pcl::SACSegmentation of removeGround, pc_preprocessing_main.cpp:95-117) ------------------------
     @staticmethod
     def _plane_cfg(distance_threshold, probability, max_iterations, optimize, seed, sum_order):

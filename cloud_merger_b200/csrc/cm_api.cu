@@ -1433,30 +1433,49 @@ int cm_memcpy_d2d(cm_handle_t h, void* dst_dev, const void* src_dev, size_t byte
 
 // ---- radius outlier removal ---------------------------------------------------------------------------------------------
 namespace {
-int radius_outlier_run(cm_handle_t h, const float4* pts, int64_t n_points, double radius, int min_neighbors, int negative,
-                       cudaStream_t st) {
+// clouds = the ranges [begin[k], begin[k+1]) of pts (frames of the cell key: no neighbours across clouds); output zone k =
+// the survivors of cloud k
+int radius_outlier_run(cm_handle_t h, const float4* pts, const int64_t* begin, int n_clouds, double radius, int min_neighbors,
+                       int negative, cudaStream_t st) {
   if (!(radius > 0.0) || min_neighbors < 0) return fail(h, CM_E_INVALID, "radius must be > 0 and min_neighbors >= 0");
+  if (n_clouds < 1 || n_clouds > CM_MAX_ZONES) return fail(h, CM_E_INVALID, "1 .. %d clouds per call", CM_MAX_ZONES);
+  if (begin[0] != 0) return fail(h, CM_E_INVALID, "begin[0] must be 0");
+  for (int c = 0; c < n_clouds; ++c)
+    if (begin[c + 1] < begin[c]) return fail(h, CM_E_INVALID, "begin must not decrease");
+  const int64_t n_points = begin[n_clouds];
   int rc = ensure_batch_ws(h);
   if (rc != CM_OK) return rc;
   Workspace& w = h->batch;
-  if (n_points < 0 || n_points > (int64_t)w.cap_points) return fail(h, CM_E_CAPACITY, "%lld points > capacity %u", (long long)n_points, w.cap_points);
+  if (n_points > (int64_t)w.cap_points) return fail(h, CM_E_CAPACITY, "%lld points > capacity %u", (long long)n_points, w.cap_points);
+  if ((uint32_t)n_clouds > w.cap_frames)
+    return fail(h, CM_E_CAPACITY, "%d clouds > max_batch_frames %u of this handle", n_clouds, w.cap_frames);
   rc = zone_ws_ensure(h, (size_t)n_points);
   if (rc != CM_OK) return rc;
   // cells a little wider than the radius: two points closer than the radius are then at most one cell apart on every
   // axis even after the float rounding of x * (1 / cell) (valid below 2^14 cells from the origin, checked on the device)
   const float cell = (float)radius * 1.00390625f;
   w.has_run = true; w.report_valid = false; w.profiled = false;
-  w.n_frames = 1; w.n_segs = 0; w.points_in = n_points; w.launches = 0;
+  w.n_frames = (uint32_t)n_clouds; w.n_segs = 0; w.points_in = n_points; w.launches = 0;
   w.ran_k1 = false; w.ran_voxel = false; w.stream = st; w.n_k1_tiles = 0; w.dense_valid = false;
   w.voxel_pts = pts;
   h->last = &w;
   CM_CUDA(h, cudaEventRecord(w.ev[EV_START], st));
   CM_CUDA(h, cudaMemsetAsync(w.meta, 0, w.ml.zero_bytes, st));
   VoxelParams vp;
-  fill_voxel_params(h, w, vp, pts, 1, (uint32_t)n_points);
+  fill_voxel_params(h, w, vp, pts, (uint32_t)n_clouds, (uint32_t)n_points);
   for (int k = 0; k < 3; ++k) vp.inv_leaf[k] = 1.0f / cell;
-  CM_CUDA(h, launch_minmax(pts, (uint32_t)n_points, vp.ctrl, vp.acc, const_cast<uint32_t*>(vp.frame_surv_start), st));
-  ++w.launches;
+  uint32_t* fss = const_cast<uint32_t*>(vp.frame_surv_start);
+  for (int c = 0; c < n_clouds; ++c) {  // bounding box of every cloud (its own cell grid)
+    const uint32_t n_here = (uint32_t)(begin[c + 1] - begin[c]);
+    if (!n_here) continue;
+    CM_CUDA(h, launch_minmax(pts + begin[c], n_here, vp.ctrl, vp.acc + c, fss + c, st));
+    ++w.launches;
+  }
+  if (n_clouds > 1 || n_points == 0) {  // the cloud ranges (the single-cloud launch above wrote them itself)
+    uint32_t starts[CM_MAX_ZONES + 1];
+    for (int c = 0; c <= n_clouds; ++c) starts[c] = (uint32_t)begin[c];
+    CM_CUDA(h, cudaMemcpyAsync(fss, starts, sizeof(uint32_t) * (size_t)(n_clouds + 1), cudaMemcpyHostToDevice, st));
+  }
   CM_CUDA(h, cudaEventRecord(w.ev[EV_K1], st));
   rc = run_voxel(h, w, vp, st, false, false);  // keys + sort only
   if (rc != CM_OK) return rc;
@@ -1470,7 +1489,7 @@ int radius_outlier_run(cm_handle_t h, const float4* pts, int64_t n_points, doubl
   CM_CUDA(h, launch_radius_count(vp, rp, st));
   ++w.launches;
   CM_CUDA(h, cudaEventRecord(w.ev[EV_CENT], st));
-  return zone_run(h, pts, n_points, st, true);
+  return zone_run(h, pts, n_points, st, true, n_clouds);
 }
 }  // namespace
 
@@ -1480,13 +1499,30 @@ int cm_dev_radius_outlier(cm_handle_t h, const float* xyzi_dev, int64_t n_points
   std::lock_guard<std::mutex> lk(h->mu);
   CM_CUDA(h, cudaSetDevice(h->device));
   if (n_points > 0 && (!xyzi_dev || (reinterpret_cast<uintptr_t>(xyzi_dev) & 15u))) return fail(h, CM_E_INVALID, "xyzi_dev must be 16-byte aligned");
-  return radius_outlier_run(h, reinterpret_cast<const float4*>(xyzi_dev), n_points, radius, min_neighbors, negative,
+  if (n_points < 0) return fail(h, CM_E_INVALID, "bad n_points");
+  const int64_t begin[2] = {0, n_points};
+  return radius_outlier_run(h, reinterpret_cast<const float4*>(xyzi_dev), begin, 1, radius, min_neighbors, negative,
                             static_cast<cudaStream_t>(stream));
 }
 
-int cm_radius_outlier(cm_handle_t h, const float* xyzi_host, int64_t n_points, double radius, int min_neighbors,
-                      int negative, float* out_xyzi, uint32_t* out_idx, int64_t capacity, int64_t* n_out) {
-  if (!h || !n_out || n_points < 0 || (n_points > 0 && !xyzi_host)) return CM_E_INVALID;
+int cm_dev_radius_outlier_multi(cm_handle_t h, const float* xyzi_dev, const int64_t* begin, int n_clouds, double radius,
+                                int min_neighbors, int negative, void* stream) {
+  if (!h || !begin) return CM_E_INVALID;
+  std::lock_guard<std::mutex> lk(h->mu);
+  CM_CUDA(h, cudaSetDevice(h->device));
+  if (n_clouds >= 1 && n_clouds <= CM_MAX_ZONES && begin[n_clouds] > 0 && (!xyzi_dev || (reinterpret_cast<uintptr_t>(xyzi_dev) & 15u)))
+    return fail(h, CM_E_INVALID, "xyzi_dev must be 16-byte aligned");
+  return radius_outlier_run(h, reinterpret_cast<const float4*>(xyzi_dev), begin, n_clouds, radius, min_neighbors, negative,
+                            static_cast<cudaStream_t>(stream));
+}
+
+int cm_radius_outlier_multi(cm_handle_t h, const float* xyzi_host, const int64_t* begin, int n_clouds, double radius,
+                            int min_neighbors, int negative, float* out_xyzi, uint32_t* out_idx, int64_t capacity,
+                            int64_t* out_begin) {
+  if (!h || !begin || !out_begin) return CM_E_INVALID;
+  if (n_clouds < 1 || n_clouds > CM_MAX_ZONES) return fail(h, CM_E_INVALID, "1 .. %d clouds per call", CM_MAX_ZONES);
+  const int64_t n_points = begin[n_clouds];
+  if (n_points < 0 || (n_points > 0 && !xyzi_host)) return CM_E_INVALID;
   cm_zone_out_t zo;
   {
     std::lock_guard<std::mutex> lk(h->mu);
@@ -1495,12 +1531,12 @@ int cm_radius_outlier(cm_handle_t h, const float* xyzi_host, int64_t n_points, d
     if (rc != CM_OK) return rc;
     cm_handle_s::ZoneWs& z = h->zw;
     if (!z.in_stage) CM_CUDA(h, dev_alloc(&z.in_stage, z.cap_points));
-    CM_CUDA(h, cudaMemcpyAsync(z.in_stage, xyzi_host, (size_t)n_points * 16, cudaMemcpyHostToDevice, nullptr));
-    rc = radius_outlier_run(h, z.in_stage, n_points, radius, min_neighbors, negative, nullptr);
+    if (n_points) CM_CUDA(h, cudaMemcpyAsync(z.in_stage, xyzi_host, (size_t)n_points * 16, cudaMemcpyHostToDevice, nullptr));
+    rc = radius_outlier_run(h, z.in_stage, begin, n_clouds, radius, min_neighbors, negative, nullptr);
     if (rc != CM_OK) return rc;
   }
   int rc = cm_get_zone_out(h, &zo);
-  *n_out = zo.begin[1];
+  for (int k = 0; k <= n_clouds; ++k) out_begin[k] = zo.begin[k];
   if (rc != CM_OK) return rc;
   {
     std::lock_guard<std::mutex> lk(h->mu);
@@ -1510,12 +1546,22 @@ int cm_radius_outlier(cm_handle_t h, const float* xyzi_host, int64_t n_points, d
     CM_CUDA(h, cudaMemcpy(&dev_err, &reinterpret_cast<Ctrl*>(w.meta + w.ml.off_ctrl)->error, sizeof(dev_err), cudaMemcpyDeviceToHost));
     if (dev_err == CM_DEV_E_KEY_RANGE) return fail(h, CM_E_KEY_RANGE, "radius too small for the extent of the cloud (cell grid exceeds the key range)");
     if (dev_err) return fail(h, CM_E_INTERNAL, "device error %u", dev_err);
-    const int64_t total = zo.begin[1];
+    const int64_t total = zo.begin[n_clouds];
     if (total > capacity) return fail(h, CM_E_CAPACITY, "%lld points kept, caller capacity %lld", (long long)total, (long long)capacity);
     if (out_xyzi && total) CM_CUDA(h, cudaMemcpy(out_xyzi, zo.xyzi, (size_t)total * 16, cudaMemcpyDeviceToHost));
     if (out_idx && total) CM_CUDA(h, cudaMemcpy(out_idx, zo.src, (size_t)total * 4, cudaMemcpyDeviceToHost));
   }
   return CM_OK;
+}
+
+int cm_radius_outlier(cm_handle_t h, const float* xyzi_host, int64_t n_points, double radius, int min_neighbors,
+                      int negative, float* out_xyzi, uint32_t* out_idx, int64_t capacity, int64_t* n_out) {
+  if (!h || !n_out || n_points < 0) return CM_E_INVALID;
+  const int64_t begin[2] = {0, n_points};
+  int64_t ob[2] = {0, 0};
+  const int rc = cm_radius_outlier_multi(h, xyzi_host, begin, 1, radius, min_neighbors, negative, out_xyzi, out_idx, capacity, ob);
+  *n_out = ob[1];
+  return rc;
 }
 
 // ---- RANSAC ground plane --------------------------------------------------------------------------------------------------

@@ -40,14 +40,22 @@ __global__ void __launch_bounds__(ROR_THREADS) k_ror_count(const VoxelParams p, 
     else return vals[j];
   };
   const uint32_t idx_bits = si.idx_bits;
-  const unsigned long long limit = idx_bits >= 64 ? ~0ull : (1ull << idx_bits);  // keys of frame >= 1: non-finite points
-  const unsigned long long key = key_at(i);
-  if (si.key_frames > 1u && key >= limit) return;  // never kept (the mask array was cleared)
-  const GridDev g = p.grid[0];
+  const unsigned long long full_key = key_at(i);
+  // several clouds in one call are frames of the key (frame f in the bits above idx_bits): neighbours are only searched
+  // inside the point's own frame. Keys of frame >= n_frames: non-finite points, never kept (the mask array was cleared).
+  const unsigned long long frame = idx_bits >= 64 ? 0ull : (full_key >> idx_bits);
+  if (frame >= p.n_frames) return;
+  const unsigned long long fbits = idx_bits >= 64 ? 0ull : (frame << idx_bits);
+  const unsigned long long key = full_key - fbits;
+  const GridDev g = p.grid[frame];
   // the cell margin (see the host side) only covers |coordinate / cell| < 2^14
   if (i == 0) {
     int worst = 0;
-    for (int a = 0; a < 3; ++a) worst = max(worst, max(abs(g.min_b[a]), abs(g.max_b[a])));
+    for (uint32_t f = 0; f < p.n_frames; ++f) {
+      if (p.frame_surv_start[f + 1] == p.frame_surv_start[f]) continue;
+      const GridDev gf = p.grid[f];
+      for (int a = 0; a < 3; ++a) worst = max(worst, max(abs(gf.min_b[a]), abs(gf.max_b[a])));
+    }
     if (worst >= (1 << 14)) atomicExch(&p.ctrl->error, (uint32_t)CM_DEV_E_KEY_RANGE);
   }
   const unsigned long long d0 = (unsigned long long)g.div_b[0], d1 = (unsigned long long)g.div_b[1],
@@ -63,7 +71,7 @@ __global__ void __launch_bounds__(ROR_THREADS) k_ror_count(const VoxelParams p, 
     for (int dy = -1; dy <= 1 && cnt < need; ++dy) {
       if ((dy < 0 && c1 == 0) || (dy > 0 && c1 + 1 >= d1)) continue;
       const unsigned long long row = ((c2 + dz) * d1 + (c1 + dy)) * d0;
-      const unsigned long long k_lo = row + x_lo, k_hi = row + x_hi;
+      const unsigned long long k_lo = fbits + row + x_lo, k_hi = fbits + row + x_hi;
       // lower bound of k_lo in the sorted keys
       uint32_t lo = 0, hi = M;
       while (lo < hi) {
@@ -80,7 +88,7 @@ __global__ void __launch_bounds__(ROR_THREADS) k_ror_count(const VoxelParams p, 
     }
   }
   const bool inlier = cnt > r.min_pts;
-  if (inlier != (r.negative != 0u)) r.mask[me] = 1;
+  if (inlier != (r.negative != 0u)) r.mask[me] = (unsigned short)(1u << frame);  // zone = cloud
 }
 
 }  // namespace

@@ -332,7 +332,13 @@ __device__ __forceinline__ void key_hist_tiles(const VoxelParams& p, uint32_t (*
   const uint32_t F = p.n_frames;
   const uint32_t n_pass = si.num_passes, idx_bits = si.idx_bits;
   const bool dense = p.tile_rec == nullptr;
-  const uint32_t n_tiles = dense ? (M + KH_DENSE_TILE - 1) / KH_DENSE_TILE : p.n_k1_tiles;
+  // dense input (no K1 tiles): frame f is the range [frame_surv_start[f], frame_surv_start[f+1]) and owns its own tiles
+  uint32_t n_tiles = p.n_k1_tiles;
+  if (dense) {
+    n_tiles = 0;
+    for (uint32_t f = 0; f < F; ++f)
+      n_tiles += (p.frame_surv_start[f + 1] - p.frame_surv_start[f] + KH_DENSE_TILE - 1) / KH_DENSE_TILE;
+  }
   KeyT* __restrict__ keys = reinterpret_cast<KeyT*>(p.keys_a);
   uint32_t* __restrict__ vals = p.vals_a;
   uint2* __restrict__ recs = reinterpret_cast<uint2*>(p.keys_a);
@@ -342,8 +348,15 @@ __device__ __forceinline__ void key_hist_tiles(const VoxelParams& p, uint32_t (*
   for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
     TileRec r;
     if (dense) {
-      r.slot0 = tile * KH_DENSE_TILE; r.dense0 = r.slot0; r.frame = 0;
-      r.count = min((uint32_t)KH_DENSE_TILE, M - r.slot0);
+      uint32_t t = tile, f = 0, f_begin = 0, f_end = 0;
+      for (; f < F; ++f) {
+        f_begin = p.frame_surv_start[f]; f_end = p.frame_surv_start[f + 1];
+        const uint32_t tf = (f_end - f_begin + KH_DENSE_TILE - 1) / KH_DENSE_TILE;
+        if (t < tf) break;
+        t -= tf;
+      }
+      r.frame = f; r.slot0 = f_begin + t * KH_DENSE_TILE; r.dense0 = r.slot0;
+      r.count = min((uint32_t)KH_DENSE_TILE, f_end - r.slot0);
     } else {
       const uint4 q = __ldg(reinterpret_cast<const uint4*>(p.tile_rec + tile));
       r.count = q.x; r.slot0 = q.y; r.frame = q.z; r.dense0 = q.w;
@@ -679,7 +692,7 @@ cudaError_t launch_grid_setup(const VoxelParams& p, cudaStream_t stream, TileRec
 }
 
 cudaError_t launch_key_hist(const VoxelParams& p, cudaStream_t stream) {
-  const uint32_t tiles = p.tile_rec ? p.n_k1_tiles : (p.max_points + KH_DENSE_TILE - 1) / KH_DENSE_TILE;
+  const uint32_t tiles = p.tile_rec ? p.n_k1_tiles : (p.max_points + KH_DENSE_TILE - 1) / KH_DENSE_TILE + p.n_frames;
   if (p.key_bytes == 4)
     k_voxel_key_hist<uint32_t><<<persistent_grid(tiles), VX_THREADS, 0, stream>>>(p);
   else

@@ -293,6 +293,15 @@ CM_API int cm_dev_radius_outlier(cm_handle_t h, const float* xyzi_dev, int64_t n
                                  int min_neighbors, int negative, void* stream);
 CM_API int cm_radius_outlier(cm_handle_t h, const float* xyzi_host, int64_t n_points, double radius, int min_neighbors,
                              int negative, float* out_xyzi, uint32_t* out_idx, int64_t capacity, int64_t* n_out);
+/* Several independent clouds in one pass (the per-zone outlierRemoval calls of one proceedX): cloud k = the points
+ * [begin[k], begin[k+1]) of the array (begin[0] == 0, n_clouds <= CM_MAX_ZONES and <= the handle's max_batch_frames).
+ * Every cloud has its own cell grid and neighbours are never counted across clouds. Results: zone k of cm_get_zone_out =
+ * the survivors of cloud k (src = index in the whole array); the host form writes n_clouds + 1 offsets to out_begin. */
+CM_API int cm_dev_radius_outlier_multi(cm_handle_t h, const float* xyzi_dev, const int64_t* begin, int n_clouds,
+                                       double radius, int min_neighbors, int negative, void* stream);
+CM_API int cm_radius_outlier_multi(cm_handle_t h, const float* xyzi_host, const int64_t* begin, int n_clouds, double radius,
+                                   int min_neighbors, int negative, float* out_xyzi, uint32_t* out_idx, int64_t capacity,
+                                   int64_t* out_begin);
 /* RANSAC ground plane. Replaces the pcl::SACSegmentation + pcl::ExtractIndices block of removeGround()
  * (pc_preprocessing_main.cpp:95-117): SACMODEL_PLANE, SAC_RANSAC (setAxis / setEpsAngle are ignored by that model, as in
  * PCL). The three-index draws are PCL 1.8.1's -- boost::mt19937 seeded with cfg->seed, uniform_int<>(0, INT_MAX), the

@@ -120,7 +120,7 @@ class Context {
     cfg.max_point_step = 32;
     cfg.frames_in_flight = 2;
     cfg.max_batch_points = max_points_per_cloud * max_sensors;
-    cfg.max_batch_frames = 1;
+    cfg.max_batch_frames = CM_MAX_ZONES;  // several zone clouds per radius_outlier_multi call
     cfg.out_point_step = 32;  // pcl::PointXYZI records straight out of the kernels
     rc_ = cm_create(&cfg, &h_);
     if (rc_ != CM_OK) { h_ = nullptr; err_ = cm_strerror(rc_); }
@@ -195,29 +195,46 @@ class Context {
     return true;
   }
 
-  // Radius outlier removal of ONE host cloud (cm_radius_outlier); out keeps input order.
-  bool radius_outlier(const Cloud& in, Cloud& out, double radius, int min_neighbors) {
-    if (!check(h_ ? CM_OK : CM_E_NO_DEVICE)) return clear(out);
-    const int64_t n = static_cast<int64_t>(in.points.size());
-    if (n > max_points_ * max_sensors_) { rc_ = CM_E_CAPACITY; err_ = "cloud larger than the context capacity"; return clear(out); }
-    tmp_.resize(static_cast<size_t>(n) * 4);
-    for (int64_t i = 0; i < n; ++i) {
-      const PointXYZI& p = in.points[static_cast<size_t>(i)];
-      tmp_[i * 4 + 0] = p.x; tmp_[i * 4 + 1] = p.y; tmp_[i * 4 + 2] = p.z; tmp_[i * 4 + 3] = p.intensity;
-    }
+  // Radius outlier removal of several host clouds in one pass (cm_radius_outlier_multi; at most CM_MAX_ZONES clouds):
+  // every cloud is filtered on its own (no neighbours across clouds); out[k] keeps the order of in[k].
+  bool radius_outlier_multi(const std::vector<const Cloud*>& in, std::vector<Cloud>& out, double radius, int min_neighbors) {
+    const size_t k = in.size();
+    out.assign(k, Cloud());
+    if (!check(h_ ? CM_OK : CM_E_NO_DEVICE)) return false;
+    std::vector<int64_t> begin(k + 1, 0);
+    for (size_t c = 0; c < k; ++c) begin[c + 1] = begin[c] + static_cast<int64_t>(in[c]->points.size());
+    const int64_t n = begin[k];
+    if (n > max_points_ * max_sensors_) { rc_ = CM_E_CAPACITY; err_ = "clouds larger than the context capacity"; return false; }
+    tmp_.resize(static_cast<size_t>(n) * 4 + 4);
+    for (size_t c = 0; c < k; ++c)
+      for (size_t i = 0; i < in[c]->points.size(); ++i) {
+        const PointXYZI& p = in[c]->points[i];
+        float* o = &tmp_[(static_cast<size_t>(begin[c]) + i) * 4];
+        o[0] = p.x; o[1] = p.y; o[2] = p.z; o[3] = p.intensity;
+      }
     zone_xyzi_.resize(static_cast<size_t>(n) * 4 + 4);
-    int64_t kept = 0;
-    if (!check(cm_radius_outlier(h_, tmp_.data(), n, radius, min_neighbors, 0, zone_xyzi_.data(), nullptr, n, &kept)))
-      return clear(out);
-    Cloud res;
-    res.points.resize(static_cast<size_t>(kept));
-    for (size_t i = 0; i < static_cast<size_t>(kept); ++i) {
-      PointXYZI& p = res.points[i];
-      p = PointXYZI();
-      p.x = zone_xyzi_[i * 4 + 0]; p.y = zone_xyzi_[i * 4 + 1]; p.z = zone_xyzi_[i * 4 + 2]; p.intensity = zone_xyzi_[i * 4 + 3];
+    std::vector<int64_t> ob(k + 1, 0);
+    if (!check(cm_radius_outlier_multi(h_, tmp_.data(), begin.data(), static_cast<int>(k), radius, min_neighbors, 0,
+                                       zone_xyzi_.data(), nullptr, n, ob.data())))
+      return false;
+    for (size_t c = 0; c < k; ++c) {
+      Cloud& res = out[c];
+      const size_t b = static_cast<size_t>(ob[c]), e = static_cast<size_t>(ob[c + 1]);
+      res.points.resize(e - b);
+      for (size_t i = b; i < e; ++i) {
+        PointXYZI& p = res.points[i - b];
+        p = PointXYZI();
+        p.x = zone_xyzi_[i * 4 + 0]; p.y = zone_xyzi_[i * 4 + 1]; p.z = zone_xyzi_[i * 4 + 2]; p.intensity = zone_xyzi_[i * 4 + 3];
+      }
+      finish(res, *in[c], true);
     }
-    finish(res, in, true);
-    out = res;
+    return true;
+  }
+  // one cloud
+  bool radius_outlier(const Cloud& in, Cloud& out, double radius, int min_neighbors) {
+    std::vector<Cloud> res;
+    if (!radius_outlier_multi({&in}, res, radius, min_neighbors)) return clear(out);
+    out = res[0];
     return true;
   }
 
@@ -450,7 +467,7 @@ inline void removeGround(Context& ctx, const Cloud::Ptr& cloud_ptr, const Cloud:
 
 // proceedFront / proceedRear / proceedTop / proceedLivox after getROI -- :228-312: per zone getCloudPart + removeGround,
 // results appended zone after zone. Here: one zone-slicing pass for all x and z windows, one multi-cloud RANSAC pass for
-// all ground windows, then per zone outlierRemoval of what is not ground and the points above the window appended.
+// all ground windows, one multi-cloud outlierRemoval pass for what is not ground, and the points above each window appended.
 inline void proceedZones(Context& ctx, const Cloud::Ptr& cloud_ROI_ptr, const std::vector<ZonePart>& parts,
                          const Cloud::Ptr& no_ground_ptr, const Cloud::Ptr& ground_ptr) {
   std::vector<Cloud::Ptr> ground_part, upper_part;
@@ -459,13 +476,16 @@ inline void proceedZones(Context& ctx, const Cloud::Ptr& cloud_ROI_ptr, const st
   for (const Cloud::Ptr& g : ground_part) in.push_back(g.get());
   std::vector<Cloud> ground, rest;
   ctx.plane_ransac_multi(in, ground, rest);
+  std::vector<const Cloud*> rest_in;
+  for (const Cloud& r : rest) rest_in.push_back(&r);
+  std::vector<Cloud> kept;  // outlierRemoval(no_ground_cloud_ptr) of every zone, one pass
+  ctx.radius_outlier_multi(rest_in, kept, static_cast<double>(ctx.params().radius), static_cast<int>(ctx.params().min_neighbor));
   Cloud no_ground_all, ground_all;
   for (size_t k = 0; k < parts.size(); ++k) {
-    Cloud::Ptr ng(new Cloud(rest[k]));
-    outlierRemoval(ctx, ng);
-    *ng += *upper_part[k];
-    if (k == 0) { no_ground_all = *ng; ground_all = ground[k]; }
-    else { no_ground_all += *ng; ground_all += ground[k]; }
+    Cloud ng = kept[k];
+    ng += *upper_part[k];
+    if (k == 0) { no_ground_all = ng; ground_all = ground[k]; }
+    else { no_ground_all += ng; ground_all += ground[k]; }
   }
   *no_ground_ptr = no_ground_all;
   *ground_ptr = ground_all;

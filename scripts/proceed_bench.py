@@ -1,6 +1,6 @@
 """The whole body of a proceedX of the reference after getROI (pc_preprocessing_main.cpp:228-312: five x windows, per window
 the two z windows, the RANSAC plane + ExtractIndices, outlierRemoval, appended) on one sensor ROI cloud: GPU (one
-zone-slicing pass, one multi-cloud RANSAC pass, per-zone radius outlier removal; device-resident between the stages) next
+zone-slicing pass, one multi-cloud RANSAC pass, one multi-cloud radius outlier removal; device-resident between the stages) next
 to the CPU restatement (oracle, one core) of the same sequence. One JSON line; wall clock, results compared."""
 import json
 import os
@@ -65,17 +65,20 @@ def gpu_chain(cms, buf, n, scratch):
     res = cp.dev_plane_ransac_multi(z_xyzi, begin[:k + 1], THR, PROB)
     p_xyzi, _, p_begin = cp.zone_out_raw()
     pb = np.array(p_begin, np.int64)
-    no_ground, ground = [], []
+    # what is not ground, zone by zone: the rest clouds are zones 1, 3, 5, ... of the plane handle; gather them side by
+    # side in the scratch buffer and filter them in one multi-cloud pass
+    rb = [0]
     for i in range(k):
         n_rest = int(pb[2 * i + 2] - pb[2 * i + 1])
-        cr.dev_radius_outlier(p_xyzi + int(pb[2 * i + 1]) * 16, n_rest, RADIUS, 1)
-        kept = cr.radius_outlier_out()[0]
-        no_ground.append(kept)
+        cr.memcpy_d2d(scratch.ptr + rb[-1] * 16, p_xyzi + int(pb[2 * i + 1]) * 16, n_rest * 16)
+        rb.append(rb[-1] + n_rest)
+    cr.dev_radius_outlier_multi(scratch.ptr, rb, RADIUS, 1)
+    kept = cr.zone_out()
     pts_plane = cp.zone_out()
     pts_zone = cz.zone_out()
-    out_ng = []
+    out_ng, ground = [], []
     for i in range(k):
-        out_ng += [no_ground[i], pts_zone[k + i][0]]
+        out_ng += [kept[i][0], pts_zone[k + i][0]]
         ground.append(pts_plane[2 * i][0])
     return np.concatenate(out_ng), np.concatenate(ground), res
 
@@ -84,16 +87,17 @@ for rings, az in ((64, 2048), (128, 4096)):
     cloud = roi_cloud(7, rings, az)
     n = len(cloud)
     zones = zones_of(PARTS)
-    cms = tuple(CloudMerger(max_sensors=1, max_points_per_sensor=n, max_batch_points=n) for _ in range(3))
+    cms = tuple(CloudMerger(max_sensors=1, max_points_per_sensor=n, max_batch_points=n, max_batch_frames=8) for _ in range(3))
     cms[0].set_zones(zones)
     buf = cms[0].upload(cloud)
+    scratch = cms[2].upload(np.zeros((n, 4), np.float32))
     for _ in range(3):
-        g_ng, g_g, res = gpu_chain(cms, buf, n, None)
+        g_ng, g_g, res = gpu_chain(cms, buf, n, scratch)
     torch.cuda.synchronize()
     steps = 10
     t0 = time.perf_counter()
     for _ in range(steps):
-        g_ng, g_g, res = gpu_chain(cms, buf, n, None)
+        g_ng, g_g, res = gpu_chain(cms, buf, n, scratch)
     gpu_ms = (time.perf_counter() - t0) * 1e3 / steps
     t0 = time.perf_counter()
     c_ng, c_g = cpu_chain(cloud, zones)

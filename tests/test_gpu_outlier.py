@@ -89,3 +89,36 @@ def test_radius_outlier_properties_full_size(gpu_ok):
     assert_bit_equal(x1, cloud[i1], "kept coordinates")
     assert set(i3.tolist()) <= set(i1.tolist()) and 0 < len(i3) < len(i1) < n
     assert len(i1) + len(in_) == n and len(np.intersect1d(i1, in_)) == 0
+
+
+def test_radius_outlier_multi_equals_separate_runs(gpu_ok, oracle):
+    """Several clouds in one call (the per-zone outlierRemoval calls of one proceedX): every cloud must come out exactly as
+    its own run -- neighbours are never counted across clouds, even where two clouds overlap in space; empty and tiny
+    clouds and clouds with non-finite points in between."""
+    a = _roi_cloud(oracle, 4400, 32, 512)
+    b = _roi_cloud(oracle, 4401, 16, 256, sensor=1)
+    shifted = a.copy()
+    shifted[:, 0] += np.float32(0.05)          # lies inside `a`'s space: cross-cloud neighbours would change the result
+    bad = b.copy()
+    bad[::53, 1] = np.nan
+    clouds = [a, shifted, np.zeros((0, 4), np.float32), b[:1], bad, b[:2], a[::3]]
+    total = sum(len(c) for c in clouds)
+    with CloudMerger(max_sensors=1, max_points_per_sensor=total, max_batch_points=total, max_batch_frames=8) as cm:
+        for min_pts, neg in ((1, False), (2, True)):
+            got = cm.radius_outlier_multi(clouds, RADIUS, min_pts, neg)
+            assert len(got) == len(clouds)
+            for c, (gx, gi) in zip(clouds, got):
+                want = oracle.radius_outlier(c, RADIUS, min_pts, neg)
+                assert len(gi) == len(want) and (gi == want).all()
+                assert_bit_equal(gx, c[want], "survivor coordinates")
+        # device form
+        begin = np.concatenate([[0], np.cumsum([len(c) for c in clouds])]).astype(np.int64)
+        buf = cm.upload(np.ascontiguousarray(np.concatenate(clouds)))
+        cm.dev_radius_outlier_multi(buf.ptr, begin, RADIUS, 1)
+        zones = cm.zone_out()
+        for k, c in enumerate(clouds):
+            want = oracle.radius_outlier(c, RADIUS, 1, False)
+            assert (zones[k][1].astype(np.int64) - begin[k] == want).all()
+    with CloudMerger(max_sensors=1, max_points_per_sensor=total, max_batch_points=total) as cm1:   # one frame only
+        with pytest.raises(CloudMergerError):
+            cm1.radius_outlier_multi(clouds[:2], RADIUS, 1)
