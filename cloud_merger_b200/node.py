@@ -1,0 +1,149 @@
+"""Device-resident mirror of one main-loop iteration of the reference's built node `pcl_preprocessing`
+(pcl_preprocessing/src/pc_preprocessing_main.cpp):
+
+    callbackX      :318-470   pcl_ros::transformPointCloud into base_footprint, then proceedX
+    proceedX       :228-312   getROI, five x windows (getCloudPart), per window removeGround:
+    removeGround   :71-122      two z windows, RANSAC plane + ExtractIndices, outlierRemoval of what is not ground,
+                                the points above the window appended
+    fusePointclouds:131-160   no_ground / ground clouds of all sensors appended in sensor order
+    voxelgrid      :168-177   VoxelGrid of the fused no_ground cloud
+
+Everything between the upload of the raw sensor clouds and the download of the three published clouds stays in device
+memory. The stages are the C-ABI calls of include/cloud_merger_gpu.h, each on its own handle because a stage's results
+live in its handle's workspace until that handle runs again: transform + ROI crop of all sensors in one launch (frame =
+sensor), per sensor one zone-slicing pass, one multi-cloud plane search and one multi-cloud radius outlier removal,
+device-to-device appends, one VoxelGrid.
+
+Host glue, not a kernel: there is no CPU fallback and no arithmetic on points here.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass, field
+from typing import List, Optional, Sequence, Tuple
+
+import numpy as np
+
+from .api import ROI_PASSES, CloudMerger, make_layout
+
+# {length, deviation, z_max_ground} per x window, front to rear: Parameter.h:45-55 with roi_mid = 15 (proceedFront)
+FRONT_PARTS = ((30.0, 30.0, 2.5), (11.0, 19.0, 2.0), (15.0, 4.0, 1.5), (8.0, -4.0, 0.3), (11.0, -15.0, 0.5))
+
+
+def zones_of_parts(parts, roi_z_max: float):
+    """The PassThrough chains getCloudPart + removeGround run per x window: first all ground windows
+    (x in [dev, dev + len], z in [-zg, zg]), then all upper windows (z in [zg + 0.01, roi_z_max]; `+ 0.01` is the reference's
+    double sum narrowed to float by setFilterLimits)."""
+    low, high = [], []
+    for (length, dev, zg) in parts:
+        x = (0, float(np.float32(dev)), float(np.float32(np.float32(dev) + np.float32(length))), 0)
+        zf = np.float32(zg)
+        low.append([x, (2, float(-zf), float(zf), 0)])
+        high.append([x, (2, float(np.float32(np.float64(zf) + 0.01)), float(np.float32(roi_z_max)), 0)])
+    return low + high
+
+
+@dataclass
+class NodeParams:
+    """Parameter.h of pcl_preprocessing (:23-42)."""
+    roi_passes: Sequence[Tuple[int, float, float, int]] = tuple(ROI_PASSES)
+    roi_z_max: float = 3.0
+    voxel_size: float = 0.1
+    points_per_voxel: int = 2
+    radius: float = float(np.float32(0.15))
+    min_neighbor: int = 1
+    max_iterations: int = 1000
+    distance_threshold: float = float(np.float32(0.3))
+    prob: float = float(np.float32(0.99))
+    sum_order: int = 0
+    parts: Sequence[Sequence[Tuple[float, float, float]]] = field(default_factory=lambda: [FRONT_PARTS])  # per sensor (cycled)
+
+
+class PreprocessingNode:
+    def __init__(self, n_sensors: int, max_points_per_sensor: int, params: Optional[NodeParams] = None, device: int = 0):
+        self.S = n_sensors
+        self.p = params or NodeParams()
+        n = n_sensors * max_points_per_sensor
+        mk = lambda frames: CloudMerger(device=device, max_sensors=n_sensors, max_points_per_sensor=max_points_per_sensor,
+                                        max_batch_points=n, max_batch_frames=frames)
+        self.crop = mk(n_sensors)   # transform + getROI of every sensor, one frame per sensor
+        self.zones = mk(1)
+        self.plane = mk(1)
+        self.ror = mk(8)
+        self.voxel = mk(1)
+        self.crop.set_crop(self.p.roi_passes)
+        self.voxel.set_voxel(self.p.voxel_size, self.p.points_per_voxel, True)
+        self.raw = [self.crop.device_buffer(max_points_per_sensor * 16) for _ in range(n_sensors)]
+        self.rest = self.ror.device_buffer(max_points_per_sensor * 16)       # what is not ground, window after window
+        self.no_ground = self.voxel.device_buffer(2 * n * 16)                # fused clouds (windows share their end points)
+        self.ground = self.voxel.device_buffer(2 * n * 16)
+        self._zones_set = None
+
+    def close(self):
+        for h in (self.crop, self.zones, self.plane, self.ror, self.voxel):
+            h.close()
+
+    def set_extrinsic(self, sensor: int, m: np.ndarray):
+        self.crop.set_extrinsic(sensor, m)
+
+    def _set_zones(self, sensor: int):
+        parts = tuple(map(tuple, self.p.parts[sensor % len(self.p.parts)]))
+        if parts != self._zones_set:
+            self.zones.set_zones(zones_of_parts(parts, self.p.roi_z_max))
+            self._zones_set = parts
+        return len(parts)
+
+    def frame(self, clouds: Sequence[np.ndarray], download: bool = True) -> dict:
+        """clouds: one packed xyzi float32 array per sensor (sensor frame). Returns the three clouds the node publishes
+        (/points_no_ground, /points_ground, /points_voxel) -- device pointers + sizes, and host copies when `download`."""
+        p = self.p
+        items = []
+        for s, c in enumerate(clouds):
+            a = np.ascontiguousarray(c, np.float32).reshape(-1, 4)
+            self.raw[s].upload(a)
+            items.append((self.raw[s].ptr, len(a), make_layout(), s, s))
+        self.crop.dev_transform_crop(self.crop.make_segments(items))
+        self.crop.sync()
+        info = self.crop.frame_info()
+        roi = self.crop.device_out().survivor_xyzi
+        n_ng = n_g = 0
+        planes: List[dict] = []
+        d2d = self.voxel.memcpy_d2d
+        for s in range(len(clouds)):
+            b, e = info[s].survivor_begin, info[s].survivor_end
+            k = self._set_zones(s)
+            self.zones.dev_zone_split(roi + b * 16, e - b)
+            z_xyzi, _, zb = self.zones.zone_out_raw()
+            res = self.plane.dev_plane_ransac_multi(z_xyzi, zb[:k + 1], p.distance_threshold, p.prob, p.max_iterations, True,
+                                                    12345, p.sum_order)
+            planes += res
+            p_xyzi, _, pb = self.plane.zone_out_raw()
+            rb = [0]
+            for i in range(k):  # the rest clouds (odd zones) side by side
+                cnt = pb[2 * i + 2] - pb[2 * i + 1]
+                d2d(self.rest.ptr + rb[-1] * 16, p_xyzi + pb[2 * i + 1] * 16, cnt * 16)
+                rb.append(rb[-1] + cnt)
+            self.ror.dev_radius_outlier_multi(self.rest.ptr, rb, p.radius, p.min_neighbor)
+            r_xyzi, _, kb = self.ror.zone_out_raw()
+            for i in range(k):
+                cnt = kb[i + 1] - kb[i]                     # outlierRemoval(no_ground) ...
+                d2d(self.no_ground.ptr + n_ng * 16, r_xyzi + kb[i] * 16, cnt * 16)
+                n_ng += cnt
+                cnt = zb[k + i + 1] - zb[k + i]             # ... += the points above the window
+                d2d(self.no_ground.ptr + n_ng * 16, z_xyzi + zb[k + i] * 16, cnt * 16)
+                n_ng += cnt
+                cnt = pb[2 * i + 1] - pb[2 * i]             # ground += the inliers
+                d2d(self.ground.ptr + n_g * 16, p_xyzi + pb[2 * i] * 16, cnt * 16)
+                n_g += cnt
+        self.voxel.dev_voxelgrid(self.no_ground.ptr, n_ng)
+        self.voxel.sync()
+        st = self.voxel.stats()
+        vo = self.voxel.device_out()
+        out = {"n_no_ground": n_ng, "n_ground": n_g, "n_voxels": int(st.voxels_out), "no_ground_ptr": self.no_ground.ptr,
+               "ground_ptr": self.ground.ptr, "voxel_ptr": vo.voxel_xyzi, "planes": planes,
+               "roi_points": [int(i.survivor_end - i.survivor_begin) for i in info[:len(clouds)]]}
+        if download:
+            out["no_ground"] = self.voxel.download(self.no_ground.ptr, np.float32, n_ng * 4).reshape(-1, 4)
+            out["ground"] = self.voxel.download(self.ground.ptr, np.float32, n_g * 4).reshape(-1, 4)
+            v = out["n_voxels"]
+            out["voxel"] = self.voxel.download(vo.voxel_xyzi, np.float32, v * 4).reshape(-1, 4)
+        return out
