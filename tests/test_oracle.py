@@ -344,3 +344,17 @@ def test_plane_ransac_degenerate_inputs(oracle):
     blob = rng.uniform(-20, 20, (4000, 4)).astype(np.float32)
     r = oracle.plane_ransac(blob, 0.05, 0.99, 40)
     assert r["found"] and r["iterations"] == 41
+
+
+def test_node_zone_chains_are_the_reference_windows():
+    """Host logic of cloud_merger_b200/node.py: the PassThrough chains it configures for FRONT_PARTS are the ten windows of
+    proceedFront (tests/helpers.reference_front_zones), ground windows first, then the upper ones."""
+    from cloud_merger_b200.node import FRONT_PARTS, zones_of_parts
+    from helpers import reference_front_zones
+    ref = reference_front_zones()            # interleaved: ground_k, upper_k
+    got = zones_of_parts(FRONT_PARTS, 3.0)   # grouped: all ground windows, then all upper windows
+    k = len(FRONT_PARTS)
+    assert len(got) == 2 * k == len(ref)
+    for i in range(k):
+        assert [tuple(p) for p in got[i]] == [tuple(p) for p in ref[2 * i]]
+        assert [tuple(p) for p in got[k + i]] == [tuple(p) for p in ref[2 * i + 1]]
