@@ -358,3 +358,27 @@ def test_node_zone_chains_are_the_reference_windows():
     for i in range(k):
         assert [tuple(p) for p in got[i]] == [tuple(p) for p in ref[2 * i]]
         assert [tuple(p) for p in got[k + i]] == [tuple(p) for p in ref[2 * i + 1]]
+
+
+def test_plane_refit_against_float64_eigensolver(oracle):
+    """The restated float32 refit (running sums in PCL's order, covariance = E[ab] - E[a]E[b], pcl::eigen33's closed-form
+    smallest eigenvector) must agree with a float64 eigen-decomposition of the same inliers' covariance to float accuracy:
+    a transcription error in the cubic's roots or in the eigenvector selection would show here."""
+    thr = float(np.float32(0.3))
+    for seed, n, frac, slope in ((1, 20000, 0.8, 0.02), (2, 5000, 0.6, -0.05), (3, 800, 0.9, 0.0), (4, 60000, 0.5, 0.1)):
+        rng = np.random.default_rng(seed)
+        x = _ground_scene(seed, n, frac, slope=slope)
+        x[:, :3] += rng.uniform(-20, 20, 3).astype(np.float32)      # away from the origin: E[ab] - E[a]E[b] cancels
+        r0 = oracle.plane_ransac(x, thr, 0.99, 1000, optimize=False)
+        r1 = oracle.plane_ransac(x, thr, 0.99, 1000, optimize=True)
+        assert r0["found"] and r1["found"]
+        inl = x[r0["inliers"], :3].astype(np.float64)             # the refit runs on the RANSAC model's inliers
+        c = inl.mean(axis=0)
+        w, v = np.linalg.eigh(np.cov((inl - c).T, bias=True))
+        nrm = v[:, 0] * np.sign(v[2, 0])
+        got = r1["coeff"].astype(np.float64) * np.sign(r1["coeff"][2])
+        # float32 sums of squares far from the origin lose ~1e-4 of relative accuracy in the covariance; the plane normal
+        # of a 60 m x 20 m patch with centimetre noise tolerates that to a few 1e-3
+        assert np.abs(got[:3] - nrm).max() < 5e-3, (seed, got[:3], nrm)
+        assert abs(got[3] + float(nrm @ c)) < 0.1, (seed, got[3], -float(nrm @ c))
+        assert abs(np.linalg.norm(got[:3]) - 1.0) < 1e-5
