@@ -160,3 +160,20 @@ def test_plane_ransac_multi_host_form(gpu_ok, oracle):
             assert (g["rest"][1] == rest).all()
             assert_bit_equal(g["ground"][0], cloud[want["inliers"]], "ground coordinates")
             assert_bit_equal(g["rest"][0], cloud[rest], "no-ground coordinates")
+
+
+def test_plane_ransac_golden_fixture(gpu_ok):
+    """The committed fixture tests/golden/plane_ransac.json (numpy restatement, no refit) through the C ABI."""
+    import json
+    import os
+    doc = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "plane_ransac.json")))
+    with CloudMerger(max_sensors=1, max_points_per_sensor=4096, max_batch_points=4096) as cm:
+        for c in doc["cases"]:
+            x = np.array(c["xyzi"], np.float32)
+            e = c["expected"]
+            r = cm.plane_ransac(x, c["threshold"], c["probability"], c["max_iterations"], False, c["seed"], c["sum_order"])
+            assert (r["found"], r["iterations"], r["draws"], r["best_count"]) == (e["found"], e["iterations"], e["draws"], e["best_count"])
+            assert r["sample"].tolist() == e["sample"]
+            if e["found"]:
+                assert r["coeff_ransac"].view(np.uint32).tolist() == e["coeff_ransac_bits"]
+            assert r["ground"][1].tolist() == e["inliers"]

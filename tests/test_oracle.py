@@ -381,3 +381,23 @@ def test_plane_refit_against_float64_eigensolver(oracle):
         assert np.abs(got[:3] - nrm).max() < 1e-4, (seed, got[:3], nrm)
         assert abs(got[3] + float(nrm @ c)) < 2e-3, (seed, got[3], -float(nrm @ c))
         assert abs(np.linalg.norm(got[:3]) - 1.0) < 1e-5
+
+
+def test_plane_ransac_golden_fixture(oracle):
+    """tests/golden/plane_ransac.json (written by the numpy restatement, tests/golden/make_plane_fixture.py) against the
+    C++ oracle: sampler engine outputs, sample, iteration / draw counts, coefficients bit for bit, inlier set."""
+    import json
+    import os
+    doc = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "plane_ransac.json")))
+    for i, v in enumerate(doc["mt19937_seed_12345_first_outputs"]):
+        assert oracle.mt19937_at(12345, i) == v
+    for c in doc["cases"]:
+        x = np.array(c["xyzi"], np.float32)
+        e = c["expected"]
+        r = oracle.plane_ransac(x, c["threshold"], c["probability"], c["max_iterations"], optimize=False, seed=c["seed"],
+                                sum_order=c["sum_order"])
+        assert (r["found"], r["iterations"], r["draws"], r["best_count"]) == (e["found"], e["iterations"], e["draws"], e["best_count"])
+        assert r["sample"].tolist() == e["sample"]
+        if e["found"]:
+            assert r["coeff_ransac"].view(np.uint32).tolist() == e["coeff_ransac_bits"]
+        assert r["inliers"].tolist() == e["inliers"]
