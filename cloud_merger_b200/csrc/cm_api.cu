@@ -1218,11 +1218,23 @@ int zone_ws_ensure(cm_handle_t h, size_t points) {
   return CM_OK;
 }
 
+// A stage writes its results into the handle's zone outputs: an input that lives there would be overwritten while it is
+// still being read (chain stages over separate handles, or copy the cloud out first).
+bool in_zone_outputs(cm_handle_t h, const void* p, int64_t n_points) {
+  const cm_handle_s::ZoneWs& z = h->zw;
+  if (!p || !z.out_xyzi || n_points <= 0) return false;
+  const uintptr_t a = reinterpret_cast<uintptr_t>(p), b = a + (uintptr_t)n_points * 16u;
+  const uintptr_t lo = reinterpret_cast<uintptr_t>(z.out_xyzi), hi = lo + (uintptr_t)z.cap_out * 16u;
+  return a < hi && b > lo;
+}
+
 int zone_run(cm_handle_t h, const float4* pts, int64_t n_points, cudaStream_t st, bool mask_given = false,
              int given_zones = 1) {
   cm_handle_s::ZoneWs& z = h->zw;
   if (!mask_given && h->zones.n_zones <= 0) return fail(h, CM_E_INVALID, "no zones configured (cm_set_zones)");
   if (n_points < 0 || n_points > 0xFFFFFFF0ll) return fail(h, CM_E_INVALID, "bad n_points");
+  if (in_zone_outputs(h, pts, n_points))
+    return fail(h, CM_E_INVALID, "the input cloud lies in this handle's own zone outputs (use another handle or copy it out)");
   int rc = zone_ws_ensure(h, (size_t)n_points);
   if (rc != CM_OK) return rc;
   ZoneParams zp;
@@ -1443,6 +1455,7 @@ int radius_outlier_run(cm_handle_t h, const float4* pts, const int64_t* begin, i
   for (int c = 0; c < n_clouds; ++c)
     if (begin[c + 1] < begin[c]) return fail(h, CM_E_INVALID, "begin must not decrease");
   const int64_t n_points = begin[n_clouds];
+  if (in_zone_outputs(h, pts, n_points)) return fail(h, CM_E_INVALID, "the input cloud lies in this handle's own zone outputs (use another handle or copy it out)");
   int rc = ensure_batch_ws(h);
   if (rc != CM_OK) return rc;
   Workspace& w = h->batch;
@@ -1723,6 +1736,7 @@ int plane_ransac_run(cm_handle_t h, const float4* pts, const int64_t* begin, int
   const int64_t n_points = begin[n_clouds];
   if (n_points > 0x7FFFFFF0ll) return fail(h, CM_E_INVALID, "bad n_points");
   if (cfg.max_iterations < 0 || cfg.sum_order < 0 || cfg.sum_order > 2) return fail(h, CM_E_INVALID, "bad plane settings");
+  if (in_zone_outputs(h, pts, n_points)) return fail(h, CM_E_INVALID, "the input cloud lies in this handle's own zone outputs (use another handle or copy it out)");
   int rc = zone_ws_ensure(h, (size_t)n_points);
   if (rc != CM_OK) return rc;
   rc = plane_ws_ensure(h);

@@ -309,6 +309,8 @@ CM_API int cm_radius_outlier_multi(cm_handle_t h, const float* xyzi_host, const 
  * to the batch in draw order, so model, iteration count and inliers are those of PCL's sequential loop. With optimize the
  * least-squares refit follows (float running sums in inlier order as computeMeanAndCovarianceMatrix forms them, pcl::eigen33
  * on the host) and the inliers are selected again.
+ * Zone slicing, radius outlier removal and the plane search write their results into the handle's zone outputs
+ * (cm_get_zone_out): an input cloud that lies there is refused with CM_E_INVALID -- chain stages over separate handles.
  *  cm_dev_plane_ransac: n packed float4 xyzi points on the device; blocks until the model is known. Results: *out, and
  *      through cm_get_zone_out two zones in input order -- zone 0 the inliers (ground_cloud), zone 1 the rest
  *      (no_ground_cloud before outlierRemoval), src = index in the input.

@@ -177,3 +177,22 @@ def test_plane_ransac_golden_fixture(gpu_ok):
             if e["found"]:
                 assert r["coeff_ransac"].view(np.uint32).tolist() == e["coeff_ransac_bits"]
             assert r["ground"][1].tolist() == e["inliers"]
+
+
+def test_stage_input_must_not_alias_the_handles_own_outputs(gpu_ok):
+    """A stage writes into its handle's zone outputs; feeding it a cloud that lives there is refused, not corrupted."""
+    from cloud_merger_b200 import CloudMergerError
+    cloud = ground_scene(51, 4000, 0.8)
+    with CloudMerger(max_sensors=1, max_points_per_sensor=8192, max_batch_points=8192) as cm:
+        buf = cm.upload(cloud)
+        cm.dev_plane_ransac(buf.ptr, len(cloud), THR)
+        xyzi, _, begin = cm.zone_out_raw()
+        for call in (lambda: cm.dev_plane_ransac(xyzi, begin[1], THR),
+                     lambda: cm.dev_radius_outlier(xyzi + begin[1] * 16, begin[2] - begin[1], 0.15, 1),
+                     lambda: (cm.set_zones([[(2, -1.0, 1.0, 0)]]), cm.dev_zone_split(xyzi, begin[1]))):
+            with pytest.raises(CloudMergerError):
+                call()
+        # the same cloud through a second handle is fine
+        with CloudMerger(max_sensors=1, max_points_per_sensor=8192, max_batch_points=8192) as other:
+            r = other.dev_plane_ransac(xyzi, begin[1], THR)
+            assert r["found"]
