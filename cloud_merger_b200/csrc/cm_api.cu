@@ -51,6 +51,7 @@ enum StageEv { EV_START = 0, EV_K1, EV_GRID, EV_KEY, EV_SORT, EV_CENT, EV_COUNT 
 struct Workspace {
   bool ready = false;
   uint32_t cap_points = 0, cap_frames = 0, cap_segs = 0;
+  uint32_t plan_idx_bits = 0, plan_total_bits = 0;  // key plan of the last unbounded run (fetched from the device)
   int out_step = 16;
   MetaLayout ml{};
   uint8_t* meta = nullptr;
@@ -164,6 +165,9 @@ struct cm_handle_s {
     ZoneParams last{};           // the last split, so that its scatter can be repeated after the outputs grew
     int n_zones_run = 0;         // zones of the last split (1 for a radius outlier removal)
   } zw;
+  // radius outlier removal: first sorted position of every cell key (allocated on first use, grows)
+  uint32_t* ror_table = nullptr;
+  size_t ror_table_cap = 0;
   // RANSAC ground plane (allocated on first use): one batch of draws and its scores, device + pinned mirrors
   struct PlaneWs {
     size_t cap_draws = 0;
@@ -377,6 +381,7 @@ int run_voxel(cm_handle_t h, Workspace& w, VoxelParams& vp, cudaStream_t st, boo
     memcpy(&si, w.report + w.ml.off_info, sizeof(si));
     vp.key_bytes = si.total_bits <= 32 ? 4 : 8;
     vp.max_passes = si.num_passes;
+    w.plan_idx_bits = si.idx_bits; w.plan_total_bits = si.total_bits;
   }
   w.key_bytes = vp.key_bytes;
   w.max_passes = vp.max_passes;
@@ -923,6 +928,7 @@ int cm_destroy(cm_handle_t h) {
     cudaFree(z.zone_total);
     cudaFree(z.out_xyzi); cudaFree(z.out_src); cudaFree(z.in_stage);
     if (z.report) cudaFreeHost(z.report);
+    cudaFree(h->ror_table);
     auto& q = h->pw;
     cudaFree(q.samples_dev); cudaFree(q.counts_dev); cudaFree(q.models_dev); cudaFree(q.acc_dev);
     if (q.samples_pin) cudaFreeHost(q.samples_pin);
@@ -1498,6 +1504,23 @@ int radius_outlier_run(cm_handle_t h, const float4* pts, const int64_t* begin, i
   rp.min_pts = (uint32_t)min_neighbors;
   rp.negative = negative ? 1u : 0u;
   rp.mask = h->zw.mask;
+  rp.cell_start = nullptr; rp.table_keys = 0;
+  // a small key space (the usual case: a cropped cloud) gets a direct-address table of the cells' first sorted positions
+  // instead of nine binary searches per point
+  // (CM_ROR_NO_TABLE=1 forces the binary searches: test hook for the large-key-space path)
+  if (n_points > 0 && w.plan_idx_bits <= 25 && ((uint64_t)n_clouds << w.plan_idx_bits) <= (1ull << 25) &&
+      !getenv("CM_ROR_NO_TABLE")) {
+    const size_t keys = (size_t)n_clouds << w.plan_idx_bits;
+    if (h->ror_table_cap < keys + 1) {
+      cudaFree(h->ror_table);
+      h->ror_table = nullptr; h->ror_table_cap = 0;
+      CM_CUDA(h, dev_alloc(&h->ror_table, keys + 1));
+      h->ror_table_cap = keys + 1;
+    }
+    rp.cell_start = h->ror_table; rp.table_keys = (uint32_t)keys;
+    CM_CUDA(h, launch_radius_table(vp, rp, st));
+    ++w.launches;
+  }
   if (n_points) CM_CUDA(h, cudaMemsetAsync(h->zw.mask, 0, (size_t)n_points * sizeof(unsigned short), st));
   CM_CUDA(h, launch_radius_count(vp, rp, st));
   ++w.launches;

@@ -12,6 +12,11 @@
 // the count decides the outcome. The keep flags go to the zone-slicing mask array, whose scan + scatter kernels then
 // compact the survivors in input order (cm_zones.cu).
 //
+// When the key space is small enough (frames << idx_bits <= 2^25, the usual case for a cropped cloud) a direct-address
+// table replaces the binary searches: k_ror_table writes, for every key k, the first sorted position whose key is >= k
+// (the heads of the key runs fill the gap up to their key, a warp per gap), and a row segment [k_lo, k_hi] is then just
+// [cell_start[k_lo], cell_start[k_hi + 1]) -- two loads instead of ~22 dependent ones per row.
+//
 // Roofline: HBM/L2 for the gathers; algorithmic bytes ~ n * (8 record + 16 point) * (neighbours visited).
 #include "cm_kernels.h"
 
@@ -21,7 +26,66 @@ namespace {
 
 constexpr int ROR_THREADS = 256;
 
+// cell_start[k] = first sorted position with key >= k, for k in [0, table_keys]. Thread i looks at sorted element i: where
+// a new key run starts, the gap (previous key, this key] is filled with i by the whole warp.
 template <typename KeyT>
+__global__ void __launch_bounds__(ROR_THREADS) k_ror_table(const VoxelParams p, const RorParams r) {
+  constexpr bool REC = sizeof(KeyT) == 4;
+  const uint32_t M = p.frame_surv_start[p.n_frames];
+  const uint32_t i = blockIdx.x * ROR_THREADS + threadIdx.x;
+  const SortInfo si = *p.info;
+  const bool odd = (si.num_passes & 1u) != 0u;
+  const void* __restrict__ sorted = odd ? p.keys_b : p.keys_a;
+  auto key_at = [&](uint32_t j) -> unsigned long long {
+    if constexpr (REC) return reinterpret_cast<const uint2*>(sorted)[j].x;
+    else return reinterpret_cast<const unsigned long long*>(sorted)[j];
+  };
+  const unsigned long long K = r.table_keys;
+  // gap of this thread: table entries (from, to] get the value i
+  unsigned long long from = 1, to = 0;  // empty
+  if (i < M) {
+    const unsigned long long k = min(key_at(i), K);
+    if (i == 0) { from = 0; to = k; r.cell_start[0] = 0; }
+    else {
+      const unsigned long long kp = min(key_at(i - 1), K);
+      if (k != kp) { from = kp + 1; to = k; }
+    }
+  } else if (i == M) {  // behind the last element: everything above the largest key
+    from = M ? min(key_at(M - 1), K) + 1 : 0;
+    to = K;
+  }
+  // short gaps: the warp of the head fills them; long ones (empty regions of the key space, the space between two
+  // clouds' cell ranges) go to a list in shared memory and are filled by the whole CTA
+  constexpr unsigned long long LONG_GAP = 2048;
+  constexpr int LIST = 32;
+  __shared__ unsigned long long s_from[LIST], s_to[LIST];
+  __shared__ uint32_t s_val[LIST];
+  __shared__ int s_n;
+  if (threadIdx.x == 0) s_n = 0;
+  __syncthreads();
+  const uint32_t lane = threadIdx.x & 31u;
+  if (from <= to && to - from >= LONG_GAP) {
+    const int slot = atomicAdd(&s_n, 1);
+    if (slot < LIST) { s_from[slot] = from; s_to[slot] = to; s_val[slot] = i; from = 1; to = 0; }
+  }
+  uint32_t todo = __ballot_sync(0xffffffffu, from <= to);
+  while (todo) {
+    const int src = __ffs(todo) - 1;
+    todo &= todo - 1;
+    const unsigned long long a = __shfl_sync(0xffffffffu, from, src), b = __shfl_sync(0xffffffffu, to, src);
+    const uint32_t val = __shfl_sync(0xffffffffu, i, src);
+    for (unsigned long long k = a + lane; k <= b; k += 32) r.cell_start[k] = val;
+  }
+  __syncthreads();
+  const int n_long = min(s_n, LIST);
+  for (int g = 0; g < n_long; ++g) {
+    const unsigned long long a = s_from[g], b = s_to[g];
+    const uint32_t val = s_val[g];
+    for (unsigned long long k = a + threadIdx.x; k <= b; k += ROR_THREADS) r.cell_start[k] = val;
+  }
+}
+
+template <typename KeyT, bool TABLE>
 __global__ void __launch_bounds__(ROR_THREADS) k_ror_count(const VoxelParams p, const RorParams r) {
   constexpr bool REC = sizeof(KeyT) == 4;
   const uint32_t M = p.frame_surv_start[p.n_frames];
@@ -66,20 +130,29 @@ __global__ void __launch_bounds__(ROR_THREADS) k_ror_count(const VoxelParams p, 
   const unsigned long long x_lo = c0 > 0 ? c0 - 1 : 0, x_hi = c0 + 1 < d0 ? c0 + 1 : d0 - 1;
   uint32_t cnt = 0;
   const uint32_t need = r.min_pts + 1u;  // the outcome is decided once this many neighbours were seen
-  for (int dz = -1; dz <= 1 && cnt < need; ++dz) {
-    if ((dz < 0 && c2 == 0) || (dz > 0 && c2 + 1 >= d2)) continue;
-    for (int dy = -1; dy <= 1 && cnt < need; ++dy) {
+  // the nine rows of cells, nearest first (own row, the four rows sharing a face, the four diagonal ones): the outcome
+  // only depends on the total count, and the close rows usually decide it before the far ones are read
+  for (int rr = 0; rr < 9 && cnt < need; ++rr) {
+    // (dz + 1, dy + 1) of row rr, two bits each: (0,0) (0,-1) (0,1) (-1,0) (1,0) (-1,-1) (-1,1) (1,-1) (1,1)
+    const int dz = (int)((0x28215u >> (2 * rr)) & 3u) - 1, dy = (int)((0x22161u >> (2 * rr)) & 3u) - 1;
+    {
+      if ((dz < 0 && c2 == 0) || (dz > 0 && c2 + 1 >= d2)) continue;
       if ((dy < 0 && c1 == 0) || (dy > 0 && c1 + 1 >= d1)) continue;
       const unsigned long long row = ((c2 + dz) * d1 + (c1 + dy)) * d0;
       const unsigned long long k_lo = fbits + row + x_lo, k_hi = fbits + row + x_hi;
-      // lower bound of k_lo in the sorted keys
       uint32_t lo = 0, hi = M;
-      while (lo < hi) {
-        const uint32_t mid = (lo + hi) >> 1;
-        if (key_at(mid) < k_lo) lo = mid + 1; else hi = mid;
+      if constexpr (TABLE) {  // the row segment straight from the table
+        lo = __ldg(r.cell_start + k_lo);
+        hi = __ldg(r.cell_start + k_hi + 1);
+      } else {                // lower bound of k_lo in the sorted keys
+        while (lo < hi) {
+          const uint32_t mid = (lo + hi) >> 1;
+          if (key_at(mid) < k_lo) lo = mid + 1; else hi = mid;
+        }
+        hi = M;
       }
-      for (uint32_t j = lo; j < M && cnt < need; ++j) {
-        if (key_at(j) > k_hi) break;
+      for (uint32_t j = lo; j < hi && cnt < need; ++j) {
+        if (!TABLE && key_at(j) > k_hi) break;
         const float4 d = __ldg(p.pts + val_at(j));
         const float ex = __fsub_rn(q.x, d.x), ey = __fsub_rn(q.y, d.y), ez = __fsub_rn(q.z, d.z);
         const float acc = __fadd_rn(__fadd_rn(__fmul_rn(ex, ex), __fmul_rn(ey, ey)), __fmul_rn(ez, ez));
@@ -93,11 +166,23 @@ __global__ void __launch_bounds__(ROR_THREADS) k_ror_count(const VoxelParams p, 
 
 }  // namespace
 
+cudaError_t launch_radius_table(const VoxelParams& p, const RorParams& r, cudaStream_t stream) {
+  const uint32_t blocks = (p.max_points + 1 + ROR_THREADS - 1) / ROR_THREADS;  // one thread behind the last element
+  if (p.key_bytes == 4) k_ror_table<uint32_t><<<blocks, ROR_THREADS, 0, stream>>>(p, r);
+  else k_ror_table<unsigned long long><<<blocks, ROR_THREADS, 0, stream>>>(p, r);
+  return cudaGetLastError();
+}
+
 cudaError_t launch_radius_count(const VoxelParams& p, const RorParams& r, cudaStream_t stream) {
   if (p.max_points == 0) return cudaSuccess;
   const uint32_t blocks = (p.max_points + ROR_THREADS - 1) / ROR_THREADS;
-  if (p.key_bytes == 4) k_ror_count<uint32_t><<<blocks, ROR_THREADS, 0, stream>>>(p, r);
-  else k_ror_count<unsigned long long><<<blocks, ROR_THREADS, 0, stream>>>(p, r);
+  if (r.cell_start) {
+    if (p.key_bytes == 4) k_ror_count<uint32_t, true><<<blocks, ROR_THREADS, 0, stream>>>(p, r);
+    else k_ror_count<unsigned long long, true><<<blocks, ROR_THREADS, 0, stream>>>(p, r);
+  } else {
+    if (p.key_bytes == 4) k_ror_count<uint32_t, false><<<blocks, ROR_THREADS, 0, stream>>>(p, r);
+    else k_ror_count<unsigned long long, false><<<blocks, ROR_THREADS, 0, stream>>>(p, r);
+  }
   return cudaGetLastError();
 }
 

@@ -122,3 +122,34 @@ def test_radius_outlier_multi_equals_separate_runs(gpu_ok, oracle):
     with CloudMerger(max_sensors=1, max_points_per_sensor=total, max_batch_points=total) as cm1:   # one frame only
         with pytest.raises(CloudMergerError):
             cm1.radius_outlier_multi(clouds[:2], RADIUS, 1)
+
+
+def test_radius_outlier_table_and_search_paths_agree(gpu_ok, oracle, monkeypatch):
+    """The direct-address cell table (small key spaces) and the binary searches (large ones, forced here through the
+    CM_ROR_NO_TABLE test hook) must give the same survivors -- on one cloud and on several clouds per call."""
+    a = _roi_cloud(oracle, 4500, 64, 1024)
+    b = _roi_cloud(oracle, 4501, 32, 512, sensor=1)
+    want_a = oracle.radius_outlier(a, RADIUS, 1, False)
+    want_b = oracle.radius_outlier(b, RADIUS, 2, False)
+    cap = len(a) + 2 * len(b)
+    with CloudMerger(max_sensors=1, max_points_per_sensor=cap, max_batch_points=cap, max_batch_frames=4) as cm:
+        for no_table in (False, True):
+            if no_table:
+                monkeypatch.setenv("CM_ROR_NO_TABLE", "1")
+            else:
+                monkeypatch.delenv("CM_ROR_NO_TABLE", raising=False)
+            gx, gi = cm.radius_outlier(a, RADIUS, 1)
+            assert (gi == want_a).all()
+            got = cm.radius_outlier_multi([b, a, b], RADIUS, 2)
+            assert (got[0][1] == want_b).all() and (got[2][1] == want_b).all()
+            assert (got[1][1] == oracle.radius_outlier(a, RADIUS, 2, False)).all()
+    # a cloud spread over kilometres: the key space is far too large for the table, the searches run by themselves
+    rng = np.random.default_rng(3)
+    wide = np.column_stack([rng.uniform(-2000, 2000, 20000), rng.uniform(-2000, 2000, 20000), rng.uniform(-5, 5, 20000),
+                            np.zeros(20000)]).astype(np.float32)
+    wide[:5000, :3] = (wide[5000:10000, :3] + rng.normal(0, 0.05, (5000, 3))).astype(np.float32)   # some close pairs
+    monkeypatch.delenv("CM_ROR_NO_TABLE", raising=False)
+    with CloudMerger(max_sensors=1, max_points_per_sensor=len(wide), max_batch_points=len(wide)) as cm:
+        gx, gi = cm.radius_outlier(wide, RADIUS, 1)
+        want = oracle.radius_outlier(wide, RADIUS, 1, False)
+        assert 0 < len(want) < len(wide) and (gi == want).all()
