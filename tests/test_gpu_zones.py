@@ -131,3 +131,21 @@ def test_zone_partition_properties_full_size(gpu_ok):
         assert ((cloud[gs, 0] >= edges[z]) & (cloud[gs, 0] < edges[z + 1])).all()
         seen[gs] += 1
     assert (seen == 1).all(), "not a partition"
+
+
+def test_zones_and_outlier_golden_fixture(gpu_ok):
+    """The committed fixture tests/golden/zones_outlier.json (plain numpy windows / O(n^2) count) through the C ABI."""
+    import json
+    import os
+    doc = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "zones_outlier.json")))
+    x = np.array([[np.nan if v == "nan" else v for v in row] for row in doc["xyzi"]], np.float32)
+    with CloudMerger(max_sensors=1, max_points_per_sensor=4096, max_batch_points=4096) as cm:
+        cm.set_zones([[tuple(p) for p in z] for z in doc["zones"]])
+        got = cm.zone_split(x, capacity=len(doc["zones"]) * len(x))
+        for (gx, gi), want in zip(got, doc["zone_indices"]):
+            assert gi.tolist() == want
+            assert gx.tobytes() == x[want].tobytes()
+        for m, want in doc["outlier_kept_by_min_pts"].items():
+            kx, ki = cm.radius_outlier(x, doc["radius"], int(m))
+            assert ki.tolist() == want
+            assert kx.tobytes() == x[want].tobytes()

@@ -401,3 +401,21 @@ def test_plane_ransac_golden_fixture(oracle):
         if e["found"]:
             assert r["coeff_ransac"].view(np.uint32).tolist() == e["coeff_ransac_bits"]
         assert r["inliers"].tolist() == e["inliers"]
+
+
+def _aux_fixture():
+    import json
+    import os
+    doc = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "zones_outlier.json")))
+    x = np.array([[np.nan if v == "nan" else v for v in row] for row in doc["xyzi"]], np.float32)
+    return doc, x
+
+
+def test_zones_and_outlier_golden_fixture(oracle):
+    """tests/golden/zones_outlier.json (plain numpy, tests/golden/make_aux_fixtures.py) against the C++ oracle."""
+    doc, x = _aux_fixture()
+    got = oracle.zone_split(x, [[tuple(p) for p in z] for z in doc["zones"]])
+    for (gx, gi), want in zip(got, doc["zone_indices"]):
+        assert gi.tolist() == want
+    for m, want in doc["outlier_kept_by_min_pts"].items():
+        assert oracle.radius_outlier(x, doc["radius"], int(m), False).tolist() == want
