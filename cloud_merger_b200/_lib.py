@@ -151,6 +151,9 @@ SYMBOLS = {
     "cm_set_profiling": (C.c_int, [_H, C.c_int]),
     "cm_stage_ms": (C.c_int, [_H, C.c_char_p, C.POINTER(C.c_float)]),
     "cm_debug_trace": (C.c_int, [_H, C.c_int, C.c_void_p, C.c_int64, C.POINTER(C.c_int64)]),
+    "cm_stream_create": (C.c_int, [_H, C.POINTER(C.c_void_p)]),
+    "cm_stream_destroy": (C.c_int, [_H, C.c_void_p]),
+    "cm_stream_sync": (C.c_int, [_H, C.c_void_p]),
     "cm_dev_alloc": (C.c_int, [_H, C.POINTER(C.c_void_p), C.c_size_t]),
     "cm_dev_free": (C.c_int, [_H, C.c_void_p]),
     "cm_memcpy_h2d": (C.c_int, [_H, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),

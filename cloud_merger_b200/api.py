@@ -363,6 +363,17 @@ class CloudMerger:
         self._check(self._lib.cm_get_zone_out(self._h, C.byref(zo)))
         return zo.xyzi, zo.src, [int(zo.begin[k]) for k in range(zo.n_zones + 1)]
 
+    def stream_create(self) -> int:
+        p = C.c_void_p()
+        self._check(self._lib.cm_stream_create(self._h, C.byref(p)))
+        return int(p.value)
+
+    def stream_destroy(self, stream: int):
+        self._check(self._lib.cm_stream_destroy(self._h, C.c_void_p(stream or None)))
+
+    def stream_sync(self, stream: int):
+        self._check(self._lib.cm_stream_sync(self._h, C.c_void_p(stream or None)))
+
     def memcpy_d2d(self, dst_ptr: int, src_ptr: int, nbytes: int, stream: int = 0):
         self._check(self._lib.cm_memcpy_d2d(self._h, C.c_void_p(dst_ptr), C.c_void_p(src_ptr), C.c_size_t(nbytes),
                                             C.c_void_p(stream or None)))

@@ -268,6 +268,8 @@ int ws_alloc(cm_handle_t h, Workspace& w, uint32_t points, uint32_t frames, uint
     CM_CUDA(h, cudaMemset(w.trace_k1, 0, w.trace_k1_n * 8));
     CM_CUDA(h, cudaMemset(w.trace_sort, 0, w.trace_sort_n * 8));
   }
+  // the clears above ran on the default stream: callers may go on with a non-blocking stream of their own
+  CM_CUDA(h, cudaDeviceSynchronize());
   w.ready = true;
   return CM_OK;
 }
@@ -1220,6 +1222,7 @@ int zone_ws_ensure(cm_handle_t h, size_t points) {
   CM_CUDA(h, dev_alloc(&z.out_xyzi, z.cap_out));
   CM_CUDA(h, dev_alloc(&z.out_src, z.cap_out));
   CM_CUDA(h, cudaMallocHost(reinterpret_cast<void**>(&z.report), sizeof(uint32_t) * (CM_MAX_ZONES + 2)));
+  CM_CUDA(h, cudaDeviceSynchronize());  // the clear above ran on the default stream (see ws_alloc)
   z.cap_points = want;
   return CM_OK;
 }
@@ -2089,6 +2092,26 @@ int cm_dev_free(cm_handle_t h, void* p) {
   if (!h) return CM_E_INVALID;
   CM_CUDA(h, cudaSetDevice(h->device));
   CM_CUDA(h, cudaFree(p));
+  return CM_OK;
+}
+int cm_stream_create(cm_handle_t h, void** stream) {
+  if (!h || !stream) return CM_E_INVALID;
+  CM_CUDA(h, cudaSetDevice(h->device));
+  cudaStream_t st = nullptr;
+  CM_CUDA(h, cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+  *stream = st;
+  return CM_OK;
+}
+int cm_stream_destroy(cm_handle_t h, void* stream) {
+  if (!h) return CM_E_INVALID;
+  CM_CUDA(h, cudaSetDevice(h->device));
+  if (stream) CM_CUDA(h, cudaStreamDestroy(static_cast<cudaStream_t>(stream)));
+  return CM_OK;
+}
+int cm_stream_sync(cm_handle_t h, void* stream) {
+  if (!h) return CM_E_INVALID;
+  CM_CUDA(h, cudaSetDevice(h->device));
+  CM_CUDA(h, cudaStreamSynchronize(static_cast<cudaStream_t>(stream)));
   return CM_OK;
 }
 int cm_memcpy_h2d(cm_handle_t h, void* dst, const void* src, size_t bytes, void* stream) {

@@ -12,7 +12,8 @@ Everything between the upload of the raw sensor clouds and the download of the t
 memory. The stages are the C-ABI calls of include/cloud_merger_gpu.h, each on its own handle because a stage's results
 live in its handle's workspace until that handle runs again: transform + ROI crop of all sensors in one launch (frame =
 sensor), per sensor one zone-slicing pass, one multi-cloud plane search and one multi-cloud radius outlier removal,
-device-to-device appends, one VoxelGrid.
+device-to-device appends, one VoxelGrid. The per-sensor stages run concurrently -- one host thread and one CUDA stream per
+sensor, as the reference's callbacks do on ros::AsyncSpinner(6) (pc_preprocessing_main.cpp:513).
 
 Host glue, not a kernel: there is no CPU fallback and no arithmetic on points here.
 """
@@ -58,44 +59,96 @@ class NodeParams:
     parts: Sequence[Sequence[Tuple[float, float, float]]] = field(default_factory=lambda: [FRONT_PARTS])  # per sensor (cycled)
 
 
+class _SensorLane:
+    """The proceedX stages of one sensor on their own handles and CUDA stream: one callback thread of the reference
+    (ros::AsyncSpinner(6), pc_preprocessing_main.cpp:513)."""
+
+    def __init__(self, device: int, max_points: int, p: NodeParams, parts):
+        mk = lambda frames: CloudMerger(device=device, max_sensors=1, max_points_per_sensor=max_points,
+                                        max_batch_points=max_points, max_batch_frames=frames)
+        self.p = p
+        self.k = len(parts)
+        self.zones, self.plane, self.ror = mk(1), mk(1), mk(8)
+        self.zones.set_zones(zones_of_parts(parts, p.roi_z_max))
+        self.rest = self.ror.device_buffer(max_points * 16)            # what is not ground, window after window
+        self.no_ground = self.zones.device_buffer(2 * max_points * 16)  # windows share their end points
+        self.ground = self.zones.device_buffer(2 * max_points * 16)
+        self.stream = self.zones.stream_create()
+        self.n_ng = self.n_g = 0
+        self.planes: List[dict] = []
+
+    def close(self):
+        self.zones.stream_destroy(self.stream)
+        for h in (self.zones, self.plane, self.ror):
+            h.close()
+
+    def run(self, roi_ptr: int, n: int):
+        p, k, st = self.p, self.k, self.stream
+        d2d = self.zones.memcpy_d2d
+        self.zones.dev_zone_split(roi_ptr, n, stream=st)
+        z_xyzi, _, zb = self.zones.zone_out_raw()
+        self.planes = self.plane.dev_plane_ransac_multi(z_xyzi, zb[:k + 1], p.distance_threshold, p.prob, p.max_iterations,
+                                                        True, 12345, p.sum_order, stream=st)
+        p_xyzi, _, pb = self.plane.zone_out_raw()
+        rb = [0]
+        for i in range(k):  # the rest clouds (odd zones) side by side
+            cnt = pb[2 * i + 2] - pb[2 * i + 1]
+            d2d(self.rest.ptr + rb[-1] * 16, p_xyzi + pb[2 * i + 1] * 16, cnt * 16, stream=st)
+            rb.append(rb[-1] + cnt)
+        self.ror.dev_radius_outlier_multi(self.rest.ptr, rb, p.radius, p.min_neighbor, stream=st)
+        r_xyzi, _, kb = self.ror.zone_out_raw()
+        n_ng = n_g = 0
+        for i in range(k):
+            cnt = kb[i + 1] - kb[i]                     # outlierRemoval(no_ground) ...
+            d2d(self.no_ground.ptr + n_ng * 16, r_xyzi + kb[i] * 16, cnt * 16, stream=st)
+            n_ng += cnt
+            cnt = zb[k + i + 1] - zb[k + i]             # ... += the points above the window
+            d2d(self.no_ground.ptr + n_ng * 16, z_xyzi + zb[k + i] * 16, cnt * 16, stream=st)
+            n_ng += cnt
+            cnt = pb[2 * i + 1] - pb[2 * i]             # ground += the inliers
+            d2d(self.ground.ptr + n_g * 16, p_xyzi + pb[2 * i] * 16, cnt * 16, stream=st)
+            n_g += cnt
+        self.zones.stream_sync(st)
+        self.n_ng, self.n_g = n_ng, n_g
+
+
 class PreprocessingNode:
-    def __init__(self, n_sensors: int, max_points_per_sensor: int, params: Optional[NodeParams] = None, device: int = 0):
+    def __init__(self, n_sensors: int, max_points_per_sensor: int, params: Optional[NodeParams] = None, device: int = 0,
+                 concurrent: bool = True):
         self.S = n_sensors
         self.p = params or NodeParams()
+        self.concurrent = concurrent
         n = n_sensors * max_points_per_sensor
         mk = lambda frames: CloudMerger(device=device, max_sensors=n_sensors, max_points_per_sensor=max_points_per_sensor,
                                         max_batch_points=n, max_batch_frames=frames)
         self.crop = mk(n_sensors)   # transform + getROI of every sensor, one frame per sensor
-        self.zones = mk(1)
-        self.plane = mk(1)
-        self.ror = mk(8)
         self.voxel = mk(1)
         self.crop.set_crop(self.p.roi_passes)
         self.voxel.set_voxel(self.p.voxel_size, self.p.points_per_voxel, True)
         self.raw = [self.crop.device_buffer(max_points_per_sensor * 16) for _ in range(n_sensors)]
-        self.rest = self.ror.device_buffer(max_points_per_sensor * 16)       # what is not ground, window after window
-        self.no_ground = self.voxel.device_buffer(2 * n * 16)                # fused clouds (windows share their end points)
+        self.lanes = [_SensorLane(device, max_points_per_sensor, self.p, tuple(map(tuple, self.p.parts[s % len(self.p.parts)])))
+                      for s in range(n_sensors)]
+        self.no_ground = self.voxel.device_buffer(2 * n * 16)   # the fused clouds
         self.ground = self.voxel.device_buffer(2 * n * 16)
-        self._zones_set = None
+        self._pool = None
+        if concurrent and n_sensors > 1:
+            from concurrent.futures import ThreadPoolExecutor
+            self._pool = ThreadPoolExecutor(max_workers=n_sensors)
 
     def close(self):
-        for h in (self.crop, self.zones, self.plane, self.ror, self.voxel):
+        if self._pool:
+            self._pool.shutdown()
+        for lane in self.lanes:
+            lane.close()
+        for h in (self.crop, self.voxel):
             h.close()
 
     def set_extrinsic(self, sensor: int, m: np.ndarray):
         self.crop.set_extrinsic(sensor, m)
 
-    def _set_zones(self, sensor: int):
-        parts = tuple(map(tuple, self.p.parts[sensor % len(self.p.parts)]))
-        if parts != self._zones_set:
-            self.zones.set_zones(zones_of_parts(parts, self.p.roi_z_max))
-            self._zones_set = parts
-        return len(parts)
-
     def frame(self, clouds: Sequence[np.ndarray], download: bool = True) -> dict:
         """clouds: one packed xyzi float32 array per sensor (sensor frame). Returns the three clouds the node publishes
         (/points_no_ground, /points_ground, /points_voxel) -- device pointers + sizes, and host copies when `download`."""
-        p = self.p
         items = []
         for s, c in enumerate(clouds):
             a = np.ascontiguousarray(c, np.float32).reshape(-1, 4)
@@ -105,35 +158,26 @@ class PreprocessingNode:
         self.crop.sync()
         info = self.crop.frame_info()
         roi = self.crop.device_out().survivor_xyzi
+        # proceedX of every sensor: concurrently, one host thread + CUDA stream per sensor (the ctypes calls release the
+        # GIL), or one after the other
+        jobs = [(self.lanes[s], roi + info[s].survivor_begin * 16, info[s].survivor_end - info[s].survivor_begin)
+                for s in range(len(clouds))]
+        if self._pool:
+            for f in [self._pool.submit(lane.run, ptr, n) for lane, ptr, n in jobs]:
+                f.result()
+        else:
+            for lane, ptr, n in jobs:
+                lane.run(ptr, n)
+        # fusePointclouds: sensor after sensor
         n_ng = n_g = 0
         planes: List[dict] = []
         d2d = self.voxel.memcpy_d2d
-        for s in range(len(clouds)):
-            b, e = info[s].survivor_begin, info[s].survivor_end
-            k = self._set_zones(s)
-            self.zones.dev_zone_split(roi + b * 16, e - b)
-            z_xyzi, _, zb = self.zones.zone_out_raw()
-            res = self.plane.dev_plane_ransac_multi(z_xyzi, zb[:k + 1], p.distance_threshold, p.prob, p.max_iterations, True,
-                                                    12345, p.sum_order)
-            planes += res
-            p_xyzi, _, pb = self.plane.zone_out_raw()
-            rb = [0]
-            for i in range(k):  # the rest clouds (odd zones) side by side
-                cnt = pb[2 * i + 2] - pb[2 * i + 1]
-                d2d(self.rest.ptr + rb[-1] * 16, p_xyzi + pb[2 * i + 1] * 16, cnt * 16)
-                rb.append(rb[-1] + cnt)
-            self.ror.dev_radius_outlier_multi(self.rest.ptr, rb, p.radius, p.min_neighbor)
-            r_xyzi, _, kb = self.ror.zone_out_raw()
-            for i in range(k):
-                cnt = kb[i + 1] - kb[i]                     # outlierRemoval(no_ground) ...
-                d2d(self.no_ground.ptr + n_ng * 16, r_xyzi + kb[i] * 16, cnt * 16)
-                n_ng += cnt
-                cnt = zb[k + i + 1] - zb[k + i]             # ... += the points above the window
-                d2d(self.no_ground.ptr + n_ng * 16, z_xyzi + zb[k + i] * 16, cnt * 16)
-                n_ng += cnt
-                cnt = pb[2 * i + 1] - pb[2 * i]             # ground += the inliers
-                d2d(self.ground.ptr + n_g * 16, p_xyzi + pb[2 * i] * 16, cnt * 16)
-                n_g += cnt
+        for lane, _, _ in jobs:
+            d2d(self.no_ground.ptr + n_ng * 16, lane.no_ground.ptr, lane.n_ng * 16)
+            d2d(self.ground.ptr + n_g * 16, lane.ground.ptr, lane.n_g * 16)
+            n_ng += lane.n_ng
+            n_g += lane.n_g
+            planes += lane.planes
         self.voxel.dev_voxelgrid(self.no_ground.ptr, n_ng)
         self.voxel.sync()
         st = self.voxel.stats()

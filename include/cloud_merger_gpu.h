@@ -369,6 +369,12 @@ CM_API int cm_dev_free(cm_handle_t h, void* p);
 CM_API int cm_memcpy_h2d(cm_handle_t h, void* dst_dev, const void* src_host, size_t bytes, void* stream);
 CM_API int cm_memcpy_d2h(cm_handle_t h, void* dst_host, const void* src_dev, size_t bytes, void* stream);
 CM_API int cm_memcpy_d2d(cm_handle_t h, void* dst_dev, const void* src_dev, size_t bytes, void* stream);
+/* a CUDA stream (non-blocking) for the `stream` argument of the device-resident calls: lets the per-sensor stages of
+ * several sensors run concurrently from their own host threads, as the reference's callbacks do on ros::AsyncSpinner(6)
+ * (pc_preprocessing_main.cpp:513). One handle must still only be used by one thread at a time. */
+CM_API int cm_stream_create(cm_handle_t h, void** stream);
+CM_API int cm_stream_destroy(cm_handle_t h, void* stream);
+CM_API int cm_stream_sync(cm_handle_t h, void* stream);
 
 #ifdef __cplusplus
 }

@@ -35,16 +35,19 @@ def oracle_frame(oracle, clouds, mats, p: NodeParams):
     return ng, np.concatenate(ground), vg
 
 
-def test_node_frame_matches_oracle_composition(gpu_ok, oracle):
+@pytest.mark.parametrize("concurrent", [True, False])
+def test_node_frame_matches_oracle_composition(gpu_ok, oracle, concurrent):
+    """concurrent: the per-sensor stages on one host thread + CUDA stream per sensor (the reference's AsyncSpinner
+    callbacks); otherwise one sensor after the other on the default stream."""
     S, rings, az = 3, 32, 512
     rear = tuple((length, -dev - length, zg) for (length, dev, zg) in FRONT_PARTS)   # a second window set (mirrored in x)
     p = NodeParams(parts=[FRONT_PARTS, rear])
-    node = PreprocessingNode(S, rings * az, p)
+    node = PreprocessingNode(S, rings * az, p, concurrent=concurrent)
     try:
         mats = [synth.extrinsic(s, S) for s in range(S)]
         for s in range(S):
             node.set_extrinsic(s, mats[s])
-        for frame in range(2):   # twice: the handles are reused from frame to frame
+        for frame in range(3):   # several frames: the handles are reused from frame to frame
             clouds = [synth.lidar_cloud(5100 + frame, s, frame, rings, az) for s in range(S)]
             got = node.frame(clouds)
             ng, g, vg = oracle_frame(oracle, clouds, mats, p)
