@@ -2,7 +2,8 @@
 """bench.py -- merged + voxel-filtered Mpoints/s of the merge hot path (BASELINE.json metric) on N B200s.
 
 A step = one pass of the whole hot path (transform -> concat -> crop -> VoxelGrid) over one batch of F frames of the
-named workload (default: BASELINE config 2, 4 sensors x 128k points, box crop, VoxelGrid 0.05 m).
+named workload (default: BASELINE config 3, 8 sensors x 256k points per frame, box crop, VoxelGrid 0.05 m -- the config
+BASELINE.json names for 1/2/4/8 GPUs; frames are sharded over the ranks with no collective).
   value    device-resident throughput: inputs already in HBM, CUDA-event timed, max over ranks
   e2e      the same metric through the host C-ABI path (cm_submit_cloud_pinned / cm_merge_frame_async / cm_wait_frame)
            from pinned HOST buffers, H2D and D2H inside the timed region
@@ -37,13 +38,16 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="cfg2", choices=["cfg1", "cfg2", "cfg3"])
+    ap.add_argument("--workload", default="cfg3", choices=["cfg1", "cfg2", "cfg3", "cfg4", "cfg5"],
+                    help="BASELINE.json config; cfg3 (8 x 256k points per frame, frame-sharded) is the 1/2/4/8-GPU config")
     ap.add_argument("--frames", type=int, default=0, help="frames per step (0 = enough to exceed L2 several times)")
     ap.add_argument("--e2e-steps", type=int, default=0, help="steps of the host-path measurement (0 = min(steps, 3))")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--no-latency", action="store_true", help="skip the single-frame p50/p99 latency measurement")
+    ap.add_argument("--sustained-seconds", type=float, default=2.0,
+                    help="length of the extra back-to-back leg that shows the number holds at steady-state clocks (0 = skip)")
     return ap.parse_args()
 
 
@@ -405,6 +409,31 @@ def main():
     st = cm.stats()
     M, V, P, kb = int(st.survivors), int(st.voxels_out), int(st.sort_passes), int(st.key_bytes)
 
+    # ---- sustained leg: the same step back to back for >= --sustained-seconds (the K-step region above lasts milliseconds,
+    # too short for the GPU to reach its steady-state power / clocks) ---------------------------------------------------------
+    sustained = None
+    if args.sustained_seconds > 0:
+        cm.set_profiling(False)
+        n_sus = max(args.steps, int(np.ceil(args.sustained_seconds * 1e3 / ms_step)))
+        sampler2 = ClockSampler(local_rank, gpu_uuid)
+        barrier()
+        sampler2.start()
+        s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s0.record()
+        for i in range(n_sus):
+            cm.run_batch(segs, stream=stream)
+        s1.record()
+        cm.sync()
+        barrier()
+        clocks2 = sampler2.stop()
+        ts = torch.tensor([s0.elapsed_time(s1)], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(ts, op=dist.ReduceOp.MAX)
+        sus_ms = float(ts.item())
+        sustained = {"steps": n_sus, "gpu_launches": int(cm.launch_count() * n_sus), "seconds": sus_ms / 1e3, "ms_per_step": sus_ms / n_sus,
+                     "value": pts_step * world * n_sus / (sus_ms / 1e3) / 1e6, "unit": UNIT, "clocks": clocks2}
+        cm.set_profiling(True)
+
     # ---- roofline: algorithmic bytes per launch / CUDA-event duration of that launch ----------------------------------
     peak, peak_src = peaks()
     stage_ms = {k: v / args.steps for k, v in stage_acc.items()}
@@ -539,7 +568,7 @@ def main():
                        "timed_region": "K steps enqueued back to back on one stream, one report read at the end; stage times = last timed step",
                        "l2": "inputs larger than L2 (%.0f MB raw input per step per GPU)" % (pts_step * 16 / 1e6)},
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "stages": stages,
-            "cpu_baseline": cpu,
+            "cpu_baseline": cpu, "sustained": sustained,
         }
         if latency:
             line["latency"] = latency

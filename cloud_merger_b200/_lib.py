@@ -107,6 +107,7 @@ SYMBOLS = {
     "cm_set_voxel": (C.c_int, [_H, C.POINTER(C.c_float), C.c_int, C.c_int]),
     "cm_set_voxel_bounds": (C.c_int, [_H, C.POINTER(C.c_float), C.POINTER(C.c_float)]),
     "cm_set_overflow_mode": (C.c_int, [_H, C.c_int]),
+    "cm_set_submit_policy": (C.c_int, [_H, C.c_int]),
     "cm_submit_cloud": (C.c_int, [_H, C.c_int, C.c_void_p, C.c_int64, C.POINTER(CmLayout), C.c_uint64]),
     "cm_submit_cloud_pinned": (C.c_int, [_H, C.c_int, C.c_void_p, C.c_int64, C.POINTER(CmLayout), C.c_uint64]),
     "cm_submit_clouds_pinned": (C.c_int, [_H, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_void_p), C.POINTER(C.c_int64),

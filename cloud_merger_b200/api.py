@@ -395,6 +395,11 @@ class CloudMerger:
     def set_overflow_mode(self, pcl_like: bool):
         self._check(self._lib.cm_set_overflow_mode(self._h, int(pcl_like)))
 
+    def set_submit_policy(self, first_wins: bool):
+        """False (default): the newest cloud of a sensor is merged (my_cloud_fusion); True: the first one after the previous
+        merge, later ones are dropped -- pcl_preprocessing's flag gate (pc_preprocessing_main.cpp:330)."""
+        self._check(self._lib.cm_set_submit_policy(self._h, 1 if first_wins else 0))
+
     def set_profiling(self, on: bool):
         self._check(self._lib.cm_set_profiling(self._h, int(on)))
 

@@ -107,8 +107,18 @@ struct SensorState {
 
 struct Slot {
   Workspace ws;
-  uint8_t* raw_dev = nullptr;
+  uint8_t* raw_dev = nullptr;     // one region per sensor (single submissions, carried-over clouds)
   uint8_t* raw_pinned = nullptr;
+  // cm_submit_clouds_pinned: host-adjacent clouds travel as one copy into this bump-allocated arena, so a coalesced run
+  // never shares bytes with a sensor's own region or with another run; reset when the slot's frame has been merged
+  uint8_t* arena_dev = nullptr;
+  size_t arena_bytes = 0, arena_used = 0;
+  // page-locked, device-mapped mirrors of the frame's voxel outputs: the last kernel of the frame (k_export_voxels) writes
+  // them over PCIe, sized on the device, so cm_wait_frame needs ONE synchronisation and no copy of its own
+  uint8_t* exp_xyzi = nullptr;
+  uint32_t* exp_count = nullptr;
+  unsigned long long* exp_idx = nullptr;
+  uint32_t exp_cap = 0;
   std::vector<SensorState> sensor;
   cudaStream_t stream = nullptr;
   cudaEvent_t done = nullptr;
@@ -188,6 +198,7 @@ struct cm_handle_s {
   int64_t ticket_counter = 0;
   bool host_ready = false;
   bool use_graph = true;  // CM_NO_GRAPH=1 switches the frame graphs off
+  int submit_policy = CM_SUBMIT_LATEST_WINS;
 };
 
 namespace {
@@ -653,6 +664,13 @@ int ensure_host_path(cm_handle_t h) {
     if (rc != CM_OK) return rc;
     CM_CUDA(h, cudaMalloc(reinterpret_cast<void**>(&sl.raw_dev), h->slot_stride * c.max_sensors));
     CM_CUDA(h, cudaMallocHost(reinterpret_cast<void**>(&sl.raw_pinned), h->slot_stride * c.max_sensors));
+    sl.arena_bytes = 2 * h->slot_stride * c.max_sensors;
+    CM_CUDA(h, cudaMalloc(reinterpret_cast<void**>(&sl.arena_dev), sl.arena_bytes));
+    sl.exp_cap = (uint32_t)pts;
+    const size_t ecap = std::max<size_t>(sl.exp_cap, 1);
+    CM_CUDA(h, cudaHostAlloc(reinterpret_cast<void**>(&sl.exp_xyzi), ecap * (size_t)c.out_point_step, cudaHostAllocMapped));
+    CM_CUDA(h, cudaHostAlloc(reinterpret_cast<void**>(&sl.exp_count), ecap * sizeof(uint32_t), cudaHostAllocMapped));
+    CM_CUDA(h, cudaHostAlloc(reinterpret_cast<void**>(&sl.exp_idx), ecap * sizeof(unsigned long long), cudaHostAllocMapped));
     sl.sensor.resize(c.max_sensors);
     for (auto& ss : sl.sensor) CM_CUDA(h, cudaEventCreateWithFlags(&ss.copied, cudaEventDisableTiming));
     CM_CUDA(h, cudaStreamCreateWithFlags(&sl.stream, cudaStreamNonBlocking));
@@ -677,6 +695,9 @@ int submit_impl(cm_handle_t h, int sensor, const void* data, int64_t n_points, c
   Slot& sl = h->slots[h->fill];
   if (sl.busy) return fail(h, CM_E_CAPACITY, "all %d frame slots are in flight: call cm_wait_frame first", h->cfg.frames_in_flight);
   SensorState& ss = sl.sensor[sensor];
+  // the reference's flag gate `if (!flag_x) { store; flag_x = true; }` (pc_preprocessing_main.cpp:330): a cloud that
+  // arrives while the sensor's previous one is still waiting to be fused is dropped
+  if (h->submit_policy == CM_SUBMIT_FIRST_WINS && ss.submitted) return CM_OK;
   const size_t bytes = (size_t)n_points * (size_t)layout->point_step;
   uint8_t* dst = sl.raw_dev + (size_t)sensor * h->slot_stride;
   cudaStream_t st = h->sensor_stream[sensor];
@@ -693,6 +714,23 @@ int submit_impl(cm_handle_t h, int sensor, const void* data, int64_t n_points, c
   CM_CUDA(h, cudaEventRecord(ss.copied, st));
   ss.submitted = true; ss.n_points = n_points; ss.layout = *layout; ss.stamp = stamp; ss.dev = dst;
   return CM_OK;
+}
+
+// Tail of a host-path frame on its stream: the voxels go to the slot's page-locked mirrors (k_export_voxels, sized by the
+// device-resident voxel count) and the control block to the pinned report -- both before the frame's `done` event, so
+// cm_wait_frame synchronises once and copies nothing over PCIe itself.
+cudaError_t enqueue_frame_export(cm_handle_t h, Slot& sl) {
+  Workspace& w = sl.ws;
+  VoxelParams vp;
+  fill_voxel_params(h, w, vp, w.surv_xyzi, 1, 0);
+  void *dx = nullptr, *dc = nullptr, *di = nullptr;
+  cudaError_t e = cudaHostGetDevicePointer(&dx, sl.exp_xyzi, 0);
+  if (e == cudaSuccess) e = cudaHostGetDevicePointer(&dc, sl.exp_count, 0);
+  if (e == cudaSuccess) e = cudaHostGetDevicePointer(&di, sl.exp_idx, 0);
+  if (e == cudaSuccess) e = launch_export_voxels(vp, dx, static_cast<uint32_t*>(dc), static_cast<unsigned long long*>(di), sl.exp_cap, sl.stream);
+  if (e != cudaSuccess) return e;
+  ++w.launches;
+  return cudaMemcpyAsync(w.report, w.meta, w.ml.total, cudaMemcpyDeviceToHost, sl.stream);
 }
 
 int merge_async_impl(cm_handle_t h, uint64_t mask, int64_t* ticket) {
@@ -745,7 +783,7 @@ int merge_async_impl(cm_handle_t h, uint64_t mask, int64_t* ticket) {
       rc = run_pipeline(h, sl.ws, segs.data(), (int)segs.size(), sl.stream, true);
       sl.ws.capturing = false;
       cudaError_t ce = cudaSuccess;
-      if (rc == CM_OK) ce = cudaMemcpyAsync(sl.ws.report, sl.ws.meta, sl.ws.ml.total, cudaMemcpyDeviceToHost, sl.stream);
+      if (rc == CM_OK) ce = enqueue_frame_export(h, sl);
       const cudaError_t ee = cudaStreamEndCapture(sl.stream, &g);
       if (rc == CM_OK && ce == cudaSuccess && ee == cudaSuccess && g &&
           cudaGraphInstantiate(&sl.graph, g, 0) == cudaSuccess) {
@@ -770,12 +808,14 @@ int merge_async_impl(cm_handle_t h, uint64_t mask, int64_t* ticket) {
     if (sl.graph && sl.graph_key != key) { cudaGraphExecDestroy(sl.graph); sl.graph = nullptr; sl.graph_key.clear(); }
     rc = run_pipeline(h, sl.ws, segs.data(), (int)segs.size(), sl.stream, true);
     if (rc != CM_OK) return rc;
-    CM_CUDA(h, cudaMemcpyAsync(sl.ws.report, sl.ws.meta, sl.ws.ml.total, cudaMemcpyDeviceToHost, sl.stream));
+    CM_CUDA(h, enqueue_frame_export(h, sl));
     sl.graph_seen = key;
   }
   CM_CUDA(h, cudaEventRecord(sl.done, sl.stream));
-  for (int s = 0; s < h->cfg.max_sensors; ++s)
-    if ((used >> s) & 1ull) sl.sensor[s].submitted = false;
+  // Every submission of this slot ends here: merged clouds are consumed; a cloud submitted for a sensor outside the mask is
+  // discarded (it would otherwise resurface, stale, when the slot comes round again frames_in_flight frames later).
+  for (int s = 0; s < h->cfg.max_sensors; ++s) sl.sensor[s].submitted = false;
+  sl.arena_used = 0;
   sl.busy = true; sl.used_mask = used; sl.stamp = stamp;
   sl.ticket = ++h->ticket_counter;
   *ticket = sl.ticket;
@@ -829,6 +869,12 @@ int wait_impl(cm_handle_t h, int64_t ticket, cm_frame_out_t* out, uint64_t* used
     }
     if (out->voxel_count) for (size_t i = 0; i < nv; ++i) out->voxel_count[i] = 1;
     if (out->voxel_idx) for (size_t i = 0; i < nv; ++i) out->voxel_idx[i] = 0;
+  } else if (nv <= (size_t)sl->exp_cap) {
+    // the frame's own stream already wrote the voxels to the slot's page-locked mirrors (k_export_voxels): plain memcpy
+    if (out->voxel_xyzi && nv) memcpy(out->voxel_xyzi, sl->exp_xyzi, nv * (size_t)w.out_step);
+    if (out->voxel_count && nv) memcpy(out->voxel_count, sl->exp_count, nv * 4);
+    if (out->voxel_idx && nv) memcpy(out->voxel_idx, sl->exp_idx, nv * 8);
+    if (!((out->survivor_xyzi || out->survivor_src) && ns)) return CM_OK;
   } else {
     if (out->voxel_xyzi && nv) CM_CUDA(h, cudaMemcpyAsync(out->voxel_xyzi, w.out_xyzi, nv * (size_t)w.out_step, cudaMemcpyDeviceToHost, st));
     if (out->voxel_count && nv) CM_CUDA(h, cudaMemcpyAsync(out->voxel_count, w.out_count, nv * 4, cudaMemcpyDeviceToHost, st));
@@ -917,7 +963,10 @@ int cm_destroy(cm_handle_t h) {
   ws_free(h->batch);
   for (auto& sl : h->slots) {
     ws_free(sl.ws);
-    cudaFree(sl.raw_dev); cudaFreeHost(sl.raw_pinned);
+    cudaFree(sl.raw_dev); cudaFreeHost(sl.raw_pinned); cudaFree(sl.arena_dev);
+    if (sl.exp_xyzi) cudaFreeHost(sl.exp_xyzi);
+    if (sl.exp_count) cudaFreeHost(sl.exp_count);
+    if (sl.exp_idx) cudaFreeHost(sl.exp_idx);
     for (auto& ss : sl.sensor) if (ss.copied) cudaEventDestroy(ss.copied);
     if (sl.graph) cudaGraphExecDestroy(sl.graph);
     if (sl.stream) cudaStreamDestroy(sl.stream);
@@ -1020,6 +1069,13 @@ int cm_set_overflow_mode(cm_handle_t h, int mode) {
   return CM_OK;
 }
 
+int cm_set_submit_policy(cm_handle_t h, int policy) {
+  if (!h || (policy != CM_SUBMIT_LATEST_WINS && policy != CM_SUBMIT_FIRST_WINS)) return CM_E_INVALID;
+  std::lock_guard<std::mutex> lk(h->mu);
+  h->submit_policy = policy;
+  return CM_OK;
+}
+
 int cm_set_profiling(cm_handle_t h, int on) {
   if (!h) return CM_E_INVALID;
   h->profiling = on != 0;
@@ -1052,29 +1108,47 @@ int cm_submit_clouds_pinned(cm_handle_t h, int count, const int* sensors, const 
     if (layouts[i].point_step > h->cfg.max_point_step) return fail(h, CM_E_CAPACITY, "cloud %d: point_step %d > max_point_step", i, layouts[i].point_step);
   }
   // Clouds that follow each other in host memory, belong to consecutive sensor ids and are 16-byte multiples travel as ONE
-  // copy (a 2 MB copy reaches ~50 GB/s over PCIe 5 x16, an 8 MB one ~54): they are laid out back to back from the first
-  // sensor's region of the slot, which only ever covers regions of the run's own members.
-  int i = 0;
-  while (i < count) {
+  // copy (a 2 MB copy reaches ~50 GB/s over PCIe 5 x16, an 8 MB one ~54) into the slot's frame arena: bump-allocated, so a
+  // coalesced run never shares bytes with a sensor's own region (single submissions) or with another run. Superseded
+  // clouds simply stay behind in the arena until the frame is merged; when it is full the clouds go one by one.
+  std::vector<int> pick;
+  pick.reserve((size_t)count);
+  for (int i = 0; i < count; ++i) {
+    if (h->submit_policy == CM_SUBMIT_FIRST_WINS && sl.sensor[sensors[i]].submitted) continue;  // the reference's flag gate
+    pick.push_back(i);
+  }
+  size_t a = 0;
+  while (a < pick.size()) {
+    const int i = pick[a];
     size_t run_bytes = (size_t)n_points[i] * (size_t)layouts[i].point_step;
-    int j = i + 1;
-    while (j < count && sensors[j] == sensors[j - 1] + 1 && run_bytes % 16 == 0 && run_bytes > 0 &&
-           static_cast<const uint8_t*>(data[j]) == static_cast<const uint8_t*>(data[i]) + run_bytes) {
-      run_bytes += (size_t)n_points[j] * (size_t)layouts[j].point_step;
-      ++j;
+    size_t b = a + 1;
+    while (b < pick.size() && pick[b] == pick[b - 1] + 1 && sensors[pick[b]] == sensors[pick[b - 1]] + 1 && run_bytes % 16 == 0 &&
+           run_bytes > 0 && static_cast<const uint8_t*>(data[pick[b]]) == static_cast<const uint8_t*>(data[i]) + run_bytes) {
+      run_bytes += (size_t)n_points[pick[b]] * (size_t)layouts[pick[b]].point_step;
+      ++b;
     }
-    uint8_t* dst = sl.raw_dev + (size_t)sensors[i] * h->slot_stride;
+    const size_t need = align_up(run_bytes, kAlign);
+    if (b - a >= 2 && sl.arena_used + need > sl.arena_bytes) b = a + 1;  // arena full: this cloud alone, into its own region
     cudaStream_t st = h->sensor_stream[sensors[i]];
+    uint8_t* dst;
+    if (b - a >= 2) {
+      dst = sl.arena_dev + sl.arena_used;
+      sl.arena_used += need;
+    } else {
+      run_bytes = (size_t)n_points[i] * (size_t)layouts[i].point_step;
+      dst = sl.raw_dev + (size_t)sensors[i] * h->slot_stride;
+    }
     if (run_bytes) CM_CUDA(h, cudaMemcpyAsync(dst, data[i], run_bytes, cudaMemcpyHostToDevice, st));
     size_t off = 0;
-    for (int k = i; k < j; ++k) {
-      SensorState& ss = sl.sensor[sensors[k]];
+    for (size_t k = a; k < b; ++k) {
+      const int c = pick[k];
+      SensorState& ss = sl.sensor[sensors[c]];
       CM_CUDA(h, cudaEventRecord(ss.copied, st));
-      ss.submitted = true; ss.n_points = n_points[k]; ss.layout = layouts[k]; ss.stamp = stamps ? stamps[k] : 0;
+      ss.submitted = true; ss.n_points = n_points[c]; ss.layout = layouts[c]; ss.stamp = stamps ? stamps[c] : 0;
       ss.dev = dst + off;
-      off += (size_t)n_points[k] * (size_t)layouts[k].point_step;
+      off += (size_t)n_points[c] * (size_t)layouts[c].point_step;
     }
-    i = j;
+    a = b;
   }
   return CM_OK;
 }

@@ -110,7 +110,11 @@ struct Ctrl {
   uint32_t total_voxels;
   uint32_t has_invalid;
   uint32_t pad_;
+  uint32_t role_counter[CM_MAX_SORT_PASSES];  // [p]: arrival ticket of the CTAs of radix pass p (the first arrivals scan)
+  uint32_t cent_ticket;       // next tile of the persistent centroid kernel
+  uint32_t pad2_[7];
 };
+static_assert(sizeof(Ctrl) == 128, "Ctrl is two cache lines");
 
 // ---- written by k_grid_setup -----------------------------------------------------------------------------------
 struct GridDev {
@@ -185,6 +189,11 @@ __device__ __forceinline__ float ldg_stream_f1(const void* p) {
 #define CM_LB_AGG 1u
 #define CM_LB_INCL 2u
 #define CM_SPIN_LIMIT (1u << 22)
+// Watchdog of the spin loops: wall-clock based (%globaltimer, nanoseconds), so that a kernel that merely shares the GPU
+// with other work (several handles sorting at once, MPS, time slicing) is not mistaken for a stuck one. The timer is read
+// once every CM_WATCHDOG_STRIDE polls.
+#define CM_WATCHDOG_NS 4000000000ull
+#define CM_WATCHDOG_STRIDE 1024u
 
 __device__ __forceinline__ unsigned long long lb_pack(uint32_t epoch, uint32_t flag, uint32_t value) {
   return ((unsigned long long)(epoch * 4u + flag) << 32) | (unsigned long long)value;
@@ -215,14 +224,32 @@ __device__ __forceinline__ bool lb_ready(unsigned long long w, uint32_t epoch) {
   return (hi >> 2) == epoch && (hi & 3u) != 0u;
 }
 
+__device__ __forceinline__ unsigned long long global_timer_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+// One poll of a spin loop went by without success: true once the loop has been spinning for CM_WATCHDOG_NS. `spins` and
+// `t0` are the loop's own state (t0 = 0 until the first timer read).
+__device__ __forceinline__ bool watchdog_expired(uint32_t& spins, unsigned long long& t0) {
+  if ((++spins & (CM_WATCHDOG_STRIDE - 1u)) != 0u) return false;
+  const unsigned long long now = global_timer_ns();
+  if (t0 == 0ull) {
+    t0 = now;
+    return false;
+  }
+  return now - t0 > CM_WATCHDOG_NS;
+}
+
 // Spin until the word of this epoch carries the INCLUSIVE flag (written by the scanner CTAs of the radix pass).
 __device__ __forceinline__ uint32_t lb_wait_inclusive(unsigned long long* p, uint32_t epoch, uint32_t* err) {
   uint32_t spins = 0;
+  unsigned long long t0 = 0ull;
   while (true) {
     const unsigned long long w = ld_relaxed_u64(p);
     const uint32_t hi = (uint32_t)(w >> 32);
     if ((hi >> 2) == epoch && (hi & 3u) == CM_LB_INCL) return (uint32_t)w;
-    if (++spins > CM_SPIN_LIMIT) {
+    if (watchdog_expired(spins, t0)) {
       atomicExch(err, (uint32_t)CM_DEV_E_INTERNAL);
       return 0u;
     }

@@ -93,6 +93,9 @@ cudaError_t launch_split_records(const void* records, uint32_t* keys, uint32_t* 
                                  uint32_t max_points, cudaStream_t stream);
 cudaError_t launch_centroid(const VoxelParams& p, cudaStream_t stream);        // 3 launches: centroid, scan, compact
 #define CM_CENTROID_LAUNCHES 3
+// host path: dense voxel outputs of a one-frame run -> device-mapped page-locked host arrays, sized by Ctrl.total_voxels
+cudaError_t launch_export_voxels(const VoxelParams& p, void* host_xyzi, uint32_t* host_count, unsigned long long* host_idx,
+                                 uint32_t cap, cudaStream_t stream);
 
 // ---- zone slicing: multi-output PassThrough compaction (cm_zones.cu) -------------------------------------------------------
 struct ZoneParams {

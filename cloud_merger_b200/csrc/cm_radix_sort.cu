@@ -84,11 +84,12 @@ constexpr int RS_SCAN_ROWS = 32;                        // rows per batch (one w
 constexpr int RS_SCAN_GROUP = RS_THREADS >= 512 ? 8 : 16;  // rows polled together (register budget of the CTA shape)
 static_assert(RS_SCAN_DIGITS == 32, "one digit per lane");
 
-__device__ __forceinline__ void scanner_cta(unsigned long long* rows /* row 0 */, uint32_t n_tiles, uint32_t epoch,
-                                            const uint32_t* hist /* this pass */, uint32_t* err, uint32_t* s_scan,
-                                            uint32_t* s_tmp /* >= 256 words */, unsigned long long* s_chain /* 32 */) {
+__device__ __forceinline__ void scanner_cta(uint32_t scanner /* 0 .. RS_SCANNERS-1 */, unsigned long long* rows /* row 0 */,
+                                            uint32_t n_tiles, uint32_t epoch, const uint32_t* hist /* this pass */,
+                                            uint32_t* err, uint32_t* s_scan, uint32_t* s_tmp /* >= 256 words */,
+                                            unsigned long long* s_chain /* 32 */) {
   const uint32_t tid = threadIdx.x, lane = tid & 31u, q = tid >> 5;
-  const uint32_t d = blockIdx.x * RS_SCAN_DIGITS + lane;  // digit
+  const uint32_t d = scanner * RS_SCAN_DIGITS + lane;  // digit
   // exclusive scan of the global digit histogram: where digit d starts in the output of this pass
   uint32_t tot;
   const uint32_t gb = block_excl_scan_256(tid < CM_RADIX ? hist[tid] : 0u, s_scan, &tot);
@@ -109,6 +110,7 @@ __device__ __forceinline__ void scanner_cta(unsigned long long* rows /* row 0 */
 #pragma unroll
     for (int g0 = 0; g0 < RS_SCAN_ROWS; g0 += RS_SCAN_GROUP) {
       uint32_t spins = 0;
+      unsigned long long wd0 = 0ull;
       while (true) {
         unsigned long long w[RS_SCAN_GROUP];
 #pragma unroll
@@ -121,7 +123,8 @@ __device__ __forceinline__ void scanner_cta(unsigned long long* rows /* row 0 */
           c[g0 + k] = (uint32_t)w[k];
         }
         if (__all_sync(0xFFFFFFFFu, all)) break;
-        if (++spins > (CM_SPIN_LIMIT >> 4)) {  // watchdog: raise the device error and let everything drain
+        // watchdog (wall clock): raise the device error and let everything drain
+        if (__any_sync(0xFFFFFFFFu, watchdog_expired(spins, wd0))) {
           atomicExch(err, (uint32_t)CM_DEV_E_INTERNAL);
           break;
         }
@@ -137,8 +140,9 @@ __device__ __forceinline__ void scanner_cta(unsigned long long* rows /* row 0 */
     // serial part: take the running sum from the previous batch's warp, pass it on
     unsigned long long x = *chain;
     uint32_t spins = 0;
+    unsigned long long wd0 = 0ull;
     while ((uint32_t)(x >> 32) != b) {
-      if (++spins > CM_SPIN_LIMIT) {
+      if (watchdog_expired(spins, wd0)) {
         atomicExch(err, (uint32_t)CM_DEV_E_INTERNAL);
         break;
       }
@@ -211,10 +215,21 @@ __global__ void __launch_bounds__(RS_THREADS, RS_MIN_CTAS) k_onesweep_pass(const
   const uint32_t epoch = *p.epoch_dev + 1u + (uint32_t)pass;
   unsigned long long* const rows = p.lb_sort + CM_RADIX;  // row -1 lives in front
   uint32_t* const err = &p.ctrl->error;
-  // CTAs of a 1-D grid are dispatched in index order, so the scanners are resident before any worker can wait for them
-  // (and the grid never exceeds what the device holds at once); the watchdogs cover the case that this fails to hold.
-  if (blockIdx.x < RS_SCANNERS) {
-    scanner_cta(rows, n_tiles, epoch, p.hist + pass * CM_RADIX, err, sm.scan, sm.hist, &sm.k[0][0]);
+  // Roles go by ARRIVAL, not by block index: the first RS_SCANNERS CTAs of the pass to start running are the scanners, so
+  // the scanners are resident by construction whatever order the hardware dispatches CTAs in and whatever else shares the
+  // GPU (several handles sorting on their own streams, MPS). Later arrivals work; a worker publishes its counts before it
+  // waits, so the pair cannot deadlock. The same shared-memory hand-over carries the worker's first tile.
+  uint32_t* const counter = &p.ctrl->tile_counter[1 + pass];
+  if (tid == 0) {
+    const uint32_t role = atomicAdd(&p.ctrl->role_counter[pass], 1u);
+    sm.next_tile[1] = role;
+    if (role >= (uint32_t)RS_SCANNERS) sm.next_tile[0] = atomicAdd(counter, 1u);
+  }
+  __syncthreads();
+  const uint32_t role = sm.next_tile[1];
+  if (role < (uint32_t)RS_SCANNERS) {
+    __syncthreads();  // every thread has read the role before the scanner reuses the shared memory
+    scanner_cta(role, rows, n_tiles, epoch, p.hist + pass * CM_RADIX, err, sm.scan, sm.hist, &sm.k[0][0]);
     return;
   }
 
@@ -223,17 +238,15 @@ __global__ void __launch_bounds__(RS_THREADS, RS_MIN_CTAS) k_onesweep_pass(const
   const uint32_t shift = (uint32_t)pass * CM_RADIX_BITS;
   const uint32_t lt = lanemask_lt(), gt = lanemask_gt();
   uint32_t* const wh = sm.hist + warp * CM_RADIX;  // the warp's own counter row
-  uint32_t* const counter = &p.ctrl->tile_counter[1 + pass];
 
   // Tiles are handed out by an atomic counter (forward progress never depends on which CTAs are resident). A CTA works
   // on two tiles at a time, software-pipelined:  front(t1): load, rank, publish counts, place into buffer b1
   //                                              back(t0):  wait for row t0-1 from the scanners, scatter buffer b0
   // so the scanners' latency (poll + chain + store + our poll, ~4-6 thousand cycles) hides behind front(t1) instead of
   // idling a third of the SM's warps as it did when a CTA handled one tile from start to end.
-  if (tid == 0) sm.next_tile[0] = atomicAdd(counter, 1u);
   if (RS_EARLY_COUNT && tid < CM_RADIX) sm.cnt[tid] = 0;
-  __syncthreads();
   uint32_t cur = sm.next_tile[0];
+  __syncthreads();  // next_tile[1] (the role) is rewritten below; sm.cnt is cleared
   uint32_t prev = 0xFFFFFFFFu, prev_n = 0;
   uint32_t buf = 0;  // also the parity of the iteration
   long long tr_cur = tr0, tr_prev = tr0;

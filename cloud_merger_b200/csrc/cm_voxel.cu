@@ -650,6 +650,28 @@ __global__ void __launch_bounds__(VX_THREADS) k_compact_voxels(const VoxelParams
   }
 }
 
+// ---- host path: the frame's dense voxel outputs -> page-locked (device-mapped) host memory ------------------------------
+// Last kernel of a host-path frame. The number of voxels is only known on the device (Ctrl.total_voxels), so a
+// cudaMemcpyAsync of the right size would need a host round trip first; this kernel reads the count itself and pushes the
+// three arrays over PCIe with 16-byte stores (a frame's voxels are ~1 MB: a few microseconds of link time).
+__global__ void __launch_bounds__(VX_THREADS) k_export_voxels(const VoxelParams p, uint4* __restrict__ host_xyzi,
+                                                             uint32_t* __restrict__ host_count,
+                                                             unsigned long long* __restrict__ host_idx, uint32_t cap) {
+  const uint32_t V = min(p.ctrl->total_voxels, cap);
+  const uint32_t stride = gridDim.x * VX_THREADS, t0 = blockIdx.x * VX_THREADS + threadIdx.x;
+  const uint32_t n16 = V * (p.out_step / 16u);
+  const uint4* __restrict__ sx = reinterpret_cast<const uint4*>(p.out_xyzi);
+  for (uint32_t i = t0; i < n16; i += stride) host_xyzi[i] = sx[i];
+  const uint4* __restrict__ sc = reinterpret_cast<const uint4*>(p.out_count);
+  for (uint32_t i = t0; i < V / 4u; i += stride) reinterpret_cast<uint4*>(host_count)[i] = sc[i];
+  const uint4* __restrict__ si = reinterpret_cast<const uint4*>(p.out_idx);
+  for (uint32_t i = t0; i < V / 2u; i += stride) reinterpret_cast<uint4*>(host_idx)[i] = si[i];
+  if (blockIdx.x == 0) {  // tails
+    for (uint32_t i = (V & ~3u) + threadIdx.x; i < V; i += VX_THREADS) host_count[i] = p.out_count[i];
+    for (uint32_t i = (V & ~1u) + threadIdx.x; i < V; i += VX_THREADS) host_idx[i] = p.out_idx[i];
+  }
+}
+
 // ---- launchers ----------------------------------------------------------------------------------------------------
 static inline uint32_t persistent_grid(uint32_t n_tiles) {
   const uint32_t cap = 148u * 8u;
@@ -713,6 +735,13 @@ cudaError_t launch_centroid(const VoxelParams& p, cudaStream_t stream) {
   e = cudaGetLastError();
   if (e != cudaSuccess) return e;
   k_compact_voxels<<<persistent_grid(tiles), VX_THREADS, 0, stream>>>(p);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_export_voxels(const VoxelParams& p, void* host_xyzi, uint32_t* host_count, unsigned long long* host_idx,
+                                 uint32_t cap, cudaStream_t stream) {
+  const uint32_t blocks = std::max(1u, std::min<uint32_t>(148u, (cap + 4u * VX_THREADS - 1u) / (4u * VX_THREADS)));
+  k_export_voxels<<<blocks, VX_THREADS, 0, stream>>>(p, static_cast<uint4*>(host_xyzi), host_count, host_idx, cap);
   return cudaGetLastError();
 }
 

@@ -229,8 +229,19 @@ CM_API int cm_set_overflow_mode(cm_handle_t h, int mode);
 /* ---- host path: one frame at a time, callable from the ROS callbacks ----
  * cm_submit_cloud replaces the body of callbackFrontRight .. callbackFrontMiddle up to the hand-off into the globals
  * (pc_preprocessing_main.cpp:318-337 ...) and add_*_velodyne (CloudFusionNode.h:506-534): it takes the raw point records,
- * copies them to the device asynchronously and returns; latest submission per sensor wins (subscriber queue size 0/1 +
- * flag gate, :330). stamp feeds operator+='s "newest stamp" rule. */
+ * copies them to the device asynchronously and returns. stamp feeds operator+='s "newest stamp" rule.
+ * Which cloud of a sensor a frame is merged from, when the sensor delivers more than one between two merges
+ * (cm_set_submit_policy):
+ *   CM_SUBMIT_LATEST_WINS (default)  the newest one -- what my_cloud_fusion does (add_*_velodyne overwrites its member cloud on
+ *                                    every callback, CloudFusionNode.h:506-534);
+ *   CM_SUBMIT_FIRST_WINS             the first one after the previous merge -- pcl_preprocessing's flag gate
+ *                                    `if (!flag_x) { store; flag_x = true; }` (pc_preprocessing_main.cpp:330-336): later clouds
+ *                                    are dropped (the call returns CM_OK without copying) until the frame has been merged.
+ * Every submission ends with the next merge: clouds of sensors in the merge mask are consumed, clouds of other sensors are
+ * discarded. */
+#define CM_SUBMIT_LATEST_WINS 0
+#define CM_SUBMIT_FIRST_WINS 1
+CM_API int cm_set_submit_policy(cm_handle_t h, int policy);
 CM_API int cm_submit_cloud(cm_handle_t h, int sensor, const void* data, int64_t n_points, const cm_layout_t* layout,
                            uint64_t stamp);
 /* Same, for a caller buffer that is page-locked (cm_host_alloc / cudaHostRegister) and stays untouched until the frame it
@@ -239,7 +250,8 @@ CM_API int cm_submit_cloud_pinned(cm_handle_t h, int sensor, const void* data, i
                                   const cm_layout_t* layout, uint64_t stamp);
 /* Several page-locked clouds of one frame at once (a rosbag replay, or a driver that delivers all sensors together):
  * the same as `count` calls of cm_submit_cloud_pinned, except that clouds which follow each other in host memory and
- * belong to consecutive sensor ids are copied with one transfer. stamps may be NULL. */
+ * belong to consecutive sensor ids are copied with one transfer (into a per-frame arena of the handle, so the run shares
+ * no device bytes with single submissions of its members). stamps may be NULL. */
 CM_API int cm_submit_clouds_pinned(cm_handle_t h, int count, const int* sensors, const void* const* data,
                                    const int64_t* n_points, const cm_layout_t* layouts, const uint64_t* stamps);
 /* cm_merge_frame replaces fusePointclouds + voxelgrid (pc_preprocessing_main.cpp:131-177, main loop :574-578):
@@ -250,7 +262,9 @@ CM_API int cm_submit_clouds_pinned(cm_handle_t h, int count, const int* sensors,
 CM_API int cm_merge_frame(cm_handle_t h, uint64_t sensor_mask, cm_frame_out_t* out, uint64_t* out_used_mask,
                           uint64_t* out_stamp);
 /* Pipelined form: cm_merge_frame_async enqueues the work and returns a ticket; cm_wait_frame blocks on that ticket and
- * copies out. Up to frames_in_flight tickets may be outstanding. */
+ * copies out. Up to frames_in_flight tickets may be outstanding. The voxel outputs travel to page-locked host memory on the
+ * frame's own stream (sized on the device), so cm_wait_frame is ONE synchronisation followed by host memcpys; only the
+ * optional survivor outputs cost a second device round trip. */
 CM_API int cm_merge_frame_async(cm_handle_t h, uint64_t sensor_mask, int64_t* ticket);
 CM_API int cm_wait_frame(cm_handle_t h, int64_t ticket, cm_frame_out_t* out, uint64_t* out_used_mask,
                          uint64_t* out_stamp);

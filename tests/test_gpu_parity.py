@@ -484,3 +484,203 @@ def test_full_size_batch_properties(gpu_ok, oracle):
             assert (out["voxel_count"][v0:v1] == fo["count"]).all()
             assert_bit_equal(out["voxel_xyzi"][v0:v1], fo["centroid"], "frame %d centroids" % f)
         del sub
+
+
+# ---- round 2: every sort instantiation and every BASELINE config at size ------------------------------------------------
+def _voxel_only(cm, x, leaf, min_points):
+    cm.set_voxel(leaf, min_points, True)
+    buf = cm.upload(x)
+    cm.dev_voxelgrid(buf.ptr, len(x))
+    out = cm.fetch_batch_outputs()
+    buf.free()
+    return out
+
+
+@pytest.mark.parametrize("leaf", [0.01, 0.02])
+def test_sort_64bit_big_tile_at_size(gpu_ok, oracle, leaf):
+    """k_onesweep_pass<unsigned long long, 8> (64-bit keys, the big tile: handle capacity above 1 363 968 keys) on
+    2.5 Mi points whose grid exceeds PCL's INT32 cell limit (36 / 39 key bits, 5 passes): membership, counts, order,
+    centroids against the 64-bit oracle."""
+    n = 5 << 19
+    x = synth.uniform_cloud(61, n, extent=(200.0, 200.0, 10.0))
+    x[:200000] = synth.uniform_cloud(62, 200000, extent=(3.0, 3.0, 1.0))  # a dense clump: runs that cross tiles
+    with CloudMerger(max_batch_points=n) as cm:
+        out = _voxel_only(cm, x, leaf, 1)
+    o = oracle.voxelgrid(x, [leaf] * 3, 1, True, force64=True)
+    o.update(n_voxels=o["n"], n_survivors=n)
+    assert out["key_bytes"] == 8 and out["stats"].key_bits > 32 and out["stats"].sort_passes >= 5
+    assert out["stats"].pcl_overflow == 1 and o["pcl_overflow"]
+    assert _check_voxels(out, out["frames"], [o]) <= 1e-5
+
+
+def test_cfg1_batch_of_64_frames_at_size(gpu_ok, oracle):
+    """BASELINE config 1 (2 x 64k points, z-only PassThrough -> unbounded grid) as a 64-frame device batch: the key plan is
+    made on the device; every frame against the oracle."""
+    c = synth.CONFIGS["cfg1"]
+    F, S = 64, c["sensors"]
+    n = c["rings"] * c["azimuth"]
+    with CloudMerger(max_sensors=S, max_batch_points=F * S * n, max_batch_frames=F) as cm:
+        for s in range(S):
+            cm.set_extrinsic(s, synth.extrinsic(s, S))
+        cm.set_crop(c["passes"])
+        cm.set_voxel(c["leaf"], c["min_points"], True)
+        frames = [[(synth.lidar_cloud(1000, s, f, c["rings"], c["azimuth"]), 1) for s in range(S)] for f in range(F)]
+        segs, per_frame = _upload_segments(cm, frames, lambda f, s: LAYOUTS["packed16"])
+        cm.run_batch(segs)
+        out = cm.fetch_batch_outputs()
+    assert out["stats"].frames == F and out["stats"].device_error == 0 and out["stats"].survivors > 1363968
+    o = _oracle_frames(oracle, per_frame, c["passes"], [c["leaf"]] * 3, c["min_points"])
+    _check_survivors(out, out["frames"], o)
+    assert _check_voxels(out, out["frames"], o) <= 1e-5
+
+
+def test_cfg3_full_size_host_path_and_batch(gpu_ok, oracle):
+    """BASELINE config 3 (8 sensors x 256k points, ROI box, leaf 0.05) at full size: one frame through the host path
+    (cm_submit_cloud x 8 + cm_merge_frame) and a 16-frame device batch (the bench shape), every frame against the oracle."""
+    c = synth.CONFIGS["cfg3"]
+    F, S = 16, c["sensors"]
+    n = c["rings"] * c["azimuth"]
+    mats = [synth.extrinsic(s, S) for s in range(S)]
+    frames = [[(synth.lidar_cloud(3000, s, f, c["rings"], c["azimuth"]), 1) for s in range(S)] for f in range(F)]
+    with CloudMerger(max_sensors=S, max_points_per_sensor=n, max_point_step=16, max_batch_points=F * S * n,
+                     max_batch_frames=F) as cm:
+        for s in range(S):
+            cm.set_extrinsic(s, mats[s])
+        cm.set_crop(c["passes"])
+        cm.set_voxel(c["leaf"], c["min_points"], True)
+        for s in range(S):
+            cm.submit_cloud(s, frames[0][s][0], n, make_layout(), stamp=s)
+        r = cm.merge_frame(capacity=S * n)
+        segs, per_frame = _upload_segments(cm, frames, lambda f, s: LAYOUTS["packed16"])
+        cm.run_batch(segs)
+        out = cm.fetch_batch_outputs()
+    o = _oracle_frames(oracle, per_frame, c["passes"], [c["leaf"]] * 3, c["min_points"])
+    assert (r.survivor_src == o[0]["survivor_src"]).all() and len(r.voxel_idx) == o[0]["n_voxels"] > 10000
+    assert_bit_equal(r.survivor_xyzi, o[0]["survivor_xyzi"], "host path survivors")
+    assert (r.voxel_idx.astype(np.int64) == o[0]["idx"]).all() and (r.voxel_count == o[0]["count"]).all()
+    assert_bit_equal(r.voxel_xyzi, o[0]["centroid"], "host path centroids")
+    assert out["stats"].frames == F and out["stats"].points_in == F * S * n and out["key_bytes"] == 4
+    _check_survivors(out, out["frames"], o)
+    assert _check_voxels(out, out["frames"], o) <= 1e-5
+
+
+@pytest.mark.parametrize("leaf,min_points", [(0.05, 1), (1.0, 2)])
+def test_cfg5_leaf_sweep_at_16mi_points(gpu_ok, oracle, leaf, min_points):
+    """BASELINE config 5 at its full 16 Mi points: the fine end (0.05 m: 8e9 cells, 64-bit keys, beyond PCL's INT32 limit,
+    nearly every point alone in its voxel) and the coarse end (1.0 m: 400 k voxels of ~42 points)."""
+    n = 1 << 24
+    x = synth.uniform_cloud(5000, n)
+    with CloudMerger(max_batch_points=n) as cm:
+        out = _voxel_only(cm, x, leaf, min_points)
+    o = oracle.voxelgrid(x, [leaf] * 3, min_points, True, force64=True)
+    o.update(n_voxels=o["n"], n_survivors=n)
+    assert out["stats"].pcl_overflow == int(o["pcl_overflow"])
+    assert out["key_bytes"] == (4 if out["stats"].key_bits <= 32 else 8)
+    assert _check_voxels(out, out["frames"], [o]) <= 1e-5
+
+
+def test_submit_policy_and_unmasked_submissions(gpu_ok, oracle):
+    """Latest-wins (my_cloud_fusion's add_*_velodyne) against first-wins (pcl_preprocessing's flag gate,
+    pc_preprocessing_main.cpp:330); a cloud submitted for a sensor outside the merge mask ends with that merge instead of
+    resurfacing frames_in_flight frames later; a single re-submission after a coalesced multi-submit replaces only its sensor."""
+    from cloud_merger_b200 import host_alloc
+    S, n = 3, 6000
+    mats = [synth.extrinsic(s, S) for s in range(S)]
+    a = [synth.lidar_cloud(91, s, 0, 8, n // 8) for s in range(S)]
+    b = [synth.lidar_cloud(91, s, 1, 8, n // 8) for s in range(S)]
+
+    def expect(clouds, sensors):
+        return oracle.merge_frame([cloud_dict(clouds[s], mats[s][:3]) for s in sensors], synth.ROI_BOX, [0.2] * 3, 1, True, True)
+
+    def same(r, o):
+        assert (r.survivor_src == o["survivor_src"]).all()
+        assert_bit_equal(r.survivor_xyzi, o["survivor_xyzi"], "survivors")
+        assert (r.voxel_idx.astype(np.int64) == o["idx"]).all() and (r.voxel_count == o["count"]).all()
+        assert_bit_equal(r.voxel_xyzi, o["centroid"], "centroids")
+
+    for first_wins in (False, True):
+        with CloudMerger(max_sensors=S, max_points_per_sensor=n, frames_in_flight=2) as cm:
+            for s in range(S):
+                cm.set_extrinsic(s, mats[s])
+            cm.set_crop(synth.ROI_BOX)
+            cm.set_voxel(0.2, 1, True)
+            cm.set_submit_policy(first_wins)
+            for s in range(S):
+                cm.submit_cloud(s, a[s], n, make_layout(), stamp=1)
+            cm.submit_cloud(1, b[1], n, make_layout(), stamp=2)      # sensor 1 delivers again before the merge
+            r = cm.merge_frame(capacity=S * n)
+            mixed = [a[0], a[1] if first_wins else b[1], a[2]]
+            same(r, expect(mixed, range(S)))
+            assert r.stamp == (1 if first_wins else 2)
+            # sensor 2 submitted but masked out: merged frame has sensors 0, 1 only; the cloud of sensor 2 is gone afterwards
+            for s in range(S):
+                cm.submit_cloud(s, b[s], n, make_layout(), stamp=3)
+            r = cm.merge_frame(capacity=S * n, sensor_mask=0b011)
+            assert r.used_mask == 0b011
+            same(r, expect(b, (0, 1)))
+            for _ in range(2):   # both slots come round: nothing stale may surface
+                cm.submit_cloud(0, a[0], n, make_layout(), stamp=4)
+                r = cm.merge_frame(capacity=S * n)
+                assert r.used_mask == 0b001
+                same(r, expect(a, (0,)))
+    # coalesced multi-submit (one PCIe copy into the frame arena), then sensor 1 alone again: only sensor 1 changes
+    arena, addr = host_alloc(S * n * 16)
+    for s in range(S):
+        arena[s * n * 16:(s + 1) * n * 16] = a[s].view(np.uint8).reshape(-1)
+    with CloudMerger(max_sensors=S, max_points_per_sensor=n, frames_in_flight=2) as cm:
+        for s in range(S):
+            cm.set_extrinsic(s, mats[s])
+        cm.set_crop(synth.ROI_BOX)
+        cm.set_voxel(0.2, 1, True)
+        for rep in range(3):
+            cm.submit_clouds_pinned(list(range(S)), [addr + s * n * 16 for s in range(S)], [n] * S, [make_layout()] * S)
+            if rep:
+                cm.submit_cloud(1, b[1][:n - 7 * rep], n - 7 * rep, make_layout())
+            r = cm.merge_frame(capacity=S * n)
+            same(r, expect([a[0], b[1][:n - 7 * rep] if rep else a[1], a[2]], range(S)))
+
+
+def test_concurrent_handles_sorting_on_one_device(gpu_ok, oracle):
+    """Six handles run their radix passes at the same time on six streams of one GPU (the node's per-sensor lanes): the
+    scanner role of a pass goes to the first CTAs to ARRIVE, so co-scheduled passes neither starve their scanners nor trip
+    the (wall-clock) watchdog. Every run must reproduce the handle's own serial result, and one of them the oracle's."""
+    import threading
+    H, n, rounds = 6, 1500000, 6
+    clouds = [synth.uniform_cloud(300 + k, n, extent=(150.0 + 10 * k, 150.0, 8.0)) for k in range(H)]
+    leaf = 0.25
+    handles = [CloudMerger(max_batch_points=n) for _ in range(H)]
+    try:
+        bufs, streams, want = [], [], []
+        for k, cm in enumerate(handles):
+            cm.set_voxel(leaf, 1, True)
+            bufs.append(cm.upload(clouds[k]))
+            streams.append(cm.stream_create())
+            cm.dev_voxelgrid(bufs[k].ptr, n, stream=streams[k])
+            o = cm.fetch_batch_outputs(want_sorted=False)
+            want.append((o["voxel_idx"].copy(), o["voxel_count"].copy(), o["voxel_xyzi"].copy()))
+        oref = oracle.voxelgrid(clouds[0], [leaf] * 3, 1, True, force64=True)
+        assert (want[0][0].astype(np.int64) == oref["idx"]).all() and (want[0][1] == oref["count"]).all()
+        assert_bit_equal(want[0][2], oref["centroid"], "serial run vs oracle")
+        errs = []
+
+        def lane(k):
+            try:
+                cm = handles[k]
+                for _ in range(rounds):
+                    cm.dev_voxelgrid(bufs[k].ptr, n, stream=streams[k])
+                    st = cm.stats()
+                    assert st.device_error == 0
+                o = cm.fetch_batch_outputs(want_sorted=False)
+                assert (o["voxel_idx"] == want[k][0]).all() and (o["voxel_count"] == want[k][1]).all()
+                assert_bit_equal(o["voxel_xyzi"], want[k][2], "handle %d" % k)
+            except Exception as e:  # noqa: BLE001
+                errs.append((k, e))
+        th = [threading.Thread(target=lane, args=(k,)) for k in range(H)]
+        for t in th:
+            t.start()
+        for t in th:
+            t.join()
+        assert not errs, errs
+    finally:
+        for cm in handles:
+            cm.close()
