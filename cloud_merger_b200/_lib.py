@@ -52,6 +52,18 @@ class CmLayout(C.Structure):
                 ("off_intensity", C.c_int32), ("is_dense", C.c_int32)]
 
 
+class CmPc2Field(C.Structure):
+    _fields_ = [("name", C.c_char_p), ("offset", C.c_uint32), ("datatype", C.c_uint8), ("count", C.c_uint32)]
+
+
+class CmPc2Desc(C.Structure):
+    _fields_ = [("height", C.c_uint32), ("width", C.c_uint32), ("point_step", C.c_uint32), ("row_step", C.c_uint32),
+                ("is_bigendian", C.c_int32), ("is_dense", C.c_int32), ("n_fields", C.c_int32), ("fields", CmPc2Field * 4)]
+
+
+CM_PC2_FLOAT32 = 7
+
+
 class CmSegment(C.Structure):
     _fields_ = [("data", C.c_void_p), ("n_points", C.c_int64), ("layout", CmLayout), ("sensor", C.c_int32),
                 ("frame", C.c_int32)]
@@ -100,6 +112,8 @@ SYMBOLS = {
     "cm_last_error": (C.c_char_p, [_H]),
     "cm_version": (C.c_char_p, []),
     "cm_device_count": (C.c_int, []),
+    "cm_layout_from_pointcloud2": (C.c_int, [C.POINTER(CmPc2Field), C.c_int, C.c_uint32, C.c_int, C.c_int, C.POINTER(CmLayout)]),
+    "cm_pointcloud2_describe": (C.c_int, [C.c_int, C.c_int64, C.POINTER(CmPc2Desc)]),
     "cm_set_extrinsic": (C.c_int, [_H, C.c_int, C.POINTER(C.c_float), C.c_int]),
     "cm_set_extrinsic_tf": (C.c_int, [_H, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
     "cm_get_extrinsic": (C.c_int, [_H, C.c_int, C.POINTER(C.c_float)]),

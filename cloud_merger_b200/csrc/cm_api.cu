@@ -908,6 +908,53 @@ const char* cm_strerror(int code) {
 
 const char* cm_last_error(cm_handle_t h) { return h ? h->last_error.c_str() : "null handle"; }
 
+// ---- sensor_msgs/PointCloud2 adapters (pure host code) -------------------------------------------------------------------
+int cm_layout_from_pointcloud2(const cm_pc2_field_t* fields, int n_fields, uint32_t point_step, int is_bigendian, int is_dense,
+                               cm_layout_t* out) {
+  if (!out || n_fields < 0 || (n_fields > 0 && !fields)) return CM_E_INVALID;
+  if (is_bigendian) return CM_E_INVALID;  // the kernels read little-endian FLOAT32 (every ROS 1 driver on x86 / ARM emits that)
+  if (point_step < 12 || point_step > 65535) return CM_E_INVALID;
+  int32_t off[4] = {-1, -1, -1, -1};
+  static const char* const kNames[4] = {"x", "y", "z", "intensity"};
+  for (int f = 0; f < n_fields; ++f) {
+    if (!fields[f].name) continue;
+    for (int k = 0; k < 4; ++k) {
+      if (strcmp(fields[f].name, kNames[k]) != 0 || off[k] >= 0) continue;
+      // pcl::FieldMatches: same name, same datatype, same count (a count of 0 is read as 1)
+      const bool match = fields[f].datatype == CM_PC2_FLOAT32 && (fields[f].count == 1 || fields[f].count == 0) &&
+                         (uint64_t)fields[f].offset + 4u <= (uint64_t)point_step;
+      if (match) off[k] = (int32_t)fields[f].offset;
+      else if (k < 3) return CM_E_INVALID;  // PCL would leave the coordinate unset: refuse instead
+    }
+  }
+  if (off[0] < 0 || off[1] < 0 || off[2] < 0) return CM_E_INVALID;
+  out->point_step = (int32_t)point_step;
+  out->off_x = off[0]; out->off_y = off[1]; out->off_z = off[2];
+  out->off_intensity = off[3] >= 0 ? off[3] : CM_NO_FIELD;
+  out->is_dense = is_dense ? 1 : 0;
+  return CM_OK;
+}
+
+int cm_pointcloud2_describe(int out_point_step, int64_t n_points, cm_pc2_desc_t* out) {
+  if (!out || (out_point_step != 16 && out_point_step != 32) || n_points < 0 || n_points > 0xFFFFFFFFll / out_point_step)
+    return CM_E_INVALID;
+  memset(out, 0, sizeof(*out));
+  out->height = 1;                       // pcl::PassThrough / VoxelGrid / operator+= all leave height = 1, width = size
+  out->width = (uint32_t)n_points;
+  out->point_step = (uint32_t)out_point_step;
+  out->row_step = (uint32_t)out_point_step * out->width;
+  out->is_bigendian = 0;
+  out->is_dense = 1;
+  out->n_fields = 4;
+  static const char* const kNames[4] = {"x", "y", "z", "intensity"};
+  const uint32_t offs[4] = {0u, 4u, 8u, out_point_step == 32 ? 16u : 12u};  // pcl::PointXYZI: intensity behind the padded xyz1
+  for (int k = 0; k < 4; ++k) {
+    out->fields[k].name = kNames[k]; out->fields[k].offset = offs[k]; out->fields[k].datatype = CM_PC2_FLOAT32;
+    out->fields[k].count = 1;
+  }
+  return CM_OK;
+}
+
 int cm_device_count(void) {
   int n = 0;
   if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;

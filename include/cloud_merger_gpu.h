@@ -121,6 +121,40 @@ typedef struct {
   int32_t is_dense;      /* PointCloud2.is_dense: 0 = non-finite points may be present and are left untransformed */
 } cm_layout_t;
 
+/* ---- sensor_msgs/PointCloud2 wire adapters (host-only helpers: no device is touched) ----
+ * cm_layout_from_pointcloud2 replaces the field lookup of the pcl_ros subscriber (pc_preprocessing_main.cpp:520-525,
+ * CloudFusionNode.h:51-56; pcl::createMapping / pcl::fromROSMsg match a field by NAME, DATATYPE and COUNT): given the
+ * message's fields[] {name, offset, datatype, count}, point_step, is_bigendian and is_dense it fills the cm_layout_t that
+ * cm_submit_cloud needs, so the message's data[] can be handed over as it arrived. "x", "y", "z" must be FLOAT32 (count 1)
+ * -> CM_E_INVALID otherwise; an "intensity" field that is missing or not FLOAT32 is treated the way PCL treats an unmatched
+ * field (not read; the value is 0) -> off_intensity = CM_NO_FIELD. Big-endian messages are refused (CM_E_INVALID).
+ * cm_pointcloud2_describe is the other direction, what pcl::toROSMsg(pcl::PointCloud<pcl::PointXYZI>) would put in the
+ * header of the published message (pc_preprocessing_main.cpp:199-220) for n_points records of out_point_step bytes as the
+ * kernels write them: height 1, width n, point_step, row_step, little-endian, dense, fields x y z intensity FLOAT32. */
+#define CM_PC2_INT8 1
+#define CM_PC2_UINT8 2
+#define CM_PC2_INT16 3
+#define CM_PC2_UINT16 4
+#define CM_PC2_INT32 5
+#define CM_PC2_UINT32 6
+#define CM_PC2_FLOAT32 7
+#define CM_PC2_FLOAT64 8
+typedef struct {
+  const char* name;   /* sensor_msgs/PointField.name */
+  uint32_t offset;
+  uint8_t datatype;   /* CM_PC2_* == sensor_msgs/PointField constants */
+  uint32_t count;
+} cm_pc2_field_t;
+typedef struct {
+  uint32_t height, width, point_step, row_step;
+  int32_t is_bigendian, is_dense;
+  int32_t n_fields;
+  cm_pc2_field_t fields[4];  /* names point to static strings */
+} cm_pc2_desc_t;
+CM_API int cm_layout_from_pointcloud2(const cm_pc2_field_t* fields, int n_fields, uint32_t point_step, int is_bigendian,
+                                      int is_dense, cm_layout_t* out);
+CM_API int cm_pointcloud2_describe(int out_point_step, int64_t n_points, cm_pc2_desc_t* out);
+
 /* ---- one segment of a device-resident batch: one sensor cloud of one frame ---- */
 typedef struct {
   const void* data;   /* DEVICE pointer, 16-byte aligned */

@@ -24,9 +24,11 @@
 #ifndef CLOUD_MERGER_SHIM_HPP_
 #define CLOUD_MERGER_SHIM_HPP_
 
+#include <atomic>
 #include <cstdint>
 #include <cstring>
 #include <memory>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -37,6 +39,23 @@
 #include <pcl/point_cloud.h>
 #include <pcl/point_types.h>
 #define CM_SHIM_HAVE_PCL 1
+#endif
+#endif
+
+// Optional adapters for the types either side of the path; each block compiles only where its header exists (ROS Melodic
+// has all of them; the build image has none, so tests/cpp/mock/ carries minimal stand-ins with the same member names).
+#if defined(__has_include)
+#if __has_include(<sensor_msgs/PointCloud2.h>) && !defined(CM_SHIM_NO_ROS)
+#include <sensor_msgs/PointCloud2.h>
+#define CM_SHIM_HAVE_ROS_MSG 1
+#endif
+#if __has_include(<Eigen/Core>) && !defined(CM_SHIM_NO_EIGEN)
+#include <Eigen/Core>
+#define CM_SHIM_HAVE_EIGEN 1
+#endif
+#if __has_include(<tf/transform_datatypes.h>) && !defined(CM_SHIM_NO_ROS)
+#include <tf/transform_datatypes.h>
+#define CM_SHIM_HAVE_TF 1
 #endif
 #endif
 
@@ -99,6 +118,34 @@ struct Params {
   float distance_threshold = 0.3f;
   float prob = 0.99f;
   int sum_order = CM_SUM4_SSE2;
+  // per-sensor zone tables (Parameter.h:45-81): zone lengths along x and the ground window |z| <= z_max_ground of each zone
+  float vf_front_length = 30.0f, vf_mid_length = 15.0f, vf_mid_length2 = 11.0f, vf_veh_length = 8.0f, vf_rear_length = 11.0f;
+  float vf_z_max_ground_front = 2.5f, vf_z_max_ground_mid2 = 2.0f, vf_z_max_ground_mid = 1.5f, vf_z_max_ground_veh = 0.3f,
+        vf_z_max_ground_rear = 0.5f;
+  float vr_front_length = 30.0f, vr_mid_length = 26.0f, vr_veh_length = 8.0f, vr_rear_length = 11.0f;
+  float vr_z_max_ground_front = 2.0f, vr_z_max_ground_mid = 1.5f, vr_z_max_ground_veh = 0.3f, vr_z_max_ground_rear = 0.5f;
+  float vt_front_length = 40.0f, vt_deviation_start_point = 20.0f, vt_z_max_ground_front = 1.0f;
+  float l_front_length = 26.0f, l_mid_length = 10.0f, l_mid2_length = 10.0f, l_rear_length = 10.0f, l_deviation_mid_point = 4.0f;
+  float l_z_max_ground_front = 1.5f, l_z_max_ground_mid2 = 1.2f, l_z_max_ground_mid = 0.8f, l_z_max_ground_rear = 0.5f;
+};
+
+// my_cloud_fusion/src/Parameter.h:15-110 -- that package's constants are `double` (narrowed to float where PCL takes them)
+struct FusionParams {
+  double radius = 0.1, min_neighbor = 1;
+  double x_transverse = 20.0, y_transverse = 25.0, x_longitudinal = 30.0, y_longitudinal = 10.0, z_min = -0.5, z_max = 3.0;
+  double lane_width = 10.0;
+  int points_per_voxel = 2;
+  double voxel_size = 0.1;
+  // zone lengths and ground windows per sensor group: [0] front Velodynes, [1] rear Velodynes, [2] top Velodyne, [3] Livox
+  // (Parameter.h:37-105; proceed_pointcloud picks the group by cloud index, CloudFusionNode.h:346-413)
+  struct Group {
+    double front_length, mid_length, rear_length;
+    double z_min_ground_front, z_max_ground_front, z_min_ground_mid, z_max_ground_mid, z_min_ground_rear, z_max_ground_rear;
+  };
+  Group group[4] = {{15.0, 10.0, 10.0, -0.5, 0.5, -0.2, 0.2, -0.5, 0.5},
+                    {10.0, 10.0, 15.0, -0.5, 0.5, -0.2, 0.2, -0.5, 0.5},
+                    {40.0, 40.0, 0.0, -1.5, 1.5, -0.5, 0.5, -0.5, 0.5},
+                    {10.0, 20.0, 0.0, -0.5, 0.5, -0.5, 0.5, -0.5, 0.5}};
 };
 
 inline cm_layout_t pcl_layout(bool is_dense) {
@@ -376,6 +423,56 @@ inline void matrix_from_transform(const Transform& t, float* m16) {
   std::memcpy(m16, m, sizeof(m));
 }
 
+// ---- adapters for the types either side of the path -----------------------------------------------------------------------
+#ifdef CM_SHIM_HAVE_EIGEN
+// Eigen::Matrix4f is column-major (Matrix4f::data() order): the extrinsic goes in as it is stored.
+inline int setExtrinsic(cm_handle_t h, int sensor, const Eigen::Matrix4f& m) { return cm_set_extrinsic(h, sensor, m.data(), 1); }
+#endif
+#ifdef CM_SHIM_HAVE_TF
+// tf::Transform(stf.getRotation(), stf.getOrigin()) as the callbacks build it (pc_preprocessing_main.cpp:320)
+inline Transform fromTf(const tf::Transform& t) {
+  Transform r;
+  const tf::Quaternion q = t.getRotation();
+  r.q[0] = q.x(); r.q[1] = q.y(); r.q[2] = q.z(); r.q[3] = q.w();
+  r.origin[0] = t.getOrigin().x(); r.origin[1] = t.getOrigin().y(); r.origin[2] = t.getOrigin().z();
+  return r;
+}
+#endif
+#ifdef CM_SHIM_HAVE_ROS_MSG
+// sensor_msgs::PointCloud2 -> cm_layout_t: the field lookup the pcl_ros subscriber does (pc_preprocessing_main.cpp:520-525);
+// msg.data can then be handed to cm_submit_cloud as it arrived (no deserialisation into pcl::PointXYZI, no by-value copy).
+inline int layoutFromMsg(const sensor_msgs::PointCloud2& msg, cm_layout_t* out) {
+  std::vector<cm_pc2_field_t> f(msg.fields.size());
+  for (size_t i = 0; i < msg.fields.size(); ++i) {
+    f[i].name = msg.fields[i].name.c_str(); f[i].offset = msg.fields[i].offset;
+    f[i].datatype = msg.fields[i].datatype; f[i].count = msg.fields[i].count;
+  }
+  return cm_layout_from_pointcloud2(f.data(), static_cast<int>(f.size()), msg.point_step, msg.is_bigendian ? 1 : 0,
+                                    msg.is_dense ? 1 : 0, out);
+}
+// What pcl::toROSMsg(cloud, msg) does for a cloud of `n` records as the kernels write them (pc_preprocessing_main.cpp:199-220):
+// header fields + one memcpy of the records. out_point_step 32 = pcl::PointXYZI records, 16 = packed xyzi.
+inline bool fillMsg(sensor_msgs::PointCloud2& msg, const void* records, int64_t n, int out_point_step = 32) {
+  cm_pc2_desc_t d;
+  if (cm_pointcloud2_describe(out_point_step, n, &d) != CM_OK) return false;
+  msg.height = d.height; msg.width = d.width; msg.point_step = d.point_step; msg.row_step = d.row_step;
+  msg.is_bigendian = d.is_bigendian != 0; msg.is_dense = d.is_dense != 0;
+  msg.fields.resize(static_cast<size_t>(d.n_fields));
+  for (int k = 0; k < d.n_fields; ++k) {
+    msg.fields[static_cast<size_t>(k)].name = d.fields[k].name; msg.fields[static_cast<size_t>(k)].offset = d.fields[k].offset;
+    msg.fields[static_cast<size_t>(k)].datatype = d.fields[k].datatype; msg.fields[static_cast<size_t>(k)].count = d.fields[k].count;
+  }
+  msg.data.resize(static_cast<size_t>(d.row_step));
+  if (d.row_step) std::memcpy(msg.data.data(), records, d.row_step);
+  return true;
+}
+inline bool toROSMsg(const Cloud& cloud, sensor_msgs::PointCloud2& msg) {
+  if (!fillMsg(msg, cloud.points.data(), static_cast<int64_t>(cloud.points.size()), 32)) return false;
+  msg.is_dense = cloud.is_dense;
+  return true;
+}
+#endif
+
 // ---- the reference's functions, same names and argument meaning -------------------------------------------------------
 
 // pcl_ros::transformPointCloud(input, *cloud_ptr, transform) -- pc_preprocessing_main.cpp:322
@@ -491,6 +588,146 @@ inline void proceedZones(Context& ctx, const Cloud::Ptr& cloud_ROI_ptr, const st
   *ground_ptr = ground_all;
 }
 
+// ---- the zone tables of the four sensor groups (pc_preprocessing_main.cpp:228-312, :428-446, :474-497; Parameter.h:45-81) ----
+// Deviations are the reference's own float expressions, summed left to right. `plain` parts are x windows that go to the
+// no-ground cloud without ground removal (callbackTopMiddle's near range, :444-446).
+struct ProceedTable {
+  std::vector<ZonePart> parts;
+  std::vector<ZonePart> plain;  // length, deviation; z_max_ground unused
+};
+inline ProceedTable frontTable(const Params& p) {  // proceedFront, both front Velodynes (and, in the built node, both rear ones: :378, :404)
+  ProceedTable t;
+  t.parts = {{p.vf_front_length, -p.roi_mid + p.vf_rear_length + p.vf_veh_length + p.vf_mid_length + p.vf_mid_length2, p.vf_z_max_ground_front},
+             {p.vf_mid_length2, -p.roi_mid + p.vf_rear_length + p.vf_veh_length + p.vf_mid_length, p.vf_z_max_ground_mid2},
+             {p.vf_mid_length, -p.roi_mid + p.vf_rear_length + p.vf_veh_length, p.vf_z_max_ground_mid},
+             {p.vf_veh_length, -p.roi_mid + p.vf_rear_length, p.vf_z_max_ground_veh},
+             {p.vf_rear_length, -p.roi_mid, p.vf_z_max_ground_rear}};
+  return t;
+}
+inline ProceedTable rearTable(const Params& p) {  // proceedRear (:277-312; defined in the reference, never called)
+  ProceedTable t;
+  t.parts = {{p.vr_front_length, -p.roi_mid + p.vr_rear_length + p.vr_veh_length + p.vr_mid_length, p.vr_z_max_ground_front},
+             {p.vr_mid_length, -p.roi_mid + p.vr_rear_length + p.vr_veh_length, p.vr_z_max_ground_mid},
+             {p.vr_veh_length, -p.roi_mid + p.vr_rear_length, p.vr_z_max_ground_veh},
+             {p.vr_rear_length, -p.roi_mid, p.vr_z_max_ground_rear}};
+  return t;
+}
+inline ProceedTable topTable(const Params& p) {  // callbackTopMiddle (:428-446)
+  ProceedTable t;
+  t.parts = {{p.vt_front_length, p.vt_deviation_start_point, p.vt_z_max_ground_front}};
+  t.plain = {{p.roi_mid + p.vt_deviation_start_point, -p.roi_mid, 0.0f}};
+  return t;
+}
+inline ProceedTable livoxTable(const Params& p) {  // callbackFrontMiddle (:474-497)
+  ProceedTable t;
+  t.parts = {{p.l_front_length, p.l_deviation_mid_point + p.l_rear_length + p.l_mid_length + p.l_mid2_length, p.l_z_max_ground_front},
+             {p.l_mid2_length, p.l_deviation_mid_point + p.l_rear_length + p.l_mid_length, p.l_z_max_ground_mid2},
+             {p.l_mid_length, p.l_deviation_mid_point + p.l_rear_length, p.l_z_max_ground_mid},
+             {p.l_rear_length, p.l_deviation_mid_point, p.l_z_max_ground_rear}};
+  return t;
+}
+// void proceedFront(const Cloud::Ptr cloud_ptr, Cloud::Ptr no_ground_ptr, Cloud::Ptr ground_ptr) -- :228-269 -- and its
+// siblings: getROI, then the table's zones, then the plain parts appended to the no-ground cloud.
+inline void proceedTable(Context& ctx, const Cloud::Ptr& cloud_ptr, const ProceedTable& table, const Cloud::Ptr& no_ground_ptr,
+                         const Cloud::Ptr& ground_ptr) {
+  Cloud::Ptr cloud_ROI_ptr(new Cloud);
+  getROI(ctx, cloud_ptr, cloud_ROI_ptr);
+  proceedZones(ctx, cloud_ROI_ptr, table.parts, no_ground_ptr, ground_ptr);
+  for (const ZonePart& pl : table.plain) {
+    Cloud::Ptr part(new Cloud);
+    getCloudPart(ctx, cloud_ROI_ptr, part, pl.length, pl.deviation);
+    *no_ground_ptr += *part;
+  }
+}
+inline void proceedFront(Context& ctx, const Cloud::Ptr& c, const Cloud::Ptr& ng, const Cloud::Ptr& g) { proceedTable(ctx, c, frontTable(ctx.params()), ng, g); }
+inline void proceedRear(Context& ctx, const Cloud::Ptr& c, const Cloud::Ptr& ng, const Cloud::Ptr& g) { proceedTable(ctx, c, rearTable(ctx.params()), ng, g); }
+inline void proceedTop(Context& ctx, const Cloud::Ptr& c, const Cloud::Ptr& ng, const Cloud::Ptr& g) { proceedTable(ctx, c, topTable(ctx.params()), ng, g); }
+inline void proceedLivox(Context& ctx, const Cloud::Ptr& c, const Cloud::Ptr& ng, const Cloud::Ptr& g) { proceedTable(ctx, c, livoxTable(ctx.params()), ng, g); }
+
+// ---- my_cloud_fusion's variant of the same path (CloudFusionNode.h) -----------------------------------------------------------
+// Its constants are double; every limit is narrowed to float where pcl::PassThrough::setFilterLimits(const float&, const
+// float&) takes it, after the double arithmetic the reference writes (e.g. `mid_length/2 + front_length`).
+inline cm_pass_t fpass(int axis, double lo, double hi) { return cm_pass_t{axis, static_cast<float>(lo), static_cast<float>(hi), 0}; }
+
+// void filter_ROI_R(cloud, front, mid, rear, front_length, mid_length, rear_length) -- CloudFusionNode.h:145-190: z window,
+// lane window in y, then three x ranges. The rear range is the reference's own [-(mid/2) - rear, rear] (its upper limit is
+// `rear_length`, not `-mid_length/2`): reproduced as written.
+inline void filter_ROI_R(Context& ctx, const FusionParams& fp, const Cloud::Ptr& cloud_ptr, const Cloud::Ptr& front_cloud_ptr,
+                         const Cloud::Ptr& mid_cloud_ptr, const Cloud::Ptr& rear_cloud_ptr, const double front_length,
+                         const double mid_length, const double rear_length) {
+  const cm_pass_t z = fpass(2, fp.z_min, fp.z_max), y = fpass(1, -fp.lane_width / 2, fp.lane_width / 2);
+  std::vector<cm_zone_t> zones(3);
+  const cm_pass_t xr[3] = {fpass(0, mid_length / 2, (mid_length / 2) + front_length), fpass(0, -mid_length / 2, mid_length / 2),
+                           fpass(0, -(mid_length / 2) - rear_length, rear_length)};
+  for (int k = 0; k < 3; ++k) { zones[k].n_pass = 3; zones[k].pass[0] = z; zones[k].pass[1] = y; zones[k].pass[2] = xr[k]; }
+  std::vector<Cloud> out;
+  ctx.zone_split(*cloud_ptr, zones, out);
+  *front_cloud_ptr = out[0]; *mid_cloud_ptr = out[1]; *rear_cloud_ptr = out[2];
+}
+// void filter_ROI_T(cloud, filtered) -- CloudFusionNode.h:87-143: the T shape = longitudinal bar += transverse bar
+inline void filter_ROI_T(Context& ctx, const FusionParams& fp, const Cloud::Ptr& cloud_ptr, const Cloud::Ptr& filtered_cloud_ptr) {
+  std::vector<cm_zone_t> zones(2);
+  zones[0].n_pass = 3;
+  zones[0].pass[0] = fpass(0, -fp.x_longitudinal / 2, fp.x_longitudinal / 2);
+  zones[0].pass[1] = fpass(1, -fp.y_longitudinal / 2, fp.y_longitudinal / 2);
+  zones[0].pass[2] = fpass(2, fp.z_min, fp.z_max);
+  zones[1].n_pass = 3;
+  zones[1].pass[0] = fpass(0, fp.x_longitudinal / 2, (fp.x_longitudinal / 2) + fp.x_transverse);
+  zones[1].pass[1] = fpass(1, -fp.y_transverse / 2, fp.y_transverse / 2);
+  zones[1].pass[2] = fpass(2, fp.z_min, fp.z_max);
+  std::vector<Cloud> out;
+  ctx.zone_split(*cloud_ptr, zones, out);
+  Cloud first_part = out[0];
+  first_part += out[1];
+  *filtered_cloud_ptr = first_part;
+}
+// void remove_ground(cloud, no_ground, ground, z_min_ground, z_max_ground, max_angle) -- CloudFusionNode.h:192-216: in this
+// package the RANSAC block is commented out (:219-271), so the function IS its two z windows.
+inline void remove_ground(Context& ctx, const FusionParams& fp, const Cloud::Ptr& cloud_ptr, const Cloud::Ptr& no_ground_cloud_ptr,
+                          const Cloud::Ptr& ground_cloud_ptr, const double z_min_ground, const double z_max_ground,
+                          const double /*max_angle*/) {
+  std::vector<cm_zone_t> zones(2);
+  zones[0].n_pass = 1; zones[0].pass[0] = fpass(2, z_min_ground, z_max_ground);
+  zones[1].n_pass = 1; zones[1].pass[0] = fpass(2, z_max_ground + 0.01, fp.z_max);
+  std::vector<Cloud> out;
+  ctx.zone_split(*cloud_ptr, zones, out);
+  *ground_cloud_ptr = out[0];
+  *no_ground_cloud_ptr = out[1];
+}
+// void remove_outliers(cloud) -- CloudFusionNode.h:74-85 (radius 0.1 m in this package)
+inline void remove_outliers(Context& ctx, const FusionParams& fp, const Cloud::Ptr& cloud_ptr) {
+  Cloud tmp;
+  ctx.radius_outlier(*cloud_ptr, tmp, fp.radius, static_cast<int>(fp.min_neighbor));
+  *cloud_ptr = tmp;
+}
+// proceed_pointcloud after the member-cloud copy (CloudFusionNode.h:327-493): filter_ROI_R, three remove_ground calls, the
+// ground / no-ground parts appended front, mid, rear. `group`: 0 front Velodynes, 1 rear, 2 top, 3 Livox (index 0-1, 2-3, 4, 5).
+// One zone-slicing pass: six chains of z, y, x-range, z-window.
+inline void proceed_pointcloud(Context& ctx, const FusionParams& fp, const Cloud::Ptr& cloud_ptr, const Cloud::Ptr& no_ground_cloud_ptr,
+                               const Cloud::Ptr& ground_cloud_ptr, int group) {
+  const FusionParams::Group& g = fp.group[group];
+  const cm_pass_t z = fpass(2, fp.z_min, fp.z_max), y = fpass(1, -fp.lane_width / 2, fp.lane_width / 2);
+  const cm_pass_t xr[3] = {fpass(0, g.mid_length / 2, (g.mid_length / 2) + g.front_length), fpass(0, -g.mid_length / 2, g.mid_length / 2),
+                           fpass(0, -(g.mid_length / 2) - g.rear_length, g.rear_length)};
+  const double zlo[3] = {g.z_min_ground_front, g.z_min_ground_mid, g.z_min_ground_rear};
+  const double zhi[3] = {g.z_max_ground_front, g.z_max_ground_mid, g.z_max_ground_rear};
+  std::vector<cm_zone_t> zones(6);
+  for (int k = 0; k < 3; ++k) {
+    for (int w = 0; w < 2; ++w) {
+      cm_zone_t& zn = zones[static_cast<size_t>(2 * k + w)];
+      zn.n_pass = 4; zn.pass[0] = z; zn.pass[1] = y; zn.pass[2] = xr[k];
+      zn.pass[3] = w == 0 ? fpass(2, zlo[k], zhi[k]) : fpass(2, zhi[k] + 0.01, fp.z_max);
+    }
+  }
+  std::vector<Cloud> out;
+  ctx.zone_split(*cloud_ptr, zones, out);
+  Cloud ground1 = out[0], noground1 = out[1];
+  ground1 += out[2]; ground1 += out[4];
+  noground1 += out[3]; noground1 += out[5];
+  *ground_cloud_ptr = ground1;
+  *no_ground_cloud_ptr = noground1;
+}
+
 // void voxelgrid(const Cloud::Ptr cloud_ptr, Cloud::Ptr voxel_cloud_ptr) -- :168-177
 inline void voxelgrid(Context& ctx, const Cloud::Ptr& cloud_ptr, const Cloud::Ptr& voxel_cloud_ptr) {
   Cloud tmp;
@@ -499,11 +736,17 @@ inline void voxelgrid(Context& ctx, const Cloud::Ptr& cloud_ptr, const Cloud::Pt
 }
 
 // ---- the fused per-frame flow: callbacks submit, the main loop merges ------------------------------------------------------
-// Replaces, together: callbackX (transform + getROI) -> globals + flags -> fusePointclouds -> voxelgrid
-// (pc_preprocessing_main.cpp:318-337, :131-177, main loop :574-578). One GPU pass per frame instead of ~20 CPU passes.
+// Replaces, together: callbackX (transform + ROI crop) -> member clouds / globals + flags -> concat -> voxelgrid, i.e. the
+// merge of my_cloud_fusion's cloud_fusion() (CloudFusionNode.h:59-72, 506-534) with a crop, and the transform / getROI /
+// fusePointclouds / voxelgrid skeleton of pcl_preprocessing (pc_preprocessing_main.cpp:318-337, :131-177, :574-578). It does
+// NOT run the per-zone ground removal and outlier removal that pcl_preprocessing's callbacks do between getROI and the
+// hand-off (proceedX): its voxel cloud is the VoxelGrid of the merged ROI cloud, not /points_voxel of that node. The whole
+// main-loop iteration of pcl_preprocessing is PreprocessingFrame below.
+// One GPU pass per frame instead of ~20 CPU passes.
 class FusedFrame {
  public:
-  FusedFrame(int n_sensors, int64_t max_points_per_sensor, uint64_t required_mask, int device = 0, Params p = Params())
+  FusedFrame(int n_sensors, int64_t max_points_per_sensor, uint64_t required_mask, int device = 0, Params p = Params(),
+             bool first_cloud_wins = true)
       : params_(p), n_sensors_(n_sensors), required_(required_mask), cap_(max_points_per_sensor * n_sensors) {
     cm_config_t cfg;
     std::memset(&cfg, 0, sizeof(cfg));
@@ -517,6 +760,8 @@ class FusedFrame {
       const float leaf[3] = {p.voxel_size, p.voxel_size, p.voxel_size};
       cm_set_voxel(h_, leaf, p.points_per_voxel, 1);
       cm_set_overflow_mode(h_, 1);  // behave like PCL when the leaf is too small
+      // pcl_preprocessing keeps the FIRST cloud of a sensor after a fusion (`if (!flag_x)`, :330); my_cloud_fusion the newest
+      cm_set_submit_policy(h_, first_cloud_wins ? CM_SUBMIT_FIRST_WINS : CM_SUBMIT_LATEST_WINS);
     }
   }
   ~FusedFrame() { if (h_) cm_destroy(h_); }
@@ -528,18 +773,50 @@ class FusedFrame {
   // once, after the TF lookup (pc_preprocessing_main.cpp:551-568)
   void setTransform(int sensor, const Transform& tf) { if (h_) cm_set_extrinsic_tf(h_, sensor, tf.q, tf.origin); }
 
-  // body of callbackFrontRight ... callbackFrontMiddle: hands the raw cloud over; thread-safe per sensor
+  // body of callbackFrontRight ... callbackFrontMiddle: hands the raw cloud over. Safe to call from the six
+  // ros::AsyncSpinner threads at once (pc_preprocessing_main.cpp:513) and concurrently with fuseAndVoxel: the hand-off
+  // (submit + flag) and the main loop's (check + merge + flag reset) exclude each other -- the reference's own globals and
+  // bool flags (pc_preprocessing_main.h:41-77) carry no such protection.
   void onCloud(int sensor, const Cloud& input) {
-    if (!h_) return;
     const cm_layout_t l = pcl_layout(input.is_dense);
-    if (cm_submit_cloud(h_, sensor, input.points.data(), static_cast<int64_t>(input.points.size()), &l, stamp_of(input)) == CM_OK)
-      seen_ |= 1ull << sensor;
+    onRecords(sensor, input.points.data(), static_cast<int64_t>(input.points.size()), l, stamp_of(input));
   }
+  // the same for raw records in any PointCloud2 layout (msg.data as it arrived)
+  void onRecords(int sensor, const void* data, int64_t n_points, const cm_layout_t& layout, uint64_t stamp) {
+    if (!h_ || sensor < 0 || sensor >= n_sensors_) return;
+    std::lock_guard<std::mutex> lk(gate_);
+    if (cm_submit_cloud(h_, sensor, data, n_points, &layout, stamp) == CM_OK)
+      seen_.fetch_or(1ull << sensor, std::memory_order_release);
+  }
+#ifdef CM_SHIM_HAVE_ROS_MSG
+  // subscriber callback on the wire type: no pcl::PointCloud deserialisation, no by-value cloud copy
+  bool onCloudMsg(int sensor, const sensor_msgs::PointCloud2& msg) {
+    cm_layout_t l;
+    if (layoutFromMsg(msg, &l) != CM_OK) return false;
+    const uint64_t stamp = static_cast<uint64_t>(msg.header.stamp.sec) * 1000000ull + msg.header.stamp.nsec / 1000u;  // pcl_conversions::toPCL
+    onRecords(sensor, msg.data.data(), static_cast<int64_t>(msg.width) * msg.height, l, stamp);
+    return true;
+  }
+#endif
+#ifdef CM_SHIM_HAVE_EIGEN
+  void setTransform(int sensor, const Eigen::Matrix4f& m) { if (h_) setExtrinsic(h_, sensor, m); }
+#endif
+  // every required sensor has delivered since the last fusion (lock-free; the reference's `if (flag_a && flag_b ...)`, :134)
+  bool ready() const { return (seen_.load(std::memory_order_acquire) & required_) == required_; }
 
   // fusePointclouds + voxelgrid. Returns false (like the reference's flag gate, :134) until every required sensor has
   // delivered; optional sensors are merged when present.
   bool fuseAndVoxel(Cloud& fused, Cloud& voxel) {
-    if (!h_ || (seen_ & required_) != required_) return false;
+    if (!h_) return false;
+    int64_t ticket = 0;
+    {
+      // check, enqueue and flag reset are one step with respect to the callbacks; the wait for the GPU happens outside
+      std::lock_guard<std::mutex> lk(gate_);
+      if (!ready()) return false;
+      const int rc = cm_merge_frame_async(h_, ~0ull, &ticket);
+      seen_.store(0, std::memory_order_release);  // every submission ends with the merge (consumed or discarded)
+      if (rc != CM_OK) { fused.points.clear(); voxel.points.clear(); return false; }
+    }
     fused.points.resize(static_cast<size_t>(cap_));
     voxel.points.resize(static_cast<size_t>(cap_));
     sx_.resize(static_cast<size_t>(cap_) * 4);
@@ -548,8 +825,7 @@ class FusedFrame {
     o.voxel_xyzi = voxel.points.data(); o.voxel_capacity = cap_;
     o.survivor_xyzi = sx_.data(); o.survivor_capacity = cap_;
     uint64_t used = 0, stamp = 0;
-    const int rc = cm_merge_frame(h_, ~0ull, &o, &used, &stamp);
-    seen_ = 0;
+    const int rc = cm_wait_frame(h_, ticket, &o, &used, &stamp);
     if (rc != CM_OK) { fused.points.clear(); voxel.points.clear(); return false; }
     fused.points.resize(static_cast<size_t>(o.n_survivors));
     for (int64_t i = 0; i < o.n_survivors; ++i) {
@@ -567,7 +843,9 @@ class FusedFrame {
  private:
   Params params_;
   int n_sensors_;
-  uint64_t required_, seen_ = 0;
+  uint64_t required_;
+  std::atomic<uint64_t> seen_{0};
+  std::mutex gate_;
   int64_t cap_;
   cm_handle_t h_ = nullptr;
   std::vector<float> sx_;

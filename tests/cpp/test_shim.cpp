@@ -90,6 +90,32 @@ static std::vector<float> oracle_passes(const std::vector<float>& in, const std:
   return cur;
 }
 
+// oracle: what a proceedX does after getROI (pc_preprocessing_main.cpp:228-312) -- per zone getCloudPart, the two z windows,
+// RANSAC plane on the lower one, outlierRemoval of its non-ground points, the upper window appended; zone after zone
+static void oracle_proceed(const std::vector<float>& roi_o, const std::vector<ZonePart>& parts, const Params& prm,
+                           std::vector<float>& want_g, std::vector<float>& want_ng) {
+  want_g.clear(); want_ng.clear();
+  for (size_t k = 0; k < parts.size(); ++k) {
+    const cmo_pass_t x = {0, parts[k].deviation, parts[k].deviation + parts[k].length, 0};
+    const std::vector<float> low = oracle_passes(roi_o, {x, {2, -parts[k].z_max_ground, parts[k].z_max_ground, 0}});
+    const std::vector<float> high = oracle_passes(roi_o, {x, {2, static_cast<float>(parts[k].z_max_ground + 0.01), prm.roi_z_max, 0}});
+    const int64_t n_low = static_cast<int64_t>(low.size() / 4);
+    std::vector<int32_t> inl(static_cast<size_t>(n_low) + 1);
+    const int64_t n_in = cmo_plane_ransac(low.data(), n_low, static_cast<double>(prm.distance_threshold), static_cast<double>(prm.prob),
+                                          prm.max_iterations, 1, 12345u, prm.sum_order, nullptr, nullptr, nullptr, inl.data());
+    std::vector<float> rest;
+    for (int64_t i = 0, j = 0; i < n_low; ++i) {
+      if (j < n_in && inl[static_cast<size_t>(j)] == i) { want_g.insert(want_g.end(), &low[i * 4], &low[i * 4] + 4); ++j; }
+      else rest.insert(rest.end(), &low[i * 4], &low[i * 4] + 4);
+    }
+    const int64_t n_rest = static_cast<int64_t>(rest.size() / 4);
+    std::vector<int32_t> keep(static_cast<size_t>(n_rest) + 1);
+    const int64_t kk = cmo_radius_outlier(rest.data(), n_rest, static_cast<double>(prm.radius), static_cast<int32_t>(prm.min_neighbor), 0, keep.data());
+    for (int64_t i = 0; i < kk; ++i) want_ng.insert(want_ng.end(), &rest[static_cast<size_t>(keep[i]) * 4], &rest[static_cast<size_t>(keep[i]) * 4] + 4);
+    want_ng.insert(want_ng.end(), high.begin(), high.end());
+  }
+}
+
 int main() {
   if (cm_device_count() == 0) {
     std::printf("no CUDA device: the shim has no CPU path (expected on the build box)\n");
@@ -165,25 +191,7 @@ int main() {
       Cloud::Ptr ng_all(new Cloud), g_all(new Cloud);
       proceedZones(ctx, roi_ptr, parts, ng_all, g_all);
       std::vector<float> want_g, want_ng;
-      for (size_t k = 0; k < parts.size(); ++k) {
-        const cmo_pass_t x = {0, parts[k].deviation, parts[k].deviation + parts[k].length, 0};
-        const std::vector<float> low = oracle_passes(roi_o, {x, {2, -parts[k].z_max_ground, parts[k].z_max_ground, 0}});
-        const std::vector<float> high = oracle_passes(roi_o, {x, {2, static_cast<float>(parts[k].z_max_ground + 0.01), prm.roi_z_max, 0}});
-        const int64_t n_low = static_cast<int64_t>(low.size() / 4);
-        std::vector<int32_t> inl(static_cast<size_t>(n_low) + 1);
-        const int64_t n_in = cmo_plane_ransac(low.data(), n_low, static_cast<double>(prm.distance_threshold), static_cast<double>(prm.prob),
-                                              prm.max_iterations, 1, 12345u, prm.sum_order, nullptr, nullptr, nullptr, inl.data());
-        std::vector<float> rest;
-        for (int64_t i = 0, j = 0; i < n_low; ++i) {
-          if (j < n_in && inl[static_cast<size_t>(j)] == i) { want_g.insert(want_g.end(), &low[i * 4], &low[i * 4] + 4); ++j; }
-          else rest.insert(rest.end(), &low[i * 4], &low[i * 4] + 4);
-        }
-        const int64_t n_rest = static_cast<int64_t>(rest.size() / 4);
-        std::vector<int32_t> keep(static_cast<size_t>(n_rest) + 1);
-        const int64_t kk = cmo_radius_outlier(rest.data(), n_rest, static_cast<double>(prm.radius), static_cast<int32_t>(prm.min_neighbor), 0, keep.data());
-        for (int64_t i = 0; i < kk; ++i) want_ng.insert(want_ng.end(), &rest[static_cast<size_t>(keep[i]) * 4], &rest[static_cast<size_t>(keep[i]) * 4] + 4);
-        want_ng.insert(want_ng.end(), high.begin(), high.end());
-      }
+      oracle_proceed(roi_o, parts, prm, want_g, want_ng);
       expect_cloud(*g_all, want_g, want_g.size() / 4, "proceedZones ground");
       expect_cloud(*ng_all, want_ng, want_ng.size() / 4, "proceedZones no_ground");
     }
@@ -235,6 +243,90 @@ int main() {
       expect_cloud(*ground, want_ground, static_cast<size_t>(n_in), "removeGround ground");
       expect_cloud(*no_ground, want_ng, want_ng.size() / 4, "removeGround no_ground");
       CHECK(info[0] == 1 && n_in > 50 && n_in < n_low, "removeGround found a plane (%lld of %lld inliers)", (long long)n_in, (long long)n_low);
+    }
+    // the four zone tables of the reference (proceedFront, proceedRear, callbackTopMiddle, callbackFrontMiddle; :228-312, :428-446,
+    // :474-497 with Parameter.h:45-81) on the TRANSFORMED cloud: getROI inside, zones, plain parts appended
+    {
+      const ProceedTable tables[4] = {frontTable(prm), rearTable(prm), topTable(prm), livoxTable(prm)};
+      const char* names[4] = {"proceedFront", "proceedRear", "proceedTop", "proceedLivox"};
+      CHECK(tables[0].parts.size() == 5 && tables[1].parts.size() == 4 && tables[2].parts.size() == 1 && tables[2].plain.size() == 1 &&
+            tables[3].parts.size() == 4, "zone tables");
+      // deviations as the reference writes them: -roi_mid + vr_rear + vr_veh + vr_mid = 30, vt: 20, plain part [-15, 20], livox front 34
+      CHECK(tables[1].parts[0].deviation == 30.0f && tables[1].parts[0].length == 30.0f && tables[2].parts[0].deviation == 20.0f &&
+            tables[2].plain[0].deviation == -15.0f && tables[2].plain[0].length == 35.0f && tables[3].parts[0].deviation == 34.0f,
+            "zone table values");
+      for (int t = 0; t < 4; ++t) {
+        if (s != (t % S)) continue;  // one table per sensor cloud keeps the test short
+        Cloud::Ptr ng(new Cloud), g(new Cloud);
+        proceedTable(ctx, cloud_ptr, tables[t], ng, g);
+        std::vector<float> want_g, want_ng;
+        oracle_proceed(roi_o, tables[t].parts, prm, want_g, want_ng);
+        for (const ZonePart& pl : tables[t].plain) {
+          const std::vector<float> part_plain = oracle_passes(roi_o, {{0, pl.deviation, pl.deviation + pl.length, 0}});
+          want_ng.insert(want_ng.end(), part_plain.begin(), part_plain.end());
+        }
+        expect_cloud(*g, want_g, want_g.size() / 4, names[t]);
+        expect_cloud(*ng, want_ng, want_ng.size() / 4, names[t]);
+        CHECK(want_ng.size() > 400, "%s: the table selects points (%zu)", names[t], want_ng.size() / 4);
+      }
+    }
+    // my_cloud_fusion's variant (CloudFusionNode.h:87-216, 327-493; my_cloud_fusion/src/Parameter.h): double constants
+    {
+      const FusionParams fp;
+      const FusionParams::Group& gr = fp.group[s % 4];
+      auto f = [](double v) { return static_cast<float>(v); };
+      const cmo_pass_t z = {2, f(fp.z_min), f(fp.z_max), 0}, y = {1, f(-fp.lane_width / 2), f(fp.lane_width / 2), 0};
+      const cmo_pass_t xr[3] = {{0, f(gr.mid_length / 2), f((gr.mid_length / 2) + gr.front_length), 0},
+                                {0, f(-gr.mid_length / 2), f(gr.mid_length / 2), 0},
+                                {0, f(-(gr.mid_length / 2) - gr.rear_length), f(gr.rear_length), 0}};
+      Cloud::Ptr fr(new Cloud), mi(new Cloud), re(new Cloud);
+      filter_ROI_R(ctx, fp, cloud_ptr, fr, mi, re, gr.front_length, gr.mid_length, gr.rear_length);
+      const Cloud::Ptr got3[3] = {fr, mi, re};
+      std::vector<float> zone_o[3];
+      for (int k = 0; k < 3; ++k) {
+        zone_o[k] = oracle_passes(tr, {z, y, xr[k]});
+        expect_cloud(*got3[k], zone_o[k], zone_o[k].size() / 4, "filter_ROI_R");
+      }
+      CHECK(zone_o[0].size() + zone_o[1].size() > 400, "filter_ROI_R selects points");
+      // remove_ground: the two z windows (RANSAC is commented out in this package)
+      Cloud::Ptr ng(new Cloud), g(new Cloud);
+      remove_ground(ctx, fp, mi, ng, g, gr.z_min_ground_mid, gr.z_max_ground_mid, 0.01);
+      const std::vector<float> g_o = oracle_passes(zone_o[1], {{2, f(gr.z_min_ground_mid), f(gr.z_max_ground_mid), 0}});
+      const std::vector<float> ng_o = oracle_passes(zone_o[1], {{2, f(gr.z_max_ground_mid + 0.01), f(fp.z_max), 0}});
+      expect_cloud(*g, g_o, g_o.size() / 4, "remove_ground ground");
+      expect_cloud(*ng, ng_o, ng_o.size() / 4, "remove_ground no_ground");
+      // proceed_pointcloud: all of it in one zone-slicing pass
+      Cloud::Ptr png(new Cloud), pg(new Cloud);
+      proceed_pointcloud(ctx, fp, cloud_ptr, png, pg, s % 4);
+      std::vector<float> want_g, want_ng;
+      const double zlo[3] = {gr.z_min_ground_front, gr.z_min_ground_mid, gr.z_min_ground_rear};
+      const double zhi[3] = {gr.z_max_ground_front, gr.z_max_ground_mid, gr.z_max_ground_rear};
+      for (int k = 0; k < 3; ++k) {
+        const std::vector<float> a = oracle_passes(zone_o[k], {{2, f(zlo[k]), f(zhi[k]), 0}});
+        const std::vector<float> b = oracle_passes(zone_o[k], {{2, f(zhi[k] + 0.01), f(fp.z_max), 0}});
+        want_g.insert(want_g.end(), a.begin(), a.end());
+        want_ng.insert(want_ng.end(), b.begin(), b.end());
+      }
+      expect_cloud(*pg, want_g, want_g.size() / 4, "proceed_pointcloud ground");
+      expect_cloud(*png, want_ng, want_ng.size() / 4, "proceed_pointcloud no_ground");
+      // filter_ROI_T: longitudinal bar += transverse bar
+      Cloud::Ptr tshape(new Cloud);
+      filter_ROI_T(ctx, fp, cloud_ptr, tshape);
+      std::vector<float> t_o = oracle_passes(tr, {{0, f(-fp.x_longitudinal / 2), f(fp.x_longitudinal / 2), 0},
+                                                  {1, f(-fp.y_longitudinal / 2), f(fp.y_longitudinal / 2), 0}, z});
+      const std::vector<float> t2 = oracle_passes(tr, {{0, f(fp.x_longitudinal / 2), f((fp.x_longitudinal / 2) + fp.x_transverse), 0},
+                                                       {1, f(-fp.y_transverse / 2), f(fp.y_transverse / 2), 0}, z});
+      t_o.insert(t_o.end(), t2.begin(), t2.end());
+      expect_cloud(*tshape, t_o, t_o.size() / 4, "filter_ROI_T");
+      // remove_outliers: radius 0.1 m in this package
+      Cloud::Ptr ro(new Cloud(*mi));
+      remove_outliers(ctx, fp, ro);
+      const int64_t n_mi = static_cast<int64_t>(zone_o[1].size() / 4);
+      std::vector<int32_t> keep(static_cast<size_t>(n_mi) + 1);
+      const int64_t kk = cmo_radius_outlier(zone_o[1].data(), n_mi, fp.radius, static_cast<int32_t>(fp.min_neighbor), 0, keep.data());
+      std::vector<float> want(static_cast<size_t>(kk) * 4);
+      for (int64_t i = 0; i < kk; ++i) std::memcpy(&want[i * 4], &zone_o[1][static_cast<size_t>(keep[i]) * 4], 16);
+      expect_cloud(*ro, want, static_cast<size_t>(kk), "remove_outliers");
     }
     // fusePointclouds: *no_ground_ptr = first; *no_ground_ptr += rest
     if (s == 0) *fused = *roi_ptr; else *fused += *roi_ptr;
@@ -289,6 +381,72 @@ int main() {
     CHECK(stamp_of(v2) == 100 + 7 * (S - 1), "fused stamp");
     // the function-by-function result and the fused result are the same clouds
     CHECK(f2.points.size() == fused->points.size() && v2.points.size() == voxel->points.size(), "fused == stepwise");
+
+    // ---- wire adapters: the same frame delivered as sensor_msgs::PointCloud2 in the sensors' own layouts, extrinsics as
+    // Eigen::Matrix4f; published clouds described the way pcl::toROSMsg does (pc_preprocessing_main.cpp:199-220, :520-525)
+#if defined(CM_SHIM_HAVE_ROS_MSG) && defined(CM_SHIM_HAVE_EIGEN)
+    {
+      struct Lay { uint32_t step, ox, oy, oz, oi; const char* extra; uint32_t oextra; uint8_t textra; };
+      const Lay lays[3] = {{32, 0, 4, 8, 16, "ring", 20, sensor_msgs::PointField::UINT16},     // Velodyne (Melodic driver)
+                           {22, 0, 4, 8, 12, "ring", 16, sensor_msgs::PointField::UINT16},     // newer Velodyne: + time f32 @ 18
+                           {18, 0, 4, 8, 12, "tag", 16, sensor_msgs::PointField::UINT8}};      // Livox
+      FusedFrame fm(S, 1 << 16, 0b111);
+      CHECK(fm.ok(), "FusedFrame (msg)");
+      for (int s = 0; s < S; ++s) {
+        float m12[12];
+        cmo_tf_to_matrix(tf[s].q, tf[s].origin, m12);
+        Eigen::Matrix4f m = Eigen::Matrix4f::Identity();
+        for (int r = 0; r < 3; ++r) for (int c = 0; c < 4; ++c) m(r, c) = m12[r * 4 + c];
+        fm.setTransform(s, m);
+        sensor_msgs::PointCloud2 msg;
+        const Lay& L = lays[s];
+        msg.height = 1; msg.width = static_cast<uint32_t>(N[s]); msg.point_step = L.step; msg.row_step = L.step * msg.width;
+        msg.is_dense = raw[s].is_dense; msg.is_bigendian = 0;
+        msg.header.stamp.sec = 100 + 7 * s; msg.header.stamp.nsec = 0;
+        const char* nm[4] = {"x", "y", "z", "intensity"};
+        const uint32_t off[4] = {L.ox, L.oy, L.oz, L.oi};
+        for (int k = 0; k < 4; ++k) {
+          sensor_msgs::PointField f; f.name = nm[k]; f.offset = off[k]; f.datatype = sensor_msgs::PointField::FLOAT32; f.count = 1;
+          msg.fields.push_back(f);
+        }
+        sensor_msgs::PointField fx; fx.name = L.extra; fx.offset = L.oextra; fx.datatype = L.textra; fx.count = 1;
+        msg.fields.insert(msg.fields.begin() + 1, fx);  // field order in the message does not matter: lookup is by name
+        msg.data.assign(static_cast<size_t>(msg.row_step), 0xA5);
+        for (size_t i = 0; i < N[s]; ++i) {
+          uint8_t* r = &msg.data[i * L.step];
+          std::memcpy(r + L.ox, &raw[s].points[i].x, 4); std::memcpy(r + L.oy, &raw[s].points[i].y, 4);
+          std::memcpy(r + L.oz, &raw[s].points[i].z, 4); std::memcpy(r + L.oi, &raw[s].points[i].intensity, 4);
+        }
+        cm_layout_t got;
+        CHECK(layoutFromMsg(msg, &got) == CM_OK && got.point_step == (int)L.step && got.off_intensity == (int)L.oi &&
+              got.is_dense == (raw[s].is_dense ? 1 : 0), "layoutFromMsg sensor %d", s);
+        CHECK(fm.onCloudMsg(s, msg), "onCloudMsg sensor %d", s);
+      }
+      Cloud f3, v3;
+      CHECK(fm.fuseAndVoxel(f3, v3), "fuseAndVoxel (msg)");
+      expect_cloud(f3, sx, static_cast<size_t>(nsurv), "PointCloud2 path fused cloud");
+      expect_cloud(v3, cen, static_cast<size_t>(v), "PointCloud2 path voxel cloud");
+      CHECK(stamp_of(v3) == (100ull + 7 * (S - 1)) * 1000000ull, "stamp converted like pcl_conversions (microseconds)");
+      // publish side: header + memcpy
+      sensor_msgs::PointCloud2 out_msg;
+      CHECK(toROSMsg(v3, out_msg), "toROSMsg");
+      CHECK(out_msg.height == 1 && out_msg.width == v3.points.size() && out_msg.point_step == 32 && out_msg.row_step == 32 * out_msg.width &&
+            !out_msg.is_bigendian && out_msg.is_dense && out_msg.fields.size() == 4 && out_msg.fields[3].name == "intensity" &&
+            out_msg.fields[3].offset == 16 && out_msg.fields[3].datatype == sensor_msgs::PointField::FLOAT32 && out_msg.fields[2].offset == 8,
+            "published message header as pcl::toROSMsg writes it");
+      CHECK(out_msg.data.size() == v3.points.size() * 32 && (v3.points.empty() || std::memcmp(out_msg.data.data(), v3.points.data(), out_msg.data.size()) == 0),
+            "published message data");
+      // a message pcl_ros could not map (x as FLOAT64, or big-endian) is refused; an integer intensity reads as absent
+      sensor_msgs::PointCloud2 bad;
+      bad.point_step = 32;
+      sensor_msgs::PointField bx; bx.name = "x"; bx.offset = 0; bx.datatype = sensor_msgs::PointField::FLOAT64; bx.count = 1;
+      bad.fields.push_back(bx);
+      cm_layout_t lb;
+      CHECK(layoutFromMsg(bad, &lb) == CM_E_INVALID, "FLOAT64 x must be refused");
+    }
+#else
+    CHECK(false, "the wire adapters were not compiled (mock ROS / Eigen headers missing from the include path)");
+#endif
   }
   std::printf("%s: %d failure(s)\n", g_fail ? "FAILED" : "shim ok", g_fail);
   return g_fail ? 1 : 0;

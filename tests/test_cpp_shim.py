@@ -36,3 +36,15 @@ def test_shim_matches_oracle_on_gpu(gpu_ok):
     r = subprocess.run([exe], capture_output=True, text=True, timeout=300)
     assert r.returncode == 0, r.stdout + r.stderr
     assert "shim ok" in r.stdout
+
+
+def test_shim_handoff_is_race_free_under_tsan():
+    """FusedFrame's hand-off between the six callback threads and the main loop (include/cloud_merger_shim.hpp), built with
+    -fsanitize=thread against a host-only stub of the C ABI (tests/cpp/stub_cm.cpp): ThreadSanitizer reports no race (it
+    would exit 66), every fused frame holds the required sensors, no delivery is lost. CPU only: CUDA does not run under TSAN."""
+    _build()
+    exe = os.path.join(CPP, "test_shim_threads")
+    env = dict(os.environ, TSAN_OPTIONS="halt_on_error=1 exitcode=66")
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=300, env=env)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-4000:]
+    assert "shim threads ok" in r.stdout and "ThreadSanitizer" not in r.stderr
