@@ -45,6 +45,22 @@ class CmPlane(C.Structure):
 
 
 CM_SUM4_SSE2, CM_SUM4_SSE3, CM_SUM4_SCALAR = 0, 1, 2
+CM_MAX_PROCEED_PARTS = 8
+
+
+class CmProceedPart(C.Structure):
+    _fields_ = [("length", C.c_float), ("deviation", C.c_float), ("z_max_ground", C.c_float), ("ground_removal", C.c_int32)]
+
+
+class CmProceedCfg(C.Structure):
+    _fields_ = [("n_parts", C.c_int32), ("min_neighbors", C.c_int32), ("part", CmProceedPart * CM_MAX_PROCEED_PARTS),
+                ("roi_z_max", C.c_float), ("reserved", C.c_float), ("radius", C.c_double), ("plane", CmPlaneCfg)]
+
+
+class CmProceedOut(C.Structure):
+    _fields_ = [("no_ground_xyzi", C.c_void_p), ("ground_xyzi", C.c_void_p), ("n_no_ground", C.c_int64),
+                ("n_ground", C.c_int64), ("plane", CmPlane * CM_MAX_PROCEED_PARTS), ("n_planes", C.c_int32),
+                ("host_syncs", C.c_int32)]
 
 
 class CmLayout(C.Structure):
@@ -152,6 +168,9 @@ SYMBOLS = {
                                         C.c_void_p, C.c_void_p, C.c_int64, C.POINTER(C.c_int64)]),
     "cm_plane_ransac": (C.c_int, [_H, C.c_void_p, C.c_int64, C.POINTER(CmPlaneCfg), C.POINTER(CmPlane), C.c_void_p,
                                   C.c_void_p, C.c_int64, C.POINTER(C.c_int64)]),
+    "cm_dev_proceed_zones": (C.c_int, [_H, C.c_void_p, C.c_int64, C.POINTER(CmProceedCfg), C.POINTER(CmProceedOut), C.c_void_p]),
+    "cm_proceed_zones": (C.c_int, [_H, C.c_void_p, C.c_int64, C.POINTER(CmProceedCfg), C.c_void_p, C.c_int64, C.POINTER(C.c_int64),
+                                   C.c_void_p, C.c_int64, C.POINTER(C.c_int64), C.POINTER(CmPlane)]),
     "cm_dev_bounds": (C.c_int, [_H, C.c_void_p, C.c_int64, C.POINTER(C.c_float), C.POINTER(C.c_float), C.POINTER(C.c_int64),
                                 C.c_void_p]),
     "cm_dev_key_histogram": (C.c_int, [_H, C.c_void_p, C.c_int64, C.POINTER(C.c_float), C.POINTER(C.c_float), C.c_int,

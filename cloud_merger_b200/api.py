@@ -331,6 +331,55 @@ class CloudMerger:
         r["rest"] = (ox[b[1]:b[2]].copy(), oi[b[1]:b[2]].copy())
         return r
 
+    # -- the body of a proceedX in one call (pc_preprocessing_main.cpp:228-312, :428-446, :474-497) ---------------------------
+    def _proceed_cfg(self, parts, roi_z_max, radius, min_neighbors, distance_threshold, probability, max_iterations, optimize,
+                     seed, sum_order):
+        """parts: (length, deviation, z_max_ground) for a ground-removal part, (length, deviation, None) for a plain one."""
+        cfg = _lib.CmProceedCfg()
+        cfg.n_parts = len(parts)
+        cfg.min_neighbors = int(min_neighbors)
+        for k, pt in enumerate(parts):
+            zg = pt[2] if len(pt) > 2 else None
+            cfg.part[k] = _lib.CmProceedPart(float(np.float32(pt[0])), float(np.float32(pt[1])),
+                                             float(np.float32(0.0 if zg is None else zg)), 0 if zg is None else 1)
+        cfg.roi_z_max = float(np.float32(roi_z_max))
+        cfg.radius = float(radius)
+        cfg.plane = self._plane_cfg(distance_threshold, probability, max_iterations, optimize, seed, sum_order)
+        return cfg
+
+    def dev_proceed_zones(self, roi_ptr: int, n_points: int, parts, roi_z_max: float = 3.0, radius: float = 0.15,
+                          min_neighbors: int = 1, distance_threshold: float = 0.3, probability: float = 0.99,
+                          max_iterations: int = 1000, optimize: bool = True, seed: int = 12345, sum_order: int = 0,
+                          stream: int = 0) -> dict:
+        """Device form: the ROI cloud at roi_ptr -> no-ground / ground clouds in device memory (pointers + sizes)."""
+        cfg = self._proceed_cfg(parts, roi_z_max, radius, min_neighbors, distance_threshold, probability, max_iterations,
+                                optimize, seed, sum_order)
+        po = _lib.CmProceedOut()
+        self._check(self._lib.cm_dev_proceed_zones(self._h, C.c_void_p(roi_ptr or None), C.c_int64(n_points), C.byref(cfg),
+                                                   C.byref(po), C.c_void_p(stream or None)))
+        return {"no_ground_ptr": po.no_ground_xyzi, "n_no_ground": int(po.n_no_ground), "ground_ptr": po.ground_xyzi,
+                "n_ground": int(po.n_ground), "planes": [self._plane_dict(po.plane[i]) for i in range(po.n_planes)],
+                "host_syncs": int(po.host_syncs)}
+
+    def proceed_zones(self, roi_xyzi: np.ndarray, parts, roi_z_max: float = 3.0, radius: float = 0.15, min_neighbors: int = 1,
+                      distance_threshold: float = 0.3, probability: float = 0.99, max_iterations: int = 1000,
+                      optimize: bool = True, seed: int = 12345, sum_order: int = 0) -> dict:
+        """Host-buffer form: (no_ground [n,4], ground [m,4], planes)."""
+        a = np.ascontiguousarray(roi_xyzi, np.float32).reshape(-1, 4)
+        n = len(a)
+        cfg = self._proceed_cfg(parts, roi_z_max, radius, min_neighbors, distance_threshold, probability, max_iterations,
+                                optimize, seed, sum_order)
+        cap = 2 * max(n, 1)
+        ng, g = np.empty((cap, 4), np.float32), np.empty((cap, 4), np.float32)
+        n_ng, n_g = C.c_int64(), C.c_int64()
+        pl = (_lib.CmPlane * _lib.CM_MAX_PROCEED_PARTS)()
+        self._check(self._lib.cm_proceed_zones(self._h, a.ctypes.data_as(C.c_void_p), C.c_int64(n), C.byref(cfg),
+                                               ng.ctypes.data_as(C.c_void_p), C.c_int64(cap), C.byref(n_ng),
+                                               g.ctypes.data_as(C.c_void_p), C.c_int64(cap), C.byref(n_g), pl))
+        k = sum(1 for pt in parts if len(pt) > 2 and pt[2] is not None)
+        return {"no_ground": ng[:n_ng.value].copy(), "ground": g[:n_g.value].copy(),
+                "planes": [self._plane_dict(pl[i]) for i in range(k)]}
+
     # -- giant-cloud mode: device-side pieces of the voxel-key range partition (BASELINE config 4) -------------------------
     def dev_bounds(self, xyzi_ptr: int, n_points: int, stream: int = 0):
         """pcl::getMinMax3D of n packed points on the device -> (min[3], max[3] float32, number of finite points)."""

@@ -190,6 +190,13 @@ struct cm_handle_s {
     float4* models_pin = nullptr;
     float* acc_pin = nullptr;
   } pw;
+  // cm_*proceed_zones: stage results parked between the three multi-cloud stages, and the two result clouds
+  struct ProceedWs {
+    size_t cap = 0;
+    float4 *low = nullptr, *high = nullptr, *rest = nullptr, *planes = nullptr;  // [cap] each
+    float4 *no_ground = nullptr, *ground = nullptr;                              // [2 cap] (windows share their end points)
+    float4* in_stage = nullptr;                                                  // host-buffer form: the uploaded ROI cloud
+  } prz;
   // host path
   std::vector<Slot> slots;
   std::vector<cudaStream_t> sensor_stream;
@@ -1027,6 +1034,8 @@ int cm_destroy(cm_handle_t h) {
     cudaFree(z.out_xyzi); cudaFree(z.out_src); cudaFree(z.in_stage);
     if (z.report) cudaFreeHost(z.report);
     cudaFree(h->ror_table);
+    cudaFree(h->prz.low); cudaFree(h->prz.high); cudaFree(h->prz.rest); cudaFree(h->prz.planes);
+    cudaFree(h->prz.no_ground); cudaFree(h->prz.ground); cudaFree(h->prz.in_stage);
     auto& q = h->pw;
     cudaFree(q.samples_dev); cudaFree(q.counts_dev); cudaFree(q.models_dev); cudaFree(q.acc_dev);
     if (q.samples_pin) cudaFreeHost(q.samples_pin);
@@ -2094,6 +2103,186 @@ int cm_plane_ransac(cm_handle_t h, const float* xyzi_host, int64_t n_points, con
   if (n_points < 0) return CM_E_INVALID;
   const int64_t begin[2] = {0, n_points};
   return cm_plane_ransac_multi(h, xyzi_host, begin, 1, cfg, out, out_xyzi, out_idx, capacity, out_begin);
+}
+
+// ---- the body of a proceedX in one call ---------------------------------------------------------------------------------------
+namespace {
+int proceed_ws_ensure(cm_handle_t h, size_t points) {
+  cm_handle_s::ProceedWs& w = h->prz;
+  const size_t want = std::max<size_t>({points, (size_t)h->cfg.max_batch_points, (size_t)1});
+  if (w.cap >= want) return CM_OK;
+  cudaFree(w.low); cudaFree(w.high); cudaFree(w.rest); cudaFree(w.planes); cudaFree(w.no_ground); cudaFree(w.ground); cudaFree(w.in_stage);
+  w = cm_handle_s::ProceedWs();
+  CM_CUDA(h, dev_alloc(&w.low, want));
+  CM_CUDA(h, dev_alloc(&w.high, 2 * want));
+  CM_CUDA(h, dev_alloc(&w.rest, want));
+  CM_CUDA(h, dev_alloc(&w.planes, want));
+  CM_CUDA(h, dev_alloc(&w.no_ground, 2 * want));
+  CM_CUDA(h, dev_alloc(&w.ground, 2 * want));
+  w.cap = want;
+  return CM_OK;
+}
+
+int proceed_run(cm_handle_t h, const float4* roi, int64_t n, const cm_proceed_cfg_t& cfg, cm_proceed_out_t* out, cudaStream_t st) {
+  if (cfg.n_parts < 1 || cfg.n_parts > CM_MAX_PROCEED_PARTS) return fail(h, CM_E_INVALID, "1 .. %d parts", CM_MAX_PROCEED_PARTS);
+  if (n < 0 || n > 0x7FFFFFF0ll) return fail(h, CM_E_INVALID, "bad n_points");
+  int ground_of[CM_MAX_PROCEED_PARTS], plain_of[CM_MAX_PROCEED_PARTS];
+  int G = 0, P = 0;
+  for (int k = 0; k < cfg.n_parts; ++k) {
+    ground_of[k] = plain_of[k] = -1;
+    if (cfg.part[k].ground_removal) ground_of[k] = G++; else plain_of[k] = P++;
+  }
+  if (2 * G + P > CM_MAX_ZONES || G > CM_MAX_PLANE_CLOUDS) return fail(h, CM_E_INVALID, "too many parts for one pass");
+  int rc = ensure_batch_ws(h);
+  if (rc != CM_OK) return rc;
+  if (G > 0 && (uint32_t)G > h->batch.cap_frames)
+    return fail(h, CM_E_CAPACITY, "%d ground-removal parts need max_batch_frames >= %d (handle has %u)", G, G, h->batch.cap_frames);
+  rc = proceed_ws_ensure(h, (size_t)n);
+  if (rc != CM_OK) return rc;
+  cm_handle_s::ProceedWs& w = h->prz;
+  memset(out, 0, sizeof(*out));
+  out->no_ground_xyzi = reinterpret_cast<const float*>(w.no_ground);
+  out->ground_xyzi = reinterpret_cast<const float*>(w.ground);
+  out->n_planes = G;
+  // ---- one zone-slicing pass: zones [0, G) the ground windows, [G, 2G) the upper windows, [2G, 2G + P) the plain parts
+  const ZoneSet saved = h->zones;
+  {
+    std::vector<cm_zone_t> zones((size_t)(2 * G + P));
+    for (int k = 0; k < cfg.n_parts; ++k) {
+      const cm_proceed_part_t& pt = cfg.part[k];
+      const cm_pass_t x = {0, pt.deviation, pt.deviation + pt.length, 0};  // float sum, as getCloudPart passes it to setFilterLimits
+      if (ground_of[k] >= 0) {
+        cm_zone_t& lo = zones[(size_t)ground_of[k]];
+        cm_zone_t& hi = zones[(size_t)(G + ground_of[k])];
+        lo.n_pass = 2; lo.pass[0] = x; lo.pass[1] = cm_pass_t{2, -pt.z_max_ground, pt.z_max_ground, 0};
+        // `z_max_ground + 0.01` is a double sum narrowed to float by setFilterLimits(const float&, const float&) (:88)
+        hi.n_pass = 2; hi.pass[0] = x; hi.pass[1] = cm_pass_t{2, (float)((double)pt.z_max_ground + 0.01), cfg.roi_z_max, 0};
+      } else {
+        cm_zone_t& pl = zones[(size_t)(2 * G + plain_of[k])];
+        pl.n_pass = 1; pl.pass[0] = x;
+      }
+    }
+    ZoneSet zs{};
+    zs.n_zones = 2 * G + P;
+    zs.all_box = 1;
+    const float fmax = std::numeric_limits<float>::max();
+    for (int z = 0; z < zs.n_zones; ++z) {
+      ZoneDev& zd = zs.zone[z];
+      zd.n_pass = zones[(size_t)z].n_pass; zd.is_box = 1; zd.use_i = 0;
+      for (int a = 0; a < 4; ++a) { zd.lo[a] = -fmax; zd.hi[a] = fmax; }
+      for (int q = 0; q < zd.n_pass; ++q) {
+        const cm_pass_t& ps = zones[(size_t)z].pass[q];
+        zd.pass[q] = PassDev{ps.axis, ps.lo, ps.hi, 0};
+        if (!(ps.lo == ps.lo) || !(ps.hi == ps.hi)) { zd.is_box = 0; zs.all_box = 0; continue; }
+        zd.lo[ps.axis] = std::max(zd.lo[ps.axis], ps.lo);
+        zd.hi[ps.axis] = std::min(zd.hi[ps.axis], ps.hi);
+      }
+    }
+    h->zones = zs;
+  }
+  rc = zone_run(h, roi, n, st);
+  h->zones = saved;
+  if (rc != CM_OK) return rc;
+  cm_zone_out_t zo;
+  rc = zone_out_locked(h, &zo);
+  ++out->host_syncs;
+  if (rc != CM_OK) return rc;
+  const int64_t n_low = zo.begin[G], n_high = zo.begin[2 * G + P] - n_low;
+  if ((size_t)n_low > w.cap || (size_t)n_high > 2 * w.cap) return fail(h, CM_E_CAPACITY, "zone windows larger than the workspace");
+  if (n_low) CM_CUDA(h, cudaMemcpyAsync(w.low, zo.xyzi, (size_t)n_low * 16, cudaMemcpyDeviceToDevice, st));
+  if (n_high) CM_CUDA(h, cudaMemcpyAsync(w.high, zo.xyzi + n_low * 4, (size_t)n_high * 16, cudaMemcpyDeviceToDevice, st));
+  int64_t zb[CM_MAX_ZONES + 1];
+  for (int z = 0; z <= 2 * G + P; ++z) zb[z] = zo.begin[z];
+
+  // ---- one multi-cloud plane search over the ground windows, one multi-cloud outlier removal over what is not ground
+  int64_t pb[2 * CM_MAX_PLANE_CLOUDS + 1] = {0}, kb[CM_MAX_PLANE_CLOUDS + 1] = {0}, rb[CM_MAX_PLANE_CLOUDS + 1] = {0};
+  const float4* kept = nullptr;
+  if (G > 0) {
+    rc = plane_ransac_run(h, w.low, zb, G, cfg.plane, out->plane, st);  // ends with the sizes on the host
+    out->host_syncs += 2 + (cfg.plane.optimize ? 1 : 0);
+    if (rc != CM_OK) return rc;
+    rc = zone_out_locked(h, &zo);
+    if (rc != CM_OK) return rc;
+    for (int z = 0; z <= 2 * G; ++z) pb[z] = zo.begin[z];
+    if (pb[2 * G]) CM_CUDA(h, cudaMemcpyAsync(w.planes, zo.xyzi, (size_t)pb[2 * G] * 16, cudaMemcpyDeviceToDevice, st));
+    for (int c = 0; c < G; ++c) {  // the non-ground points of every window side by side
+      const int64_t cnt = pb[2 * c + 2] - pb[2 * c + 1];
+      if (cnt) CM_CUDA(h, cudaMemcpyAsync(w.rest + rb[c], w.planes + pb[2 * c + 1], (size_t)cnt * 16, cudaMemcpyDeviceToDevice, st));
+      rb[c + 1] = rb[c] + cnt;
+    }
+    rc = radius_outlier_run(h, w.rest, rb, G, cfg.radius, cfg.min_neighbors, 0, st);
+    if (rc != CM_OK) return rc;
+    rc = zone_out_locked(h, &zo);
+    out->host_syncs += 2;
+    if (rc != CM_OK) return rc;
+    for (int c = 0; c <= G; ++c) kb[c] = zo.begin[c];
+    kept = reinterpret_cast<const float4*>(zo.xyzi);
+    uint32_t dev_err = 0;  // key-range / watchdog errors of the cell sort
+    CM_CUDA(h, cudaMemcpyAsync(&dev_err, &reinterpret_cast<Ctrl*>(h->batch.meta + h->batch.ml.off_ctrl)->error, sizeof(dev_err), cudaMemcpyDeviceToHost, st));
+    CM_CUDA(h, cudaStreamSynchronize(st));
+    if (dev_err == CM_DEV_E_KEY_RANGE) return fail(h, CM_E_KEY_RANGE, "radius too small for the extent of a zone (cell grid exceeds the key range)");
+    if (dev_err) return fail(h, CM_E_INTERNAL, "device error %u", dev_err);
+  }
+  // ---- the appends, in part order
+  int64_t n_ng = 0, n_g = 0;
+  for (int k = 0; k < cfg.n_parts; ++k) {
+    if (ground_of[k] >= 0) {
+      const int c = ground_of[k];
+      int64_t cnt = kb[c + 1] - kb[c];                    // outlierRemoval(no_ground_cloud_ptr) ...
+      if (cnt) CM_CUDA(h, cudaMemcpyAsync(w.no_ground + n_ng, kept + kb[c], (size_t)cnt * 16, cudaMemcpyDeviceToDevice, st));
+      n_ng += cnt;
+      cnt = zb[G + c + 1] - zb[G + c];                    // ... += *no_ground_part_ptr (the upper window)
+      if (cnt) CM_CUDA(h, cudaMemcpyAsync(w.no_ground + n_ng, w.high + (zb[G + c] - n_low), (size_t)cnt * 16, cudaMemcpyDeviceToDevice, st));
+      n_ng += cnt;
+      cnt = pb[2 * c + 1] - pb[2 * c];                    // ground: the inliers
+      if (cnt) CM_CUDA(h, cudaMemcpyAsync(w.ground + n_g, w.planes + pb[2 * c], (size_t)cnt * 16, cudaMemcpyDeviceToDevice, st));
+      n_g += cnt;
+    } else {
+      const int z = 2 * G + plain_of[k];
+      const int64_t cnt = zb[z + 1] - zb[z];
+      if (cnt) CM_CUDA(h, cudaMemcpyAsync(w.no_ground + n_ng, w.high + (zb[z] - n_low), (size_t)cnt * 16, cudaMemcpyDeviceToDevice, st));
+      n_ng += cnt;
+    }
+  }
+  out->n_no_ground = n_ng;
+  out->n_ground = n_g;
+  return CM_OK;
+}
+}  // namespace
+
+int cm_dev_proceed_zones(cm_handle_t h, const float* roi_xyzi_dev, int64_t n_points, const cm_proceed_cfg_t* cfg,
+                         cm_proceed_out_t* out, void* stream) {
+  if (!h || !cfg || !out) return CM_E_INVALID;
+  std::lock_guard<std::mutex> lk(h->mu);
+  CM_CUDA(h, cudaSetDevice(h->device));
+  if (n_points > 0 && (!roi_xyzi_dev || (reinterpret_cast<uintptr_t>(roi_xyzi_dev) & 15u))) return fail(h, CM_E_INVALID, "roi_xyzi_dev must be 16-byte aligned");
+  return proceed_run(h, reinterpret_cast<const float4*>(roi_xyzi_dev), n_points, *cfg, out, static_cast<cudaStream_t>(stream));
+}
+
+int cm_proceed_zones(cm_handle_t h, const float* roi_xyzi_host, int64_t n_points, const cm_proceed_cfg_t* cfg, float* out_no_ground,
+                     int64_t no_ground_capacity, int64_t* n_no_ground, float* out_ground, int64_t ground_capacity, int64_t* n_ground,
+                     cm_plane_t* out_planes) {
+  if (!h || !cfg || !n_no_ground || !n_ground || n_points < 0 || (n_points > 0 && !roi_xyzi_host)) return CM_E_INVALID;
+  std::lock_guard<std::mutex> lk(h->mu);
+  CM_CUDA(h, cudaSetDevice(h->device));
+  int rc = proceed_ws_ensure(h, (size_t)n_points);
+  if (rc != CM_OK) return rc;
+  cm_handle_s::ProceedWs& w = h->prz;
+  if (!w.in_stage) CM_CUDA(h, dev_alloc(&w.in_stage, w.cap));
+  if (n_points) CM_CUDA(h, cudaMemcpyAsync(w.in_stage, roi_xyzi_host, (size_t)n_points * 16, cudaMemcpyHostToDevice, nullptr));
+  cm_proceed_out_t po;
+  rc = proceed_run(h, w.in_stage, n_points, *cfg, &po, nullptr);
+  if (rc != CM_OK) return rc;
+  *n_no_ground = po.n_no_ground;
+  *n_ground = po.n_ground;
+  if (out_planes) for (int c = 0; c < po.n_planes; ++c) out_planes[c] = po.plane[c];
+  if (po.n_no_ground > no_ground_capacity || po.n_ground > ground_capacity)
+    return fail(h, CM_E_CAPACITY, "%lld / %lld points, caller capacities %lld / %lld", (long long)po.n_no_ground, (long long)po.n_ground,
+                (long long)no_ground_capacity, (long long)ground_capacity);
+  if (out_no_ground && po.n_no_ground) CM_CUDA(h, cudaMemcpyAsync(out_no_ground, po.no_ground_xyzi, (size_t)po.n_no_ground * 16, cudaMemcpyDeviceToHost, nullptr));
+  if (out_ground && po.n_ground) CM_CUDA(h, cudaMemcpyAsync(out_ground, po.ground_xyzi, (size_t)po.n_ground * 16, cudaMemcpyDeviceToHost, nullptr));
+  CM_CUDA(h, cudaStreamSynchronize(nullptr));
+  return CM_OK;
 }
 
 int cm_sync(cm_handle_t h) {

@@ -9,11 +9,12 @@
     voxelgrid      :168-177   VoxelGrid of the fused no_ground cloud
 
 Everything between the upload of the raw sensor clouds and the download of the three published clouds stays in device
-memory. The stages are the C-ABI calls of include/cloud_merger_gpu.h, each on its own handle because a stage's results
-live in its handle's workspace until that handle runs again: transform + ROI crop of all sensors in one launch (frame =
-sensor), per sensor one zone-slicing pass, one multi-cloud plane search and one multi-cloud radius outlier removal,
-device-to-device appends, one VoxelGrid. The per-sensor stages run concurrently -- one host thread and one CUDA stream per
-sensor, as the reference's callbacks do on ros::AsyncSpinner(6) (pc_preprocessing_main.cpp:513).
+memory. The stages are the C-ABI calls of include/cloud_merger_gpu.h: transform + ROI crop of all sensors in one launch
+(frame = sensor), per sensor ONE call for the whole proceedX body (cm_dev_proceed_zones: one zone-slicing pass, one
+multi-cloud plane search, one multi-cloud radius outlier removal, the appends), device-to-device appends of the sensors,
+one VoxelGrid. The per-sensor calls run concurrently -- one host thread, one handle and one CUDA stream per sensor, as the
+reference's callbacks do on ros::AsyncSpinner(6) (pc_preprocessing_main.cpp:513). The C++ counterpart is
+cloud_merger::PreprocessingFrame in include/cloud_merger_shim.hpp.
 
 Host glue, not a kernel: there is no CPU fallback and no arithmetic on points here.
 """
@@ -60,56 +61,31 @@ class NodeParams:
 
 
 class _SensorLane:
-    """The proceedX stages of one sensor on their own handles and CUDA stream: one callback thread of the reference
-    (ros::AsyncSpinner(6), pc_preprocessing_main.cpp:513)."""
+    """The proceedX body of one sensor: ONE handle, ONE C call (cm_dev_proceed_zones), its own CUDA stream -- one callback
+    thread of the reference (ros::AsyncSpinner(6), pc_preprocessing_main.cpp:513)."""
 
     def __init__(self, device: int, max_points: int, p: NodeParams, parts):
-        mk = lambda frames: CloudMerger(device=device, max_sensors=1, max_points_per_sensor=max_points,
-                                        max_batch_points=max_points, max_batch_frames=frames)
         self.p = p
-        self.k = len(parts)
-        self.zones, self.plane, self.ror = mk(1), mk(1), mk(8)
-        self.zones.set_zones(zones_of_parts(parts, p.roi_z_max))
-        self.rest = self.ror.device_buffer(max_points * 16)            # what is not ground, window after window
-        self.no_ground = self.zones.device_buffer(2 * max_points * 16)  # windows share their end points
-        self.ground = self.zones.device_buffer(2 * max_points * 16)
-        self.stream = self.zones.stream_create()
+        self.parts = [tuple(pt) for pt in parts]
+        self.h = CloudMerger(device=device, max_sensors=1, max_points_per_sensor=max_points, max_batch_points=max_points,
+                             max_batch_frames=8)
+        self.stream = self.h.stream_create()
         self.n_ng = self.n_g = 0
+        self.no_ground_ptr = self.ground_ptr = 0
         self.planes: List[dict] = []
 
     def close(self):
-        self.zones.stream_destroy(self.stream)
-        for h in (self.zones, self.plane, self.ror):
-            h.close()
+        self.h.stream_destroy(self.stream)
+        self.h.close()
 
     def run(self, roi_ptr: int, n: int):
-        p, k, st = self.p, self.k, self.stream
-        d2d = self.zones.memcpy_d2d
-        self.zones.dev_zone_split(roi_ptr, n, stream=st)
-        z_xyzi, _, zb = self.zones.zone_out_raw()
-        self.planes = self.plane.dev_plane_ransac_multi(z_xyzi, zb[:k + 1], p.distance_threshold, p.prob, p.max_iterations,
-                                                        True, 12345, p.sum_order, stream=st)
-        p_xyzi, _, pb = self.plane.zone_out_raw()
-        rb = [0]
-        for i in range(k):  # the rest clouds (odd zones) side by side
-            cnt = pb[2 * i + 2] - pb[2 * i + 1]
-            d2d(self.rest.ptr + rb[-1] * 16, p_xyzi + pb[2 * i + 1] * 16, cnt * 16, stream=st)
-            rb.append(rb[-1] + cnt)
-        self.ror.dev_radius_outlier_multi(self.rest.ptr, rb, p.radius, p.min_neighbor, stream=st)
-        r_xyzi, _, kb = self.ror.zone_out_raw()
-        n_ng = n_g = 0
-        for i in range(k):
-            cnt = kb[i + 1] - kb[i]                     # outlierRemoval(no_ground) ...
-            d2d(self.no_ground.ptr + n_ng * 16, r_xyzi + kb[i] * 16, cnt * 16, stream=st)
-            n_ng += cnt
-            cnt = zb[k + i + 1] - zb[k + i]             # ... += the points above the window
-            d2d(self.no_ground.ptr + n_ng * 16, z_xyzi + zb[k + i] * 16, cnt * 16, stream=st)
-            n_ng += cnt
-            cnt = pb[2 * i + 1] - pb[2 * i]             # ground += the inliers
-            d2d(self.ground.ptr + n_g * 16, p_xyzi + pb[2 * i] * 16, cnt * 16, stream=st)
-            n_g += cnt
-        self.zones.stream_sync(st)
-        self.n_ng, self.n_g = n_ng, n_g
+        p = self.p
+        r = self.h.dev_proceed_zones(roi_ptr, n, self.parts, p.roi_z_max, p.radius, p.min_neighbor, p.distance_threshold, p.prob,
+                                     p.max_iterations, True, 12345, p.sum_order, stream=self.stream)
+        self.h.stream_sync(self.stream)
+        self.n_ng, self.n_g = r["n_no_ground"], r["n_ground"]
+        self.no_ground_ptr, self.ground_ptr = r["no_ground_ptr"], r["ground_ptr"]
+        self.planes = r["planes"]
 
 
 class PreprocessingNode:
@@ -173,8 +149,8 @@ class PreprocessingNode:
         planes: List[dict] = []
         d2d = self.voxel.memcpy_d2d
         for lane, _, _ in jobs:
-            d2d(self.no_ground.ptr + n_ng * 16, lane.no_ground.ptr, lane.n_ng * 16)
-            d2d(self.ground.ptr + n_g * 16, lane.ground.ptr, lane.n_g * 16)
+            d2d(self.no_ground.ptr + n_ng * 16, lane.no_ground_ptr, lane.n_ng * 16)
+            d2d(self.ground.ptr + n_g * 16, lane.ground_ptr, lane.n_g * 16)
             n_ng += lane.n_ng
             n_g += lane.n_g
             planes += lane.planes

@@ -378,6 +378,50 @@ CM_API int cm_plane_ransac_multi(cm_handle_t h, const float* xyzi_host, const in
                                  int64_t capacity, int64_t* out_begin);
 CM_API int cm_plane_ransac(cm_handle_t h, const float* xyzi_host, int64_t n_points, const cm_plane_cfg_t* cfg,
                            cm_plane_t* out, float* out_xyzi, uint32_t* out_idx, int64_t capacity, int64_t* out_begin);
+/* ---- the body of a proceedX in ONE call ----
+ * Replaces what proceedFront / proceedRear / callbackTopMiddle / callbackFrontMiddle do after getROI
+ * (pc_preprocessing_main.cpp:228-312, :428-446, :474-497): for every part of the sensor's zone table
+ *     getCloudPart(cloud_ROI_ptr, part, length, deviation);                                   x in [deviation, deviation + length]
+ *     removeGround(part, no_ground, ground, -z_max_ground, z_max_ground, max_angle);          :71-122
+ *         z windows [-z_max_ground, z_max_ground] and [z_max_ground + 0.01, roi_z_max], RANSAC plane + ExtractIndices on the
+ *         lower one, outlierRemoval of its non-ground points, the upper window appended
+ *     no_ground += ...; ground += ...;
+ * and a part with ground_removal == 0 is appended to the no-ground cloud as it is (the near range of the top sensor,
+ * :444-446). One zone-slicing pass for every window, one multi-cloud plane search, one multi-cloud outlier removal and the
+ * appends, all on one handle and one stream, device-resident in between (the host only sees the stopping rule of the plane
+ * search, the 3 x 3 refit and the sizes). Needs max_batch_frames >= the number of ground-removal parts.
+ *  cm_dev_proceed_zones  n packed float4 xyzi points on the device (the ROI cloud); results stay on the device (valid until
+ *                        the next cm_*proceed_zones on the handle);
+ *  cm_proceed_zones      host buffers in and out; *n_no_ground / *n_ground receive the sizes (also on CM_E_CAPACITY). */
+#define CM_MAX_PROCEED_PARTS 8
+typedef struct {
+  float length, deviation;  /* getCloudPart arguments */
+  float z_max_ground;       /* ground window |z| <= z_max_ground */
+  int32_t ground_removal;   /* 1: removeGround on the part; 0: the part goes to the no-ground cloud unchanged */
+} cm_proceed_part_t;
+typedef struct {
+  int32_t n_parts;
+  int32_t min_neighbors;    /* outlierRemoval: Parameter.h:24 */
+  cm_proceed_part_t part[CM_MAX_PROCEED_PARTS];
+  float roi_z_max;          /* upper end of the no-ground window (Parameter.h:35) */
+  float reserved;
+  double radius;            /* outlierRemoval: Parameter.h:23 */
+  cm_plane_cfg_t plane;     /* SACSegmentation settings (Parameter.h:38-42) */
+} cm_proceed_cfg_t;
+typedef struct {
+  const float* no_ground_xyzi;  /* DEVICE [n_no_ground][4] */
+  const float* ground_xyzi;     /* DEVICE [n_ground][4] */
+  int64_t n_no_ground, n_ground;
+  cm_plane_t plane[CM_MAX_PROCEED_PARTS];  /* the model of every ground-removal part, in part order */
+  int32_t n_planes;
+  int32_t host_syncs;           /* device round trips the call needed (diagnostic) */
+} cm_proceed_out_t;
+CM_API int cm_dev_proceed_zones(cm_handle_t h, const float* roi_xyzi_dev, int64_t n_points, const cm_proceed_cfg_t* cfg,
+                                cm_proceed_out_t* out, void* stream);
+CM_API int cm_proceed_zones(cm_handle_t h, const float* roi_xyzi_host, int64_t n_points, const cm_proceed_cfg_t* cfg,
+                            float* out_no_ground, int64_t no_ground_capacity, int64_t* n_no_ground, float* out_ground,
+                            int64_t ground_capacity, int64_t* n_ground, cm_plane_t* out_planes);
+
 /* ---- single giant cloud over several GPUs (BASELINE config 4): device-side pieces of the voxel-key range partition ----
  * The reference has no counterpart (one process). Every rank holds a block of the cloud; all ranks must build the SAME
  * voxel grid, a voxel must not straddle ranks, and the rank outputs concatenated in rank order must be PCL's order:

@@ -341,6 +341,44 @@ class Context {
     return ok;
   }
 
+  // The body of a proceedX after getROI in ONE library call (cm_proceed_zones): every x / z window, the plane search of every
+  // ground window, the outlier removal of what is not ground and the appends stay on the device in between.
+  bool proceed(const Cloud& roi, const cm_proceed_cfg_t& cfg, Cloud& no_ground, Cloud& ground, std::vector<cm_plane_t>* models = nullptr) {
+    if (!check(h_ ? CM_OK : CM_E_NO_DEVICE)) { clear(no_ground); return clear(ground); }
+    const int64_t n = static_cast<int64_t>(roi.points.size());
+    tmp_.resize(static_cast<size_t>(n) * 4 + 4);
+    for (int64_t i = 0; i < n; ++i) {
+      const PointXYZI& p = roi.points[static_cast<size_t>(i)];
+      tmp_[i * 4 + 0] = p.x; tmp_[i * 4 + 1] = p.y; tmp_[i * 4 + 2] = p.z; tmp_[i * 4 + 3] = p.intensity;
+    }
+    const int64_t cap = 2 * n + 16;
+    zone_xyzi_.resize(static_cast<size_t>(cap) * 4);
+    std::vector<float> g(static_cast<size_t>(cap) * 4);
+    int64_t n_ng = 0, n_g = 0;
+    cm_plane_t pl[CM_MAX_PROCEED_PARTS];
+    if (!check(cm_proceed_zones(h_, tmp_.data(), n, &cfg, zone_xyzi_.data(), cap, &n_ng, g.data(), cap, &n_g, pl))) {
+      clear(no_ground);
+      return clear(ground);
+    }
+    auto fill = [&](Cloud& c, const float* src, int64_t k) {
+      c.points.resize(static_cast<size_t>(k));
+      for (int64_t i = 0; i < k; ++i) {
+        PointXYZI& p = c.points[static_cast<size_t>(i)];
+        p = PointXYZI();
+        p.x = src[i * 4 + 0]; p.y = src[i * 4 + 1]; p.z = src[i * 4 + 2]; p.intensity = src[i * 4 + 3];
+      }
+      finish(c, roi, true);
+    };
+    fill(no_ground, zone_xyzi_.data(), n_ng);
+    fill(ground, g.data(), n_g);
+    if (models) {
+      models->clear();
+      for (int k = 0, c = 0; k < cfg.n_parts; ++k)
+        if (cfg.part[k].ground_removal) models->push_back(pl[c++]);
+    }
+    return true;
+  }
+
   // Zone slicing of ONE host cloud (cm_zone_split): one ordered output cloud per PassThrough chain, one GPU pass.
   bool zone_split(const Cloud& in, const std::vector<cm_zone_t>& zones, std::vector<Cloud>& out) {
     out.assign(zones.size(), Cloud());
@@ -562,30 +600,40 @@ inline void removeGround(Context& ctx, const Cloud::Ptr& cloud_ptr, const Cloud:
   *no_ground_cloud_ptr += parts[1];
 }
 
-// proceedFront / proceedRear / proceedTop / proceedLivox after getROI -- :228-312: per zone getCloudPart + removeGround,
-// results appended zone after zone. Here: one zone-slicing pass for all x and z windows, one multi-cloud RANSAC pass for
-// all ground windows, one multi-cloud outlierRemoval pass for what is not ground, and the points above each window appended.
-inline void proceedZones(Context& ctx, const Cloud::Ptr& cloud_ROI_ptr, const std::vector<ZonePart>& parts,
-                         const Cloud::Ptr& no_ground_ptr, const Cloud::Ptr& ground_ptr) {
-  std::vector<Cloud::Ptr> ground_part, upper_part;
-  getCloudPartsZSplit(ctx, cloud_ROI_ptr, parts, ctx.params().roi_z_max, ground_part, upper_part);
-  std::vector<const Cloud*> in;
-  for (const Cloud::Ptr& g : ground_part) in.push_back(g.get());
-  std::vector<Cloud> ground, rest;
-  ctx.plane_ransac_multi(in, ground, rest);
-  std::vector<const Cloud*> rest_in;
-  for (const Cloud& r : rest) rest_in.push_back(&r);
-  std::vector<Cloud> kept;  // outlierRemoval(no_ground_cloud_ptr) of every zone, one pass
-  ctx.radius_outlier_multi(rest_in, kept, static_cast<double>(ctx.params().radius), static_cast<int>(ctx.params().min_neighbor));
-  Cloud no_ground_all, ground_all;
-  for (size_t k = 0; k < parts.size(); ++k) {
-    Cloud ng = kept[k];
-    ng += *upper_part[k];
-    if (k == 0) { no_ground_all = ng; ground_all = ground[k]; }
-    else { no_ground_all += ng; ground_all += ground[k]; }
+// proceedFront / proceedRear / proceedTop / proceedLivox after getROI -- :228-312, :428-446, :474-497: per zone getCloudPart +
+// removeGround, results appended zone after zone, `plain` x windows appended to the no-ground cloud unchanged. ONE library
+// call (cm_proceed_zones): one zone-slicing pass for all x and z windows, one multi-cloud RANSAC pass for all ground windows,
+// one multi-cloud outlierRemoval pass for what is not ground, the appends -- device-resident in between.
+inline cm_proceed_cfg_t proceedConfig(const Params& p, const std::vector<ZonePart>& parts, const std::vector<ZonePart>& plain) {
+  cm_proceed_cfg_t cfg;
+  std::memset(&cfg, 0, sizeof(cfg));
+  for (const ZonePart& pt : parts) {
+    if (cfg.n_parts >= CM_MAX_PROCEED_PARTS) break;
+    cfg.part[cfg.n_parts++] = cm_proceed_part_t{pt.length, pt.deviation, pt.z_max_ground, 1};
   }
-  *no_ground_ptr = no_ground_all;
-  *ground_ptr = ground_all;
+  for (const ZonePart& pt : plain) {
+    if (cfg.n_parts >= CM_MAX_PROCEED_PARTS) break;
+    cfg.part[cfg.n_parts++] = cm_proceed_part_t{pt.length, pt.deviation, 0.0f, 0};
+  }
+  cfg.roi_z_max = p.roi_z_max;
+  cfg.radius = static_cast<double>(p.radius);
+  cfg.min_neighbors = static_cast<int>(p.min_neighbor);
+  cfg.plane.distance_threshold = static_cast<double>(p.distance_threshold);
+  cfg.plane.probability = static_cast<double>(p.prob);
+  cfg.plane.max_iterations = p.max_iterations;
+  cfg.plane.optimize = 1;
+  cfg.plane.seed = 12345u;
+  cfg.plane.sum_order = p.sum_order;
+  return cfg;
+}
+inline void proceedZones(Context& ctx, const Cloud::Ptr& cloud_ROI_ptr, const std::vector<ZonePart>& parts,
+                         const Cloud::Ptr& no_ground_ptr, const Cloud::Ptr& ground_ptr,
+                         const std::vector<ZonePart>& plain = std::vector<ZonePart>()) {
+  const cm_proceed_cfg_t cfg = proceedConfig(ctx.params(), parts, plain);
+  Cloud ng, g;
+  ctx.proceed(*cloud_ROI_ptr, cfg, ng, g);
+  *no_ground_ptr = ng;
+  *ground_ptr = g;
 }
 
 // ---- the zone tables of the four sensor groups (pc_preprocessing_main.cpp:228-312, :428-446, :474-497; Parameter.h:45-81) ----
@@ -632,12 +680,7 @@ inline void proceedTable(Context& ctx, const Cloud::Ptr& cloud_ptr, const Procee
                          const Cloud::Ptr& ground_ptr) {
   Cloud::Ptr cloud_ROI_ptr(new Cloud);
   getROI(ctx, cloud_ptr, cloud_ROI_ptr);
-  proceedZones(ctx, cloud_ROI_ptr, table.parts, no_ground_ptr, ground_ptr);
-  for (const ZonePart& pl : table.plain) {
-    Cloud::Ptr part(new Cloud);
-    getCloudPart(ctx, cloud_ROI_ptr, part, pl.length, pl.deviation);
-    *no_ground_ptr += *part;
-  }
+  proceedZones(ctx, cloud_ROI_ptr, table.parts, no_ground_ptr, ground_ptr, table.plain);
 }
 inline void proceedFront(Context& ctx, const Cloud::Ptr& c, const Cloud::Ptr& ng, const Cloud::Ptr& g) { proceedTable(ctx, c, frontTable(ctx.params()), ng, g); }
 inline void proceedRear(Context& ctx, const Cloud::Ptr& c, const Cloud::Ptr& ng, const Cloud::Ptr& g) { proceedTable(ctx, c, rearTable(ctx.params()), ng, g); }
@@ -849,6 +892,167 @@ class FusedFrame {
   int64_t cap_;
   cm_handle_t h_ = nullptr;
   std::vector<float> sx_;
+};
+
+// ---- one whole main-loop iteration of pcl_preprocessing, device-resident ----------------------------------------------------
+// Replaces callbackX (transformPointCloud + proceedX: getROI, zones, removeGround per zone) -> globals + flags ->
+// fusePointclouds -> voxelgrid -> the three published clouds (pc_preprocessing_main.cpp:318-508, :228-312, :131-177, :574-578).
+// Each sensor has its own lane (handle + CUDA stream), so the six callbacks run concurrently like the reference's on
+// ros::AsyncSpinner(6); a lane keeps the sensor's (no_ground, ground) clouds IN DEVICE MEMORY the way the reference keeps them
+// in its globals: stored when the sensor's flag is clear (`if (!flag_x)`, :330), appended by every fusion -- also when stale or
+// still empty, which is what happens to the optional top sensor there (:134-149) --, flags cleared by the fusion.
+class PreprocessingFrame {
+ public:
+  // tables[s]: the zone table of sensor s (frontTable / rearTable / topTable / livoxTable)
+  PreprocessingFrame(const std::vector<ProceedTable>& tables, int64_t max_points_per_sensor, uint64_t required_mask, int device = 0,
+                     Params p = Params())
+      : params_(p), required_(required_mask), cap_(max_points_per_sensor) {
+    const int S = static_cast<int>(tables.size());
+    lanes_.resize(static_cast<size_t>(S));
+    ok_ = S > 0 && S <= 64;
+    for (int s = 0; s < S && ok_; ++s) {
+      Lane& l = *(lanes_[static_cast<size_t>(s)] = std::unique_ptr<Lane>(new Lane));
+      cm_config_t cfg;
+      std::memset(&cfg, 0, sizeof(cfg));
+      cfg.device = device; cfg.max_sensors = 1; cfg.max_points_per_sensor = max_points_per_sensor; cfg.max_point_step = 32;
+      cfg.max_batch_points = max_points_per_sensor; cfg.max_batch_frames = CM_MAX_PROCEED_PARTS; cfg.out_point_step = 32;
+      ok_ = cm_create(&cfg, &l.h) == CM_OK;
+      if (!ok_) { l.h = nullptr; break; }
+      const cm_pass_t passes[3] = {{2, p.roi_z_min, p.roi_z_max, 0}, {1, -p.roi_width / 2, p.roi_width / 2, 0},
+                                   {0, -p.roi_mid, p.roi_length - p.roi_mid, 0}};
+      ok_ = cm_set_crop(l.h, 3, passes) == CM_OK && cm_stream_create(l.h, &l.stream) == CM_OK &&
+            cm_dev_alloc(l.h, &l.raw, static_cast<size_t>(max_points_per_sensor) * 32 + 64) == CM_OK;
+      l.cfg = proceedConfig(p, tables[static_cast<size_t>(s)].parts, tables[static_cast<size_t>(s)].plain);
+    }
+    if (ok_) {
+      cm_config_t cfg;
+      std::memset(&cfg, 0, sizeof(cfg));
+      cfg.device = device; cfg.max_sensors = 1; cfg.max_points_per_sensor = 2 * max_points_per_sensor * S; cfg.max_point_step = 32;
+      cfg.max_batch_points = 2 * max_points_per_sensor * S; cfg.max_batch_frames = 1; cfg.out_point_step = 32;
+      ok_ = cm_create(&cfg, &voxel_) == CM_OK;
+      if (!ok_) voxel_ = nullptr;
+      const float leaf[3] = {p.voxel_size, p.voxel_size, p.voxel_size};
+      const size_t bytes = static_cast<size_t>(2 * max_points_per_sensor * S) * 16 + 64;
+      ok_ = ok_ && cm_set_voxel(voxel_, leaf, p.points_per_voxel, 1) == CM_OK && cm_dev_alloc(voxel_, &fused_ng_, bytes) == CM_OK &&
+            cm_dev_alloc(voxel_, &fused_g_, bytes) == CM_OK;
+    }
+  }
+  ~PreprocessingFrame() {
+    for (auto& lp : lanes_) {
+      if (!lp || !lp->h) continue;
+      if (lp->stream) cm_stream_destroy(lp->h, lp->stream);
+      if (lp->raw) cm_dev_free(lp->h, lp->raw);
+      cm_destroy(lp->h);
+    }
+    if (voxel_) {
+      if (fused_ng_) cm_dev_free(voxel_, fused_ng_);
+      if (fused_g_) cm_dev_free(voxel_, fused_g_);
+      cm_destroy(voxel_);
+    }
+  }
+  PreprocessingFrame(const PreprocessingFrame&) = delete;
+  PreprocessingFrame& operator=(const PreprocessingFrame&) = delete;
+  bool ok() const { return ok_; }
+
+  void setTransform(int sensor, const Transform& tf) {
+    if (ok_ && sensor >= 0 && sensor < static_cast<int>(lanes_.size())) cm_set_extrinsic_tf(lanes_[static_cast<size_t>(sensor)]->h, 0, tf.q, tf.origin);
+  }
+
+  // body of callbackFrontRight ... callbackFrontMiddle: transform, proceedX, hand-off. One thread per sensor at a time.
+  bool onCloud(int sensor, const Cloud& input) {
+    if (!ok_ || sensor < 0 || sensor >= static_cast<int>(lanes_.size())) return false;
+    Lane& l = *lanes_[static_cast<size_t>(sensor)];
+    std::lock_guard<std::mutex> lk(l.mu);
+    // `if (!flag_x) { store; flag_x = true; }`: the reference computes first and drops afterwards; skipping the work is the
+    // same observable behaviour
+    if (seen_.load(std::memory_order_acquire) & (1ull << sensor)) return true;
+    const int64_t n = static_cast<int64_t>(input.points.size());
+    if (n > cap_) return false;
+    if (n && cm_memcpy_h2d(l.h, l.raw, input.points.data(), static_cast<size_t>(n) * 32, l.stream) != CM_OK) return false;
+    cm_segment_t seg;
+    seg.data = l.raw; seg.n_points = n; seg.layout = pcl_layout(input.is_dense); seg.sensor = 0; seg.frame = 0;
+    cm_stats_t st;
+    cm_device_out_t o;
+    if (cm_dev_transform_crop(l.h, &seg, 1, l.stream) != CM_OK || cm_get_stats(l.h, &st) != CM_OK || cm_get_device_out(l.h, &o) != CM_OK)
+      return false;
+    cm_proceed_out_t po;
+    if (cm_dev_proceed_zones(l.h, o.survivor_xyzi, st.survivors, &l.cfg, &po, l.stream) != CM_OK) return false;
+    if (cm_stream_sync(l.h, l.stream) != CM_OK) return false;
+    l.out = po;
+    l.stamp = stamp_of(input);
+    seen_.fetch_or(1ull << sensor, std::memory_order_release);
+    return true;
+  }
+
+  bool ready() const { return (seen_.load(std::memory_order_acquire) & required_) == required_; }
+
+  // fusePointclouds + voxelgrid + what publishPointcloud is handed: /points_no_ground, /points_ground, /points_voxel
+  bool fuseAndVoxel(Cloud& no_ground, Cloud& ground, Cloud& voxel) {
+    if (!ok_ || !ready()) return false;
+    int64_t n_ng = 0, n_g = 0;
+    uint64_t stamp = 0;
+    for (auto& lp : lanes_) {  // sensor order; every lane's STORED clouds, fresh or not (the reference's globals)
+      Lane& l = *lp;
+      std::lock_guard<std::mutex> lk(l.mu);
+      if (l.out.n_no_ground && cm_memcpy_d2d(voxel_, static_cast<char*>(fused_ng_) + n_ng * 16, l.out.no_ground_xyzi,
+                                             static_cast<size_t>(l.out.n_no_ground) * 16, nullptr) != CM_OK) return false;
+      if (l.out.n_ground && cm_memcpy_d2d(voxel_, static_cast<char*>(fused_g_) + n_g * 16, l.out.ground_xyzi,
+                                          static_cast<size_t>(l.out.n_ground) * 16, nullptr) != CM_OK) return false;
+      if (cm_stream_sync(voxel_, nullptr) != CM_OK) return false;  // the lane may be overwritten once its lock is released
+      n_ng += l.out.n_no_ground; n_g += l.out.n_ground;
+      if (l.stamp > stamp) stamp = l.stamp;
+    }
+    seen_.store(0, std::memory_order_release);
+    cm_stats_t st;
+    cm_device_out_t o;
+    if (cm_dev_voxelgrid(voxel_, static_cast<const float*>(fused_ng_), n_ng, 1, nullptr) != CM_OK || cm_get_stats(voxel_, &st) != CM_OK ||
+        cm_get_device_out(voxel_, &o) != CM_OK)
+      return false;
+    auto fetch = [&](Cloud& c, const void* dev, int64_t n) {
+      buf_.resize(static_cast<size_t>(n) * 4 + 4);
+      if (n && cm_memcpy_d2h(voxel_, buf_.data(), dev, static_cast<size_t>(n) * 16, nullptr) != CM_OK) return false;
+      c.points.resize(static_cast<size_t>(n));
+      for (int64_t i = 0; i < n; ++i) {
+        PointXYZI& p = c.points[static_cast<size_t>(i)];
+        p = PointXYZI();
+        p.x = buf_[i * 4 + 0]; p.y = buf_[i * 4 + 1]; p.z = buf_[i * 4 + 2]; p.intensity = buf_[i * 4 + 3];
+      }
+      return true;
+    };
+    if (!fetch(no_ground, fused_ng_, n_ng) || !fetch(ground, fused_g_, n_g)) return false;
+    if (st.pcl_overflow) {
+      voxel = no_ground;  // PCL 1.8.1: leaf too small -> output = input
+    } else {
+      voxel.points.resize(static_cast<size_t>(st.voxels_out));
+      if (st.voxels_out && cm_memcpy_d2h(voxel_, voxel.points.data(), o.voxel_xyzi, static_cast<size_t>(st.voxels_out) * 32, nullptr) != CM_OK)
+        return false;
+    }
+    for (Cloud* c : {&no_ground, &ground, &voxel}) {
+      c->width = static_cast<uint32_t>(c->points.size()); c->height = 1; c->is_dense = true; set_stamp(*c, stamp);
+    }
+    return true;
+  }
+
+ private:
+  struct Lane {
+    cm_handle_t h = nullptr;
+    void* stream = nullptr;
+    void* raw = nullptr;
+    cm_proceed_cfg_t cfg;
+    cm_proceed_out_t out;
+    uint64_t stamp = 0;
+    std::mutex mu;
+    Lane() { std::memset(&cfg, 0, sizeof(cfg)); std::memset(&out, 0, sizeof(out)); }
+  };
+  Params params_;
+  uint64_t required_;
+  std::atomic<uint64_t> seen_{0};
+  int64_t cap_;
+  bool ok_ = false;
+  std::vector<std::unique_ptr<Lane>> lanes_;
+  cm_handle_t voxel_ = nullptr;
+  void *fused_ng_ = nullptr, *fused_g_ = nullptr;
+  std::vector<float> buf_;
 };
 
 }  // namespace cloud_merger

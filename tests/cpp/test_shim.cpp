@@ -8,6 +8,7 @@
 #include <cstdio>
 #include <cstring>
 #include <limits>
+#include <thread>
 #include <vector>
 
 #include "cloud_merger_shim.hpp"
@@ -447,6 +448,71 @@ int main() {
 #else
     CHECK(false, "the wire adapters were not compiled (mock ROS / Eigen headers missing from the include path)");
 #endif
+  }
+  // ---- one whole main-loop iteration of pcl_preprocessing, device-resident, callbacks on their own threads ---------------------
+  {
+    const std::vector<ProceedTable> tables = {frontTable(prm), livoxTable(prm), topTable(prm)};
+    PreprocessingFrame pf(tables, 1 << 16, /*required*/ 0b011);
+    CHECK(pf.ok(), "PreprocessingFrame");
+    for (int s = 0; s < S; ++s) pf.setTransform(s, tf[s]);
+    Cloud ng, g, vx;
+    CHECK(!pf.fuseAndVoxel(ng, g, vx), "fuse must wait for the required sensors");
+    auto oracle_node = [&](const std::vector<const Cloud*>& in, std::vector<float>& want_ng, std::vector<float>& want_g) {
+      want_ng.clear(); want_g.clear();
+      for (int s = 0; s < S; ++s) {
+        if (!in[static_cast<size_t>(s)]) continue;
+        float m12[12];
+        cmo_tf_to_matrix(tf[s].q, tf[s].origin, m12);
+        const Cloud& c = *in[static_cast<size_t>(s)];
+        std::vector<float> pk = packed(c), tr(pk.size());
+        cmo_transform(pk.data(), static_cast<int64_t>(c.points.size()), m12, c.is_dense ? 1 : 0, tr.data());
+        const std::vector<float> roi_o = oracle_passes(tr, roi);
+        std::vector<float> a, b;
+        oracle_proceed(roi_o, tables[static_cast<size_t>(s)].parts, prm, a, b);
+        for (const ZonePart& pl : tables[static_cast<size_t>(s)].plain) {
+          const std::vector<float> part_plain = oracle_passes(roi_o, {{0, pl.deviation, pl.deviation + pl.length, 0}});
+          b.insert(b.end(), part_plain.begin(), part_plain.end());
+        }
+        want_g.insert(want_g.end(), a.begin(), a.end());
+        want_ng.insert(want_ng.end(), b.begin(), b.end());
+      }
+    };
+    auto check_frame = [&](const std::vector<const Cloud*>& in, const char* what) {
+      std::vector<float> want_ng, want_g;
+      oracle_node(in, want_ng, want_g);
+      expect_cloud(ng, want_ng, want_ng.size() / 4, what);
+      expect_cloud(g, want_g, want_g.size() / 4, what);
+      const int64_t m = static_cast<int64_t>(want_ng.size() / 4);
+      const float leaf[3] = {prm.voxel_size, prm.voxel_size, prm.voxel_size};
+      std::vector<float> cen(static_cast<size_t>(m) * 4 + 4);
+      int32_t flags = 0;
+      const int64_t v = cmo_voxelgrid(want_ng.data(), m, 1, leaf, prm.points_per_voxel, 1, 0, cen.data(), nullptr, nullptr, nullptr,
+                                      nullptr, nullptr, nullptr, &flags);
+      expect_cloud(vx, cen, static_cast<size_t>(v), what);
+      CHECK(v > 50 && want_g.size() > 400, "%s: non-trivial frame", what);
+    };
+    // frame 1: the two required sensors only (the optional one has never delivered: its stored clouds are empty)
+    {
+      std::thread t0([&] { pf.onCloud(0, raw[0]); }), t1([&] { pf.onCloud(1, raw[1]); });
+      t0.join(); t1.join();
+    }
+    CHECK(pf.fuseAndVoxel(ng, g, vx), "PreprocessingFrame frame 1");
+    check_frame({&raw[0], &raw[1], nullptr}, "node frame 1");
+    // frame 2: all three from their own threads; sensor 0 delivers twice -- the first cloud after the fusion wins (:330)
+    Cloud other = make_cloud(30000, false, 500);
+    {
+      pf.onCloud(0, raw[0]);
+      std::thread t0([&] { pf.onCloud(0, other); }), t1([&] { pf.onCloud(1, raw[1]); }), t2([&] { pf.onCloud(2, raw[2]); });
+      t0.join(); t1.join(); t2.join();
+    }
+    CHECK(pf.fuseAndVoxel(ng, g, vx), "PreprocessingFrame frame 2");
+    check_frame({&raw[0], &raw[1], &raw[2]}, "node frame 2");
+    // frame 3: the optional sensor stays silent -- its STORED clouds are appended again, as the reference's globals are
+    pf.onCloud(0, other);
+    pf.onCloud(1, raw[1]);
+    CHECK(pf.fuseAndVoxel(ng, g, vx), "PreprocessingFrame frame 3");
+    check_frame({&other, &raw[1], &raw[2]}, "node frame 3 (stale optional sensor)");
+    CHECK(stamp_of(vx) == 500, "newest stamp");
   }
   std::printf("%s: %d failure(s)\n", g_fail ? "FAILED" : "shim ok", g_fail);
   return g_fail ? 1 : 0;
