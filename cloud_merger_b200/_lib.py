@@ -48,6 +48,16 @@ CM_SUM4_SSE2, CM_SUM4_SSE3, CM_SUM4_SCALAR = 0, 1, 2
 CM_MAX_PROCEED_PARTS = 8
 
 
+CM_GIANT_ID_BYTES = 128
+
+
+class CmGiantInfo(C.Structure):
+    _fields_ = [("points_local", C.c_int64), ("points_received", C.c_int64), ("points_sent_away", C.c_int64),
+                ("points_total_finite", C.c_int64), ("voxels_local", C.c_int64), ("splitter", C.c_uint64 * CM_MAX_ZONES),
+                ("min_p", C.c_float * 3), ("max_p", C.c_float * 3), ("min_b", C.c_int32 * 3), ("div_b", C.c_int32 * 3),
+                ("key_bits", C.c_int32), ("host_syncs", C.c_int32), ("send_begin", C.c_int64 * (CM_MAX_ZONES + 1))]
+
+
 class CmProceedPart(C.Structure):
     _fields_ = [("length", C.c_float), ("deviation", C.c_float), ("z_max_ground", C.c_float), ("ground_removal", C.c_int32)]
 
@@ -177,6 +187,11 @@ SYMBOLS = {
                                        C.c_void_p, C.POINTER(C.c_uint64), C.c_void_p]),
     "cm_dev_route_by_key": (C.c_int, [_H, C.c_void_p, C.c_int64, C.POINTER(C.c_float), C.POINTER(C.c_float),
                                       C.POINTER(C.c_uint64), C.c_int, C.c_int, C.c_void_p]),
+    "cm_giant_unique_id": (C.c_int, [C.c_void_p]),
+    "cm_giant_create": (C.c_int, [_H, C.c_int, C.c_int, C.c_void_p, C.POINTER(C.c_void_p)]),
+    "cm_giant_destroy": (C.c_int, [C.c_void_p]),
+    "cm_giant_voxelgrid": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.POINTER(CmGiantInfo), C.c_void_p]),
+    "cm_giant_last_error": (C.c_char_p, [C.c_void_p]),
     "cm_sync": (C.c_int, [_H]),
     "cm_get_stats": (C.c_int, [_H, C.POINTER(CmStats)]),
     "cm_get_device_out": (C.c_int, [_H, C.POINTER(CmDeviceOut)]),

@@ -671,6 +671,49 @@ class CloudMerger:
         return res
 
 
+def giant_unique_id() -> bytes:
+    """ncclGetUniqueId through the C ABI (rank 0 calls it and ships the 128 bytes to every rank)."""
+    lib = _lib.load()
+    buf = C.create_string_buffer(_lib.CM_GIANT_ID_BYTES)
+    rc = lib.cm_giant_unique_id(buf)
+    if rc != _lib.CM_OK:
+        raise CloudMergerError(rc, "cm_giant_unique_id (is libnccl.so.2 loadable?)")
+    return buf.raw
+
+
+class GiantCloud:
+    """BASELINE config 4 behind the C ABI (cm_giant_*): VoxelGrid of one cloud block-distributed over the GPUs of a box --
+    C++ + NCCL inside the library (bounding-box and histogram all-reduces, device-side splitters, one all-to-all, local
+    VoxelGrid). nccl_id=None with world > 1 gives a dry object that stops after the grouping (single-GPU tests)."""
+
+    def __init__(self, merger: CloudMerger, rank: int, world: int, nccl_id: Optional[bytes] = None):
+        self.m = merger
+        self.rank, self.world = rank, world
+        self._g = C.c_void_p()
+        idp = C.create_string_buffer(nccl_id, _lib.CM_GIANT_ID_BYTES) if nccl_id is not None else None
+        merger._check(merger._lib.cm_giant_create(merger._h, rank, world, idp, C.byref(self._g)))
+
+    def close(self):
+        if self._g:
+            self.m._lib.cm_giant_destroy(self._g)
+            self._g = None
+
+    def voxelgrid(self, xyzi_ptr: int, n_local: int, stream: int = 0) -> dict:
+        """Enqueues the whole partitioned VoxelGrid of this rank's block; the voxels are fetched like any other run's
+        (merger.stats() / device_out())."""
+        info = _lib.CmGiantInfo()
+        rc = self.m._lib.cm_giant_voxelgrid(self._g, C.c_void_p(xyzi_ptr or None), C.c_int64(n_local), C.byref(info),
+                                            C.c_void_p(stream or None))
+        if rc != _lib.CM_OK:
+            raise CloudMergerError(rc, self.m._lib.cm_giant_last_error(self._g).decode())
+        w = self.world
+        return {"points_received": int(info.points_received), "points_sent_away": int(info.points_sent_away),
+                "points_total_finite": int(info.points_total_finite), "splitters": [int(info.splitter[r]) for r in range(w - 1)],
+                "min_p": np.array(info.min_p, np.float32), "max_p": np.array(info.max_p, np.float32),
+                "min_b": np.array(info.min_b, np.int64), "div_b": np.array(info.div_b, np.int64), "key_bits": int(info.key_bits),
+                "host_syncs": int(info.host_syncs), "send_begin": [int(info.send_begin[r]) for r in range(w + 1)]}
+
+
 def host_alloc(nbytes: int) -> Tuple[np.ndarray, int]:
     """Page-locked host memory as a uint8 numpy array (cm_host_alloc). Returns (array, address); never freed by GC."""
     lib = _lib.load()

@@ -5,11 +5,14 @@
 //     memset(control block) -> K1 transform_crop -> grid_setup -> key_hist -> P x onesweep pass -> centroid
 // There is no CPU implementation behind any entry point: without a CUDA device cm_create fails.
 #include <cuda_runtime.h>
+#include <dlfcn.h>
+#include <nccl.h>  // types only: the library is loaded at run time (cm_giant_*), see NcclApi
 
 #include <algorithm>
 #include <chrono>
 #include <cmath>
 #include <cstdarg>
+#include <cstddef>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -375,11 +378,12 @@ void fill_voxel_params(cm_handle_t h, Workspace& w, VoxelParams& vp, const float
 
 // VoxelGrid stages on vp.pts. bounded: the crop box bounds the key width, so no device round trip is needed.
 int run_voxel(cm_handle_t h, Workspace& w, VoxelParams& vp, cudaStream_t st, bool scan_k1_tiles = false,
-              bool with_centroid = true) {
+              bool with_centroid = true, int known_idx_bits = -1) {
   unsigned long long cells = 0;
-  const bool bounded = w.ran_k1 && crop_cell_bound(h, &cells);
+  // known_idx_bits: the caller already knows an upper bound of the voxel-index width (giant-cloud mode: from the global grid)
+  const bool bounded = known_idx_bits >= 0 || (w.ran_k1 && crop_cell_bound(h, &cells));
   if (bounded) {
-    const uint32_t bits = bits_for(cells) + bits_for(vp.n_frames);
+    const uint32_t bits = (known_idx_bits >= 0 ? (uint32_t)known_idx_bits : bits_for(cells)) + bits_for(vp.n_frames);
     vp.key_bytes = bits <= 32 ? 4 : 8;
     vp.max_passes = std::max<uint32_t>(1, (bits + CM_RADIX_BITS - 1) / CM_RADIX_BITS);
   } else {
@@ -1257,21 +1261,19 @@ int cm_dev_transform_crop(cm_handle_t h, const cm_segment_t* segments, int n_seg
   return run_pipeline(h, h->batch, segments, n_segments, static_cast<cudaStream_t>(stream), false);
 }
 
-int cm_dev_voxelgrid(cm_handle_t h, const float* xyzi_dev, int64_t n_points, int is_dense, void* stream) {
-  (void)is_dense;  // non-finite points are skipped either way (PCL skips them when !is_dense; undefined otherwise)
-  if (!h) return CM_E_INVALID;
-  std::lock_guard<std::mutex> lk(h->mu);
-  CM_CUDA(h, cudaSetDevice(h->device));
+namespace {
+// VoxelGrid of n packed points on the batch workspace. seed_enc_dev: device-resident bounds (GiantPlan::enc) folded into the
+// local box; known_idx_bits >= 0: the key plan is known on the host, no device round trip.
+int voxelgrid_run(cm_handle_t h, const float4* pts, int64_t n_points, cudaStream_t st, const uint32_t* seed_enc_dev = nullptr,
+                  int known_idx_bits = -1) {
   int rc = ensure_batch_ws(h);
   if (rc != CM_OK) return rc;
   Workspace& w = h->batch;
   if (n_points < 0 || n_points > (int64_t)w.cap_points) return fail(h, CM_E_CAPACITY, "%lld points > capacity %u", (long long)n_points, w.cap_points);
-  if (n_points > 0 && (!xyzi_dev || (reinterpret_cast<uintptr_t>(xyzi_dev) & 15u))) return fail(h, CM_E_INVALID, "xyzi_dev must be 16-byte aligned");
-  cudaStream_t st = static_cast<cudaStream_t>(stream);
   w.has_run = true; w.report_valid = false; w.profiled = h->profiling;
   w.n_frames = 1; w.n_segs = 0; w.points_in = n_points; w.launches = 0;
   w.ran_k1 = false; w.ran_voxel = false; w.stream = st; w.n_k1_tiles = 0; w.dense_valid = false;
-  w.voxel_pts = reinterpret_cast<const float4*>(xyzi_dev);
+  w.voxel_pts = pts;
   h->last = &w;
   CM_CUDA(h, cudaEventRecord(w.ev[EV_START], st));
   CM_CUDA(h, cudaMemsetAsync(w.meta, 0, w.ml.zero_bytes, st));
@@ -1279,12 +1281,25 @@ int cm_dev_voxelgrid(cm_handle_t h, const float* xyzi_dev, int64_t n_points, int
   fill_voxel_params(h, w, vp, w.voxel_pts, 1, (uint32_t)n_points);
   CM_CUDA(h, launch_minmax(w.voxel_pts, (uint32_t)n_points, vp.ctrl, vp.acc, const_cast<uint32_t*>(vp.frame_surv_start), st));
   ++w.launches;
-  if (h->have_bounds) {
+  if (seed_enc_dev) {
+    CM_CUDA(h, launch_seed_bounds_enc(vp.acc, seed_enc_dev, st));
+    ++w.launches;
+  } else if (h->have_bounds) {
     CM_CUDA(h, launch_seed_bounds(vp.acc, h->bounds_min, h->bounds_max, st));
     ++w.launches;
   }
   CM_CUDA(h, cudaEventRecord(w.ev[EV_K1], st));
-  return run_voxel(h, w, vp, st);
+  return run_voxel(h, w, vp, st, false, true, known_idx_bits);
+}
+}  // namespace
+
+int cm_dev_voxelgrid(cm_handle_t h, const float* xyzi_dev, int64_t n_points, int is_dense, void* stream) {
+  (void)is_dense;  // non-finite points are skipped either way (PCL skips them when !is_dense; undefined otherwise)
+  if (!h) return CM_E_INVALID;
+  std::lock_guard<std::mutex> lk(h->mu);
+  CM_CUDA(h, cudaSetDevice(h->device));
+  if (n_points > 0 && (!xyzi_dev || (reinterpret_cast<uintptr_t>(xyzi_dev) & 15u))) return fail(h, CM_E_INVALID, "xyzi_dev must be 16-byte aligned");
+  return voxelgrid_run(h, reinterpret_cast<const float4*>(xyzi_dev), n_points, static_cast<cudaStream_t>(stream));
 }
 
 // ---- zone slicing ---------------------------------------------------------------------------------------------------------
@@ -2283,6 +2298,247 @@ int cm_proceed_zones(cm_handle_t h, const float* roi_xyzi_host, int64_t n_points
   if (out_ground && po.n_ground) CM_CUDA(h, cudaMemcpyAsync(out_ground, po.ground_xyzi, (size_t)po.n_ground * 16, cudaMemcpyDeviceToHost, nullptr));
   CM_CUDA(h, cudaStreamSynchronize(nullptr));
   return CM_OK;
+}
+
+// ---- giant-cloud mode behind one call: C++ + NCCL ----------------------------------------------------------------------------
+namespace {
+// NCCL entry points resolved at run time: libcloud_merger_gpu.so carries no link-time dependency on libnccl, so a process that
+// never uses the giant-cloud mode does not need it, and a process that already holds a libnccl.so.2 (PyTorch ships its own)
+// keeps using that one copy.
+struct NcclApi {
+  void* lib = nullptr;
+  ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+  ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+  ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+  ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*Send)(const void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*Recv)(void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*GroupStart)() = nullptr;
+  ncclResult_t (*GroupEnd)() = nullptr;
+  const char* (*GetErrorString)(ncclResult_t) = nullptr;
+  std::string why;
+};
+NcclApi* nccl_api() {
+  static NcclApi api;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    api.lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_NOLOAD);           // the copy the process already has, if any
+    if (!api.lib) api.lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+    if (!api.lib) api.lib = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+    if (!api.lib) { api.why = std::string("libnccl.so.2 not found: ") + (dlerror() ? dlerror() : ""); return; }
+    bool ok = true;
+    auto sym = [&](const char* name) { void* p = dlsym(api.lib, name); if (!p) { ok = false; api.why = std::string("missing NCCL symbol ") + name; } return p; };
+    api.GetUniqueId = reinterpret_cast<decltype(api.GetUniqueId)>(sym("ncclGetUniqueId"));
+    api.CommInitRank = reinterpret_cast<decltype(api.CommInitRank)>(sym("ncclCommInitRank"));
+    api.CommDestroy = reinterpret_cast<decltype(api.CommDestroy)>(sym("ncclCommDestroy"));
+    api.AllReduce = reinterpret_cast<decltype(api.AllReduce)>(sym("ncclAllReduce"));
+    api.AllGather = reinterpret_cast<decltype(api.AllGather)>(sym("ncclAllGather"));
+    api.Send = reinterpret_cast<decltype(api.Send)>(sym("ncclSend"));
+    api.Recv = reinterpret_cast<decltype(api.Recv)>(sym("ncclRecv"));
+    api.GroupStart = reinterpret_cast<decltype(api.GroupStart)>(sym("ncclGroupStart"));
+    api.GroupEnd = reinterpret_cast<decltype(api.GroupEnd)>(sym("ncclGroupEnd"));
+    api.GetErrorString = reinterpret_cast<decltype(api.GetErrorString)>(sym("ncclGetErrorString"));
+    if (!ok) api.lib = nullptr;
+  });
+  return api.lib ? &api : nullptr;
+}
+static_assert(sizeof(ncclUniqueId) == CM_GIANT_ID_BYTES, "ncclUniqueId is 128 bytes");
+}  // namespace
+
+struct cm_giant_s {
+  cm_handle_t h = nullptr;
+  int rank = 0, world = 1;
+  ncclComm_t comm = nullptr;
+  NcclApi* api = nullptr;
+  uint32_t bins = 1u << 14;
+  GiantPlan* plan = nullptr;            // device
+  unsigned long long* hist = nullptr;   // device [bins]
+  uint32_t* counts = nullptr;           // device [world][CM_MAX_ZONES + 2]: every rank's zone_begin
+  float4* recv = nullptr;               // device [recv_cap]: what the all-to-all delivers
+  size_t recv_cap = 0;
+  GiantPlan* plan_pin = nullptr;        // pinned mirrors
+  uint32_t* counts_pin = nullptr;
+  std::string err;
+};
+
+namespace {
+int gfail(cm_giant_t g, int code, const char* fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  g->err = buf;
+  if (g->h) g->h->last_error = buf;
+  return code;
+}
+#define CM_G_CUDA(g, expr)                                                                                  \
+  do {                                                                                                      \
+    cudaError_t e__ = (expr);                                                                               \
+    if (e__ != cudaSuccess) return gfail(g, CM_E_CUDA, "%s: %s (%s:%d)", #expr, cudaGetErrorString(e__), __FILE__, __LINE__); \
+  } while (0)
+#define CM_G_NCCL(g, expr)                                                                                  \
+  do {                                                                                                      \
+    ncclResult_t r__ = (expr);                                                                              \
+    if (r__ != ncclSuccess) return gfail(g, CM_E_CUDA, "%s: NCCL %s (%s:%d)", #expr, (g)->api->GetErrorString(r__), __FILE__, __LINE__); \
+  } while (0)
+constexpr int kCountStride = CM_MAX_ZONES + 2;
+}  // namespace
+
+int cm_giant_unique_id(void* id_bytes) {
+  if (!id_bytes) return CM_E_INVALID;
+  NcclApi* api = nccl_api();
+  if (!api) return CM_E_CUDA;
+  ncclUniqueId id;
+  if (api->GetUniqueId(&id) != ncclSuccess) return CM_E_CUDA;
+  memcpy(id_bytes, &id, sizeof(id));
+  return CM_OK;
+}
+
+const char* cm_giant_last_error(cm_giant_t g) { return g ? g->err.c_str() : "null giant handle"; }
+
+int cm_giant_create(cm_handle_t h, int rank, int world, const void* nccl_id, cm_giant_t* out) {
+  if (!h || !out || world < 1 || world > CM_MAX_ZONES || rank < 0 || rank >= world) return CM_E_INVALID;
+  *out = nullptr;
+  std::lock_guard<std::mutex> lk(h->mu);
+  CM_CUDA(h, cudaSetDevice(h->device));
+  cm_giant_t g = new (std::nothrow) cm_giant_s();
+  if (!g) return CM_E_INTERNAL;
+  g->h = h; g->rank = rank; g->world = world;
+  auto bail = [&](int code) { cudaFree(g->plan); cudaFree(g->hist); cudaFree(g->counts); cudaFree(g->recv);
+                              if (g->plan_pin) cudaFreeHost(g->plan_pin); if (g->counts_pin) cudaFreeHost(g->counts_pin);
+                              delete g; return code; };
+  if (world > 1 && nccl_id) {
+    g->api = nccl_api();
+    if (!g->api) { h->last_error = "NCCL unavailable"; return bail(CM_E_CUDA); }
+    ncclUniqueId id;
+    memcpy(&id, nccl_id, sizeof(id));
+    const ncclResult_t r = g->api->CommInitRank(&g->comm, world, id, rank);
+    if (r != ncclSuccess) { h->last_error = std::string("ncclCommInitRank: ") + g->api->GetErrorString(r); return bail(CM_E_CUDA); }
+  }
+  int rc = ensure_batch_ws(h);
+  if (rc != CM_OK) return bail(rc);
+  g->recv_cap = h->batch.cap_points;
+  if (cudaMalloc(reinterpret_cast<void**>(&g->plan), sizeof(GiantPlan)) != cudaSuccess ||
+      cudaMalloc(reinterpret_cast<void**>(&g->hist), sizeof(unsigned long long) * g->bins) != cudaSuccess ||
+      cudaMalloc(reinterpret_cast<void**>(&g->counts), sizeof(uint32_t) * kCountStride * world) != cudaSuccess ||
+      (world > 1 && g->comm && dev_alloc(&g->recv, g->recv_cap) != cudaSuccess) ||
+      cudaMallocHost(reinterpret_cast<void**>(&g->plan_pin), sizeof(GiantPlan)) != cudaSuccess ||
+      cudaMallocHost(reinterpret_cast<void**>(&g->counts_pin), sizeof(uint32_t) * kCountStride * world) != cudaSuccess) {
+    h->last_error = "cm_giant_create: allocation failed";
+    cudaGetLastError();
+    return bail(CM_E_CUDA);
+  }
+  *out = g;
+  return CM_OK;
+}
+
+int cm_giant_destroy(cm_giant_t g) {
+  if (!g) return CM_E_INVALID;
+  cudaSetDevice(g->h->device);
+  cudaDeviceSynchronize();
+  if (g->comm && g->api) g->api->CommDestroy(g->comm);
+  cudaFree(g->plan); cudaFree(g->hist); cudaFree(g->counts); cudaFree(g->recv);
+  if (g->plan_pin) cudaFreeHost(g->plan_pin);
+  if (g->counts_pin) cudaFreeHost(g->counts_pin);
+  delete g;
+  return CM_OK;
+}
+
+int cm_giant_voxelgrid(cm_giant_t g, const float* local_xyzi_dev, int64_t n_local, cm_giant_info_t* info, void* stream) {
+  if (!g || n_local < 0 || n_local > 0xFFFFFFF0ll) return CM_E_INVALID;
+  cm_handle_t h = g->h;
+  std::lock_guard<std::mutex> lk(h->mu);
+  CM_G_CUDA(g, cudaSetDevice(h->device));
+  if (n_local > 0 && (!local_xyzi_dev || (reinterpret_cast<uintptr_t>(local_xyzi_dev) & 15u))) return gfail(g, CM_E_INVALID, "local_xyzi_dev must be 16-byte aligned");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const float4* pts = reinterpret_cast<const float4*>(local_xyzi_dev);
+  const int W = g->world, me = g->rank;
+  int rc = ensure_batch_ws(h);
+  if (rc != CM_OK) return rc;
+  rc = zone_ws_ensure(h, (size_t)n_local);
+  if (rc != CM_OK) return rc;
+  Workspace& w = h->batch;
+  Ctrl* ctrl = reinterpret_cast<Ctrl*>(w.meta + w.ml.off_ctrl);
+  FrameAcc* acc = reinterpret_cast<FrameAcc*>(w.meta + w.ml.off_acc);
+  uint32_t* fss = reinterpret_cast<uint32_t*>(w.meta + w.ml.off_fstart);
+  cm_giant_info_t gi;
+  memset(&gi, 0, sizeof(gi));
+  gi.points_local = n_local;
+  // ---- global bounding box -> grid, on the device
+  CM_G_CUDA(g, cudaMemsetAsync(w.meta, 0, w.ml.zero_bytes, st));
+  CM_G_CUDA(g, launch_minmax(pts, (uint32_t)n_local, ctrl, acc, fss, st));
+  if (g->comm) CM_G_NCCL(g, g->api->AllReduce(acc, acc, 6, ncclUint32, ncclMax, g->comm, st));  // max_enc[3], nmin_enc[3]
+  CM_G_CUDA(g, launch_giant_plan(g->plan, acc, h->inv_leaf, g->bins, st));
+  // ---- balancing splitters from the all-reduced histogram of the voxel index, on the device
+  if (W > 1) {
+    CM_G_CUDA(g, cudaMemsetAsync(g->hist, 0, sizeof(unsigned long long) * g->bins, st));
+    CM_G_CUDA(g, launch_giant_hist(pts, (uint32_t)n_local, g->plan, g->bins, g->hist, st));
+    if (g->comm) CM_G_NCCL(g, g->api->AllReduce(g->hist, g->hist, g->bins, ncclUint64, ncclSum, g->comm, st));
+    CM_G_CUDA(g, launch_giant_splitters(g->plan, g->hist, g->bins, (uint32_t)W, st));
+    // ---- group the block by destination (source order kept inside a destination): the send buffer of the all-to-all
+    CM_G_CUDA(g, launch_giant_mask(pts, (uint32_t)n_local, g->plan, (uint32_t)W, (uint32_t)me, h->zw.mask, st));
+    rc = zone_run(h, pts, n_local, st, true, W);
+    if (rc != CM_OK) return rc;
+    // every rank's per-destination offsets (NCCL takes the counts of a send / recv as host arguments)
+    if (g->comm) CM_G_NCCL(g, g->api->AllGather(h->zw.zone_begin, g->counts, kCountStride, ncclUint32, g->comm, st));
+    else CM_G_CUDA(g, cudaMemcpyAsync(g->counts + (size_t)me * kCountStride, h->zw.zone_begin, sizeof(uint32_t) * kCountStride, cudaMemcpyDeviceToDevice, st));
+    CM_G_CUDA(g, cudaMemcpyAsync(g->counts_pin, g->counts, sizeof(uint32_t) * kCountStride * W, cudaMemcpyDeviceToHost, st));
+  }
+  CM_G_CUDA(g, cudaMemcpyAsync(g->plan_pin, g->plan, sizeof(GiantPlan), cudaMemcpyDeviceToHost, st));
+  CM_G_CUDA(g, cudaStreamSynchronize(st));
+  ++gi.host_syncs;
+  const GiantPlan& P = *g->plan_pin;
+  for (int k = 0; k < 3; ++k) {
+    const uint32_t hi = f32_order_dec(P.enc[k]), lo = f32_order_dec(~P.enc[3 + k]);
+    memcpy(&gi.max_p[k], &hi, 4); memcpy(&gi.min_p[k], &lo, 4);
+    gi.min_b[k] = P.min_b[k]; gi.div_b[k] = P.div_b[k];
+  }
+  gi.key_bits = (int32_t)P.key_bits;
+  gi.points_total_finite = (int64_t)P.total;
+  for (int r = 0; r + 1 < W; ++r) gi.splitter[r] = P.splitter[r];
+  if (P.error) return gfail(g, CM_E_KEY_RANGE, "the global voxel grid exceeds the key range (leaf too small for the extent)");
+  const float4* vox_in = pts;
+  int64_t n_vox = n_local;
+  if (W > 1) {
+    const uint32_t* mine = g->counts_pin + (size_t)me * kCountStride;
+    for (int r = 0; r <= W; ++r) gi.send_begin[r] = mine[r];
+    gi.points_sent_away = n_local - (int64_t)(mine[me + 1] - mine[me]);
+    if (!g->comm) {  // dry mode: the grouping is the result (cm_get_zone_out)
+      if (info) *info = gi;
+      return CM_OK;
+    }
+    int64_t roff[CM_MAX_ZONES + 1];
+    roff[0] = 0;
+    for (int s = 0; s < W; ++s) {
+      const uint32_t* row = g->counts_pin + (size_t)s * kCountStride;
+      roff[s + 1] = roff[s] + (int64_t)(row[me + 1] - row[me]);
+    }
+    gi.points_received = roff[W];
+    if ((size_t)roff[W] > g->recv_cap)
+      return gfail(g, CM_E_CAPACITY, "this rank receives %lld points, max_batch_points of the handle is %zu", (long long)roff[W], g->recv_cap);
+    // ---- ONE all-to-all, straight out of the grouped array
+    const float4* send = h->zw.out_xyzi;
+    CM_G_NCCL(g, g->api->GroupStart());
+    for (int r = 0; r < W; ++r) {
+      const size_t sc = (size_t)(mine[r + 1] - mine[r]), rcnt = (size_t)(roff[r + 1] - roff[r]);
+      if (r == me) continue;
+      if (sc) CM_G_NCCL(g, g->api->Send(send + mine[r], sc * 4, ncclFloat, r, g->comm, st));
+      if (rcnt) CM_G_NCCL(g, g->api->Recv(g->recv + roff[r], rcnt * 4, ncclFloat, r, g->comm, st));
+    }
+    CM_G_NCCL(g, g->api->GroupEnd());
+    const size_t self = (size_t)(mine[me + 1] - mine[me]);
+    if (self) CM_G_CUDA(g, cudaMemcpyAsync(g->recv + roff[me], send + mine[me], self * 16, cudaMemcpyDeviceToDevice, st));
+    vox_in = g->recv;
+    n_vox = roff[W];
+  } else {
+    gi.points_received = n_local;
+  }
+  if (info) *info = gi;
+  // ---- the ordinary single-GPU VoxelGrid on what arrived, global box folded in, key plan known from the global grid
+  const uint32_t* enc_dev = reinterpret_cast<const uint32_t*>(reinterpret_cast<const char*>(g->plan) + offsetof(GiantPlan, enc));
+  return voxelgrid_run(h, vox_in, n_vox, st, enc_dev, (int)P.key_bits);
 }
 
 int cm_sync(cm_handle_t h) {

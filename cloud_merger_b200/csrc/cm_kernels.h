@@ -173,6 +173,28 @@ cudaError_t launch_route_hist(const float4* pts, uint32_t n, const RouteGrid& g,
                               unsigned long long* hist, cudaStream_t stream);
 cudaError_t launch_route_mask(const float4* pts, uint32_t n, const RouteGrid& g, const RouteSplit& sp, unsigned short* mask,
                               cudaStream_t stream);
+// Device-resident plan of one giant-cloud run (cm_giant_voxelgrid): everything the routing kernels need comes from device
+// memory, so no step of the partition waits for the host.
+struct GiantPlan {
+  RouteGrid grid;                               // PCL's grid on the all-reduced bounding box
+  unsigned long long width;                     // voxel indices per histogram bin
+  unsigned long long cells;                     // div_x * div_y * div_z
+  unsigned long long total;                     // finite points of the whole cloud (sum of the all-reduced histogram)
+  unsigned long long splitter[CM_MAX_ZONES];    // rank r owns voxel indices in [splitter[r-1], splitter[r])
+  uint32_t enc[6];                              // the all-reduced bounds as FrameAcc holds them: max_enc[3], nmin_enc[3]
+  int32_t min_b[3], div_b[3];
+  uint32_t key_bits;                            // bits of the largest voxel index
+  uint32_t error;                               // CM_DEV_E_KEY_RANGE: grid outside the key range
+};
+cudaError_t launch_giant_plan(GiantPlan* plan, const FrameAcc* acc_reduced, const float* inv_leaf3, uint32_t bins, cudaStream_t stream);
+cudaError_t launch_giant_hist(const float4* pts, uint32_t n, const GiantPlan* plan, uint32_t bins, unsigned long long* hist,
+                              cudaStream_t stream);
+cudaError_t launch_giant_splitters(GiantPlan* plan, const unsigned long long* hist_reduced, uint32_t bins, uint32_t n_parts,
+                                   cudaStream_t stream);
+cudaError_t launch_giant_mask(const float4* pts, uint32_t n, const GiantPlan* plan, uint32_t n_parts, uint32_t invalid_part,
+                              unsigned short* mask, cudaStream_t stream);
+// folds device-resident bounds (GiantPlan::enc) into frame 0's accumulator: every rank then builds the same grid
+cudaError_t launch_seed_bounds_enc(FrameAcc* acc, const uint32_t* enc6, cudaStream_t stream);
 // bounding box of n packed points into acc (frame 0), as launch_minmax does for the VoxelGrid-only entry
 uint32_t zone_tile_points();
 cudaError_t launch_zone_split(const ZoneParams& p, cudaStream_t stream);  // 3 launches

@@ -72,7 +72,181 @@ __global__ void __launch_bounds__(RT_THREADS) k_route_mask(const float4* __restr
   }
 }
 
+// ---- the same steps with the plan in device memory (cm_giant_voxelgrid: no host round trip between them) ----------------------
+// PCL's grid on the all-reduced bounding box (VoxelGrid::applyFilter, float32): min_b = floor(min_p * inv), div_b = max_b - min_b + 1
+__global__ void k_giant_plan(GiantPlan* plan, const FrameAcc* __restrict__ acc, float inv0, float inv1, float inv2, uint32_t bins) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  GiantPlan p;
+  const float inv[3] = {inv0, inv1, inv2};
+  p.error = 0;
+  const bool empty = acc->max_enc[0] == 0u && acc->nmin_enc[0] == 0u;  // no finite point anywhere
+  long long div[3] = {1, 1, 1};
+  for (int k = 0; k < 3; ++k) {
+    p.enc[k] = acc->max_enc[k];
+    p.enc[3 + k] = acc->nmin_enc[k];
+    p.grid.inv[k] = inv[k];
+    p.grid.min_b[k] = 0;
+    if (!empty) {
+      const float mn = __uint_as_float(f32_order_dec(~acc->nmin_enc[k])), mx = __uint_as_float(f32_order_dec(acc->max_enc[k]));
+      const float fmn = floorf(__fmul_rn(mn, inv[k])), fmx = floorf(__fmul_rn(mx, inv[k]));
+      if (!(fabsf(fmn) < 1073741824.f) || !(fabsf(fmx) < 1073741824.f) || fmx < fmn) p.error = CM_DEV_E_KEY_RANGE;
+      else {
+        p.grid.min_b[k] = (long long)fmn;
+        div[k] = (long long)fmx - (long long)fmn + 1;
+        if (div[k] > (1ll << 21)) { p.error = CM_DEV_E_KEY_RANGE; div[k] = 1; }
+      }
+    }
+    p.min_b[k] = (int32_t)p.grid.min_b[k];
+    p.div_b[k] = (int32_t)div[k];
+  }
+  p.grid.div0 = div[0];
+  p.grid.div01 = div[0] * div[1];
+  p.cells = (unsigned long long)div[0] * (unsigned long long)div[1] * (unsigned long long)div[2];
+  p.width = (p.cells + (unsigned long long)bins - 1ull) / (unsigned long long)bins;
+  if (p.width == 0) p.width = 1;
+  p.key_bits = p.cells <= 1ull ? 0u : (uint32_t)(64 - __clzll((long long)(p.cells - 1ull)));
+  p.total = 0;
+  for (int r = 0; r < CM_MAX_ZONES; ++r) p.splitter[r] = ~0ull;
+  *plan = p;
+}
+
+__global__ void __launch_bounds__(RT_HIST_THREADS) k_giant_hist(const float4* __restrict__ pts, uint32_t n,
+                                                                const GiantPlan* __restrict__ plan, uint32_t bins,
+                                                                unsigned long long* __restrict__ hist, int use_smem) {
+  extern __shared__ uint32_t s_bins[];
+  const RouteGrid g = plan->grid;
+  const unsigned long long width = plan->width;
+  if (use_smem) {
+    for (uint32_t b = threadIdx.x; b < bins; b += RT_HIST_THREADS) s_bins[b] = 0;
+    __syncthreads();
+  }
+  for (uint32_t i = blockIdx.x * RT_HIST_THREADS + threadIdx.x; i < n; i += gridDim.x * RT_HIST_THREADS) {
+    unsigned long long key;
+    if (route_key(g, ldg_stream_f4(pts + i), &key)) {
+      unsigned long long b = key / width;
+      if (b >= bins) b = bins - 1;
+      if (use_smem) atomicAdd(&s_bins[(uint32_t)b], 1u);
+      else atomicAdd(hist + b, 1ull);
+    }
+  }
+  if (use_smem) {
+    __syncthreads();
+    for (uint32_t b = threadIdx.x; b < bins; b += RT_HIST_THREADS) {
+      const uint32_t c = s_bins[b];
+      if (c) atomicAdd(hist + b, (unsigned long long)c);
+    }
+  }
+}
+
+// One CTA: running sum of the all-reduced histogram, then the n_parts - 1 splitters that balance the point counts: the first
+// bin boundary at or after total * r / n_parts (what pick_splitters of the gloo-tested host protocol computes).
+constexpr int GS_THREADS = 1024;
+__global__ void __launch_bounds__(GS_THREADS) k_giant_splitters(GiantPlan* plan, const unsigned long long* __restrict__ hist,
+                                                                uint32_t bins, uint32_t n_parts) {
+  __shared__ unsigned long long s_part[GS_THREADS];
+  __shared__ unsigned long long s_total;
+  const uint32_t tid = threadIdx.x;
+  const uint32_t chunk = (bins + GS_THREADS - 1) / GS_THREADS;
+  const uint32_t b0 = min(bins, tid * chunk), b1 = min(bins, b0 + chunk);
+  unsigned long long sum = 0;
+  for (uint32_t b = b0; b < b1; ++b) sum += hist[b];
+  s_part[tid] = sum;
+  __syncthreads();
+  if (tid == 0) {  // 1024 partial sums: a serial exclusive scan is a few microseconds
+    unsigned long long run = 0;
+    for (int i = 0; i < GS_THREADS; ++i) {
+      const unsigned long long t = s_part[i];
+      s_part[i] = run;
+      run += t;
+    }
+    s_total = run;
+    plan->total = run;
+  }
+  __syncthreads();
+  const unsigned long long total = s_total, width = plan->width;
+  // every thread walks its own bins; a target falls into exactly one thread's range of the running sum
+  unsigned long long cum = s_part[tid];
+  for (uint32_t b = b0; b < b1; ++b) {
+    const unsigned long long before = cum;
+    cum += hist[b];
+    for (uint32_t r = 1; r < n_parts; ++r) {
+      const unsigned long long target = total * r / n_parts;
+      // first index i with cum[i] >= target (inclusive running sum), + 1; a target of 0 is met by bin 0
+      const bool first = (cum >= target) && (b == 0 ? true : before < target);
+      if (first) plan->splitter[r - 1] = (unsigned long long)min(b + 1u, bins) * width;
+    }
+  }
+  if (tid == 0 && total == 0)  // an empty cloud: every splitter at the first boundary (nothing moves)
+    for (uint32_t r = 1; r < n_parts; ++r) plan->splitter[r - 1] = width;
+}
+
+__global__ void __launch_bounds__(RT_THREADS) k_giant_mask(const float4* __restrict__ pts, uint32_t n,
+                                                           const GiantPlan* __restrict__ plan, uint32_t n_parts,
+                                                           uint32_t invalid_part, unsigned short* __restrict__ mask) {
+  __shared__ unsigned long long s_split[CM_MAX_ZONES];
+  if (threadIdx.x < CM_MAX_ZONES) s_split[threadIdx.x] = plan->splitter[threadIdx.x];
+  const RouteGrid g = plan->grid;
+  __syncthreads();
+  for (uint32_t i = blockIdx.x * RT_THREADS + threadIdx.x; i < n; i += gridDim.x * RT_THREADS) {
+    unsigned long long key;
+    uint32_t dest = invalid_part;  // non-finite points stay where they are (VoxelGrid skips them)
+    if (route_key(g, ldg_stream_f4(pts + i), &key)) {
+      dest = 0;
+      for (uint32_t k = 0; k + 1 < n_parts; ++k) dest += (key >= s_split[k]) ? 1u : 0u;
+    }
+    mask[i] = (unsigned short)(1u << dest);
+  }
+}
+
+__global__ void k_seed_bounds_enc(FrameAcc* acc, const uint32_t* __restrict__ enc6) {
+  const uint32_t k = threadIdx.x;
+  if (blockIdx.x == 0 && k < 6) {
+    if (k < 3) atomicMax(&acc->max_enc[k], enc6[k]);
+    else atomicMax(&acc->nmin_enc[k - 3], enc6[k]);
+  }
+}
+
 }  // namespace
+
+cudaError_t launch_giant_plan(GiantPlan* plan, const FrameAcc* acc_reduced, const float* inv_leaf3, uint32_t bins, cudaStream_t stream) {
+  k_giant_plan<<<1, 32, 0, stream>>>(plan, acc_reduced, inv_leaf3[0], inv_leaf3[1], inv_leaf3[2], bins);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_giant_hist(const float4* pts, uint32_t n, const GiantPlan* plan, uint32_t bins, unsigned long long* hist,
+                              cudaStream_t stream) {
+  if (n == 0) return cudaSuccess;
+  const int use_smem = bins <= RT_SMEM_BINS ? 1 : 0;
+  const size_t smem = use_smem ? (size_t)bins * sizeof(uint32_t) : 0;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(k_giant_hist, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(RT_SMEM_BINS * sizeof(uint32_t)));
+    if (e != cudaSuccess) return e;
+    configured = true;
+  }
+  const uint32_t blocks = std::min<uint32_t>((n + RT_HIST_THREADS - 1) / RT_HIST_THREADS, 148u * 2u);
+  k_giant_hist<<<blocks, RT_HIST_THREADS, smem, stream>>>(pts, n, plan, bins, hist, use_smem);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_giant_splitters(GiantPlan* plan, const unsigned long long* hist_reduced, uint32_t bins, uint32_t n_parts,
+                                   cudaStream_t stream) {
+  k_giant_splitters<<<1, GS_THREADS, 0, stream>>>(plan, hist_reduced, bins, n_parts);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_giant_mask(const float4* pts, uint32_t n, const GiantPlan* plan, uint32_t n_parts, uint32_t invalid_part,
+                              unsigned short* mask, cudaStream_t stream) {
+  if (n == 0) return cudaSuccess;
+  const uint32_t blocks = std::min<uint32_t>((n + RT_THREADS - 1) / RT_THREADS, 148u * 8u);
+  k_giant_mask<<<blocks, RT_THREADS, 0, stream>>>(pts, n, plan, n_parts, invalid_part, mask);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_seed_bounds_enc(FrameAcc* acc, const uint32_t* enc6, cudaStream_t stream) {
+  k_seed_bounds_enc<<<1, 32, 0, stream>>>(acc, enc6);
+  return cudaGetLastError();
+}
 
 cudaError_t launch_route_hist(const float4* pts, uint32_t n, const RouteGrid& g, unsigned long long width, uint32_t bins,
                               unsigned long long* hist, cudaStream_t stream) {

@@ -439,6 +439,38 @@ CM_API int cm_dev_key_histogram(cm_handle_t h, const float* xyzi_dev, int64_t n_
                                 const float* max3, int bins, uint64_t* hist_dev, uint64_t* out_bin_width, void* stream);
 CM_API int cm_dev_route_by_key(cm_handle_t h, const float* xyzi_dev, int64_t n_points, const float* min3,
                                const float* max3, const uint64_t* splitters, int n_parts, int invalid_part, void* stream);
+/* ---- the whole giant-cloud VoxelGrid behind ONE call, C++ + NCCL (BASELINE config 4) ----
+ * One process per GPU; every rank holds a block of the cloud in device memory. cm_giant_voxelgrid does, on `stream`:
+ *   bounding box of the block -> ncclAllReduce (max of order-preserving encodings) -> PCL's grid on the global box, ON THE DEVICE
+ *   -> histogram of the voxel index -> ncclAllReduce (sum) -> balancing splitters, ON THE DEVICE -> group the block by
+ *   destination rank (source order kept) -> ncclAllGather of the per-destination counts -> ONE all-to-all (grouped
+ *   ncclSend / ncclRecv straight out of the grouped array, 16 bytes per point) -> the single-GPU VoxelGrid on what arrived,
+ *   with the global box folded in so that every rank builds the same grid.
+ * The host is needed twice: for the counts of the all-to-all (NCCL takes them as host arguments) and for the final report.
+ * A voxel never straddles ranks, and the rank outputs (cm_get_device_out on each rank: voxel_xyzi / voxel_count / voxel_idx)
+ * concatenated in rank order are PCL's order. Leaf and min_points: cm_set_voxel on the handle. The handle's
+ * max_batch_points bounds what a rank may RECEIVE (balanced splitters give ~n / world; size it with headroom).
+ * NCCL is loaded at run time (libnccl.so.2 -- the copy already in the process if there is one, e.g. PyTorch's);
+ * communicator bootstrap: rank 0 calls cm_giant_unique_id and ships the 128 bytes to every rank by any means.
+ * With nccl_id == NULL and world > 1 the object is "dry": no communicator, the collectives are identities, and
+ * cm_giant_voxelgrid stops after the grouping (results through cm_get_zone_out) -- the routing can be tested on one GPU. */
+typedef struct cm_giant_s* cm_giant_t;
+#define CM_GIANT_ID_BYTES 128
+typedef struct {
+  int64_t points_local, points_received, points_sent_away, points_total_finite;
+  int64_t voxels_local;            /* filled by cm_giant_report */
+  uint64_t splitter[CM_MAX_ZONES]; /* world - 1 valid entries */
+  float min_p[3], max_p[3];        /* global bounding box */
+  int32_t min_b[3], div_b[3];      /* PCL's grid on it */
+  int32_t key_bits, host_syncs;
+  int64_t send_begin[CM_MAX_ZONES + 1]; /* where the points for rank r start in the grouped array */
+} cm_giant_info_t;
+CM_API int cm_giant_unique_id(void* id_bytes);
+CM_API int cm_giant_create(cm_handle_t h, int rank, int world, const void* nccl_id, cm_giant_t* out);
+CM_API int cm_giant_destroy(cm_giant_t g);
+CM_API int cm_giant_voxelgrid(cm_giant_t g, const float* local_xyzi_dev, int64_t n_local, cm_giant_info_t* info, void* stream);
+CM_API const char* cm_giant_last_error(cm_giant_t g);
+
 /* Blocks until the last run on the handle finished, then reports. */
 CM_API int cm_sync(cm_handle_t h);
 CM_API int cm_get_stats(cm_handle_t h, cm_stats_t* out);

@@ -1,6 +1,7 @@
 #!/usr/bin/env python
 """BASELINE config 4: VoxelGrid of one aggregated map cloud partitioned over the GPUs of one box by voxel-key range, with
-one NCCL all-to-all (cloud_merger_b200/multi_gpu.py). Launch with torchrun (one rank per GPU) or plainly for one GPU.
+one NCCL all-to-all -- cm_giant_voxelgrid, C++ + NCCL behind the C ABI. Launch with torchrun (one rank per GPU) or plainly
+for one GPU.
 Prints one JSON line on rank 0. --check compares against the CPU oracle (small clouds only)."""
 import argparse
 import json
@@ -14,7 +15,7 @@ import torch.distributed as dist
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-from cloud_merger_b200 import CloudMerger, multi_gpu, synth  # noqa: E402
+from cloud_merger_b200 import CloudMerger, GiantCloud, giant_unique_id, synth  # noqa: E402
 
 
 def main():
@@ -44,20 +45,34 @@ def main():
     # capacity: a rank may receive more than its share
     cap = int(min(n, (hi - lo) * 2 + 1024))
     cm = CloudMerger(device=local_rank, max_batch_points=cap)
-    backend = multi_gpu.cuda_voxelgrid_backend(cm, a.leaf, a.min_points, download=a.check)
-    router = multi_gpu.CudaRouter(cm)
+    cm.set_voxel(a.leaf, a.min_points, True)
+    # the product path: the whole partitioned VoxelGrid behind the C ABI (C++ + NCCL inside the library). torch only ships
+    # the 128-byte NCCL id to the ranks and holds the input tensor.
+    nccl_id = None
+    if world > 1:
+        box = [giant_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(box, src=0)
+        nccl_id = box[0]
+    giant = GiantCloud(cm, rank, world, nccl_id)
+    stream = torch.cuda.current_stream().cuda_stream
     times, out = [], None
     for it in range(a.iters + 1):
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
         t0 = time.perf_counter()
-        out = multi_gpu.giant_cloud_voxelgrid(local, [a.leaf] * 3, a.min_points, backend, rank, world, router=router)
-        torch.cuda.synchronize()
+        out = giant.voxelgrid(local.data_ptr(), int(local.shape[0]), stream=stream)
+        st = cm.stats()   # blocks until the voxels are there
         if world > 1:
             dist.barrier()
         if it:
             times.append(time.perf_counter() - t0)
+    out.update(n_voxels=int(st.voxels_out), gpu_ms=float(st.gpu_ms), key_bits=int(st.key_bits))
+    if a.check:
+        o = cm.device_out()
+        v = out["n_voxels"]
+        out.update(idx=cm.download(o.voxel_idx, np.uint64, v).astype(np.int64), count=cm.download(o.voxel_count, np.uint32, v),
+                   centroid=cm.download(o.voxel_xyzi, np.float32, v * 4).reshape(v, 4))
     dt = float(np.median(times))
     stats = torch.tensor([out["points_received"], out["points_sent_away"], out["n_voxels"]], dtype=torch.int64, device="cuda")
     if world > 1:
@@ -89,7 +104,9 @@ def main():
                           "n_gpus": world, "points": n, "voxels": int(sum(int(v[2]) for v in allv)), "ms": dt * 1e3,
                           "mpoints_per_s": n / dt / 1e6, "points_exchanged": sent, "bytes_exchanged": sent * 16,
                           "points_per_rank_after": [int(v[0]) for v in allv], "key_bits": out.get("key_bits"),
-                          "local_voxelgrid_ms": out.get("gpu_ms"), "check": check}) + "\n").encode())
+                          "local_voxelgrid_ms": out.get("gpu_ms"), "host_syncs_before_report": out.get("host_syncs"),
+                          "api": "cm_giant_voxelgrid (C++ + NCCL behind the C ABI)", "check": check}) + "\n").encode())
+    giant.close()
     cm.close()
     if world > 1:
         dist.destroy_process_group()

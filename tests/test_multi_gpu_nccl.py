@@ -1,5 +1,8 @@
-"""GPU tests of the giant-cloud mode: the CUDA backend behind multi_gpu.giant_cloud_voxelgrid (cm_set_voxel_bounds +
-cm_dev_voxelgrid), on one GPU always and on two ranks over NCCL when the box has two GPUs."""
+"""GPU tests of the giant-cloud mode (BASELINE config 4). The product path is cm_giant_voxelgrid -- C++ + NCCL behind the C
+ABI: tested on one GPU at 20 M points against the oracle, on one GPU in "dry" mode (four virtual ranks: device-side grid,
+histogram, splitters and grouping against the torch formulation of the gloo-tested host protocol), and on two ranks over
+NCCL when the box has two GPUs. The building blocks (cm_set_voxel_bounds + cm_dev_voxelgrid, the routing kernels) keep their
+own tests."""
 import json
 import os
 import subprocess
@@ -73,6 +76,72 @@ def test_cuda_router_pieces_single_gpu(gpu_ok):
             want = np.nonzero(dest == r)[0]
             assert (got[r][1] == want).all(), "part %d" % r
             assert (got[r][0].view(np.uint32) == whole[want].view(np.uint32)).all()
+
+
+def test_giant_c_abi_single_gpu_at_20m_points(gpu_ok, oracle):
+    """cfg 4 at 20 M points on one GPU through cm_giant_voxelgrid (world 1: global grid on the device, key plan known from
+    it, 64-bit keys on the big sort tile, 39 bits / 5 passes at leaf 0.02): voxel ids, counts, order bit-exact, centroids
+    bit-equal to the float oracle and within 1e-5 of the float64 one."""
+    from cloud_merger_b200 import GiantCloud
+    n, leaf = 20_000_000, 0.02
+    whole = synth.map_cloud(4000, n)
+    with CloudMerger(max_batch_points=n) as cm:
+        cm.set_voxel(leaf, 1, True)
+        buf = cm.upload(whole)
+        g = GiantCloud(cm, 0, 1)
+        info = g.voxelgrid(buf.ptr, n)
+        st = cm.stats()
+        v = int(st.voxels_out)
+        o_dev = cm.device_out()
+        idx = cm.download(o_dev.voxel_idx, np.uint64, v).astype(np.int64)
+        cnt = cm.download(o_dev.voxel_count, np.uint32, v)
+        cen = cm.download(o_dev.voxel_xyzi, np.float32, v * 4).reshape(v, 4)
+        g.close()
+    o = oracle.voxelgrid(whole, [leaf] * 3, 1, True, force64=True)
+    assert st.key_bytes == 8 and st.key_bits == info["key_bits"] > 32 and st.sort_passes == 5 and st.device_error == 0
+    assert info["min_b"].tolist() == o["min_b"].tolist() and info["div_b"].tolist() == o["div_b"].tolist()
+    assert v == o["n"] and (idx == o["idx"]).all() and (cnt == o["count"]).all()
+    assert (cen.view(np.uint32) == o["centroid"].view(np.uint32)).all()
+    err = np.abs(cen.astype(np.float64) - o["centroid_f64"]) / np.maximum(np.abs(o["centroid_f64"]), 1e-2)
+    assert err.max() <= 1e-5
+
+
+def test_giant_dry_routing_four_virtual_ranks(gpu_ok):
+    """The device-side partition plan of cm_giant_voxelgrid without a communicator: grid, bin width, histogram, balancing
+    splitters and the grouping by destination for four virtual ranks, against the torch formulation of the host protocol
+    (multi_gpu.global_grid / voxel_keys / pick_splitters, which the gloo tests exercise on CPU)."""
+    import torch
+    from cloud_merger_b200 import GiantCloud
+    n, leaf, world, me = 700000, 0.1, 4, 1
+    whole = synth.map_cloud(11, n, extent=(150.0, 90.0, 9.0), n_boxes=120)
+    whole[::991, 2] = np.nan
+    pts = torch.from_numpy(whole).cuda()
+    with CloudMerger(max_batch_points=n) as cm:
+        cm.set_voxel(leaf, 1, True)
+        g = GiantCloud(cm, me, world, None)
+        info = g.voxelgrid(pts.data_ptr(), n, stream=torch.cuda.current_stream().cuda_stream)
+        got = cm.zone_out()
+        g.close()
+    mn, mx, min_b, div_b = multi_gpu.global_grid(pts, [leaf] * 3)
+    assert (info["min_p"].view(np.uint32) == mn.view(np.uint32)).all() and (info["max_p"].view(np.uint32) == mx.view(np.uint32)).all()
+    assert (info["min_b"] == min_b).all() and (info["div_b"] == div_b).all()
+    keys = multi_gpu.voxel_keys(pts, [leaf] * 3, min_b, div_b)
+    n_cells = int(div_b[0]) * int(div_b[1]) * int(div_b[2])
+    want_split = multi_gpu.pick_splitters(keys, n_cells, world, bins=1 << 14)
+    assert info["splitters"] == want_split.cpu().tolist()
+    assert info["points_total_finite"] == int((keys >= 0).sum().item())
+    dest = torch.searchsorted(want_split.to(keys.device), keys, right=True)
+    dest = torch.where(keys < 0, torch.full_like(dest, me), dest).cpu().numpy()
+    assert len(got) == world and sum(len(s) for _, s in got) == n
+    sizes = []
+    for r in range(world):
+        want = np.nonzero(dest == r)[0]
+        assert (got[r][1] == want).all(), "part %d" % r
+        assert (got[r][0].view(np.uint32) == whole[want].view(np.uint32)).all()
+        sizes.append(len(want))
+    assert info["send_begin"] == [0] + np.cumsum(sizes).tolist()
+    assert info["points_sent_away"] == n - sizes[me]
+    assert max(sizes) < 1.3 * n / world, "splitters balance the point counts (%r)" % sizes
 
 
 def test_giant_cloud_two_ranks_nccl(gpu_ok):
