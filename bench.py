@@ -46,6 +46,7 @@ def parse_args():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--no-latency", action="store_true", help="skip the single-frame p50/p99 latency measurement")
+    ap.add_argument("--points", type=int, default=0, help="cfg4 / cfg5: points of the cloud (0 = 100 M / 16 Mi)")
     ap.add_argument("--sustained-seconds", type=float, default=2.0,
                     help="length of the extra back-to-back leg that shows the number holds at steady-state clocks (0 = skip)")
     return ap.parse_args()
@@ -299,6 +300,237 @@ def run_reference(args):
     return 0
 
 
+CLOUD_WORKLOADS = {
+    "cfg4": dict(points=100_000_000, leaves=[0.02], min_points=1,
+                 what="single 100M-pt aggregated map cloud VoxelGrid 0.02 m, voxel-key range partition + one NCCL all-to-all"),
+    "cfg5": dict(points=1 << 24, leaves=[0.01, 0.02, 0.05, 0.1, 0.2, 0.5, 1.0], min_points=1,
+                 what="VoxelGrid leaf-size sweep 0.01-1.0 m on 16 Mi pts (uniform 200 x 200 x 10 m)"),
+}
+
+
+def cloud_of(name: str, n: int, rank: int, world: int):
+    """This rank's block of the workload's cloud (cfg4: every rank generates the seeded map and keeps its block)."""
+    from cloud_merger_b200 import synth
+    if name == "cfg5":
+        return synth.uniform_cloud(5000, n)
+    whole = synth.map_cloud(4, n)
+    lo, hi = rank * n // world, (rank + 1) * n // world
+    return np.ascontiguousarray(whole[lo:hi])
+
+
+def run_cloud_reference(args):
+    """--impl reference for cfg4 / cfg5: the oracle's VoxelGrid (port of PCL 1.8.1's, 64-bit index extension) on a bounded
+    sample of the cloud, one leaf per thread."""
+    if int(os.environ.get("RANK", "0")) != 0:
+        return 0
+    from concurrent.futures import ThreadPoolExecutor
+
+    from oracle import cm_oracle_py as oracle
+    wl = CLOUD_WORKLOADS[args.workload]
+    n = min(args.points or wl["points"], 4_000_000)
+    x = cloud_of(args.workload, n, 0, 1)
+    cores = os.cpu_count() or 1
+    jobs = wl["leaves"] if len(wl["leaves"]) > 1 else wl["leaves"] * min(cores, 4)
+    workers = min(cores, len(jobs))
+
+    def one(leaf):
+        return oracle.voxelgrid(x, [leaf] * 3, wl["min_points"], True, force64=True)["n"]
+    with ThreadPoolExecutor(max_workers=workers) as ex:
+        for _ in range(min(args.warmup, 1)):
+            list(ex.map(one, jobs))
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            list(ex.map(one, jobs))
+        dt = time.perf_counter() - t0
+    value = n * len(jobs) * args.steps / dt / 1e6
+    sample = "%d-point sample, %d VoxelGrid runs per step on %d threads (oracle port of PCL 1.8.1 VoxelGrid, 64-bit index)" % (n, len(jobs), workers)
+    emit({"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+          "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True,
+          "scaling": "strong" if args.workload == "cfg4" else "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+          "config": {"workload": "%s: %s" % (args.workload, wl["what"]), "points": n, "leaves_m": wl["leaves"]},
+          "cpu_baseline": {"value": value, "unit": UNIT, "cores": workers, "kind": "port", "sample": sample},
+          "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0})
+    return 0
+
+
+def run_cloud_workload(args):
+    """cfg4 (one giant cloud, partitioned over the ranks: cm_giant_voxelgrid, strong scaling) and cfg5 (leaf sweep on one
+    cloud per GPU; N > 1 = independent replicas). A step = the VoxelGrid of the cloud at every leaf of the workload."""
+    import torch
+    import torch.distributed as dist
+
+    from cloud_merger_b200 import CloudMerger, GiantCloud, giant_unique_id, host_alloc
+    rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (the product path has no CPU fallback)")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+    wl = CLOUD_WORKLOADS[args.workload]
+    giant_mode = args.workload == "cfg4"
+    n_total = args.points or wl["points"]
+    local = cloud_of(args.workload, n_total, rank if giant_mode else 0, world if giant_mode else 1)
+    n = len(local)
+    pinned, addr = host_alloc(n * 16)
+    pinned[:] = local.view(np.uint8).reshape(-1)
+    cap = n if not giant_mode or world == 1 else int(min(n_total, 2 * n + 1024))
+    cm = CloudMerger(device=local_rank, max_batch_points=cap)
+    dev = cm.device_buffer(n * 16)
+    dev.upload(local)
+    stream = torch.cuda.current_stream().cuda_stream
+    giant = None
+    if giant_mode:
+        nccl_id = None
+        if world > 1:
+            box = [giant_unique_id() if rank == 0 else None]
+            dist.broadcast_object_list(box, src=0)
+            nccl_id = box[0]
+        giant = GiantCloud(cm, rank, world, nccl_id)
+    cm.set_profiling(True)
+    leaves = wl["leaves"]
+    per_leaf = {}
+
+    def one_leaf(leaf, record=False):
+        cm.set_voxel(leaf, wl["min_points"], True)
+        if giant:
+            info = giant.voxelgrid(dev.ptr, n, stream=stream)
+        else:
+            info = {}
+            cm.dev_voxelgrid(dev.ptr, n, stream=stream)
+        if record:
+            st = cm.stats()
+            per_leaf[leaf] = dict(st=st, info=info, sort_ms=cm.stage_ms("sort"), key_ms=cm.stage_ms("key_hist"),
+                                  cent_ms=cm.stage_ms("centroid"), launches=cm.launch_count())
+        return info
+
+    def step(record=False):
+        for leaf in leaves:
+            one_leaf(leaf, record)
+    for _ in range(max(args.warmup, 3)):
+        step()
+        cm.sync()
+    try:
+        gpu_uuid = str(torch.cuda.get_device_properties(torch.cuda.current_device()).uuid)
+    except Exception:
+        gpu_uuid = ""
+    sampler = ClockSampler(local_rank, gpu_uuid)
+    barrier()
+    sampler.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for k in range(args.steps):
+        step(record=(k == args.steps - 1))
+    ev1.record()
+    cm.sync()
+    barrier()
+    clocks = sampler.stop()
+    t = torch.tensor([ev0.elapsed_time(ev1)], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_total = float(t.item())
+    ms_step = ms_total / args.steps
+    pts_job = (n_total if giant_mode else n * world) * len(leaves)
+    value = pts_job * args.steps / (ms_total / 1e3) / 1e6
+    peak, peak_src = peaks()
+    stages, sort_bytes, sort_ms, sort_launches, launches = {}, 0, 0.0, 0, 0
+    for leaf, r in per_leaf.items():
+        st = r["st"]
+        M, V, P, kb = int(st.points_in), int(st.voxels_out), int(st.sort_passes), int(st.key_bytes)
+        b_vg = M * (16 + 2 * kb + 2 * P * (kb + 4) + (kb + 4) + 16) + 20 * V
+        b_io = 16 * M + 20 * V
+        ms = float(st.gpu_ms)
+        stages["leaf_%g" % leaf] = {"ms": round(ms, 4), "points": M, "voxels": V, "key_bytes": kb, "passes": P, "key_bits": int(st.key_bits),
+                                    "B_vg_bytes": int(b_vg), "frac": round(b_vg / (ms * 1e-3) / 1e9 / peak, 4) if ms > 0 else 0,
+                                    "B_io_bytes": int(b_io), "frac_io": round(b_io / (ms * 1e-3) / 1e9 / peak, 4) if ms > 0 else 0,
+                                    "pcl_could_run": not bool(st.pcl_overflow), "sort_ms": round(r["sort_ms"], 4),
+                                    "key_hist_ms": round(r["key_ms"], 4), "centroid_ms": round(r["cent_ms"], 4)}
+        if r["info"]:
+            stages["leaf_%g" % leaf].update(points_received=r["info"]["points_received"], points_sent_away=r["info"]["points_sent_away"],
+                                            bytes_sent=r["info"]["points_sent_away"] * 16)
+        sort_bytes += M * 2 * (kb + 4) * P
+        sort_ms += r["sort_ms"]
+        sort_launches += P
+        launches += r["launches"]
+    achieved = sort_bytes / (sort_ms * 1e-3) / 1e9 if sort_ms > 0 else 0.0
+    roofline = {"bound": "hbm", "kernel": "k_onesweep_pass", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
+                "frac": round(achieved / peak, 4), "traffic": None, "peak_source": peak_src,
+                "launch_ms": round(sort_ms / max(sort_launches, 1), 4),
+                "algorithmic_bytes_per_launch": int(sort_bytes / max(sort_launches, 1)), "share_of_step": round(sort_ms / ms_step, 3)}
+    # ---- end to end: the block from page-locked host memory in, centroids + counts + voxel ids out, every step ------------
+    e2e = None
+    if not args.no_e2e:
+        e2e_steps = args.e2e_steps or min(args.steps, 2)
+        cm.set_profiling(False)
+        out_pin, _ = host_alloc(cap * 28)
+        h2d = d2h = 0
+
+        def host_step(count):
+            nonlocal h2d, d2h
+            cm._check(cm._lib.cm_memcpy_h2d(cm._h, dev.ptr, addr, n * 16, stream))
+            for leaf in leaves:
+                one_leaf(leaf)
+                st = cm.stats()
+                o = cm.device_out()
+                v = int(st.voxels_out)
+                base = out_pin.ctypes.data
+                cm._check(cm._lib.cm_memcpy_d2h(cm._h, base, o.voxel_xyzi, v * 16, stream))
+                cm._check(cm._lib.cm_memcpy_d2h(cm._h, base + v * 16, o.voxel_count, v * 4, stream))
+                cm._check(cm._lib.cm_memcpy_d2h(cm._h, base + v * 20, o.voxel_idx, v * 8, stream))
+                if count:
+                    d2h += v * 28
+            if count:
+                h2d += n * 16
+        host_step(False)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            host_step(True)
+        barrier()
+        dt = time.perf_counter() - t0
+        tt = torch.tensor([dt], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        dt = float(tt.item())
+        e2e = {"value": pts_job * e2e_steps / dt / 1e6, "unit": UNIT, "h2d_bytes_per_step": int(h2d / e2e_steps),
+               "d2h_bytes_per_step": int(d2h / e2e_steps), "steps": e2e_steps, "ms_per_step": dt / e2e_steps * 1e3,
+               "api": ("cm_giant_voxelgrid" if giant else "cm_dev_voxelgrid") + " between cm_memcpy_h2d of the block and cm_memcpy_d2h of the voxels"}
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        from oracle import cm_oracle_py as oracle
+        ns = min(n, 4_000_000)
+        t0 = time.perf_counter()
+        done = 0
+        while time.perf_counter() - t0 < args.cpu_seconds:
+            oracle.voxelgrid(local[:ns], [leaves[done % len(leaves)]] * 3, wl["min_points"], True, force64=True)
+            done += 1
+        secs = time.perf_counter() - t0
+        cpu = {"value": ns * done / secs / 1e6, "unit": UNIT, "cores": 1, "kind": "port",
+               "sample": "%d VoxelGrid runs over the first %d points in %.1f s on one thread (PCL's VoxelGrid is single-threaded; oracle port)" % (done, ns, secs)}
+    if rank == 0:
+        emit({"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+              "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong" if giant_mode else "weak", "vs_baseline": None,
+              "dtype": "f32", "data": "synthetic",
+              "config": {"workload": "%s: %s" % (args.workload, wl["what"]), "points": n_total, "points_per_gpu": n, "leaves_m": leaves,
+                         "min_points": wl["min_points"],
+                         "sharding": ("voxel-key range partition, one NCCL all-to-all (cm_giant_voxelgrid)" if giant_mode and world > 1
+                                      else "single GPU" if world == 1 else "independent replicas, one cloud per GPU"),
+                         "l2": "inputs larger than L2 (%.0f MB per GPU)" % (n * 16 / 1e6)},
+              "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches * args.steps), "roofline": roofline, "stages": stages,
+              "cpu_baseline": cpu})
+    if giant:
+        giant.close()
+    cm.close()
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
 _REAL_STDOUT = None
 
 
@@ -324,7 +556,9 @@ def main():
     args = parse_args()
     guard_stdout()
     if args.impl == "reference":
-        return run_reference(args)
+        return run_cloud_reference(args) if args.workload in CLOUD_WORKLOADS else run_reference(args)
+    if args.workload in CLOUD_WORKLOADS:
+        return run_cloud_workload(args)
 
     import torch
     import torch.distributed as dist
@@ -543,7 +777,7 @@ def main():
                     hl.append((time.perf_counter() - t0) * 1e3)
             hl.sort()
             latency.update({"host_p50_ms": hl[len(hl) // 2], "host_p99_ms": hl[int(len(hl) * 0.99)],
-                            "host_what": "wall time of one frame through cm_submit_clouds_pinned + merge + wait (8 MB in, voxels out)"})
+                            "host_what": "wall time of one frame through cm_submit_clouds_pinned + merge + wait (%.0f MB in, voxels out)" % (S * n * 16 / 1e6)})
 
     # ---- CPU baseline on this box's host cores (rank 0, N = 1 only) ------------------------------------------------------
     cpu = None
