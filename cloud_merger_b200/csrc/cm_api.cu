@@ -68,13 +68,10 @@ struct Workspace {
   void *keys_a = nullptr, *keys_b = nullptr;
   uint32_t *vals_a = nullptr, *vals_b = nullptr;
   TileRec* tile_rec = nullptr;          // [lb_k1_n] K1 tile records
-  uint32_t* cent_count = nullptr;       // [lb_cent_n]
+  unsigned long long* cent_status = nullptr;  // [lb_cent_n] look-back words of the voxel compaction
   unsigned long long* lb_sort = nullptr;
   uint32_t* epoch_dev = nullptr;        // run epoch of the look-back words (device-resident, see VoxelParams)
   size_t lb_k1_n = 0, lb_sort_n = 0, lb_cent_n = 0;
-  void* tmp_xyzi = nullptr;             // tile-local voxel records before compaction
-  uint32_t* tmp_count = nullptr;
-  unsigned long long* tmp_idx = nullptr;
   float4* dense_xyzi = nullptr;         // dense merged cloud, allocated and filled on request only
   uint32_t* dense_src = nullptr;
   uint32_t* dense_slot = nullptr;
@@ -239,8 +236,7 @@ void ws_free(Workspace& w) {
   if (!w.ready) return;
   cudaFree(w.meta); cudaFreeHost(w.report); cudaFree(w.segs); cudaFree(w.tile_seg); cudaFree(w.surv_xyzi); cudaFree(w.surv_src);
   cudaFree(w.keys_a); cudaFree(w.keys_b); cudaFree(w.vals_a); cudaFree(w.vals_b);
-  cudaFree(w.tile_rec); cudaFree(w.lb_sort); cudaFree(w.cent_count); cudaFree(w.epoch_dev);
-  cudaFree(w.tmp_xyzi); cudaFree(w.tmp_count); cudaFree(w.tmp_idx);
+  cudaFree(w.tile_rec); cudaFree(w.lb_sort); cudaFree(w.cent_status); cudaFree(w.epoch_dev);
   cudaFree(w.dense_xyzi); cudaFree(w.dense_src); cudaFree(w.dense_slot);
   cudaFree(w.out_xyzi); cudaFree(w.out_count); cudaFree(w.out_idx);
   cudaFree(w.trace_k1); cudaFree(w.trace_sort);
@@ -270,14 +266,11 @@ int ws_alloc(cm_handle_t h, Workspace& w, uint32_t points, uint32_t frames, uint
   w.lb_cent_n = np / centroid_tile_items() + 2;
   CM_CUDA(h, dev_alloc(&w.tile_rec, w.lb_k1_n));
   CM_CUDA(h, dev_alloc(&w.lb_sort, w.lb_sort_n));
-  CM_CUDA(h, dev_alloc(&w.cent_count, w.lb_cent_n));
+  CM_CUDA(h, dev_alloc(&w.cent_status, w.lb_cent_n));
+  CM_CUDA(h, cudaMemset(w.cent_status, 0, w.lb_cent_n * 8));
   CM_CUDA(h, cudaMemset(w.lb_sort, 0, w.lb_sort_n * 8));
   CM_CUDA(h, dev_alloc(&w.epoch_dev, (size_t)1));
   CM_CUDA(h, cudaMemset(w.epoch_dev, 0, sizeof(uint32_t)));
-  const size_t nt = np + centroid_tile_items();
-  CM_CUDA(h, cudaMalloc(&w.tmp_xyzi, nt * 16));
-  CM_CUDA(h, dev_alloc(&w.tmp_count, nt));
-  CM_CUDA(h, dev_alloc(&w.tmp_idx, nt));
   CM_CUDA(h, cudaMalloc(&w.out_xyzi, np * (size_t)out_step));
   CM_CUDA(h, dev_alloc(&w.out_count, np));
   CM_CUDA(h, dev_alloc(&w.out_idx, np));
@@ -363,8 +356,8 @@ void fill_voxel_params(cm_handle_t h, Workspace& w, VoxelParams& vp, const float
   vp.info = reinterpret_cast<SortInfo*>(w.meta + w.ml.off_info);
   vp.hist = reinterpret_cast<uint32_t*>(w.meta + w.ml.off_hist);
   vp.keys_a = w.keys_a; vp.keys_b = w.keys_b; vp.vals_a = w.vals_a; vp.vals_b = w.vals_b;
-  vp.lb_sort = w.lb_sort; vp.cent_count = w.cent_count;
-  vp.tmp_xyzi = w.tmp_xyzi; vp.tmp_count = w.tmp_count; vp.tmp_idx = w.tmp_idx;
+  vp.lb_sort = w.lb_sort; vp.cent_status = w.cent_status;
+  vp.cent_status_words = (uint32_t)std::min<size_t>(w.lb_cent_n, 0xFFFFFFFFu);
   vp.tile_rec = w.ran_k1 ? w.tile_rec : nullptr;
   vp.n_k1_tiles = w.n_k1_tiles;
   vp.epoch_dev = w.epoch_dev;

@@ -63,10 +63,8 @@ struct VoxelParams {
   uint32_t* vals_a;                  // values of 64-bit keys (unused by the record layout)
   uint32_t* vals_b;
   unsigned long long* lb_sort;       // [sort tiles][256]
-  uint32_t* cent_count;              // [centroid tiles] voxels emitted per tile, then their exclusive prefix
-  void* tmp_xyzi;                    // tile-local voxel outputs before compaction
-  uint32_t* tmp_count;
-  unsigned long long* tmp_idx;
+  unsigned long long* cent_status;   // [centroid tiles] look-back words of the voxel compaction (epoch-tagged, never cleared)
+  uint32_t cent_status_words;
   uint32_t* epoch_dev;               // device-resident run epoch: advanced by 16 in k_grid_setup, read by the sort passes
                                      // (pass p tags its look-back words with *epoch_dev + 1 + p), so no kernel argument
                                      // changes from run to run and a captured launch sequence can be replayed as a graph
@@ -91,8 +89,8 @@ cudaError_t launch_sort_pass(const VoxelParams& p, int pass, cudaStream_t stream
 // 32-bit keys are sorted as 8-byte (key, value) records in keys_a/keys_b; this splits the first *n_ptr records into two arrays
 cudaError_t launch_split_records(const void* records, uint32_t* keys, uint32_t* vals, const uint32_t* n_ptr,
                                  uint32_t max_points, cudaStream_t stream);
-cudaError_t launch_centroid(const VoxelParams& p, cudaStream_t stream);        // 3 launches: centroid, scan, compact
-#define CM_CENTROID_LAUNCHES 3
+cudaError_t launch_centroid(const VoxelParams& p, cudaStream_t stream);        // one launch: runs, centroids, dense ordered output
+#define CM_CENTROID_LAUNCHES 1
 // host path: dense voxel outputs of a one-frame run -> device-mapped page-locked host arrays, sized by Ctrl.total_voxels
 cudaError_t launch_export_voxels(const VoxelParams& p, void* host_xyzi, uint32_t* host_count, unsigned long long* host_idx,
                                  uint32_t cap, cudaStream_t stream);

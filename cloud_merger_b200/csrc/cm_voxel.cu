@@ -163,27 +163,6 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_tile_scan(TileRec* __restrict_
   tile_scan_body(rec, n_tiles, segs, n_seg, n_frames, frame_surv_start, seg_surv_start, s_scr);
 }
 
-// ---- one CTA: in-place exclusive scan of n counters (+ total) ----------------------------------------------------------
-__global__ void __launch_bounds__(SCAN_THREADS) k_scan_u32(uint32_t* __restrict__ v, const uint32_t* n_ptr, uint32_t per,
-                                                          uint32_t n_max, uint32_t* total_out) {
-  __shared__ uint32_t s_scr[33];
-  const uint32_t tid = threadIdx.x;
-  // n = ceil(*n_ptr / per): the number of live counters is only known on the device
-  const uint32_t n = min(n_max, (*n_ptr + per - 1) / per);
-  const uint32_t chunk = (n + SCAN_THREADS - 1) / SCAN_THREADS;
-  const uint32_t b = min(n, tid * chunk), e = min(n, b + chunk);
-  uint32_t sum = 0;
-  for (uint32_t i = b; i < e; ++i) sum += v[i];
-  uint32_t total;
-  uint32_t run = block_excl_scan_1024(sum, s_scr, &total);
-  for (uint32_t i = b; i < e; ++i) {
-    const uint32_t c = v[i];
-    v[i] = run;
-    run += c;
-  }
-  if (tid == 0) *total_out = total;
-}
-
 // ---- dense copy of the merged cropped cloud, on request ---------------------------------------------------------------------
 __global__ void __launch_bounds__(VX_THREADS) k_compact_survivors(const TileRec* __restrict__ rec, uint32_t n_tiles,
                                                                  const float4* __restrict__ slot_xyzi,
@@ -286,8 +265,10 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_grid_setup(const VoxelParams p
   {
     const uint32_t e = *p.epoch_dev;
     const bool wrap = e + 64u >= (1u << 30);
-    if (wrap)
+    if (wrap) {
       for (uint32_t i = tid; i < p.lb_sort_words; i += SCAN_THREADS) p.lb_sort[i] = 0ull;
+      for (uint32_t i = tid; i < p.cent_status_words; i += SCAN_THREADS) p.cent_status[i] = 0ull;
+    }
     __syncthreads();
     if (tid == 0) *p.epoch_dev = wrap ? 16u : e + 16u;
   }
@@ -435,6 +416,11 @@ __global__ void __launch_bounds__(VX_THREADS) k_voxel_key_hist(const VoxelParams
 // order: the float accumulation below is sequential in that order (one valid order of PCL's CentroidPoint loop, whose
 // own order is unspecified because std::sort is unstable). centroid = sum / (float)n with an IEEE division.
 //
+// The voxels leave the kernel dense and in order: a tile publishes its voxel count as soon as it is known and obtains the
+// number of voxels of all earlier tiles by a decoupled look-back (one warp, 32 tiles per round, epoch-tagged words) that runs
+// while the other warps already sum their first voxel -- the separate scan + compaction launches (and the 56 bytes per voxel
+// they moved) are gone. Tiles are handed out by an arrival ticket, so a tile only ever waits for tiles that are running.
+//
 // Two phases per 2048-item tile, both with every lane busy:
 //   per item  (thread t owns items 8t .. 8t+7): records in with 16-byte loads, neighbour keys by shuffle, head-of-run
 //             and min-points flags as bit masks, the points of surviving runs gathered into shared memory (independent
@@ -452,16 +438,22 @@ __global__ void __launch_bounds__(VX_THREADS, CE_MIN_CTAS) k_voxel_centroid(cons
   __shared__ __align__(16) float4 s_pts[CE_TILE];
   __shared__ uint32_t s_headw[CE_TILE / 32 + 1];  // bit i: item i starts a run; bit tile_n: sentinel
   __shared__ unsigned short s_start[CE_TILE];     // tile-local position of the r-th surviving run
+  __shared__ uint32_t s_tile, s_base;
   const uint32_t tid = threadIdx.x, lane = tid & 31u;
   const uint32_t F = p.n_frames;
   const uint32_t M = p.frame_surv_start[F];
   const uint32_t n_tiles = (M + CE_TILE - 1) / CE_TILE;
-  const uint32_t tile = blockIdx.x;
+  // Tiles are handed out by arrival (a ticket), not by block index: the dense output position of a tile's voxels comes from
+  // a look-back over the tiles before it, and a tile may only wait for tiles that are already running or done.
+  if (tid == 0) s_tile = atomicAdd(&p.ctrl->cent_ticket, 1u);
+  __syncthreads();
+  const uint32_t tile = s_tile;
   if (tile >= n_tiles) return;
 
   const SortInfo si = *p.info;
   const uint32_t idx_bits = si.idx_bits;
   const bool odd = (si.num_passes & 1u) != 0u;
+  const uint32_t epoch = *p.epoch_dev + 9u;  // the radix passes of this run use + 1 .. + 8
   // 32-bit keys arrive as 8-byte (key, value) records, 64-bit keys as two arrays
   const void* __restrict__ sorted = odd ? p.keys_b : p.keys_a;
   const uint32_t* __restrict__ vals = odd ? p.vals_b : p.vals_a;
@@ -570,10 +562,47 @@ __global__ void __launch_bounds__(VX_THREADS, CE_MIN_CTAS) k_voxel_centroid(cons
     }
     if (tid == 0) {
       atomicOr(&s_headw[tile_n >> 5], 1u << (tile_n & 31u));  // sentinel: every run ends at the end of the tile at the latest
-      p.cent_count[tile] = total;  // this tile's voxels go to tmp[tile_base + r]; k_scan_u32 + k_compact_voxels make them dense
+      // this tile's voxel count, published at once: later tiles add it up while this one is still summing its points
+      st_relaxed_u64(p.cent_status + tile, lb_pack(epoch, tile == 0u ? CM_LB_INCL : CM_LB_AGG, total));
     }
   }
   __syncthreads();
+
+  // ---- dense output position of this tile's first voxel: decoupled look-back, one warp, 32 earlier tiles per round -------------
+  // (the other warps go on to their first voxel and meet this one at the barrier before the stores)
+  if (tid < 32) {
+    uint32_t base = 0;
+    if (tile > 0) {
+      long long j = (long long)tile - 1;  // newest tile of the window; lane l looks at tile j - l
+      uint32_t spins = 0;
+      unsigned long long wd0 = 0ull;
+      while (true) {
+        const long long t = j - (long long)lane;
+        // tiles before the first one: an inclusive prefix of zero
+        const unsigned long long w = t >= 0 ? ld_cg_u64(p.cent_status + t) : lb_pack(epoch, CM_LB_INCL, 0u);
+        const uint32_t hi = (uint32_t)(w >> 32);
+        const bool ready = (hi >> 2) == epoch && (hi & 3u) != 0u;
+        if (!__all_sync(0xFFFFFFFFu, ready)) {
+          if (__any_sync(0xFFFFFFFFu, watchdog_expired(spins, wd0))) {
+            atomicExch(&p.ctrl->error, (uint32_t)CM_DEV_E_INTERNAL);
+            break;
+          }
+          if (spins > 4) __nanosleep(30);
+          continue;
+        }
+        const uint32_t incl = __ballot_sync(0xFFFFFFFFu, (hi & 3u) == CM_LB_INCL);
+        const uint32_t stop = incl ? (uint32_t)__ffs(incl) - 1u : 32u;  // nearest tile that already knows its inclusive prefix
+        base += warp_sum_u32(lane <= stop ? (uint32_t)w : 0u);
+        if (incl) break;
+        j -= 32;
+      }
+      if (lane == 0) st_relaxed_u64(p.cent_status + tile, lb_pack(epoch, CM_LB_INCL, base + total));
+    }
+    if (lane == 0) {
+      s_base = base;
+      if (tile == n_tiles - 1u) p.ctrl->total_voxels = base + total;
+    }
+  }
 
   // per-frame voxel counts: one atomic per tile unless the tile straddles frames
   bool per_voxel_count = false;
@@ -590,7 +619,9 @@ __global__ void __launch_bounds__(VX_THREADS, CE_MIN_CTAS) k_voxel_centroid(cons
   }
 
   // ---- per voxel ----------------------------------------------------------------------------------------------------
-  for (uint32_t r = tid; r < total; r += VX_THREADS) {
+  // The first voxel of every thread is summed BEFORE the barrier that delivers the tile's output position, so the look-back
+  // of warp 0 hides behind it; further voxels (tiles with more than 256 surviving runs) follow after the barrier.
+  auto voxel = [&](uint32_t r, float4& cen, uint32_t& n_out, KeyT& key_out) {
     const uint32_t s0 = s_start[r];
     const KeyT key = key_at(tile_base + s0);
     // end of the run inside the tile: the next head bit after s0 (the sentinel at tile_n bounds the search)
@@ -614,39 +645,35 @@ __global__ void __launch_bounds__(VX_THREADS, CE_MIN_CTAS) k_voxel_centroid(cons
       }
     }
     const float nf = (float)n;
-    const float cx = __fdiv_rn(sx, nf), cy = __fdiv_rn(sy, nf), cz = __fdiv_rn(sz, nf);
-    const float ci = p.downsample_all ? __fdiv_rn(sw, nf) : 0.f;
-    const uint32_t slot = tile_base + r;
-    reinterpret_cast<float4*>(p.tmp_xyzi)[slot] = make_float4(cx, cy, cz, ci);
-    p.tmp_count[slot] = n;
-    p.tmp_idx[slot] = (unsigned long long)key & idx_mask;
+    cen = make_float4(__fdiv_rn(sx, nf), __fdiv_rn(sy, nf), __fdiv_rn(sz, nf), p.downsample_all ? __fdiv_rn(sw, nf) : 0.f);
+    n_out = n;
+    key_out = key;
+  };
+  auto emit = [&](uint32_t dst, const float4& c, uint32_t n, KeyT key) {
+    if (p.out_step == 32) {  // pcl::PointXYZI record: x y z 1.0f | intensity 0 0 0
+      float4* o = reinterpret_cast<float4*>(reinterpret_cast<uint8_t*>(p.out_xyzi) + (size_t)dst * 32);
+      o[0] = make_float4(c.x, c.y, c.z, 1.0f);
+      o[1] = make_float4(c.w, 0.f, 0.f, 0.f);
+    } else {
+      reinterpret_cast<float4*>(p.out_xyzi)[dst] = c;
+    }
+    p.out_count[dst] = n;
+    p.out_idx[dst] = (unsigned long long)key & idx_mask;
     if (per_voxel_count) {
       const unsigned long long f = (unsigned long long)key >> idx_bits;
       if (f < F) atomicAdd(&p.acc[f].voxel_count, 1u);
     }
-  }
-}
-
-// ---- tile-local voxel records -> dense, ordered output ----------------------------------------------------------------------
-__global__ void __launch_bounds__(VX_THREADS) k_compact_voxels(const VoxelParams p) {
-  const uint32_t M = p.frame_surv_start[p.n_frames];
-  const uint32_t n_tiles = (M + CE_TILE - 1) / CE_TILE;
-  for (uint32_t t = blockIdx.x; t < n_tiles; t += gridDim.x) {
-    const uint32_t d0 = p.cent_count[t];  // exclusive prefix after k_scan_u32
-    const uint32_t d1 = (t + 1 < n_tiles) ? p.cent_count[t + 1] : p.ctrl->total_voxels;
-    const uint32_t src0 = t * CE_TILE;
-    for (uint32_t j = threadIdx.x; j < d1 - d0; j += VX_THREADS) {
-      const float4 c = reinterpret_cast<const float4*>(p.tmp_xyzi)[src0 + j];
-      if (p.out_step == 32) {
-        float4* o = reinterpret_cast<float4*>(reinterpret_cast<uint8_t*>(p.out_xyzi) + (size_t)(d0 + j) * 32);
-        o[0] = make_float4(c.x, c.y, c.z, 1.0f);
-        o[1] = make_float4(c.w, 0.f, 0.f, 0.f);
-      } else {
-        reinterpret_cast<float4*>(p.out_xyzi)[d0 + j] = c;
-      }
-      p.out_count[d0 + j] = p.tmp_count[src0 + j];
-      p.out_idx[d0 + j] = p.tmp_idx[src0 + j];
-    }
+  };
+  float4 c0 = make_float4(0.f, 0.f, 0.f, 0.f);
+  uint32_t n0 = 0;
+  KeyT k0 = (KeyT)0;
+  if (tid < total) voxel(tid, c0, n0, k0);
+  __syncthreads();  // s_base: the look-back of warp 0 is done
+  const uint32_t out0 = s_base;
+  if (tid < total) emit(out0 + tid, c0, n0, k0);
+  for (uint32_t r = tid + VX_THREADS; r < total; r += VX_THREADS) {
+    voxel(r, c0, n0, k0);
+    emit(out0 + r, c0, n0, k0);
   }
 }
 
@@ -729,12 +756,6 @@ cudaError_t launch_centroid(const VoxelParams& p, cudaStream_t stream) {
     k_voxel_centroid<uint32_t><<<tiles, VX_THREADS, 0, stream>>>(p);
   else
     k_voxel_centroid<unsigned long long><<<tiles, VX_THREADS, 0, stream>>>(p);
-  cudaError_t e = cudaGetLastError();
-  if (e != cudaSuccess) return e;
-  k_scan_u32<<<1, SCAN_THREADS, 0, stream>>>(p.cent_count, p.frame_surv_start + p.n_frames, CE_TILE, tiles, &p.ctrl->total_voxels);
-  e = cudaGetLastError();
-  if (e != cudaSuccess) return e;
-  k_compact_voxels<<<persistent_grid(tiles), VX_THREADS, 0, stream>>>(p);
   return cudaGetLastError();
 }
 
