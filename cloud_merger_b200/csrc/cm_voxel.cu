@@ -28,6 +28,12 @@ constexpr int SCAN_THREADS = 1024;
 #ifndef CE_MIN_CTAS
 #define CE_MIN_CTAS 4
 #endif
+#ifndef CE_LB_POLL_ONE
+#define CE_LB_POLL_ONE 0
+#endif
+#ifndef CE_LB_POLL_NS
+#define CE_LB_POLL_NS 30
+#endif
 constexpr int CE_IPT = 8;
 constexpr int CE_TILE = VX_THREADS * CE_IPT;  // 2048 sorted items per centroid tile
 
@@ -443,11 +449,12 @@ __global__ void __launch_bounds__(VX_THREADS, CE_MIN_CTAS) k_voxel_centroid(cons
   const uint32_t F = p.n_frames;
   const uint32_t M = p.frame_surv_start[F];
   const uint32_t n_tiles = (M + CE_TILE - 1) / CE_TILE;
-  // Tiles are handed out by arrival (a ticket), not by block index: the dense output position of a tile's voxels comes from
-  // a look-back over the tiles before it, and a tile may only wait for tiles that are already running or done.
+  // Persistent CTAs; tiles are handed out by arrival (a ticket), not by block index: the dense output position of a tile's
+  // voxels comes from a look-back over the tiles before it, and a tile may only wait for tiles that are already running or
+  // done.
   if (tid == 0) s_tile = atomicAdd(&p.ctrl->cent_ticket, 1u);
   __syncthreads();
-  const uint32_t tile = s_tile;
+  uint32_t tile = s_tile;
   if (tile >= n_tiles) return;
 
   const SortInfo si = *p.info;
@@ -470,80 +477,120 @@ __global__ void __launch_bounds__(VX_THREADS, CE_MIN_CTAS) k_voxel_centroid(cons
   const unsigned long long idx_mask = idx_bits >= 64 ? ~0ull : ((1ull << idx_bits) - 1ull);
   const uint32_t m_req = p.min_points > 1u ? p.min_points : 1u;
 
+  const uint32_t loc = tid * CE_IPT;  // tile-local index of this thread's first item
+
+  // keys (and point slots) of this thread's eight items of the tile at tile_base, and what they say about runs:
+  //   head bit j: item j starts a run; pass bit j: ... a run that survives the min-points filter; need bit j: its point is summed
+  auto item_flags = [&](uint32_t tile_base, KeyT (&k)[CE_IPT], uint32_t (&v)[CE_IPT], bool want_vals, uint32_t& head, uint32_t& pass,
+                        uint32_t& need) {
+    const uint32_t base = tile_base + loc;
+    if (base + CE_IPT <= M) {
+      if constexpr (REC) {
+        const uint4* src = reinterpret_cast<const uint4*>(reinterpret_cast<const uint2*>(sorted) + base);
+#pragma unroll
+        for (int j = 0; j < CE_IPT; j += 2) {
+          const uint4 r = src[j / 2];
+          k[j] = (KeyT)r.x; v[j] = r.y; k[j + 1] = (KeyT)r.z; v[j + 1] = r.w;
+        }
+      } else {
+        const ulonglong2* ks = reinterpret_cast<const ulonglong2*>(reinterpret_cast<const KeyT*>(sorted) + base);
+#pragma unroll
+        for (int j = 0; j < CE_IPT; j += 2) {
+          const ulonglong2 r = ks[j / 2];
+          k[j] = (KeyT)r.x; k[j + 1] = (KeyT)r.y;
+        }
+        if (want_vals) {
+          const uint4* vs = reinterpret_cast<const uint4*>(vals + base);
+#pragma unroll
+          for (int j = 0; j < CE_IPT; j += 4) {
+            const uint4 r = vs[j / 4];
+            v[j] = r.x; v[j + 1] = r.y; v[j + 2] = r.z; v[j + 3] = r.w;
+          }
+        }
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < CE_IPT; ++j) {
+        const bool in = base + j < M;
+        k[j] = in ? key_at(base + j) : (KeyT)0;
+        v[j] = (in && want_vals) ? val_at(base + j) : 0u;
+      }
+    }
+    // keys of the items just before and just after this thread's eight
+    KeyT prev = (KeyT)__shfl_up_sync(0xFFFFFFFFu, k[CE_IPT - 1], 1);
+    KeyT next = (KeyT)__shfl_down_sync(0xFFFFFFFFu, k[0], 1);
+    if (lane == 0 && base > 0 && base < M) prev = key_at(base - 1);
+    if (lane == 31 && base + CE_IPT < M) next = key_at(base + CE_IPT);
+    // eq bit j: item j exists and continues the run of item j-1 (bit CE_IPT: the item after this thread's last)
+    uint32_t eq = 0, valid = 0;
+#pragma unroll
+    for (int j = 0; j < CE_IPT; ++j) {
+      const bool in = base + j < M;
+      const KeyT before = j == 0 ? prev : k[j - 1];
+      valid |= (in ? 1u : 0u) << j;
+      eq |= ((in && (base + j > 0) && k[j] == before) ? 1u : 0u) << j;
+    }
+    eq |= ((base + CE_IPT < M && next == k[CE_IPT - 1]) ? 1u : 0u) << CE_IPT;
+    head = valid & ~eq;  // bits 0..7
+    // which heads survive the min-points filter, and which points are therefore needed
+    pass = head; need = valid;
+    if (m_req == 2u) {
+      pass = head & (eq >> 1);          // the next item continues the run
+      need = valid & (eq | (eq >> 1));  // the item has an equal neighbour
+    } else if (m_req > 2u) {
+      pass = 0;
+#pragma unroll
+      for (int j = 0; j < CE_IPT; ++j) {
+        if (head & (1u << j)) {
+          const unsigned long long i2 = (unsigned long long)base + j + m_req - 1ull;
+          if (i2 < (unsigned long long)M && key_at((uint32_t)i2) == k[j]) pass |= 1u << j;
+        }
+      }
+    }
+    if (has_sentinel) {
+#pragma unroll
+      for (int j = 0; j < CE_IPT; ++j)
+        if ((unsigned long long)k[j] >= limit) pass &= ~(1u << j);
+    }
+  };
+
+  // The voxel count of a tile, published the moment the tile is claimed -- a whole tile-time before any later tile looks for
+  // it: the CTA counts its NEXT tile (keys only: one coalesced sweep, no point gathers) before it works on the current one.
+  // With the counts that early, the look-back further down never waits for a tile that is still busy; without this, every tile
+  // stalled for the slowest of its ~600 co-resident predecessors and the launch took 0.18 ms instead of 0.12 (measured).
+  auto count_and_publish = [&](uint32_t t) -> uint32_t {
+    KeyT k[CE_IPT];
+    uint32_t v[CE_IPT];
+    uint32_t head, pass, need;
+    item_flags(t * CE_TILE, k, v, false, head, pass, need);
+    const uint32_t wsum = warp_sum_u32((uint32_t)__popc(pass));
+    __syncthreads();  // s_scan is free (the previous tile's scans are over)
+    if (lane == 0) s_scan[tid >> 5] = wsum;
+    __syncthreads();
+    uint32_t tot = 0;
+#pragma unroll
+    for (int w = 0; w < VX_THREADS / 32; ++w) tot += s_scan[w];
+    if (tid == 0) st_relaxed_u64(p.cent_status + t, lb_pack(epoch, t == 0u ? CM_LB_INCL : CM_LB_AGG, tot));
+    __syncthreads();
+    return tot;
+  };
+
+  count_and_publish(tile);
+  while (true) {
+  // claim and count the next tile first
+  if (tid == 0) s_tile = atomicAdd(&p.ctrl->cent_ticket, 1u);
+  __syncthreads();
+  const uint32_t next_tile = s_tile;
+  if (next_tile < n_tiles) count_and_publish(next_tile);
+
   const uint32_t tile_base = tile * CE_TILE;
   const uint32_t tile_n = min((uint32_t)CE_TILE, M - tile_base);
-  const uint32_t loc = tid * CE_IPT;  // tile-local index of this thread's first item
-  const uint32_t base = tile_base + loc;
 
   // ---- per item -----------------------------------------------------------------------------------------------------
   KeyT k[CE_IPT];
   uint32_t v[CE_IPT];
-  if (base + CE_IPT <= M) {
-    if constexpr (REC) {
-      const uint4* src = reinterpret_cast<const uint4*>(reinterpret_cast<const uint2*>(sorted) + base);
-#pragma unroll
-      for (int j = 0; j < CE_IPT; j += 2) {
-        const uint4 r = src[j / 2];
-        k[j] = (KeyT)r.x; v[j] = r.y; k[j + 1] = (KeyT)r.z; v[j + 1] = r.w;
-      }
-    } else {
-      const ulonglong2* ks = reinterpret_cast<const ulonglong2*>(reinterpret_cast<const KeyT*>(sorted) + base);
-      const uint4* vs = reinterpret_cast<const uint4*>(vals + base);
-#pragma unroll
-      for (int j = 0; j < CE_IPT; j += 2) {
-        const ulonglong2 r = ks[j / 2];
-        k[j] = (KeyT)r.x; k[j + 1] = (KeyT)r.y;
-      }
-#pragma unroll
-      for (int j = 0; j < CE_IPT; j += 4) {
-        const uint4 r = vs[j / 4];
-        v[j] = r.x; v[j + 1] = r.y; v[j + 2] = r.z; v[j + 3] = r.w;
-      }
-    }
-  } else {
-#pragma unroll
-    for (int j = 0; j < CE_IPT; ++j) {
-      const bool in = base + j < M;
-      k[j] = in ? key_at(base + j) : (KeyT)0;
-      v[j] = in ? val_at(base + j) : 0u;
-    }
-  }
-  // keys of the items just before and just after this thread's eight
-  KeyT prev = (KeyT)__shfl_up_sync(0xFFFFFFFFu, k[CE_IPT - 1], 1);
-  KeyT next = (KeyT)__shfl_down_sync(0xFFFFFFFFu, k[0], 1);
-  if (lane == 0 && base > 0 && base < M) prev = key_at(base - 1);
-  if (lane == 31 && base + CE_IPT < M) next = key_at(base + CE_IPT);
-  // eq bit j: item j exists and continues the run of item j-1 (bit CE_IPT: the item after this thread's last)
-  uint32_t eq = 0, valid = 0;
-#pragma unroll
-  for (int j = 0; j < CE_IPT; ++j) {
-    const bool in = base + j < M;
-    const KeyT before = j == 0 ? prev : k[j - 1];
-    valid |= (in ? 1u : 0u) << j;
-    eq |= ((in && (base + j > 0) && k[j] == before) ? 1u : 0u) << j;
-  }
-  eq |= ((base + CE_IPT < M && next == k[CE_IPT - 1]) ? 1u : 0u) << CE_IPT;
-  const uint32_t head = valid & ~eq;  // bits 0..7
-  // which heads survive the min-points filter, and which points are therefore needed
-  uint32_t pass = head, need = valid;
-  if (m_req == 2u) {
-    pass = head & (eq >> 1);          // the next item continues the run
-    need = valid & (eq | (eq >> 1));  // the item has an equal neighbour
-  } else if (m_req > 2u) {
-    pass = 0;
-#pragma unroll
-    for (int j = 0; j < CE_IPT; ++j) {
-      if (head & (1u << j)) {
-        const unsigned long long i2 = (unsigned long long)base + j + m_req - 1ull;
-        if (i2 < (unsigned long long)M && key_at((uint32_t)i2) == k[j]) pass |= 1u << j;
-      }
-    }
-  }
-  if (has_sentinel) {
-#pragma unroll
-    for (int j = 0; j < CE_IPT; ++j)
-      if ((unsigned long long)k[j] >= limit) pass &= ~(1u << j);
-  }
+  uint32_t head, pass, need;
+  item_flags(tile_base, k, v, true, head, pass, need);
 #pragma unroll
   for (int j = 0; j < CE_IPT; ++j)
     if (need & (1u << j)) s_pts[loc + j] = __ldg(p.pts + v[j]);
@@ -562,18 +609,20 @@ __global__ void __launch_bounds__(VX_THREADS, CE_MIN_CTAS) k_voxel_centroid(cons
     }
     if (tid == 0) {
       atomicOr(&s_headw[tile_n >> 5], 1u << (tile_n & 31u));  // sentinel: every run ends at the end of the tile at the latest
-      // this tile's voxel count, published at once: later tiles add it up while this one is still summing its points
-      st_relaxed_u64(p.cent_status + tile, lb_pack(epoch, tile == 0u ? CM_LB_INCL : CM_LB_AGG, total));
     }
   }
   __syncthreads();
 
-  // ---- dense output position of this tile's first voxel: decoupled look-back, one warp, 32 earlier tiles per round -------------
-  // (the other warps go on to their first voxel and meet this one at the barrier before the stores)
+  // ---- dense output position of this tile's first voxel: decoupled look-back, one warp, 32 earlier tiles per round (lane l
+  // looks at tile j - l). The other warps go on to their first voxel and meet this one at the barrier before the stores.
   if (tid < 32) {
     uint32_t base = 0;
+#ifdef CE_DEBUG_NO_LOOKBACK   // timing experiment only (wrong output positions): what the kernel costs without the chain
+    if (false) {
+#else
     if (tile > 0) {
-      long long j = (long long)tile - 1;  // newest tile of the window; lane l looks at tile j - l
+#endif
+      long long j = (long long)tile - 1;  // newest tile of the window
       uint32_t spins = 0;
       unsigned long long wd0 = 0ull;
       while (true) {
@@ -582,12 +631,32 @@ __global__ void __launch_bounds__(VX_THREADS, CE_MIN_CTAS) k_voxel_centroid(cons
         const unsigned long long w = t >= 0 ? ld_cg_u64(p.cent_status + t) : lb_pack(epoch, CM_LB_INCL, 0u);
         const uint32_t hi = (uint32_t)(w >> 32);
         const bool ready = (hi >> 2) == epoch && (hi & 3u) != 0u;
-        if (!__all_sync(0xFFFFFFFFu, ready)) {
+        const uint32_t not_ready = __ballot_sync(0xFFFFFFFFu, !ready);
+        if (not_ready) {
+#if CE_LB_POLL_ONE
+          // wait on the nearest unpublished word with ONE lane, then read the window again
+          const long long wait_for = j - (long long)(__ffs(not_ready) - 1);
+          bool expired = false;
+          if (lane == 0) {
+            while (true) {
+              const unsigned long long x = ld_relaxed_u64(p.cent_status + wait_for);
+              const uint32_t xh = (uint32_t)(x >> 32);
+              if ((xh >> 2) == epoch && (xh & 3u) != 0u) break;
+              if (watchdog_expired(spins, wd0)) { expired = true; break; }
+              __nanosleep(CE_LB_POLL_NS);
+            }
+          }
+          if (__any_sync(0xFFFFFFFFu, expired)) {
+            atomicExch(&p.ctrl->error, (uint32_t)CM_DEV_E_INTERNAL);
+            break;
+          }
+#else
           if (__any_sync(0xFFFFFFFFu, watchdog_expired(spins, wd0))) {
             atomicExch(&p.ctrl->error, (uint32_t)CM_DEV_E_INTERNAL);
             break;
           }
-          if (spins > 4) __nanosleep(30);
+          if (spins > 4) __nanosleep(CE_LB_POLL_NS);
+#endif
           continue;
         }
         const uint32_t incl = __ballot_sync(0xFFFFFFFFu, (hi & 3u) == CM_LB_INCL);
@@ -675,6 +744,10 @@ __global__ void __launch_bounds__(VX_THREADS, CE_MIN_CTAS) k_voxel_centroid(cons
     voxel(r, c0, n0, k0);
     emit(out0 + r, c0, n0, k0);
   }
+  __syncthreads();  // every read of this tile's shared memory is done
+  tile = next_tile;
+  if (tile >= n_tiles) break;
+  }  // while (true): next tile
 }
 
 // ---- host path: the frame's dense voxel outputs -> page-locked (device-mapped) host memory ------------------------------
@@ -752,10 +825,12 @@ cudaError_t launch_key_hist(const VoxelParams& p, cudaStream_t stream) {
 cudaError_t launch_centroid(const VoxelParams& p, cudaStream_t stream) {
   const uint32_t tiles = (p.max_points + CE_TILE - 1) / CE_TILE;
   if (tiles == 0) return cudaSuccess;
+  // persistent: what the device holds at once (tiles are handed out by a ticket)
+  const uint32_t grid = std::min<uint32_t>(tiles, 148u * (uint32_t)CE_MIN_CTAS);
   if (p.key_bytes == 4)
-    k_voxel_centroid<uint32_t><<<tiles, VX_THREADS, 0, stream>>>(p);
+    k_voxel_centroid<uint32_t><<<grid, VX_THREADS, 0, stream>>>(p);
   else
-    k_voxel_centroid<unsigned long long><<<tiles, VX_THREADS, 0, stream>>>(p);
+    k_voxel_centroid<unsigned long long><<<grid, VX_THREADS, 0, stream>>>(p);
   return cudaGetLastError();
 }
 
