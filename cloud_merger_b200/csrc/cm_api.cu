@@ -91,6 +91,7 @@ struct Workspace {
   uint32_t key_bytes = 8, max_passes = 8;
   const float4* voxel_pts = nullptr;  // points the voxel stage read (survivors or the caller's cloud)
   bool ran_k1 = false, ran_voxel = false;
+  bool dual_width = false; // last run: both key widths were enqueued, the device picked one (key_bytes comes with the report)
   bool capturing = false;  // the run is being captured into a graph: its timing events are recorded around the graph launch instead
   int64_t launches = 0;
   cudaStream_t stream = nullptr;
@@ -363,6 +364,7 @@ void fill_voxel_params(cm_handle_t h, Workspace& w, VoxelParams& vp, const float
   vp.epoch_dev = w.epoch_dev;
   vp.lb_sort_words = (uint32_t)std::min<size_t>(w.lb_sort_n, 0xFFFFFFFFu);
   vp.max_passes = CM_MAX_SORT_PASSES;
+  vp.dual_width = 0;
   vp.out_xyzi = w.out_xyzi; vp.out_count = w.out_count; vp.out_idx = w.out_idx;
   vp.trace = w.trace_sort;
   const char* tp = getenv("CM_TRACE_PASS");
@@ -383,6 +385,15 @@ int run_voxel(cm_handle_t h, Workspace& w, VoxelParams& vp, cudaStream_t st, boo
     vp.key_bytes = 8;
     vp.max_passes = CM_MAX_SORT_PASSES;
   }
+  // An unbounded grid (no crop box on x, y, z) has its key width decided on the device. For the VoxelGrid proper the host
+  // then enqueues BOTH key widths of every kernel and the launches that do not apply exit at once (a dozen empty launches,
+  // ~2 us each): no host round trip in the middle of the frame, so cm_merge_frame_async stays asynchronous and the frame
+  // can be captured as a CUDA graph like a bounded one. (The radius outlier removal keeps the round trip: it sizes its
+  // cell table from the plan.)
+  static const bool no_dual = getenv("CM_NO_DUAL") != nullptr;
+  const bool dual = !bounded && with_centroid && !no_dual;
+  w.dual_width = dual;
+  vp.dual_width = dual ? 1u : 0u;
   if (scan_k1_tiles)
     CM_CUDA(h, launch_grid_setup(vp, st, w.tile_rec, w.n_k1_tiles, w.segs, w.n_segs,
                                  reinterpret_cast<uint32_t*>(w.meta + w.ml.off_segstart)));
@@ -390,6 +401,26 @@ int run_voxel(cm_handle_t h, Workspace& w, VoxelParams& vp, cudaStream_t st, boo
     CM_CUDA(h, launch_grid_setup(vp, st));
   ++w.launches;
   if (h->profiling) CM_CUDA(h, cudaEventRecord(w.ev[EV_GRID], st));
+  if (dual) {
+    w.key_bytes = 0;  // known with the report (fetch_report)
+    w.max_passes = CM_MAX_SORT_PASSES;
+    VoxelParams v4 = vp, v8 = vp;
+    v4.key_bytes = 4; v8.key_bytes = 8;
+    CM_CUDA(h, launch_key_hist(v4, st));
+    CM_CUDA(h, launch_key_hist(v8, st));
+    w.launches += 2;
+    if (h->profiling) CM_CUDA(h, cudaEventRecord(w.ev[EV_KEY], st));
+    for (uint32_t ps = 0; ps < 4; ++ps) CM_CUDA(h, launch_sort_pass(v4, (int)ps, st));
+    for (uint32_t ps = 0; ps < CM_MAX_SORT_PASSES; ++ps) CM_CUDA(h, launch_sort_pass(v8, (int)ps, st));
+    w.launches += 4 + CM_MAX_SORT_PASSES;
+    if (h->profiling) CM_CUDA(h, cudaEventRecord(w.ev[EV_SORT], st));
+    CM_CUDA(h, launch_centroid(v4, st));
+    CM_CUDA(h, launch_centroid(v8, st));
+    w.launches += 2 * CM_CENTROID_LAUNCHES;
+    if (!w.capturing) CM_CUDA(h, cudaEventRecord(w.ev[EV_CENT], st));
+    w.ran_voxel = true;
+    return CM_OK;
+  }
   if (!bounded) {
     // the key width is only known on the device: fetch the plan (one small round trip), then size the sort to it
     SortInfo si;
@@ -623,6 +654,7 @@ int fetch_report(cm_handle_t h, Workspace& w, cudaEvent_t already_copied = nullp
     s.voxels_out = ctrl->total_voxels;
     s.key_bits = (int32_t)si->total_bits;
     s.sort_passes = (int32_t)si->num_passes;
+    if (w.dual_width) w.key_bytes = si->total_bits <= 32u ? 4u : 8u;
     s.key_bytes = (int32_t)w.key_bytes;
   }
   const int last_ev = w.ran_voxel ? EV_CENT : EV_K1;
@@ -758,8 +790,8 @@ int merge_async_impl(cm_handle_t h, uint64_t mask, int64_t* ticket) {
   }
   if (segs.empty()) return fail(h, CM_E_NOT_READY, "no submitted cloud for any sensor in the mask");
   // ---- replay / capture / plain enqueue ---------------------------------------------------------------------------------
-  unsigned long long cells = 0;
-  bool graphable = h->use_graph && !h->profiling && crop_cell_bound(h, &cells);  // an unbounded grid needs a host round trip
+  // (an unbounded grid is as capturable as a bounded one: its key width is resolved on the device, see run_voxel)
+  bool graphable = h->use_graph && !h->profiling;
   std::string key;
   if (graphable) {
     key.assign(reinterpret_cast<const char*>(segs.data()), segs.size() * sizeof(cm_segment_t));

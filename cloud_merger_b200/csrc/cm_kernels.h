@@ -70,6 +70,8 @@ struct VoxelParams {
                                      // changes from run to run and a captured launch sequence can be replayed as a graph
   uint32_t lb_sort_words;            // size of lb_sort, for the clear on epoch wrap-around
   uint32_t max_passes;               // how many pass launches the host enqueues
+  uint32_t dual_width;               // the key width is only known on the device (SortInfo.total_bits): the host enqueues the
+                                     // 32-bit AND the 64-bit instantiation of every kernel, the one that does not apply exits
   void* out_xyzi;
   uint32_t* out_count;
   unsigned long long* out_idx;

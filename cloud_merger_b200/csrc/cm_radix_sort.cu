@@ -207,6 +207,7 @@ __global__ void __launch_bounds__(RS_THREADS, RS_MIN_CTAS) k_onesweep_pass(const
   const long long tr0 = clock64();
   const SortInfo si = *p.info;
   if ((uint32_t)pass >= si.num_passes) return;
+  if (p.dual_width && ((si.total_bits <= 32u) != (sizeof(KeyT) == 4))) return;  // the other key width runs
   const uint32_t M = si.n_keys;
   const uint32_t n_tiles = (M + TILE - 1) / TILE;
 

@@ -404,6 +404,7 @@ template <typename KeyT>
 __global__ void __launch_bounds__(VX_THREADS) k_voxel_key_hist(const VoxelParams p) {
   __shared__ uint32_t s_hist[CM_MAX_SORT_PASSES][CM_RADIX];
   const uint32_t tid = threadIdx.x;
+  if (p.dual_width && ((p.info->total_bits <= 32u) != (sizeof(KeyT) == 4))) return;  // the other key width runs
   for (uint32_t i = tid; i < CM_MAX_SORT_PASSES * CM_RADIX; i += VX_THREADS) (&s_hist[0][0])[i] = 0;
   __syncthreads();
   const uint32_t M = p.frame_surv_start[p.n_frames];
@@ -449,6 +450,7 @@ __global__ void __launch_bounds__(VX_THREADS, CE_MIN_CTAS) k_voxel_centroid(cons
   const uint32_t F = p.n_frames;
   const uint32_t M = p.frame_surv_start[F];
   const uint32_t n_tiles = (M + CE_TILE - 1) / CE_TILE;
+  if (p.dual_width && ((p.info->total_bits <= 32u) != (sizeof(KeyT) == 4))) return;  // the other key width runs
   // Persistent CTAs; tiles are handed out by arrival (a ticket), not by block index: the dense output position of a tile's
   // voxels comes from a look-back over the tiles before it, and a tile may only wait for tiles that are already running or
   // done.

@@ -684,3 +684,33 @@ def test_concurrent_handles_sorting_on_one_device(gpu_ok, oracle):
     finally:
         for cm in handles:
             cm.close()
+
+
+def test_unbounded_crop_host_path_is_asynchronous_and_graph_replayed(gpu_ok, oracle):
+    """A crop that does not bound x, y, z (BASELINE config 1: PassThrough z only) leaves the key width to the device: the host
+    enqueues both key widths and never waits in the middle of the frame, so such frames pipeline (merge_async returns before the
+    GPU is done) and replay as CUDA graphs like bounded ones. Frames alternate between a 32-bit and a 64-bit grid."""
+    S, rings, az = 2, 32, 256
+    n = rings * az
+    with CloudMerger(max_sensors=S, max_points_per_sensor=n, frames_in_flight=3) as cm:
+        mats = [synth.extrinsic(s, S) for s in range(S)]
+        for s in range(S):
+            cm.set_extrinsic(s, mats[s])
+        cm.set_crop([(2, -0.5, 3.0, 0)])
+        for leaf, want_bytes in ((0.1, 4), (0.002, 8), (0.1, 4)):
+            cm.set_voxel(leaf, 1, True)
+            tickets, expect = [], []
+            for f in range(3):
+                clouds = [synth.lidar_cloud(640, s, f, rings, az) for s in range(S)]
+                for s in range(S):
+                    cm.submit_cloud(s, clouds[s], n, make_layout(), stamp=f)
+                tickets.append(cm.merge_frame_async())
+                expect.append(oracle.merge_frame([cloud_dict(c, m[:3]) for c, m in zip(clouds, mats)], [(2, -0.5, 3.0, 0)],
+                                                 [leaf] * 3, 1, True, True))
+            for f in range(3):
+                r = cm.wait_frame(tickets[f], capacity=S * n)
+                o = expect[f]
+                assert (r.survivor_src == o["survivor_src"]).all()
+                assert (r.voxel_idx.astype(np.int64) == o["idx"]).all() and (r.voxel_count == o["count"]).all(), (leaf, f)
+                assert_bit_equal(r.voxel_xyzi, o["centroid"], "leaf %g frame %d" % (leaf, f))
+                assert cm.stats().key_bytes == want_bytes
