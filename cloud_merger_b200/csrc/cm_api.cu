@@ -6,6 +6,7 @@
 // There is no CPU implementation behind any entry point: without a CUDA device cm_create fails.
 #include <cuda_runtime.h>
 #include <dlfcn.h>
+#include <sched.h>
 #include <nccl.h>  // types only: the library is loaded at run time (cm_giant_*), see NcclApi
 
 #include <algorithm>
@@ -228,6 +229,62 @@ int fail(cm_handle_t h, int code, const char* fmt, ...) {
                                         __FILE__, __LINE__);                                          \
   } while (0)
 
+// ---- page-locked host memory next to the GPU ---------------------------------------------------------------------------------
+// A frame travels host -> device at PCIe speed only if its pages sit on the NUMA node the GPU hangs off: with one process per
+// GPU and eight GPUs copying at once, arenas that all landed on one node share that node's memory controllers and the
+// inter-socket link. Pages are placed where the allocating thread runs (first touch), so the thread is moved to the CPUs of
+// the current device's node for the duration of the allocation (sysfs: /sys/bus/pci/devices/<bdf>/numa_node). A platform
+// that does not tell (numa_node = -1, single node, restricted cpuset) gets the plain allocation. CM_NO_NUMA=1 switches it off.
+int numa_node_of_current_device() {
+  int dev = 0;
+  char bus[64] = {0};
+  if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetPCIBusId(bus, (int)sizeof(bus), dev) != cudaSuccess) { cudaGetLastError(); return -1; }
+  for (char* c = bus; *c; ++c) *c = (char)tolower(*c);
+  char path[160];
+  snprintf(path, sizeof(path), "/sys/bus/pci/devices/%s/numa_node", bus);
+  FILE* f = fopen(path, "r");
+  if (!f) return -1;
+  int node = -1;
+  if (fscanf(f, "%d", &node) != 1) node = -1;
+  fclose(f);
+  return node;
+}
+bool cpus_of_node(int node, cpu_set_t* set) {
+  char path[96];
+  snprintf(path, sizeof(path), "/sys/devices/system/node/node%d/cpulist", node);
+  FILE* f = fopen(path, "r");
+  if (!f) return false;
+  CPU_ZERO(set);
+  int a = 0, b = 0, n = 0;
+  char sep = 0;
+  while (fscanf(f, "%d", &a) == 1) {
+    b = a;
+    int c = fgetc(f);
+    if (c == '-') { if (fscanf(f, "%d", &b) != 1) break; c = fgetc(f); }
+    for (int k = a; k <= b && k < CPU_SETSIZE; ++k) { CPU_SET(k, set); ++n; }
+    sep = (char)c;
+    if (sep != ',') break;
+  }
+  fclose(f);
+  return n > 0;
+}
+cudaError_t pinned_alloc(void** p, size_t bytes, unsigned flags) {
+  static const bool no_numa = getenv("CM_NO_NUMA") != nullptr;
+  cpu_set_t old_set, local;
+  bool moved = false;
+  if (!no_numa) {
+    const int node = numa_node_of_current_device();
+    if (node >= 0 && cpus_of_node(node, &local) && sched_getaffinity(0, sizeof(old_set), &old_set) == 0) {
+      cpu_set_t both;
+      CPU_AND(&both, &local, &old_set);  // stay inside what the process is allowed to use
+      if (CPU_COUNT(&both) > 0 && !CPU_EQUAL(&both, &old_set)) moved = sched_setaffinity(0, sizeof(both), &both) == 0;
+    }
+  }
+  const cudaError_t e = cudaHostAlloc(p, bytes ? bytes : 1, flags);
+  if (moved) sched_setaffinity(0, sizeof(old_set), &old_set);
+  return e;
+}
+
 template <typename T>
 cudaError_t dev_alloc(T** p, size_t count) {
   return cudaMalloc(reinterpret_cast<void**>(p), std::max<size_t>(count * sizeof(T), kAlign));
@@ -251,7 +308,7 @@ int ws_alloc(cm_handle_t h, Workspace& w, uint32_t points, uint32_t frames, uint
   const size_t np = std::max<uint32_t>(points, 1);
   CM_CUDA(h, dev_alloc(&w.meta, w.ml.total));
   CM_CUDA(h, cudaMemset(w.meta, 0, w.ml.total));
-  CM_CUDA(h, cudaMallocHost(reinterpret_cast<void**>(&w.report), w.ml.total));
+  CM_CUDA(h, pinned_alloc(reinterpret_cast<void**>(&w.report), w.ml.total, cudaHostAllocDefault));
   memset(w.report, 0, w.ml.total);
   CM_CUDA(h, dev_alloc(&w.segs, segs));
   CM_CUDA(h, dev_alloc(&w.surv_xyzi, np));
@@ -699,14 +756,14 @@ int ensure_host_path(cm_handle_t h) {
     int rc = ws_alloc(h, sl.ws, (uint32_t)pts, 1, (uint32_t)c.max_sensors, c.out_point_step);
     if (rc != CM_OK) return rc;
     CM_CUDA(h, cudaMalloc(reinterpret_cast<void**>(&sl.raw_dev), h->slot_stride * c.max_sensors));
-    CM_CUDA(h, cudaMallocHost(reinterpret_cast<void**>(&sl.raw_pinned), h->slot_stride * c.max_sensors));
+    CM_CUDA(h, pinned_alloc(reinterpret_cast<void**>(&sl.raw_pinned), h->slot_stride * c.max_sensors, cudaHostAllocDefault));
     sl.arena_bytes = 2 * h->slot_stride * c.max_sensors;
     CM_CUDA(h, cudaMalloc(reinterpret_cast<void**>(&sl.arena_dev), sl.arena_bytes));
     sl.exp_cap = (uint32_t)pts;
     const size_t ecap = std::max<size_t>(sl.exp_cap, 1);
-    CM_CUDA(h, cudaHostAlloc(reinterpret_cast<void**>(&sl.exp_xyzi), ecap * (size_t)c.out_point_step, cudaHostAllocMapped));
-    CM_CUDA(h, cudaHostAlloc(reinterpret_cast<void**>(&sl.exp_count), ecap * sizeof(uint32_t), cudaHostAllocMapped));
-    CM_CUDA(h, cudaHostAlloc(reinterpret_cast<void**>(&sl.exp_idx), ecap * sizeof(unsigned long long), cudaHostAllocMapped));
+    CM_CUDA(h, pinned_alloc(reinterpret_cast<void**>(&sl.exp_xyzi), ecap * (size_t)c.out_point_step, cudaHostAllocMapped));
+    CM_CUDA(h, pinned_alloc(reinterpret_cast<void**>(&sl.exp_count), ecap * sizeof(uint32_t), cudaHostAllocMapped));
+    CM_CUDA(h, pinned_alloc(reinterpret_cast<void**>(&sl.exp_idx), ecap * sizeof(unsigned long long), cudaHostAllocMapped));
     sl.sensor.resize(c.max_sensors);
     for (auto& ss : sl.sensor) CM_CUDA(h, cudaEventCreateWithFlags(&ss.copied, cudaEventDisableTiming));
     CM_CUDA(h, cudaStreamCreateWithFlags(&sl.stream, cudaStreamNonBlocking));
@@ -1264,7 +1321,7 @@ int cm_merge_frame(cm_handle_t h, uint64_t sensor_mask, cm_frame_out_t* out, uin
 
 int cm_host_alloc(void** p, size_t bytes) {
   if (!p) return CM_E_INVALID;
-  return cudaMallocHost(p, bytes ? bytes : 1) == cudaSuccess ? CM_OK : CM_E_CUDA;
+  return pinned_alloc(p, bytes, cudaHostAllocDefault) == cudaSuccess ? CM_OK : CM_E_CUDA;
 }
 int cm_host_free(void* p) { return cudaFreeHost(p) == cudaSuccess ? CM_OK : CM_E_CUDA; }
 

@@ -302,7 +302,10 @@ CM_API int cm_merge_frame(cm_handle_t h, uint64_t sensor_mask, cm_frame_out_t* o
 CM_API int cm_merge_frame_async(cm_handle_t h, uint64_t sensor_mask, int64_t* ticket);
 CM_API int cm_wait_frame(cm_handle_t h, int64_t ticket, cm_frame_out_t* out, uint64_t* out_used_mask,
                          uint64_t* out_stamp);
-/* Pinned host memory for callers that want true asynchronous H2D/D2H (e.g. the ROS message buffers). */
+/* Pinned host memory for callers that want true asynchronous H2D/D2H (e.g. the ROS message buffers). The pages are placed
+ * on the NUMA node of the CURRENT CUDA device (cudaSetDevice before the call; the library's own staging buffers follow the
+ * handle's device) where the platform tells which node that is -- eight processes feeding eight GPUs from arenas that all
+ * landed on one node share one set of memory controllers. CM_NO_NUMA=1 in the environment switches the placement off. */
 CM_API int cm_host_alloc(void** p, size_t bytes);
 CM_API int cm_host_free(void* p);
 
