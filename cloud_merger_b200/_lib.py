@@ -129,6 +129,11 @@ class CmFrameOut(C.Structure):
                 ("info", CmFrameInfo)]
 
 
+class CmFrameView(C.Structure):
+    _fields_ = [("voxel_xyzi", C.c_void_p), ("voxel_count", C.c_void_p), ("voxel_idx", C.c_void_p), ("n_voxels", C.c_int64),
+                ("n_survivors", C.c_int64), ("info", CmFrameInfo), ("used_mask", C.c_uint64), ("stamp", C.c_uint64)]
+
+
 # every symbol include/cloud_merger_gpu.h declares: name -> (restype, argtypes)
 _H = C.c_void_p
 SYMBOLS = {
@@ -155,6 +160,7 @@ SYMBOLS = {
     "cm_merge_frame": (C.c_int, [_H, C.c_uint64, C.POINTER(CmFrameOut), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
     "cm_merge_frame_async": (C.c_int, [_H, C.c_uint64, C.POINTER(C.c_int64)]),
     "cm_wait_frame": (C.c_int, [_H, C.c_int64, C.POINTER(CmFrameOut), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
+    "cm_wait_frame_view": (C.c_int, [_H, C.c_int64, C.POINTER(CmFrameView)]),
     "cm_host_alloc": (C.c_int, [C.POINTER(C.c_void_p), C.c_size_t]),
     "cm_host_free": (C.c_int, [C.c_void_p]),
     "cm_run_batch": (C.c_int, [_H, C.POINTER(CmSegment), C.c_int, C.c_void_p]),

@@ -554,6 +554,24 @@ class CloudMerger:
         self._check(self._lib.cm_wait_frame(self._h, ticket, C.byref(out), None, None))
         return out
 
+    def wait_frame_view(self, ticket: int, view: Optional["_lib.CmFrameView"] = None):
+        """cm_wait_frame_view: one synchronisation, no copy -- the returned struct points into the library's page-locked
+        result mirrors of that frame (valid until frames_in_flight further frames have been merged). view_arrays() wraps
+        them as numpy arrays without copying."""
+        v = view if view is not None else _lib.CmFrameView()
+        self._check(self._lib.cm_wait_frame_view(self._h, ticket, C.byref(v)))
+        return v
+
+    def view_arrays(self, v) -> dict:
+        n, step_f = int(v.n_voxels), self.out_point_step // 4
+        if n == 0:
+            return dict(voxel_xyzi=np.zeros((0, step_f), np.float32), voxel_count=np.zeros(0, np.uint32), voxel_idx=np.zeros(0, np.uint64))
+
+        def arr(ptr, dtype, count):
+            return np.frombuffer((C.c_uint8 * (count * np.dtype(dtype).itemsize)).from_address(ptr), dtype=dtype, count=count)
+        return dict(voxel_xyzi=arr(v.voxel_xyzi, np.float32, n * step_f).reshape(n, step_f), voxel_count=arr(v.voxel_count, np.uint32, n),
+                    voxel_idx=arr(v.voxel_idx, np.uint64, n))
+
     def wait_frame(self, ticket: int, capacity: int, want_survivors: bool = True) -> FrameResult:
         out, bufs = self._make_out(capacity, capacity, want_survivors)
         used, stamp = C.c_uint64(), C.c_uint64()

@@ -1309,6 +1309,31 @@ int cm_wait_frame(cm_handle_t h, int64_t ticket, cm_frame_out_t* out, uint64_t* 
   return wait_impl(h, ticket, out, out_used_mask, out_stamp);
 }
 
+int cm_wait_frame_view(cm_handle_t h, int64_t ticket, cm_frame_view_t* view) {
+  if (!h || !view) return CM_E_INVALID;
+  std::lock_guard<std::mutex> lk(h->mu);
+  CM_CUDA(h, cudaSetDevice(h->device));
+  Slot* sl = nullptr;
+  for (auto& s : h->slots) if (s.busy && s.ticket == ticket) sl = &s;
+  if (!sl) return fail(h, CM_E_INVALID, "unknown ticket %lld", (long long)ticket);
+  uint64_t used = 0, stamp = 0;
+  int rc = wait_impl(h, ticket, nullptr, &used, &stamp);  // one synchronisation; nothing is copied
+  if (rc != CM_OK) return rc;
+  const cm_frame_info_t& fi = h->frame_info[0];
+  memset(view, 0, sizeof(*view));
+  view->info = fi;
+  view->n_survivors = fi.survivor_end - fi.survivor_begin;
+  view->n_voxels = fi.voxel_end - fi.voxel_begin;
+  view->used_mask = used; view->stamp = stamp;
+  if (h->overflow_mode == 1 && fi.pcl_overflow)
+    return fail(h, CM_E_INVALID, "PCL would refuse this frame (leaf too small): its result is the merged cloud, use cm_wait_frame");
+  if ((uint64_t)view->n_voxels > sl->exp_cap) return fail(h, CM_E_CAPACITY, "more voxels than the result mirror holds");
+  view->voxel_xyzi = sl->exp_xyzi;
+  view->voxel_count = sl->exp_count;
+  view->voxel_idx = reinterpret_cast<const uint64_t*>(sl->exp_idx);
+  return CM_OK;
+}
+
 int cm_merge_frame(cm_handle_t h, uint64_t sensor_mask, cm_frame_out_t* out, uint64_t* out_used_mask, uint64_t* out_stamp) {
   if (!h) return CM_E_INVALID;
   std::lock_guard<std::mutex> lk(h->mu);

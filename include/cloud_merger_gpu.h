@@ -302,6 +302,19 @@ CM_API int cm_merge_frame(cm_handle_t h, uint64_t sensor_mask, cm_frame_out_t* o
 CM_API int cm_merge_frame_async(cm_handle_t h, uint64_t sensor_mask, int64_t* ticket);
 CM_API int cm_wait_frame(cm_handle_t h, int64_t ticket, cm_frame_out_t* out, uint64_t* out_used_mask,
                          uint64_t* out_stamp);
+/* Zero-copy form of cm_wait_frame: instead of copying the voxels into caller buffers it hands out pointers into the
+ * library's own page-locked result mirrors of that frame -- the frame's stream wrote them there itself. The view stays valid
+ * until frames_in_flight further frames have been merged on the handle (the frame slot is reused then). With PCL-like
+ * overflow mode and a frame PCL would refuse, use cm_wait_frame (the result is the merged cloud, which has no mirror). */
+typedef struct {
+  const void* voxel_xyzi;       /* HOST, page-locked: [n_voxels] records of out_point_step bytes */
+  const uint32_t* voxel_count;  /* HOST [n_voxels] */
+  const uint64_t* voxel_idx;    /* HOST [n_voxels] */
+  int64_t n_voxels, n_survivors;
+  cm_frame_info_t info;
+  uint64_t used_mask, stamp;
+} cm_frame_view_t;
+CM_API int cm_wait_frame_view(cm_handle_t h, int64_t ticket, cm_frame_view_t* view);
 /* Pinned host memory for callers that want true asynchronous H2D/D2H (e.g. the ROS message buffers). The pages are placed
  * on the NUMA node of the CURRENT CUDA device (cudaSetDevice before the call; the library's own staging buffers follow the
  * handle's device) where the platform tells which node that is -- eight processes feeding eight GPUs from arenas that all

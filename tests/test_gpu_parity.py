@@ -714,3 +714,34 @@ def test_unbounded_crop_host_path_is_asynchronous_and_graph_replayed(gpu_ok, ora
                 assert (r.voxel_idx.astype(np.int64) == o["idx"]).all() and (r.voxel_count == o["count"]).all(), (leaf, f)
                 assert_bit_equal(r.voxel_xyzi, o["centroid"], "leaf %g frame %d" % (leaf, f))
                 assert cm.stats().key_bytes == want_bytes
+
+
+def test_wait_frame_view_is_the_same_result_without_a_copy(gpu_ok, oracle):
+    """cm_wait_frame_view: pointers into the frame's page-locked result mirrors (written by the frame's own stream) instead of
+    copies into caller buffers; three frames in flight, both record layouts."""
+    S, n = 3, 5000
+    for step in (16, 32):
+        with CloudMerger(max_sensors=S, max_points_per_sensor=n, frames_in_flight=3, out_point_step=step) as cm:
+            mats = [synth.extrinsic(s, S) for s in range(S)]
+            for s in range(S):
+                cm.set_extrinsic(s, mats[s])
+            cm.set_crop(synth.ROI_BOX)
+            cm.set_voxel(0.2, 1, True)
+            tickets, expect = [], []
+            for f in range(3):
+                clouds = [synth.lidar_cloud(66, s, f, 10, n // 10) for s in range(S)]
+                for s in range(S):
+                    cm.submit_cloud(s, clouds[s], n, make_layout(), stamp=10 + f)
+                tickets.append(cm.merge_frame_async())
+                expect.append(oracle.merge_frame([cloud_dict(c, m[:3]) for c, m in zip(clouds, mats)], synth.ROI_BOX, [0.2] * 3, 1, True, True))
+            for f in range(3):
+                v = cm.wait_frame_view(tickets[f])
+                a = cm.view_arrays(v)
+                o = expect[f]
+                assert v.n_voxels == o["n_voxels"] > 50 and v.n_survivors == o["n_survivors"] and v.stamp == 10 + f and v.used_mask == 0b111
+                assert (a["voxel_idx"].astype(np.int64) == o["idx"]).all() and (a["voxel_count"] == o["count"]).all()
+                rec = a["voxel_xyzi"]
+                xyzi = rec if step == 16 else np.concatenate([rec[:, 0:3], rec[:, 4:5]], axis=1)
+                assert_bit_equal(xyzi, o["centroid"], "frame %d (view, %d-byte records)" % (f, step))
+                if step == 32:
+                    assert (rec[:, 3] == 1.0).all()
