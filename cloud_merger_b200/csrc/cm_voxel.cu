@@ -28,6 +28,9 @@ constexpr int SCAN_THREADS = 1024;
 #ifndef CE_MIN_CTAS
 #define CE_MIN_CTAS 4
 #endif
+#ifndef CE_PREFETCH
+#define CE_PREFETCH 0   // tried: L2 prefetch of the next tile's points from the count sweep. cfg3 batch: no change (0.148 vs 0.146 ms);
+#endif                  // cfg5 sweep: 17 % SLOWER (every point is gathered there and the prefetch only adds requests). Off.
 #ifndef CE_LB_POLL_ONE
 #define CE_LB_POLL_ONE 0
 #endif
@@ -446,6 +449,7 @@ __global__ void __launch_bounds__(VX_THREADS, CE_MIN_CTAS) k_voxel_centroid(cons
   __shared__ uint32_t s_headw[CE_TILE / 32 + 1];  // bit i: item i starts a run; bit tile_n: sentinel
   __shared__ unsigned short s_start[CE_TILE];     // tile-local position of the r-th surviving run
   __shared__ uint32_t s_tile, s_base;
+  __shared__ uint32_t s_cnt8[VX_THREADS / 32];
   const uint32_t tid = threadIdx.x, lane = tid & 31u;
   const uint32_t F = p.n_frames;
   const uint32_t M = p.frame_surv_start[F];
@@ -560,21 +564,28 @@ __global__ void __launch_bounds__(VX_THREADS, CE_MIN_CTAS) k_voxel_centroid(cons
   // it: the CTA counts its NEXT tile (keys only: one coalesced sweep, no point gathers) before it works on the current one.
   // With the counts that early, the look-back further down never waits for a tile that is still busy; without this, every tile
   // stalled for the slowest of its ~600 co-resident predecessors and the launch took 0.18 ms instead of 0.12 (measured).
-  auto count_and_publish = [&](uint32_t t) -> uint32_t {
+  // (CE_PREFETCH: the count sweep can also ask L2 for the points the tile will gather one tile-time later; measured, it does
+  // not pay -- see the macro.)
+  auto count_and_publish = [&](uint32_t t) {
     KeyT k[CE_IPT];
     uint32_t v[CE_IPT];
     uint32_t head, pass, need;
-    item_flags(t * CE_TILE, k, v, false, head, pass, need);
-    const uint32_t wsum = warp_sum_u32((uint32_t)__popc(pass));
-    __syncthreads();  // s_scan is free (the previous tile's scans are over)
-    if (lane == 0) s_scan[tid >> 5] = wsum;
-    __syncthreads();
-    uint32_t tot = 0;
+    item_flags(t * CE_TILE, k, v, CE_PREFETCH != 0, head, pass, need);
+#if CE_PREFETCH
 #pragma unroll
-    for (int w = 0; w < VX_THREADS / 32; ++w) tot += s_scan[w];
-    if (tid == 0) st_relaxed_u64(p.cent_status + t, lb_pack(epoch, t == 0u ? CM_LB_INCL : CM_LB_AGG, tot));
+    for (int j = 0; j < CE_IPT; ++j)
+      if (need & (1u << j)) asm volatile("prefetch.global.L2 [%0];" ::"l"(p.pts + v[j]));
+#endif
+    const uint32_t wsum = warp_sum_u32((uint32_t)__popc(pass));
+    // s_cnt8 is this lambda's own scratch: its previous use lies a whole tile (several barriers) back
+    if (lane == 0) s_cnt8[tid >> 5] = wsum;
     __syncthreads();
-    return tot;
+    if (tid == 0) {
+      uint32_t tot = 0;
+#pragma unroll
+      for (int w = 0; w < VX_THREADS / 32; ++w) tot += s_cnt8[w];
+      st_relaxed_u64(p.cent_status + t, lb_pack(epoch, t == 0u ? CM_LB_INCL : CM_LB_AGG, tot));
+    }
   };
 
   count_and_publish(tile);
