@@ -671,14 +671,19 @@ def main():
     # ---- roofline: algorithmic bytes per launch / CUDA-event duration of that launch ----------------------------------
     peak, peak_src = peaks()
     stage_ms = {k: v / args.steps for k, v in stage_acc.items()}
+    # K1 writes the voxel keys itself (4 B per survivor, at the survivor's slot) when the crop box bounds the grid: there is
+    # then no key kernel, and radix pass 0 reads 4-byte keys instead of 8-byte records
+    fused_keys = stage_ms["key_hist"] < 0.01
     algo = {
-        "transform_crop": pts_step * 16 + M * 20,
+        "transform_crop": pts_step * 16 + M * (24 if fused_keys else 20),
         "key_hist": M * (16 + kb + 4),
-        "sort": M * (2 * (kb + 4) * P),
+        "sort": M * (2 * (kb + 4) * P) - (4 * M if fused_keys else 0),
         "centroid": M * (kb + 4 + 16) + V * 28,
     }
     stages = {}
     for k in ("transform_crop", "key_hist", "sort", "centroid"):
+        if k == "key_hist" and fused_keys:
+            continue
         ms = stage_ms[k]
         gbs = algo[k] / (ms * 1e-3) / 1e9 if ms > 0 else 0.0
         stages[k] = {"ms": round(ms, 4), "algorithmic_bytes": int(algo[k]), "achieved_gbs": round(gbs, 1),
@@ -798,6 +803,7 @@ def main():
                        "points_per_frame": S * n, "points_per_step_per_gpu": pts_step, "leaf_m": spec["leaf"],
                        "min_points": spec["min_points"], "crop": spec["passes"], "survivors_per_step": M,
                        "voxels_per_step": V, "key_bytes": kb, "sort_passes": P, "key_bits": int(st.key_bits),
+                       "keys_from": "k_transform_crop (crop-box grid)" if fused_keys else "k_voxel_key_hist",
                        "sharding": "frames round-robin over ranks, no collective",
                        "timed_region": "K steps enqueued back to back on one stream, one report read at the end; stage times = last timed step",
                        "l2": "inputs larger than L2 (%.0f MB raw input per step per GPU)" % (pts_step * 16 / 1e6)},

@@ -66,6 +66,10 @@ struct Workspace {
   std::vector<uint32_t> tile_seg_host;
   float4* surv_xyzi = nullptr;
   uint32_t* surv_src = nullptr;
+  uint32_t* surv_key = nullptr;          // box-grid voxel keys written by K1 (fused-key runs)
+  uint32_t* first_k1 = nullptr;          // [sort tiles] K1 tile holding the first key of every radix tile
+  bool fused_keys = false;               // last run: K1 produced the keys
+  BoxGrid box{};
   void *keys_a = nullptr, *keys_b = nullptr;
   uint32_t *vals_a = nullptr, *vals_b = nullptr;
   TileRec* tile_rec = nullptr;          // [lb_k1_n] K1 tile records
@@ -293,6 +297,7 @@ cudaError_t dev_alloc(T** p, size_t count) {
 void ws_free(Workspace& w) {
   if (!w.ready) return;
   cudaFree(w.meta); cudaFreeHost(w.report); cudaFree(w.segs); cudaFree(w.tile_seg); cudaFree(w.surv_xyzi); cudaFree(w.surv_src);
+  cudaFree(w.surv_key); cudaFree(w.first_k1);
   cudaFree(w.keys_a); cudaFree(w.keys_b); cudaFree(w.vals_a); cudaFree(w.vals_b);
   cudaFree(w.tile_rec); cudaFree(w.lb_sort); cudaFree(w.cent_status); cudaFree(w.epoch_dev);
   cudaFree(w.dense_xyzi); cudaFree(w.dense_src); cudaFree(w.dense_slot);
@@ -313,6 +318,8 @@ int ws_alloc(cm_handle_t h, Workspace& w, uint32_t points, uint32_t frames, uint
   CM_CUDA(h, dev_alloc(&w.segs, segs));
   CM_CUDA(h, dev_alloc(&w.surv_xyzi, np));
   CM_CUDA(h, dev_alloc(&w.surv_src, np));
+  CM_CUDA(h, dev_alloc(&w.surv_key, np));
+  CM_CUDA(h, dev_alloc(&w.first_k1, sort_lookback_rows((uint32_t)np)));
   CM_CUDA(h, cudaMalloc(&w.keys_a, np * 8));
   CM_CUDA(h, cudaMalloc(&w.keys_b, np * 8));
   CM_CUDA(h, dev_alloc(&w.vals_a, np));
@@ -397,6 +404,32 @@ bool crop_cell_bound(cm_handle_t h, unsigned long long* cells) {
   return true;
 }
 
+// The voxel grid of the crop BOX (cm_set_crop chains that are one box bounding x, y and z): it contains the grid PCL derives
+// from the data of any frame, so K1 can key the survivors against it (see BoxGrid). false: not a bounding box / too many cells.
+bool crop_box_grid(cm_handle_t h, uint32_t n_frames, BoxGrid* g) {
+  const CropDev& c = h->crop;
+  if (!c.is_box) return false;
+  const float fmax = std::numeric_limits<float>::max();
+  unsigned long long div[3];
+  for (int a = 0; a < 3; ++a) {
+    if (!(c.lo[a] > -fmax) || !(c.hi[a] < fmax) || !(c.hi[a] >= c.lo[a])) return false;
+    const float flo = std::floor(c.lo[a] * h->inv_leaf[a]), fhi = std::floor(c.hi[a] * h->inv_leaf[a]);
+    if (!(std::fabs(flo) < 1e9f) || !(std::fabs(fhi) < 1e9f)) return false;
+    g->inv[a] = h->inv_leaf[a];
+    g->min_b[a] = (int32_t)flo;
+    div[a] = (unsigned long long)((long long)fhi - (long long)flo + 1);
+    if (div[a] > (1ull << 21)) return false;
+  }
+  const unsigned long long cells = div[0] * div[1] * div[2];
+  const uint32_t idx_bits = bits_for(cells), bits = idx_bits + bits_for(n_frames);
+  if (bits > 32u || cells > 0xFFFFFFFFull) return false;
+  g->mul1 = (uint32_t)div[0];
+  g->mul2 = (uint32_t)(div[0] * div[1]);
+  g->idx_bits = idx_bits;
+  g->n_pass = std::max<uint32_t>(1u, (bits + CM_RADIX_BITS - 1) / CM_RADIX_BITS);
+  return true;
+}
+
 void fill_voxel_params(cm_handle_t h, Workspace& w, VoxelParams& vp, const float4* pts, uint32_t n_frames,
                        uint32_t max_points) {
   vp.pts = pts;
@@ -421,6 +454,8 @@ void fill_voxel_params(cm_handle_t h, Workspace& w, VoxelParams& vp, const float
   vp.epoch_dev = w.epoch_dev;
   vp.lb_sort_words = (uint32_t)std::min<size_t>(w.lb_sort_n, 0xFFFFFFFFu);
   vp.max_passes = CM_MAX_SORT_PASSES;
+  vp.fused_keys = 0; vp.surv_key = w.surv_key; vp.box = BoxGrid{}; vp.first_k1 = w.first_k1;
+  vp.sort_tile = sort_tile_items(4, max_points);
   vp.dual_width = 0;
   vp.out_xyzi = w.out_xyzi; vp.out_count = w.out_count; vp.out_idx = w.out_idx;
   vp.trace = w.trace_sort;
@@ -433,8 +468,11 @@ int run_voxel(cm_handle_t h, Workspace& w, VoxelParams& vp, cudaStream_t st, boo
               bool with_centroid = true, int known_idx_bits = -1) {
   unsigned long long cells = 0;
   // known_idx_bits: the caller already knows an upper bound of the voxel-index width (giant-cloud mode: from the global grid)
-  const bool bounded = known_idx_bits >= 0 || (w.ran_k1 && crop_cell_bound(h, &cells));
-  if (bounded) {
+  const bool bounded = vp.fused_keys || known_idx_bits >= 0 || (w.ran_k1 && crop_cell_bound(h, &cells));
+  if (vp.fused_keys) {  // K1 keyed the survivors against the crop box's grid and counted the digits
+    vp.key_bytes = 4;
+    vp.max_passes = vp.box.n_pass;
+  } else if (bounded) {
     const uint32_t bits = (known_idx_bits >= 0 ? (uint32_t)known_idx_bits : bits_for(cells)) + bits_for(vp.n_frames);
     vp.key_bytes = bits <= 32 ? 4 : 8;
     vp.max_passes = std::max<uint32_t>(1, (bits + CM_RADIX_BITS - 1) / CM_RADIX_BITS);
@@ -490,8 +528,10 @@ int run_voxel(cm_handle_t h, Workspace& w, VoxelParams& vp, cudaStream_t st, boo
   }
   w.key_bytes = vp.key_bytes;
   w.max_passes = vp.max_passes;
-  CM_CUDA(h, launch_key_hist(vp, st));
-  ++w.launches;
+  if (!vp.fused_keys) {
+    CM_CUDA(h, launch_key_hist(vp, st));
+    ++w.launches;
+  }
   if (h->profiling) CM_CUDA(h, cudaEventRecord(w.ev[EV_KEY], st));
   for (uint32_t ps = 0; ps < vp.max_passes; ++ps) {
     CM_CUDA(h, launch_sort_pass(vp, (int)ps, st));
@@ -638,6 +678,15 @@ int run_pipeline(cm_handle_t h, Workspace& w, const cm_segment_t* segs, int n_se
   kp.acc = reinterpret_cast<FrameAcc*>(w.meta + w.ml.off_acc);
   kp.tile_rec = w.tile_rec;
   kp.trace = w.trace_k1;
+  // K1 keys the survivors itself when the crop is a box that bounds the grid (no k_voxel_key_hist): CM_NO_FUSED_KEYS=1 keeps
+  // the separate key kernel (A/B and test hook)
+  static const bool no_fused = getenv("CM_NO_FUSED_KEYS") != nullptr;
+  BoxGrid box{};
+  const bool fused = with_voxel && !no_fused && crop_box_grid(h, n_frames, &box);
+  w.fused_keys = fused; w.box = box;
+  kp.surv_key = fused ? w.surv_key : nullptr;
+  kp.hist = reinterpret_cast<uint32_t*>(w.meta + w.ml.off_hist);
+  kp.box = box;
   w.n_k1_tiles = plan.n_tiles;
   w.dense_valid = false;
   CM_CUDA(h, launch_transform_crop(kp, plan.tile_points, plan.mode, plan.staged_smem, st));
@@ -653,6 +702,8 @@ int run_pipeline(cm_handle_t h, Workspace& w, const cm_segment_t* segs, int n_se
   if (!w.capturing) CM_CUDA(h, cudaEventRecord(w.ev[EV_K1], st));
   VoxelParams vp;
   fill_voxel_params(h, w, vp, w.surv_xyzi, n_frames, (uint32_t)total);
+  vp.fused_keys = fused ? 1u : 0u;
+  vp.box = box;
   return run_voxel(h, w, vp, st, true);  // the tile scan rides in the grid-setup launch
 }
 
@@ -1380,7 +1431,7 @@ int voxelgrid_run(cm_handle_t h, const float4* pts, int64_t n_points, cudaStream
   w.has_run = true; w.report_valid = false; w.profiled = h->profiling;
   w.n_frames = 1; w.n_segs = 0; w.points_in = n_points; w.launches = 0;
   w.ran_k1 = false; w.ran_voxel = false; w.stream = st; w.n_k1_tiles = 0; w.dense_valid = false;
-  w.voxel_pts = pts;
+  w.voxel_pts = pts; w.fused_keys = false;
   h->last = &w;
   CM_CUDA(h, cudaEventRecord(w.ev[EV_START], st));
   CM_CUDA(h, cudaMemsetAsync(w.meta, 0, w.ml.zero_bytes, st));
@@ -1731,7 +1782,7 @@ int radius_outlier_run(cm_handle_t h, const float4* pts, const int64_t* begin, i
   w.has_run = true; w.report_valid = false; w.profiled = false;
   w.n_frames = (uint32_t)n_clouds; w.n_segs = 0; w.points_in = n_points; w.launches = 0;
   w.ran_k1 = false; w.ran_voxel = false; w.stream = st; w.n_k1_tiles = 0; w.dense_valid = false;
-  w.voxel_pts = pts;
+  w.voxel_pts = pts; w.fused_keys = false;
   h->last = &w;
   CM_CUDA(h, cudaEventRecord(w.ev[EV_START], st));
   CM_CUDA(h, cudaMemsetAsync(w.meta, 0, w.ml.zero_bytes, st));
@@ -2687,7 +2738,12 @@ int cm_get_device_out(cm_handle_t h, cm_device_out_t* out) {
     if (w.key_bytes == 4) {
       // 32-bit keys are sorted as 8-byte (key, value) records: split them into the two arrays this struct promises
       const uint32_t* n_ptr = reinterpret_cast<const uint32_t*>(w.meta + w.ml.off_fstart) + w.n_frames;
-      CM_CUDA(h, launch_split_records(odd ? w.keys_b : w.keys_a, w.vals_a, w.vals_b, n_ptr, (uint32_t)w.points_in, w.stream));
+      VoxelParams vp;  // fused-key runs sorted box-grid keys: hand out PCL's index, like every other run
+      fill_voxel_params(h, w, vp, w.voxel_pts, w.n_frames, (uint32_t)w.points_in);
+      vp.fused_keys = w.fused_keys ? 1u : 0u;
+      vp.box = w.box;
+      CM_CUDA(h, launch_split_records(odd ? w.keys_b : w.keys_a, w.vals_a, w.vals_b, n_ptr, (uint32_t)w.points_in, w.stream,
+                                      w.fused_keys ? &vp : nullptr));
       CM_CUDA(h, cudaStreamSynchronize(w.stream));
       out->sorted_key = w.vals_a;
       out->sorted_point = w.vals_b;

@@ -9,6 +9,20 @@ namespace cm {
 
 // ---- K1: fused unpack + transform + crop + stable compaction (cm_transform_crop.cu) ---------------------------------
 #define K1_BIG_BATCH_POINTS (1u << 21)
+// Voxel keys straight out of K1 (round 2). When the crop chain is a box that bounds x, y and z, the voxel grid of that BOX
+// contains the grid PCL derives from the data of any frame, and ordering by (k, j, i) does not depend on the grid origin:
+// K1 can key every survivor against the box grid the moment it is transformed, and count the digits of every radix pass
+// while it is at it. That removes k_voxel_key_hist (a 16-byte re-read of every survivor plus a launch). The key of a
+// survivor is written at its slot (4 bytes; the slot is the read position, so no value travels), radix pass 0 reads the
+// keys tile-locally through the K1 tile records, and k_voxel_centroid turns the box-grid index of a voxel back into PCL's
+// idx = i + j*div_x + k*div_x*div_y on the frame's data-derived grid.
+struct BoxGrid {
+  float inv[3];              // inverse leaf
+  int32_t min_b[3];          // floor(box_lo * inv)
+  uint32_t mul1, mul2;       // div_x, div_x * div_y of the box grid
+  uint32_t idx_bits;         // bits of the largest box-grid index: key = (frame << idx_bits) | idx
+  uint32_t n_pass;           // radix passes the run will make
+};
 struct K1Params {
   const SegDev* segs;
   uint32_t n_seg;
@@ -21,6 +35,9 @@ struct K1Params {
   uint32_t* surv_src;  // may be null
   Ctrl* ctrl;
   FrameAcc* acc;
+  uint32_t* surv_key;          // [slots] box-grid voxel key of every survivor, or null: keys come from k_voxel_key_hist
+  uint32_t* hist;              // [CM_MAX_SORT_PASSES][256] digit histograms of all passes (with surv_key)
+  BoxGrid box;
   TileRec* tile_rec;           // [n_tiles] out: count / slot0 / frame of every tile
   unsigned long long* trace;   // debug: 8 clock64 stamps per tile, or null
 };
@@ -70,6 +87,12 @@ struct VoxelParams {
                                      // changes from run to run and a captured launch sequence can be replayed as a graph
   uint32_t lb_sort_words;            // size of lb_sort, for the clear on epoch wrap-around
   uint32_t max_passes;               // how many pass launches the host enqueues
+  uint32_t fused_keys;               // K1 already wrote the (box-grid) keys at the survivors' slots and counted the digits:
+                                     // no k_voxel_key_hist; radix pass 0 reads surv_key through the K1 tile records
+  const uint32_t* surv_key;          // [slots]
+  BoxGrid box;
+  uint32_t* first_k1;                // [sort tiles] K1 tile that holds dense position t * sort_tile (written by k_grid_setup)
+  uint32_t sort_tile;                // keys per tile of the radix passes of this run
   uint32_t dual_width;               // the key width is only known on the device (SortInfo.total_bits): the host enqueues the
                                      // 32-bit AND the 64-bit instantiation of every kernel, the one that does not apply exits
   void* out_xyzi;
@@ -89,8 +112,10 @@ cudaError_t launch_grid_setup(const VoxelParams& p, cudaStream_t stream, TileRec
 cudaError_t launch_key_hist(const VoxelParams& p, cudaStream_t stream);
 cudaError_t launch_sort_pass(const VoxelParams& p, int pass, cudaStream_t stream);
 // 32-bit keys are sorted as 8-byte (key, value) records in keys_a/keys_b; this splits the first *n_ptr records into two arrays
+// remap != null (fused-key run): the keys index the crop box's grid; they are handed out re-based on each frame's data-derived
+// grid (PCL's idx), frame bits kept
 cudaError_t launch_split_records(const void* records, uint32_t* keys, uint32_t* vals, const uint32_t* n_ptr,
-                                 uint32_t max_points, cudaStream_t stream);
+                                 uint32_t max_points, cudaStream_t stream, const VoxelParams* remap = nullptr);
 cudaError_t launch_centroid(const VoxelParams& p, cudaStream_t stream);        // one launch: runs, centroids, dense ordered output
 #define CM_CENTROID_LAUNCHES 1
 // host path: dense voxel outputs of a one-frame run -> device-mapped page-locked host arrays, sized by Ctrl.total_voxels

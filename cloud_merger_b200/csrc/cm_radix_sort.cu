@@ -193,10 +193,13 @@ struct SortSmem {
   uint32_t scatter[2][CM_RADIX];       // global position of sorted-tile position 0 of digit d
   uint32_t scan[12];
   uint32_t cnt[CM_RADIX];              // RS_EARLY_COUNT: the tile's digit counts, taken before the ranking
+  uint32_t later[3][CM_RADIX];         // FUSED0: digit counts of passes 1..3, taken while pass 0 holds the keys
   uint32_t next_tile[2];               // written by thread 0 one iteration ahead (parity-indexed)
 };
 
-template <typename KeyT, int IPT>
+// FUSED0: pass 0 of a run whose keys were written by K1 at the survivors' slots (VoxelParams::fused_keys): the tile's keys
+// are read through the K1 tile records, the value of a key is the slot it was read from.
+template <typename KeyT, int IPT, bool FUSED0 = false>
 __global__ void __launch_bounds__(RS_THREADS, RS_MIN_CTAS) k_onesweep_pass(const VoxelParams p, const int pass) {
   constexpr int TILE = RS_THREADS * IPT;
   constexpr int WARP_ITEMS = 32 * IPT;
@@ -246,6 +249,8 @@ __global__ void __launch_bounds__(RS_THREADS, RS_MIN_CTAS) k_onesweep_pass(const
   // so the scanners' latency (poll + chain + store + our poll, ~4-6 thousand cycles) hides behind front(t1) instead of
   // idling a third of the SM's warps as it did when a CTA handled one tile from start to end.
   if (RS_EARLY_COUNT && tid < CM_RADIX) sm.cnt[tid] = 0;
+  if (FUSED0)
+    for (uint32_t i = tid; i < 3u * CM_RADIX; i += RS_THREADS) (&sm.later[0][0])[i] = 0u;
   uint32_t cur = sm.next_tile[0];
   __syncthreads();  // next_tile[1] (the role) is rewritten below; sm.cnt is cleared
   uint32_t prev = 0xFFFFFFFFu, prev_n = 0;
@@ -268,7 +273,58 @@ __global__ void __launch_bounds__(RS_THREADS, RS_MIN_CTAS) k_onesweep_pass(const
       // of that digit, so they land at sorted-tile positions >= n_here and are simply not written back.
       KeyT key[IPT];
       uint32_t val[IPT];
-      if (AOS) {
+      if (FUSED0) {
+        // Dense position d of the merged cropped cloud -> slot: K1 tile e holds positions [dense0_e, dense0_e + count_e) at slots
+        // slot0_e + (d - dense0_e). Lane l of every warp holds the record of K1 tile first + l (a radix tile spans a handful
+        // of K1 tiles); the tile of a position is the last one whose dense0 does not exceed it.
+        const uint32_t k1_first = p.first_k1[cur];
+        const uint32_t e = k1_first + lane;
+        uint32_t e_dense = 0xFFFFFFFFu, e_slot = 0u, e_end = 0xFFFFFFFFu;
+        if (e < p.n_k1_tiles) {
+          const uint4 q = __ldg(reinterpret_cast<const uint4*>(p.tile_rec + e));
+          e_dense = q.w; e_slot = q.y; e_end = q.w + q.x;
+        }
+        const uint32_t last_end = __shfl_sync(0xFFFFFFFFu, e_end, 31);
+        const bool covered = last_end >= tile_base + n_here;  // (entries past the last K1 tile count as covering)
+        const uint32_t w0 = tile_base + warp * WARP_ITEMS;
+        uint32_t kk = (uint32_t)__popc(__ballot_sync(0xFFFFFFFFu, e_dense <= w0));
+        kk = kk ? kk - 1u : 0u;
+        const uint32_t* __restrict__ tdense = reinterpret_cast<const uint32_t*>(p.tile_rec);
+#pragma unroll
+        for (int i = 0; i < IPT; ++i) {
+          const uint32_t d = tile_base + item0 + 32 * i;
+          uint32_t slot;
+          if (covered) {
+            bool adv;
+            do {  // positions grow with i, so the entry index only ever moves forward
+              const uint32_t nd = __shfl_sync(0xFFFFFFFFu, e_dense, (kk + 1u) & 31u);
+              adv = kk < 31u && nd <= d;
+              kk += adv ? 1u : 0u;
+            } while (__any_sync(0xFFFFFFFFu, adv));
+            slot = __shfl_sync(0xFFFFFFFFu, e_slot, kk) + (d - __shfl_sync(0xFFFFFFFFu, e_dense, kk));
+          } else {
+            // a radix tile that spans more than 32 K1 tiles (a crop that keeps a few percent): binary search in global memory
+            uint32_t lo = k1_first, hi = p.n_k1_tiles - 1u;
+            while (lo < hi) {
+              const uint32_t mid = (lo + hi + 1u) >> 1;
+              if (tdense[mid * 4u + 3u] <= d) lo = mid; else hi = mid - 1u;
+            }
+            slot = tdense[lo * 4u + 1u] + (d - tdense[lo * 4u + 3u]);
+          }
+          const bool in = d < M;
+          key[i] = in ? (KeyT)p.surv_key[slot] : ~(KeyT)0;
+          val[i] = in ? slot : 0u;
+        }
+        // K1 counted the digits of pass 0 only; the later passes' histograms are taken here, where every key passes once
+#pragma unroll
+        for (int i = 0; i < IPT; ++i) {
+          if (tile_base + item0 + 32 * i < M) {
+#pragma unroll
+            for (uint32_t ps = 1; ps < 4; ++ps)
+              if (ps < si.num_passes) atomicAdd(&sm.later[ps - 1][((uint32_t)key[i] >> (ps * CM_RADIX_BITS)) & (CM_RADIX - 1)], 1u);
+          }
+        }
+      } else if (AOS) {
         const uint2* __restrict__ in = reinterpret_cast<const uint2*>(odd ? p.keys_b : p.keys_a) + tile_base + item0;
         if (full) {
 #pragma unroll
@@ -468,15 +524,34 @@ __global__ void __launch_bounds__(RS_THREADS, RS_MIN_CTAS) k_onesweep_pass(const
     __syncthreads();
     cur = sm.next_tile[buf];
   }
+  if (FUSED0) {  // this CTA's share of the histograms of passes 1.. (a persistent CTA flushes once)
+    __syncthreads();
+    for (uint32_t i = tid; i < 3u * CM_RADIX; i += RS_THREADS) {
+      const uint32_t c = (&sm.later[0][0])[i];
+      if (c && (i >> 8) + 1u < si.num_passes) atomicAdd(p.hist + CM_RADIX + i, c);
+    }
+  }
 }
 
 // 32-bit keys leave the sort as 8-byte (key, value) records; callers that want two plain arrays get them from here.
 __global__ void __launch_bounds__(256) k_split_records(const uint2* __restrict__ rec, uint32_t* __restrict__ keys,
-                                                       uint32_t* __restrict__ vals, const uint32_t* n_ptr) {
+                                                       uint32_t* __restrict__ vals, const uint32_t* n_ptr, const BoxGrid box,
+                                                       const GridDev* __restrict__ grid, const SortInfo* info, uint32_t n_frames) {
   const uint32_t n = *n_ptr;
+  const uint32_t idx_bits = info ? info->idx_bits : 0u;
   for (uint32_t i = blockIdx.x * 256u + threadIdx.x; i < n; i += gridDim.x * 256u) {
     const uint2 r = rec[i];
-    keys[i] = r.x;
+    uint32_t key = r.x;
+    if (grid) {  // box-grid index -> PCL's idx on the frame's own grid
+      const uint32_t f = idx_bits < 32u ? key >> idx_bits : 0u;
+      const uint32_t b = idx_bits < 32u ? key & ((1u << idx_bits) - 1u) : key;
+      const uint32_t k2 = b / box.mul2, r2 = b - k2 * box.mul2, k1 = r2 / box.mul1, k0 = r2 - k1 * box.mul1;
+      const GridDev* g = grid + (f < n_frames ? f : 0u);
+      const long long c0 = (long long)k0 + box.min_b[0] - g->min_b[0], c1 = (long long)k1 + box.min_b[1] - g->min_b[1],
+                      c2 = (long long)k2 + box.min_b[2] - g->min_b[2];
+      key = (idx_bits < 32u ? f << idx_bits : 0u) | (uint32_t)(c0 + c1 * (long long)g->mul1 + c2 * (long long)g->mul2);
+    }
+    keys[i] = key;
     vals[i] = r.y;
   }
 }
@@ -504,14 +579,14 @@ size_t sort_lookback_rows(uint32_t capacity) {
 }
 
 namespace {
-template <typename KeyT, int IPT>
+template <typename KeyT, int IPT, bool FUSED0 = false>
 struct PassLaunch {
   static inline int ctas_per_sm = 0;
   static cudaError_t configure() {
-    cudaError_t e = cudaFuncSetAttribute(k_onesweep_pass<KeyT, IPT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    cudaError_t e = cudaFuncSetAttribute(k_onesweep_pass<KeyT, IPT, FUSED0>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)sizeof(SortSmem<KeyT, IPT>));
     if (e != cudaSuccess) return e;
-    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, k_onesweep_pass<KeyT, IPT>, RS_THREADS,
+    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, k_onesweep_pass<KeyT, IPT, FUSED0>, RS_THREADS,
                                                          sizeof(SortSmem<KeyT, IPT>));
   }
   static cudaError_t launch(const VoxelParams& p, int pass, int sms, cudaStream_t stream) {
@@ -520,7 +595,7 @@ struct PassLaunch {
     if (tiles == 0) return cudaSuccess;
     // persistent workers: at most what the device holds at once (tiles are handed out by an atomic counter)
     const uint32_t workers = std::min<uint32_t>(tiles, (uint32_t)(sms * std::max(1, ctas_per_sm)) - RS_SCANNERS);
-    k_onesweep_pass<KeyT, IPT><<<workers + RS_SCANNERS, RS_THREADS, sizeof(SortSmem<KeyT, IPT>), stream>>>(p, pass);
+    k_onesweep_pass<KeyT, IPT, FUSED0><<<workers + RS_SCANNERS, RS_THREADS, sizeof(SortSmem<KeyT, IPT>), stream>>>(p, pass);
     return cudaGetLastError();
   }
 };
@@ -533,6 +608,8 @@ cudaError_t configure_sort_kernels() {
   if (e == cudaSuccess) e = PassLaunch<unsigned long long, SortCfg<unsigned long long>::IPT>::configure();
   if (e == cudaSuccess) e = PassLaunch<uint32_t, RS_IPT_SMALL>::configure();
   if (e == cudaSuccess) e = PassLaunch<unsigned long long, RS_IPT_SMALL>::configure();
+  if (e == cudaSuccess) e = PassLaunch<uint32_t, SortCfg<uint32_t>::IPT, true>::configure();
+  if (e == cudaSuccess) e = PassLaunch<uint32_t, RS_IPT_SMALL, true>::configure();
   if (e != cudaSuccess) return e;
   if (getenv("CM_DEBUG"))
     fprintf(stderr, "[cm] sort pass CTAs per SM: %d / %d (32 / 64-bit keys), small tile %d / %d\n",
@@ -548,6 +625,9 @@ cudaError_t launch_sort_pass(const VoxelParams& p, int pass, cudaStream_t stream
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   const bool small = sort_uses_small_tile(p.max_points);
+  if (p.fused_keys && pass == 0)  // 32-bit keys by construction
+    return small ? PassLaunch<uint32_t, RS_IPT_SMALL, true>::launch(p, pass, sms, stream)
+                 : PassLaunch<uint32_t, SortCfg<uint32_t>::IPT, true>::launch(p, pass, sms, stream);
   if (p.key_bytes == 4)
     return small ? PassLaunch<uint32_t, RS_IPT_SMALL>::launch(p, pass, sms, stream)
                  : PassLaunch<uint32_t, SortCfg<uint32_t>::IPT>::launch(p, pass, sms, stream);
@@ -556,10 +636,12 @@ cudaError_t launch_sort_pass(const VoxelParams& p, int pass, cudaStream_t stream
 }
 
 cudaError_t launch_split_records(const void* records, uint32_t* keys, uint32_t* vals, const uint32_t* n_ptr,
-                                 uint32_t max_points, cudaStream_t stream) {
+                                 uint32_t max_points, cudaStream_t stream, const VoxelParams* remap) {
   if (max_points == 0) return cudaSuccess;
   const uint32_t blocks = std::min<uint32_t>((max_points + 255u) / 256u, 148u * 8u);
-  k_split_records<<<blocks, 256, 0, stream>>>(reinterpret_cast<const uint2*>(records), keys, vals, n_ptr);
+  k_split_records<<<blocks, 256, 0, stream>>>(reinterpret_cast<const uint2*>(records), keys, vals, n_ptr,
+                                              remap ? remap->box : BoxGrid{}, remap ? remap->grid : nullptr,
+                                              remap ? remap->info : nullptr, remap ? remap->n_frames : 0u);
   return cudaGetLastError();
 }
 

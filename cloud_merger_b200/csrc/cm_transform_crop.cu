@@ -83,11 +83,15 @@ __device__ __forceinline__ void minmax_if(bool on, float v, float& mn, float& mx
       : "r"((int)on), "f"(v));
 }
 
-template <int THREADS, int IPT, int MODE, int BOX>
+template <int THREADS, int IPT, int MODE, int BOX, bool KEYS>
 __global__ void __launch_bounds__(THREADS, (THREADS >= 512 ? 2 : 4)) k_transform_crop(const K1Params p) {
   constexpr int TILE = THREADS * IPT;
   constexpr int WARPS = THREADS / 32;
+  static_assert(!KEYS || BOX != 0, "keys are emitted against the crop box");
   extern __shared__ __align__(16) uint8_t stage[];
+  // digit counts of this tile's survivors for radix pass 0 (pass 0 itself counts the digits of the later passes: K1 runs
+  // one CTA per tile, and four histograms per CTA were 5 M global reductions per batch -- measured +34 us on the kernel)
+  __shared__ uint32_t s_hist[KEYS ? CM_RADIX : 1];
   __shared__ uint32_t s_warp_tot[WARPS], s_warp_inv[WARPS];
   __shared__ uint32_t s_mm[WARPS][6];  // order-preserving encodings: ~enc(min) x3, enc(max) x3
   __shared__ __align__(8) unsigned long long s_bar;
@@ -95,6 +99,7 @@ __global__ void __launch_bounds__(THREADS, (THREADS >= 512 ? 2 : 4)) k_transform
   const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
   const uint32_t tile = blockIdx.x;
   const long long tr0 = clock64();
+  if (KEYS && tid < CM_RADIX) s_hist[tid] = 0u;  // ordered by the barrier further down
 #define K1_TRACE(i) do { if (p.trace && tid == 0) p.trace[(size_t)tile * 8 + (i)] = (unsigned long long)(clock64() - tr0); } while (0)
 
   // which segment owns this tile: uniform batches by division, others through the host-built table
@@ -344,22 +349,42 @@ __global__ void __launch_bounds__(THREADS, (THREADS >= 512 ? 2 : 4)) k_transform
   const uint32_t src0 = sg->src_base + pt0 + li0;
   const uint32_t lt = lanemask_lt();
   const bool want_src = p.surv_src != nullptr;
+  const uint32_t fbits = KEYS ? (sg->frame << p.box.idx_bits) : 0u;
 #pragma unroll
   for (int i = 0; i < IPT; ++i) {
     if (keep_bits & (1u << i)) {
       const uint32_t q = pos + __popc(ballots[i] & lt);
       p.surv_xyzi[q] = make_float4(x[i], y[i], z[i], it[i]);
       if (want_src) p.surv_src[q] = src0 + 32 * i;
+      if (KEYS) {
+        // PCL: ijk = floor(p * inv_leaf) - min_b with a separately rounded multiply; here against the box grid's origin
+        const uint32_t i0 = (uint32_t)(__float2int_rd(__fmul_rn(x[i], p.box.inv[0])) - p.box.min_b[0]);
+        const uint32_t i1 = (uint32_t)(__float2int_rd(__fmul_rn(y[i], p.box.inv[1])) - p.box.min_b[1]);
+        const uint32_t i2 = (uint32_t)(__float2int_rd(__fmul_rn(z[i], p.box.inv[2])) - p.box.min_b[2]);
+        const uint32_t key = fbits | (i0 + i1 * p.box.mul1 + i2 * p.box.mul2);
+        p.surv_key[q] = key;
+        atomicAdd(&s_hist[key & (CM_RADIX - 1)], 1u);
+      }
     }
     pos += __popc(ballots[i]);
+  }
+  if (KEYS) {  // this tile's digit counts -> the run's pass-0 histogram (fire-and-forget reductions; empty bins cost nothing)
+    __syncthreads();
+    if (tid < CM_RADIX) {
+      const uint32_t c = s_hist[tid];
+      if (c) atomicAdd(p.hist + tid, c);
+    }
   }
   K1_TRACE(5);
 }
 
 template <int THREADS, int IPT>
 cudaError_t launch_cfg(const K1Params& p, int mode, int box, uint32_t smem, cudaStream_t stream) {
-#define CM_K1_LAUNCH(MODE, BOX) k_transform_crop<THREADS, IPT, MODE, BOX><<<p.n_tiles, THREADS, smem, stream>>>(p)
-#define CM_K1_BOX(MODE) do { if (box == 1) CM_K1_LAUNCH(MODE, 1); else if (box == 2) CM_K1_LAUNCH(MODE, 2); else CM_K1_LAUNCH(MODE, 0); } while (0)
+  const bool keys = p.surv_key != nullptr && box != 0;
+#define CM_K1_LAUNCH(MODE, BOX, KEYS) k_transform_crop<THREADS, IPT, MODE, BOX, KEYS><<<p.n_tiles, THREADS, smem, stream>>>(p)
+#define CM_K1_BOX(MODE) do { if (box == 1) { if (keys) CM_K1_LAUNCH(MODE, 1, true); else CM_K1_LAUNCH(MODE, 1, false); } \
+                             else if (box == 2) { if (keys) CM_K1_LAUNCH(MODE, 2, true); else CM_K1_LAUNCH(MODE, 2, false); } \
+                             else CM_K1_LAUNCH(MODE, 0, false); } while (0)
   if (mode == (int)SEG_PACKED16) CM_K1_BOX((int)SEG_PACKED16);
   else if (mode == (int)SEG_PCL32) CM_K1_BOX((int)SEG_PCL32);
   else CM_K1_BOX(MODE_GENERIC);
@@ -384,17 +409,15 @@ cudaError_t configure_device_kernels() {
   const int big = 200 * 1024;  // the host falls back to 1024-point tiles when a staged layout needs more
   const int small = (int)k1_staged_smem(1024u, CM_MAX_STAGED_STEP);
   cudaError_t e;
-  e = cudaFuncSetAttribute(k_transform_crop<512, 8, MODE_GENERIC, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
+#define CM_K1_ATTR(T, I, B, K, BYTES)                                                                                      \
+  e = cudaFuncSetAttribute(k_transform_crop<T, I, MODE_GENERIC, B, K>, cudaFuncAttributeMaxDynamicSharedMemorySize, BYTES); \
   if (e != cudaSuccess) return e;
-  e = cudaFuncSetAttribute(k_transform_crop<512, 8, MODE_GENERIC, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
-  if (e != cudaSuccess) return e;
-  e = cudaFuncSetAttribute(k_transform_crop<512, 8, MODE_GENERIC, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
-  if (e != cudaSuccess) return e;
-  e = cudaFuncSetAttribute(k_transform_crop<256, 4, MODE_GENERIC, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, small);
-  if (e != cudaSuccess) return e;
-  e = cudaFuncSetAttribute(k_transform_crop<256, 4, MODE_GENERIC, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, small);
-  if (e != cudaSuccess) return e;
-  return cudaFuncSetAttribute(k_transform_crop<256, 4, MODE_GENERIC, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, small);
+  CM_K1_ATTR(512, 8, 0, false, big) CM_K1_ATTR(512, 8, 1, false, big) CM_K1_ATTR(512, 8, 2, false, big)
+  CM_K1_ATTR(512, 8, 1, true, big) CM_K1_ATTR(512, 8, 2, true, big)
+  CM_K1_ATTR(256, 4, 0, false, small) CM_K1_ATTR(256, 4, 1, false, small) CM_K1_ATTR(256, 4, 2, false, small)
+  CM_K1_ATTR(256, 4, 1, true, small) CM_K1_ATTR(256, 4, 2, true, small)
+#undef CM_K1_ATTR
+  return cudaSuccess;
 }
 
 cudaError_t launch_transform_crop(const K1Params& p, uint32_t tile_points, int mode, uint32_t staged_smem_bytes,

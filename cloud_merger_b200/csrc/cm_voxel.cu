@@ -221,6 +221,18 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_grid_setup(const VoxelParams p
   if (ts.rec) tile_scan_body(ts.rec, ts.n_tiles, ts.segs, ts.n_seg, p.n_frames, const_cast<uint32_t*>(p.frame_surv_start),
                              ts.seg_surv_start, s_scr);
   __syncthreads();
+  if (ts.rec && p.fused_keys) {
+    // which K1 tile holds the first key of every radix tile (pass 0 reads the keys where K1 left them): a K1 tile has at
+    // most 4096 survivors, fewer than a radix tile, so at most one radix-tile boundary falls into it
+    const unsigned long long T = p.sort_tile;
+    for (uint32_t i = tid; i < ts.n_tiles; i += SCAN_THREADS) {
+      const uint32_t c = ts.rec[i].count;
+      if (!c) continue;
+      const unsigned long long d0 = ts.rec[i].dense0;
+      const unsigned long long t = (d0 + T - 1ull) / T;
+      if (t * T < d0 + c) p.first_k1[t] = i;
+    }
+  }
   for (uint32_t f = tid; f < p.n_frames; f += SCAN_THREADS) {
     const FrameAcc a = p.acc[f];
     GridDev g;
@@ -285,6 +297,7 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_grid_setup(const VoxelParams p
     const uint32_t key_frames = p.n_frames + (p.ctrl->has_invalid ? 1u : 0u);
     const uint32_t frame_bits = key_frames <= 1u ? 0u : (uint32_t)(32 - __clz((int)(key_frames - 1u)));
     uint32_t idx_bits = s_maxbits;
+    if (p.fused_keys) idx_bits = p.box.idx_bits;  // the keys K1 wrote are built on the crop box's grid, which holds every frame's
     uint32_t total = frame_bits + idx_bits;
     if (total > p.key_bytes * 8u) {
       atomicExch(&p.ctrl->error, (uint32_t)CM_DEV_E_KEY_RANGE);
@@ -740,7 +753,20 @@ __global__ void __launch_bounds__(VX_THREADS, CE_MIN_CTAS) k_voxel_centroid(cons
       reinterpret_cast<float4*>(p.out_xyzi)[dst] = c;
     }
     p.out_count[dst] = n;
-    p.out_idx[dst] = (unsigned long long)key & idx_mask;
+    unsigned long long vidx = (unsigned long long)key & idx_mask;
+    if (p.fused_keys) {
+      // the key indexes the crop box's grid: back to PCL's idx on the frame's data-derived grid (same cells, other origin)
+      const uint32_t b = (uint32_t)vidx;
+      const uint32_t k2 = b / p.box.mul2, r2 = b - k2 * p.box.mul2;
+      const uint32_t k1 = r2 / p.box.mul1, k0 = r2 - k1 * p.box.mul1;
+      const unsigned long long f = (unsigned long long)key >> idx_bits;
+      const GridDev* __restrict__ g = p.grid + (f < F ? f : 0ull);
+      const long long c0 = (long long)k0 + p.box.min_b[0] - g->min_b[0];
+      const long long c1 = (long long)k1 + p.box.min_b[1] - g->min_b[1];
+      const long long c2 = (long long)k2 + p.box.min_b[2] - g->min_b[2];
+      vidx = (unsigned long long)(c0 + c1 * (long long)g->mul1 + c2 * (long long)g->mul2);
+    }
+    p.out_idx[dst] = vidx;
     if (per_voxel_count) {
       const unsigned long long f = (unsigned long long)key >> idx_bits;
       if (f < F) atomicAdd(&p.acc[f].voxel_count, 1u);
