@@ -748,13 +748,13 @@ def test_wait_frame_view_is_the_same_result_without_a_copy(gpu_ok, oracle):
 
 
 @pytest.mark.parametrize("leaf,box", [(0.05, [(0, 3.0, 4.5, 0), (1, -1.0, 0.25, 0), (2, -0.5, 3.0, 0)]),      # ~1 % of the points survive
-                                      (0.013, [(2, -2.25, 7.1, 0), (0, -33.3, 41.7, 0), (1, -17.9, 12.2, 0)]),  # box not aligned to the leaf, 31 key bits
+                                      (0.035, [(2, -2.25, 7.1, 0), (0, -33.3, 41.7, 0), (1, -17.9, 12.2, 0)]),  # box not aligned to the leaf, 32 key bits
                                       (0.25, [(0, -60.0, 60.0, 0), (1, -60.0, 60.0, 0), (2, -60.0, 60.0, 0), (3, 20.0, 230.0, 0)])])
 def test_keys_from_the_crop_box_grid(gpu_ok, oracle, leaf, box):
     """When the crop is a box that bounds x, y, z, K1 keys the survivors against the BOX's voxel grid and radix pass 0 reads
     the keys through the K1 tile records; the voxel index handed out is re-based on each frame's data-derived grid. Checked
     against the oracle (which follows PCL: grid from the data) for a crop that keeps ~1 % of the points (a radix tile then
-    spans hundreds of K1 tiles: the binary-search path), a box that is not aligned to the leaf with a 31-bit key, and an
+    spans hundreds of K1 tiles: the binary-search path), a box that is not aligned to the leaf with a 32-bit key, and an
     intensity window on top of the box; five frames of different sizes, 2.3 M points (the 4096-point K1 tile, the big radix tile)."""
     F, S = 5, 3
     frames = [[(synth.lidar_cloud(900 + f, s, f, 128, 1100 + 97 * f + 13 * s), 1) for s in range(S)] for f in range(F)]
@@ -770,6 +770,8 @@ def test_keys_from_the_crop_box_grid(gpu_ok, oracle, leaf, box):
         out = cm.fetch_batch_outputs()
     o = _oracle_frames(oracle, per_frame, box, [leaf] * 3, 1)
     assert out["key_bytes"] == 4 and out["stats"].device_error == 0
+    if leaf == 0.035:
+        assert out["stats"].key_bits == 32
     _check_survivors(out, out["frames"], o)
     assert _check_voxels(out, out["frames"], o) <= 1e-5
     assert sum(fo["n_voxels"] for fo in o) > 1000
