@@ -1540,15 +1540,9 @@ bool in_zone_outputs(cm_handle_t h, const void* p, int64_t n_points) {
   return a < hi && b > lo;
 }
 
-int zone_run(cm_handle_t h, const float4* pts, int64_t n_points, cudaStream_t st, bool mask_given = false,
-             int given_zones = 1) {
+// the launch parameters of one split of `pts` over the handle's zone workspace (which must hold n_points)
+ZoneParams zone_params(cm_handle_t h, const float4* pts, int64_t n_points, bool mask_given, int given_zones) {
   cm_handle_s::ZoneWs& z = h->zw;
-  if (!mask_given && h->zones.n_zones <= 0) return fail(h, CM_E_INVALID, "no zones configured (cm_set_zones)");
-  if (n_points < 0 || n_points > 0xFFFFFFF0ll) return fail(h, CM_E_INVALID, "bad n_points");
-  if (in_zone_outputs(h, pts, n_points))
-    return fail(h, CM_E_INVALID, "the input cloud lies in this handle's own zone outputs (use another handle or copy it out)");
-  int rc = zone_ws_ensure(h, (size_t)n_points);
-  if (rc != CM_OK) return rc;
   ZoneParams zp;
   zp.pts = pts; zp.n_points = (uint32_t)n_points;
   zp.n_tiles = (uint32_t)((n_points + zone_tile_points() - 1) / zone_tile_points());
@@ -1563,6 +1557,21 @@ int zone_run(cm_handle_t h, const float4* pts, int64_t n_points, cudaStream_t st
   zp.zone_total = z.zone_total; zp.scan_ticket = z.zone_total + CM_MAX_ZONES;
   zp.overflow = z.overflow; zp.out_capacity = (uint32_t)std::min<size_t>(z.cap_out, 0xFFFFFFF0u);
   zp.out_xyzi = z.out_xyzi; zp.out_src = z.out_src;
+  for (int i = 0; i < CM_MAX_ZONES; ++i) zp.zone_ptr[i] = nullptr;
+  zp.zone_remote_base = nullptr;
+  return zp;
+}
+
+int zone_run(cm_handle_t h, const float4* pts, int64_t n_points, cudaStream_t st, bool mask_given = false,
+             int given_zones = 1) {
+  cm_handle_s::ZoneWs& z = h->zw;
+  if (!mask_given && h->zones.n_zones <= 0) return fail(h, CM_E_INVALID, "no zones configured (cm_set_zones)");
+  if (n_points < 0 || n_points > 0xFFFFFFF0ll) return fail(h, CM_E_INVALID, "bad n_points");
+  if (in_zone_outputs(h, pts, n_points))
+    return fail(h, CM_E_INVALID, "the input cloud lies in this handle's own zone outputs (use another handle or copy it out)");
+  int rc = zone_ws_ensure(h, (size_t)n_points);
+  if (rc != CM_OK) return rc;
+  ZoneParams zp = zone_params(h, pts, n_points, mask_given, given_zones);
   CM_CUDA(h, cudaMemsetAsync(z.overflow, 0, sizeof(uint32_t), st));
   CM_CUDA(h, launch_zone_split(zp, st));
   CM_CUDA(h, cudaMemcpyAsync(z.report, z.zone_begin, sizeof(uint32_t) * (CM_MAX_ZONES + 1), cudaMemcpyDeviceToHost, st));
@@ -2516,7 +2525,12 @@ struct cm_giant_s {
   float4* recv = nullptr;               // device [recv_cap]: what the all-to-all delivers
   size_t recv_cap = 0;
   GiantPlan* plan_pin = nullptr;        // pinned mirrors
-  uint32_t* counts_pin = nullptr;
+  uint32_t* counts_pin = nullptr;       // [world][stride] + 1: the overflow word of the peer exchange
+  // the exchange fused into the grouping kernel: every rank's receive buffer mapped here through CUDA IPC
+  bool p2p = false;
+  float4* peer_recv[CM_MAX_ZONES] = {};
+  uint32_t* p2p_words = nullptr;        // device: [0..world) remote_base, [world] barrier word, [world + 1] my receive capacity
+  cudaEvent_t plan_ready = nullptr;     // the host waits for the counts, not for the exchange
   std::string err;
 };
 
@@ -2542,6 +2556,64 @@ int gfail(cm_giant_t g, int code, const char* fmt, ...) {
     if (r__ != ncclSuccess) return gfail(g, CM_E_CUDA, "%s: NCCL %s (%s:%d)", #expr, (g)->api->GetErrorString(r__), __FILE__, __LINE__); \
   } while (0)
 constexpr int kCountStride = CM_MAX_ZONES + 2;
+
+// Maps every peer's receive buffer into this process (CUDA IPC; NVLink peer access is enabled lazily by the open). All or
+// nothing: a rank that could not map a peer (two ranks in one process, no P2P between the devices) makes everybody fall back
+// to the NCCL exchange, agreed through an all-reduce. Runs on the legacy stream inside cm_giant_create.
+void giant_setup_p2p(cm_giant_t g) {
+  const char* off = getenv("CM_GIANT_NO_P2P");
+  int want = (off && off[0] == '1') ? 0 : 1;
+  const int W = g->world;
+  cudaIpcMemHandle_t mine;
+  memset(&mine, 0, sizeof(mine));
+  if (want && cudaIpcGetMemHandle(&mine, g->recv) != cudaSuccess) { want = 0; cudaGetLastError(); }
+  cudaIpcMemHandle_t* all_dev = nullptr;
+  int* ok_dev = nullptr;
+  std::vector<cudaIpcMemHandle_t> all((size_t)W);
+  int ok = want;
+  if (cudaMalloc(reinterpret_cast<void**>(&all_dev), sizeof(mine) * (size_t)(W + 1)) != cudaSuccess ||
+      cudaMalloc(reinterpret_cast<void**>(&ok_dev), sizeof(int)) != cudaSuccess) { cudaGetLastError(); ok = 0; }
+  // every rank takes part in both collectives whatever its own state, or the others would hang
+  if (all_dev && ok_dev) {
+    cudaMemcpy(all_dev + W, &mine, sizeof(mine), cudaMemcpyHostToDevice);
+    if (g->api->AllGather(all_dev + W, all_dev, sizeof(mine), ncclUint8, g->comm, nullptr) != ncclSuccess) ok = 0;
+    if (cudaMemcpy(all.data(), all_dev, sizeof(mine) * (size_t)W, cudaMemcpyDeviceToHost) != cudaSuccess) { ok = 0; cudaGetLastError(); }
+  }
+  int opened = 0;
+  if (ok) {
+    for (int r = 0; r < W && ok; ++r) {
+      if (r == g->rank) { g->peer_recv[r] = g->recv; continue; }
+      void* p = nullptr;
+      if (cudaIpcOpenMemHandle(&p, all[(size_t)r], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { ok = 0; cudaGetLastError(); break; }
+      g->peer_recv[r] = static_cast<float4*>(p);
+      ++opened;
+    }
+  }
+  if (all_dev && ok_dev) {
+    cudaMemcpy(ok_dev, &ok, sizeof(int), cudaMemcpyHostToDevice);
+    int agreed = 0;
+    if (g->api->AllReduce(ok_dev, ok_dev, 1, ncclInt32, ncclMin, g->comm, nullptr) == ncclSuccess &&
+        cudaMemcpy(&agreed, ok_dev, sizeof(int), cudaMemcpyDeviceToHost) == cudaSuccess) ok = ok && agreed;
+    else ok = 0;
+  }
+  cudaFree(all_dev); cudaFree(ok_dev);
+  if (ok && (cudaMalloc(reinterpret_cast<void**>(&g->p2p_words), sizeof(uint32_t) * (size_t)(W + 2)) != cudaSuccess ||
+             cudaEventCreateWithFlags(&g->plan_ready, cudaEventDisableTiming) != cudaSuccess)) { ok = 0; cudaGetLastError(); }
+  if (ok) {
+    std::vector<uint32_t> init((size_t)W + 2, 0u);
+    init[(size_t)W + 1] = (uint32_t)std::min<size_t>(g->recv_cap, 0xFFFFFFF0u);
+    cudaMemcpy(g->p2p_words, init.data(), sizeof(uint32_t) * init.size(), cudaMemcpyHostToDevice);
+  }
+  if (!ok) {
+    for (int r = 0; r < W; ++r) {
+      if (r != g->rank && g->peer_recv[r]) cudaIpcCloseMemHandle(g->peer_recv[r]);
+      g->peer_recv[r] = nullptr;
+    }
+    cudaGetLastError();
+  }
+  (void)opened;
+  g->p2p = ok != 0;
+}
 }  // namespace
 
 int cm_giant_unique_id(void* id_bytes) {
@@ -2583,11 +2655,12 @@ int cm_giant_create(cm_handle_t h, int rank, int world, const void* nccl_id, cm_
       cudaMalloc(reinterpret_cast<void**>(&g->counts), sizeof(uint32_t) * kCountStride * world) != cudaSuccess ||
       (world > 1 && g->comm && dev_alloc(&g->recv, g->recv_cap) != cudaSuccess) ||
       cudaMallocHost(reinterpret_cast<void**>(&g->plan_pin), sizeof(GiantPlan)) != cudaSuccess ||
-      cudaMallocHost(reinterpret_cast<void**>(&g->counts_pin), sizeof(uint32_t) * kCountStride * world) != cudaSuccess) {
+      cudaMallocHost(reinterpret_cast<void**>(&g->counts_pin), sizeof(uint32_t) * (kCountStride * world + 1)) != cudaSuccess) {
     h->last_error = "cm_giant_create: allocation failed";
     cudaGetLastError();
     return bail(CM_E_CUDA);
   }
+  if (g->comm && g->recv) giant_setup_p2p(g);
   *out = g;
   return CM_OK;
 }
@@ -2595,7 +2668,11 @@ int cm_giant_create(cm_handle_t h, int rank, int world, const void* nccl_id, cm_
 int cm_giant_destroy(cm_giant_t g) {
   if (!g) return CM_E_INVALID;
   cudaSetDevice(g->h->device);
-  cudaDeviceSynchronize();
+  cudaDeviceSynchronize();  // past this rank's last barrier: no peer is still storing into g->recv
+  for (int r = 0; r < g->world; ++r)
+    if (g->p2p && r != g->rank && g->peer_recv[r]) cudaIpcCloseMemHandle(g->peer_recv[r]);
+  cudaFree(g->p2p_words);
+  if (g->plan_ready) cudaEventDestroy(g->plan_ready);
   if (g->comm && g->api) g->api->CommDestroy(g->comm);
   cudaFree(g->plan); cudaFree(g->hist); cudaFree(g->counts); cudaFree(g->recv);
   if (g->plan_pin) cudaFreeHost(g->plan_pin);
@@ -2624,6 +2701,7 @@ int cm_giant_voxelgrid(cm_giant_t g, const float* local_xyzi_dev, int64_t n_loca
   cm_giant_info_t gi;
   memset(&gi, 0, sizeof(gi));
   gi.points_local = n_local;
+  ZoneParams zp;
   // ---- global bounding box -> grid, on the device
   CM_G_CUDA(g, cudaMemsetAsync(w.meta, 0, w.ml.zero_bytes, st));
   CM_G_CUDA(g, launch_minmax(pts, (uint32_t)n_local, ctrl, acc, fss, st));
@@ -2637,15 +2715,40 @@ int cm_giant_voxelgrid(cm_giant_t g, const float* local_xyzi_dev, int64_t n_loca
     CM_G_CUDA(g, launch_giant_splitters(g->plan, g->hist, g->bins, (uint32_t)W, st));
     // ---- group the block by destination (source order kept inside a destination): the send buffer of the all-to-all
     CM_G_CUDA(g, launch_giant_mask(pts, (uint32_t)n_local, g->plan, (uint32_t)W, (uint32_t)me, h->zw.mask, st));
-    rc = zone_run(h, pts, n_local, st, true, W);
-    if (rc != CM_OK) return rc;
+    if (g->p2p) {
+      // count + scan only; the scatter below IS the all-to-all (stores into the owners' receive buffers over NVLink)
+      if (in_zone_outputs(h, pts, n_local)) return gfail(g, CM_E_INVALID, "the input cloud lies in this handle's own zone outputs");
+      zp = zone_params(h, pts, n_local, true, W);
+      zp.out_capacity = 0xFFFFFFF0u;  // nothing lands in the local outputs; the receivers' capacities are checked on the device
+      CM_G_CUDA(g, cudaMemsetAsync(h->zw.overflow, 0, sizeof(uint32_t), st));
+      CM_G_CUDA(g, launch_zone_count_scan(zp, st));
+      CM_G_CUDA(g, cudaMemcpyAsync(h->zw.zone_begin + CM_MAX_ZONES + 1, g->p2p_words + W + 1, sizeof(uint32_t), cudaMemcpyDeviceToDevice, st));
+      h->zw.ran = false;  // no grouped array on this handle after this call
+    } else {
+      rc = zone_run(h, pts, n_local, st, true, W);
+      if (rc != CM_OK) return rc;
+    }
     // every rank's per-destination offsets (NCCL takes the counts of a send / recv as host arguments)
     if (g->comm) CM_G_NCCL(g, g->api->AllGather(h->zw.zone_begin, g->counts, kCountStride, ncclUint32, g->comm, st));
     else CM_G_CUDA(g, cudaMemcpyAsync(g->counts + (size_t)me * kCountStride, h->zw.zone_begin, sizeof(uint32_t) * kCountStride, cudaMemcpyDeviceToDevice, st));
     CM_G_CUDA(g, cudaMemcpyAsync(g->counts_pin, g->counts, sizeof(uint32_t) * kCountStride * W, cudaMemcpyDeviceToHost, st));
+    if (g->p2p) {
+      CM_G_CUDA(g, launch_giant_offsets(g->counts, kCountStride, (uint32_t)W, (uint32_t)me, g->p2p_words, h->zw.overflow, st));
+      CM_G_CUDA(g, cudaMemcpyAsync(g->counts_pin + (size_t)kCountStride * W, h->zw.overflow, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+    }
   }
   CM_G_CUDA(g, cudaMemcpyAsync(g->plan_pin, g->plan, sizeof(GiantPlan), cudaMemcpyDeviceToHost, st));
-  CM_G_CUDA(g, cudaStreamSynchronize(st));
+  if (W > 1 && g->p2p) {
+    CM_G_CUDA(g, cudaEventRecord(g->plan_ready, st));
+    for (int r = 0; r < W; ++r) zp.zone_ptr[r] = g->peer_recv[r];
+    zp.zone_remote_base = g->p2p_words;
+    CM_G_CUDA(g, launch_zone_scatter_remote(zp, st));
+    // every store of every rank has landed once this one-word all-reduce completes (stream order on each rank)
+    CM_G_NCCL(g, g->api->AllReduce(g->p2p_words + W, g->p2p_words + W, 1, ncclUint32, ncclMax, g->comm, st));
+    CM_G_CUDA(g, cudaEventSynchronize(g->plan_ready));  // the counts are here; the exchange is still in flight
+  } else {
+    CM_G_CUDA(g, cudaStreamSynchronize(st));
+  }
   ++gi.host_syncs;
   const GiantPlan& P = *g->plan_pin;
   for (int k = 0; k < 3; ++k) {
@@ -2674,22 +2777,32 @@ int cm_giant_voxelgrid(cm_giant_t g, const float* local_xyzi_dev, int64_t n_loca
       roff[s + 1] = roff[s] + (int64_t)(row[me + 1] - row[me]);
     }
     gi.points_received = roff[W];
-    if ((size_t)roff[W] > g->recv_cap)
-      return gfail(g, CM_E_CAPACITY, "this rank receives %lld points, max_batch_points of the handle is %zu", (long long)roff[W], g->recv_cap);
-    // ---- ONE all-to-all, straight out of the grouped array
-    const float4* send = h->zw.out_xyzi;
-    CM_G_NCCL(g, g->api->GroupStart());
-    for (int r = 0; r < W; ++r) {
-      const size_t sc = (size_t)(mine[r + 1] - mine[r]), rcnt = (size_t)(roff[r + 1] - roff[r]);
-      if (r == me) continue;
-      if (sc) CM_G_NCCL(g, g->api->Send(send + mine[r], sc * 4, ncclFloat, r, g->comm, st));
-      if (rcnt) CM_G_NCCL(g, g->api->Recv(g->recv + roff[r], rcnt * 4, ncclFloat, r, g->comm, st));
+    if (g->p2p) {
+      // the device already decided (every rank the same): with an overflow nobody stored anything
+      const uint32_t over = g->counts_pin[(size_t)kCountStride * W];
+      if (over) return gfail(g, CM_E_CAPACITY, "a rank would receive %u points, more than max_batch_points of its handle", over);
+      gi.exchange = CM_GIANT_EXCHANGE_PEER;
+      vox_in = g->recv;
+      n_vox = roff[W];
+    } else {
+      if ((size_t)roff[W] > g->recv_cap)
+        return gfail(g, CM_E_CAPACITY, "this rank receives %lld points, max_batch_points of the handle is %zu", (long long)roff[W], g->recv_cap);
+      gi.exchange = CM_GIANT_EXCHANGE_NCCL;
+      // ---- ONE all-to-all, straight out of the grouped array
+      const float4* send = h->zw.out_xyzi;
+      CM_G_NCCL(g, g->api->GroupStart());
+      for (int r = 0; r < W; ++r) {
+        const size_t sc = (size_t)(mine[r + 1] - mine[r]), rcnt = (size_t)(roff[r + 1] - roff[r]);
+        if (r == me) continue;
+        if (sc) CM_G_NCCL(g, g->api->Send(send + mine[r], sc * 4, ncclFloat, r, g->comm, st));
+        if (rcnt) CM_G_NCCL(g, g->api->Recv(g->recv + roff[r], rcnt * 4, ncclFloat, r, g->comm, st));
+      }
+      CM_G_NCCL(g, g->api->GroupEnd());
+      const size_t self = (size_t)(mine[me + 1] - mine[me]);
+      if (self) CM_G_CUDA(g, cudaMemcpyAsync(g->recv + roff[me], send + mine[me], self * 16, cudaMemcpyDeviceToDevice, st));
+      vox_in = g->recv;
+      n_vox = roff[W];
     }
-    CM_G_NCCL(g, g->api->GroupEnd());
-    const size_t self = (size_t)(mine[me + 1] - mine[me]);
-    if (self) CM_G_CUDA(g, cudaMemcpyAsync(g->recv + roff[me], send + mine[me], self * 16, cudaMemcpyDeviceToDevice, st));
-    vox_in = g->recv;
-    n_vox = roff[W];
   } else {
     gi.points_received = n_local;
   }

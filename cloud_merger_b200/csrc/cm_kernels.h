@@ -139,6 +139,10 @@ struct ZoneParams {
   uint32_t out_capacity;
   float4* out_xyzi;
   uint32_t* out_src;         // index of every output point in the input cloud
+  // giant-cloud exchange fused into the scatter (cm_giant_voxelgrid over peer memory): zone r is written straight into rank
+  // r's receive buffer (an IPC-mapped pointer; NVLink stores), from element zone_remote_base[r] on; no source indices
+  float4* zone_ptr[CM_MAX_ZONES];        // all null: the ordinary local outputs
+  const uint32_t* zone_remote_base;      // [n_zones], device
 };
 // ---- radius outlier removal on the sorted cell keys (cm_outlier.cu) -------------------------------------------------------
 struct RorParams {
@@ -222,6 +226,13 @@ cudaError_t launch_giant_mask(const float4* pts, uint32_t n, const GiantPlan* pl
 cudaError_t launch_seed_bounds_enc(FrameAcc* acc, const uint32_t* enc6, cudaStream_t stream);
 // bounding box of n packed points into acc (frame 0), as launch_minmax does for the VoxelGrid-only entry
 uint32_t zone_tile_points();
+cudaError_t launch_zone_count_scan(const ZoneParams& p, cudaStream_t stream);      // the first two launches of a split
+cudaError_t launch_zone_scatter_remote(const ZoneParams& p, cudaStream_t stream);  // the third, into zone_ptr[] (peer memory)
+// where this rank's part of every destination starts in that destination's receive buffer, from the all-gathered offsets
+// (row s = rank s's zone_begin[0 .. world], entry CM_MAX_ZONES + 1 = its receive capacity); *overflow != 0: some rank would
+// receive more than it can hold (every rank sees the same) and nobody writes
+cudaError_t launch_giant_offsets(const uint32_t* counts_all, uint32_t stride, uint32_t world, uint32_t me, uint32_t* remote_base,
+                                 uint32_t* overflow, cudaStream_t stream);
 cudaError_t launch_zone_split(const ZoneParams& p, cudaStream_t stream);  // 3 launches
 cudaError_t launch_zone_scatter(const ZoneParams& p, cudaStream_t stream);  // the last of them again, after out_* grew
 #define CM_ZONE_LAUNCHES 3

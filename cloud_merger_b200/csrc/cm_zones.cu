@@ -171,6 +171,7 @@ __global__ void __launch_bounds__(1024) k_zone_scan(const ZoneParams p) {
   }
 }
 
+template <bool REMOTE>
 __global__ void __launch_bounds__(ZN_THREADS) k_zone_scatter(const ZoneParams p) {
   __shared__ uint32_t s_wcnt[ZN_WARPS][CM_MAX_ZONES];
   const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
@@ -205,7 +206,9 @@ __global__ void __launch_bounds__(ZN_THREADS) k_zone_scatter(const ZoneParams p)
   const uint32_t lt = lanemask_lt();
   for (uint32_t zs = present; zs; zs &= zs - 1u) {
     const uint32_t z = (uint32_t)__ffs(zs) - 1u;
-    uint32_t pos = p.zone_begin[z] + p.tile_offset[(size_t)z * p.n_tiles + tile];
+    // REMOTE: the zone is a destination rank; its points go straight into that rank's receive buffer over NVLink
+    uint32_t pos = (REMOTE ? p.zone_remote_base[z] : p.zone_begin[z]) + p.tile_offset[(size_t)z * p.n_tiles + tile];
+    float4* __restrict__ dst = REMOTE ? p.zone_ptr[z] : p.out_xyzi;
     for (uint32_t w2 = 0; w2 < warp; ++w2) pos += s_wcnt[w2][z];
 #pragma unroll
     for (int i = 0; i < ZN_IPT; ++i) {
@@ -213,8 +216,8 @@ __global__ void __launch_bounds__(ZN_THREADS) k_zone_scatter(const ZoneParams p)
       const uint32_t b = __ballot_sync(0xFFFFFFFFu, in);
       if (in) {
         const uint32_t q = pos + (uint32_t)__popc(b & lt);
-        p.out_xyzi[q] = v[i];
-        p.out_src[q] = base + 32 * i;
+        dst[q] = v[i];
+        if (!REMOTE) p.out_src[q] = base + 32 * i;
       }
       pos += (uint32_t)__popc(b);
     }
@@ -229,7 +232,47 @@ uint32_t zone_tile_points() { return ZN_TILE; }
 // the output arrays had to grow.
 cudaError_t launch_zone_scatter(const ZoneParams& p, cudaStream_t stream) {
   if (!p.n_tiles) return cudaSuccess;
-  k_zone_scatter<<<p.n_tiles, ZN_THREADS, 0, stream>>>(p);
+  k_zone_scatter<false><<<p.n_tiles, ZN_THREADS, 0, stream>>>(p);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_zone_scatter_remote(const ZoneParams& p, cudaStream_t stream) {
+  if (!p.n_tiles) return cudaSuccess;
+  k_zone_scatter<true><<<p.n_tiles, ZN_THREADS, 0, stream>>>(p);
+  return cudaGetLastError();
+}
+
+// rank `me`'s part of destination r starts after the parts of the ranks before it (rank order = source order)
+__global__ void k_giant_offsets(const uint32_t* __restrict__ counts_all, uint32_t stride, uint32_t world, uint32_t me,
+                                uint32_t* remote_base, uint32_t* overflow) {
+  const uint32_t r = threadIdx.x;
+  if (r >= world) return;
+  uint32_t before = 0, total = 0;
+  for (uint32_t s = 0; s < world; ++s) {
+    const uint32_t c = counts_all[s * stride + r + 1u] - counts_all[s * stride + r];
+    if (s < me) before += c;
+    total += c;
+  }
+  remote_base[r] = before;
+  const uint32_t cap = counts_all[r * stride + CM_MAX_ZONES + 1u];
+  if (total > cap) atomicMax(overflow, total);
+}
+
+cudaError_t launch_giant_offsets(const uint32_t* counts_all, uint32_t stride, uint32_t world, uint32_t me, uint32_t* remote_base,
+                                 uint32_t* overflow, cudaStream_t stream) {
+  k_giant_offsets<<<1, 32, 0, stream>>>(counts_all, stride, world, me, remote_base, overflow);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_zone_count_scan(const ZoneParams& p, cudaStream_t stream) {
+  if (p.n_tiles) {
+    if (p.mask_given) k_zone_count<false, true><<<p.n_tiles, ZN_THREADS, 0, stream>>>(p);
+    else if (p.zones.all_box) k_zone_count<true, false><<<p.n_tiles, ZN_THREADS, 0, stream>>>(p);
+    else k_zone_count<false, false><<<p.n_tiles, ZN_THREADS, 0, stream>>>(p);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+  }
+  k_zone_scan<<<p.zones.n_zones, 1024, 0, stream>>>(p);
   return cudaGetLastError();
 }
 
@@ -245,7 +288,7 @@ cudaError_t launch_zone_split(const ZoneParams& p, cudaStream_t stream) {
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return e;
   if (p.n_tiles) {
-    k_zone_scatter<<<p.n_tiles, ZN_THREADS, 0, stream>>>(p);
+    k_zone_scatter<false><<<p.n_tiles, ZN_THREADS, 0, stream>>>(p);
     e = cudaGetLastError();
   }
   return e;

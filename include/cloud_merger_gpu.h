@@ -472,6 +472,14 @@ CM_API int cm_dev_route_by_key(cm_handle_t h, const float* xyzi_dev, int64_t n_p
  * cm_giant_voxelgrid stops after the grouping (results through cm_get_zone_out) -- the routing can be tested on one GPU. */
 typedef struct cm_giant_s* cm_giant_t;
 #define CM_GIANT_ID_BYTES 128
+/* The exchange: PEER = the grouping kernel stores every point straight into its owner's receive buffer over NVLink (the
+ * buffers are mapped into every rank through CUDA IPC at cm_giant_create; one kernel is scatter and all-to-all at once,
+ * closed by a one-word all-reduce); NCCL = grouped into a local send buffer, then one grouped ncclSend / ncclRecv. PEER is
+ * chosen when every rank could map every peer (one process per GPU on an NVLink box); CM_GIANT_NO_P2P=1 in the environment
+ * forces NCCL. Both deliver the same points in the same order. */
+#define CM_GIANT_EXCHANGE_NONE 0
+#define CM_GIANT_EXCHANGE_NCCL 1
+#define CM_GIANT_EXCHANGE_PEER 2
 typedef struct {
   int64_t points_local, points_received, points_sent_away, points_total_finite;
   int64_t voxels_local;            /* filled by cm_giant_report */
@@ -479,6 +487,8 @@ typedef struct {
   float min_p[3], max_p[3];        /* global bounding box */
   int32_t min_b[3], div_b[3];      /* PCL's grid on it */
   int32_t key_bits, host_syncs;
+  int32_t exchange;                /* CM_GIANT_EXCHANGE_*: how the points reached their owners in this call */
+  int32_t reserved;
   int64_t send_begin[CM_MAX_ZONES + 1]; /* where the points for rank r start in the grouped array */
 } cm_giant_info_t;
 CM_API int cm_giant_unique_id(void* id_bytes);

@@ -105,6 +105,7 @@ def main():
                           "mpoints_per_s": n / dt / 1e6, "points_exchanged": sent, "bytes_exchanged": sent * 16,
                           "points_per_rank_after": [int(v[0]) for v in allv], "key_bits": out.get("key_bits"),
                           "local_voxelgrid_ms": out.get("gpu_ms"), "host_syncs_before_report": out.get("host_syncs"),
+                          "exchange": out.get("exchange"),
                           "api": "cm_giant_voxelgrid (C++ + NCCL behind the C ABI)", "check": check}) + "\n").encode())
     giant.close()
     cm.close()

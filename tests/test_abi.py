@@ -45,10 +45,10 @@ def test_struct_sizes_match_the_header():
 #include <stdio.h>
 #include "cloud_merger_gpu.h"
 int main(void) {
-  printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu\n", sizeof(cm_pass_t), sizeof(cm_layout_t), sizeof(cm_segment_t),
+  printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu\n", sizeof(cm_pass_t), sizeof(cm_layout_t), sizeof(cm_segment_t),
          sizeof(cm_config_t), sizeof(cm_stats_t), sizeof(cm_frame_info_t), sizeof(cm_device_out_t), sizeof(cm_frame_out_t),
          sizeof(cm_zone_t), sizeof(cm_zone_out_t), sizeof(cm_plane_cfg_t), sizeof(cm_plane_t), sizeof(cm_pc2_field_t),
-         sizeof(cm_pc2_desc_t), sizeof(cm_proceed_cfg_t), sizeof(cm_proceed_out_t));
+         sizeof(cm_pc2_desc_t), sizeof(cm_proceed_cfg_t), sizeof(cm_proceed_out_t), sizeof(cm_giant_info_t), sizeof(cm_frame_view_t));
   return 0;
 }'''
     with tempfile.TemporaryDirectory() as d:
@@ -60,7 +60,7 @@ int main(void) {
     mirror = [C.sizeof(t) for t in (_lib.CmPass, _lib.CmLayout, _lib.CmSegment, _lib.CmConfig, _lib.CmStats,
                                     _lib.CmFrameInfo, _lib.CmDeviceOut, _lib.CmFrameOut, _lib.CmZone, _lib.CmZoneOut,
                                     _lib.CmPlaneCfg, _lib.CmPlane, _lib.CmPc2Field, _lib.CmPc2Desc, _lib.CmProceedCfg,
-                                    _lib.CmProceedOut)]
+                                    _lib.CmProceedOut, _lib.CmGiantInfo, _lib.CmFrameView)]
     assert sizes == mirror
 
 
