@@ -68,6 +68,10 @@ struct Workspace {
   uint32_t* surv_src = nullptr;
   uint32_t* surv_key = nullptr;          // box-grid voxel keys written by K1 (fused-key runs)
   uint32_t* first_k1 = nullptr;          // [sort tiles] K1 tile holding the first key of every radix tile
+  SegTile* seg_tile = nullptr;           // frame-segmented sort (batches of several frames): [sort tiles + frames]
+  uint32_t* seg_hist = nullptr;          //   [frames][CM_SEG_PASSES][256]
+  uint32_t* seg_frame_tile0 = nullptr;   //   [frames + 1]
+  bool segmented = false;                // last run: the frame-segmented kernels were enqueued (SortInfo says whether they ran)
   bool fused_keys = false;               // last run: K1 produced the keys
   BoxGrid box{};
   void *keys_a = nullptr, *keys_b = nullptr;
@@ -297,7 +301,7 @@ cudaError_t dev_alloc(T** p, size_t count) {
 void ws_free(Workspace& w) {
   if (!w.ready) return;
   cudaFree(w.meta); cudaFreeHost(w.report); cudaFree(w.segs); cudaFree(w.tile_seg); cudaFree(w.surv_xyzi); cudaFree(w.surv_src);
-  cudaFree(w.surv_key); cudaFree(w.first_k1);
+  cudaFree(w.surv_key); cudaFree(w.first_k1); cudaFree(w.seg_tile); cudaFree(w.seg_hist); cudaFree(w.seg_frame_tile0);
   cudaFree(w.keys_a); cudaFree(w.keys_b); cudaFree(w.vals_a); cudaFree(w.vals_b);
   cudaFree(w.tile_rec); cudaFree(w.lb_sort); cudaFree(w.cent_status); cudaFree(w.epoch_dev);
   cudaFree(w.dense_xyzi); cudaFree(w.dense_src); cudaFree(w.dense_slot);
@@ -327,7 +331,12 @@ int ws_alloc(cm_handle_t h, Workspace& w, uint32_t points, uint32_t frames, uint
   // every segment owns at least one K1 tile
   w.lb_k1_n = np / k1_min_tile_points() + segs + 2;
   CM_CUDA(h, dev_alloc(&w.tile_seg, w.lb_k1_n));
-  w.lb_sort_n = sort_lookback_rows((uint32_t)np) * CM_RADIX;
+  w.lb_sort_n = (sort_lookback_rows((uint32_t)np) + (frames > 1 ? frames : 0u)) * CM_RADIX;  // segmented: a partial tile per frame
+  if (frames > 1) {
+    CM_CUDA(h, dev_alloc(&w.seg_tile, sort_lookback_rows((uint32_t)np) + frames));
+    CM_CUDA(h, dev_alloc(&w.seg_hist, (size_t)frames * CM_SEG_PASSES * CM_RADIX));
+    CM_CUDA(h, dev_alloc(&w.seg_frame_tile0, (size_t)frames + 1));
+  }
   w.lb_cent_n = np / centroid_tile_items() + 2;
   CM_CUDA(h, dev_alloc(&w.tile_rec, w.lb_k1_n));
   CM_CUDA(h, dev_alloc(&w.lb_sort, w.lb_sort_n));
@@ -457,6 +466,7 @@ void fill_voxel_params(cm_handle_t h, Workspace& w, VoxelParams& vp, const float
   vp.fused_keys = 0; vp.surv_key = w.surv_key; vp.box = BoxGrid{}; vp.first_k1 = w.first_k1;
   vp.sort_tile = sort_tile_items(4, max_points);
   vp.dual_width = 0;
+  vp.segmented = 0; vp.seg_tile = w.seg_tile; vp.seg_hist = w.seg_hist; vp.seg_frame_tile0 = w.seg_frame_tile0;
   vp.out_xyzi = w.out_xyzi; vp.out_count = w.out_count; vp.out_idx = w.out_idx;
   vp.trace = w.trace_sort;
   const char* tp = getenv("CM_TRACE_PASS");
@@ -489,6 +499,27 @@ int run_voxel(cm_handle_t h, Workspace& w, VoxelParams& vp, cudaStream_t st, boo
   const bool dual = !bounded && with_centroid && !no_dual;
   w.dual_width = dual;
   vp.dual_width = dual ? 1u : 0u;
+  // Batches of several frames: the frame bits need not be sorted (the input is frame-ordered). Taken where it pays -- fewer
+  // passes or 32-bit records instead of 64-bit keys: decided here when the grid is bounded, on the device when it is not
+  // (then the 32-bit kernels enqueued are the segmented ones: a batch whose voxel index fits 32 bits never needs frame bits).
+  static const bool no_seg = getenv("CM_NO_SEGMENTED") != nullptr;
+  vp.segmented = 0;
+  if (!no_seg && with_centroid && vp.n_frames > 1 && w.seg_tile && !vp.fused_keys) {
+    if (dual) {
+      vp.segmented = 1;
+    } else if (bounded) {
+      const uint32_t ib = known_idx_bits >= 0 ? (uint32_t)known_idx_bits : bits_for(cells), fb = bits_for(vp.n_frames);
+      const uint32_t p_seg = std::max<uint32_t>(1, (ib + CM_RADIX_BITS - 1) / CM_RADIX_BITS);
+      if (ib <= 32 && (p_seg < vp.max_passes || ib + fb > 32)) {
+        vp.segmented = 2;
+        vp.key_bytes = 4;
+        vp.max_passes = p_seg;
+      }
+    }
+  }
+  w.segmented = vp.segmented != 0;
+  if (vp.segmented)
+    CM_CUDA(h, cudaMemsetAsync(w.seg_hist, 0, (size_t)vp.n_frames * CM_SEG_PASSES * CM_RADIX * sizeof(uint32_t), st));
   if (scan_k1_tiles)
     CM_CUDA(h, launch_grid_setup(vp, st, w.tile_rec, w.n_k1_tiles, w.segs, w.n_segs,
                                  reinterpret_cast<uint32_t*>(w.meta + w.ml.off_segstart)));
@@ -504,6 +535,10 @@ int run_voxel(cm_handle_t h, Workspace& w, VoxelParams& vp, cudaStream_t st, boo
     CM_CUDA(h, launch_key_hist(v4, st));
     CM_CUDA(h, launch_key_hist(v8, st));
     w.launches += 2;
+    if (vp.segmented) {
+      CM_CUDA(h, launch_seg_base(v4, st));
+      ++w.launches;
+    }
     if (h->profiling) CM_CUDA(h, cudaEventRecord(w.ev[EV_KEY], st));
     for (uint32_t ps = 0; ps < 4; ++ps) CM_CUDA(h, launch_sort_pass(v4, (int)ps, st));
     for (uint32_t ps = 0; ps < CM_MAX_SORT_PASSES; ++ps) CM_CUDA(h, launch_sort_pass(v8, (int)ps, st));
@@ -530,6 +565,10 @@ int run_voxel(cm_handle_t h, Workspace& w, VoxelParams& vp, cudaStream_t st, boo
   w.max_passes = vp.max_passes;
   if (!vp.fused_keys) {
     CM_CUDA(h, launch_key_hist(vp, st));
+    ++w.launches;
+  }
+  if (vp.segmented) {
+    CM_CUDA(h, launch_seg_base(vp, st));
     ++w.launches;
   }
   if (h->profiling) CM_CUDA(h, cudaEventRecord(w.ev[EV_KEY], st));
@@ -762,7 +801,7 @@ int fetch_report(cm_handle_t h, Workspace& w, cudaEvent_t already_copied = nullp
     s.voxels_out = ctrl->total_voxels;
     s.key_bits = (int32_t)si->total_bits;
     s.sort_passes = (int32_t)si->num_passes;
-    if (w.dual_width) w.key_bytes = si->total_bits <= 32u ? 4u : 8u;
+    if (w.dual_width) w.key_bytes = si->width == 4u ? 4u : 8u;
     s.key_bytes = (int32_t)w.key_bytes;
   }
   const int last_ev = w.ran_voxel ? EV_CENT : EV_K1;
@@ -2848,7 +2887,20 @@ int cm_get_device_out(cm_handle_t h, cm_device_out_t* out) {
   }
   if (w.ran_voxel) {
     const bool odd = (h->stats.sort_passes & 1) != 0;
-    if (w.key_bytes == 4) {
+    const SortInfo* si_rep = reinterpret_cast<const SortInfo*>(w.report + w.ml.off_info);
+    out->key_bytes = (int32_t)w.key_bytes;
+    if (w.key_bytes == 4 && si_rep->segmented) {
+      // a frame-segmented run sorted bare voxel indices: hand out (frame << idx_bits | idx), as every other run does,
+      // in the ping-pong buffer the last pass did not write
+      VoxelParams vp;
+      fill_voxel_params(h, w, vp, w.voxel_pts, w.n_frames, (uint32_t)w.points_in);
+      unsigned long long* k64 = reinterpret_cast<unsigned long long*>(odd ? w.keys_a : w.keys_b);
+      CM_CUDA(h, launch_seg_keys64(odd ? w.keys_b : w.keys_a, k64, w.vals_b, vp, w.stream));
+      CM_CUDA(h, cudaStreamSynchronize(w.stream));
+      out->sorted_key = k64;
+      out->sorted_point = w.vals_b;
+      out->key_bytes = 8;
+    } else if (w.key_bytes == 4) {
       // 32-bit keys are sorted as 8-byte (key, value) records: split them into the two arrays this struct promises
       const uint32_t* n_ptr = reinterpret_cast<const uint32_t*>(w.meta + w.ml.off_fstart) + w.n_frames;
       VoxelParams vp;  // fused-key runs sorted box-grid keys: hand out PCL's index, like every other run
@@ -2867,9 +2919,7 @@ int cm_get_device_out(cm_handle_t h, cm_device_out_t* out) {
     out->voxel_xyzi = w.out_xyzi;
     out->voxel_count = w.out_count;
     out->voxel_idx = reinterpret_cast<const uint64_t*>(w.out_idx);
-    out->key_bytes = (int32_t)w.key_bytes;
-    const SortInfo* si = reinterpret_cast<const SortInfo*>(w.report + w.ml.off_info);
-    out->key_idx_bits = (int32_t)si->idx_bits;
+    out->key_idx_bits = (int32_t)si_rep->idx_bits;
   }
   return rc;
 }

@@ -133,8 +133,21 @@ struct SortInfo {
   uint32_t idx_bits;
   uint32_t n_keys;      // = survivors
   uint32_t key_frames;  // F (+1 when a sentinel frame is needed for invalid points)
-  uint32_t pad_[3];
+  uint32_t width;       // bytes of the keys that travel through the sort: 4 (8-byte records) or 8
+  uint32_t segmented;   // frame-segmented sort: the keys are the voxel index alone (no frame bits), every frame is sorted as its
+                        // own segment of the frame-ordered input, the frame of a key is known from its position
+  uint32_t n_seg_tiles; // segmented: number of (frame-aligned) radix tiles
 };
+
+// One radix tile of a frame-segmented sort: tiles never straddle frames.
+struct SegTile {
+  uint32_t base;   // position of the tile's first key (in every ping-pong buffer: a frame keeps its range)
+  uint32_t n;      // keys in the tile (< tile size only for the last tile of a frame)
+  uint32_t frame;  // bit 31: first tile of its frame
+  uint32_t pad;
+};
+constexpr uint32_t CM_SEG_FIRST = 0x80000000u;
+constexpr uint32_t CM_SEG_PASSES = 4;  // a segmented key is 32 bits wide at most
 
 // ---- float <-> order-preserving uint -----------------------------------------------------------------------------
 __host__ __device__ __forceinline__ uint32_t f32_order_enc(uint32_t bits) {

@@ -93,8 +93,16 @@ struct VoxelParams {
   BoxGrid box;
   uint32_t* first_k1;                // [sort tiles] K1 tile that holds dense position t * sort_tile (written by k_grid_setup)
   uint32_t sort_tile;                // keys per tile of the radix passes of this run
-  uint32_t dual_width;               // the key width is only known on the device (SortInfo.total_bits): the host enqueues the
+  uint32_t dual_width;               // the key width is only known on the device (SortInfo.width): the host enqueues the
                                      // 32-bit AND the 64-bit instantiation of every kernel, the one that does not apply exits
+  // Frame-segmented sort (batches of several frames): the frame bits are not sorted -- the input is frame-ordered already --
+  // so the keys are the bare voxel index: 32-bit records where (frame, index) needed 64 bits, and fewer passes.
+  uint32_t segmented;                // 0: never; 1: the device decides (dual_width runs: segmented 32-bit or plain 64-bit);
+                                     // 2: the host decided (bounded grid)
+  SegTile* seg_tile;                 // [sort tiles + frames] written by k_grid_setup
+  uint32_t* seg_hist;                // [n_frames][CM_SEG_PASSES][256] digit counts per frame, turned into first positions
+                                     // (frame start + exclusive scan) by k_seg_base
+  uint32_t* seg_frame_tile0;         // [n_frames + 1] scratch of k_grid_setup
   void* out_xyzi;
   uint32_t* out_count;
   unsigned long long* out_idx;
@@ -110,6 +118,10 @@ cudaError_t launch_seed_bounds(FrameAcc* acc, const float* mn, const float* mx, 
 cudaError_t launch_grid_setup(const VoxelParams& p, cudaStream_t stream, TileRec* scan_rec = nullptr, uint32_t scan_tiles = 0,
                               const SegDev* segs = nullptr, uint32_t n_seg = 0, uint32_t* seg_surv_start = nullptr);
 cudaError_t launch_key_hist(const VoxelParams& p, cudaStream_t stream);
+cudaError_t launch_seg_base(const VoxelParams& p, cudaStream_t stream);  // segmented runs: between key_hist and the passes
+// segmented runs sort bare voxel indices; this hands out (frame << idx_bits | idx) keys and the values as two arrays
+cudaError_t launch_seg_keys64(const void* records, unsigned long long* keys, uint32_t* vals, const VoxelParams& p,
+                              cudaStream_t stream);
 cudaError_t launch_sort_pass(const VoxelParams& p, int pass, cudaStream_t stream);
 // 32-bit keys are sorted as 8-byte (key, value) records in keys_a/keys_b; this splits the first *n_ptr records into two arrays
 // remap != null (fused-key run): the keys index the crop box's grid; they are handed out re-based on each frame's data-derived

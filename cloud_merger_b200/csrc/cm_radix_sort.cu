@@ -84,21 +84,31 @@ constexpr int RS_SCAN_ROWS = 32;                        // rows per batch (one w
 constexpr int RS_SCAN_GROUP = RS_THREADS >= 512 ? 8 : 16;  // rows polled together (register budget of the CTA shape)
 static_assert(RS_SCAN_DIGITS == 32, "one digit per lane");
 
+//
+// SEG (frame-segmented sort): the tiles are frame-aligned and every frame is a sort of its own, so the running sum restarts
+// at the first tile of a frame from that frame's own first positions (seg_base: frame start + exclusive scan of the frame's
+// digit counts, prepared by k_seg_base); a worker on the first tile of a frame reads them itself and waits for nobody.
+template <bool SEG>
 __device__ __forceinline__ void scanner_cta(uint32_t scanner /* 0 .. RS_SCANNERS-1 */, unsigned long long* rows /* row 0 */,
                                             uint32_t n_tiles, uint32_t epoch, const uint32_t* hist /* this pass */,
                                             uint32_t* err, uint32_t* s_scan, uint32_t* s_tmp /* >= 256 words */,
-                                            unsigned long long* s_chain /* 32 */) {
+                                            unsigned long long* s_chain /* 32 */, const SegTile* __restrict__ seg_tile,
+                                            const uint32_t* __restrict__ seg_base /* [frame][CM_SEG_PASSES][256], at this pass */) {
   const uint32_t tid = threadIdx.x, lane = tid & 31u, q = tid >> 5;
   const uint32_t d = scanner * RS_SCAN_DIGITS + lane;  // digit
-  // exclusive scan of the global digit histogram: where digit d starts in the output of this pass
-  uint32_t tot;
-  const uint32_t gb = block_excl_scan_256(tid < CM_RADIX ? hist[tid] : 0u, s_scan, &tot);
-  if (tid < CM_RADIX) s_tmp[tid] = gb;
-  __syncthreads();
-  if (q == 0) {
-    const uint32_t run0 = s_tmp[d];
-    st_cg_u64(rows - CM_RADIX + d, lb_pack(epoch, CM_LB_INCL, run0));  // row -1
-    s_chain[lane] = (unsigned long long)run0;                           // sequence number 0: the sum before batch 0
+  if (SEG) {
+    if (q == 0) s_chain[lane] = 0ull;  // sequence number 0; the value is never used (tile 0 starts a frame)
+  } else {
+    // exclusive scan of the global digit histogram: where digit d starts in the output of this pass
+    uint32_t tot;
+    const uint32_t gb = block_excl_scan_256(tid < CM_RADIX ? hist[tid] : 0u, s_scan, &tot);
+    if (tid < CM_RADIX) s_tmp[tid] = gb;
+    __syncthreads();
+    if (q == 0) {
+      const uint32_t run0 = s_tmp[d];
+      st_cg_u64(rows - CM_RADIX + d, lb_pack(epoch, CM_LB_INCL, run0));  // row -1
+      s_chain[lane] = (unsigned long long)run0;                           // sequence number 0: the sum before batch 0
+    }
   }
   __syncthreads();
   const uint32_t n_batches = (n_tiles + RS_SCAN_ROWS - 1) / RS_SCAN_ROWS;
@@ -132,10 +142,26 @@ __device__ __forceinline__ void scanner_cta(uint32_t scanner /* 0 .. RS_SCANNERS
       }
     }
     uint32_t sum = 0;
+    uint32_t abs_from = RS_SCAN_ROWS;  // SEG: rows from here on carry absolute positions (a frame started inside the batch)
+    if (SEG) {
+      const uint32_t mine = (r0 + lane < n_tiles) ? __ldg(&seg_tile[r0 + lane].frame) : 0u;  // lane k: row r0 + k
+      const uint32_t firsts = __ballot_sync(0xFFFFFFFFu, (mine & CM_SEG_FIRST) != 0u);
+      if (firsts) abs_from = (uint32_t)__ffs(firsts) - 1u;
 #pragma unroll
-    for (int k = 0; k < RS_SCAN_ROWS; ++k) {
-      sum += c[k];
-      c[k] = sum;  // inclusive within the batch
+      for (int k = 0; k < RS_SCAN_ROWS; ++k) {
+        if (firsts & (1u << k)) {  // warp-uniform
+          const uint32_t f = __shfl_sync(0xFFFFFFFFu, mine, k) & ~CM_SEG_FIRST;
+          sum = __ldg(seg_base + (size_t)f * (CM_SEG_PASSES * CM_RADIX) + d);
+        }
+        sum += c[k];
+        c[k] = sum;
+      }
+    } else {
+#pragma unroll
+      for (int k = 0; k < RS_SCAN_ROWS; ++k) {
+        sum += c[k];
+        c[k] = sum;  // inclusive within the batch
+      }
     }
     // serial part: take the running sum from the previous batch's warp, pass it on
     unsigned long long x = *chain;
@@ -149,10 +175,18 @@ __device__ __forceinline__ void scanner_cta(uint32_t scanner /* 0 .. RS_SCANNERS
       x = *chain;
     }
     const uint32_t run = (uint32_t)x;
-    *chain = ((unsigned long long)(b + 1u) << 32) | (unsigned long long)(run + sum);
+    if (SEG) {
+      *chain = ((unsigned long long)(b + 1u) << 32) | (unsigned long long)(abs_from < RS_SCAN_ROWS ? sum : run + sum);
 #pragma unroll
-    for (int k = 0; k < RS_SCAN_ROWS; ++k)
-      if (r0 + k < n_tiles) st_cg_u64(base + (size_t)k * CM_RADIX, lb_pack(epoch, CM_LB_INCL, run + c[k]));
+      for (int k = 0; k < RS_SCAN_ROWS; ++k)
+        if (r0 + k < n_tiles)
+          st_cg_u64(base + (size_t)k * CM_RADIX, lb_pack(epoch, CM_LB_INCL, (uint32_t)k >= abs_from ? c[k] : run + c[k]));
+    } else {
+      *chain = ((unsigned long long)(b + 1u) << 32) | (unsigned long long)(run + sum);
+#pragma unroll
+      for (int k = 0; k < RS_SCAN_ROWS; ++k)
+        if (r0 + k < n_tiles) st_cg_u64(base + (size_t)k * CM_RADIX, lb_pack(epoch, CM_LB_INCL, run + c[k]));
+    }
   }
 }
 
@@ -199,8 +233,10 @@ struct SortSmem {
 
 // FUSED0: pass 0 of a run whose keys were written by K1 at the survivors' slots (VoxelParams::fused_keys): the tile's keys
 // are read through the K1 tile records, the value of a key is the slot it was read from.
-template <typename KeyT, int IPT, bool FUSED0 = false>
+// SEG: frame-segmented sort (see scanner_cta): tile t is seg_tile[t] -- a range of one frame -- instead of [t TILE, (t+1) TILE).
+template <typename KeyT, int IPT, bool FUSED0 = false, bool SEG = false>
 __global__ void __launch_bounds__(RS_THREADS, RS_MIN_CTAS) k_onesweep_pass(const VoxelParams p, const int pass) {
+  static_assert(!SEG || (sizeof(KeyT) == 4 && !FUSED0), "segmented keys are 32-bit records written by k_voxel_key_hist");
   constexpr int TILE = RS_THREADS * IPT;
   constexpr int WARP_ITEMS = 32 * IPT;
   constexpr bool AOS = sizeof(KeyT) == 4;  // (key, value) records of 8 bytes
@@ -210,9 +246,11 @@ __global__ void __launch_bounds__(RS_THREADS, RS_MIN_CTAS) k_onesweep_pass(const
   const long long tr0 = clock64();
   const SortInfo si = *p.info;
   if ((uint32_t)pass >= si.num_passes) return;
-  if (p.dual_width && ((si.total_bits <= 32u) != (sizeof(KeyT) == 4))) return;  // the other key width runs
+  if (p.dual_width && ((si.width == 4u) != (sizeof(KeyT) == 4))) return;  // the other key width runs
+  if (SEG != (si.segmented != 0u)) return;
   const uint32_t M = si.n_keys;
-  const uint32_t n_tiles = (M + TILE - 1) / TILE;
+  const uint32_t n_tiles = SEG ? si.n_seg_tiles : (M + TILE - 1) / TILE;
+  const uint32_t* const seg_base = SEG ? p.seg_hist + (size_t)pass * CM_RADIX : nullptr;
 
   const uint32_t tid = threadIdx.x, lane = tid & 31u;
   const uint32_t warp = __shfl_sync(0xFFFFFFFFu, tid >> 5, 0);  // provably warp-uniform
@@ -233,7 +271,7 @@ __global__ void __launch_bounds__(RS_THREADS, RS_MIN_CTAS) k_onesweep_pass(const
   const uint32_t role = sm.next_tile[1];
   if (role < (uint32_t)RS_SCANNERS) {
     __syncthreads();  // every thread has read the role before the scanner reuses the shared memory
-    scanner_cta(role, rows, n_tiles, epoch, p.hist + pass * CM_RADIX, err, sm.scan, sm.hist, &sm.k[0][0]);
+    scanner_cta<SEG>(role, rows, n_tiles, epoch, p.hist + pass * CM_RADIX, err, sm.scan, sm.hist, &sm.k[0][0], p.seg_tile, seg_base);
     return;
   }
 
@@ -254,6 +292,7 @@ __global__ void __launch_bounds__(RS_THREADS, RS_MIN_CTAS) k_onesweep_pass(const
   uint32_t cur = sm.next_tile[0];
   __syncthreads();  // next_tile[1] (the role) is rewritten below; sm.cnt is cleared
   uint32_t prev = 0xFFFFFFFFu, prev_n = 0;
+  uint32_t prev_seg = 0;  // SEG: frame (and first-of-frame bit) of the tile in back()
   uint32_t buf = 0;  // also the parity of the iteration
   long long tr_cur = tr0, tr_prev = tr0;
   uint32_t claimed = 0xFFFFFFFFu;
@@ -262,10 +301,16 @@ __global__ void __launch_bounds__(RS_THREADS, RS_MIN_CTAS) k_onesweep_pass(const
     tr_cur = clock64();
     const bool have = cur < n_tiles;
     uint32_t n_here = 0;
+    uint32_t cur_seg = 0;
     if (have) {
       // ================================= front(cur) ==========================================================
-      const uint32_t tile_base = cur * TILE;
-      n_here = min((uint32_t)TILE, M - tile_base);
+      uint32_t tile_base = cur * TILE;
+      if (SEG) {
+        const uint4 q = __ldg(reinterpret_cast<const uint4*>(p.seg_tile + cur));
+        tile_base = q.x; n_here = q.y; cur_seg = q.z;
+      } else {
+        n_here = min((uint32_t)TILE, M - tile_base);
+      }
       const bool full = n_here == (uint32_t)TILE;
       const uint32_t item0 = warp * WARP_ITEMS + lane;  // tile-local index of item 0 of this thread; item i = item0 + 32 i
       // ---- load keys and values (warp-striped, coalesced). Slots past the end of a partial (last) tile get the
@@ -447,7 +492,11 @@ __global__ void __launch_bounds__(RS_THREADS, RS_MIN_CTAS) k_onesweep_pass(const
       RS_TRACE(prev, 7, tr_prev);
       // ---- one row from the scanners: where this tile's keys of digit d start in the output ----------------------
       if (RS_THREADS == CM_RADIX || tid < CM_RADIX) {
-        const uint32_t first = lb_wait_inclusive(rows + ((long long)prev - 1) * CM_RADIX + tid, epoch, err);
+        uint32_t first;
+        if (SEG && (prev_seg & CM_SEG_FIRST))  // first tile of its frame: the frame's own first positions, nobody to wait for
+          first = __ldg(seg_base + (size_t)(prev_seg & ~CM_SEG_FIRST) * (CM_SEG_PASSES * CM_RADIX) + tid);
+        else
+          first = lb_wait_inclusive(rows + ((long long)prev - 1) * CM_RADIX + tid, epoch, err);
         sm.scatter[pb][tid] += first;  // modulo 2^32
       }
       __syncthreads();
@@ -518,6 +567,7 @@ __global__ void __launch_bounds__(RS_THREADS, RS_MIN_CTAS) k_onesweep_pass(const
     if (tid == 0) sm.next_tile[buf ^ 1u] = claimed;
     prev = cur;
     prev_n = n_here;
+    prev_seg = cur_seg;
     buf ^= 1u;
     // Orders this iteration's shared-memory reads (placement reads of the counter rows, scatter reads of the other
     // buffer) before the next iteration's writes, and makes next_tile (written long ago by thread 0) visible.
@@ -571,6 +621,7 @@ uint32_t sort_tile_items(uint32_t key_bytes, uint32_t max_points) {
 }
 
 // rows of look-back words a workspace of `capacity` points needs (+1 for row -1, +1 spare)
+// (a frame-segmented sort needs one more row per frame: see ws_alloc)
 size_t sort_lookback_rows(uint32_t capacity) {
   const uint32_t small_part = std::min(capacity, RS_SMALL_LIMIT);
   const size_t rows_small = small_part / (RS_THREADS * RS_IPT_SMALL) + 1;
@@ -579,23 +630,23 @@ size_t sort_lookback_rows(uint32_t capacity) {
 }
 
 namespace {
-template <typename KeyT, int IPT, bool FUSED0 = false>
+template <typename KeyT, int IPT, bool FUSED0 = false, bool SEG = false>
 struct PassLaunch {
   static inline int ctas_per_sm = 0;
   static cudaError_t configure() {
-    cudaError_t e = cudaFuncSetAttribute(k_onesweep_pass<KeyT, IPT, FUSED0>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    cudaError_t e = cudaFuncSetAttribute(k_onesweep_pass<KeyT, IPT, FUSED0, SEG>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)sizeof(SortSmem<KeyT, IPT>));
     if (e != cudaSuccess) return e;
-    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, k_onesweep_pass<KeyT, IPT, FUSED0>, RS_THREADS,
+    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, k_onesweep_pass<KeyT, IPT, FUSED0, SEG>, RS_THREADS,
                                                          sizeof(SortSmem<KeyT, IPT>));
   }
   static cudaError_t launch(const VoxelParams& p, int pass, int sms, cudaStream_t stream) {
     const uint32_t tile = RS_THREADS * IPT;
-    const uint32_t tiles = (p.max_points + tile - 1) / tile;
+    const uint32_t tiles = (p.max_points + tile - 1) / tile + (SEG ? p.n_frames : 0u);  // SEG: a partial tile per frame
     if (tiles == 0) return cudaSuccess;
     // persistent workers: at most what the device holds at once (tiles are handed out by an atomic counter)
     const uint32_t workers = std::min<uint32_t>(tiles, (uint32_t)(sms * std::max(1, ctas_per_sm)) - RS_SCANNERS);
-    k_onesweep_pass<KeyT, IPT, FUSED0><<<workers + RS_SCANNERS, RS_THREADS, sizeof(SortSmem<KeyT, IPT>), stream>>>(p, pass);
+    k_onesweep_pass<KeyT, IPT, FUSED0, SEG><<<workers + RS_SCANNERS, RS_THREADS, sizeof(SortSmem<KeyT, IPT>), stream>>>(p, pass);
     return cudaGetLastError();
   }
 };
@@ -610,6 +661,8 @@ cudaError_t configure_sort_kernels() {
   if (e == cudaSuccess) e = PassLaunch<unsigned long long, RS_IPT_SMALL>::configure();
   if (e == cudaSuccess) e = PassLaunch<uint32_t, SortCfg<uint32_t>::IPT, true>::configure();
   if (e == cudaSuccess) e = PassLaunch<uint32_t, RS_IPT_SMALL, true>::configure();
+  if (e == cudaSuccess) e = PassLaunch<uint32_t, SortCfg<uint32_t>::IPT, false, true>::configure();
+  if (e == cudaSuccess) e = PassLaunch<uint32_t, RS_IPT_SMALL, false, true>::configure();
   if (e != cudaSuccess) return e;
   if (getenv("CM_DEBUG"))
     fprintf(stderr, "[cm] sort pass CTAs per SM: %d / %d (32 / 64-bit keys), small tile %d / %d\n",
@@ -628,6 +681,9 @@ cudaError_t launch_sort_pass(const VoxelParams& p, int pass, cudaStream_t stream
   if (p.fused_keys && pass == 0)  // 32-bit keys by construction
     return small ? PassLaunch<uint32_t, RS_IPT_SMALL, true>::launch(p, pass, sms, stream)
                  : PassLaunch<uint32_t, SortCfg<uint32_t>::IPT, true>::launch(p, pass, sms, stream);
+  if (p.key_bytes == 4 && p.segmented)
+    return small ? PassLaunch<uint32_t, RS_IPT_SMALL, false, true>::launch(p, pass, sms, stream)
+                 : PassLaunch<uint32_t, SortCfg<uint32_t>::IPT, false, true>::launch(p, pass, sms, stream);
   if (p.key_bytes == 4)
     return small ? PassLaunch<uint32_t, RS_IPT_SMALL>::launch(p, pass, sms, stream)
                  : PassLaunch<uint32_t, SortCfg<uint32_t>::IPT>::launch(p, pass, sms, stream);

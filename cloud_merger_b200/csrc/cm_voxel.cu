@@ -293,15 +293,25 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_grid_setup(const VoxelParams p
     __syncthreads();
     if (tid == 0) *p.epoch_dev = wrap ? 16u : e + 16u;
   }
+  __shared__ SortInfo s_si;
   if (tid == 0) {
-    const uint32_t key_frames = p.n_frames + (p.ctrl->has_invalid ? 1u : 0u);
-    const uint32_t frame_bits = key_frames <= 1u ? 0u : (uint32_t)(32 - __clz((int)(key_frames - 1u)));
+    const bool has_invalid = p.ctrl->has_invalid != 0u;
+    const uint32_t key_frames = p.n_frames + (has_invalid ? 1u : 0u);
+    uint32_t frame_bits = key_frames <= 1u ? 0u : (uint32_t)(32 - __clz((int)(key_frames - 1u)));
     uint32_t idx_bits = s_maxbits;
     if (p.fused_keys) idx_bits = p.box.idx_bits;  // the keys K1 wrote are built on the crop box's grid, which holds every frame's
+    // Frame-segmented sort: the batch is frame-ordered, so the frame bits need no sorting. Possible when no survivor is
+    // non-finite (those are keyed into a sentinel frame of their own) and the voxel index alone fits 32 bits -- which PCL
+    // itself requires of a frame it filters.
+    bool seg = p.segmented == 2u;
+    if (p.segmented == 1u) seg = !has_invalid && idx_bits <= 32u;
+    if (seg) frame_bits = 0u;
+    uint32_t width = p.key_bytes;
+    if (p.dual_width) width = p.segmented == 1u ? (seg ? 4u : 8u) : (frame_bits + idx_bits <= 32u ? 4u : 8u);
     uint32_t total = frame_bits + idx_bits;
-    if (total > p.key_bytes * 8u) {
+    if (total > width * 8u) {
       atomicExch(&p.ctrl->error, (uint32_t)CM_DEV_E_KEY_RANGE);
-      total = p.key_bytes * 8u;
+      total = width * 8u;
       idx_bits = total - frame_bits;
     }
     uint32_t passes = (total + CM_RADIX_BITS - 1) / CM_RADIX_BITS;
@@ -316,9 +326,42 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_grid_setup(const VoxelParams p
     si.idx_bits = idx_bits;
     si.n_keys = p.frame_surv_start[p.n_frames];
     si.key_frames = key_frames;
-    si.pad_[0] = si.pad_[1] = si.pad_[2] = 0;
-    *p.info = si;
+    si.width = width;
+    si.segmented = seg ? 1u : 0u;
+    si.n_seg_tiles = 0;
+    s_si = si;
   }
+  __syncthreads();
+  if (s_si.segmented) {
+    // the frame-aligned radix tiles: frame f owns ceil(n_f / T) consecutive tiles
+    const uint32_t T = p.sort_tile, F = p.n_frames;
+    uint32_t carry = 0;
+    for (uint32_t f0 = 0; f0 < F; f0 += SCAN_THREADS) {
+      const uint32_t f = f0 + tid;
+      const uint32_t nf = f < F ? p.frame_surv_start[f + 1] - p.frame_surv_start[f] : 0u;
+      uint32_t tot;
+      const uint32_t ex = block_excl_scan_1024((nf + T - 1u) / T, s_scr, &tot);
+      if (f < F) p.seg_frame_tile0[f] = carry + ex;
+      carry += tot;
+    }
+    if (tid == 0) { p.seg_frame_tile0[F] = carry; s_si.n_seg_tiles = carry; }
+    __syncthreads();
+    const uint32_t warp = tid >> 5, lane = tid & 31u;
+    for (uint32_t f = warp; f < F; f += SCAN_THREADS / 32) {
+      const uint32_t b = p.frame_surv_start[f], e = p.frame_surv_start[f + 1];
+      const uint32_t t0 = p.seg_frame_tile0[f], nt = p.seg_frame_tile0[f + 1] - t0;
+      for (uint32_t t = lane; t < nt; t += 32u) {
+        SegTile st;
+        st.base = b + t * T;
+        st.n = min(T, e - st.base);
+        st.frame = f | (t == 0u ? CM_SEG_FIRST : 0u);
+        st.pad = 0u;
+        p.seg_tile[t0 + t] = st;
+      }
+    }
+    __syncthreads();
+  }
+  if (tid == 0) *p.info = s_si;
 }
 
 // ---- voxel key per point + the digit histograms of every radix pass -----------------------------------------------------
@@ -328,7 +371,9 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_grid_setup(const VoxelParams p
 // (SASS ATOMS.POPC.INC), so neither the warp-uniform high digits nor the scattered low digits need software matching.
 // CHECK: non-finite survivors are possible (no crop pass configured) and get the sentinel frame; any PassThrough stage
 // rejects them, so the common instantiation carries no finite tests.
-template <typename KeyT, bool CHECK>
+// SEG (frame-segmented sort): the key is the voxel index alone, and the digits are counted per frame -- the counters are
+// flushed to the frame's own histogram whenever the CTA moves on to a tile of another frame.
+template <typename KeyT, bool CHECK, bool SEG = false>
 __device__ __forceinline__ void key_hist_tiles(const VoxelParams& p, uint32_t (*s_hist)[CM_RADIX], const SortInfo& si,
                                                uint32_t M) {
   const uint32_t tid = threadIdx.x;
@@ -348,6 +393,18 @@ __device__ __forceinline__ void key_hist_tiles(const VoxelParams& p, uint32_t (*
   const unsigned long long sentinel = (unsigned long long)F << idx_bits;
   const float inv0 = p.inv_leaf[0], inv1 = p.inv_leaf[1], inv2 = p.inv_leaf[2];
 
+  uint32_t hist_frame = 0xFFFFFFFFu;  // SEG: the frame the shared counters belong to
+  auto flush_frame = [&]() {
+    __syncthreads();
+    if (hist_frame != 0xFFFFFFFFu) {
+      uint32_t* dst = p.seg_hist + (size_t)hist_frame * (CM_SEG_PASSES * CM_RADIX);
+      for (uint32_t i = tid; i < n_pass * CM_RADIX; i += VX_THREADS) {
+        const uint32_t c = (&s_hist[0][0])[i];
+        if (c) { atomicAdd(dst + i, c); (&s_hist[0][0])[i] = 0u; }
+      }
+    }
+    __syncthreads();
+  };
   for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
     TileRec r;
     if (dense) {
@@ -365,8 +422,12 @@ __device__ __forceinline__ void key_hist_tiles(const VoxelParams& p, uint32_t (*
       r.count = q.x; r.slot0 = q.y; r.frame = q.z; r.dense0 = q.w;
     }
     if (r.count == 0) continue;
+    if (SEG && r.frame != hist_frame) {
+      flush_frame();
+      hist_frame = r.frame;
+    }
     const GridDev* __restrict__ g = p.grid + r.frame;
-    const KeyT fbits = (KeyT)((unsigned long long)r.frame << idx_bits);
+    const KeyT fbits = SEG ? (KeyT)0 : (KeyT)((unsigned long long)r.frame << idx_bits);
     const KeyT mul1 = (KeyT)g->mul1, mul2 = (KeyT)g->mul2;  // 32-bit arithmetic when the key is 32-bit
     const int mb0 = g->min_b[0], mb1 = g->min_b[1], mb2 = g->min_b[2];
     const float4* __restrict__ src = p.pts + r.slot0;
@@ -414,23 +475,58 @@ __device__ __forceinline__ void key_hist_tiles(const VoxelParams& p, uint32_t (*
       }
     }
   }
+  if (SEG) flush_frame();
 }
 
 template <typename KeyT>
 __global__ void __launch_bounds__(VX_THREADS) k_voxel_key_hist(const VoxelParams p) {
   __shared__ uint32_t s_hist[CM_MAX_SORT_PASSES][CM_RADIX];
   const uint32_t tid = threadIdx.x;
-  if (p.dual_width && ((p.info->total_bits <= 32u) != (sizeof(KeyT) == 4))) return;  // the other key width runs
+  const SortInfo si = *p.info;
+  if (p.dual_width && ((si.width == 4u) != (sizeof(KeyT) == 4))) return;  // the other key width runs
   for (uint32_t i = tid; i < CM_MAX_SORT_PASSES * CM_RADIX; i += VX_THREADS) (&s_hist[0][0])[i] = 0;
   __syncthreads();
   const uint32_t M = p.frame_surv_start[p.n_frames];
-  const SortInfo si = *p.info;
+  if (sizeof(KeyT) == 4 && si.segmented) {
+    key_hist_tiles<uint32_t, false, true>(p, s_hist, si, M);  // the frames' own histograms are complete: nothing global
+    return;
+  }
   if (si.key_frames > p.n_frames) key_hist_tiles<KeyT, true>(p, s_hist, si, M);
   else key_hist_tiles<KeyT, false>(p, s_hist, si, M);
   __syncthreads();
   for (uint32_t i = tid; i < si.num_passes * CM_RADIX; i += VX_THREADS) {
     const uint32_t c = (&s_hist[0][0])[i];
     if (c) atomicAdd(p.hist + i, c);
+  }
+}
+
+// ---- segmented runs: per-frame digit counts -> where the frame's keys of digit d start in the output of pass ps ------------
+__global__ void __launch_bounds__(CM_RADIX) k_seg_base(const VoxelParams p) {
+  __shared__ uint32_t s_scan[12];
+  const SortInfo si = *p.info;
+  if (!si.segmented || blockIdx.y >= si.num_passes) return;
+  const uint32_t f = blockIdx.x, tid = threadIdx.x;
+  uint32_t* h = p.seg_hist + ((size_t)f * CM_SEG_PASSES + blockIdx.y) * CM_RADIX;
+  uint32_t tot;
+  const uint32_t ex = block_excl_scan_256(h[tid], s_scan, &tot);
+  h[tid] = p.frame_surv_start[f] + ex;
+}
+
+// segmented runs sort (idx, slot) records; callers of cm_get_device_out get (frame << idx_bits | idx) and the slots
+__global__ void __launch_bounds__(VX_THREADS) k_seg_keys64(const uint2* __restrict__ rec, unsigned long long* __restrict__ keys,
+                                                          uint32_t* __restrict__ vals, const VoxelParams p) {
+  const uint32_t F = p.n_frames, idx_bits = p.info->idx_bits;
+  const uint32_t* __restrict__ fss = p.frame_surv_start;
+  const uint32_t n = fss[F];
+  for (uint32_t i = blockIdx.x * VX_THREADS + threadIdx.x; i < n; i += gridDim.x * VX_THREADS) {
+    uint32_t lo = 0, hi = F - 1u;  // the last frame that starts at or before i
+    while (lo < hi) {
+      const uint32_t mid = (lo + hi + 1u) >> 1;
+      if (fss[mid] <= i) lo = mid; else hi = mid - 1u;
+    }
+    const uint2 r = rec[i];
+    keys[i] = ((unsigned long long)lo << idx_bits) | (unsigned long long)r.x;
+    vals[i] = r.y;
   }
 }
 
@@ -454,9 +550,16 @@ __global__ void __launch_bounds__(VX_THREADS) k_voxel_key_hist(const VoxelParams
 // The first version did the per-voxel work in the thread that owned the head item: with ~1 surviving head per 8 items
 // the warp executed the whole epilogue (four divisions, stores, atomics) for a handful of active lanes at a time, and
 // the kernel issued 190 instructions per item.
-template <typename KeyT>
+//
+// SEG (frame-segmented sort): the records carry the bare voxel index; frame f occupies positions [frame_surv_start[f],
+// frame_surv_start[f+1]) of the sorted array exactly as it did before the sort, so the frame of an item follows from its
+// position and the kernel works on the logical key (frame << idx_bits | idx) like the unsegmented 64-bit one.
+constexpr uint32_t CE_SEG_SMEM_FRAMES = 256;  // frame starts staged in shared memory up to here (else read from L2)
+template <typename KeyT, bool SEG = false>
 __global__ void __launch_bounds__(VX_THREADS, CE_MIN_CTAS) k_voxel_centroid(const VoxelParams p) {
-  constexpr bool REC = sizeof(KeyT) == 4;  // 8-byte (key, value) records
+  static_assert(!SEG || sizeof(KeyT) == 8, "the logical key of a segmented run is 64 bits wide");
+  constexpr bool REC = SEG || sizeof(KeyT) == 4;  // 8-byte (key, value) records
+  __shared__ uint32_t s_fss[SEG ? CE_SEG_SMEM_FRAMES + 1 : 1];
   __shared__ uint32_t s_scan[9];
   __shared__ __align__(16) float4 s_pts[CE_TILE];
   __shared__ uint32_t s_headw[CE_TILE / 32 + 1];  // bit i: item i starts a run; bit tile_n: sentinel
@@ -467,7 +570,8 @@ __global__ void __launch_bounds__(VX_THREADS, CE_MIN_CTAS) k_voxel_centroid(cons
   const uint32_t F = p.n_frames;
   const uint32_t M = p.frame_surv_start[F];
   const uint32_t n_tiles = (M + CE_TILE - 1) / CE_TILE;
-  if (p.dual_width && ((p.info->total_bits <= 32u) != (sizeof(KeyT) == 4))) return;  // the other key width runs
+  if (p.dual_width && ((p.info->width == 4u) != REC)) return;  // the other key width runs
+  if (SEG != (p.info->segmented != 0u)) return;
   // Persistent CTAs; tiles are handed out by arrival (a ticket), not by block index: the dense output position of a tile's
   // voxels comes from a look-back over the tiles before it, and a tile may only wait for tiles that are already running or
   // done.
@@ -483,8 +587,30 @@ __global__ void __launch_bounds__(VX_THREADS, CE_MIN_CTAS) k_voxel_centroid(cons
   // 32-bit keys arrive as 8-byte (key, value) records, 64-bit keys as two arrays
   const void* __restrict__ sorted = odd ? p.keys_b : p.keys_a;
   const uint32_t* __restrict__ vals = odd ? p.vals_b : p.vals_a;
+  // SEG: start of frame f / the last frame that starts at or before position i (empty frames in front of it are skipped)
+  const bool fss_staged = SEG && F <= CE_SEG_SMEM_FRAMES;
+  if (fss_staged) {
+    for (uint32_t i = tid; i <= F; i += VX_THREADS) s_fss[i] = p.frame_surv_start[i];
+    __syncthreads();
+  }
+  auto fss_at = [&](uint32_t f) -> uint32_t { return fss_staged ? s_fss[f] : p.frame_surv_start[f]; };
+  auto frame_between = [&](uint32_t i, uint32_t lo, uint32_t hi) -> uint32_t {
+    while (lo < hi) {
+      const uint32_t mid = (lo + hi + 1u) >> 1;
+      if (fss_at(mid) <= i) lo = mid; else hi = mid - 1u;
+    }
+    return lo;
+  };
+  // the frames of the tile the CTA looked at last (item_flags): nearly every tile lies inside one frame, and then nothing is
+  // searched for its items
+  uint32_t rng_b = 0, rng_e = 0, rng_lo = 0, rng_hi = 0;
+  auto frame_of = [&](uint32_t i) -> uint32_t {
+    if (i >= rng_b && i < rng_e) return rng_lo == rng_hi ? rng_lo : frame_between(i, rng_lo, rng_hi);
+    return frame_between(i, 0u, F - 1u);
+  };
   auto key_at = [&](uint32_t i) -> KeyT {
-    if constexpr (REC) return (KeyT) reinterpret_cast<const uint2*>(sorted)[i].x;
+    if constexpr (SEG) return ((KeyT)frame_of(i) << idx_bits) | (KeyT) reinterpret_cast<const uint2*>(sorted)[i].x;
+    else if constexpr (REC) return (KeyT) reinterpret_cast<const uint2*>(sorted)[i].x;
     else return reinterpret_cast<const KeyT*>(sorted)[i];
   };
   auto val_at = [&](uint32_t i) -> uint32_t {
@@ -531,8 +657,28 @@ __global__ void __launch_bounds__(VX_THREADS, CE_MIN_CTAS) k_voxel_centroid(cons
 #pragma unroll
       for (int j = 0; j < CE_IPT; ++j) {
         const bool in = base + j < M;
-        k[j] = in ? key_at(base + j) : (KeyT)0;
+        if constexpr (SEG) k[j] = in ? (KeyT) reinterpret_cast<const uint2*>(sorted)[base + j].x : (KeyT)0;
+        else k[j] = in ? key_at(base + j) : (KeyT)0;
         v[j] = (in && want_vals) ? val_at(base + j) : 0u;
+      }
+    }
+    if constexpr (SEG) {  // frame bits from the position
+      rng_b = tile_base;
+      rng_e = min(tile_base + (uint32_t)CE_TILE, M);
+      rng_lo = frame_between(rng_b, 0u, F - 1u);       // the same in every thread: broadcast reads
+      rng_hi = frame_between(rng_e - 1u, rng_lo, F - 1u);
+      if (rng_lo == rng_hi) {
+        const KeyT fb = (KeyT)rng_lo << idx_bits;
+#pragma unroll
+        for (int j = 0; j < CE_IPT; ++j)
+          if (base + j < M) k[j] |= fb;
+      } else if (base < M) {  // a frame boundary inside the tile: one search for the first item, then forward
+        uint32_t f = frame_between(base, rng_lo, rng_hi);
+#pragma unroll
+        for (int j = 0; j < CE_IPT; ++j) {
+          while (f < rng_hi && fss_at(f + 1u) <= base + j) ++f;
+          if (base + j < M) k[j] |= (KeyT)f << idx_bits;
+        }
       }
     }
     // keys of the items just before and just after this thread's eight
@@ -861,12 +1007,28 @@ cudaError_t launch_key_hist(const VoxelParams& p, cudaStream_t stream) {
   return cudaGetLastError();
 }
 
+cudaError_t launch_seg_base(const VoxelParams& p, cudaStream_t stream) {
+  if (p.n_frames == 0) return cudaSuccess;
+  k_seg_base<<<dim3(p.n_frames, CM_SEG_PASSES), CM_RADIX, 0, stream>>>(p);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_seg_keys64(const void* records, unsigned long long* keys, uint32_t* vals, const VoxelParams& p,
+                              cudaStream_t stream) {
+  if (p.max_points == 0) return cudaSuccess;
+  const uint32_t blocks = std::min<uint32_t>((p.max_points + VX_THREADS - 1u) / VX_THREADS, 148u * 8u);
+  k_seg_keys64<<<blocks, VX_THREADS, 0, stream>>>(reinterpret_cast<const uint2*>(records), keys, vals, p);
+  return cudaGetLastError();
+}
+
 cudaError_t launch_centroid(const VoxelParams& p, cudaStream_t stream) {
   const uint32_t tiles = (p.max_points + CE_TILE - 1) / CE_TILE;
   if (tiles == 0) return cudaSuccess;
   // persistent: what the device holds at once (tiles are handed out by a ticket)
   const uint32_t grid = std::min<uint32_t>(tiles, 148u * (uint32_t)CE_MIN_CTAS);
-  if (p.key_bytes == 4)
+  if (p.key_bytes == 4 && p.segmented)
+    k_voxel_centroid<unsigned long long, true><<<grid, VX_THREADS, 0, stream>>>(p);
+  else if (p.key_bytes == 4)
     k_voxel_centroid<uint32_t><<<grid, VX_THREADS, 0, stream>>>(p);
   else
     k_voxel_centroid<unsigned long long><<<grid, VX_THREADS, 0, stream>>>(p);

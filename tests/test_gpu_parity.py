@@ -529,7 +529,74 @@ def test_cfg1_batch_of_64_frames_at_size(gpu_ok, oracle):
         cm.run_batch(segs)
         out = cm.fetch_batch_outputs()
     assert out["stats"].frames == F and out["stats"].device_error == 0 and out["stats"].survivors > 1363968
+    # frame-segmented: the 6 frame bits are not sorted -- 32-bit records and 4 passes where (frame, index) took 64 bits and 5
+    assert out["stats"].key_bytes == 4 and out["stats"].sort_passes == 4 and out["stats"].key_bits == out["key_idx_bits"]
     o = _oracle_frames(oracle, per_frame, c["passes"], [c["leaf"]] * 3, c["min_points"])
+    _check_survivors(out, out["frames"], o)
+    assert _check_voxels(out, out["frames"], o) <= 1e-5
+
+
+def _ragged_batch(cm, oracle, sizes, passes, leaf, min_points, extent, same_cloud=False, seed=7000):
+    """A one-sensor device batch whose frames hold sizes[f] points; returns (outputs, oracle frames)."""
+    cm.set_extrinsic(0, synth.extrinsic(0, 1))
+    cm.set_crop(passes)
+    cm.set_voxel(leaf, min_points, True)
+    frames = [[(synth.uniform_cloud(seed if same_cloud else seed + f, n, extent=extent)[:n], 1)] for f, n in enumerate(sizes)]
+    segs, per_frame = _upload_segments(cm, frames, lambda f, s: LAYOUTS["packed16"])
+    cm.run_batch(segs)
+    out = cm.fetch_batch_outputs()
+    return out, _oracle_frames(oracle, per_frame, passes, [leaf] * 3, min_points)
+
+
+@pytest.mark.parametrize("min_points", [1, 2, 3])
+def test_frame_segmented_sort_ragged_frames(gpu_ok, oracle, min_points):
+    """Batches of several frames on an unbounded grid sort the bare voxel index, every frame as a segment of its own
+    (SortInfo.segmented; 32-bit records, no frame bits): frames that are empty, hold one point, exactly one radix tile, one
+    more than a tile, several tiles, and frames whose points the crop removes entirely -- small sort tile (1536 keys)."""
+    sizes = [0, 1, 5, 1536, 1537, 0, 9000, 3072, 2, 4607, 4608, 4609, 0, 0, 700, 12000, 1]
+    z_only = [(2, -1.5, 1.5, 0)]
+    with CloudMerger(max_sensors=1, max_batch_points=sum(sizes), max_batch_frames=len(sizes)) as cm:
+        out, o = _ragged_batch(cm, oracle, sizes, z_only, 0.25, min_points, (30.0, 30.0, 4.0))
+    st = out["stats"]
+    assert st.device_error == 0 and st.frames == len(sizes) and st.key_bytes == 4
+    assert st.key_bits == out["key_idx_bits"], "no frame bits were sorted"
+    _check_survivors(out, out["frames"], o)
+    assert _check_voxels(out, out["frames"], o) <= 1e-5
+
+
+def test_frame_segmented_sort_same_cells_in_adjacent_frames(gpu_ok, oracle):
+    """Every frame holds the SAME cloud: the last voxel of a frame and the first of the next differ only by the frame, and
+    equal indices meet at every frame boundary of the sorted array -- runs must end there. 300 frames (frame starts read from
+    global memory past 256), all points kept (no crop window cuts), min_points 2."""
+    sizes = [2500] * 300
+    z_only = [(2, -100.0, 100.0, 0)]
+    with CloudMerger(max_sensors=1, max_batch_points=sum(sizes), max_batch_frames=len(sizes)) as cm:
+        out, o = _ragged_batch(cm, oracle, sizes, z_only, 0.5, 2, (12.0, 12.0, 3.0), same_cloud=True)
+    st = out["stats"]
+    assert st.device_error == 0 and st.key_bytes == 4 and st.key_bits == out["key_idx_bits"]
+    assert all(fo["n_voxels"] == o[0]["n_voxels"] for fo in o)
+    _check_survivors(out, out["frames"], o)
+    assert _check_voxels(out, out["frames"], o) <= 1e-5
+
+
+def test_frame_segmented_sort_big_tile_and_bounded_plan(gpu_ok, oracle):
+    """(i) the big sort tile (capacity above 1 363 968 keys) with frames of unequal size; (ii) a crop BOX whose grid needs
+    31 index bits: with the frame bits the key would not fit 32 bits, so the host plans a segmented run (32-bit records,
+    4 passes) instead of 64-bit keys."""
+    sizes = [400000, 1, 310000, 0, 520000, 250001]
+    z_only = [(2, -1.5, 1.5, 0)]
+    with CloudMerger(max_sensors=1, max_batch_points=sum(sizes), max_batch_frames=len(sizes)) as cm:
+        out, o = _ragged_batch(cm, oracle, sizes, z_only, 0.1, 2, (150.0, 150.0, 4.0))
+    st = out["stats"]
+    assert st.device_error == 0 and st.key_bytes == 4 and st.key_bits == out["key_idx_bits"] and st.survivors > 400000
+    _check_survivors(out, out["frames"], o)
+    assert _check_voxels(out, out["frames"], o) <= 1e-5
+    sizes = [60000, 80000, 0, 70000, 50000]
+    box = [(2, -1.0, 1.0, 0), (1, -60.0, 60.0, 0), (0, -60.0, 60.0, 0)]       # 0.02 m: 6001 x 6001 x 101 cells: 32 bits
+    with CloudMerger(max_sensors=1, max_batch_points=sum(sizes), max_batch_frames=len(sizes)) as cm:
+        out, o = _ragged_batch(cm, oracle, sizes, box, 0.02, 1, (100.0, 100.0, 3.0))
+    st = out["stats"]
+    assert st.device_error == 0 and st.key_bytes == 4 and st.sort_passes == 4 and st.key_bits == out["key_idx_bits"]
     _check_survivors(out, out["frames"], o)
     assert _check_voxels(out, out["frames"], o) <= 1e-5
 
