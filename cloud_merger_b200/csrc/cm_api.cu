@@ -71,6 +71,7 @@ struct Workspace {
   SegTile* seg_tile = nullptr;           // frame-segmented sort (batches of several frames): [sort tiles + frames]
   uint32_t* seg_hist = nullptr;          //   [frames][CM_SEG_PASSES][256]
   uint32_t* seg_frame_tile0 = nullptr;   //   [frames + 1]
+  uint2* seg_cent_range = nullptr;       //   [centroid tiles]
   bool segmented = false;                // last run: the frame-segmented kernels were enqueued (SortInfo says whether they ran)
   bool fused_keys = false;               // last run: K1 produced the keys
   BoxGrid box{};
@@ -301,7 +302,7 @@ cudaError_t dev_alloc(T** p, size_t count) {
 void ws_free(Workspace& w) {
   if (!w.ready) return;
   cudaFree(w.meta); cudaFreeHost(w.report); cudaFree(w.segs); cudaFree(w.tile_seg); cudaFree(w.surv_xyzi); cudaFree(w.surv_src);
-  cudaFree(w.surv_key); cudaFree(w.first_k1); cudaFree(w.seg_tile); cudaFree(w.seg_hist); cudaFree(w.seg_frame_tile0);
+  cudaFree(w.surv_key); cudaFree(w.first_k1); cudaFree(w.seg_tile); cudaFree(w.seg_hist); cudaFree(w.seg_frame_tile0); cudaFree(w.seg_cent_range);
   cudaFree(w.keys_a); cudaFree(w.keys_b); cudaFree(w.vals_a); cudaFree(w.vals_b);
   cudaFree(w.tile_rec); cudaFree(w.lb_sort); cudaFree(w.cent_status); cudaFree(w.epoch_dev);
   cudaFree(w.dense_xyzi); cudaFree(w.dense_src); cudaFree(w.dense_slot);
@@ -336,6 +337,7 @@ int ws_alloc(cm_handle_t h, Workspace& w, uint32_t points, uint32_t frames, uint
     CM_CUDA(h, dev_alloc(&w.seg_tile, sort_lookback_rows((uint32_t)np) + frames));
     CM_CUDA(h, dev_alloc(&w.seg_hist, (size_t)frames * CM_SEG_PASSES * CM_RADIX));
     CM_CUDA(h, dev_alloc(&w.seg_frame_tile0, (size_t)frames + 1));
+    CM_CUDA(h, dev_alloc(&w.seg_cent_range, np / centroid_tile_items() + 2));
   }
   w.lb_cent_n = np / centroid_tile_items() + 2;
   CM_CUDA(h, dev_alloc(&w.tile_rec, w.lb_k1_n));
@@ -467,6 +469,7 @@ void fill_voxel_params(cm_handle_t h, Workspace& w, VoxelParams& vp, const float
   vp.sort_tile = sort_tile_items(4, max_points);
   vp.dual_width = 0;
   vp.segmented = 0; vp.seg_tile = w.seg_tile; vp.seg_hist = w.seg_hist; vp.seg_frame_tile0 = w.seg_frame_tile0;
+  vp.seg_cent_range = w.seg_cent_range;
   vp.out_xyzi = w.out_xyzi; vp.out_count = w.out_count; vp.out_idx = w.out_idx;
   vp.trace = w.trace_sort;
   const char* tp = getenv("CM_TRACE_PASS");

@@ -103,6 +103,7 @@ struct VoxelParams {
   uint32_t* seg_hist;                // [n_frames][CM_SEG_PASSES][256] digit counts per frame, turned into first positions
                                      // (frame start + exclusive scan) by k_seg_base
   uint32_t* seg_frame_tile0;         // [n_frames + 1] scratch of k_grid_setup
+  uint2* seg_cent_range;             // [centroid tiles] first and last frame with items in the tile (k_grid_setup)
   void* out_xyzi;
   uint32_t* out_count;
   unsigned long long* out_idx;

@@ -359,6 +359,21 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_grid_setup(const VoxelParams p
         p.seg_tile[t0 + t] = st;
       }
     }
+    // ... and which frames every tile of the centroid pass touches (nearly always one: no search per item there)
+    const uint32_t M = s_si.n_keys;
+    auto frame_from = [&](uint32_t i, uint32_t lo) {  // the last frame that starts at or before position i
+      uint32_t hi = F - 1u;
+      while (lo < hi) {
+        const uint32_t mid = (lo + hi + 1u) >> 1;
+        if (p.frame_surv_start[mid] <= i) lo = mid; else hi = mid - 1u;
+      }
+      return lo;
+    };
+    for (uint32_t t = tid; (unsigned long long)t * CE_TILE < M; t += SCAN_THREADS) {
+      const uint32_t b = t * CE_TILE, e = min(b + (uint32_t)CE_TILE, M);
+      const uint32_t lo = frame_from(b, 0u);
+      p.seg_cent_range[t] = make_uint2(lo, frame_from(e - 1u, lo));
+    }
     __syncthreads();
   }
   if (tid == 0) *p.info = s_si;
@@ -665,8 +680,9 @@ __global__ void __launch_bounds__(VX_THREADS, CE_MIN_CTAS) k_voxel_centroid(cons
     if constexpr (SEG) {  // frame bits from the position
       rng_b = tile_base;
       rng_e = min(tile_base + (uint32_t)CE_TILE, M);
-      rng_lo = frame_between(rng_b, 0u, F - 1u);       // the same in every thread: broadcast reads
-      rng_hi = frame_between(rng_e - 1u, rng_lo, F - 1u);
+      const uint2 fr = __ldg(p.seg_cent_range + tile_base / CE_TILE);  // the same in every thread
+      rng_lo = fr.x;
+      rng_hi = fr.y;
       if (rng_lo == rng_hi) {
         const KeyT fb = (KeyT)rng_lo << idx_bits;
 #pragma unroll
