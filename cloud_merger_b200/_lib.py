@@ -56,6 +56,7 @@ class CmGiantInfo(C.Structure):
                 ("points_total_finite", C.c_int64), ("voxels_local", C.c_int64), ("splitter", C.c_uint64 * CM_MAX_ZONES),
                 ("min_p", C.c_float * 3), ("max_p", C.c_float * 3), ("min_b", C.c_int32 * 3), ("div_b", C.c_int32 * 3),
                 ("key_bits", C.c_int32), ("host_syncs", C.c_int32), ("exchange", C.c_int32), ("reserved", C.c_int32),
+                ("stage_ms", C.c_float * 4),
                 ("send_begin", C.c_int64 * (CM_MAX_ZONES + 1))]
 
 

@@ -730,7 +730,8 @@ class GiantCloud:
                 "min_p": np.array(info.min_p, np.float32), "max_p": np.array(info.max_p, np.float32),
                 "min_b": np.array(info.min_b, np.int64), "div_b": np.array(info.div_b, np.int64), "key_bits": int(info.key_bits),
                 "host_syncs": int(info.host_syncs), "send_begin": [int(info.send_begin[r]) for r in range(w + 1)],
-                "exchange": {0: "none", 1: "nccl", 2: "peer"}.get(int(info.exchange), "?")}
+                "exchange": {0: "none", 1: "nccl", 2: "peer"}.get(int(info.exchange), "?"),
+                "stage_ms": [float(x) for x in info.stage_ms]}
 
 
 def host_alloc(nbytes: int) -> Tuple[np.ndarray, int]:

@@ -2573,6 +2573,7 @@ struct cm_giant_s {
   float4* peer_recv[CM_MAX_ZONES] = {};
   uint32_t* p2p_words = nullptr;        // device: [0..world) remote_base, [world] barrier word, [world + 1] my receive capacity
   cudaEvent_t plan_ready = nullptr;     // the host waits for the counts, not for the exchange
+  cudaEvent_t prof[5] = {};             // stage boundaries (cm_set_profiling)
   std::string err;
 };
 
@@ -2715,6 +2716,7 @@ int cm_giant_destroy(cm_giant_t g) {
     if (g->p2p && r != g->rank && g->peer_recv[r]) cudaIpcCloseMemHandle(g->peer_recv[r]);
   cudaFree(g->p2p_words);
   if (g->plan_ready) cudaEventDestroy(g->plan_ready);
+  for (auto& e : g->prof) if (e) cudaEventDestroy(e);
   if (g->comm && g->api) g->api->CommDestroy(g->comm);
   cudaFree(g->plan); cudaFree(g->hist); cudaFree(g->counts); cudaFree(g->recv);
   if (g->plan_pin) cudaFreeHost(g->plan_pin);
@@ -2744,6 +2746,11 @@ int cm_giant_voxelgrid(cm_giant_t g, const float* local_xyzi_dev, int64_t n_loca
   memset(&gi, 0, sizeof(gi));
   gi.points_local = n_local;
   ZoneParams zp;
+  const bool prof = h->profiling;
+  if (prof)
+    for (auto& e : g->prof) if (!e) CM_G_CUDA(g, cudaEventCreate(&e));
+  auto mark = [&](int i) { return prof ? cudaEventRecord(g->prof[i], st) : cudaSuccess; };
+  CM_G_CUDA(g, mark(0));
   // ---- global bounding box -> grid, on the device
   CM_G_CUDA(g, cudaMemsetAsync(w.meta, 0, w.ml.zero_bytes, st));
   CM_G_CUDA(g, launch_minmax(pts, (uint32_t)n_local, ctrl, acc, fss, st));
@@ -2755,6 +2762,7 @@ int cm_giant_voxelgrid(cm_giant_t g, const float* local_xyzi_dev, int64_t n_loca
     CM_G_CUDA(g, launch_giant_hist(pts, (uint32_t)n_local, g->plan, g->bins, g->hist, st));
     if (g->comm) CM_G_NCCL(g, g->api->AllReduce(g->hist, g->hist, g->bins, ncclUint64, ncclSum, g->comm, st));
     CM_G_CUDA(g, launch_giant_splitters(g->plan, g->hist, g->bins, (uint32_t)W, st));
+    CM_G_CUDA(g, mark(1));
     // ---- group the block by destination (source order kept inside a destination): the send buffer of the all-to-all
     CM_G_CUDA(g, launch_giant_mask(pts, (uint32_t)n_local, g->plan, (uint32_t)W, (uint32_t)me, h->zw.mask, st));
     if (g->p2p) {
@@ -2780,6 +2788,7 @@ int cm_giant_voxelgrid(cm_giant_t g, const float* local_xyzi_dev, int64_t n_loca
     }
   }
   CM_G_CUDA(g, cudaMemcpyAsync(g->plan_pin, g->plan, sizeof(GiantPlan), cudaMemcpyDeviceToHost, st));
+  if (W > 1) CM_G_CUDA(g, mark(2));
   if (W > 1 && g->p2p) {
     CM_G_CUDA(g, cudaEventRecord(g->plan_ready, st));
     for (int r = 0; r < W; ++r) zp.zone_ptr[r] = g->peer_recv[r];
@@ -2851,7 +2860,16 @@ int cm_giant_voxelgrid(cm_giant_t g, const float* local_xyzi_dev, int64_t n_loca
   if (info) *info = gi;
   // ---- the ordinary single-GPU VoxelGrid on what arrived, global box folded in, key plan known from the global grid
   const uint32_t* enc_dev = reinterpret_cast<const uint32_t*>(reinterpret_cast<const char*>(g->plan) + offsetof(GiantPlan, enc));
-  return voxelgrid_run(h, vox_in, n_vox, st, enc_dev, (int)P.key_bits);
+  CM_G_CUDA(g, mark(3));
+  rc = voxelgrid_run(h, vox_in, n_vox, st, enc_dev, (int)P.key_bits);
+  if (rc == CM_OK && prof && W > 1) {
+    CM_G_CUDA(g, mark(4));
+    CM_G_CUDA(g, cudaEventSynchronize(g->prof[4]));
+    for (int i = 0; i < 4; ++i)
+      if (cudaEventElapsedTime(&gi.stage_ms[i], g->prof[i], g->prof[i + 1]) != cudaSuccess) { gi.stage_ms[i] = 0.f; cudaGetLastError(); }
+    if (info) *info = gi;
+  }
+  return rc;
 }
 
 int cm_sync(cm_handle_t h) {

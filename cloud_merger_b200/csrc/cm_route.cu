@@ -110,28 +110,57 @@ __global__ void k_giant_plan(GiantPlan* plan, const FrameAcc* __restrict__ acc, 
   *plan = p;
 }
 
-__global__ void __launch_bounds__(RT_HIST_THREADS) k_giant_hist(const float4* __restrict__ pts, uint32_t n,
-                                                                const GiantPlan* __restrict__ plan, uint32_t bins,
-                                                                unsigned long long* __restrict__ hist, int use_smem) {
+// floor(key / width) without the 64-bit division sequence (~100 instructions per point): the quotient is below 2^15 bins, so the
+// double-precision estimate is off by one at most, and one multiply-subtract puts it right. Exactly key / width.
+__device__ __forceinline__ unsigned long long div_small_quotient(unsigned long long key, unsigned long long width, double inv_w) {
+  unsigned long long q = __double2ull_rz(__ull2double_rn(key) * inv_w);
+  const long long r = (long long)(key - q * width);
+  if (r < 0) --q;
+  else if ((unsigned long long)r >= width) ++q;
+  return q;
+}
+
+// Four points per thread in flight; one CTA per SM flushes its shared-memory bins once, starting at a bin of its own so that
+// the CTAs do not queue up on the same counters.
+constexpr int GH_THREADS = 1024;
+constexpr int GH_UNROLL = 4;
+__global__ void __launch_bounds__(GH_THREADS) k_giant_hist(const float4* __restrict__ pts, uint32_t n,
+                                                           const GiantPlan* __restrict__ plan, uint32_t bins,
+                                                           unsigned long long* __restrict__ hist, int use_smem) {
   extern __shared__ uint32_t s_bins[];
   const RouteGrid g = plan->grid;
   const unsigned long long width = plan->width;
+  const double inv_w = 1.0 / __ull2double_rn(width);
+  const bool small_q = plan->cells / width < (1ull << 40);  // always, by the choice of the width; the exact division otherwise
   if (use_smem) {
-    for (uint32_t b = threadIdx.x; b < bins; b += RT_HIST_THREADS) s_bins[b] = 0;
+    for (uint32_t b = threadIdx.x; b < bins; b += GH_THREADS) s_bins[b] = 0;
     __syncthreads();
   }
-  for (uint32_t i = blockIdx.x * RT_HIST_THREADS + threadIdx.x; i < n; i += gridDim.x * RT_HIST_THREADS) {
-    unsigned long long key;
-    if (route_key(g, ldg_stream_f4(pts + i), &key)) {
-      unsigned long long b = key / width;
-      if (b >= bins) b = bins - 1;
-      if (use_smem) atomicAdd(&s_bins[(uint32_t)b], 1u);
-      else atomicAdd(hist + b, 1ull);
+  const uint32_t stride = gridDim.x * GH_THREADS;
+  for (uint32_t i0 = blockIdx.x * GH_THREADS + threadIdx.x; i0 < n; i0 += GH_UNROLL * stride) {
+    float4 v[GH_UNROLL];
+#pragma unroll
+    for (int u = 0; u < GH_UNROLL; ++u) {
+      const uint32_t i = i0 + (uint32_t)u * stride;
+      v[u] = (i < n && i >= i0) ? ldg_stream_f4(pts + i) : make_float4(__int_as_float(0x7fc00000), 0.f, 0.f, 0.f);  // NaN: skipped
+    }
+#pragma unroll
+    for (int u = 0; u < GH_UNROLL; ++u) {
+      unsigned long long key;
+      if (route_key(g, v[u], &key)) {
+        unsigned long long b = small_q ? div_small_quotient(key, width, inv_w) : key / width;
+        if (b >= bins) b = bins - 1;
+        if (use_smem) atomicAdd(&s_bins[(uint32_t)b], 1u);
+        else atomicAdd(hist + b, 1ull);
+      }
     }
   }
   if (use_smem) {
     __syncthreads();
-    for (uint32_t b = threadIdx.x; b < bins; b += RT_HIST_THREADS) {
+    const uint32_t rot = (uint32_t)(((unsigned long long)blockIdx.x * bins) / gridDim.x);
+    for (uint32_t t = threadIdx.x; t < bins; t += GH_THREADS) {
+      uint32_t b = t + rot;
+      if (b >= bins) b -= bins;
       const uint32_t c = s_bins[b];
       if (c) atomicAdd(hist + b, (unsigned long long)c);
     }
@@ -143,34 +172,46 @@ __global__ void __launch_bounds__(RT_HIST_THREADS) k_giant_hist(const float4* __
 constexpr int GS_THREADS = 1024;
 __global__ void __launch_bounds__(GS_THREADS) k_giant_splitters(GiantPlan* plan, const unsigned long long* __restrict__ hist,
                                                                 uint32_t bins, uint32_t n_parts) {
-  __shared__ unsigned long long s_part[GS_THREADS];
+  __shared__ unsigned long long s_warp[GS_THREADS / 32];
+  __shared__ unsigned long long s_target[CM_MAX_ZONES];
   __shared__ unsigned long long s_total;
-  const uint32_t tid = threadIdx.x;
+  const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
   const uint32_t chunk = (bins + GS_THREADS - 1) / GS_THREADS;
   const uint32_t b0 = min(bins, tid * chunk), b1 = min(bins, b0 + chunk);
   unsigned long long sum = 0;
   for (uint32_t b = b0; b < b1; ++b) sum += hist[b];
-  s_part[tid] = sum;
+  // exclusive scan of the 1024 partial sums: shuffles inside a warp, the 32 warp totals by warp 0
+  unsigned long long incl = sum;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const unsigned long long t = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+    if ((int)lane >= o) incl += t;
+  }
+  if (lane == 31) s_warp[warp] = incl;
   __syncthreads();
-  if (tid == 0) {  // 1024 partial sums: a serial exclusive scan is a few microseconds
-    unsigned long long run = 0;
-    for (int i = 0; i < GS_THREADS; ++i) {
-      const unsigned long long t = s_part[i];
-      s_part[i] = run;
-      run += t;
+  if (warp == 0) {
+    const unsigned long long w = s_warp[lane];
+    unsigned long long wi = w;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const unsigned long long t = __shfl_up_sync(0xFFFFFFFFu, wi, o);
+      if ((int)lane >= o) wi += t;
     }
-    s_total = run;
-    plan->total = run;
+    s_warp[lane] = wi - w;
+    if (lane == 31) { s_total = wi; plan->total = wi; }
   }
   __syncthreads();
   const unsigned long long total = s_total, width = plan->width;
+  if (tid >= 1 && tid < n_parts) s_target[tid] = total * tid / n_parts;
+  __syncthreads();
   // every thread walks its own bins; a target falls into exactly one thread's range of the running sum
-  unsigned long long cum = s_part[tid];
+  unsigned long long cum = s_warp[warp] + incl - sum;
   for (uint32_t b = b0; b < b1; ++b) {
     const unsigned long long before = cum;
     cum += hist[b];
+    if (cum == before && b != 0) continue;  // an empty bin (other than the first) is the first to reach no target
     for (uint32_t r = 1; r < n_parts; ++r) {
-      const unsigned long long target = total * r / n_parts;
+      const unsigned long long target = s_target[r];
       // first index i with cum[i] >= target (inclusive running sum), + 1; a target of 0 is met by bin 0
       const bool first = (cum >= target) && (b == 0 ? true : before < target);
       if (first) plan->splitter[r - 1] = (unsigned long long)min(b + 1u, bins) * width;
@@ -187,14 +228,27 @@ __global__ void __launch_bounds__(RT_THREADS) k_giant_mask(const float4* __restr
   if (threadIdx.x < CM_MAX_ZONES) s_split[threadIdx.x] = plan->splitter[threadIdx.x];
   const RouteGrid g = plan->grid;
   __syncthreads();
-  for (uint32_t i = blockIdx.x * RT_THREADS + threadIdx.x; i < n; i += gridDim.x * RT_THREADS) {
-    unsigned long long key;
-    uint32_t dest = invalid_part;  // non-finite points stay where they are (VoxelGrid skips them)
-    if (route_key(g, ldg_stream_f4(pts + i), &key)) {
-      dest = 0;
-      for (uint32_t k = 0; k + 1 < n_parts; ++k) dest += (key >= s_split[k]) ? 1u : 0u;
+  constexpr int U = 4;  // points per thread in flight
+  const uint32_t stride = gridDim.x * RT_THREADS;
+  for (uint32_t i0 = blockIdx.x * RT_THREADS + threadIdx.x; i0 < n; i0 += U * stride) {
+    float4 v[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const uint32_t i = i0 + (uint32_t)u * stride;
+      v[u] = (i < n && i >= i0) ? ldg_stream_f4(pts + i) : make_float4(0.f, 0.f, 0.f, 0.f);
     }
-    mask[i] = (unsigned short)(1u << dest);
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const uint32_t i = i0 + (uint32_t)u * stride;
+      if (!(i < n && i >= i0)) continue;
+      unsigned long long key;
+      uint32_t dest = invalid_part;  // non-finite points stay where they are (VoxelGrid skips them)
+      if (route_key(g, v[u], &key)) {
+        dest = 0;
+        for (uint32_t k = 0; k + 1 < n_parts; ++k) dest += (key >= s_split[k]) ? 1u : 0u;
+      }
+      mask[i] = (unsigned short)(1u << dest);
+    }
   }
 }
 
@@ -224,8 +278,8 @@ cudaError_t launch_giant_hist(const float4* pts, uint32_t n, const GiantPlan* pl
     if (e != cudaSuccess) return e;
     configured = true;
   }
-  const uint32_t blocks = std::min<uint32_t>((n + RT_HIST_THREADS - 1) / RT_HIST_THREADS, 148u * 2u);
-  k_giant_hist<<<blocks, RT_HIST_THREADS, smem, stream>>>(pts, n, plan, bins, hist, use_smem);
+  const uint32_t blocks = std::min<uint32_t>((n + GH_THREADS * GH_UNROLL - 1) / (GH_THREADS * GH_UNROLL), 148u);
+  k_giant_hist<<<blocks, GH_THREADS, smem, stream>>>(pts, n, plan, bins, hist, use_smem);
   return cudaGetLastError();
 }
 

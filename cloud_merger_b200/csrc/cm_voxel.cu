@@ -901,8 +901,12 @@ __global__ void __launch_bounds__(VX_THREADS, CE_MIN_CTAS) k_voxel_centroid(cons
         ++n; ++g;
       }
     }
-    const float nf = (float)n;
-    cen = make_float4(__fdiv_rn(sx, nf), __fdiv_rn(sy, nf), __fdiv_rn(sz, nf), p.downsample_all ? __fdiv_rn(sw, nf) : 0.f);
+    if (n == 1u) {  // x / 1.0f == x: a voxel of one point (most voxels of a fine leaf) needs no division
+      cen = make_float4(sx, sy, sz, p.downsample_all ? sw : 0.f);
+    } else {
+      const float nf = (float)n;
+      cen = make_float4(__fdiv_rn(sx, nf), __fdiv_rn(sy, nf), __fdiv_rn(sz, nf), p.downsample_all ? __fdiv_rn(sw, nf) : 0.f);
+    }
     n_out = n;
     key_out = key;
   };

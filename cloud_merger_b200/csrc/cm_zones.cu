@@ -14,6 +14,8 @@
 // Three launches: k_zone_count (membership mask per point + per-tile counts per zone), k_zone_scan (one CTA per zone:
 // per-tile offsets; the last CTA to finish lays the zones out one after the other), k_zone_scatter (ranks from warp ballots -> points and source indices to their final place).
 // Roofline: HBM. Algorithmic bytes = n * (16 read + 2 mask written + 16 + 2 read again) + sum(zone sizes) * (16 + 4).
+#include <cstdlib>
+
 #include "cm_kernels.h"
 
 namespace cm {
@@ -224,6 +226,82 @@ __global__ void __launch_bounds__(ZN_THREADS) k_zone_scatter(const ZoneParams p)
   }
 }
 
+// The exchange of the giant-cloud mode: zone z is destination rank z and its points are stored into that rank's receive
+// buffer over NVLink (zone_ptr[z], from element zone_remote_base[z] + the tile's offset on). The tile is first grouped by
+// destination in shared memory and then written out linearly, so that a destination receives its ~TILE / world points of the
+// tile as ONE contiguous run of 16-byte stores (2 KB at world = 8) instead of the ~64-byte pieces a warp's ballot ranks
+// produce: NVLink moves large writes at close to its line rate and small ones at a fraction of it.
+__global__ void __launch_bounds__(ZN_THREADS) k_zone_scatter_remote(const ZoneParams p) {
+  __shared__ uint32_t s_wcnt[ZN_WARPS][CM_MAX_ZONES];
+  __shared__ uint32_t s_zoff[CM_MAX_ZONES + 1];  // where zone z starts in the staged tile
+  __shared__ uint32_t s_zdst[CM_MAX_ZONES];      // ... and in its destination buffer
+  __shared__ __align__(16) float4 s_pts[ZN_TILE];
+  __shared__ unsigned char s_zone[ZN_TILE];
+  const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+  if (*p.overflow) return;
+  const uint32_t n = p.n_points;
+  const uint32_t tile = blockIdx.x;
+  const int nz = p.zones.n_zones;
+  const uint32_t base = tile * ZN_TILE + warp * (32 * ZN_IPT) + lane;
+  float4 v[ZN_IPT];
+  uint32_t m[ZN_IPT];
+#pragma unroll
+  for (int i = 0; i < ZN_IPT; ++i) {
+    const uint32_t g = base + 32 * i;
+    m[i] = g < n ? (uint32_t)p.mask[g] : 0u;
+    m[i] &= 0u - m[i];  // one destination per point (the masks of k_giant_mask are one-hot already)
+    v[i] = (g < n && m[i]) ? ldg_stream_f4(p.pts + g) : make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  uint32_t present = 0;
+#pragma unroll
+  for (int i = 0; i < ZN_IPT; ++i) present |= __reduce_or_sync(0xFFFFFFFFu, m[i]);
+  uint32_t cnt_z = 0;
+  for (uint32_t zs = present; zs; zs &= zs - 1u) {
+    const uint32_t z = (uint32_t)__ffs(zs) - 1u;
+    uint32_t c = 0;
+#pragma unroll
+    for (int i = 0; i < ZN_IPT; ++i) c += (uint32_t)__popc(__ballot_sync(0xFFFFFFFFu, (m[i] >> z) & 1u));
+    if (lane == z) cnt_z = c;
+  }
+  if ((int)lane < CM_MAX_ZONES) s_wcnt[warp][lane] = cnt_z;
+  __syncthreads();
+  if (warp == 0) {  // lane z: the tile's points for destination z -> start of the zone in the staged tile
+    uint32_t c = 0;
+    if ((int)lane < nz)
+      for (int w2 = 0; w2 < ZN_WARPS; ++w2) c += s_wcnt[w2][lane];
+    const uint32_t incl = warp_incl_scan_u32(c);
+    if ((int)lane < nz) {
+      s_zoff[lane] = incl - c;
+      s_zdst[lane] = p.zone_remote_base[lane] + p.tile_offset[(size_t)lane * p.n_tiles + tile];
+    }
+    if ((int)lane == nz - 1) s_zoff[nz] = incl;
+  }
+  __syncthreads();
+  const uint32_t lt = lanemask_lt();
+  for (uint32_t zs = present; zs; zs &= zs - 1u) {
+    const uint32_t z = (uint32_t)__ffs(zs) - 1u;
+    uint32_t pos = s_zoff[z];
+    for (uint32_t w2 = 0; w2 < warp; ++w2) pos += s_wcnt[w2][z];
+#pragma unroll
+    for (int i = 0; i < ZN_IPT; ++i) {
+      const bool in = (m[i] >> z) & 1u;
+      const uint32_t b = __ballot_sync(0xFFFFFFFFu, in);
+      if (in) {
+        const uint32_t q = pos + (uint32_t)__popc(b & lt);
+        s_pts[q] = v[i];
+        s_zone[q] = (unsigned char)z;
+      }
+      pos += (uint32_t)__popc(b);
+    }
+  }
+  __syncthreads();
+  const uint32_t total = s_zoff[nz];
+  for (uint32_t q = tid; q < total; q += ZN_THREADS) {
+    const uint32_t z = s_zone[q];
+    p.zone_ptr[z][s_zdst[z] + (q - s_zoff[z])] = s_pts[q];
+  }
+}
+
 }  // namespace
 
 uint32_t zone_tile_points() { return ZN_TILE; }
@@ -238,7 +316,9 @@ cudaError_t launch_zone_scatter(const ZoneParams& p, cudaStream_t stream) {
 
 cudaError_t launch_zone_scatter_remote(const ZoneParams& p, cudaStream_t stream) {
   if (!p.n_tiles) return cudaSuccess;
-  k_zone_scatter<true><<<p.n_tiles, ZN_THREADS, 0, stream>>>(p);
+  static const bool direct = getenv("CM_GIANT_DIRECT_STORES") != nullptr;  // A/B: the unstaged ballot-rank stores
+  if (direct) k_zone_scatter<true><<<p.n_tiles, ZN_THREADS, 0, stream>>>(p);
+  else k_zone_scatter_remote<<<p.n_tiles, ZN_THREADS, 0, stream>>>(p);
   return cudaGetLastError();
 }
 

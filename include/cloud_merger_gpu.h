@@ -489,6 +489,9 @@ typedef struct {
   int32_t key_bits, host_syncs;
   int32_t exchange;                /* CM_GIANT_EXCHANGE_*: how the points reached their owners in this call */
   int32_t reserved;
+  float stage_ms[4];               /* with cm_set_profiling(h, 1) (the call then blocks until its last kernel is done): device
+                                    * time of [0] bounds + histogram + splitters, [1] grouping (mask, count, scan, offsets),
+                                    * [2] the exchange, [3] the local VoxelGrid; else zeros */
   int64_t send_begin[CM_MAX_ZONES + 1]; /* where the points for rank r start in the grouped array */
 } cm_giant_info_t;
 CM_API int cm_giant_unique_id(void* id_bytes);

@@ -29,6 +29,7 @@ def main():
     ap.add_argument("--min-points", type=int, default=1)
     ap.add_argument("--iters", type=int, default=3)
     ap.add_argument("--check", action="store_true")
+    ap.add_argument("--stages", action="store_true", help="one more (profiled, blocking) call after the timed ones: device time per stage")
     a = ap.parse_args()
     rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
     local_rank = int(os.environ.get("LOCAL_RANK", 0))
@@ -67,6 +68,14 @@ def main():
             dist.barrier()
         if it:
             times.append(time.perf_counter() - t0)
+    stage_ms = None
+    if a.stages:
+        cm.set_profiling(True)
+        if world > 1:
+            dist.barrier()
+        stage_ms = giant.voxelgrid(local.data_ptr(), int(local.shape[0]), stream=stream)["stage_ms"]
+        st = cm.stats()
+        cm.set_profiling(False)
     out.update(n_voxels=int(st.voxels_out), gpu_ms=float(st.gpu_ms), key_bits=int(st.key_bits))
     if a.check:
         o = cm.device_out()
@@ -106,6 +115,7 @@ def main():
                           "points_per_rank_after": [int(v[0]) for v in allv], "key_bits": out.get("key_bits"),
                           "local_voxelgrid_ms": out.get("gpu_ms"), "host_syncs_before_report": out.get("host_syncs"),
                           "exchange": out.get("exchange"),
+                          "stage_ms_rank0": dict(zip(["plan", "group", "exchange", "voxelgrid"], stage_ms)) if stage_ms else None,
                           "api": "cm_giant_voxelgrid (C++ + NCCL behind the C ABI)", "check": check}) + "\n").encode())
     giant.close()
     cm.close()
