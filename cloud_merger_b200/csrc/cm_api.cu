@@ -1601,11 +1601,13 @@ ZoneParams zone_params(cm_handle_t h, const float4* pts, int64_t n_points, bool 
   zp.out_xyzi = z.out_xyzi; zp.out_src = z.out_src;
   for (int i = 0; i < CM_MAX_ZONES; ++i) zp.zone_ptr[i] = nullptr;
   zp.zone_remote_base = nullptr;
+  zp.giant_plan = nullptr; zp.giant_invalid_part = 0;
   return zp;
 }
 
+// giant != null: the zones are the given_zones ranks of the giant-cloud mode and the masks come from the device-resident plan
 int zone_run(cm_handle_t h, const float4* pts, int64_t n_points, cudaStream_t st, bool mask_given = false,
-             int given_zones = 1) {
+             int given_zones = 1, const GiantPlan* giant = nullptr, uint32_t giant_invalid_part = 0) {
   cm_handle_s::ZoneWs& z = h->zw;
   if (!mask_given && h->zones.n_zones <= 0) return fail(h, CM_E_INVALID, "no zones configured (cm_set_zones)");
   if (n_points < 0 || n_points > 0xFFFFFFF0ll) return fail(h, CM_E_INVALID, "bad n_points");
@@ -1614,6 +1616,7 @@ int zone_run(cm_handle_t h, const float4* pts, int64_t n_points, cudaStream_t st
   int rc = zone_ws_ensure(h, (size_t)n_points);
   if (rc != CM_OK) return rc;
   ZoneParams zp = zone_params(h, pts, n_points, mask_given, given_zones);
+  if (giant) { zp.mask_given = 0; zp.giant_plan = giant; zp.giant_invalid_part = giant_invalid_part; }
   CM_CUDA(h, cudaMemsetAsync(z.overflow, 0, sizeof(uint32_t), st));
   CM_CUDA(h, launch_zone_split(zp, st));
   CM_CUDA(h, cudaMemcpyAsync(z.report, z.zone_begin, sizeof(uint32_t) * (CM_MAX_ZONES + 1), cudaMemcpyDeviceToHost, st));
@@ -2764,18 +2767,19 @@ int cm_giant_voxelgrid(cm_giant_t g, const float* local_xyzi_dev, int64_t n_loca
     CM_G_CUDA(g, launch_giant_splitters(g->plan, g->hist, g->bins, (uint32_t)W, st));
     CM_G_CUDA(g, mark(1));
     // ---- group the block by destination (source order kept inside a destination): the send buffer of the all-to-all
-    CM_G_CUDA(g, launch_giant_mask(pts, (uint32_t)n_local, g->plan, (uint32_t)W, (uint32_t)me, h->zw.mask, st));
+    // (the destination masks are derived inside the count sweep from the device-resident plan)
     if (g->p2p) {
       // count + scan only; the scatter below IS the all-to-all (stores into the owners' receive buffers over NVLink)
       if (in_zone_outputs(h, pts, n_local)) return gfail(g, CM_E_INVALID, "the input cloud lies in this handle's own zone outputs");
       zp = zone_params(h, pts, n_local, true, W);
+      zp.mask_given = 0; zp.giant_plan = g->plan; zp.giant_invalid_part = (uint32_t)me;
       zp.out_capacity = 0xFFFFFFF0u;  // nothing lands in the local outputs; the receivers' capacities are checked on the device
       CM_G_CUDA(g, cudaMemsetAsync(h->zw.overflow, 0, sizeof(uint32_t), st));
       CM_G_CUDA(g, launch_zone_count_scan(zp, st));
       CM_G_CUDA(g, cudaMemcpyAsync(h->zw.zone_begin + CM_MAX_ZONES + 1, g->p2p_words + W + 1, sizeof(uint32_t), cudaMemcpyDeviceToDevice, st));
       h->zw.ran = false;  // no grouped array on this handle after this call
     } else {
-      rc = zone_run(h, pts, n_local, st, true, W);
+      rc = zone_run(h, pts, n_local, st, true, W, g->plan, (uint32_t)me);
       if (rc != CM_OK) return rc;
     }
     // every rank's per-destination offsets (NCCL takes the counts of a send / recv as host arguments)

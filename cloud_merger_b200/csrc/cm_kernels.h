@@ -136,6 +136,7 @@ cudaError_t launch_export_voxels(const VoxelParams& p, void* host_xyzi, uint32_t
                                  uint32_t cap, cudaStream_t stream);
 
 // ---- zone slicing: multi-output PassThrough compaction (cm_zones.cu) -------------------------------------------------------
+struct GiantPlan;
 struct ZoneParams {
   const float4* pts;         // n packed xyzi points
   uint32_t n_points;
@@ -156,6 +157,10 @@ struct ZoneParams {
   // r's receive buffer (an IPC-mapped pointer; NVLink stores), from element zone_remote_base[r] on; no source indices
   float4* zone_ptr[CM_MAX_ZONES];        // all null: the ordinary local outputs
   const uint32_t* zone_remote_base;      // [n_zones], device
+  // giant-cloud mode: the "zone" of a point is the rank that owns its voxel index (device-resident plan: global grid and
+  // splitters); the count kernel derives the masks from it in the same sweep (mask_given must be 0)
+  const GiantPlan* giant_plan;           // null: zones / given masks
+  uint32_t giant_invalid_part;           // where non-finite points go (the local rank)
 };
 // ---- radius outlier removal on the sorted cell keys (cm_outlier.cu) -------------------------------------------------------
 struct RorParams {
@@ -206,6 +211,17 @@ struct RouteGrid {  // PCL's grid on the GLOBAL bounding box
   long long min_b[3];
   long long div0, div01;  // div_x, div_x * div_y
 };
+#ifdef __CUDACC__
+// PCL's voxel index of a point on the global grid (VoxelGrid::applyFilter, float32 multiply); false: a non-finite point
+__device__ __forceinline__ bool route_key(const RouteGrid& g, const float4& v, unsigned long long* key) {
+  if (!(finite_f32(v.x) && finite_f32(v.y) && finite_f32(v.z))) return false;
+  const long long i0 = (long long)__float2int_rd(__fmul_rn(v.x, g.inv[0])) - g.min_b[0];
+  const long long i1 = (long long)__float2int_rd(__fmul_rn(v.y, g.inv[1])) - g.min_b[1];
+  const long long i2 = (long long)__float2int_rd(__fmul_rn(v.z, g.inv[2])) - g.min_b[2];
+  *key = (unsigned long long)(i0 + i1 * g.div0 + i2 * g.div01);
+  return true;
+}
+#endif
 struct RouteSplit {
   int32_t n_parts;                           // <= CM_MAX_ZONES
   uint32_t invalid_part;                     // where non-finite points go (the local rank)
@@ -233,8 +249,6 @@ cudaError_t launch_giant_hist(const float4* pts, uint32_t n, const GiantPlan* pl
                               cudaStream_t stream);
 cudaError_t launch_giant_splitters(GiantPlan* plan, const unsigned long long* hist_reduced, uint32_t bins, uint32_t n_parts,
                                    cudaStream_t stream);
-cudaError_t launch_giant_mask(const float4* pts, uint32_t n, const GiantPlan* plan, uint32_t n_parts, uint32_t invalid_part,
-                              unsigned short* mask, cudaStream_t stream);
 // folds device-resident bounds (GiantPlan::enc) into frame 0's accumulator: every rank then builds the same grid
 cudaError_t launch_seed_bounds_enc(FrameAcc* acc, const uint32_t* enc6, cudaStream_t stream);
 // bounding box of n packed points into acc (frame 0), as launch_minmax does for the VoxelGrid-only entry

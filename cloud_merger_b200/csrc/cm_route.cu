@@ -18,15 +18,6 @@ namespace {
 
 constexpr int RT_THREADS = 256;
 
-__device__ __forceinline__ bool route_key(const RouteGrid& g, const float4& v, unsigned long long* key) {
-  if (!(finite_f32(v.x) && finite_f32(v.y) && finite_f32(v.z))) return false;
-  const long long i0 = (long long)__float2int_rd(__fmul_rn(v.x, g.inv[0])) - g.min_b[0];
-  const long long i1 = (long long)__float2int_rd(__fmul_rn(v.y, g.inv[1])) - g.min_b[1];
-  const long long i2 = (long long)__float2int_rd(__fmul_rn(v.z, g.inv[2])) - g.min_b[2];
-  *key = (unsigned long long)(i0 + i1 * g.div0 + i2 * g.div01);
-  return true;
-}
-
 // Up to RT_SMEM_BINS bins the histogram is privatised per CTA in shared memory (hardware-aggregated increments) and
 // flushed once: a map cloud puts most of its points on a few planes, and 50 M global atomics on those hot bins took
 // 4.7 ms; above that size the counters are updated in global memory directly.
@@ -178,8 +169,25 @@ __global__ void __launch_bounds__(GS_THREADS) k_giant_splitters(GiantPlan* plan,
   const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
   const uint32_t chunk = (bins + GS_THREADS - 1) / GS_THREADS;
   const uint32_t b0 = min(bins, tid * chunk), b1 = min(bins, b0 + chunk);
+  // the thread's bins, fetched once with 16-byte loads when the chunk is the usual 16 bins (16 Ki bins / 1024 threads)
+  constexpr uint32_t GS_CHUNK = 16;
+  unsigned long long hv[GS_CHUNK];
+  const bool in_regs = chunk == GS_CHUNK && b1 - b0 == GS_CHUNK;
+  if (in_regs) {
+    const ulonglong2* src = reinterpret_cast<const ulonglong2*>(hist + b0);
+#pragma unroll
+    for (uint32_t k = 0; k < GS_CHUNK; k += 2) {
+      const ulonglong2 t = src[k / 2];
+      hv[k] = t.x; hv[k + 1] = t.y;
+    }
+  }
   unsigned long long sum = 0;
-  for (uint32_t b = b0; b < b1; ++b) sum += hist[b];
+  if (in_regs) {
+#pragma unroll
+    for (uint32_t k = 0; k < GS_CHUNK; ++k) sum += hv[k];
+  } else {
+    for (uint32_t b = b0; b < b1; ++b) sum += hist[b];
+  }
   // exclusive scan of the 1024 partial sums: shuffles inside a warp, the 32 warp totals by warp 0
   unsigned long long incl = sum;
 #pragma unroll
@@ -206,50 +214,25 @@ __global__ void __launch_bounds__(GS_THREADS) k_giant_splitters(GiantPlan* plan,
   __syncthreads();
   // every thread walks its own bins; a target falls into exactly one thread's range of the running sum
   unsigned long long cum = s_warp[warp] + incl - sum;
-  for (uint32_t b = b0; b < b1; ++b) {
+  auto step = [&](uint32_t b, unsigned long long count) {
     const unsigned long long before = cum;
-    cum += hist[b];
-    if (cum == before && b != 0) continue;  // an empty bin (other than the first) is the first to reach no target
+    cum += count;
+    if (cum == before && b != 0) return;  // an empty bin (other than the first) is the first to reach no target
     for (uint32_t r = 1; r < n_parts; ++r) {
       const unsigned long long target = s_target[r];
       // first index i with cum[i] >= target (inclusive running sum), + 1; a target of 0 is met by bin 0
       const bool first = (cum >= target) && (b == 0 ? true : before < target);
       if (first) plan->splitter[r - 1] = (unsigned long long)min(b + 1u, bins) * width;
     }
+  };
+  if (in_regs) {
+#pragma unroll
+    for (uint32_t k = 0; k < GS_CHUNK; ++k) step(b0 + k, hv[k]);
+  } else {
+    for (uint32_t b = b0; b < b1; ++b) step(b, hist[b]);
   }
   if (tid == 0 && total == 0)  // an empty cloud: every splitter at the first boundary (nothing moves)
     for (uint32_t r = 1; r < n_parts; ++r) plan->splitter[r - 1] = width;
-}
-
-__global__ void __launch_bounds__(RT_THREADS) k_giant_mask(const float4* __restrict__ pts, uint32_t n,
-                                                           const GiantPlan* __restrict__ plan, uint32_t n_parts,
-                                                           uint32_t invalid_part, unsigned short* __restrict__ mask) {
-  __shared__ unsigned long long s_split[CM_MAX_ZONES];
-  if (threadIdx.x < CM_MAX_ZONES) s_split[threadIdx.x] = plan->splitter[threadIdx.x];
-  const RouteGrid g = plan->grid;
-  __syncthreads();
-  constexpr int U = 4;  // points per thread in flight
-  const uint32_t stride = gridDim.x * RT_THREADS;
-  for (uint32_t i0 = blockIdx.x * RT_THREADS + threadIdx.x; i0 < n; i0 += U * stride) {
-    float4 v[U];
-#pragma unroll
-    for (int u = 0; u < U; ++u) {
-      const uint32_t i = i0 + (uint32_t)u * stride;
-      v[u] = (i < n && i >= i0) ? ldg_stream_f4(pts + i) : make_float4(0.f, 0.f, 0.f, 0.f);
-    }
-#pragma unroll
-    for (int u = 0; u < U; ++u) {
-      const uint32_t i = i0 + (uint32_t)u * stride;
-      if (!(i < n && i >= i0)) continue;
-      unsigned long long key;
-      uint32_t dest = invalid_part;  // non-finite points stay where they are (VoxelGrid skips them)
-      if (route_key(g, v[u], &key)) {
-        dest = 0;
-        for (uint32_t k = 0; k + 1 < n_parts; ++k) dest += (key >= s_split[k]) ? 1u : 0u;
-      }
-      mask[i] = (unsigned short)(1u << dest);
-    }
-  }
 }
 
 __global__ void k_seed_bounds_enc(FrameAcc* acc, const uint32_t* __restrict__ enc6) {
@@ -286,14 +269,6 @@ cudaError_t launch_giant_hist(const float4* pts, uint32_t n, const GiantPlan* pl
 cudaError_t launch_giant_splitters(GiantPlan* plan, const unsigned long long* hist_reduced, uint32_t bins, uint32_t n_parts,
                                    cudaStream_t stream) {
   k_giant_splitters<<<1, GS_THREADS, 0, stream>>>(plan, hist_reduced, bins, n_parts);
-  return cudaGetLastError();
-}
-
-cudaError_t launch_giant_mask(const float4* pts, uint32_t n, const GiantPlan* plan, uint32_t n_parts, uint32_t invalid_part,
-                              unsigned short* mask, cudaStream_t stream) {
-  if (n == 0) return cudaSuccess;
-  const uint32_t blocks = std::min<uint32_t>((n + RT_THREADS - 1) / RT_THREADS, 148u * 8u);
-  k_giant_mask<<<blocks, RT_THREADS, 0, stream>>>(pts, n, plan, n_parts, invalid_part, mask);
   return cudaGetLastError();
 }
 

@@ -63,13 +63,21 @@ __device__ __forceinline__ uint32_t zone_mask_box(const float4* s_lo, const floa
   return m;
 }
 
-template <bool BOX, bool GIVEN>
+// GIANT: the zones are the ranks of the giant-cloud mode; the mask of a point (one bit: the rank owning its voxel index, from
+// the device-resident plan) is derived here, in the sweep that counts -- no separate mask kernel and no second read.
+template <bool BOX, bool GIVEN, bool GIANT = false>
 __global__ void __launch_bounds__(ZN_THREADS) k_zone_count(const ZoneParams p) {
   __shared__ uint32_t s_cnt[CM_MAX_ZONES];
   __shared__ __align__(16) float4 s_lo[CM_MAX_ZONES], s_hi[CM_MAX_ZONES];
+  __shared__ unsigned long long s_split[CM_MAX_ZONES];
   const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
   const uint32_t n = p.n_points;
   const uint32_t tile = blockIdx.x;
+  RouteGrid rg;
+  if (GIANT) {
+    rg = p.giant_plan->grid;
+    if (tid < CM_MAX_ZONES) s_split[tid] = p.giant_plan->splitter[tid];
+  }
   if (tid < CM_MAX_ZONES) {
     s_cnt[tid] = 0;
     if (BOX && (int)tid < p.zones.n_zones) {
@@ -96,6 +104,15 @@ __global__ void __launch_bounds__(ZN_THREADS) k_zone_count(const ZoneParams p) {
     if (g < n) {
       if (GIVEN) {
         m = p.mask[g];
+      } else if (GIANT) {
+        unsigned long long key;
+        uint32_t dest = p.giant_invalid_part;  // non-finite points stay where they are (VoxelGrid skips them)
+        if (route_key(rg, v[i], &key)) {
+          dest = 0;
+          for (int k = 0; k + 1 < p.zones.n_zones; ++k) dest += (key >= s_split[k]) ? 1u : 0u;
+        }
+        m = 1u << dest;
+        p.mask[g] = (unsigned short)m;
       } else {
         m = BOX ? zone_mask_box(s_lo, s_hi, p.zones.n_zones, no_i_mask, v[i]) : zone_mask_chain(p.zones, v[i]);
         p.mask[g] = (unsigned short)m;
@@ -249,7 +266,7 @@ __global__ void __launch_bounds__(ZN_THREADS) k_zone_scatter_remote(const ZonePa
   for (int i = 0; i < ZN_IPT; ++i) {
     const uint32_t g = base + 32 * i;
     m[i] = g < n ? (uint32_t)p.mask[g] : 0u;
-    m[i] &= 0u - m[i];  // one destination per point (the masks of k_giant_mask are one-hot already)
+    m[i] &= 0u - m[i];  // one destination per point (the masks of the giant-cloud count sweep are one-hot already)
     v[i] = (g < n && m[i]) ? ldg_stream_f4(p.pts + g) : make_float4(0.f, 0.f, 0.f, 0.f);
   }
   uint32_t present = 0;
@@ -346,7 +363,8 @@ cudaError_t launch_giant_offsets(const uint32_t* counts_all, uint32_t stride, ui
 
 cudaError_t launch_zone_count_scan(const ZoneParams& p, cudaStream_t stream) {
   if (p.n_tiles) {
-    if (p.mask_given) k_zone_count<false, true><<<p.n_tiles, ZN_THREADS, 0, stream>>>(p);
+    if (p.giant_plan) k_zone_count<false, false, true><<<p.n_tiles, ZN_THREADS, 0, stream>>>(p);
+    else if (p.mask_given) k_zone_count<false, true><<<p.n_tiles, ZN_THREADS, 0, stream>>>(p);
     else if (p.zones.all_box) k_zone_count<true, false><<<p.n_tiles, ZN_THREADS, 0, stream>>>(p);
     else k_zone_count<false, false><<<p.n_tiles, ZN_THREADS, 0, stream>>>(p);
     cudaError_t e = cudaGetLastError();
@@ -357,15 +375,7 @@ cudaError_t launch_zone_count_scan(const ZoneParams& p, cudaStream_t stream) {
 }
 
 cudaError_t launch_zone_split(const ZoneParams& p, cudaStream_t stream) {
-  if (p.n_tiles) {
-    if (p.mask_given) k_zone_count<false, true><<<p.n_tiles, ZN_THREADS, 0, stream>>>(p);
-    else if (p.zones.all_box) k_zone_count<true, false><<<p.n_tiles, ZN_THREADS, 0, stream>>>(p);
-    else k_zone_count<false, false><<<p.n_tiles, ZN_THREADS, 0, stream>>>(p);
-    cudaError_t e = cudaGetLastError();
-    if (e != cudaSuccess) return e;
-  }
-  k_zone_scan<<<p.zones.n_zones, 1024, 0, stream>>>(p);
-  cudaError_t e = cudaGetLastError();
+  cudaError_t e = launch_zone_count_scan(p, stream);
   if (e != cudaSuccess) return e;
   if (p.n_tiles) {
     k_zone_scatter<false><<<p.n_tiles, ZN_THREADS, 0, stream>>>(p);
