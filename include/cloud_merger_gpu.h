@@ -459,10 +459,13 @@ CM_API int cm_dev_route_by_key(cm_handle_t h, const float* xyzi_dev, int64_t n_p
  * One process per GPU; every rank holds a block of the cloud in device memory. cm_giant_voxelgrid does, on `stream`:
  *   bounding box of the block -> ncclAllReduce (max of order-preserving encodings) -> PCL's grid on the global box, ON THE DEVICE
  *   -> histogram of the voxel index -> ncclAllReduce (sum) -> balancing splitters, ON THE DEVICE -> group the block by
- *   destination rank (source order kept) -> ncclAllGather of the per-destination counts -> ONE all-to-all (grouped
- *   ncclSend / ncclRecv straight out of the grouped array, 16 bytes per point) -> the single-GPU VoxelGrid on what arrived,
- *   with the global box folded in so that every rank builds the same grid.
- * The host is needed twice: for the counts of the all-to-all (NCCL takes them as host arguments) and for the final report.
+ *   destination rank (source order kept) -> ncclAllGather of the per-destination counts -> ONE exchange, 16 bytes per
+ *   point (see CM_GIANT_EXCHANGE_* below: stores into the owners' buffers over NVLink from inside the grouping kernel, or a
+ *   grouped ncclSend / ncclRecv) -> the single-GPU VoxelGrid on what arrived, with the global box folded in so that every
+ *   rank builds the same grid.
+ * The host is needed twice: for the counts (they size the VoxelGrid launches; NCCL also takes them as host arguments) and
+ * for the final report. Calls on one object must be stream-ordered on every rank (the same stream, or streams the caller
+ * orders): a peer may store into this rank's receive buffer as soon as this rank has entered the next call.
  * A voxel never straddles ranks, and the rank outputs (cm_get_device_out on each rank: voxel_xyzi / voxel_count / voxel_idx)
  * concatenated in rank order are PCL's order. Leaf and min_points: cm_set_voxel on the handle. The handle's
  * max_batch_points bounds what a rank may RECEIVE (balanced splitters give ~n / world; size it with headroom).
