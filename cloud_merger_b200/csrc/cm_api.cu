@@ -50,7 +50,7 @@ struct MetaLayout {
   }
 };
 
-enum StageEv { EV_START = 0, EV_K1, EV_GRID, EV_KEY, EV_SORT, EV_CENT, EV_COUNT };
+enum StageEv { EV_START = 0, EV_K1, EV_GRID, EV_KEY, EV_SORT, EV_CENT, EV_SORT0 /* after radix pass 0 */, EV_COUNT };
 
 struct Workspace {
   bool ready = false;
@@ -72,6 +72,7 @@ struct Workspace {
   uint32_t* seg_hist = nullptr;          //   [frames][CM_SEG_PASSES][256]
   uint32_t* seg_frame_tile0 = nullptr;   //   [frames + 1]
   uint2* seg_cent_range = nullptr;       //   [centroid tiles]
+  bool timed_pass0 = false;              // last run: an event was recorded after radix pass 0 (profiling, host-planned key width)
   bool segmented = false;                // last run: the frame-segmented kernels were enqueued (SortInfo says whether they ran)
   bool fused_keys = false;               // last run: K1 produced the keys
   BoxGrid box{};
@@ -575,9 +576,14 @@ int run_voxel(cm_handle_t h, Workspace& w, VoxelParams& vp, cudaStream_t st, boo
     ++w.launches;
   }
   if (h->profiling) CM_CUDA(h, cudaEventRecord(w.ev[EV_KEY], st));
+  w.timed_pass0 = false;
   for (uint32_t ps = 0; ps < vp.max_passes; ++ps) {
     CM_CUDA(h, launch_sort_pass(vp, (int)ps, st));
     ++w.launches;
+    if (ps == 0 && h->profiling) {  // pass 0 of a fused-key run does the key kernel's histogram work too: timed on its own
+      CM_CUDA(h, cudaEventRecord(w.ev[EV_SORT0], st));
+      w.timed_pass0 = true;
+    }
   }
   if (h->profiling) CM_CUDA(h, cudaEventRecord(w.ev[EV_SORT], st));
   if (!with_centroid) {  // the caller only wants the points sorted by cell (radius outlier removal)
@@ -820,6 +826,7 @@ int fetch_report(cm_handle_t h, Workspace& w, cudaEvent_t already_copied = nullp
       if (cudaEventElapsedTime(&t, w.ev[EV_K1], w.ev[EV_GRID]) == cudaSuccess) h->stage_ms[EV_GRID] = t;
       if (cudaEventElapsedTime(&t, w.ev[EV_GRID], w.ev[EV_KEY]) == cudaSuccess) h->stage_ms[EV_KEY] = t;
       if (cudaEventElapsedTime(&t, w.ev[EV_KEY], w.ev[EV_SORT]) == cudaSuccess) h->stage_ms[EV_SORT] = t;
+      if (w.timed_pass0 && cudaEventElapsedTime(&t, w.ev[EV_KEY], w.ev[EV_SORT0]) == cudaSuccess) h->stage_ms[EV_SORT0] = t;
       if (cudaEventElapsedTime(&t, w.ev[EV_SORT], w.ev[EV_CENT]) == cudaSuccess) h->stage_ms[EV_CENT] = t;
     }
   }
@@ -2976,6 +2983,7 @@ int cm_stage_ms(cm_handle_t h, const char* stage, float* ms) {
   else if (!strcmp(stage, "grid")) which = EV_GRID;
   else if (!strcmp(stage, "key_hist")) which = EV_KEY;
   else if (!strcmp(stage, "sort")) which = EV_SORT;
+  else if (!strcmp(stage, "sort_pass0")) which = EV_SORT0;
   else if (!strcmp(stage, "centroid")) which = EV_CENT;
   if (which < 0) return fail(h, CM_E_INVALID, "unknown stage '%s'", stage);
   *ms = h->stage_ms[which];

@@ -511,7 +511,8 @@ CM_API int cm_get_frame_info(cm_handle_t h, cm_frame_info_t* out, int capacity, 
 /* Number of kernel launches the last run enqueued (the caller's "gpu_launches" evidence). */
 CM_API int64_t cm_launch_count(cm_handle_t h);
 /* Device time (ms) of one named stage of the last run, measured with CUDA events on the run's stream:
- * "transform_crop", "grid", "key_hist", "sort", "centroid", "total". Needs cm_set_profiling(h, 1). */
+ * "transform_crop", "grid", "key_hist", "sort", "centroid", "total", and "sort_pass0" (the first radix pass alone; -1 when
+ * the key width was decided on the device). Needs cm_set_profiling(h, 1). */
 CM_API int cm_set_profiling(cm_handle_t h, int on);
 CM_API int cm_stage_ms(cm_handle_t h, const char* stage, float* ms);
 
