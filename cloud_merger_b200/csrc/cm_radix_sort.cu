@@ -10,6 +10,10 @@
 // digit-contiguous. The number of passes is decided on the device (SortInfo.num_passes, from the significant key bits); a
 // pass beyond it returns immediately, and every kernel derives the ping-pong buffer it reads from the pass number.
 //
+// Batches of several frames can be sorted frame by frame inside the same launches (SEG instantiations: frame-aligned tiles,
+// per-frame first positions, scanners that restart at frame starts) -- the frame bits of the key then need no pass at all;
+// see scanner_cta and DESIGN.md "Frame-segmented sort".
+//
 // Record layout in HBM: 32-bit keys travel as 8-byte (key, value) records in keys_a / keys_b (one 8-byte load and one
 // 8-byte store per item and pass, digit runs of 128 bytes on average); 64-bit keys travel as separate key and value
 // arrays (keys_*, vals_*).

@@ -3,7 +3,9 @@
 //
 // Replaces pcl::VoxelGrid<pcl::PointXYZI>::applyFilter as configured by the reference's voxelgrid()
 // (pc_preprocessing_main.cpp:168-177, CloudFusionNode.h:276-289, PreprocessingNode.h:236-249):
-//   first pass  (idx per point)             -> k_voxel_key_hist   (key = (frame << idx_bits) | idx, idx = i + j*div_x + k*div_x*div_y)
+//   first pass  (idx per point)             -> k_voxel_key_hist   (key = (frame << idx_bits) | idx, idx = i + j*div_x + k*div_x*div_y;
+//                                              frame-segmented runs: the bare idx, the frame is the position's -- k_grid_setup
+//                                              plans that, k_seg_base prepares the per-frame first positions)
 //   second pass (std::sort)                 -> cm_radix_sort.cu   (onesweep LSD radix sort of key / point-index pairs)
 //   third+fourth pass (runs, CentroidPoint) -> k_voxel_centroid
 // The voxel index arithmetic repeats PCL's float32 formulas exactly (floorf(x * inv_leaf) with a separately rounded
