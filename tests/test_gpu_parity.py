@@ -579,6 +579,20 @@ def test_frame_segmented_sort_same_cells_in_adjacent_frames(gpu_ok, oracle):
     assert _check_voxels(out, out["frames"], o) <= 1e-5
 
 
+def test_frame_segmented_sort_more_frames_than_threads(gpu_ok, oracle):
+    """1500 small frames of 0..600 points: more frames than k_grid_setup has threads (its frame loops run twice), more than
+    the centroid pass stages in shared memory, most radix tiles partial."""
+    rng = np.random.default_rng(77)
+    sizes = [int(v) for v in rng.integers(0, 601, size=1500)]
+    z_only = [(2, -1.5, 1.5, 0)]
+    with CloudMerger(max_sensors=1, max_batch_points=sum(sizes), max_batch_frames=len(sizes)) as cm:
+        out, o = _ragged_batch(cm, oracle, sizes, z_only, 0.3, 2, (20.0, 20.0, 4.0))
+    st = out["stats"]
+    assert st.device_error == 0 and st.frames == len(sizes) and st.key_bytes == 4 and st.key_bits == out["key_idx_bits"]
+    _check_survivors(out, out["frames"], o)
+    assert _check_voxels(out, out["frames"], o) <= 1e-5
+
+
 def test_frame_segmented_sort_big_tile_and_bounded_plan(gpu_ok, oracle):
     """(i) the big sort tile (capacity above 1 363 968 keys) with frames of unequal size; (ii) a crop BOX whose grid needs
     31 index bits: with the frame bits the key would not fit 32 bits, so the host plans a segmented run (32-bit records,
