@@ -571,6 +571,112 @@ __global__ void __launch_bounds__(VX_THREADS) k_seg_keys64(const uint2* __restri
 // SEG (frame-segmented sort): the records carry the bare voxel index; frame f occupies positions [frame_surv_start[f],
 // frame_surv_start[f+1]) of the sorted array exactly as it did before the sort, so the frame of an item follows from its
 // position and the kernel works on the logical key (frame << idx_bits | idx) like the unsegmented 64-bit one.
+// ---- tail runs ---------------------------------------------------------------------------------------------------------------
+// A run that continues past the centroid tile in which it starts is walked by the thread that owns its head, two dependent
+// global loads per point: fine for the two or three points most tiles' last run has left, a second for a voxel of a million
+// points (a driver that reports invalid returns as zeros puts them all into the voxel at the origin). After CE_TAIL_INLINE
+// points the thread hands the run over (TailRun in shared memory) and the whole CTA finishes it at the end of the tile:
+// rounds of CE_TAIL_ITEMS sorted items -- every thread tests its items' keys and fetches the matching points into shared
+// memory, all loads in flight together; the run ends at the first item that does not match; one thread extends the sum over
+// the matched prefix, in the same strictly sequential order. Not inlined, and fed from a shared-memory copy of the launch
+// parameters: the per-voxel code of the kernel keeps its registers and its instruction footprint.
+constexpr uint32_t CE_TAIL_INLINE = 24;
+constexpr int CE_TAIL_U = 4;
+constexpr int CE_TAIL_ITEMS = CE_TAIL_U * VX_THREADS;
+struct TailRun {
+  float sx, sy, sz, sw;
+  unsigned long long key;  // the logical key (frame bits included)
+  uint32_t n, dst, g;      // points summed so far, index of the voxel in the dense output, first sorted position not yet summed
+  uint32_t count_frame;    // 1: the voxel still has to be counted for its frame
+};
+template <typename KeyT, bool SEG>
+__device__ __noinline__ void finish_tail_run(const VoxelParams* pp, const TailRun* tr_s, float4* s_pts, uint32_t* s_lead) {
+  constexpr bool REC = SEG || sizeof(KeyT) == 4;
+  const VoxelParams& p = *pp;
+  const TailRun tr = *tr_s;
+  const uint32_t tid = threadIdx.x, lane = tid & 31u;
+  const SortInfo si = *p.info;
+  const uint32_t F = p.n_frames, idx_bits = si.idx_bits;
+  const bool odd = (si.num_passes & 1u) != 0u;
+  const void* __restrict__ sorted = odd ? p.keys_b : p.keys_a;
+  const uint32_t* __restrict__ vals = odd ? p.vals_b : p.vals_a;
+  // the sorted keys that continue the run: the key itself; for frame-segmented runs the bare index, inside the frame's range
+  uint32_t limit = p.frame_surv_start[F];
+  unsigned long long want = tr.key;
+  if (SEG) {
+    limit = p.frame_surv_start[(tr.key >> idx_bits) + 1ull];
+    want = tr.key & ((1ull << idx_bits) - 1ull);
+  }
+  float sx = tr.sx, sy = tr.sy, sz = tr.sz, sw = tr.sw;
+  uint32_t n = tr.n, g = tr.g;
+  while (true) {
+#pragma unroll 1
+    for (int u = 0; u < CE_TAIL_U; ++u) {
+      const uint32_t i = g + (uint32_t)u * VX_THREADS + tid;
+      bool m = i < limit && i >= g;
+      uint32_t slot = 0;
+      if (m) {
+        if (REC) {
+          const uint2 r = reinterpret_cast<const uint2*>(sorted)[i];
+          m = (unsigned long long)r.x == want;
+          slot = r.y;
+        } else {
+          m = (unsigned long long)reinterpret_cast<const KeyT*>(sorted)[i] == want;
+          slot = vals[i];
+        }
+      }
+      const uint32_t bal = __ballot_sync(0xFFFFFFFFu, m);
+      if (lane == 0) s_lead[u * (VX_THREADS / 32) + (tid >> 5)] = bal == 0xFFFFFFFFu ? 32u : (uint32_t)__ffs(~bal) - 1u;
+      if (m) s_pts[u * VX_THREADS + tid] = __ldg(p.pts + slot);
+    }
+    __syncthreads();
+    uint32_t matched = 0;
+    bool open = true;
+#pragma unroll 1
+    for (int w = 0; w < CE_TAIL_U * (VX_THREADS / 32); ++w) {
+      const uint32_t l = s_lead[w];
+      matched += open ? l : 0u;
+      open = open && l == 32u;
+    }
+    if (tid == 0) {
+      for (uint32_t q = 0; q < matched; ++q) {
+        const float4 pt = s_pts[q];
+        sx = __fadd_rn(sx, pt.x); sy = __fadd_rn(sy, pt.y); sz = __fadd_rn(sz, pt.z); sw = __fadd_rn(sw, pt.w);
+      }
+    }
+    n += matched;
+    g += matched;
+    __syncthreads();  // s_pts and s_lead are rewritten by the next round
+    if (matched < (uint32_t)CE_TAIL_ITEMS) break;
+  }
+  if (tid == 0) {
+    const float nf = (float)n;
+    const float4 c = make_float4(__fdiv_rn(sx, nf), __fdiv_rn(sy, nf), __fdiv_rn(sz, nf), p.downsample_all ? __fdiv_rn(sw, nf) : 0.f);
+    if (p.out_step == 32) {  // pcl::PointXYZI record: x y z 1.0f | intensity 0 0 0
+      float4* o = reinterpret_cast<float4*>(reinterpret_cast<uint8_t*>(p.out_xyzi) + (size_t)tr.dst * 32);
+      o[0] = make_float4(c.x, c.y, c.z, 1.0f);
+      o[1] = make_float4(c.w, 0.f, 0.f, 0.f);
+    } else {
+      reinterpret_cast<float4*>(p.out_xyzi)[tr.dst] = c;
+    }
+    p.out_count[tr.dst] = n;
+    const unsigned long long f = idx_bits >= 64 ? 0ull : tr.key >> idx_bits;
+    unsigned long long vidx = idx_bits >= 64 ? tr.key : tr.key & ((1ull << idx_bits) - 1ull);
+    if (p.fused_keys) {  // box-grid index -> PCL's idx on the frame's data-derived grid (as in the kernel's emit)
+      const uint32_t b = (uint32_t)vidx;
+      const uint32_t k2 = b / p.box.mul2, r2 = b - k2 * p.box.mul2;
+      const uint32_t k1 = r2 / p.box.mul1, k0 = r2 - k1 * p.box.mul1;
+      const GridDev* __restrict__ gd = p.grid + (f < F ? f : 0ull);
+      const long long c0 = (long long)k0 + p.box.min_b[0] - gd->min_b[0];
+      const long long c1 = (long long)k1 + p.box.min_b[1] - gd->min_b[1];
+      const long long c2 = (long long)k2 + p.box.min_b[2] - gd->min_b[2];
+      vidx = (unsigned long long)(c0 + c1 * (long long)gd->mul1 + c2 * (long long)gd->mul2);
+    }
+    p.out_idx[tr.dst] = vidx;
+    if (tr.count_frame && f < F) atomicAdd(&p.acc[f].voxel_count, 1u);
+  }
+}
+
 constexpr uint32_t CE_SEG_SMEM_FRAMES = 256;  // frame starts staged in shared memory up to here (else read from L2)
 template <typename KeyT, bool SEG = false>
 __global__ void __launch_bounds__(VX_THREADS, CE_MIN_CTAS) k_voxel_centroid(const VoxelParams p) {
@@ -583,6 +689,10 @@ __global__ void __launch_bounds__(VX_THREADS, CE_MIN_CTAS) k_voxel_centroid(cons
   __shared__ unsigned short s_start[CE_TILE];     // tile-local position of the r-th surviving run
   __shared__ uint32_t s_tile, s_base;
   __shared__ uint32_t s_cnt8[VX_THREADS / 32];
+  __shared__ VoxelParams s_params;  // for finish_tail_run (a kernel parameter has no address a call could take cheaply)
+  __shared__ TailRun s_tail;
+  __shared__ uint32_t s_tail_r;     // which run of the tile was handed over (0xFFFFFFFF: none)
+  __shared__ uint32_t s_tail_lead[CE_TAIL_U * (VX_THREADS / 32)];
   const uint32_t tid = threadIdx.x, lane = tid & 31u;
   const uint32_t F = p.n_frames;
   const uint32_t M = p.frame_surv_start[F];
@@ -596,6 +706,8 @@ __global__ void __launch_bounds__(VX_THREADS, CE_MIN_CTAS) k_voxel_centroid(cons
   __syncthreads();
   uint32_t tile = s_tile;
   if (tile >= n_tiles) return;
+  for (uint32_t i = tid; i < sizeof(VoxelParams) / 4; i += VX_THREADS)
+    reinterpret_cast<uint32_t*>(&s_params)[i] = reinterpret_cast<const uint32_t*>(&p)[i];
 
   const SortInfo si = *p.info;
   const uint32_t idx_bits = si.idx_bits;
@@ -785,7 +897,7 @@ __global__ void __launch_bounds__(VX_THREADS, CE_MIN_CTAS) k_voxel_centroid(cons
   for (int j = 0; j < CE_IPT; ++j)
     if (need & (1u << j)) s_pts[loc + j] = __ldg(p.pts + v[j]);
   reinterpret_cast<unsigned char*>(s_headw)[tid] = (unsigned char)head;  // bit position 8*tid + j == item loc + j
-  if (tid == 0) s_headw[CE_TILE / 32] = 0u;
+  if (tid == 0) { s_headw[CE_TILE / 32] = 0u; s_tail_r = 0xFFFFFFFFu; }
   const uint32_t cnt = (uint32_t)__popc(pass);
 
   uint32_t total;
@@ -880,7 +992,8 @@ __global__ void __launch_bounds__(VX_THREADS, CE_MIN_CTAS) k_voxel_centroid(cons
   // ---- per voxel ----------------------------------------------------------------------------------------------------
   // The first voxel of every thread is summed BEFORE the barrier that delivers the tile's output position, so the look-back
   // of warp 0 hides behind it; further voxels (tiles with more than 256 surviving runs) follow after the barrier.
-  auto voxel = [&](uint32_t r, float4& cen, uint32_t& n_out, KeyT& key_out) {
+  // false: the run was handed over to the CTA (tail run) -- nothing to emit here
+  auto voxel = [&](uint32_t r, float4& cen, uint32_t& n_out, KeyT& key_out) -> bool {
     const uint32_t s0 = s_start[r];
     const KeyT key = key_at(tile_base + s0);
     // end of the run inside the tile: the next head bit after s0 (the sentinel at tile_n bounds the search)
@@ -898,6 +1011,12 @@ __global__ void __launch_bounds__(VX_THREADS, CE_MIN_CTAS) k_voxel_centroid(cons
     if (end == tile_n) {  // the run may continue in the following tiles: global memory
       uint32_t g = tile_base + tile_n;
       while (g < M && key_at(g) == key) {
+        if (g - (tile_base + tile_n) == CE_TAIL_INLINE) {  // a long run: the CTA finishes it (finish_tail_run)
+          s_tail.sx = sx; s_tail.sy = sy; s_tail.sz = sz; s_tail.sw = sw;
+          s_tail.key = (unsigned long long)key; s_tail.n = n; s_tail.g = g;
+          s_tail_r = r;
+          return false;
+        }
         const float4 pt = __ldg(p.pts + val_at(g));
         sx = __fadd_rn(sx, pt.x); sy = __fadd_rn(sy, pt.y); sz = __fadd_rn(sz, pt.z); sw = __fadd_rn(sw, pt.w);
         ++n; ++g;
@@ -911,6 +1030,7 @@ __global__ void __launch_bounds__(VX_THREADS, CE_MIN_CTAS) k_voxel_centroid(cons
     }
     n_out = n;
     key_out = key;
+    return true;
   };
   auto emit = [&](uint32_t dst, const float4& c, uint32_t n, KeyT key) {
     if (p.out_step == 32) {  // pcl::PointXYZI record: x y z 1.0f | intensity 0 0 0
@@ -943,15 +1063,23 @@ __global__ void __launch_bounds__(VX_THREADS, CE_MIN_CTAS) k_voxel_centroid(cons
   float4 c0 = make_float4(0.f, 0.f, 0.f, 0.f);
   uint32_t n0 = 0;
   KeyT k0 = (KeyT)0;
-  if (tid < total) voxel(tid, c0, n0, k0);
+  bool whole0 = false;
+  if (tid < total) whole0 = voxel(tid, c0, n0, k0);
   __syncthreads();  // s_base: the look-back of warp 0 is done
   const uint32_t out0 = s_base;
-  if (tid < total) emit(out0 + tid, c0, n0, k0);
-  for (uint32_t r = tid + VX_THREADS; r < total; r += VX_THREADS) {
-    voxel(r, c0, n0, k0);
-    emit(out0 + r, c0, n0, k0);
-  }
+  if (whole0) emit(out0 + tid, c0, n0, k0);
+  for (uint32_t r = tid + VX_THREADS; r < total; r += VX_THREADS)
+    if (voxel(r, c0, n0, k0)) emit(out0 + r, c0, n0, k0);
   __syncthreads();  // every read of this tile's shared memory is done
+  if (s_tail_r != 0xFFFFFFFFu) {  // (block-uniform) at most one run per tile is handed over
+    if (tid == 0) {
+      s_tail.dst = out0 + s_tail_r;
+      s_tail.count_frame = per_voxel_count ? 1u : 0u;
+    }
+    __syncthreads();
+    finish_tail_run<KeyT, SEG>(&s_params, &s_tail, s_pts, s_tail_lead);
+    __syncthreads();
+  }
   tile = next_tile;
   if (tile >= n_tiles) break;
   }  // while (true): next tile

@@ -496,6 +496,30 @@ def _voxel_only(cm, x, leaf, min_points):
     return out
 
 
+@pytest.mark.parametrize("dense_points", [20, 5000, 700001])
+def test_one_voxel_holding_most_of_the_cloud(gpu_ok, oracle, dense_points):
+    """A voxel with far more points than a centroid tile (sensors that report invalid returns as zeros put them all into
+    the voxel at the origin): its run spans hundreds of tiles and is finished by the whole CTA (finish_tail_run), in PCL's
+    strictly sequential float order -- bit-equal to the float oracle -- and in milliseconds, not the second a lone thread
+    took. (20 points: the hand-over threshold is not reached; 5000: a few tiles.)"""
+    rng = np.random.default_rng(31)
+    x = synth.uniform_cloud(91, 300000, extent=(60.0, 60.0, 6.0))
+    blob = np.empty((dense_points, 4), np.float32)
+    blob[:, :3] = rng.uniform(0.01, 0.09, size=(dense_points, 3)).astype(np.float32)
+    blob[:, 3] = rng.uniform(0, 255, size=dense_points).astype(np.float32)
+    blob[::3, :3] = 0.0   # and a third of them exactly at the origin
+    x = np.concatenate([x, blob])[rng.permutation(len(x) + dense_points)]
+    with CloudMerger(max_batch_points=len(x)) as cm:
+        out = _voxel_only(cm, x, 0.1, 2)
+    o = oracle.voxelgrid(x, [0.1] * 3, 2, True, force64=True)
+    st = out["stats"]
+    assert st.device_error == 0 and st.voxels_out == o["n"]
+    assert (out["voxel_idx"].astype(np.int64) == o["idx"]).all() and (out["voxel_count"] == o["count"]).all()
+    assert out["voxel_count"].max() >= dense_points
+    assert_bit_equal(out["voxel_xyzi"], o["centroid"], "centroids vs the float oracle (ascending index order)")
+    assert st.gpu_ms < 30.0, "the giant voxel must not serialise the launch (%.1f ms)" % st.gpu_ms
+
+
 @pytest.mark.parametrize("leaf", [0.01, 0.02])
 def test_sort_64bit_big_tile_at_size(gpu_ok, oracle, leaf):
     """k_onesweep_pass<unsigned long long, 8> (64-bit keys, the big tile: handle capacity above 1 363 968 keys) on
