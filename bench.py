@@ -254,8 +254,9 @@ def run_reference(args):
     if rank != 0:
         return 0
     spec = workload_spec(args.workload, args.frames)
-    cores = os.cpu_count() or 1
-    sample_frames = min(spec["frames"], max(4, cores))
+    cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    # one frame per thread and at least one thread per core the process may use: every host core is busy in every step
+    sample_frames = max(4, min(64, max(spec["frames"], cores)))
     spec_small = dict(spec, frames=sample_frames)
     _, frames = make_host_frames(spec_small, args.workload, 0, pinned=False)
     from concurrent.futures import ThreadPoolExecutor
