@@ -197,7 +197,6 @@ __global__ void __launch_bounds__(ZN_THREADS) k_zone_scatter(const ZoneParams p)
   if (*p.overflow) return;
   const uint32_t n = p.n_points;
   const uint32_t tile = blockIdx.x;
-  const int nz = p.zones.n_zones;
   const uint32_t base = tile * ZN_TILE + warp * (32 * ZN_IPT) + lane;
   float4 v[ZN_IPT];
   uint32_t m[ZN_IPT];
